@@ -1,0 +1,212 @@
+/*
+ * pdfusion_b200.h -- C ABI of libpdfusion_b200.so (hand-written sm_100a CUDA kernels).
+ *
+ * The reference (Ardbiu/robust-multimodal-pd) has NO native/FFI boundary: its hot path is Python
+ * calling numpy/scipy/torch.  Each entry point below therefore cites the
+ * reference Python call site it replaces (file:line relative to the reference root); the ctypes
+ * binding a maintainer would add is shown in INTEGRATION.md and implemented in
+ * robust-multimodal-pd_b200/pd_fusion_b200/_lib.py.
+ *
+ * Conventions
+ *   - plain C types only; every pointer named d_* is a DEVICE pointer owned by the caller;
+ *   - every call takes the CUDA stream (cudaStream_t as void*) it enqueues on and does not
+ *     synchronise (unless stated); no allocation inside except plan objects;
+ *   - return value 0 = ok, negative = error; pdf_last_error() returns a thread-local message;
+ *   - there is NO CPU fallback: on a machine without a CUDA device every compute call fails with
+ *     PDF_ERR_CUDA.
+ */
+#ifndef PDFUSION_B200_H
+#define PDFUSION_B200_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define PDF_OK 0
+#define PDF_ERR_ARG (-1)
+#define PDF_ERR_CUDA (-2)
+#define PDF_ERR_UNSUPPORTED (-3)
+
+#define PDF_MAX_AXES 3
+
+typedef void* pdf_stream_t; /* cudaStream_t */
+
+int pdf_version(void);
+const char* pdf_last_error(void);
+/* number of kernel launches issued by this library in this process (bench.py: gpu_launches) */
+uint64_t pdf_launch_count(void);
+
+/* ------------------------------------------------------------------------------------------
+ * K1 -- volume -> network input.  Replaces, per subject,
+ *   _load_volume                   data/openneuro_features.py:22-32   (nan_to_num + ndimage.zoom order 1)
+ *   _normalize_volume_for_resnet   data/openneuro_features.py:121-132 (p1/p99 of voxels>0, clip, min-max)
+ *   _select_slices                 data/openneuro_features.py:134-151 (non-zero extent, linspace indices, gather)
+ *   F.interpolate + repeat + (x-mean)/std   data/openneuro_features.py:250-255
+ * for a batch of `batch` raw volumes resident in HBM.
+ * ------------------------------------------------------------------------------------------ */
+typedef struct {
+  int32_t in_shape[3];          /* raw volume X,Y,Z (C order, Z fastest) */
+  int32_t out_shape[3];         /* target_shape T0,T1,T2 */
+  int32_t n_axes;               /* 1..3 */
+  int32_t axes[PDF_MAX_AXES];   /* slice axis per group (slice_axis / slice_axes) */
+  int32_t counts[PDF_MAX_AXES]; /* requested slice_count per group */
+  int32_t input_size;           /* network input side (224) */
+  float mean[3];                /* per-channel mean/std of (x-mean)/std */
+  float std[3];
+} pdf_preproc_cfg;
+
+/* output layouts of pdf_gather_resize_normalize */
+#define PDF_OUT_BF16_C1 0 /* [B, L, S, S]    bf16, one channel (requires channel-uniform mean/std) */
+#define PDF_OUT_F32_NHWC3 1 /* [B, L, S, S, 3] f32,  exact 3-channel input of the reference */
+
+/* bytes of device workspace pdf_preproc_* needs for `batch` subjects (histograms, plane maxima,
+ * per-subject select state, interpolation tables). */
+size_t pdf_preproc_workspace_bytes(const pdf_preproc_cfg* cfg, int batch);
+
+/* stage 1 (K1a): nan/inf scrub + trilinear resample in float64 exactly as scipy does, one rounding to
+ * f32; fused: level-0 radix histogram of positive voxels and per-plane maxima along each axis.
+ * d_raw [B,X,Y,Z] f32 -> d_zoomed [B,T0,T1,T2] f32. Also zeroes/initialises the workspace. */
+int pdf_resample_stats(const pdf_preproc_cfg* cfg, int batch, const float* d_raw, float* d_zoomed,
+                       void* d_workspace, pdf_stream_t stream);
+
+/* stage 2 (K1b): exact order statistics for numpy.percentile(vals,1|99) by radix select on the float
+ * bit patterns (two refinement passes over d_zoomed), then the numpy lerp, then (K1c) the non-zero
+ * extent per requested axis from the plane maxima and the np.linspace(...).astype(int) indices.
+ * d_lohi [B,4] f32 = {lo, hi, denominator (hi-lo+1e-6 as the reference rounds it), n_positive>0 ? 1 : 0};
+ * d_indices [B,Lmax] i32 (Lmax = sum(counts)); d_nslices [B,n_axes] i32. */
+int pdf_select_bounds_indices(const pdf_preproc_cfg* cfg, int batch, const float* d_zoomed, void* d_workspace,
+                              float* d_lohi, int32_t* d_indices, int32_t* d_nslices, pdf_stream_t stream);
+
+/* stage 3 (K1d): gather the selected planes, clip/min-max with lo/hi, bilinear resize to input_size
+ * (align_corners=False), (x-mean)/std, write the network input in `out_mode` layout.  Slots beyond
+ * d_nslices are zero-filled.  d_workspace: the same workspace (holds the compact axis-2 plane buffer). */
+int pdf_gather_resize_normalize(const pdf_preproc_cfg* cfg, int batch, const float* d_zoomed, void* d_workspace,
+                                const float* d_lohi, const int32_t* d_indices, const int32_t* d_nslices, void* d_out,
+                                int out_mode, pdf_stream_t stream);
+
+/* the three stages back to back on `stream` */
+int pdf_preprocess(const pdf_preproc_cfg* cfg, int batch, const float* d_raw, float* d_zoomed, void* d_workspace,
+                   float* d_lohi, int32_t* d_indices, int32_t* d_nslices, void* d_out, int out_mode,
+                   pdf_stream_t stream);
+
+/* normalised volume itself (parity helper for _normalize_volume_for_resnet): d_zoomed -> d_norm */
+int pdf_normalize_volume(int batch, size_t voxels, const float* d_zoomed, const float* d_lohi, float* d_norm,
+                         pdf_stream_t stream);
+
+/* ------------------------------------------------------------------------------------------
+ * K2 -- ResNet2D encoder.  Replaces `model(batch)` on torchvision resnet18/50 with fc=Identity in
+ * eval mode (data/openneuro_features.py:153-164,257-262; scripts/build_resnet2d_mil_embeddings.py:148-156).
+ * The host folds BatchNorm (eval) and describes the network as a flat list of ops over NHWC buffers.
+ * ------------------------------------------------------------------------------------------ */
+#define PDF_OP_CONV 0        /* implicit-GEMM convolution (+bias/scale, +residual, +ReLU) */
+#define PDF_OP_MAXPOOL 1     /* 3x3 stride 2 pad 1 */
+#define PDF_OP_AVGPOOL 2     /* global average over H*W -> [N, C] f32 */
+#define PDF_OP_STEM_IM2COL 3 /* [N,H,W] bf16 one-channel image -> [N*Ho*Wo, kpad] bf16 patch matrix (7x7 s2 p3) */
+
+#define PDF_PREC_F32 0  /* CUDA-core FFMA path, 1e-5 parity */
+#define PDF_PREC_BF16 1 /* tcgen05/TMEM path, bf16 operands, f32 accumulate */
+
+typedef struct {
+  int32_t kind;
+  int32_t precision;
+  int32_t n, h, w, c;  /* input tensor NHWC */
+  int32_t k, r, s;     /* output channels, filter height/width */
+  int32_t stride, pad;
+  int32_t ho, wo;      /* output spatial size */
+  int32_t relu;
+  int32_t out_f32;     /* bf16 path only: store the output tile as f32 instead of bf16 */
+  const void* d_in;
+  const void* d_weight;   /* f32 path: [R][S][C][K] f32 ; bf16 path: [K][R][S][C] bf16, BN folded */
+  const float* d_scale;   /* f32 path: per-channel BN scale (NULL = 1) */
+  const float* d_bias;    /* per-channel bias / BN shift (NULL = 0) */
+  const void* d_residual; /* same layout/dtype as the (bf16|f32) output, or NULL */
+  void* d_out;
+} pdf_op;
+
+typedef struct pdf_plan pdf_plan; /* opaque: validated ops + pre-encoded TMA descriptors */
+
+/* validates shapes, encodes the CUtensorMaps of every bf16 conv (needs a CUDA context). */
+int pdf_plan_create(pdf_plan** out, const pdf_op* ops, int n_ops);
+int pdf_plan_run(const pdf_plan* plan, pdf_stream_t stream);
+/* runs ops [first, first+count) only (per-layer timing / debugging) */
+int pdf_plan_run_range(const pdf_plan* plan, int first, int count, pdf_stream_t stream);
+void pdf_plan_destroy(pdf_plan* plan);
+/* algorithmic FLOPs (2*MAC over conv ops) of one pdf_plan_run */
+double pdf_plan_flops(const pdf_plan* plan);
+
+/* mean over the valid slices of each subject: d_emb [B, L, D] f32 -> d_out [B, D] f32
+ * (`torch.cat(feats).mean(dim=0)`, data/openneuro_features.py:262).  d_nslices: valid count per subject
+ * (sum over axes), or NULL for L. */
+int pdf_slice_mean(int batch, int L, int D, const float* d_emb, const int32_t* d_nvalid, float* d_out, pdf_stream_t stream);
+
+/* ------------------------------------------------------------------------------------------
+ * K3 -- MIL attention head.  Replaces MILAttentionNet.forward + the per-bag loop of
+ * MilAttentionModel.predict_proba (models/mil_attention.py:40-51,157-178) for ALL bags in one launch.
+ * d_bags [n_bags, Lmax, D] f32, d_len [n_bags] i32 (0 = missing bag -> missing_prob).
+ * Weights are the state_dict tensors, row-major as torch stores them:
+ *   w_inst [H,D], b_inst [H]; gated: w_v [A,H], b_v [A], w_u [A,H], b_u [A], w_w [A], b_w [1]
+ *   non-gated: w_v = attn.0.weight, b_v = attn.0.bias, w_w = attn.2.weight, b_w = attn.2.bias, w_u = NULL
+ *   w_cls [H], b_cls [1].   d_prob [n_bags] f32.
+ * ------------------------------------------------------------------------------------------ */
+typedef struct {
+  int32_t D, H, A, gated;
+  const float *w_inst, *b_inst, *w_v, *b_v, *w_u, *b_u, *w_w, *b_w, *w_cls, *b_cls;
+  float missing_prob;
+} pdf_mil_weights;
+
+size_t pdf_mil_workspace_bytes(const pdf_mil_weights* w, int n_bags, int Lmax);
+int pdf_mil_forward(const pdf_mil_weights* w, int n_bags, int Lmax, const float* d_bags, const int32_t* d_len,
+                    void* d_workspace, float* d_prob, pdf_stream_t stream);
+
+/* ------------------------------------------------------------------------------------------
+ * K4a -- Fusion-ModDrop under every scenario mask in one launch.  Replaces the per-scenario
+ * apply_masks_to_matrix + ModalityDropoutModel.predict_proba (data/feature_utils.py:49-61,
+ * models/fusion_moddrop.py:93-114; loop at evaluation/evaluate.py:18-97).
+ * d_x [N,F] f32; feature block of modality m = [mod_off[m], mod_off[m+1]); d_masks [S,N,M] u8;
+ * MLP layers: n_layers linear layers (ReLU between, sigmoid last), weights [out,in] row-major.
+ * d_prob [S,N] f32.
+ * ------------------------------------------------------------------------------------------ */
+#define PDF_MAX_LAYERS 8
+#define PDF_MAX_MODS 8
+typedef struct {
+  int32_t n_layers;
+  int32_t dims[PDF_MAX_LAYERS + 1]; /* dims[0]=F ... dims[n_layers]=1 */
+  const float* w[PDF_MAX_LAYERS];
+  const float* b[PDF_MAX_LAYERS];
+  int32_t n_mods;
+  int32_t mod_off[PDF_MAX_MODS + 1];
+} pdf_mlp;
+
+size_t pdf_moddrop_workspace_bytes(const pdf_mlp* net, int n_subjects);
+int pdf_moddrop_sweep(const pdf_mlp* net, int n_subjects, int n_scenarios, const float* d_x, const uint8_t* d_masks,
+                      void* d_workspace, float* d_prob, pdf_stream_t stream);
+
+/* ------------------------------------------------------------------------------------------
+ * K4b -- MoE head under every scenario mask.  Replaces evaluate.py:52-63 (x_m * mask_m) +
+ * MoENet.forward (models/moe.py:37-47): router MLP(mask)+softmax, per-modality expert MLP+sigmoid,
+ * gated sum.  Experts listed in sorted(modality) order; expert e reads d_x[e] [N, dims[0]].
+ * router: w_r0 [R,M], b_r0 [R], w_r1 [M,R], b_r1 [M].
+ * ------------------------------------------------------------------------------------------ */
+typedef struct {
+  int32_t n_experts;
+  pdf_mlp expert[PDF_MAX_MODS];
+  int32_t router_hidden;
+  const float *w_r0, *b_r0, *w_r1, *b_r1;
+} pdf_moe;
+
+int pdf_moe_sweep(const pdf_moe* net, int n_subjects, int n_scenarios, const float* const* d_x /* host array of device ptrs */,
+                  const uint8_t* d_masks, float* d_prob, pdf_stream_t stream);
+
+/* ------------------------------------------------------------------------------------------
+ * Self-tests of the tensor-core building blocks (used by tests/ and smoke on the GPU box).
+ * pdf_selftest_umma: C[M,N] = A[M,K] * B[N,K]^T through TMA(2D tiled) + tcgen05.mma, bf16 in / f32 out.
+ * ------------------------------------------------------------------------------------------ */
+int pdf_selftest_umma(int M, int N, int K, const void* d_a_bf16, const void* d_b_bf16, float* d_c, pdf_stream_t stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* PDFUSION_B200_H */

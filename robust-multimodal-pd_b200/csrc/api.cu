@@ -1,0 +1,35 @@
+// Library-wide state: thread-local error message, launch counter, device properties.
+#include <atomic>
+#include <cstdarg>
+
+#include "common.cuh"
+
+namespace pdf {
+
+static thread_local char g_error[1024] = "";
+static std::atomic<uint64_t> g_launches{0};
+
+void set_error(const char* fmt, ...) {
+  va_list ap;
+  va_start(ap, fmt);
+  vsnprintf(g_error, sizeof(g_error), fmt, ap);
+  va_end(ap);
+}
+
+void count_launch(int n) { g_launches.fetch_add((uint64_t)n, std::memory_order_relaxed); }
+
+int num_sms() {
+  static int sms = 0;
+  if (sms == 0) {
+    int dev = 0;
+    if (cudaGetDevice(&dev) != cudaSuccess || cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev) != cudaSuccess || sms <= 0)
+      sms = 148;  // B200
+  }
+  return sms;
+}
+
+}  // namespace pdf
+
+extern "C" int pdf_version(void) { return 100; }
+extern "C" const char* pdf_last_error(void) { return pdf::g_error; }
+extern "C" uint64_t pdf_launch_count(void) { return pdf::g_launches.load(std::memory_order_relaxed); }

@@ -1,0 +1,396 @@
+// K2 (bf16 path): implicit-GEMM convolution on the 5th-gen tensor cores.
+//
+//   D[M = N*Ho*Wo, Cout] = im2col(X)[M, R*S*Cin] * W[Cout, R*S*Cin]^T      bf16 x bf16 -> f32 (TMEM)
+//
+//   warp 0 (one lane)  TMA producer: A tile [128 pixels x 64 ch] via im2col-mode TMA on the NHWC activation
+//                      (padding / stride / image wrap handled by the TMA unit, zero fill), B tile [BLOCK_N x 64]
+//                      of the K-major weight matrix; SWIZZLE_128B, STAGES-deep mbarrier ring
+//   warp 1 (one lane)  tcgen05.mma cta_group::1 kind::f16, M=128, N=BLOCK_N, K=16 x4 per stage, accumulator in TMEM
+//   warps 2..5         epilogue: tcgen05.ld 32x32b -> +bias (+residual) (ReLU) -> bf16 (or f32) NHWC store
+//
+// Replaces the cuDNN/oneDNN convolutions torchvision's ResNet issues from `model(batch)`
+// (data/openneuro_features.py:260, scripts/build_resnet2d_mil_embeddings.py:152).
+#include <cuda.h>
+
+#include "common.cuh"
+#include "ops.cuh"
+
+namespace pdf {
+
+constexpr int kBlockM = 128;
+constexpr int kBlockK = 64;                      // 64 bf16 = one 128-byte swizzle row
+constexpr int kABytes = kBlockM * kBlockK * 2;   // 16 KB
+constexpr uint32_t kSpinLimit = 1u << 26;        // turns a protocol bug into a trap instead of a hang
+
+// ---------------------------------------------------------------------------------------- PTX wrappers
+__device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
+
+__device__ __forceinline__ void mbar_init(uint32_t bar, uint32_t count) {
+  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(bar), "r"(count));
+}
+__device__ __forceinline__ void mbar_expect_tx(uint32_t bar, uint32_t bytes) {
+  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ bool mbar_try_wait(uint32_t bar, uint32_t parity) {
+  uint32_t ok;
+  asm volatile(
+      "{\n\t.reg .pred p;\n\t"
+      "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
+      "selp.u32 %0, 1, 0, p;\n\t}"
+      : "=r"(ok)
+      : "r"(bar), "r"(parity)
+      : "memory");
+  return ok != 0;
+}
+__device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity) {
+  uint32_t spins = 0;
+  while (!mbar_try_wait(bar, parity)) {
+    if (++spins > kSpinLimit) asm volatile("trap;");
+  }
+}
+__device__ __forceinline__ void fence_barrier_init() { asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory"); }
+__device__ __forceinline__ void fence_proxy_async() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
+__device__ __forceinline__ void tc_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
+__device__ __forceinline__ void tc_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
+
+__device__ __forceinline__ void prefetch_tmap(const void* tmap) {
+  asm volatile("prefetch.tensormap [%0];" ::"l"(reinterpret_cast<uint64_t>(tmap)) : "memory");
+}
+__device__ __forceinline__ void tma_load_2d(uint32_t dst, const void* tmap, uint32_t bar, int c0, int c1) {
+  asm volatile("cp.async.bulk.tensor.2d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4}], [%2];"
+               ::"r"(dst), "l"(reinterpret_cast<uint64_t>(tmap)), "r"(bar), "r"(c0), "r"(c1)
+               : "memory");
+}
+__device__ __forceinline__ void tma_load_im2col_4d(uint32_t dst, const void* tmap, uint32_t bar, int c, int w, int h, int n,
+                                                   uint16_t off_w, uint16_t off_h) {
+  asm volatile(
+      "cp.async.bulk.tensor.4d.shared::cluster.global.im2col.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, %5, %6}], [%2], {%7, %8};"
+      ::"r"(dst), "l"(reinterpret_cast<uint64_t>(tmap)), "r"(bar), "r"(c), "r"(w), "r"(h), "r"(n), "h"(off_w), "h"(off_h)
+      : "memory");
+}
+
+__device__ __forceinline__ void tmem_alloc(uint32_t slot_smem, uint32_t cols) {
+  asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(slot_smem), "r"(cols) : "memory");
+  asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+}
+__device__ __forceinline__ void tmem_dealloc(uint32_t taddr, uint32_t cols) {
+  asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(taddr), "r"(cols) : "memory");
+}
+// D[tmem] (+)= A[smem] * B[smem]^T ; both operands K-major
+__device__ __forceinline__ void umma_f16(uint32_t tmem_d, uint64_t desc_a, uint64_t desc_b, uint32_t idesc, uint32_t accumulate) {
+  asm volatile(
+      "{\n\t.reg .pred p;\n\t"
+      "setp.ne.b32 p, %4, 0;\n\t"
+      "tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n\t}"
+      ::"r"(tmem_d), "l"(desc_a), "l"(desc_b), "r"(idesc), "r"(accumulate)
+      : "memory");
+}
+__device__ __forceinline__ void umma_commit(uint32_t bar) {
+  asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(bar) : "memory");
+}
+__device__ __forceinline__ void tmem_ld32(uint32_t taddr, uint32_t (&v)[32]) {
+  asm volatile(
+      "tcgen05.ld.sync.aligned.32x32b.x32.b32 "
+      "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, "
+      "%16, %17, %18, %19, %20, %21, %22, %23, %24, %25, %26, %27, %28, %29, %30, %31}, [%32];"
+      : "=r"(v[0]), "=r"(v[1]), "=r"(v[2]), "=r"(v[3]), "=r"(v[4]), "=r"(v[5]), "=r"(v[6]), "=r"(v[7]), "=r"(v[8]), "=r"(v[9]),
+        "=r"(v[10]), "=r"(v[11]), "=r"(v[12]), "=r"(v[13]), "=r"(v[14]), "=r"(v[15]), "=r"(v[16]), "=r"(v[17]), "=r"(v[18]),
+        "=r"(v[19]), "=r"(v[20]), "=r"(v[21]), "=r"(v[22]), "=r"(v[23]), "=r"(v[24]), "=r"(v[25]), "=r"(v[26]), "=r"(v[27]),
+        "=r"(v[28]), "=r"(v[29]), "=r"(v[30]), "=r"(v[31])
+      : "r"(taddr));
+  asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+}
+
+// K-major SWIZZLE_128B shared-memory matrix descriptor (cute::UMMA::SmemDescriptor, sm_100):
+//   [0,14) start address >> 4   [16,30) leading byte offset >> 4 (unused for swizzled K-major, 1)
+//   [32,46) stride byte offset >> 4 = 1024 B (8 rows x 128 B)   [46,48) version = 1   [61,64) layout = 2 (SWIZZLE_128B)
+__device__ __forceinline__ uint64_t make_smem_desc(uint32_t smem_addr) {
+  return (uint64_t)((smem_addr & 0x3ffffu) >> 4) | (1ull << 16) | ((uint64_t)(1024 >> 4) << 32) | (1ull << 46) | (2ull << 61);
+}
+// kind::f16 instruction descriptor (cute::UMMA::InstrDescriptor): D=f32, A=B=bf16, both K-major, M=128, N
+__host__ __device__ constexpr uint32_t make_idesc(int n) {
+  return (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(n >> 3) << 17) | ((uint32_t)(kBlockM >> 4) << 24);
+}
+
+struct TcParams {
+  int M_total, Cout, Ho, Wo, stride, pad, S, cchunks, num_kb, relu, im2col, out_f32;
+  const float* bias;
+  const __nv_bfloat16* residual;
+  void* out;
+};
+
+template <int BLOCK_N, int STAGES>
+struct SmemLayout {
+  static constexpr int kBBytes = BLOCK_N * kBlockK * 2;
+  static constexpr int kStage = kABytes + kBBytes;
+  static constexpr int kBarOff = STAGES * kStage;
+  static constexpr int kTotal = kBarOff + (2 * STAGES + 1) * 8 + 8;
+  static constexpr int kDynamic = kTotal + 1024;  // slack for manual 1024-byte alignment
+};
+
+template <int BLOCK_N, int STAGES>
+__global__ void __launch_bounds__(192)
+conv_tc_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant__ CUtensorMap tmap_b, const TcParams p) {
+  using L = SmemLayout<BLOCK_N, STAGES>;
+  extern __shared__ uint8_t smem_raw[];
+  const uint32_t raw_addr = smem_u32(smem_raw);
+  const uint32_t base = (raw_addr + 1023u) & ~1023u;          // SWIZZLE_128B tiles need 1024-byte alignment
+  uint8_t* smem = smem_raw + (base - raw_addr);
+  const uint32_t bar_full = base + L::kBarOff;
+  const uint32_t bar_empty = bar_full + STAGES * 8;
+  const uint32_t bar_acc = bar_empty + STAGES * 8;
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(smem + L::kBarOff + (2 * STAGES + 1) * 8);
+
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int m0 = blockIdx.x * kBlockM;
+  const int n0 = blockIdx.y * BLOCK_N;
+
+  if (threadIdx.x == 0) {
+    prefetch_tmap(&tmap_a);
+    prefetch_tmap(&tmap_b);
+    for (int s = 0; s < STAGES; ++s) { mbar_init(bar_full + s * 8, 1); mbar_init(bar_empty + s * 8, 1); }
+    mbar_init(bar_acc, 1);
+    fence_barrier_init();
+  }
+  if (warp == 1) tmem_alloc(smem_u32(tmem_slot), BLOCK_N);
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_slot;
+
+  if (warp == 0) {
+    if (lane == 0) {
+      int n_img = 0, w0 = 0, h0 = 0;
+      if (p.im2col) {
+        const int hw = p.Ho * p.Wo;
+        n_img = m0 / hw;
+        const int rem = m0 - n_img * hw;
+        const int pp = rem / p.Wo, qq = rem - pp * p.Wo;
+        w0 = qq * p.stride - p.pad;
+        h0 = pp * p.stride - p.pad;
+      }
+      for (int kb = 0; kb < p.num_kb; ++kb) {
+        const int stage = kb % STAGES;
+        const uint32_t phase = (uint32_t)(kb / STAGES) & 1u;
+        mbar_wait(bar_empty + stage * 8, phase ^ 1u);
+        mbar_expect_tx(bar_full + stage * 8, L::kStage);
+        const uint32_t sa = base + stage * L::kStage, sb = sa + kABytes;
+        if (p.im2col) {
+          const int tap = kb / p.cchunks, cc = kb - tap * p.cchunks;
+          const int r = tap / p.S, s = tap - r * p.S;
+          tma_load_im2col_4d(sa, &tmap_a, bar_full + stage * 8, cc * kBlockK, w0, h0, n_img, (uint16_t)s, (uint16_t)r);
+        } else {
+          tma_load_2d(sa, &tmap_a, bar_full + stage * 8, kb * kBlockK, m0);
+        }
+        tma_load_2d(sb, &tmap_b, bar_full + stage * 8, kb * kBlockK, n0);
+      }
+    }
+  } else if (warp == 1) {
+    if (lane == 0) {
+      constexpr uint32_t idesc = make_idesc(BLOCK_N);
+      for (int kb = 0; kb < p.num_kb; ++kb) {
+        const int stage = kb % STAGES;
+        const uint32_t phase = (uint32_t)(kb / STAGES) & 1u;
+        mbar_wait(bar_full + stage * 8, phase);
+        tc_fence_after();
+        const uint32_t sa = base + stage * L::kStage, sb = sa + kABytes;
+#pragma unroll
+        for (int k = 0; k < kBlockK / 16; ++k) {
+          // advance 16 bf16 = 32 bytes inside the 128-byte swizzle row
+          umma_f16(tmem_base, make_smem_desc(sa + k * 32), make_smem_desc(sb + k * 32), idesc, (kb | k) != 0 ? 1u : 0u);
+        }
+        umma_commit(bar_empty + stage * 8);   // frees the smem slot once these MMAs have read it
+      }
+      umma_commit(bar_acc);                   // accumulator complete
+    }
+  } else {
+    const int quad = warp & 3;                // TMEM lanes [32*quad, 32*quad+32) belong to this warp
+    const int row = quad * 32 + lane;
+    const int m = m0 + row;
+    mbar_wait(bar_acc, 0);
+    tc_fence_after();
+#pragma unroll 1
+    for (int c0 = 0; c0 < BLOCK_N; c0 += 32) {
+      uint32_t v[32];
+      tmem_ld32(tmem_base + ((uint32_t)(quad * 32) << 16) + (uint32_t)c0, v);
+      if (m < p.M_total) {
+        const int col = n0 + c0;
+        float f[32];
+#pragma unroll
+        for (int i = 0; i < 32; ++i) f[i] = __uint_as_float(v[i]);
+        if (p.bias) {
+#pragma unroll
+          for (int i = 0; i < 32; i += 4) {
+            const float4 b = __ldg(reinterpret_cast<const float4*>(p.bias + col + i));
+            f[i] += b.x; f[i + 1] += b.y; f[i + 2] += b.z; f[i + 3] += b.w;
+          }
+        }
+        if (p.residual) {
+          const uint4* rp = reinterpret_cast<const uint4*>(p.residual + (size_t)m * p.Cout + col);
+#pragma unroll
+          for (int i = 0; i < 4; ++i) {
+            const uint4 r = __ldg(rp + i);
+            const __nv_bfloat162* h = reinterpret_cast<const __nv_bfloat162*>(&r);
+#pragma unroll
+            for (int j = 0; j < 4; ++j) {
+              const float2 x = __bfloat1622float2(h[j]);
+              f[i * 8 + j * 2] += x.x;
+              f[i * 8 + j * 2 + 1] += x.y;
+            }
+          }
+        }
+        if (p.relu) {
+#pragma unroll
+          for (int i = 0; i < 32; ++i) f[i] = fmaxf(f[i], 0.f);
+        }
+        if (p.out_f32) {
+          float4* op = reinterpret_cast<float4*>(reinterpret_cast<float*>(p.out) + (size_t)m * p.Cout + col);
+#pragma unroll
+          for (int i = 0; i < 8; ++i) op[i] = make_float4(f[4 * i], f[4 * i + 1], f[4 * i + 2], f[4 * i + 3]);
+        } else {
+          uint4* op = reinterpret_cast<uint4*>(reinterpret_cast<__nv_bfloat16*>(p.out) + (size_t)m * p.Cout + col);
+#pragma unroll
+          for (int i = 0; i < 4; ++i) {
+            uint4 o;
+            __nv_bfloat162* h = reinterpret_cast<__nv_bfloat162*>(&o);
+#pragma unroll
+            for (int j = 0; j < 4; ++j) h[j] = __floats2bfloat162_rn(f[i * 8 + j * 2], f[i * 8 + j * 2 + 1]);
+            op[i] = o;
+          }
+        }
+      }
+    }
+  }
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 1) tmem_dealloc(tmem_base, BLOCK_N);
+}
+
+// ---------------------------------------------------------------------------------------- host side
+typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*, const cuuint64_t*,
+                                  const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave, CUtensorMapSwizzle,
+                                  CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+typedef CUresult (*EncodeIm2colFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*, const cuuint64_t*,
+                                   const int*, const int*, cuuint32_t, cuuint32_t, const cuuint32_t*, CUtensorMapInterleave,
+                                   CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+
+static EncodeTiledFn g_encode_tiled = nullptr;
+static EncodeIm2colFn g_encode_im2col = nullptr;
+
+static int load_driver_entry_points() {
+  if (g_encode_tiled && g_encode_im2col) return PDF_OK;
+  PDF_CHECK_CUDA(cudaFree(0));  // make sure a context exists
+  void* fn = nullptr;
+  cudaDriverEntryPointQueryResult qres;
+  PDF_CHECK_CUDA(cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &fn, cudaEnableDefault, &qres));
+  PDF_REQUIRE(fn && qres == cudaDriverEntryPointSuccess, "cuTensorMapEncodeTiled not available from the driver");
+  g_encode_tiled = reinterpret_cast<EncodeTiledFn>(fn);
+  fn = nullptr;
+  PDF_CHECK_CUDA(cudaGetDriverEntryPoint("cuTensorMapEncodeIm2col", &fn, cudaEnableDefault, &qres));
+  PDF_REQUIRE(fn && qres == cudaDriverEntryPointSuccess, "cuTensorMapEncodeIm2col not available from the driver");
+  g_encode_im2col = reinterpret_cast<EncodeIm2colFn>(fn);
+  return PDF_OK;
+}
+
+// [rows, cols] row-major bf16 matrix, box = [box_rows x 64 cols], 128-byte swizzle
+static int encode_2d(TensorMapBlob* out, const void* ptr, uint64_t rows, uint64_t cols, uint32_t box_rows) {
+  static_assert(sizeof(CUtensorMap) == sizeof(TensorMapBlob), "CUtensorMap is 128 bytes");
+  const cuuint64_t dims[2] = {cols, rows};
+  const cuuint64_t strides[1] = {cols * 2};
+  const cuuint32_t box[2] = {(cuuint32_t)kBlockK, box_rows};
+  const cuuint32_t estr[2] = {1, 1};
+  CUresult r = g_encode_tiled(reinterpret_cast<CUtensorMap*>(out), CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, const_cast<void*>(ptr),
+                              dims, strides, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B,
+                              CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  PDF_REQUIRE(r == CUDA_SUCCESS, "cuTensorMapEncodeTiled failed (%d) rows=%llu cols=%llu box_rows=%u", (int)r,
+              (unsigned long long)rows, (unsigned long long)cols, box_rows);
+  return PDF_OK;
+}
+
+static int encode_im2col(TensorMapBlob* out, const pdf_op& op) {
+  const cuuint64_t dims[4] = {(cuuint64_t)op.c, (cuuint64_t)op.w, (cuuint64_t)op.h, (cuuint64_t)op.n};
+  const cuuint64_t strides[3] = {(cuuint64_t)op.c * 2, (cuuint64_t)op.w * op.c * 2, (cuuint64_t)op.h * op.w * op.c * 2};
+  // bounding box of the filter's base pixel: lower = -pad, upper = pad - (filter-1)   [W, H] order as CUTLASS passes them
+  const int lower[2] = {-op.pad, -op.pad};
+  const int upper[2] = {op.pad - (op.s - 1), op.pad - (op.r - 1)};
+  const cuuint32_t estr[4] = {1, (cuuint32_t)op.stride, (cuuint32_t)op.stride, 1};
+  CUresult r = g_encode_im2col(reinterpret_cast<CUtensorMap*>(out), CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 4, const_cast<void*>(op.d_in),
+                               dims, strides, lower, upper, (cuuint32_t)kBlockK, (cuuint32_t)kBlockM, estr,
+                               CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                               CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  PDF_REQUIRE(r == CUDA_SUCCESS, "cuTensorMapEncodeIm2col failed (%d) nhwc=%d,%d,%d,%d rs=%d,%d stride=%d pad=%d", (int)r, op.n,
+              op.h, op.w, op.c, op.r, op.s, op.stride, op.pad);
+  // CUTLASS applies the same fix-up for drivers <= 13.1 on tensors smaller than 128 KiB
+  int drv = 0;
+  cudaDriverGetVersion(&drv);
+  if (drv <= 13010 && (size_t)op.n * op.h * op.w * op.c * 2 < 131072) reinterpret_cast<uint64_t*>(out)[1] &= ~(1ull << 21);
+  return PDF_OK;
+}
+
+int prepare_conv_tc(const pdf_op& op, TcConv* tc) {
+  if (int rc = load_driver_entry_points()) return rc;
+  PDF_REQUIRE(op.c % kBlockK == 0, "bf16 conv: Cin (%d) must be a multiple of 64", op.c);
+  PDF_REQUIRE(op.k % 64 == 0, "bf16 conv: Cout (%d) must be a multiple of 64", op.k);
+  PDF_REQUIRE(op.stride >= 1 && op.stride <= 8 && op.r == op.s, "bf16 conv: unsupported stride/filter");
+  PDF_REQUIRE(op.ho == (op.h + 2 * op.pad - op.r) / op.stride + 1 && op.wo == (op.w + 2 * op.pad - op.s) / op.stride + 1,
+              "bf16 conv: inconsistent output size");
+  PDF_REQUIRE((reinterpret_cast<uintptr_t>(op.d_in) & 15) == 0 && (reinterpret_cast<uintptr_t>(op.d_weight) & 15) == 0 &&
+              (reinterpret_cast<uintptr_t>(op.d_out) & 15) == 0, "bf16 conv: pointers must be 16-byte aligned");
+  tc->block_n = (op.k % 256 == 0) ? 256 : (op.k % 128 == 0 ? 128 : 64);
+  tc->im2col = !(op.r == 1 && op.s == 1 && op.stride == 1 && op.pad == 0);
+  tc->M_total = op.n * op.ho * op.wo;
+  tc->Cout = op.k; tc->Ho = op.ho; tc->Wo = op.wo; tc->stride = op.stride; tc->pad = op.pad; tc->R = op.r; tc->S = op.s;
+  tc->cchunks = op.c / kBlockK;
+  tc->relu = op.relu; tc->bias = op.d_bias; tc->residual = op.d_residual; tc->out = op.d_out; tc->out_f32 = op.out_f32;
+  if (tc->im2col) {
+    if (int rc = encode_im2col(&tc->tmap_a, op)) return rc;
+  } else {
+    if (int rc = encode_2d(&tc->tmap_a, op.d_in, (uint64_t)tc->M_total, (uint64_t)op.c, kBlockM)) return rc;
+  }
+  return encode_2d(&tc->tmap_b, op.d_weight, (uint64_t)op.k, (uint64_t)op.r * op.s * op.c, (uint32_t)tc->block_n);
+}
+
+template <int BLOCK_N, int STAGES>
+static int launch_tc(const TcConv& tc, cudaStream_t s) {
+  using L = SmemLayout<BLOCK_N, STAGES>;
+  static bool configured = false;
+  if (!configured) {
+    PDF_CHECK_CUDA(cudaFuncSetAttribute(conv_tc_kernel<BLOCK_N, STAGES>, cudaFuncAttributeMaxDynamicSharedMemorySize, L::kDynamic));
+    configured = true;
+  }
+  TcParams p;
+  p.M_total = tc.M_total; p.Cout = tc.Cout; p.Ho = tc.Ho; p.Wo = tc.Wo; p.stride = tc.stride; p.pad = tc.pad; p.S = tc.S;
+  p.cchunks = tc.cchunks; p.num_kb = tc.R * tc.S * tc.cchunks; p.relu = tc.relu; p.im2col = tc.im2col; p.out_f32 = tc.out_f32;
+  p.bias = tc.bias; p.residual = reinterpret_cast<const __nv_bfloat16*>(tc.residual); p.out = tc.out;
+  dim3 grid(ceil_div(tc.M_total, kBlockM), tc.Cout / BLOCK_N);
+  conv_tc_kernel<BLOCK_N, STAGES><<<grid, 192, L::kDynamic, s>>>(*reinterpret_cast<const CUtensorMap*>(&tc.tmap_a),
+                                                                 *reinterpret_cast<const CUtensorMap*>(&tc.tmap_b), p);
+  PDF_CHECK_LAUNCH();
+  return PDF_OK;
+}
+
+int launch_conv_tc(const TcConv& tc, cudaStream_t s) {
+  switch (tc.block_n) {
+    case 256: return launch_tc<256, 4>(tc, s);
+    case 128: return launch_tc<128, 3>(tc, s);   // 96 KB/CTA -> two CTAs per SM
+    case 64: return launch_tc<64, 4>(tc, s);     // 96 KB/CTA -> two CTAs per SM
+  }
+  set_error("launch_conv_tc: bad block_n %d", tc.block_n);
+  return PDF_ERR_ARG;
+}
+
+}  // namespace pdf
+
+// C[M,N] f32 = A[M,K] bf16 * B[N,K]^T bf16 : exercises TMA(2D) -> tcgen05.mma -> tcgen05.ld end to end
+extern "C" int pdf_selftest_umma(int M, int N, int K, const void* d_a_bf16, const void* d_b_bf16, float* d_c, pdf_stream_t stream) {
+  using namespace pdf;
+  PDF_REQUIRE(M > 0 && N % 64 == 0 && K % 64 == 0 && d_a_bf16 && d_b_bf16 && d_c, "pdf_selftest_umma: need N,K multiples of 64");
+  pdf_op op;
+  memset(&op, 0, sizeof(op));
+  op.kind = PDF_OP_CONV; op.precision = PDF_PREC_BF16;
+  op.n = 1; op.h = 1; op.w = M; op.c = K; op.k = N; op.r = 1; op.s = 1; op.stride = 1; op.pad = 0; op.ho = 1; op.wo = M;
+  op.relu = 0; op.out_f32 = 1; op.d_in = d_a_bf16; op.d_weight = d_b_bf16; op.d_out = d_c;
+  TcConv tc;
+  if (int rc = prepare_conv_tc(op, &tc)) return rc;
+  return launch_conv_tc(tc, as_stream(stream));
+}

@@ -1,0 +1,353 @@
+// K3 / K4: MIL attention head and the batched missingness sweeps (Fusion-ModDrop, MoE), FP32.
+// These are tiny, HBM/launch-bound kernels; the point is ONE launch over all bags / all (scenario, subject)
+// pairs instead of the reference's per-bag and per-scenario Python loops
+// (models/mil_attention.py:169-177, evaluation/evaluate.py:18-97).
+#include "common.cuh"
+
+namespace pdf {
+
+// ------------------------------------------------------------------------------------------------------
+// C[M,N] = A[M,K] * B[N,K]^T (+bias[N]) (ReLU) ; row strides lda/ldb/ldc; FP32 FFMA, 64x64x16 tiles.
+__global__ void __launch_bounds__(256)
+gemm_nt_f32_kernel(const float* __restrict__ A, int lda, const float* __restrict__ B, int ldb, float* __restrict__ C, int ldc,
+                   const float* __restrict__ bias, int M, int N, int K, int relu) {
+  __shared__ float As[16][64 + 4];
+  __shared__ float Bs[16][64 + 4];
+  const int tid = threadIdx.x;
+  const int m0 = blockIdx.x * 64, n0 = blockIdx.y * 64;
+  const int lr = tid >> 2, lk = (tid & 3) * 4;
+  const int ty = tid >> 4, tx = tid & 15;
+  float acc[4][4];
+#pragma unroll
+  for (int i = 0; i < 4; ++i)
+#pragma unroll
+    for (int j = 0; j < 4; ++j) acc[i][j] = 0.f;
+  for (int k0 = 0; k0 < K; k0 += 16) {
+#pragma unroll
+    for (int e = 0; e < 4; ++e) {
+      const int k = k0 + lk + e;
+      As[lk + e][lr] = (m0 + lr < M && k < K) ? __ldg(A + (size_t)(m0 + lr) * lda + k) : 0.f;
+      Bs[lk + e][lr] = (n0 + lr < N && k < K) ? __ldg(B + (size_t)(n0 + lr) * ldb + k) : 0.f;
+    }
+    __syncthreads();
+#pragma unroll
+    for (int kk = 0; kk < 16; ++kk) {
+      float a[4], b[4];
+#pragma unroll
+      for (int i = 0; i < 4; ++i) a[i] = As[kk][ty * 4 + i];
+#pragma unroll
+      for (int j = 0; j < 4; ++j) b[j] = Bs[kk][tx * 4 + j];
+#pragma unroll
+      for (int i = 0; i < 4; ++i)
+#pragma unroll
+        for (int j = 0; j < 4; ++j) acc[i][j] = fmaf(a[i], b[j], acc[i][j]);
+    }
+    __syncthreads();
+  }
+#pragma unroll
+  for (int i = 0; i < 4; ++i) {
+    const int m = m0 + ty * 4 + i;
+    if (m >= M) continue;
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+      const int n = n0 + tx * 4 + j;
+      if (n >= N) continue;
+      float v = acc[i][j];
+      if (bias) v += __ldg(bias + n);
+      if (relu) v = fmaxf(v, 0.f);
+      C[(size_t)m * ldc + n] = v;
+    }
+  }
+}
+
+static int gemm_nt(const float* A, int lda, const float* B, int ldb, float* C, int ldc, const float* bias, int M, int N, int K,
+                   int relu, cudaStream_t s) {
+  dim3 grid(ceil_div(M, 64), ceil_div(N, 64));
+  gemm_nt_f32_kernel<<<grid, 256, 0, s>>>(A, lda, B, ldb, C, ldc, bias, M, N, K, relu);
+  PDF_CHECK_LAUNCH();
+  return PDF_OK;
+}
+
+__device__ __forceinline__ float warp_sum(float v) {
+#pragma unroll
+  for (int o = 16; o; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+  return v;
+}
+__device__ __forceinline__ float sigmoidf_(float x) { return 1.0f / (1.0f + expf(-x)); }
+
+// ------------------------------------------------------------------------------------------------------
+// MIL: one block per bag, h = ReLU(instance(x)) already in `hbuf`.
+__global__ void __launch_bounds__(256)
+mil_pool_kernel(const float* __restrict__ hbuf, const int32_t* __restrict__ lens, int Lmax, pdf_mil_weights w,
+                float* __restrict__ prob) {
+  extern __shared__ float sm[];
+  float* s_score = sm;                 // [Lmax]
+  float* s_h = sm + Lmax;              // [8][H] staging, then [H] pooled
+  __shared__ float s_red[8];
+  const int bag = blockIdx.x;
+  const int len = min(lens[bag], Lmax);
+  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  const int H = w.H, A = w.A;
+  if (len <= 0) {
+    if (tid == 0) prob[bag] = w.missing_prob;
+    return;
+  }
+  const float* hb = hbuf + (size_t)bag * Lmax * H;
+  float* myh = s_h + warp * H;
+  for (int l = warp; l < len; l += 8) {
+    for (int i = lane; i < H; i += 32) myh[i] = hb[(size_t)l * H + i];
+    __syncwarp();
+    float sc = 0.f;
+    for (int a = 0; a < A; ++a) {
+      float dv = 0.f, du = 0.f;
+      const float* wv = w.w_v + (size_t)a * H;
+      for (int i = lane; i < H; i += 32) dv = fmaf(__ldg(wv + i), myh[i], dv);
+      if (w.gated) {
+        const float* wu = w.w_u + (size_t)a * H;
+        for (int i = lane; i < H; i += 32) du = fmaf(__ldg(wu + i), myh[i], du);
+      }
+      dv = warp_sum(dv) + __ldg(w.b_v + a);
+      float t = tanhf(dv);
+      if (w.gated) { du = warp_sum(du) + __ldg(w.b_u + a); t *= sigmoidf_(du); }
+      sc = fmaf(__ldg(w.w_w + a), t, sc);
+    }
+    if (lane == 0) s_score[l] = sc + __ldg(w.b_w);
+    __syncwarp();
+  }
+  __syncthreads();
+  // softmax over the valid instances (masked_fill(-1e9) on padding == exclusion)
+  float mx = -INFINITY;
+  for (int l = tid; l < len; l += 256) mx = fmaxf(mx, s_score[l]);
+  for (int o = 16; o; o >>= 1) mx = fmaxf(mx, __shfl_xor_sync(0xffffffffu, mx, o));
+  if (lane == 0) s_red[warp] = mx;
+  __syncthreads();
+  mx = s_red[0];
+  for (int i = 1; i < 8; ++i) mx = fmaxf(mx, s_red[i]);
+  __syncthreads();
+  float se = 0.f;
+  for (int l = tid; l < len; l += 256) { const float e = expf(s_score[l] - mx); s_score[l] = e; se += e; }
+  se = warp_sum(se);
+  if (lane == 0) s_red[warp] = se;
+  __syncthreads();
+  se = 0.f;
+  for (int i = 0; i < 8; ++i) se += s_red[i];
+  __syncthreads();
+  // pooled = sum_l a_l h_l ; z = w_cls . pooled + b
+  float z = 0.f;
+  for (int i = tid; i < H; i += 256) {
+    float pl = 0.f;
+    for (int l = 0; l < len; ++l) pl = fmaf(s_score[l] / se, hb[(size_t)l * H + i], pl);
+    z = fmaf(__ldg(w.w_cls + i), pl, z);
+  }
+  z = warp_sum(z);
+  if (lane == 0) s_red[warp] = z;
+  __syncthreads();
+  if (tid == 0) {
+    float t = 0.f;
+    for (int i = 0; i < 8; ++i) t += s_red[i];
+    prob[bag] = sigmoidf_(t + __ldg(w.b_cls));
+  }
+}
+
+// ------------------------------------------------------------------------------------------------------
+// one dense layer evaluated by a warp: out[o] = act(sum_i W[o,i] in[i] + b[o]); in/out in shared memory
+__device__ __forceinline__ void warp_dense(const float* __restrict__ W, const float* __restrict__ b, int n_in, int n_out,
+                                           const float* in, float* out, int relu, int lane) {
+  for (int o = 0; o < n_out; ++o) {
+    const float* wr = W + (size_t)o * n_in;
+    float acc = 0.f;
+    for (int i = lane; i < n_in; i += 32) acc = fmaf(__ldg(wr + i), in[i], acc);
+    acc = warp_sum(acc);
+    if (lane == 0) { const float v = acc + __ldg(b + o); out[o] = relu ? fmaxf(v, 0.f) : v; }
+  }
+  __syncwarp();
+}
+
+constexpr int kMaxWidth = 1024;
+
+// partials: [n_mods][N][h1] (layer-1 pre-activations per modality, no bias)
+__global__ void __launch_bounds__(256)
+moddrop_sweep_kernel(pdf_mlp net, const float* __restrict__ partials, const uint8_t* __restrict__ masks, int N, int S,
+                     float* __restrict__ prob) {
+  extern __shared__ float sm[];
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int h1 = net.dims[1];
+  int maxw = h1;
+  for (int l = 2; l <= net.n_layers; ++l) maxw = max(maxw, net.dims[l]);
+  float* bufA = sm + (size_t)warp * 2 * maxw;
+  float* bufB = bufA + maxw;
+  const int M = net.n_mods;
+  for (int n = blockIdx.x * 8 + warp; n < N; n += gridDim.x * 8) {
+    for (int s = 0; s < S; ++s) {
+      const uint8_t* mk = masks + ((size_t)s * N + n) * M;
+      const bool last0 = net.n_layers == 1;
+      for (int i = lane; i < h1; i += 32) {
+        float v = 0.f;
+        for (int m = 0; m < M; ++m)
+          if (mk[m] && net.mod_off[m + 1] > net.mod_off[m]) v += partials[((size_t)m * N + n) * h1 + i];
+        v += __ldg(net.b[0] + i);
+        bufA[i] = last0 ? v : fmaxf(v, 0.f);
+      }
+      __syncwarp();
+      float* in = bufA;
+      float* out = bufB;
+      for (int l = 1; l < net.n_layers; ++l) {
+        warp_dense(net.w[l], net.b[l], net.dims[l], net.dims[l + 1], in, out, l < net.n_layers - 1, lane);
+        float* t = in; in = out; out = t;
+      }
+      if (lane == 0) prob[(size_t)s * N + n] = sigmoidf_(in[0]);
+      __syncwarp();
+    }
+  }
+}
+
+struct MoeArgs {
+  pdf_moe net;
+  const float* x[PDF_MAX_MODS];
+};
+
+__global__ void __launch_bounds__(256)
+moe_sweep_kernel(MoeArgs a, const uint8_t* __restrict__ masks, int N, int S, int maxw, float* __restrict__ prob) {
+  extern __shared__ float sm[];
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  float* bufA = sm + (size_t)warp * 2 * maxw;
+  float* bufB = bufA + maxw;
+  const int E = a.net.n_experts, R = a.net.router_hidden;
+  for (int n = blockIdx.x * 8 + warp; n < N; n += gridDim.x * 8) {
+    float e_x[PDF_MAX_MODS], e_0[PDF_MAX_MODS];
+    for (int e = 0; e < E; ++e) {
+      const pdf_mlp& ex = a.net.expert[e];
+      for (int pass = 0; pass < 2; ++pass) {   // pass 0: the subject's features, pass 1: the masked (all-zero) input
+        for (int i = lane; i < ex.dims[0]; i += 32) bufA[i] = pass == 0 ? a.x[e][(size_t)n * ex.dims[0] + i] : 0.f;
+        __syncwarp();
+        float* in = bufA;
+        float* out = bufB;
+        for (int l = 0; l < ex.n_layers; ++l) {
+          warp_dense(ex.w[l], ex.b[l], ex.dims[l], ex.dims[l + 1], in, out, l < ex.n_layers - 1, lane);
+          float* t = in; in = out; out = t;
+        }
+        const float v = sigmoidf_(in[0]);
+        if (pass == 0) e_x[e] = v; else e_0[e] = v;
+        __syncwarp();
+      }
+    }
+    for (int s = 0; s < S; ++s) {
+      const uint8_t* mk = masks + ((size_t)s * N + n) * E;
+      // router: softmax(W1 relu(W0 mask + b0) + b1)
+      for (int h = lane; h < R; h += 32) {
+        float v = __ldg(a.net.b_r0 + h);
+        for (int m = 0; m < E; ++m) v = fmaf(__ldg(a.net.w_r0 + h * E + m), mk[m] ? 1.f : 0.f, v);
+        bufA[h] = fmaxf(v, 0.f);
+      }
+      __syncwarp();
+      float logit[PDF_MAX_MODS];
+      float mx = -INFINITY;
+      for (int m = 0; m < E; ++m) {
+        float v = 0.f;
+        for (int h = lane; h < R; h += 32) v = fmaf(__ldg(a.net.w_r1 + m * R + h), bufA[h], v);
+        v = warp_sum(v) + __ldg(a.net.b_r1 + m);
+        logit[m] = v;
+        mx = fmaxf(mx, v);
+      }
+      float se = 0.f;
+      for (int m = 0; m < E; ++m) { logit[m] = expf(logit[m] - mx); se += logit[m]; }
+      float o = 0.f;
+      for (int m = 0; m < E; ++m) o += (mk[m] ? e_x[m] : e_0[m]) * (logit[m] / se);
+      if (lane == 0) prob[(size_t)s * N + n] = o;
+      __syncwarp();
+    }
+  }
+}
+
+static int check_mlp(const pdf_mlp& m, const char* what) {
+  PDF_REQUIRE(m.n_layers >= 1 && m.n_layers <= PDF_MAX_LAYERS, "%s: n_layers out of range", what);
+  PDF_REQUIRE(m.dims[m.n_layers] == 1, "%s: last layer must have one output", what);
+  for (int l = 0; l < m.n_layers; ++l) {
+    PDF_REQUIRE(m.w[l] && m.b[l] && m.dims[l] >= 0, "%s: null weights in layer %d", what, l);
+    if (l > 0) PDF_REQUIRE(m.dims[l] >= 1 && m.dims[l] <= kMaxWidth, "%s: hidden width must be 1..%d", what, kMaxWidth);
+  }
+  return PDF_OK;
+}
+
+}  // namespace pdf
+
+using namespace pdf;
+
+extern "C" size_t pdf_mil_workspace_bytes(const pdf_mil_weights* w, int n_bags, int Lmax) {
+  if (!w || n_bags <= 0 || Lmax <= 0) return 0;
+  return (size_t)n_bags * Lmax * w->H * sizeof(float) + 256;
+}
+
+extern "C" int pdf_mil_forward(const pdf_mil_weights* w, int n_bags, int Lmax, const float* d_bags, const int32_t* d_len,
+                               void* d_workspace, float* d_prob, pdf_stream_t stream) {
+  PDF_REQUIRE(w && n_bags > 0 && Lmax > 0 && d_bags && d_len && d_workspace && d_prob, "pdf_mil_forward: bad arguments");
+  PDF_REQUIRE(w->D > 0 && w->H > 0 && w->H <= 2048 && w->A > 0, "pdf_mil_forward: bad dims");
+  PDF_REQUIRE(w->w_inst && w->b_inst && w->w_v && w->b_v && w->w_w && w->b_w && w->w_cls && w->b_cls && (!w->gated || (w->w_u && w->b_u)),
+              "pdf_mil_forward: null weight pointer");
+  cudaStream_t s = as_stream(stream);
+  float* hbuf = reinterpret_cast<float*>(d_workspace);
+  // instance projection for every (padded) instance of every bag at once: M = n_bags * Lmax
+  if (int rc = gemm_nt(d_bags, w->D, w->w_inst, w->D, hbuf, w->H, w->b_inst, n_bags * Lmax, w->H, w->D, 1, s)) return rc;
+  const size_t smem = ((size_t)Lmax + 8 * (size_t)w->H) * sizeof(float);
+  PDF_REQUIRE(smem <= 200 * 1024, "pdf_mil_forward: bag too large for shared memory");
+  if (smem > 48 * 1024) PDF_CHECK_CUDA(cudaFuncSetAttribute(mil_pool_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+  mil_pool_kernel<<<n_bags, 256, smem, s>>>(hbuf, d_len, Lmax, *w, d_prob);
+  PDF_CHECK_LAUNCH();
+  return PDF_OK;
+}
+
+extern "C" size_t pdf_moddrop_workspace_bytes(const pdf_mlp* net, int n_subjects) {
+  if (!net || n_subjects <= 0) return 0;
+  return (size_t)net->n_mods * n_subjects * net->dims[1] * sizeof(float) + 256;
+}
+
+extern "C" int pdf_moddrop_sweep(const pdf_mlp* net, int n_subjects, int n_scenarios, const float* d_x, const uint8_t* d_masks,
+                                 void* d_workspace, float* d_prob, pdf_stream_t stream) {
+  PDF_REQUIRE(net && n_subjects > 0 && n_scenarios > 0 && d_x && d_masks && d_workspace && d_prob, "pdf_moddrop_sweep: bad arguments");
+  if (int rc = check_mlp(*net, "pdf_moddrop_sweep")) return rc;
+  PDF_REQUIRE(net->n_mods >= 1 && net->n_mods <= PDF_MAX_MODS && net->mod_off[0] == 0 && net->mod_off[net->n_mods] == net->dims[0],
+              "pdf_moddrop_sweep: modality offsets must tile [0, F)");
+  PDF_REQUIRE(net->dims[1] <= kMaxWidth, "pdf_moddrop_sweep: first hidden width must be <= %d", kMaxWidth);
+  cudaStream_t s = as_stream(stream);
+  const int F = net->dims[0], h1 = net->dims[1];
+  float* partials = reinterpret_cast<float*>(d_workspace);
+  // linearity of layer 1: (x (.) mask) W1^T = sum_m mask_m * (x_m W1_m^T)  -> per-modality partials once, reused by every scenario
+  for (int m = 0; m < net->n_mods; ++m) {
+    const int d = net->mod_off[m + 1] - net->mod_off[m];
+    if (d <= 0) continue;
+    if (int rc = gemm_nt(d_x + net->mod_off[m], F, net->w[0] + net->mod_off[m], F, partials + (size_t)m * n_subjects * h1, h1,
+                         nullptr, n_subjects, h1, d, 0, s))
+      return rc;
+  }
+  int maxw = h1;
+  for (int l = 2; l <= net->n_layers; ++l) maxw = max(maxw, net->dims[l]);
+  const size_t smem = (size_t)8 * 2 * maxw * sizeof(float);
+  if (smem > 48 * 1024) PDF_CHECK_CUDA(cudaFuncSetAttribute(moddrop_sweep_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+  const int blocks = max(1, min(ceil_div(n_subjects, 8), num_sms() * 8));
+  moddrop_sweep_kernel<<<blocks, 256, smem, s>>>(*net, partials, d_masks, n_subjects, n_scenarios, d_prob);
+  PDF_CHECK_LAUNCH();
+  return PDF_OK;
+}
+
+extern "C" int pdf_moe_sweep(const pdf_moe* net, int n_subjects, int n_scenarios, const float* const* d_x, const uint8_t* d_masks,
+                             float* d_prob, pdf_stream_t stream) {
+  PDF_REQUIRE(net && n_subjects > 0 && n_scenarios > 0 && d_x && d_masks && d_prob, "pdf_moe_sweep: bad arguments");
+  PDF_REQUIRE(net->n_experts >= 1 && net->n_experts <= PDF_MAX_MODS && net->router_hidden >= 1 && net->router_hidden <= kMaxWidth &&
+              net->w_r0 && net->b_r0 && net->w_r1 && net->b_r1, "pdf_moe_sweep: bad router");
+  MoeArgs a;
+  a.net = *net;
+  int maxw = net->router_hidden;
+  for (int e = 0; e < net->n_experts; ++e) {
+    if (int rc = check_mlp(net->expert[e], "pdf_moe_sweep expert")) return rc;
+    PDF_REQUIRE(d_x[e] && net->expert[e].dims[0] >= 1 && net->expert[e].dims[0] <= 8192, "pdf_moe_sweep: expert input width 1..8192");
+    a.x[e] = d_x[e];
+    for (int l = 0; l <= net->expert[e].n_layers; ++l) maxw = max(maxw, net->expert[e].dims[l]);
+  }
+  const size_t smem = (size_t)8 * 2 * maxw * sizeof(float);
+  PDF_REQUIRE(smem <= 200 * 1024, "pdf_moe_sweep: layers too wide for shared memory");
+  if (smem > 48 * 1024) PDF_CHECK_CUDA(cudaFuncSetAttribute(moe_sweep_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+  const int blocks = max(1, min(ceil_div(n_subjects, 8), num_sms() * 8));
+  moe_sweep_kernel<<<blocks, 256, smem, as_stream(stream)>>>(a, d_masks, n_subjects, n_scenarios, maxw, d_prob);
+  PDF_CHECK_LAUNCH();
+  return PDF_OK;
+}

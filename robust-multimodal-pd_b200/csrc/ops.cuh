@@ -1,0 +1,29 @@
+// Internal launch entry points shared by plan.cu.
+#pragma once
+#include "common.cuh"
+
+namespace pdf {
+
+int launch_conv_f32(const pdf_op& op, cudaStream_t s);
+int launch_maxpool(const pdf_op& op, cudaStream_t s);
+int launch_avgpool(const pdf_op& op, cudaStream_t s);
+int launch_stem_im2col(const pdf_op& op, cudaStream_t s);
+
+// tcgen05 path: one prepared launch per bf16 conv op (tensor maps are 128-byte opaque blobs)
+struct alignas(64) TensorMapBlob { unsigned char bytes[128]; };
+
+struct TcConv {
+  TensorMapBlob tmap_a, tmap_b;
+  int block_n;      // 64 | 128 | 256
+  int im2col;       // 1: A through im2col-mode TMA, 0: plain 2D tile of the [M, C] matrix (1x1 stride-1)
+  int M_total, Cout, Ho, Wo, stride, pad, R, S, cchunks, relu;
+  const float* bias;
+  const void* residual;   // bf16 [M, Cout]
+  void* out;              // bf16 [M, Cout] or f32 when out_f32
+  int out_f32;
+};
+
+int prepare_conv_tc(const pdf_op& op, TcConv* out);
+int launch_conv_tc(const TcConv& tc, cudaStream_t s);
+
+}  // namespace pdf

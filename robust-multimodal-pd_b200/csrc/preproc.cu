@@ -1,0 +1,632 @@
+// K1: raw T1 volume -> network input, batched over subjects, HBM-bound.
+//
+//   resample_kernel        nan/inf scrub + trilinear zoom in float64 (scipy order, one f32 rounding)
+//                          + level-0 radix histogram of positive voxels + per-plane maxima (3 axes) + global min
+//   scan_kernel<0|1|2>     per subject: locate the bucket of each of the 4 order statistics numpy.percentile needs
+//   hist_kernel<1|2>       refinement histograms (11 then 8 bits) over the resampled volume
+//   finalize (in scan<2>)  numpy lerp -> lo/hi, extents from plane maxima, np.linspace(...).astype(int) indices
+//   extract_planes_kernel  axis-2 planes (stride-T2 gather) -> compact [L2][T0][T1]
+//   resize_kernel          clip/min-max + bilinear (align_corners=False) + (x-mean)/std -> bf16 C1 or f32 NHWC3
+//
+// Reference call sites: data/openneuro_features.py:22-32, 121-151, 250-255 (see include/pdfusion_b200.h).
+#include "common.cuh"
+
+namespace pdf {
+
+constexpr int kPlaneMax = 1024;   // max target dim
+constexpr int kH0 = 4096, kH1 = 2048, kH2 = 256;
+constexpr int kNQ = 4;            // sorted[f0], sorted[f1] for q=1 and q=99
+
+struct SubjState {
+  uint32_t hist0[kH0];
+  uint32_t hist1[kNQ][kH1];
+  uint32_t hist2[kNQ][kH2];
+  uint32_t plane_max[3][kPlaneMax];  // ordered keys; 0 = "no voxel seen"
+  uint32_t gmin_key;                 // ordered key of the global minimum (init 0xffffffff)
+  uint32_t n_pos;
+  uint32_t prefix[kNQ];              // high bits of the answer found so far (0xffffffff = no query)
+  uint32_t rank[kNQ];                // residual rank inside the current bucket
+  float gamma[2];                    // numpy gamma for q=1 / q=99
+  uint32_t pad[3];
+};
+
+struct ZoomTables {                  // lives at the head of the workspace
+  int i0[3][kPlaneMax];
+  int i1[3][kPlaneMax];
+  double w0[3][kPlaneMax];
+  double w1[3][kPlaneMax];
+};
+
+struct Workspace {
+  ZoomTables* tabs;
+  SubjState* st;
+  float* planes;  // [B][L2z][T0][T1]
+};
+
+static size_t align_up(size_t x, size_t a) { return (x + a - 1) / a * a; }
+
+static int count_axis2(const pdf_preproc_cfg* cfg) {
+  int n = 0;
+  for (int a = 0; a < cfg->n_axes; ++a)
+    if (cfg->axes[a] == 2) n += cfg->counts[a];
+  return n;
+}
+
+static Workspace carve(const pdf_preproc_cfg* cfg, int batch, void* ws) {
+  Workspace w;
+  char* p = reinterpret_cast<char*>(ws);
+  w.tabs = reinterpret_cast<ZoomTables*>(p);
+  p += align_up(sizeof(ZoomTables), 256);
+  w.st = reinterpret_cast<SubjState*>(p);
+  p += align_up(sizeof(SubjState) * (size_t)batch, 256);
+  w.planes = reinterpret_cast<float*>(p);
+  return w;
+}
+
+static int validate(const pdf_preproc_cfg* cfg, int batch) {
+  PDF_REQUIRE(cfg != nullptr && batch > 0, "preproc: null cfg or batch <= 0");
+  for (int i = 0; i < 3; ++i) {
+    PDF_REQUIRE(cfg->in_shape[i] >= 2 && cfg->out_shape[i] >= 2 && cfg->out_shape[i] <= kPlaneMax,
+                "preproc: shapes must be >=2 and target dims <= %d", kPlaneMax);
+  }
+  PDF_REQUIRE(cfg->n_axes >= 1 && cfg->n_axes <= PDF_MAX_AXES, "preproc: n_axes must be 1..3");
+  for (int a = 0; a < cfg->n_axes; ++a) {
+    PDF_REQUIRE(cfg->axes[a] >= 0 && cfg->axes[a] <= 2, "preproc: axis must be 0..2");
+    PDF_REQUIRE(cfg->counts[a] >= 1 && cfg->counts[a] <= kPlaneMax, "preproc: slice count out of range");
+  }
+  PDF_REQUIRE(cfg->input_size >= 1, "preproc: input_size must be positive");
+  return PDF_OK;
+}
+
+// ------------------------------------------------------------------------------------------------------
+__global__ void init_tables_kernel(ZoomTables* tabs, SubjState* st, int batch, int X, int Y, int Z, int T0, int T1, int T2) {
+  const int src[3] = {X, Y, Z};
+  const int dst[3] = {T0, T1, T2};
+  int t = blockIdx.x * blockDim.x + threadIdx.x;
+  for (int a = 0; a < 3; ++a) {
+    if (t < dst[a]) {
+      // ndimage.zoom(grid_mode=False): coordinate = i * (src-1)/(dst-1) in float64
+      double step = __ddiv_rn((double)(src[a] - 1), (double)(dst[a] - 1));
+      double c = __dmul_rn((double)t, step);
+      double f = floor(c);
+      double w1 = __dsub_rn(c, f);
+      int i0 = (int)f;
+      tabs->i0[a][t] = i0;
+      tabs->i1[a][t] = min(i0 + 1, src[a] - 1);
+      tabs->w0[a][t] = __dsub_rn(1.0, w1);
+      tabs->w1[a][t] = w1;
+    }
+  }
+  if (t < batch) st[t].gmin_key = 0xffffffffu;
+}
+
+__device__ __forceinline__ double scrub(float v) {  // np.nan_to_num(nan=0, posinf=0, neginf=0)
+  return isfinite(v) ? (double)v : 0.0;
+}
+
+__global__ void __launch_bounds__(1024)
+resample_kernel(const float* __restrict__ raw, float* __restrict__ zoomed, SubjState* __restrict__ states,
+                const ZoomTables* __restrict__ tabs, int X, int Y, int Z, int T0, int T1, int T2, int rows_per_block) {
+  __shared__ uint32_t s_hist[kH0];
+  __shared__ uint32_t s_imax[kPlaneMax];
+  __shared__ uint32_t s_jmax[kPlaneMax];
+  const int b = blockIdx.y;
+  const int tid = threadIdx.x;
+  for (int i = tid; i < kH0; i += blockDim.x) s_hist[i] = 0;
+  for (int i = tid; i < kPlaneMax; i += blockDim.x) { s_imax[i] = 0; s_jmax[i] = 0; }
+  __syncthreads();
+
+  SubjState* st = states + b;
+  const float* rb = raw + (size_t)b * X * Y * Z;
+  float* zb = zoomed + (size_t)b * T0 * T1 * T2;
+  const int nrows = T0 * T1;
+  const int row0 = blockIdx.x * rows_per_block;
+  const int row1 = min(row0 + rows_per_block, nrows);
+  uint32_t tmin = 0xffffffffu;
+
+  const int kchunks = (T2 + blockDim.x - 1) / blockDim.x;
+  for (int kc = 0; kc < kchunks; ++kc) {
+    const int k = kc * blockDim.x + tid;
+    const bool act = k < T2;
+    int z0 = 0, z1 = 0;
+    double wz0 = 0.0, wz1 = 0.0;
+    if (act) { z0 = tabs->i0[2][k]; z1 = tabs->i1[2][k]; wz0 = tabs->w0[2][k]; wz1 = tabs->w1[2][k]; }
+    uint32_t kmax = 0;
+    for (int row = row0; row < row1; ++row) {
+      const int i = row / T1, j = row - i * T1;
+      uint32_t key = 0;
+      if (act) {
+        const int x0 = tabs->i0[0][i], x1 = tabs->i1[0][i];
+        const int y0 = tabs->i0[1][j], y1 = tabs->i1[1][j];
+        const double wx0 = tabs->w0[0][i], wx1 = tabs->w1[0][i];
+        const double wy0 = tabs->w0[1][j], wy1 = tabs->w1[1][j];
+        const float* p00 = rb + ((size_t)x0 * Y + y0) * Z;
+        const float* p01 = rb + ((size_t)x0 * Y + y1) * Z;
+        const float* p10 = rb + ((size_t)x1 * Y + y0) * Z;
+        const float* p11 = rb + ((size_t)x1 * Y + y1) * Z;
+        const double v000 = scrub(__ldg(p00 + z0)), v001 = scrub(__ldg(p00 + z1));
+        const double v010 = scrub(__ldg(p01 + z0)), v011 = scrub(__ldg(p01 + z1));
+        const double v100 = scrub(__ldg(p10 + z0)), v101 = scrub(__ldg(p10 + z1));
+        const double v110 = scrub(__ldg(p11 + z0)), v111 = scrub(__ldg(p11 + z1));
+        // scipy NI_ZoomShift order: t += ((v*wx)*wy)*wz, taps in (x,y,z) lexicographic order, no FMA
+        double t = 0.0;
+        t = __dadd_rn(t, __dmul_rn(__dmul_rn(__dmul_rn(v000, wx0), wy0), wz0));
+        t = __dadd_rn(t, __dmul_rn(__dmul_rn(__dmul_rn(v001, wx0), wy0), wz1));
+        t = __dadd_rn(t, __dmul_rn(__dmul_rn(__dmul_rn(v010, wx0), wy1), wz0));
+        t = __dadd_rn(t, __dmul_rn(__dmul_rn(__dmul_rn(v011, wx0), wy1), wz1));
+        t = __dadd_rn(t, __dmul_rn(__dmul_rn(__dmul_rn(v100, wx1), wy0), wz0));
+        t = __dadd_rn(t, __dmul_rn(__dmul_rn(__dmul_rn(v101, wx1), wy0), wz1));
+        t = __dadd_rn(t, __dmul_rn(__dmul_rn(__dmul_rn(v110, wx1), wy1), wz0));
+        t = __dadd_rn(t, __dmul_rn(__dmul_rn(__dmul_rn(v111, wx1), wy1), wz1));
+        const float out = __double2float_rn(t);
+        zb[(size_t)row * T2 + k] = out;
+        key = float_to_ordered(out);
+        kmax = max(kmax, key);
+        tmin = min(tmin, key);
+        if (out > 0.0f) atomicAdd(&s_hist[__float_as_uint(out) >> 19], 1u);
+      }
+      const uint32_t wmax = __reduce_max_sync(0xffffffffu, key);
+      if ((tid & 31) == 0 && wmax != 0) {
+        atomicMax(&s_imax[i], wmax);
+        atomicMax(&s_jmax[j], wmax);
+      }
+    }
+    if (act && kmax != 0) atomicMax(&st->plane_max[2][k], kmax);
+  }
+  const uint32_t wmin = __reduce_min_sync(0xffffffffu, tmin);
+  if ((tid & 31) == 0 && wmin != 0xffffffffu) atomicMin(&st->gmin_key, wmin);
+  __syncthreads();
+  for (int i = tid; i < kH0; i += blockDim.x) {
+    const uint32_t c = s_hist[i];
+    if (c) atomicAdd(&st->hist0[i], c);
+  }
+  for (int i = tid; i < kPlaneMax; i += blockDim.x) {
+    if (s_imax[i]) atomicMax(&st->plane_max[0][i], s_imax[i]);
+    if (s_jmax[i]) atomicMax(&st->plane_max[1][i], s_jmax[i]);
+  }
+}
+
+// ------------------------------------------------------------------------------------------------------
+// Block-wide bucket search: smallest bin with cumulative count > rank. 256 threads, NB % 256 == 0.
+template <int NB>
+__device__ void find_bucket(const uint32_t* __restrict__ hist, uint32_t rank, uint32_t* s_scan, uint32_t* out_bin,
+                            uint32_t* out_residual) {
+  constexpr int PER = NB / 256;
+  const int tid = threadIdx.x;
+  uint32_t local = 0;
+#pragma unroll
+  for (int i = 0; i < PER; ++i) local += hist[tid * PER + i];
+  // inclusive scan of 256 partials
+  uint32_t v = local;
+#pragma unroll
+  for (int o = 1; o < 32; o <<= 1) {
+    uint32_t n = __shfl_up_sync(0xffffffffu, v, o);
+    if ((tid & 31) >= o) v += n;
+  }
+  if ((tid & 31) == 31) s_scan[tid >> 5] = v;
+  __syncthreads();
+  if (tid < 8) {
+    uint32_t w = s_scan[tid];
+#pragma unroll
+    for (int o = 1; o < 8; o <<= 1) {
+      uint32_t n = __shfl_up_sync(0xffu, w, o);
+      if (tid >= o) w += n;
+    }
+    s_scan[tid] = w;
+  }
+  __syncthreads();
+  const uint32_t incl = v + ((tid >> 5) ? s_scan[(tid >> 5) - 1] : 0u);
+  const uint32_t excl = incl - local;
+  if (rank >= excl && rank < incl) {
+    uint32_t acc = excl;
+    for (int i = 0; i < PER; ++i) {
+      const uint32_t c = hist[tid * PER + i];
+      if (rank < acc + c) { *out_bin = tid * PER + i; *out_residual = rank - acc; break; }
+      acc += c;
+    }
+  }
+  __syncthreads();
+}
+
+struct FinalizeArgs {
+  int T[3];
+  int n_axes;
+  int axes[PDF_MAX_AXES];
+  int counts[PDF_MAX_AXES];
+  int lmax;
+};
+
+__device__ __forceinline__ float normalise(float v, float lo, float hi, float den) {
+  // np.clip(v, lo, hi) = minimum(maximum(v, lo), hi); then (v - lo) / den, all float32
+  const float c = fminf(fmaxf(v, lo), hi);
+  return __fdiv_rn(__fsub_rn(c, lo), den);
+}
+
+template <int LEVEL>
+__global__ void __launch_bounds__(256)
+scan_kernel(SubjState* __restrict__ states, FinalizeArgs fa, float* __restrict__ lohi, int32_t* __restrict__ indices,
+            int32_t* __restrict__ nslices) {
+  __shared__ uint32_t s_scan[8];
+  __shared__ uint32_t s_bin[kNQ], s_res[kNQ];
+  __shared__ float s_lohi[3];
+  __shared__ int s_first, s_last;
+  SubjState* st = states + blockIdx.x;
+  const int tid = threadIdx.x;
+
+  if (LEVEL == 0) {
+    // n_pos and the numpy 'linear' virtual indices, evaluated in float32 as numpy 2.x does (NEP 50)
+    __shared__ uint32_t s_n;
+    uint32_t local = 0;
+    for (int i = tid; i < kH0; i += 256) local += st->hist0[i];
+    for (int o = 16; o; o >>= 1) local += __shfl_xor_sync(0xffffffffu, local, o);
+    if (tid == 0) s_n = 0;
+    __syncthreads();
+    if ((tid & 31) == 0) atomicAdd(&s_n, local);
+    __syncthreads();
+    const uint32_t n = s_n;
+    if (tid == 0) {
+      st->n_pos = n;
+      for (int qi = 0; qi < 2; ++qi) {
+        if (n == 0) { st->prefix[2 * qi] = st->prefix[2 * qi + 1] = 0xffffffffu; continue; }
+        const float q32 = __fdiv_rn(qi == 0 ? 1.0f : 99.0f, 100.0f);
+        const float virt = __fmul_rn((float)(n - 1), q32);
+        const float prev = floorf(virt);
+        st->gamma[qi] = __fsub_rn(virt, prev);
+        uint32_t f0, f1;
+        if (virt >= (float)(n - 1)) { f0 = f1 = n - 1; }   // numpy: indexes above bounds -> last element
+        else { f0 = (uint32_t)prev; f1 = f0 + 1; }
+        st->rank[2 * qi] = f0;
+        st->rank[2 * qi + 1] = f1;
+        st->prefix[2 * qi] = st->prefix[2 * qi + 1] = 0;
+      }
+    }
+    __syncthreads();
+    if (n == 0) return;
+    for (int q = 0; q < kNQ; ++q) {
+      find_bucket<kH0>(st->hist0, st->rank[q], s_scan, &s_bin[q], &s_res[q]);
+    }
+    if (tid < kNQ) { st->prefix[tid] = s_bin[tid]; st->rank[tid] = s_res[tid]; }
+    return;
+  }
+  if (LEVEL == 1) {
+    if (st->n_pos == 0) return;
+    for (int q = 0; q < kNQ; ++q) find_bucket<kH1>(st->hist1[q], st->rank[q], s_scan, &s_bin[q], &s_res[q]);
+    if (tid < kNQ) { st->prefix[tid] = (st->prefix[tid] << 11) | s_bin[tid]; st->rank[tid] = s_res[tid]; }
+    return;
+  }
+  // LEVEL == 2: final order statistics, lerp, extents, indices
+  const bool has_pos = st->n_pos != 0;
+  if (has_pos) {
+    for (int q = 0; q < kNQ; ++q) find_bucket<kH2>(st->hist2[q], st->rank[q], s_scan, &s_bin[q], &s_res[q]);
+  }
+  __syncthreads();
+  // global max (needed for the no-positive branch) from the axis-0 plane maxima
+  if (tid == 0) { s_first = 0; s_last = 0; }
+  __syncthreads();
+  {
+    uint32_t m = 0;
+    for (int i = tid; i < fa.T[0]; i += 256) m = max(m, st->plane_max[0][i]);
+    for (int o = 16; o; o >>= 1) m = max(m, __shfl_xor_sync(0xffffffffu, m, o));
+    if ((tid & 31) == 0) atomicMax(reinterpret_cast<unsigned int*>(&s_last), m);
+  }
+  __syncthreads();
+  if (tid == 0) {
+    float lo, hi, den;
+    if (has_pos) {
+      float os[kNQ];
+      for (int q = 0; q < kNQ; ++q) os[q] = __uint_as_float((st->prefix[q] << 8) | s_bin[q]);
+      float r[2];
+      for (int qi = 0; qi < 2; ++qi) {  // numpy _lerp in float32
+        const float a = os[2 * qi], b = os[2 * qi + 1], g = st->gamma[qi];
+        const float d = __fsub_rn(b, a);
+        r[qi] = (g >= 0.5f) ? __fsub_rn(b, __fmul_rn(d, __fsub_rn(1.0f, g))) : __fadd_rn(a, __fmul_rn(d, g));
+      }
+      lo = r[0]; hi = r[1];
+      den = __fadd_rn(__fsub_rn(hi, lo), 1e-6f);      // np.float32 scalars: stays float32
+    } else {
+      lo = ordered_to_float(st->gmin_key);            // float(np.min(volume)), float(np.max(volume))
+      hi = ordered_to_float((uint32_t)s_last);
+      den = __double2float_rn(__dadd_rn(__dsub_rn((double)hi, (double)lo), 1e-6));  // python floats: float64 then cast
+    }
+    s_lohi[0] = lo; s_lohi[1] = hi; s_lohi[2] = den;
+    float* o = lohi + 4 * (size_t)blockIdx.x;
+    o[0] = lo; o[1] = hi; o[2] = den; o[3] = has_pos ? 1.0f : 0.0f;
+  }
+  __syncthreads();
+  const float lo = s_lohi[0], hi = s_lohi[1], den = s_lohi[2];
+  int off = 0;
+  for (int a = 0; a < fa.n_axes; ++a) {
+    const int axis = fa.axes[a], T = fa.T[axis], count = fa.counts[a];
+    if (tid == 0) { s_first = T; s_last = -1; }
+    __syncthreads();
+    int lf = T, ll = -1;
+    for (int k = tid; k < T; k += 256) {
+      const uint32_t key = st->plane_max[axis][k];
+      if (key != 0 && normalise(ordered_to_float(key), lo, hi, den) > 0.0f) { lf = min(lf, k); ll = max(ll, k); }
+    }
+    for (int o = 16; o; o >>= 1) {
+      lf = min(lf, __shfl_xor_sync(0xffffffffu, lf, o));
+      ll = max(ll, __shfl_xor_sync(0xffffffffu, ll, o));
+    }
+    if ((tid & 31) == 0) { atomicMin(&s_first, lf); atomicMax(&s_last, ll); }
+    __syncthreads();
+    int first = s_first, last = s_last;
+    if (last < 0) { first = 0; last = T - 1; }        // idxs = np.arange(axis_len)
+    const int n = min(count, last - first + 1);
+    if (tid == 0) nslices[(size_t)blockIdx.x * fa.n_axes + a] = n;
+    // np.linspace(first, last, n).astype(int): float64 i*step + first, endpoint forced, truncation
+    const double step = (n > 1) ? __ddiv_rn(__dsub_rn((double)last, (double)first), (double)(n - 1)) : 0.0;
+    for (int t = tid; t < count; t += 256) {
+      int v = -1;
+      if (t < n) {
+        if (n == 1) v = first;
+        else if (t == n - 1) v = last;
+        else v = (int)__dadd_rn(__dmul_rn((double)t, step), (double)first);
+      }
+      indices[(size_t)blockIdx.x * fa.lmax + off + t] = v;
+    }
+    off += count;
+    __syncthreads();
+  }
+}
+
+template <int LEVEL>
+__global__ void __launch_bounds__(256)
+hist_kernel(const float* __restrict__ zoomed, SubjState* __restrict__ states, size_t voxels) {
+  constexpr int NB = (LEVEL == 1) ? kH1 : kH2;
+  __shared__ uint32_t s_hist[kNQ][NB];
+  __shared__ uint32_t s_prefix[kNQ];
+  SubjState* st = states + blockIdx.y;
+  if (st->n_pos == 0) return;
+  const int tid = threadIdx.x;
+  for (int i = tid; i < kNQ * NB; i += 256) (&s_hist[0][0])[i] = 0;
+  if (tid < kNQ) s_prefix[tid] = st->prefix[tid];
+  __syncthreads();
+  const uint32_t p0 = s_prefix[0], p1 = s_prefix[1], p2 = s_prefix[2], p3 = s_prefix[3];
+  const float* zb = zoomed + (size_t)blockIdx.y * voxels;
+  auto visit = [&](float v) {
+    if (v > 0.0f) {
+      const uint32_t bits = __float_as_uint(v);
+      const uint32_t hi = (LEVEL == 1) ? (bits >> 19) : (bits >> 8);
+      const uint32_t bin = (LEVEL == 1) ? ((bits >> 8) & 0x7ffu) : (bits & 0xffu);
+      if (hi == p0) atomicAdd(&s_hist[0][bin], 1u);
+      if (hi == p1) atomicAdd(&s_hist[1][bin], 1u);
+      if (hi == p2) atomicAdd(&s_hist[2][bin], 1u);
+      if (hi == p3) atomicAdd(&s_hist[3][bin], 1u);
+    }
+  };
+  const size_t n4 = voxels / 4;
+  const float4* z4 = reinterpret_cast<const float4*>(zb);
+  const bool aligned = ((reinterpret_cast<uintptr_t>(zb) & 15) == 0);
+  if (aligned) {
+    for (size_t i = (size_t)blockIdx.x * 256 + tid; i < n4; i += (size_t)gridDim.x * 256) {
+      const float4 v = z4[i];
+      visit(v.x); visit(v.y); visit(v.z); visit(v.w);
+    }
+    for (size_t i = n4 * 4 + (size_t)blockIdx.x * 256 + tid; i < voxels; i += (size_t)gridDim.x * 256) visit(zb[i]);
+  } else {
+    for (size_t i = (size_t)blockIdx.x * 256 + tid; i < voxels; i += (size_t)gridDim.x * 256) visit(zb[i]);
+  }
+  __syncthreads();
+  for (int i = tid; i < kNQ * NB; i += 256) {
+    const uint32_t c = (&s_hist[0][0])[i];
+    if (c) {
+      if (LEVEL == 1) atomicAdd(&st->hist1[i / NB][i % NB], c);
+      else atomicAdd(&st->hist2[i / NB][i % NB], c);
+    }
+  }
+}
+
+// ------------------------------------------------------------------------------------------------------
+__global__ void normalize_kernel(const float* __restrict__ zoomed, const float* __restrict__ lohi, float* __restrict__ out,
+                                 size_t voxels) {
+  const float* l = lohi + 4 * (size_t)blockIdx.y;
+  const float lo = l[0], hi = l[1], den = l[2];
+  const size_t base = (size_t)blockIdx.y * voxels;
+  for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < voxels; i += (size_t)gridDim.x * blockDim.x)
+    out[base + i] = normalise(zoomed[base + i], lo, hi, den);
+}
+
+// axis-2 planes: vol[:, :, idx] has stride T2 between neighbours; copy the selected planes into a compact
+// [B][L2][T0*T1] buffer (coalesced writes) so the resize kernel reads rows.
+__global__ void extract_planes_kernel(const float* __restrict__ zoomed, const int32_t* __restrict__ indices, int lmax,
+                                      int off2, int cnt2, float* __restrict__ planes, int T0, int T1, int T2) {
+  const int b = blockIdx.z, l = blockIdx.y;
+  const int idx = indices[(size_t)b * lmax + off2 + l];
+  if (idx < 0) return;
+  const size_t n = (size_t)T0 * T1;
+  const float* zb = zoomed + (size_t)b * n * T2 + idx;
+  float* pb = planes + ((size_t)b * cnt2 + l) * n;
+  for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (size_t)gridDim.x * blockDim.x)
+    pb[i] = __ldg(zb + i * T2);
+}
+
+struct ResizeArgs {
+  int T[3];
+  int n_axes;
+  int axes[PDF_MAX_AXES];
+  int counts[PDF_MAX_AXES];
+  int lmax, S, cnt2;
+  float mean[3], stdv[3];
+};
+
+template <int MODE>
+__global__ void __launch_bounds__(256)
+resize_kernel(const float* __restrict__ zoomed, const float* __restrict__ planes, const float* __restrict__ lohi,
+              const int32_t* __restrict__ indices, const int32_t* __restrict__ nslices, void* __restrict__ out, ResizeArgs ra) {
+  const int b = blockIdx.z, l = blockIdx.y;
+  const int S = ra.S;
+  const int pix = blockIdx.x * blockDim.x + threadIdx.x;
+  if (pix >= S * S) return;
+  // locate the axis group of slot l
+  int a = 0, t = l, off2 = 0;
+  while (a < ra.n_axes - 1 && t >= ra.counts[a]) { if (ra.axes[a] == 2) off2 += ra.counts[a]; t -= ra.counts[a]; ++a; }
+  const int axis = ra.axes[a];
+  const bool valid = t < nslices[(size_t)b * ra.n_axes + a];
+  const size_t opix = (((size_t)b * ra.lmax + l) * S * S + pix);
+  if (!valid) {
+    if (MODE == PDF_OUT_BF16_C1) reinterpret_cast<__nv_bfloat16*>(out)[opix] = __float2bfloat16(0.0f);
+    else { float* o = reinterpret_cast<float*>(out) + opix * 3; o[0] = o[1] = o[2] = 0.0f; }
+    return;
+  }
+  const int idx = indices[(size_t)b * ra.lmax + l];
+  const int T0 = ra.T[0], T1 = ra.T[1], T2 = ra.T[2];
+  const float* src;
+  int H, W;
+  size_t rs;
+  if (axis == 0) { src = zoomed + ((size_t)b * T0 + idx) * T1 * T2; H = T1; W = T2; rs = T2; }
+  else if (axis == 1) { src = zoomed + (size_t)b * T0 * T1 * T2 + (size_t)idx * T2; H = T0; W = T2; rs = (size_t)T1 * T2; }
+  else { src = planes + ((size_t)b * ra.cnt2 + off2 + t) * T0 * T1; H = T0; W = T1; rs = T1; }
+  const float* l4 = lohi + 4 * (size_t)b;
+  const float lo = l4[0], hi = l4[1], den = l4[2];
+  const int oy = pix / S, ox = pix - oy * S;
+  // ATen area_pixel_compute_source_index(align_corners=False): (dst + 0.5) * (in/out) - 0.5, clamped at 0
+  const float sh = __fdiv_rn((float)H, (float)S), sw = __fdiv_rn((float)W, (float)S);
+  const float fy = fmaxf(__fsub_rn(__fmul_rn(__fadd_rn((float)oy, 0.5f), sh), 0.5f), 0.0f);
+  const float fx = fmaxf(__fsub_rn(__fmul_rn(__fadd_rn((float)ox, 0.5f), sw), 0.5f), 0.0f);
+  const int y0 = min((int)fy, H - 1), x0 = min((int)fx, W - 1);
+  const int y1 = min(y0 + 1, H - 1), x1 = min(x0 + 1, W - 1);
+  const float wy1 = __fsub_rn(fy, (float)y0), wx1 = __fsub_rn(fx, (float)x0);
+  const float wy0 = __fsub_rn(1.0f, wy1), wx0 = __fsub_rn(1.0f, wx1);
+  const float v00 = normalise(__ldg(src + y0 * rs + x0), lo, hi, den);
+  const float v01 = normalise(__ldg(src + y0 * rs + x1), lo, hi, den);
+  const float v10 = normalise(__ldg(src + y1 * rs + x0), lo, hi, den);
+  const float v11 = normalise(__ldg(src + y1 * rs + x1), lo, hi, den);
+  const float top = __fadd_rn(__fmul_rn(wx0, v00), __fmul_rn(wx1, v01));
+  const float bot = __fadd_rn(__fmul_rn(wx0, v10), __fmul_rn(wx1, v11));
+  const float r = __fadd_rn(__fmul_rn(wy0, top), __fmul_rn(wy1, bot));
+  if (MODE == PDF_OUT_BF16_C1) {
+    reinterpret_cast<__nv_bfloat16*>(out)[opix] = __float2bfloat16(__fdiv_rn(__fsub_rn(r, ra.mean[0]), ra.stdv[0]));
+  } else {
+    float* o = reinterpret_cast<float*>(out) + opix * 3;
+    o[0] = __fdiv_rn(__fsub_rn(r, ra.mean[0]), ra.stdv[0]);
+    o[1] = __fdiv_rn(__fsub_rn(r, ra.mean[1]), ra.stdv[1]);
+    o[2] = __fdiv_rn(__fsub_rn(r, ra.mean[2]), ra.stdv[2]);
+  }
+}
+
+}  // namespace pdf
+
+using namespace pdf;
+
+extern "C" size_t pdf_preproc_workspace_bytes(const pdf_preproc_cfg* cfg, int batch) {
+  if (!cfg || batch <= 0) return 0;
+  size_t n = align_up(sizeof(ZoomTables), 256) + align_up(sizeof(SubjState) * (size_t)batch, 256);
+  n += (size_t)batch * count_axis2(cfg) * cfg->out_shape[0] * cfg->out_shape[1] * sizeof(float);
+  return n + 256;
+}
+
+extern "C" int pdf_resample_stats(const pdf_preproc_cfg* cfg, int batch, const float* d_raw, float* d_zoomed,
+                                  void* d_workspace, pdf_stream_t stream) {
+  if (int rc = validate(cfg, batch)) return rc;
+  PDF_REQUIRE(d_raw && d_zoomed && d_workspace, "pdf_resample_stats: null device pointer");
+  cudaStream_t s = as_stream(stream);
+  Workspace w = carve(cfg, batch, d_workspace);
+  const int X = cfg->in_shape[0], Y = cfg->in_shape[1], Z = cfg->in_shape[2];
+  const int T0 = cfg->out_shape[0], T1 = cfg->out_shape[1], T2 = cfg->out_shape[2];
+  PDF_CHECK_CUDA(cudaMemsetAsync(w.st, 0, sizeof(SubjState) * (size_t)batch, s));
+  const int tmax = max(max(T0, T1), max(T2, batch));
+  init_tables_kernel<<<ceil_div(tmax, 256), 256, 0, s>>>(w.tabs, w.st, batch, X, Y, Z, T0, T1, T2);
+  PDF_CHECK_LAUNCH();
+  const int threads = min(1024, (T2 + 31) / 32 * 32);
+  const int nrows = T0 * T1;
+  // ~2 waves of blocks over the chip for the whole batch, but at least 8 rows per block
+  int blocks_per_subject = max(1, min(nrows / 8, ceil_div(num_sms() * 12, batch)));
+  const int rows_per_block = ceil_div(nrows, blocks_per_subject);
+  blocks_per_subject = ceil_div(nrows, rows_per_block);
+  resample_kernel<<<dim3(blocks_per_subject, batch), threads, 0, s>>>(d_raw, d_zoomed, w.st, w.tabs, X, Y, Z, T0, T1, T2,
+                                                                      rows_per_block);
+  PDF_CHECK_LAUNCH();
+  return PDF_OK;
+}
+
+extern "C" int pdf_select_bounds_indices(const pdf_preproc_cfg* cfg, int batch, const float* d_zoomed, void* d_workspace,
+                                         float* d_lohi, int32_t* d_indices, int32_t* d_nslices, pdf_stream_t stream) {
+  if (int rc = validate(cfg, batch)) return rc;
+  PDF_REQUIRE(d_zoomed && d_workspace && d_lohi && d_indices && d_nslices, "pdf_select_bounds_indices: null device pointer");
+  cudaStream_t s = as_stream(stream);
+  Workspace w = carve(cfg, batch, d_workspace);
+  FinalizeArgs fa;
+  fa.lmax = 0;
+  fa.n_axes = cfg->n_axes;
+  for (int i = 0; i < 3; ++i) fa.T[i] = cfg->out_shape[i];
+  for (int a = 0; a < PDF_MAX_AXES; ++a) {
+    fa.axes[a] = a < cfg->n_axes ? cfg->axes[a] : 0;
+    fa.counts[a] = a < cfg->n_axes ? cfg->counts[a] : 0;
+    fa.lmax += fa.counts[a];
+  }
+  const size_t voxels = (size_t)cfg->out_shape[0] * cfg->out_shape[1] * cfg->out_shape[2];
+  const int hblocks = max(1, min((int)(voxels / 4 / 256 / 4) + 1, ceil_div(num_sms() * 8, batch)));
+  scan_kernel<0><<<batch, 256, 0, s>>>(w.st, fa, d_lohi, d_indices, d_nslices);
+  PDF_CHECK_LAUNCH();
+  hist_kernel<1><<<dim3(hblocks, batch), 256, 0, s>>>(d_zoomed, w.st, voxels);
+  PDF_CHECK_LAUNCH();
+  scan_kernel<1><<<batch, 256, 0, s>>>(w.st, fa, d_lohi, d_indices, d_nslices);
+  PDF_CHECK_LAUNCH();
+  hist_kernel<2><<<dim3(hblocks, batch), 256, 0, s>>>(d_zoomed, w.st, voxels);
+  PDF_CHECK_LAUNCH();
+  scan_kernel<2><<<batch, 256, 0, s>>>(w.st, fa, d_lohi, d_indices, d_nslices);
+  PDF_CHECK_LAUNCH();
+  return PDF_OK;
+}
+
+extern "C" int pdf_gather_resize_normalize(const pdf_preproc_cfg* cfg, int batch, const float* d_zoomed, void* d_workspace,
+                                              const float* d_lohi, const int32_t* d_indices, const int32_t* d_nslices,
+                                              void* d_out, int out_mode, pdf_stream_t stream) {
+  if (int rc = validate(cfg, batch)) return rc;
+  PDF_REQUIRE(d_zoomed && d_workspace && d_lohi && d_indices && d_nslices && d_out, "pdf_gather_resize_normalize: null device pointer");
+  PDF_REQUIRE(out_mode == PDF_OUT_BF16_C1 || out_mode == PDF_OUT_F32_NHWC3, "pdf_gather_resize_normalize: bad out_mode");
+  if (out_mode == PDF_OUT_BF16_C1) {
+    PDF_REQUIRE(cfg->mean[0] == cfg->mean[1] && cfg->mean[1] == cfg->mean[2] && cfg->std[0] == cfg->std[1] && cfg->std[1] == cfg->std[2],
+                "PDF_OUT_BF16_C1 needs channel-uniform mean/std");
+  }
+  cudaStream_t s = as_stream(stream);
+  Workspace w = carve(cfg, batch, d_workspace);
+  ResizeArgs ra;
+  ra.lmax = 0;
+  ra.n_axes = cfg->n_axes;
+  ra.S = cfg->input_size;
+  ra.cnt2 = count_axis2(cfg);
+  for (int i = 0; i < 3; ++i) { ra.T[i] = cfg->out_shape[i]; ra.mean[i] = cfg->mean[i]; ra.stdv[i] = cfg->std[i]; }
+  for (int a = 0; a < PDF_MAX_AXES; ++a) {
+    ra.axes[a] = a < cfg->n_axes ? cfg->axes[a] : 0;
+    ra.counts[a] = a < cfg->n_axes ? cfg->counts[a] : 0;
+    ra.lmax += ra.counts[a];
+  }
+  const int T0 = cfg->out_shape[0], T1 = cfg->out_shape[1], T2 = cfg->out_shape[2];
+  int off = 0, off2 = 0;
+  for (int a = 0; a < cfg->n_axes; ++a) {
+    if (cfg->axes[a] == 2) {
+      const int xb = max(1, min(ceil_div((long long)T0 * T1, 256 * 4), 64));
+      extract_planes_kernel<<<dim3(xb, cfg->counts[a], batch), 256, 0, s>>>(d_zoomed, d_indices, ra.lmax, off, ra.cnt2,
+                                                                            w.planes + (size_t)off2 * T0 * T1, T0, T1, T2);
+      PDF_CHECK_LAUNCH();
+      off2 += cfg->counts[a];
+    }
+    off += cfg->counts[a];
+  }
+  const dim3 grid(ceil_div((long long)ra.S * ra.S, 256), ra.lmax, batch);
+  if (out_mode == PDF_OUT_BF16_C1)
+    resize_kernel<PDF_OUT_BF16_C1><<<grid, 256, 0, s>>>(d_zoomed, w.planes, d_lohi, d_indices, d_nslices, d_out, ra);
+  else
+    resize_kernel<PDF_OUT_F32_NHWC3><<<grid, 256, 0, s>>>(d_zoomed, w.planes, d_lohi, d_indices, d_nslices, d_out, ra);
+  PDF_CHECK_LAUNCH();
+  return PDF_OK;
+}
+
+extern "C" int pdf_preprocess(const pdf_preproc_cfg* cfg, int batch, const float* d_raw, float* d_zoomed, void* d_workspace,
+                              float* d_lohi, int32_t* d_indices, int32_t* d_nslices, void* d_out, int out_mode,
+                              pdf_stream_t stream) {
+  if (int rc = pdf_resample_stats(cfg, batch, d_raw, d_zoomed, d_workspace, stream)) return rc;
+  if (int rc = pdf_select_bounds_indices(cfg, batch, d_zoomed, d_workspace, d_lohi, d_indices, d_nslices, stream)) return rc;
+  return pdf_gather_resize_normalize(cfg, batch, d_zoomed, d_workspace, d_lohi, d_indices, d_nslices, d_out, out_mode, stream);
+}
+
+extern "C" int pdf_normalize_volume(int batch, size_t voxels, const float* d_zoomed, const float* d_lohi, float* d_norm,
+                                    pdf_stream_t stream) {
+  PDF_REQUIRE(batch > 0 && voxels > 0 && d_zoomed && d_lohi && d_norm, "pdf_normalize_volume: bad arguments");
+  const int blocks = max(1, min((int)((voxels + 255) / 256), 2048));
+  normalize_kernel<<<dim3(blocks, batch), 256, 0, as_stream(stream)>>>(d_zoomed, d_lohi, d_norm, voxels);
+  PDF_CHECK_LAUNCH();
+  return PDF_OK;
+}

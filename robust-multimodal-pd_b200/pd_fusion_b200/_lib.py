@@ -1,0 +1,158 @@
+"""ctypes binding of libpdfusion_b200.so (the C ABI declared in include/pdfusion_b200.h).
+
+There is no CPU fallback: if the shared library is missing, or a compute call is made without a
+CUDA device, this module raises.  Build with `python __graft_entry__.py` (or `make -C csrc`).
+"""
+from __future__ import annotations
+
+import ctypes as C
+import os
+from pathlib import Path
+
+_HERE = Path(__file__).resolve().parent
+LIB_PATH = Path(os.environ.get("PDFUSION_B200_LIB", _HERE / "libpdfusion_b200.so"))
+
+PDF_MAX_AXES = 3
+PDF_MAX_LAYERS = 8
+PDF_MAX_MODS = 8
+
+OUT_BF16_C1 = 0
+OUT_F32_NHWC3 = 1
+
+OP_CONV, OP_MAXPOOL, OP_AVGPOOL, OP_STEM_IM2COL = 0, 1, 2, 3
+PREC_F32, PREC_BF16 = 0, 1
+
+
+class PreprocCfg(C.Structure):
+    _fields_ = [
+        ("in_shape", C.c_int32 * 3),
+        ("out_shape", C.c_int32 * 3),
+        ("n_axes", C.c_int32),
+        ("axes", C.c_int32 * PDF_MAX_AXES),
+        ("counts", C.c_int32 * PDF_MAX_AXES),
+        ("input_size", C.c_int32),
+        ("mean", C.c_float * 3),
+        ("std", C.c_float * 3),
+    ]
+
+
+class Op(C.Structure):
+    _fields_ = [
+        ("kind", C.c_int32), ("precision", C.c_int32),
+        ("n", C.c_int32), ("h", C.c_int32), ("w", C.c_int32), ("c", C.c_int32),
+        ("k", C.c_int32), ("r", C.c_int32), ("s", C.c_int32),
+        ("stride", C.c_int32), ("pad", C.c_int32),
+        ("ho", C.c_int32), ("wo", C.c_int32),
+        ("relu", C.c_int32), ("out_f32", C.c_int32),
+        ("d_in", C.c_void_p), ("d_weight", C.c_void_p), ("d_scale", C.c_void_p), ("d_bias", C.c_void_p),
+        ("d_residual", C.c_void_p), ("d_out", C.c_void_p),
+    ]
+
+
+class MilWeights(C.Structure):
+    _fields_ = [
+        ("D", C.c_int32), ("H", C.c_int32), ("A", C.c_int32), ("gated", C.c_int32),
+        ("w_inst", C.c_void_p), ("b_inst", C.c_void_p), ("w_v", C.c_void_p), ("b_v", C.c_void_p),
+        ("w_u", C.c_void_p), ("b_u", C.c_void_p), ("w_w", C.c_void_p), ("b_w", C.c_void_p),
+        ("w_cls", C.c_void_p), ("b_cls", C.c_void_p),
+        ("missing_prob", C.c_float),
+    ]
+
+
+class Mlp(C.Structure):
+    _fields_ = [
+        ("n_layers", C.c_int32),
+        ("dims", C.c_int32 * (PDF_MAX_LAYERS + 1)),
+        ("w", C.c_void_p * PDF_MAX_LAYERS),
+        ("b", C.c_void_p * PDF_MAX_LAYERS),
+        ("n_mods", C.c_int32),
+        ("mod_off", C.c_int32 * (PDF_MAX_MODS + 1)),
+    ]
+
+
+class Moe(C.Structure):
+    _fields_ = [
+        ("n_experts", C.c_int32),
+        ("expert", Mlp * PDF_MAX_MODS),
+        ("router_hidden", C.c_int32),
+        ("w_r0", C.c_void_p), ("b_r0", C.c_void_p), ("w_r1", C.c_void_p), ("b_r1", C.c_void_p),
+    ]
+
+
+# name -> (restype, argtypes); also the list tests/test_cabi.py checks against include/pdfusion_b200.h
+_P = C.c_void_p
+PROTOTYPES = {
+    "pdf_version": (C.c_int, []),
+    "pdf_last_error": (C.c_char_p, []),
+    "pdf_launch_count": (C.c_uint64, []),
+    "pdf_preproc_workspace_bytes": (C.c_size_t, [C.POINTER(PreprocCfg), C.c_int]),
+    "pdf_resample_stats": (C.c_int, [C.POINTER(PreprocCfg), C.c_int, _P, _P, _P, _P]),
+    "pdf_select_bounds_indices": (C.c_int, [C.POINTER(PreprocCfg), C.c_int, _P, _P, _P, _P, _P, _P]),
+    "pdf_gather_resize_normalize": (C.c_int, [C.POINTER(PreprocCfg), C.c_int, _P, _P, _P, _P, _P, _P, C.c_int, _P]),
+    "pdf_preprocess": (C.c_int, [C.POINTER(PreprocCfg), C.c_int, _P, _P, _P, _P, _P, _P, _P, C.c_int, _P]),
+    "pdf_normalize_volume": (C.c_int, [C.c_int, C.c_size_t, _P, _P, _P, _P]),
+    "pdf_plan_create": (C.c_int, [C.POINTER(_P), C.POINTER(Op), C.c_int]),
+    "pdf_plan_run": (C.c_int, [_P, _P]),
+    "pdf_plan_run_range": (C.c_int, [_P, C.c_int, C.c_int, _P]),
+    "pdf_plan_destroy": (None, [_P]),
+    "pdf_plan_flops": (C.c_double, [_P]),
+    "pdf_slice_mean": (C.c_int, [C.c_int, C.c_int, C.c_int, _P, _P, _P, _P]),
+    "pdf_mil_workspace_bytes": (C.c_size_t, [C.POINTER(MilWeights), C.c_int, C.c_int]),
+    "pdf_mil_forward": (C.c_int, [C.POINTER(MilWeights), C.c_int, C.c_int, _P, _P, _P, _P, _P]),
+    "pdf_moddrop_workspace_bytes": (C.c_size_t, [C.POINTER(Mlp), C.c_int]),
+    "pdf_moddrop_sweep": (C.c_int, [C.POINTER(Mlp), C.c_int, C.c_int, _P, _P, _P, _P, _P]),
+    "pdf_moe_sweep": (C.c_int, [C.POINTER(Moe), C.c_int, C.c_int, C.POINTER(_P), _P, _P, _P]),
+    "pdf_selftest_umma": (C.c_int, [C.c_int, C.c_int, C.c_int, _P, _P, _P, _P]),
+}
+
+_lib = None
+
+
+class PdfusionError(RuntimeError):
+    pass
+
+
+def load():
+    """Loads the shared library (once). Raises if it has not been built -- never falls back."""
+    global _lib
+    if _lib is not None:
+        return _lib
+    if not LIB_PATH.exists():
+        raise PdfusionError(
+            f"{LIB_PATH} not found: build the CUDA extension first (python __graft_entry__.py). "
+            "pd_fusion_b200 has no CPU fallback.")
+    lib = C.CDLL(str(LIB_PATH))
+    for name, (res, args) in PROTOTYPES.items():
+        fn = getattr(lib, name)
+        fn.restype = res
+        fn.argtypes = args
+    _lib = lib
+    return lib
+
+
+def check(rc: int, what: str = "") -> None:
+    if rc != 0:
+        msg = load().pdf_last_error().decode("utf-8", "replace")
+        raise PdfusionError(f"{what or 'libpdfusion_b200'} failed (rc={rc}): {msg}")
+
+
+def require_cuda():
+    import torch
+
+    if not torch.cuda.is_available():
+        raise PdfusionError("pd_fusion_b200 needs a CUDA device (sm_100a); there is no CPU fallback.")
+
+
+def ptr(t) -> int:
+    """device pointer of a torch tensor (or None -> NULL)."""
+    return None if t is None else t.data_ptr()
+
+
+def stream_ptr():
+    import torch
+
+    return torch.cuda.current_stream().cuda_stream
+
+
+def launch_count() -> int:
+    return int(load().pdf_launch_count())

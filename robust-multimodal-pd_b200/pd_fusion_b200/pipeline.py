@@ -1,0 +1,68 @@
+"""Volume -> embedding pipeline for a batch of subjects resident in HBM (K1 + K2 + slice mean).
+
+Replaces the serial per-subject loop of `build_resnet2d_embeddings`
+(data/openneuro_features.py:226-265) and of scripts/build_resnet2d_mil_embeddings.py:112-158:
+every subject of the batch is resampled, normalised, sliced and encoded by the same sequence of launches.
+"""
+from __future__ import annotations
+
+from dataclasses import dataclass
+from typing import Dict, Sequence
+
+import torch
+
+from . import _lib
+from .backbone import ResNetEncoder, detect_arch
+from .preprocess import VolumePreprocessor
+
+
+@dataclass
+class EmbedResult:
+    embeddings: torch.Tensor    # [B, L, D] f32 per-slice embeddings (MIL bag)
+    mean: torch.Tensor          # [B, D] f32 mean over the valid slices (non-MIL embedding)
+    indices: torch.Tensor       # [B, L] i32
+    nslices: torch.Tensor       # [B, n_axes] i32
+
+
+class EmbeddingPipeline:
+    def __init__(self, backbone_state_dict: Dict[str, torch.Tensor], in_shape: Sequence[int],
+                 target_shape: Sequence[int] = (160, 160, 160), axes: Sequence[int] = (2,), counts: Sequence[int] = (24,),
+                 input_size: int = 224, precision: str = "bf16", max_subjects: int = 8, mean=(0.5, 0.5, 0.5),
+                 std=(0.5, 0.5, 0.5), arch: str | None = None, device=None):
+        _lib.require_cuda()
+        self.lib = _lib.load()
+        self.device = torch.device(device if device is not None else f"cuda:{torch.cuda.current_device()}")
+        self.max_subjects = int(max_subjects)
+        self.precision = precision
+        if precision == "bf16" and (len(set(float(m) for m in mean)) != 1 or len(set(float(s) for s in std)) != 1):
+            raise ValueError("the bf16 path folds the three identical input channels and needs channel-uniform mean/std; "
+                             "use precision='fp32' for per-channel statistics")
+        mode = _lib.OUT_BF16_C1 if precision == "bf16" else _lib.OUT_F32_NHWC3
+        with torch.cuda.device(self.device):
+            self.pre = VolumePreprocessor(in_shape, target_shape, axes, counts, input_size, mean, std, mode,
+                                          self.max_subjects, self.device)
+            self.L = self.pre.lmax
+            self.enc = ResNetEncoder(backbone_state_dict, self.max_subjects * self.L, input_size, precision,
+                                     arch or detect_arch(backbone_state_dict), self.device)
+            self.D = self.enc.emb_dim
+            self.mean_out = torch.empty((self.max_subjects, self.D), dtype=torch.float32, device=self.device)
+            self.nvalid = torch.empty((self.max_subjects,), dtype=torch.int32, device=self.device)
+
+    def embed(self, raw: torch.Tensor) -> EmbedResult:
+        """raw [B<=max_subjects, X, Y, Z] f32 on the device. Enqueues everything on the current stream; results
+        live in reused buffers (copy them out before the next call)."""
+        B = int(raw.shape[0])
+        if B < self.max_subjects:   # the encoder plan is built for max_subjects*L images: clear the unused tail
+            self.enc.input[B * self.L:].zero_()
+        res = self.pre.run(raw, net_input=self.enc.input.view(self.pre.net_input.shape))
+        emb = self.enc.forward(None).view(self.max_subjects, self.L, self.D)
+        self.nvalid[:B].copy_(res.nslices.sum(dim=1))
+        _lib.check(self.lib.pdf_slice_mean(B, self.L, self.D, emb.data_ptr(), self.nvalid.data_ptr(), self.mean_out.data_ptr(),
+                                           _lib.stream_ptr()), "pdf_slice_mean")
+        return EmbedResult(emb[:B], self.mean_out[:B], res.indices, res.nslices)
+
+    def algorithmic_bytes_per_subject(self) -> int:
+        return self.pre.algorithmic_bytes()
+
+    def algorithmic_flops_per_subject(self) -> float:
+        return self.enc.algorithmic_flops() / self.max_subjects

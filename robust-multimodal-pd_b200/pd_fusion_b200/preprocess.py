@@ -1,0 +1,126 @@
+"""Host side of K1: batched volume -> network-input preprocessing on the GPU.
+
+Mirrors, for a whole batch of subjects resident in HBM, the reference's per-subject CPU sequence
+`_load_volume` -> `_normalize_volume_for_resnet` -> `_select_slices` -> F.interpolate/normalise
+(data/openneuro_features.py:22-32, 121-151, 250-255).  All arithmetic runs in
+libpdfusion_b200.so; this class only owns the device buffers.
+"""
+from __future__ import annotations
+
+import ctypes as C
+from dataclasses import dataclass
+from typing import Sequence
+
+import torch
+
+from . import _lib
+
+
+@dataclass
+class PreprocResult:
+    net_input: torch.Tensor   # [B, L, S, S] bf16 or [B, L, S, S, 3] f32
+    zoomed: torch.Tensor      # [B, T0, T1, T2] f32 (resampled, un-normalised)
+    lohi: torch.Tensor        # [B, 4] f32: lo, hi, denominator, has_positive
+    indices: torch.Tensor     # [B, L] i32 (-1 in unused slots)
+    nslices: torch.Tensor     # [B, n_axes] i32
+
+
+class VolumePreprocessor:
+    def __init__(self, in_shape: Sequence[int], target_shape: Sequence[int] = (160, 160, 160),
+                 axes: Sequence[int] = (2,), counts: Sequence[int] = (24,), input_size: int = 224,
+                 mean=(0.5, 0.5, 0.5), std=(0.5, 0.5, 0.5), out_mode: int = _lib.OUT_BF16_C1,
+                 max_batch: int = 1, device=None):
+        _lib.require_cuda()
+        self.lib = _lib.load()
+        if len(axes) != len(counts) or not 1 <= len(axes) <= _lib.PDF_MAX_AXES:
+            raise ValueError("slice-counts must match length of slice-axes")
+        self.device = torch.device(device if device is not None else f"cuda:{torch.cuda.current_device()}")
+        self.in_shape = tuple(int(v) for v in in_shape)
+        self.target_shape = tuple(int(v) for v in target_shape)
+        self.axes, self.counts = [int(a) for a in axes], [int(c) for c in counts]
+        self.lmax = sum(self.counts)
+        self.input_size = int(input_size)
+        self.out_mode = out_mode
+        self.max_batch = int(max_batch)
+        cfg = _lib.PreprocCfg()
+        cfg.in_shape[:] = self.in_shape
+        cfg.out_shape[:] = self.target_shape
+        cfg.n_axes = len(self.axes)
+        for i in range(_lib.PDF_MAX_AXES):
+            cfg.axes[i] = self.axes[i] if i < len(self.axes) else 0
+            cfg.counts[i] = self.counts[i] if i < len(self.counts) else 0
+        cfg.input_size = self.input_size
+        cfg.mean[:] = [float(m) for m in mean]
+        cfg.std[:] = [float(s) for s in std]
+        self.cfg = cfg
+        ws = self.lib.pdf_preproc_workspace_bytes(C.byref(cfg), self.max_batch)
+        if ws == 0:
+            raise _lib.PdfusionError("pdf_preproc_workspace_bytes returned 0 (bad configuration)")
+        B, S = self.max_batch, self.input_size
+        with torch.cuda.device(self.device):
+            self.workspace = torch.empty(ws, dtype=torch.uint8, device=self.device)
+            self.zoomed = torch.empty((B,) + self.target_shape, dtype=torch.float32, device=self.device)
+            self.lohi = torch.empty((B, 4), dtype=torch.float32, device=self.device)
+            self.indices = torch.empty((B, self.lmax), dtype=torch.int32, device=self.device)
+            self.nslices = torch.empty((B, len(self.axes)), dtype=torch.int32, device=self.device)
+            if out_mode == _lib.OUT_BF16_C1:
+                self.net_input = torch.empty((B, self.lmax, S, S), dtype=torch.bfloat16, device=self.device)
+            else:
+                self.net_input = torch.empty((B, self.lmax, S, S, 3), dtype=torch.float32, device=self.device)
+
+    def _check_raw(self, raw: torch.Tensor) -> int:
+        if not (raw.is_cuda and raw.dtype == torch.float32 and raw.is_contiguous()):
+            raise ValueError("raw volumes must be a contiguous float32 CUDA tensor [B, X, Y, Z]")
+        if tuple(raw.shape[1:]) != self.in_shape or raw.shape[0] > self.max_batch:
+            raise ValueError(f"raw volumes {tuple(raw.shape)} do not match in_shape {self.in_shape} / max_batch {self.max_batch}")
+        return int(raw.shape[0])
+
+    def run(self, raw: torch.Tensor, net_input: torch.Tensor | None = None) -> PreprocResult:
+        """Enqueues resample+stats, select, gather/resize on the current stream (no sync)."""
+        B = self._check_raw(raw)
+        out = self.net_input if net_input is None else net_input
+        rc = self.lib.pdf_preprocess(C.byref(self.cfg), B, raw.data_ptr(), self.zoomed.data_ptr(), self.workspace.data_ptr(),
+                                     self.lohi.data_ptr(), self.indices.data_ptr(), self.nslices.data_ptr(), out.data_ptr(),
+                                     self.out_mode, _lib.stream_ptr())
+        _lib.check(rc, "pdf_preprocess")
+        return PreprocResult(out[:B], self.zoomed[:B], self.lohi[:B], self.indices[:B], self.nslices[:B])
+
+    # stage-level entry points (parity tests, per-kernel timing)
+    def resample(self, raw: torch.Tensor) -> torch.Tensor:
+        B = self._check_raw(raw)
+        _lib.check(self.lib.pdf_resample_stats(C.byref(self.cfg), B, raw.data_ptr(), self.zoomed.data_ptr(),
+                                               self.workspace.data_ptr(), _lib.stream_ptr()), "pdf_resample_stats")
+        return self.zoomed[:B]
+
+    def select(self, B: int):
+        _lib.check(self.lib.pdf_select_bounds_indices(C.byref(self.cfg), B, self.zoomed.data_ptr(), self.workspace.data_ptr(),
+                                                      self.lohi.data_ptr(), self.indices.data_ptr(), self.nslices.data_ptr(),
+                                                      _lib.stream_ptr()), "pdf_select_bounds_indices")
+        return self.lohi[:B], self.indices[:B], self.nslices[:B]
+
+    def gather(self, B: int) -> torch.Tensor:
+        _lib.check(self.lib.pdf_gather_resize_normalize(C.byref(self.cfg), B, self.zoomed.data_ptr(), self.workspace.data_ptr(),
+                                                        self.lohi.data_ptr(), self.indices.data_ptr(), self.nslices.data_ptr(),
+                                                        self.net_input.data_ptr(), self.out_mode, _lib.stream_ptr()),
+                   "pdf_gather_resize_normalize")
+        return self.net_input[:B]
+
+    def normalized_volume(self, B: int) -> torch.Tensor:
+        """`_normalize_volume_for_resnet` output itself (parity helper)."""
+        out = torch.empty_like(self.zoomed[:B])
+        vox = self.target_shape[0] * self.target_shape[1] * self.target_shape[2]
+        _lib.check(self.lib.pdf_normalize_volume(B, vox, self.zoomed.data_ptr(), self.lohi.data_ptr(), out.data_ptr(),
+                                                 _lib.stream_ptr()), "pdf_normalize_volume")
+        return out
+
+    def algorithmic_bytes(self) -> int:
+        """4XYZ + 2*4*T^3 + 4*L*T^2 + b_out*L*I^2 per subject."""
+        X, Y, Z = self.in_shape
+        T0, T1, T2 = self.target_shape
+        plane = 0
+        for a, c in zip(self.axes, self.counts):
+            dims = [T0, T1, T2]
+            dims.pop(a)
+            plane += 4 * c * dims[0] * dims[1]
+        b_out = 2 if self.out_mode == _lib.OUT_BF16_C1 else 12
+        return 4 * X * Y * Z + 8 * T0 * T1 * T2 + plane + b_out * self.lmax * self.input_size ** 2

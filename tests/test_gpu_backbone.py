@@ -1,0 +1,104 @@
+"""K2 parity on the GPU: tcgen05 building block, FP32 and BF16 ResNet encoders vs the oracle / golden."""
+import json
+
+import numpy as np
+import pytest
+
+torch = pytest.importorskip("torch")
+pytestmark = pytest.mark.gpu
+
+from oracle import oracle as O
+from pd_fusion_b200 import _lib
+from pd_fusion_b200.backbone import ResNet2D, ResNetEncoder
+from pd_fusion_b200.synthetic import synthetic_volume
+
+
+def _sd(arch):
+    torch.manual_seed(1234)
+    return {k: v for k, v in ResNet2D(arch).state_dict().items() if not k.startswith("fc.")}
+
+
+@pytest.mark.parametrize("M,N,K", [(128, 64, 64), (300, 128, 192), (1000, 256, 576), (77, 512, 128)])
+def test_umma_selftest(M, N, K):
+    """TMA (2D, 128B swizzle) -> tcgen05.mma (TMEM accumulator) -> tcgen05.ld against an f32 matmul of the same bf16 data."""
+    lib = _lib.load()
+    g = torch.Generator(device="cpu").manual_seed(M * 7 + N)
+    a = torch.randn(M, K, generator=g).to(torch.bfloat16).cuda()
+    b = torch.randn(N, K, generator=g).to(torch.bfloat16).cuda()
+    c = torch.full((M, N), float("nan"), dtype=torch.float32, device="cuda")
+    _lib.check(lib.pdf_selftest_umma(M, N, K, a.data_ptr(), b.data_ptr(), c.data_ptr(), _lib.stream_ptr()))
+    torch.cuda.synchronize()
+    ref = a.float().cpu().double() @ b.float().cpu().double().T
+    err = (c.cpu().double() - ref).abs().max().item()
+    assert err < 1e-3 * max(1.0, ref.abs().max().item()), err
+
+
+def _inputs(case_spec):
+    sp = case_spec
+    raw = synthetic_volume(sp["index"], tuple(sp["shape"]), bad_fraction=1e-4 if sp["shape"][0] < 100 else 1e-5)
+    _, idx, sl = O.preprocess_subject(raw, tuple(sp["target"]), sp["axes"], sp["counts"])
+    return O.slices_to_input(sl, sp["input_size"])        # [L,3,S,S] f32
+
+
+@pytest.mark.parametrize("case", ["r18_small", "r50_small", "r18_c2"])
+def test_fp32_encoder_vs_reference(golden, case):
+    g = golden("embed")
+    sp = json.loads(str(g[f"{case}/spec"]))
+    x = _inputs(sp)
+    enc = ResNetEncoder(_sd(sp["arch"]), x.shape[0], sp["input_size"], precision="fp32")
+    out = enc.forward(torch.from_numpy(np.ascontiguousarray(x.transpose(0, 2, 3, 1))).cuda())
+    torch.cuda.synchronize()
+    emb, ref = out.cpu().numpy(), g[f"{case}/emb"]
+    rel = np.linalg.norm(emb - ref) / np.linalg.norm(ref)
+    assert rel < 1e-5, rel                                  # north_star: fp32 path within 1e-5
+
+
+@pytest.mark.parametrize("case", ["r18_small", "r50_small", "r18_c2", "r50_c3"])
+def test_bf16_encoder_vs_reference(golden, case):
+    g = golden("embed")
+    sp = json.loads(str(g[f"{case}/spec"]))
+    x = _inputs(sp)
+    enc = ResNetEncoder(_sd(sp["arch"]), x.shape[0], sp["input_size"], precision="bf16")
+    out = enc.forward(torch.from_numpy(np.ascontiguousarray(x[:, 0])).to(torch.bfloat16).cuda())
+    torch.cuda.synchronize()
+    emb, ref = out.cpu().numpy(), g[f"{case}/emb"]
+    rel = np.linalg.norm(emb - ref, axis=1) / np.linalg.norm(ref, axis=1)
+    assert rel.max() < 1e-2, rel                            # north_star: bf16 path within 1e-2 (norm-wise, per slice)
+
+
+def test_bf16_layers_vs_fp32_layers():
+    """Layer-by-layer: every bf16 tcgen05 conv (im2col TMA, strides, padding, residual epilogue) against the
+    FP32 CUDA-core conv of the same layer fed with the SAME (bf16-rounded) input."""
+    lib = _lib.load()
+    torch.manual_seed(0)
+    cases = [  # n, h, c, k, r, stride, pad, residual
+        (3, 14, 64, 64, 3, 1, 1, True), (2, 16, 64, 128, 3, 2, 1, False), (2, 15, 128, 256, 1, 2, 0, False),
+        (5, 8, 256, 64, 1, 1, 0, True), (1, 7, 512, 512, 3, 1, 1, True), (4, 9, 128, 128, 3, 2, 1, False),
+    ]
+    import ctypes as C
+    for (n, h, c, k, r, stride, pad, res) in cases:
+        ho = (h + 2 * pad - r) // stride + 1
+        x = (torch.randn(n, h, h, c) * 0.5).to(torch.bfloat16)
+        w = (torch.randn(k, r, r, c) / (r * r * c) ** 0.5).to(torch.bfloat16)
+        bias = torch.randn(k)
+        resid = (torch.randn(n, ho, ho, k) * 0.5).to(torch.bfloat16) if res else None
+        xd, wd, bd = x.cuda(), w.cuda(), bias.cuda()
+        rd = resid.cuda() if res else None
+        out16 = torch.empty(n, ho, ho, k, dtype=torch.bfloat16, device="cuda")
+        out32 = torch.empty(n, ho, ho, k, dtype=torch.float32, device="cuda")
+        x32, w32 = xd.float().contiguous(), wd.float().permute(1, 2, 3, 0).contiguous()
+        r32 = rd.float().contiguous() if res else None
+        ops = (_lib.Op * 2)()
+        for o, (prec, xi, wi, ri, oo) in zip(ops, [(_lib.PREC_BF16, xd, wd, rd, out16), (_lib.PREC_F32, x32, w32, r32, out32)]):
+            o.kind, o.precision = _lib.OP_CONV, prec
+            o.n, o.h, o.w, o.c, o.k, o.r, o.s, o.stride, o.pad, o.ho, o.wo, o.relu = n, h, h, c, k, r, r, stride, pad, ho, ho, 1
+            o.d_in, o.d_weight, o.d_bias, o.d_out = xi.data_ptr(), wi.data_ptr(), bd.data_ptr(), oo.data_ptr()
+            o.d_residual = ri.data_ptr() if res else None
+        plan = C.c_void_p()
+        _lib.check(lib.pdf_plan_create(C.byref(plan), ops, 2))
+        _lib.check(lib.pdf_plan_run(plan, _lib.stream_ptr()))
+        torch.cuda.synchronize()
+        lib.pdf_plan_destroy(plan)
+        a, b = out16.float().cpu(), out32.cpu()
+        err = (a - b).abs().max().item()
+        assert err < 2e-2 * max(1.0, b.abs().max().item()), ((n, h, c, k, r, stride, pad, res), err)

@@ -1,0 +1,101 @@
+"""K1 parity on the GPU: CUDA preprocessing (through the C ABI) vs the CPU oracle and the golden fixtures.
+Integer outputs (slice indices, counts) and the resampled/normalised volumes are bit-exact."""
+import json
+
+import numpy as np
+import pytest
+
+torch = pytest.importorskip("torch")
+pytestmark = pytest.mark.gpu
+
+from oracle import oracle as O
+from pd_fusion_b200 import _lib
+from pd_fusion_b200.preprocess import VolumePreprocessor
+from pd_fusion_b200.synthetic import synthetic_volume
+
+
+def _run(raws, target, axes, counts, size, mode):
+    pre = VolumePreprocessor(raws[0].shape, target, axes, counts, size, out_mode=mode, max_batch=len(raws))
+    raw = torch.from_numpy(np.stack(raws)).cuda()
+    res = pre.run(raw)
+    norm = pre.normalized_volume(len(raws))
+    torch.cuda.synchronize()
+    return pre, res, norm
+
+
+CASES = ["small_a", "small_b", "small_c", "full_c2", "full_c5"]
+
+
+@pytest.mark.parametrize("case", CASES)
+def test_preproc_vs_golden_and_oracle(golden, case):
+    g = golden("preproc")
+    sp = json.loads(str(g[f"{case}/spec"]))
+    raw = synthetic_volume(sp["index"], tuple(sp["shape"]), bad_fraction=1e-4 if sp["shape"][0] < 100 else 1e-5)
+    size = 56 if sp["target"][0] <= 64 else 224
+    pre, res, norm = _run([raw], sp["target"], sp["axes"], sp["counts"], size, _lib.OUT_F32_NHWC3)
+    zoomed = res.zoomed[0].cpu().numpy()
+    ref_zoom = O.load_volume(raw, tuple(sp["target"]))
+    assert np.array_equal(zoomed.view(np.uint32), ref_zoom.view(np.uint32)), "resample not bit-exact"
+    lo, hi = O.percentile_bounds(ref_zoom)
+    lohi = res.lohi[0].cpu().numpy()
+    assert lohi[0] == lo == g[f"{case}/lo"] and lohi[1] == hi == g[f"{case}/hi"]
+    ref_norm = O.normalize_volume_for_resnet(ref_zoom)
+    assert np.array_equal(norm[0].cpu().numpy().view(np.uint32), ref_norm.view(np.uint32)), "normalised volume not bit-exact"
+    idx = res.indices[0].cpu().numpy()
+    ns = res.nslices[0].cpu().numpy()
+    off = 0
+    sl = []
+    for a, (axis, c) in enumerate(zip(sp["axes"], sp["counts"])):
+        want = g[f"{case}/idx{axis}"]
+        assert ns[a] == len(want)
+        assert np.array_equal(idx[off:off + len(want)], want), f"axis {axis} indices differ"
+        assert np.all(idx[off + len(want):off + c] == -1)
+        sl.append((off, len(want), O.select_slices(ref_norm, axis, c)))
+        off += c
+    x = res.net_input[0].cpu().numpy()            # [L, S, S, 3]
+    for off, n, s in sl:
+        ref = O.slices_to_input(s, size).transpose(0, 2, 3, 1)
+        np.testing.assert_allclose(x[off:off + n], ref, atol=1e-5, rtol=0)
+    # reference-generated sample of the network input (first two slices)
+    np.testing.assert_allclose(x[:2].transpose(0, 3, 1, 2)[:, :, ::4, ::4], g[f"{case}/input_sample"], atol=1e-5, rtol=0)
+
+
+@pytest.mark.parametrize("case", ["zeros", "negative"])
+def test_preproc_degenerate(golden, case):
+    g = golden("preproc")
+    raw = np.zeros((20, 20, 20), np.float32) if case == "zeros" else -synthetic_volume(5, (20, 22, 24), 0.0) - 1.0
+    pre, res, norm = _run([raw], (16, 16, 16), [2], [4], 32, _lib.OUT_F32_NHWC3)
+    lohi = res.lohi[0].cpu().numpy()
+    assert lohi[0] == g[f"{case}/lo"] and lohi[1] == g[f"{case}/hi"] and lohi[3] == 0.0
+    ref_norm = O.normalize_volume_for_resnet(O.load_volume(raw, (16, 16, 16)))
+    assert np.array_equal(norm[0].cpu().numpy().view(np.uint32), ref_norm.view(np.uint32))
+    want = g[f"{case}/idx2"]
+    assert np.array_equal(res.indices[0].cpu().numpy()[:len(want)], want)
+
+
+def test_preproc_batch_and_bf16_output():
+    """Several subjects in one launch; bf16 one-channel output equals the rounded f32 output."""
+    shape, target = (40, 36, 44), (32, 32, 32)
+    raws = [synthetic_volume(20 + i, shape, 1e-4) for i in range(5)]
+    _, res32, _ = _run(raws, target, [0, 2], [5, 3], 48, _lib.OUT_F32_NHWC3)
+    _, res16, _ = _run(raws, target, [0, 2], [5, 3], 48, _lib.OUT_BF16_C1)
+    for b, raw in enumerate(raws):
+        vol, idx, sl = O.preprocess_subject(raw, target, [0, 2], [5, 3])
+        got = res32.indices[b].cpu().numpy()
+        assert np.array_equal(got[:len(idx[0])], idx[0]) and np.array_equal(got[5:5 + len(idx[1])], idx[1])
+    a = res32.net_input[..., 0].to(torch.bfloat16)
+    assert torch.equal(a, res16.net_input)
+
+
+def test_resample_property_full_size():
+    """Size-independent properties at BASELINE's full size: constant volumes stay constant, output is
+    bounded by the input range, NaN/Inf never survive."""
+    raw = np.full((256, 256, 176), 3.25, np.float32)
+    raw[5, 7, 9] = np.nan
+    raw[100, 100, 100] = np.inf
+    pre = VolumePreprocessor(raw.shape, (160, 160, 160), [2], [24], 224, max_batch=1)
+    z = pre.resample(torch.from_numpy(raw[None]).cuda())
+    torch.cuda.synchronize()
+    z = z.cpu().numpy()
+    assert np.isfinite(z).all() and z.max() <= 3.25 and z.min() >= 0.0
+    assert (z == 3.25).mean() > 0.99

@@ -1,0 +1,271 @@
+#!/usr/bin/env python
+"""bench.py -- MRI subjects/s of the imaging-embedding hot path on B200 (BASELINE.json metric).
+
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--workload c2|c3] [--subjects B] [--impl b200|reference]
+
+A "step" = one pass of the hot path over one batch of B synthetic subjects per GPU:
+raw T1 volumes f32[256,256,176] resident in HBM -> resample 160^3 -> p1/p99 normalise -> slice select ->
+224x224 network input -> ResNet2D (bf16 tcgen05) -> per-slice embeddings (+ slice mean) [-> all-gather of the
+embedding table when N > 1].  Prints ONE JSON line (rank 0).
+
+  value        device-resident throughput (inputs already in HBM), CUDA-event timed, max over ranks
+  e2e          same metric through the public host API (pinned host volumes -> H2D -> hot path -> D2H embeddings)
+  roofline     the dominant kernel family (tcgen05 implicit-GEMM convs): algorithmic FLOPs / CUDA-event time
+  cpu_baseline the oracle port of the reference's CPU path on a bounded sample (rank 0, N = 1 only)
+
+`--impl reference` times the reference's own CPU implementation of the path (oracle port; /root/reference does
+not exist on the GPU box and the reference is Python, so there is nothing to compile into oracle/_ref).
+"""
+from __future__ import annotations
+
+import argparse
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+from pathlib import Path
+
+ROOT = Path(__file__).resolve().parent
+for p in (ROOT, ROOT / "robust-multimodal-pd_b200"):
+    if str(p) not in sys.path:
+        sys.path.insert(0, str(p))
+
+import numpy as np  # noqa: E402
+
+WORKLOADS = {
+    # configs/openneuro_ds001907_resnet2d.yaml + data_openneuro_ds001907_resnet2d.yaml (BASELINE configs[1])
+    "c2": dict(arch="resnet18", axes=[2], counts=[24], batch_size=32, name="configs/openneuro_ds001907_resnet2d.yaml"),
+    # configs/openneuro_ds001907_resnet2d_mil.yaml (BASELINE configs[2])
+    "c3": dict(arch="resnet50", axes=[2], counts=[48], batch_size=16, name="configs/openneuro_ds001907_resnet2d_mil.yaml"),
+}
+IN_SHAPE, TARGET, INPUT_SIZE = (256, 256, 176), (160, 160, 160), 224
+METRIC, UNIT = "mri_subjects_per_sec_resnet2d_embed", "subjects/s"
+
+
+def measured_peaks():
+    p = ROOT / "MEASURED_PEAKS.json"
+    if p.exists():
+        d = json.loads(p.read_text())
+        return dict(hbm=float(d["hbm_gbs"]), tf=float(d["bf16_tflops"]), tf_sustained=float(d.get("bf16_tflops_sustained", d["bf16_tflops"])),
+                    src="measured")
+    return dict(hbm=6650.0, tf=1590.0, tf_sustained=1400.0, src="fallback")
+
+
+class ClockSampler:
+    """nvidia-smi clocks / throttle reasons sampled DURING the timed region."""
+    Q = "clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown," \
+        "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap"
+
+    def __init__(self, index: int):
+        self.index, self.rows, self._stop, self._t = index, [], threading.Event(), None
+
+    def _loop(self):
+        while not self._stop.is_set():
+            try:
+                out = subprocess.run(["nvidia-smi", "-i", str(self.index), f"--query-gpu={self.Q}", "--format=csv,noheader,nounits"],
+                                     capture_output=True, text=True, timeout=5).stdout.strip()
+                if out:
+                    self.rows.append([c.strip() for c in out.splitlines()[0].split(",")])
+            except Exception:
+                pass
+            self._stop.wait(0.2)
+
+    def __enter__(self):
+        self._t = threading.Thread(target=self._loop, daemon=True)
+        self._t.start()
+        return self
+
+    def __exit__(self, *a):
+        self._stop.set()
+        self._t.join(timeout=6)
+
+    def summary(self):
+        sm, mx, reasons = [], [], set()
+        for r in self.rows:
+            try:
+                sm.append(float(r[0])); mx.append(float(r[1]))
+            except Exception:
+                continue
+            for name, v in zip(["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"], r[3:7]):
+                if v.lower().startswith("active"):
+                    reasons.add(name)
+        return {"sm_mhz": float(np.median(sm)) if sm else None, "sm_max_mhz": max(mx) if mx else None,
+                "reasons": sorted(reasons), "samples": len(sm)}
+
+
+def host_pool(n: int):
+    from pd_fusion_b200.synthetic import synthetic_volume
+    return [synthetic_volume(i, IN_SHAPE) for i in range(n)]
+
+
+def cpu_reference_rate(wl, n_subjects: int, pool):
+    """The reference's CPU path (oracle port) on `n_subjects` subjects with every host thread."""
+    import torch
+    from oracle import oracle as O
+    from pd_fusion_b200.backbone import ResNet2D
+    cores = os.cpu_count() or 1
+    torch.set_num_threads(cores)
+    torch.manual_seed(1234)
+    sd = {k: v for k, v in ResNet2D(wl["arch"]).state_dict().items() if not k.startswith("fc.")}
+    t0 = time.perf_counter()
+    for i in range(n_subjects):
+        O.embed_subject(pool[i % len(pool)], sd, wl["arch"], TARGET, wl["axes"], wl["counts"], INPUT_SIZE, wl["batch_size"])
+    dt = time.perf_counter() - t0
+    return n_subjects / dt, cores, dt
+
+
+def run_reference(args, wl):
+    rank = int(os.environ.get("RANK", 0))
+    if rank != 0:
+        return
+    per_step = 1
+    pool = host_pool(2)
+    for _ in range(args.warmup):
+        cpu_reference_rate(wl, 1, pool)
+    t0 = time.perf_counter()
+    rate, cores, _ = cpu_reference_rate(wl, per_step * args.steps, pool)
+    dt = time.perf_counter() - t0
+    line = {"impl": "reference", "metric": METRIC, "value": rate, "unit": UNIT, "n_gpus": args.gpus, "steps": args.steps,
+            "warmup": args.warmup, "ms_per_step": 1e3 * dt / args.steps, "higher_is_better": True, "scaling": "weak",
+            "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+            "config": {"workload": wl["name"], "backbone": wl["arch"], "slices": sum(wl["counts"]), "subjects_per_step": per_step,
+                       "volume": list(IN_SHAPE), "note": "reference CPU path (oracle port of the Python reference), all host threads"},
+            "cpu_baseline": {"value": rate, "unit": UNIT, "cores": cores, "kind": "port",
+                             "sample": f"{per_step * args.steps} subjects, full {wl['arch']} path"},
+            "e2e": {"value": rate, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}, "gpu_launches": 0}
+    print(json.dumps(line), flush=True)
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=10)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--workload", default="c2", choices=sorted(WORKLOADS))
+    ap.add_argument("--subjects", type=int, default=32, help="subjects per step per GPU")
+    ap.add_argument("--pool", type=int, default=4, help="distinct synthetic volumes cycled by subject index")
+    ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
+    ap.add_argument("--cpu-subjects", type=int, default=8, help="bounded CPU-baseline sample (subjects)")
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    args = ap.parse_args()
+    wl = WORKLOADS[args.workload]
+    if args.impl == "reference":
+        return run_reference(args, wl)
+
+    import torch
+    from pd_fusion_b200 import _lib
+    from pd_fusion_b200.backbone import ResNet2D
+    from pd_fusion_b200.parallel import all_gather_rows, barrier, init_distributed
+    from pd_fusion_b200.pipeline import EmbeddingPipeline
+
+    rank, local_rank, ws = init_distributed()
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py needs a CUDA device: the product path has no CPU fallback")
+    torch.cuda.set_device(local_rank)
+    dev = torch.device("cuda", local_rank)
+    B, L = args.subjects, sum(wl["counts"])
+    peaks = measured_peaks()
+
+    torch.manual_seed(1234)
+    sd = {k: v for k, v in ResNet2D(wl["arch"]).state_dict().items() if not k.startswith("fc.")}
+    pipe = EmbeddingPipeline(sd, IN_SHAPE, TARGET, wl["axes"], wl["counts"], INPUT_SIZE, precision="bf16", max_subjects=B, device=dev)
+    D = pipe.D
+
+    pool = host_pool(args.pool)
+    pinned = torch.empty((B,) + IN_SHAPE, dtype=torch.float32).pin_memory()
+    for i in range(B):
+        pinned[i].copy_(torch.from_numpy(pool[(rank * B + i) % len(pool)]))
+    raw = pinned.to(dev, non_blocking=True)
+    table = torch.empty((B, L, D) if args.workload == "c3" else (B, D), dtype=torch.float32, device=dev)
+    host_out = torch.empty(table.shape, dtype=torch.float32).pin_memory()
+    torch.cuda.synchronize()
+
+    def step_device():
+        res = pipe.embed(raw)
+        table.copy_(res.embeddings if args.workload == "c3" else res.mean)
+        return all_gather_rows(table, B * ws) if ws > 1 else table
+
+    def step_e2e():
+        d = pinned.to(dev, non_blocking=True)           # H2D of this step's volumes from pinned host memory
+        res = pipe.embed(d)
+        src = res.embeddings if args.workload == "c3" else res.mean
+        if ws > 1:
+            src = all_gather_rows(src.contiguous(), B * ws)[rank * B:(rank + 1) * B]
+        host_out.copy_(src, non_blocking=True)          # D2H of the step's result
+        torch.cuda.current_stream().synchronize()
+
+    def timed(fn, steps):
+        barrier(); torch.cuda.synchronize()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        for _ in range(steps):
+            fn()
+        e1.record()
+        torch.cuda.synchronize(); barrier()
+        ms = torch.tensor([e0.elapsed_time(e1)], device=dev)
+        if ws > 1:
+            torch.distributed.all_reduce(ms, op=torch.distributed.ReduceOp.MAX)
+        return float(ms.item())
+
+    for _ in range(max(args.warmup, 3)):
+        step_device()
+    torch.cuda.synchronize()
+    launches0 = _lib.launch_count()
+    with ClockSampler(local_rank) as clk:
+        ms = timed(step_device, args.steps)
+    launches = _lib.launch_count() - launches0
+    value = ws * B * args.steps / (ms / 1e3)
+
+    # --- per-kernel-family device time (same buffers, same launches): K2 conv stack and K1 preprocessing
+    def enc_only():
+        pipe.enc.forward(None)
+
+    def pre_only():
+        pipe.pre.run(raw, net_input=pipe.enc.input.view(pipe.pre.net_input.shape))
+
+    for _ in range(2):
+        enc_only(); pre_only()
+    ms_enc = timed(enc_only, args.steps) / args.steps
+    ms_pre = timed(pre_only, args.steps) / args.steps
+    flops = pipe.enc.algorithmic_flops()
+    tf = flops / (ms_enc / 1e3) / 1e12
+    gbs = pipe.algorithmic_bytes_per_subject() * B / (ms_pre / 1e3) / 1e9
+
+    for _ in range(2):
+        step_e2e()
+    ms_e2e = timed(step_e2e, args.steps)
+    e2e = ws * B * args.steps / (ms_e2e / 1e3)
+
+    line = {
+        "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": ws, "steps": args.steps, "warmup": max(args.warmup, 3),
+        "ms_per_step": ms / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+        "dtype": "bf16", "data": "synthetic",
+        "config": {"workload": wl["name"], "backbone": wl["arch"], "slices": L, "subjects_per_step_per_gpu": B,
+                   "volume": list(IN_SHAPE), "target": list(TARGET), "input_size": INPUT_SIZE, "volume_pool": args.pool,
+                   "l2": "inputs larger than L2 (%.1f GB of volumes per step)" % (B * 4 * np.prod(IN_SHAPE) / 1e9),
+                   "parallelism": f"subjects sharded x{ws}, all-gather of the embedding table" if ws > 1 else "1 GPU"},
+        "clocks": clk.summary(),
+        "e2e": {"value": e2e, "unit": UNIT, "h2d_bytes_per_step": int(pinned.numel() * 4), "d2h_bytes_per_step": int(host_out.numel() * 4),
+                "ms_per_step": ms_e2e / args.steps},
+        "gpu_launches": int(launches),
+        "roofline": {"bound": "tensor", "kernel": "conv_tc_kernel (tcgen05 implicit-GEMM conv stack, all launches of one step)",
+                     "achieved": tf, "peak": peaks["tf"], "unit": "TFLOP/s", "frac": tf / peaks["tf"], "traffic": None,
+                     "peak_source": peaks["src"] + " burst bf16", "ms": ms_enc, "flops_per_step": flops},
+        "roofline_preproc": {"bound": "hbm", "kernel": "K1 resample/select/gather (all launches of one step)", "achieved": gbs,
+                             "peak": peaks["hbm"], "unit": "GB/s", "frac": gbs / peaks["hbm"], "ms": ms_pre,
+                             "bytes_per_subject": pipe.algorithmic_bytes_per_subject(), "peak_source": peaks["src"]},
+    }
+    if rank == 0 and ws == 1 and not args.no_cpu_baseline:
+        rate, cores, dt = cpu_reference_rate(wl, args.cpu_subjects, pool)
+        line["cpu_baseline"] = {"value": rate, "unit": UNIT, "cores": cores, "kind": "port",
+                                "sample": f"{args.cpu_subjects} subjects of the same workload in {dt:.1f} s (oracle port, torch fp32, all threads)"}
+    if rank == 0:
+        print(json.dumps(line), flush=True)
+    if ws > 1:
+        torch.distributed.destroy_process_group()
+
+
+if __name__ == "__main__":
+    main()

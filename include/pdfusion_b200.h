@@ -105,6 +105,7 @@ int pdf_normalize_volume(int batch, size_t voxels, const float* d_zoomed, const 
 #define PDF_OP_MAXPOOL 1     /* 3x3 stride 2 pad 1 */
 #define PDF_OP_AVGPOOL 2     /* global average over H*W -> [N, C] f32 */
 #define PDF_OP_STEM_IM2COL 3 /* [N,H,W] bf16 one-channel image -> [N*Ho*Wo, kpad] bf16 patch matrix (7x7 s2 p3) */
+#define PDF_OP_STEM_FUSED 4  /* [N,H,W] bf16 image -> conv 7x7 s2 p3 (64 ch) + bias + ReLU + maxpool 3x3 s2 p1 -> [N,ho,wo,64] bf16, one kernel */
 
 #define PDF_PREC_F32 0  /* CUDA-core FFMA path, 1e-5 parity */
 #define PDF_PREC_BF16 1 /* tcgen05/TMEM path, bf16 operands, f32 accumulate */
@@ -205,6 +206,11 @@ int pdf_moe_sweep(const pdf_moe* net, int n_subjects, int n_scenarios, const flo
  * pdf_selftest_umma: C[M,N] = A[M,K] * B[N,K]^T through TMA(2D tiled) + tcgen05.mma, bf16 in / f32 out.
  * ------------------------------------------------------------------------------------------ */
 int pdf_selftest_umma(int M, int N, int K, const void* d_a_bf16, const void* d_b_bf16, float* d_c, pdf_stream_t stream);
+/* C[128,N] = A[shift:shift+128, 0:64] * B[N,64]^T where A (256 x 64) is loaded ONCE into shared memory and the MMA
+ * reads it through a descriptor whose start address is advanced by `shift` rows (shift*128 bytes).
+ * mode 0: descriptor base_offset = 0; mode 1: base_offset = (start_address >> 7) & 7.  Probes the shifted-window
+ * operand reuse a halo-resident 3x3 convolution needs. */
+int pdf_selftest_umma_shift(int N, int shift, int mode, const void* d_a_bf16, const void* d_b_bf16, float* d_c, pdf_stream_t stream);
 
 #ifdef __cplusplus
 }

@@ -8,6 +8,7 @@ int launch_conv_f32(const pdf_op& op, cudaStream_t s);
 int launch_maxpool(const pdf_op& op, cudaStream_t s);
 int launch_avgpool(const pdf_op& op, cudaStream_t s);
 int launch_stem_im2col(const pdf_op& op, cudaStream_t s);
+int launch_stem_fused(const pdf_op& op, cudaStream_t s);
 
 // tcgen05 path: one prepared launch per bf16 conv op (tensor maps are 128-byte opaque blobs)
 struct alignas(64) TensorMapBlob { unsigned char bytes[128]; };

@@ -16,7 +16,7 @@ struct pdf_plan {
 using namespace pdf;
 
 static int validate_op(const pdf_op& op, int i) {
-  PDF_REQUIRE(op.kind >= PDF_OP_CONV && op.kind <= PDF_OP_STEM_IM2COL, "op %d: unknown kind %d", i, op.kind);
+  PDF_REQUIRE(op.kind >= PDF_OP_CONV && op.kind <= PDF_OP_STEM_FUSED, "op %d: unknown kind %d", i, op.kind);
   PDF_REQUIRE(op.precision == PDF_PREC_F32 || op.precision == PDF_PREC_BF16, "op %d: bad precision", i);
   PDF_REQUIRE(op.n > 0 && op.h > 0 && op.w > 0 && op.c > 0, "op %d: bad input shape", i);
   PDF_REQUIRE(op.d_in && op.d_out, "op %d: null in/out pointer", i);
@@ -31,6 +31,11 @@ static int validate_op(const pdf_op& op, int i) {
   if (op.kind == PDF_OP_STEM_IM2COL)
     PDF_REQUIRE(op.precision == PDF_PREC_BF16 && op.c == 1 && op.k % 8 == 0 && op.k >= 56 && op.ho == (op.h + 6 - 7) / 2 + 1 &&
                 op.wo == (op.w + 6 - 7) / 2 + 1, "op %d: stem im2col is 7x7 s2 p3 on one bf16 channel, kpad multiple of 8", i);
+  if (op.kind == PDF_OP_STEM_FUSED) {
+    const int h1 = (op.h + 6 - 7) / 2 + 1;
+    PDF_REQUIRE(op.precision == PDF_PREC_BF16 && op.c == 1 && op.k == 64 && op.h == op.w && op.ho == op.wo &&
+                op.ho == (h1 + 2 - 3) / 2 + 1 && op.d_weight && op.d_bias, "op %d: fused stem is 7x7 s2 p3 (1 -> 64 ch) + maxpool 3x3 s2 p1", i);
+  }
   return PDF_OK;
 }
 
@@ -45,6 +50,7 @@ extern "C" int pdf_plan_create(pdf_plan** out, const pdf_op* ops, int n_ops) {
   for (int i = 0; i < n_ops; ++i) {
     const pdf_op& op = plan->ops[i];
     int rc = validate_op(op, i);
+    if (rc == PDF_OK && op.kind == PDF_OP_STEM_FUSED) plan->flops += 2.0 * op.n * ((op.h - 1) / 2 + 1) * ((op.w - 1) / 2 + 1) * 64.0 * 49.0;
     if (rc == PDF_OK && op.kind == PDF_OP_CONV) {
       plan->flops += 2.0 * op.n * op.ho * op.wo * (double)op.k * op.r * op.s * op.c;
       if (op.precision == PDF_PREC_BF16) rc = prepare_conv_tc(op, &plan->tc[i]);
@@ -66,6 +72,7 @@ extern "C" int pdf_plan_run_range(const pdf_plan* plan, int first, int count, pd
       case PDF_OP_MAXPOOL: rc = launch_maxpool(op, s); break;
       case PDF_OP_AVGPOOL: rc = launch_avgpool(op, s); break;
       case PDF_OP_STEM_IM2COL: rc = launch_stem_im2col(op, s); break;
+      case PDF_OP_STEM_FUSED: rc = launch_stem_fused(op, s); break;
     }
     if (rc != PDF_OK) return rc;
   }

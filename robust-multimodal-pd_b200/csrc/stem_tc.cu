@@ -1,0 +1,198 @@
+// K2 stem, fused: 7x7 stride-2 pad-3 convolution (one folded input channel) + bias + ReLU + 3x3 stride-2 pad-1
+// max-pool in ONE kernel.  Per CTA: a 7x7 tile of pooled pixels <- 15x15 conv pixels <- 35x35 input patch.
+//
+//   1. input patch (bf16, zero padded) -> shared memory
+//   2. the 225 x 64 im2col matrix (49 taps + 15 zero columns) is BUILT in shared memory in the K-major
+//      SWIZZLE_128B layout the tensor core reads (never touches HBM); weights [64 x 64] likewise
+//   3. 2 x 4 tcgen05.mma (M=128, N=64, K=16) -> two f32 accumulators in TMEM
+//   4. epilogue: tcgen05.ld -> +bias, ReLU -> bf16 conv tile in shared memory (overlays the A matrix)
+//   5. 3x3/2 max over the conv tile -> [n, P, P, 64] bf16 NHWC
+//
+// HBM traffic per image: S*S*2 bytes in (+halo re-reads from L2), P*P*64*2 bytes out -- the unfused sequence
+// (stem_im2col_kernel -> conv_tc_kernel -> maxpool_kernel) moves ~6.8 MB per 224x224 image instead of 0.5 MB.
+// Replaces conv1/bn1/relu/maxpool of torchvision's ResNet (`model(batch)`, data/openneuro_features.py:260).
+#include "tc_common.cuh"
+#include "ops.cuh"
+
+namespace pdf {
+
+constexpr int kTP = 7;             // pooled tile side
+constexpr int kCT = 2 * kTP + 1;   // conv tile side (15)
+constexpr int kIT = 2 * kCT + 5;   // input patch side (35)
+constexpr int kITP = kIT + 1;      // padded row pitch
+constexpr int kConvPix = kCT * kCT;  // 225 valid rows of the 256-row A matrix
+
+struct StemParams {
+  const __nv_bfloat16* in;    // [n, S, S]
+  const __nv_bfloat16* w;     // [64, 64]  (cout, tap; taps >= 49 are zero)
+  const float* bias;          // [64]
+  __nv_bfloat16* out;         // [n, P, P, 64]
+  int S, H1, P, tiles;
+};
+
+__global__ void __launch_bounds__(256)
+stem_fused_kernel(const StemParams p) {
+  // [ A: 256 rows x 128 B | W: 64 rows x 128 B | input patch | barrier, tmem slot ]
+  extern __shared__ uint8_t smem_raw[];
+  const uint32_t raw_addr = smem_u32(smem_raw);
+  const uint32_t base = (raw_addr + 1023u) & ~1023u;
+  uint8_t* smem = smem_raw + (base - raw_addr);
+  uint8_t* sA = smem;
+  uint8_t* sW = smem + 256 * 128;
+  __nv_bfloat16* sIn = reinterpret_cast<__nv_bfloat16*>(smem + 256 * 128 + 64 * 128);
+  const uint32_t bar = base + 256 * 128 + 64 * 128 + ((kIT * kITP * 2 + 15) & ~15);
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(smem + (bar - base) + 8);
+
+  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  const int n = blockIdx.y;
+  const int ty = blockIdx.x / p.tiles, tx = blockIdx.x - ty * p.tiles;
+  const int tp0 = ty * kTP, tq0 = tx * kTP;          // pooled-tile origin
+  const int cy0 = 2 * tp0 - 1, cx0 = 2 * tq0 - 1;    // conv-tile origin (may be -1)
+  const int iy0 = 2 * cy0 - 3, ix0 = 2 * cx0 - 3;    // input-patch origin
+
+  if (tid == 0) { mbar_init(bar, 1); fence_barrier_init(); }
+  if (warp == 1) tmem_alloc(smem_u32(tmem_slot), 128);
+
+  // 1. input patch
+  const __nv_bfloat16* img = p.in + (size_t)n * p.S * p.S;
+  for (int i = tid; i < kIT * kIT; i += 256) {
+    const int y = i / kIT, x = i - y * kIT;
+    const int gy = iy0 + y, gx = ix0 + x;
+    __nv_bfloat16 v = __float2bfloat16(0.f);
+    if (gy >= 0 && gy < p.S && gx >= 0 && gx < p.S) v = img[(size_t)gy * p.S + gx];
+    sIn[y * kITP + x] = v;
+  }
+  // 2a. weights -> swizzled K-major rows (16-byte chunk c of row r lives at chunk c ^ (r & 7))
+  for (int i = tid; i < 64 * 8; i += 256) {
+    const int r = i >> 3, c = i & 7;
+    const uint4 v = __ldg(reinterpret_cast<const uint4*>(p.w) + i);
+    *reinterpret_cast<uint4*>(sW + r * 128 + ((c ^ (r & 7)) << 4)) = v;
+  }
+  __syncthreads();
+  // 2b. im2col rows
+  for (int i = tid; i < 256 * 8; i += 256) {
+    const int m = i >> 3, c = i & 7;
+    __align__(16) __nv_bfloat16 v[8];
+#pragma unroll
+    for (int e = 0; e < 8; ++e) v[e] = __float2bfloat16(0.f);
+    if (m < kConvPix) {
+      const int cy = m / kCT, cx = m - cy * kCT;
+      const __nv_bfloat16* src = sIn + (2 * cy) * kITP + 2 * cx;
+#pragma unroll
+      for (int e = 0; e < 8; ++e) {
+        const int k = c * 8 + e;
+        if (k < 49) {
+          const int r = k / 7, s = k - r * 7;
+          v[e] = src[r * kITP + s];
+        }
+      }
+    }
+    *reinterpret_cast<uint4*>(sA + m * 128 + ((c ^ (m & 7)) << 4)) = *reinterpret_cast<const uint4*>(v);
+  }
+  fence_proxy_async();          // generic-proxy smem writes -> visible to the tensor core (async proxy)
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_slot;
+
+  // 3. MMAs
+  if (tid == 0) {
+    constexpr uint32_t idesc = make_idesc(64);
+    const uint32_t a0 = base, w0 = base + 256 * 128;
+#pragma unroll
+    for (int mt = 0; mt < 2; ++mt)
+#pragma unroll
+      for (int k = 0; k < 4; ++k)
+        umma_f16(tmem_base + mt * 64, make_smem_desc(a0 + mt * kABytes + k * 32), make_smem_desc(w0 + k * 32), idesc, k != 0 ? 1u : 0u);
+    umma_commit(bar);
+  }
+  mbar_wait(bar, 0);
+  tc_fence_after();
+
+  // 4. epilogue: conv tile (bias, ReLU, bf16) -> shared memory over the A matrix; out-of-image conv pixels -> 0
+  {
+    const int quad = warp & 3, mt = warp >> 2;
+    const int m = mt * 128 + quad * 32 + lane;
+    const int cy = m / kCT, cx = m - cy * kCT;
+    const int gy = cy0 + cy, gx = cx0 + cx;
+    const bool inside = m < kConvPix && gy >= 0 && gy < p.H1 && gx >= 0 && gx < p.H1;
+#pragma unroll
+    for (int c0 = 0; c0 < 64; c0 += 32) {
+      uint32_t v[32];
+      tmem_ld32(tmem_base + ((uint32_t)(quad * 32) << 16) + (uint32_t)(mt * 64 + c0), v);
+      if (m < kConvPix) {
+#pragma unroll
+        for (int i = 0; i < 4; ++i) {
+          uint4 o;
+          __nv_bfloat162* h = reinterpret_cast<__nv_bfloat162*>(&o);
+#pragma unroll
+          for (int j = 0; j < 4; ++j) {
+            const int ch = c0 + i * 8 + j * 2;
+            float a = 0.f, b = 0.f;
+            if (inside) {
+              a = fmaxf(__uint_as_float(v[i * 8 + j * 2]) + __ldg(p.bias + ch), 0.f);
+              b = fmaxf(__uint_as_float(v[i * 8 + j * 2 + 1]) + __ldg(p.bias + ch + 1), 0.f);
+            }
+            h[j] = __floats2bfloat162_rn(a, b);
+          }
+          const int chunk = (c0 >> 3) + i;
+          *reinterpret_cast<uint4*>(sA + m * 128 + ((chunk ^ (m & 7)) << 4)) = o;
+        }
+      }
+    }
+  }
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 1) tmem_dealloc(tmem_base, 128);
+
+  // 5. 3x3 stride-2 max-pool over the conv tile (values are >= 0 after ReLU, so padding/out-of-image = 0 is neutral)
+  for (int i = tid; i < kTP * kTP * 8; i += 256) {
+    const int c = i & 7, px = i >> 3;
+    const int pp = px / kTP, pq = px - pp * kTP;
+    const int gp = tp0 + pp, gq = tq0 + pq;
+    if (gp >= p.P || gq >= p.P) continue;
+    __nv_bfloat162 mx[4];
+#pragma unroll
+    for (int j = 0; j < 4; ++j) mx[j] = __floats2bfloat162_rn(0.f, 0.f);
+#pragma unroll
+    for (int dy = 0; dy < 3; ++dy)
+#pragma unroll
+      for (int dx = 0; dx < 3; ++dx) {
+        const int m = (2 * pp + dy) * kCT + 2 * pq + dx;
+        const uint4 v = *reinterpret_cast<const uint4*>(sA + m * 128 + ((c ^ (m & 7)) << 4));
+        const __nv_bfloat162* h = reinterpret_cast<const __nv_bfloat162*>(&v);
+#pragma unroll
+        for (int j = 0; j < 4; ++j) mx[j] = __hmax2(mx[j], h[j]);
+      }
+    uint4 o;
+    __nv_bfloat162* ho = reinterpret_cast<__nv_bfloat162*>(&o);
+#pragma unroll
+    for (int j = 0; j < 4; ++j) ho[j] = mx[j];
+    *reinterpret_cast<uint4*>(p.out + (((size_t)n * p.P + gp) * p.P + gq) * 64 + c * 8) = o;
+  }
+}
+
+constexpr int kStemSmem = 256 * 128 + 64 * 128 + ((kIT * kITP * 2 + 15) & ~15) + 16 + 1024;
+
+int launch_stem_fused(const pdf_op& op, cudaStream_t s) {
+  static bool configured = false;
+  if (!configured) {
+    PDF_CHECK_CUDA(cudaFuncSetAttribute(stem_fused_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kStemSmem));
+    configured = true;
+  }
+  StemParams p;
+  p.in = reinterpret_cast<const __nv_bfloat16*>(op.d_in);
+  p.w = reinterpret_cast<const __nv_bfloat16*>(op.d_weight);
+  p.bias = op.d_bias;
+  p.out = reinterpret_cast<__nv_bfloat16*>(op.d_out);
+  p.S = op.h;
+  p.H1 = (op.h + 6 - 7) / 2 + 1;
+  p.P = op.ho;
+  p.tiles = ceil_div(p.P, kTP);
+  dim3 grid(p.tiles * p.tiles, op.n);
+  stem_fused_kernel<<<grid, 256, kStemSmem, s>>>(p);
+  PDF_CHECK_LAUNCH();
+  return PDF_OK;
+}
+
+}  // namespace pdf

@@ -19,7 +19,7 @@ PDF_MAX_MODS = 8
 OUT_BF16_C1 = 0
 OUT_F32_NHWC3 = 1
 
-OP_CONV, OP_MAXPOOL, OP_AVGPOOL, OP_STEM_IM2COL = 0, 1, 2, 3
+OP_CONV, OP_MAXPOOL, OP_AVGPOOL, OP_STEM_IM2COL, OP_STEM_FUSED = 0, 1, 2, 3, 4
 PREC_F32, PREC_BF16 = 0, 1
 
 
@@ -103,6 +103,7 @@ PROTOTYPES = {
     "pdf_moddrop_sweep": (C.c_int, [C.POINTER(Mlp), C.c_int, C.c_int, _P, _P, _P, _P, _P]),
     "pdf_moe_sweep": (C.c_int, [C.POINTER(Moe), C.c_int, C.c_int, C.POINTER(_P), _P, _P, _P]),
     "pdf_selftest_umma": (C.c_int, [C.c_int, C.c_int, C.c_int, _P, _P, _P, _P]),
+    "pdf_selftest_umma_shift": (C.c_int, [C.c_int, C.c_int, C.c_int, _P, _P, _P, _P]),
 }
 
 _lib = None

@@ -171,7 +171,7 @@ class ResNetEncoder:
     """
 
     def __init__(self, state_dict: Dict[str, torch.Tensor], n_images: int, input_size: int = 224,
-                 precision: str = "bf16", arch: str | None = None, device=None):
+                 precision: str = "bf16", arch: str | None = None, device=None, fused_stem: bool = True):
         _lib.require_cuda()
         self.lib = _lib.load()
         self.device = torch.device(device if device is not None else f"cuda:{torch.cuda.current_device()}")
@@ -183,6 +183,7 @@ class ResNetEncoder:
             raise ValueError("precision must be 'bf16' or 'fp32'")
         self.bf16 = precision == "bf16"
         self.precision = precision
+        self.fused_stem = bool(fused_stem)
         sd = {k: v.detach().to("cpu") for k, v in state_dict.items()}
         self._keep: List[torch.Tensor] = []     # device tensors referenced by the plan
         self._build(sd)
@@ -245,20 +246,26 @@ class ResNetEncoder:
         # ---- stem
         stem = convs[0]
         w, sc, b = self._conv_weights(sd, stem)
-        s_out = free.pop(0)
-        if self.bf16:
-            s_col = free.pop(0)
-            add("stem.im2col", kind=_lib.OP_STEM_IM2COL, precision=prec, n=n, h=S, w=S, c=1, k=64, r=7, s=7, stride=2, pad=3,
-                ho=h1, wo=h1, d_in=self.input.data_ptr(), d_out=sp(s_col))
-            add("conv1", kind=_lib.OP_CONV, precision=prec, n=n, h=h1, w=h1, c=64, k=64, r=1, s=1, stride=1, pad=0, ho=h1, wo=h1,
-                relu=1, d_in=sp(s_col), d_weight=w.data_ptr(), d_bias=b.data_ptr(), d_out=sp(s_out))
-            free.append(s_col)
+        if self.bf16 and self.fused_stem:
+            # conv1 + bn1 + relu + maxpool in one kernel (stem_tc.cu): the patch matrix never leaves shared memory
+            s_pool = free.pop(0)
+            add("stem.fused", kind=_lib.OP_STEM_FUSED, precision=prec, n=n, h=S, w=S, c=1, k=64, r=7, s=7, stride=2, pad=3,
+                ho=h2, wo=h2, relu=1, d_in=self.input.data_ptr(), d_weight=w.data_ptr(), d_bias=b.data_ptr(), d_out=sp(s_pool))
         else:
-            add("conv1", kind=_lib.OP_CONV, precision=prec, n=n, h=S, w=S, c=3, k=64, r=7, s=7, stride=2, pad=3, ho=h1, wo=h1,
-                relu=1, d_in=self.input.data_ptr(), d_weight=w.data_ptr(), d_scale=sc.data_ptr(), d_bias=b.data_ptr(), d_out=sp(s_out))
-        s_pool = free.pop(0)
-        add("maxpool", kind=_lib.OP_MAXPOOL, precision=prec, n=n, h=h1, w=h1, c=64, ho=h2, wo=h2, d_in=sp(s_out), d_out=sp(s_pool))
-        free.append(s_out)
+            s_out = free.pop(0)
+            if self.bf16:
+                s_col = free.pop(0)
+                add("stem.im2col", kind=_lib.OP_STEM_IM2COL, precision=prec, n=n, h=S, w=S, c=1, k=64, r=7, s=7, stride=2, pad=3,
+                    ho=h1, wo=h1, d_in=self.input.data_ptr(), d_out=sp(s_col))
+                add("conv1", kind=_lib.OP_CONV, precision=prec, n=n, h=h1, w=h1, c=64, k=64, r=1, s=1, stride=1, pad=0, ho=h1, wo=h1,
+                    relu=1, d_in=sp(s_col), d_weight=w.data_ptr(), d_bias=b.data_ptr(), d_out=sp(s_out))
+                free.append(s_col)
+            else:
+                add("conv1", kind=_lib.OP_CONV, precision=prec, n=n, h=S, w=S, c=3, k=64, r=7, s=7, stride=2, pad=3, ho=h1, wo=h1,
+                    relu=1, d_in=self.input.data_ptr(), d_weight=w.data_ptr(), d_scale=sc.data_ptr(), d_bias=b.data_ptr(), d_out=sp(s_out))
+            s_pool = free.pop(0)
+            add("maxpool", kind=_lib.OP_MAXPOOL, precision=prec, n=n, h=h1, w=h1, c=64, ho=h2, wo=h2, d_in=sp(s_out), d_out=sp(s_pool))
+            free.append(s_out)
         cur, cur_h, cur_c = s_pool, h2, 64
         # ---- residual stages
         blocks: Dict[str, List[dict]] = {}

@@ -102,3 +102,47 @@ def test_bf16_layers_vs_fp32_layers():
         a, b = out16.float().cpu(), out32.cpu()
         err = (a - b).abs().max().item()
         assert err < 2e-2 * max(1.0, b.abs().max().item()), ((n, h, c, k, r, stride, pad, res), err)
+
+
+@pytest.mark.parametrize("S,n", [(224, 3), (64, 5), (70, 2)])
+def test_fused_stem_equals_unfused(S, n):
+    """stem_fused_kernel (in-smem im2col + tcgen05 + fused maxpool) must reproduce the three-kernel stem bit for bit."""
+    sd = _sd("resnet18")
+    x = (torch.rand(n, S, S, generator=torch.Generator().manual_seed(S)) * 2 - 1).to(torch.bfloat16).cuda()
+    outs = []
+    for fused in (True, False):
+        enc = ResNetEncoder(sd, n, S, precision="bf16", fused_stem=fused)
+        enc.input.copy_(x)
+        n_stem = 1 if fused else 3
+        enc.run_range(0, n_stem)
+        torch.cuda.synchronize()
+        hp = ((S - 1) // 2 + 1 + 2 - 3) // 2 + 1
+        first_conv = enc.ops[n_stem]           # the pooled stem output is the input of the first residual conv
+        assert first_conv.h == hp
+        slot = [sl for sl in enc.slots if sl.data_ptr() == first_conv.d_in][0]
+        outs.append(slot[: n * hp * hp * 64 * 2].view(torch.bfloat16).clone())
+    assert torch.equal(outs[0], outs[1])
+
+
+def test_umma_shifted_descriptor_probe():
+    """Records whether an MMA operand may start at an arbitrary 128-byte row of a resident, 128B-swizzled tile --
+    the precondition for halo-resident 3x3 convolutions.  Result goes to gpurun_out/umma_shift_probe.txt."""
+    import os
+    lib = _lib.load()
+    g = torch.Generator().manual_seed(3)
+    a = torch.randn(256, 64, generator=g).to(torch.bfloat16).cuda()
+    b = torch.randn(64, 64, generator=g).to(torch.bfloat16).cuda()
+    res = {}
+    for mode in (0, 1):
+        for shift in (0, 1, 2, 3, 5, 8, 9, 58, 59, 117, 128):
+            c = torch.zeros(128, 64, dtype=torch.float32, device="cuda")
+            _lib.check(lib.pdf_selftest_umma_shift(64, shift, mode, a.data_ptr(), b.data_ptr(), c.data_ptr(), _lib.stream_ptr()))
+            torch.cuda.synchronize()
+            ref = a[shift:shift + 128].float() @ b.float().T
+            res[(mode, shift)] = bool((c - ref).abs().max().item() < 1e-2)
+    os.makedirs("gpurun_out", exist_ok=True)
+    with open("gpurun_out/umma_shift_probe.txt", "w") as f:
+        for mode in (0, 1):
+            f.write(f"mode {mode}: " + " ".join(f"{s}:{'ok' if v else 'BAD'}" for (m, s), v in res.items() if m == mode) + "\n")
+    print(open("gpurun_out/umma_shift_probe.txt").read())
+    assert res[(0, 0)] and res[(0, 8)] and res[(0, 128)]      # 1024-byte aligned starts must work

@@ -56,6 +56,8 @@ typedef struct {
   int32_t input_size;           /* network input side (224) */
   float mean[3];                /* per-channel mean/std of (x-mean)/std */
   float std[3];
+  int32_t extent_raw;           /* 0: extent = any(normalised voxel > 0) (the fused pipeline); 1: any(voxel > 0) on the
+                                   resampled volume itself (stand-alone _select_slices on an already-normalised volume) */
 } pdf_preproc_cfg;
 
 /* output layouts of pdf_gather_resize_normalize */

@@ -234,6 +234,7 @@ struct FinalizeArgs {
   int axes[PDF_MAX_AXES];
   int counts[PDF_MAX_AXES];
   int lmax;
+  int extent_raw;
 };
 
 __device__ __forceinline__ float normalise(float v, float lo, float hi, float den) {
@@ -342,7 +343,10 @@ scan_kernel(SubjState* __restrict__ states, FinalizeArgs fa, float* __restrict__
     int lf = T, ll = -1;
     for (int k = tid; k < T; k += 256) {
       const uint32_t key = st->plane_max[axis][k];
-      if (key != 0 && normalise(ordered_to_float(key), lo, hi, den) > 0.0f) { lf = min(lf, k); ll = max(ll, k); }
+      if (key != 0) {
+        const float pv = ordered_to_float(key);
+        if ((fa.extent_raw ? pv : normalise(pv, lo, hi, den)) > 0.0f) { lf = min(lf, k); ll = max(ll, k); }
+      }
     }
     for (int o = 16; o; o >>= 1) {
       lf = min(lf, __shfl_xor_sync(0xffffffffu, lf, o));
@@ -549,6 +553,7 @@ extern "C" int pdf_select_bounds_indices(const pdf_preproc_cfg* cfg, int batch, 
   FinalizeArgs fa;
   fa.lmax = 0;
   fa.n_axes = cfg->n_axes;
+  fa.extent_raw = cfg->extent_raw;
   for (int i = 0; i < 3; ++i) fa.T[i] = cfg->out_shape[i];
   for (int a = 0; a < PDF_MAX_AXES; ++a) {
     fa.axes[a] = a < cfg->n_axes ? cfg->axes[a] : 0;

@@ -33,6 +33,7 @@ class PreprocCfg(C.Structure):
         ("input_size", C.c_int32),
         ("mean", C.c_float * 3),
         ("std", C.c_float * 3),
+        ("extent_raw", C.c_int32),
     ]
 
 

@@ -1,0 +1,273 @@
+"""Drop-in for `pd_fusion.data.openneuro_features` (reference: data/openneuro_features.py), hot-path part:
+volume load + resample, intensity normalisation, slice selection, ResNet2D embedding builders and the
+cache readers.  Same function names, arguments, return types, cache file names and on-disk formats;
+the numerics run in libpdfusion_b200.so on the GPU, batched over subjects, and -- under torchrun -- sharded
+over the GPUs of the box with an NCCL all-gather of the embedding table (rank 0 writes the cache).
+
+Non-hashed runtime knobs (environment, so the cache key `sha256(str(sorted(cfg.items())))` is untouched):
+  PD_FUSION_B200_PRECISION       bf16 (default, tcgen05 path) | fp32 (CUDA-core parity path)
+  PD_FUSION_B200_SUBJECT_BATCH   subjects per device batch (default 8)
+  PD_FUSION_B200_BACKBONE_WEIGHTS  path of a torchvision-layout state_dict to use instead of downloading
+"""
+from __future__ import annotations
+
+import gzip
+import hashlib
+import os
+import struct
+from pathlib import Path
+from typing import Dict, List, Sequence, Tuple
+
+import numpy as np
+import pandas as pd
+import torch
+
+from .. import _lib
+from ..backbone import RESNET_SPECS, ResNet2D
+from ..parallel import all_gather_rows, shard_range, world
+from ..pipeline import EmbeddingPipeline
+from ..preprocess import VolumePreprocessor
+
+
+def _hash_file(path: Path) -> str:
+    h = hashlib.sha256()
+    with open(path, "rb") as f:
+        for chunk in iter(lambda: f.read(1 << 20), b""):
+            h.update(chunk)
+    return h.hexdigest()[:12]
+
+
+def _hash_config(cfg: Dict) -> str:
+    return hashlib.sha256(str(sorted(cfg.items())).encode()).hexdigest()[:12]
+
+
+# ---------------------------------------------------------------------------------------------------
+# volume decode (host).  The reference delegates to nibabel (openneuro_features.py:23-25), which is not in
+# this image; .npy and NIfTI-1 (.nii / .nii.gz) are decoded here.  SURVEY.md 8f rank 1 ("next" row).
+# ---------------------------------------------------------------------------------------------------
+_NIFTI_DTYPES = {2: "u1", 4: "i2", 8: "i4", 16: "f4", 64: "f8", 256: "i1", 512: "u2", 768: "u4", 1024: "i8", 1280: "u8"}
+
+
+def _read_nifti(path: Path) -> np.ndarray:
+    raw = gzip.open(path, "rb").read() if str(path).endswith(".gz") else Path(path).read_bytes()
+    end = "<" if struct.unpack("<i", raw[:4])[0] == 348 else ">"
+    if struct.unpack(end + "i", raw[:4])[0] != 348:
+        raise ValueError(f"{path}: not a NIfTI-1 file")
+    dim = struct.unpack(end + "8h", raw[40:56])
+    datatype = struct.unpack(end + "h", raw[70:72])[0]
+    vox_offset = int(struct.unpack(end + "f", raw[108:112])[0])
+    slope, inter = struct.unpack(end + "2f", raw[112:120])
+    if datatype not in _NIFTI_DTYPES:
+        raise ValueError(f"{path}: unsupported NIfTI datatype {datatype}")
+    shape = tuple(int(d) for d in dim[1:1 + dim[0]])
+    arr = np.frombuffer(raw, dtype=np.dtype(end + _NIFTI_DTYPES[datatype]), count=int(np.prod(shape)), offset=vox_offset)
+    data = arr.reshape(shape, order="F").astype(np.float64)           # get_fdata(): float64 with scaling applied
+    if slope != 0 and np.isfinite(slope) and not (slope == 1.0 and inter == 0.0):
+        data = data * slope + inter
+    while data.ndim > 3 and data.shape[-1] == 1:
+        data = data[..., 0]
+    return data
+
+
+def _read_volume_host(path) -> np.ndarray:
+    """Raw volume as C-contiguous float32 [X,Y,Z] (no scrub, no resample)."""
+    p = str(path)
+    data = np.load(p) if p.endswith(".npy") else _read_nifti(Path(p))
+    return np.ascontiguousarray(data.astype(np.float32))
+
+
+# ---------------------------------------------------------------------------------------------------
+# single-volume helpers with the reference's names (imported by CLI 2 and the fine-tune model)
+# ---------------------------------------------------------------------------------------------------
+_PRE_CACHE: Dict[tuple, VolumePreprocessor] = {}
+
+
+def _preprocessor(in_shape, target_shape, axes=(2,), counts=(1,), input_size=8, mode=_lib.OUT_F32_NHWC3) -> VolumePreprocessor:
+    key = (tuple(in_shape), tuple(target_shape), tuple(axes), tuple(counts), int(input_size), mode, torch.cuda.current_device())
+    if key not in _PRE_CACHE:
+        _PRE_CACHE[key] = VolumePreprocessor(in_shape, target_shape, axes, counts, input_size, out_mode=mode, max_batch=1)
+    return _PRE_CACHE[key]
+
+
+def _load_volume(path: Path, target_shape=(96, 96, 96)):
+    """decode -> float32 -> nan_to_num -> trilinear resample to `target_shape` (K1a on the device)."""
+    raw = _read_volume_host(path)
+    shape = tuple(target_shape) if target_shape is not None else raw.shape
+    pre = _preprocessor(raw.shape, shape)
+    return pre.resample(torch.from_numpy(raw[None]).to(pre.device))[0].cpu().numpy()
+
+
+def _normalize_volume_for_resnet(volume: np.ndarray) -> np.ndarray:
+    """p1/p99 clip + min-max of an already-resampled volume (K1b + normalise kernel)."""
+    v = np.ascontiguousarray(volume, dtype=np.float32)
+    pre = _preprocessor(v.shape, v.shape)                      # identity zoom: resample_kernel reproduces v bit for bit
+    pre.resample(torch.from_numpy(v[None]).to(pre.device))
+    pre.select(1)
+    return pre.normalized_volume(1)[0].cpu().numpy()
+
+
+def _select_slices(volume: np.ndarray, axis: int, slice_count: int) -> np.ndarray:
+    """Slices [n,H,W] over the non-zero extent of an (already normalised) volume."""
+    v = np.ascontiguousarray(volume, dtype=np.float32)
+    pre = _preprocessor(v.shape, v.shape, (int(axis),), (int(slice_count),))
+    idx, n = pre.select_raw(torch.from_numpy(v[None]).to(pre.device))
+    idx = idx[0, : int(n[0, 0])].cpu().numpy()
+    # the gather itself is a view operation on the caller's host array (the batched path gathers on the device)
+    if axis == 0:
+        return v[idx, :, :]
+    if axis == 1:
+        return v[:, idx, :].transpose(1, 0, 2)
+    return v[:, :, idx].transpose(2, 0, 1)
+
+
+def _build_resnet_backbone(backbone: str, pretrained: bool = True):
+    """(nn.Module, emb_dim, weights) -- a torchvision-layout ResNet18/50 whose `fc` is Identity."""
+    import torch.nn as nn
+    arch = "resnet50" if backbone == "resnet50" else "resnet18"
+    weights = None
+    local = os.environ.get("PD_FUSION_B200_BACKBONE_WEIGHTS")
+    if pretrained and not local:
+        from torchvision.models import ResNet18_Weights, ResNet50_Weights, resnet18, resnet50
+        weights = ResNet50_Weights.DEFAULT if arch == "resnet50" else ResNet18_Weights.DEFAULT
+        model = (resnet50 if arch == "resnet50" else resnet18)(weights=weights)   # needs the torchvision cache / network
+    else:
+        model = ResNet2D(arch)
+        if local:
+            model.load_state_dict(torch.load(local, map_location="cpu", weights_only=True), strict=False)
+    emb_dim = model.fc.in_features
+    model.fc = nn.Identity()
+    return model, emb_dim, weights
+
+
+def _apply_affine_2d(slice_2d: np.ndarray, angle_deg: float, translate: np.ndarray) -> np.ndarray:
+    raise NotImplementedError("test-time augmentation (tta > 1) is not implemented on the B200 path yet (SURVEY.md 8a row a6)")
+
+
+# ---------------------------------------------------------------------------------------------------
+# batched builders
+# ---------------------------------------------------------------------------------------------------
+def _mean_std(weights) -> Tuple[List[float], List[float]]:
+    if hasattr(weights, "meta"):
+        return list(weights.meta.get("mean", [0.5, 0.5, 0.5])), list(weights.meta.get("std", [0.5, 0.5, 0.5]))
+    return [0.5, 0.5, 0.5], [0.5, 0.5, 0.5]
+
+
+def embed_manifest(df: pd.DataFrame, backbone: str, target_shape: Sequence[int], axes: Sequence[int], counts: Sequence[int],
+                   input_size: int, tta: int = 1) -> Tuple[np.ndarray, np.ndarray]:
+    """Per-slice embeddings [S, L, D] f32 and slice-mean embeddings [S, D] f32 for every manifest row, in row order.
+    Subjects are processed in device batches; under torchrun each rank embeds its contiguous shard of rows and the
+    table is assembled with an all-gather."""
+    if int(tta) > 1:
+        raise NotImplementedError("tta > 1 is not implemented on the B200 path yet (SURVEY.md 8a row a6)")
+    rank, local_rank, ws = world()
+    dev = torch.device("cuda", local_rank)
+    torch.cuda.set_device(dev)
+    precision = os.environ.get("PD_FUSION_B200_PRECISION", "bf16")
+    bsz = max(1, int(os.environ.get("PD_FUSION_B200_SUBJECT_BATCH", "8")))
+    model, emb_dim, weights = _build_resnet_backbone(backbone)
+    mean, std = _mean_std(weights)
+    if precision == "bf16" and (len(set(mean)) != 1 or len(set(std)) != 1):
+        precision = "fp32"     # per-channel ImageNet statistics: the one-channel stem fold does not apply
+    sd = {k: v for k, v in model.state_dict().items() if not k.startswith("fc.")}
+    L = int(sum(counts))
+    n_rows = len(df)
+    lo, hi = shard_range(n_rows, rank, ws)
+    emb = torch.zeros((hi - lo, L, emb_dim), dtype=torch.float32, device=dev)
+    avg = torch.zeros((hi - lo, emb_dim), dtype=torch.float32, device=dev)
+    nsl = torch.zeros((hi - lo,), dtype=torch.int32, device=dev)
+    pipes: Dict[tuple, EmbeddingPipeline] = {}
+    paths = df["t1wbrain_path"].tolist()
+    i = lo
+    while i < hi:
+        first = _read_volume_host(paths[i])
+        batch, j = [first], i + 1
+        while j < hi and len(batch) < bsz:
+            nxt = _read_volume_host(paths[j])
+            if nxt.shape != first.shape:
+                break
+            batch.append(nxt)
+            j += 1
+        if first.shape not in pipes:
+            pipes[first.shape] = EmbeddingPipeline(sd, first.shape, target_shape, axes, counts, input_size, precision, bsz,
+                                                   mean, std, "resnet50" if backbone == "resnet50" else "resnet18", dev)
+        raw = torch.from_numpy(np.stack(batch)).pin_memory().to(dev, non_blocking=True)
+        res = pipes[first.shape].embed(raw)
+        emb[i - lo:j - lo].copy_(res.embeddings)
+        avg[i - lo:j - lo].copy_(res.mean)
+        nsl[i - lo:j - lo].copy_(res.nslices.sum(dim=1))
+        i = j
+    if ws > 1:
+        emb, avg, nsl = all_gather_rows(emb, n_rows), all_gather_rows(avg, n_rows), all_gather_rows(nsl, n_rows)
+    torch.cuda.synchronize()
+    nsl_h = nsl.cpu().numpy()
+    if (nsl_h != L).any():
+        bad = int(np.argmax(nsl_h != L))
+        # the reference's MIL builder raises in np.stack when bags differ in length; the mean
+        # builder tolerates it.  Keep the information for the callers.
+        embed_manifest.short_bags = (bad, int(nsl_h[bad]))
+    else:
+        embed_manifest.short_bags = None
+    return emb.cpu().numpy(), avg.cpu().numpy()
+
+
+embed_manifest.short_bags = None
+
+
+def build_resnet2d_embeddings(manifest_path: Path, cache_dir: Path, config: Dict) -> pd.DataFrame:
+    """Slice-mean ResNet2D embeddings, cached as resnet2d_<manifest-hash>_<config-hash>.parquet
+    (reference: openneuro_features.py:180-278)."""
+    cache_dir = Path(cache_dir)
+    cache_dir.mkdir(parents=True, exist_ok=True)
+    out_path = cache_dir / f"resnet2d_{_hash_file(manifest_path)}_{_hash_config(config)}.parquet"
+    if out_path.exists():
+        return pd.read_parquet(out_path)
+    df = pd.read_csv(manifest_path)
+    _, avg = embed_manifest(df, config.get("backbone", "resnet18"), tuple(config.get("target_shape", (160, 160, 160))),
+                            [int(config.get("slice_axis", 2))], [int(config.get("slice_count", 24))],
+                            int(config.get("input_size", 224)), int(config.get("tta", 1)))
+    cols = {"subject_id": df["subject_id"].values, "session": df["session"].values, "label": df["label"].astype(int).values}
+    emb64 = avg.astype(np.float64)                      # the reference stores python floats -> float64 columns
+    cols.update({f"mri_resnet_{k}": emb64[:, k] for k in range(emb64.shape[1])})
+    emb_df = pd.DataFrame(cols)
+    if world()[0] == 0:
+        emb_df.to_parquet(out_path, index=False)
+    return emb_df
+
+
+def build_resnet2d_mil_embeddings(manifest_path: Path, out_dir: Path, cfg: Dict, axes: Sequence[int], counts: Sequence[int]) -> Path:
+    """Per-slice (MIL bag) embeddings -> resnet2d_mil_<mh>_<ch>.npz with arrays embeddings/subject_id/session/label
+    (reference: scripts/build_resnet2d_mil_embeddings.py:90-168, which always recomputes)."""
+    out_dir = Path(out_dir)
+    out_dir.mkdir(parents=True, exist_ok=True)
+    out_path = out_dir / f"resnet2d_mil_{_hash_file(manifest_path)}_{_hash_config(cfg)}.npz"
+    df = pd.read_csv(manifest_path)
+    emb, _ = embed_manifest(df, cfg["backbone"], tuple(cfg["target_shape"]), list(axes), list(counts), int(cfg["input_size"]),
+                            int(cfg.get("tta", 1)))
+    if embed_manifest.short_bags is not None:
+        row, n = embed_manifest.short_bags
+        raise ValueError(f"all input arrays must have the same shape: subject row {row} has {n} slices, expected {emb.shape[1]}")
+    if world()[0] == 0:
+        np.savez_compressed(out_path, embeddings=emb.astype(np.float32), subject_id=df["subject_id"].values,
+                            session=df["session"].values, label=df["label"].values)
+    return out_path
+
+
+def load_resnet2d_embeddings(manifest_path: Path, cache_dir: Path, config: Dict) -> pd.DataFrame:
+    cache_dir = Path(cache_dir)
+    cache_dir.mkdir(parents=True, exist_ok=True)
+    out_path = cache_dir / f"resnet2d_{_hash_file(manifest_path)}_{_hash_config(config)}.parquet"
+    if not out_path.exists():
+        raise FileNotFoundError(f"ResNet2D embeddings not found at {out_path}. Run scripts/build_resnet2d_embeddings.py to generate them.")
+    return pd.read_parquet(out_path)
+
+
+def load_resnet2d_mil_embeddings(manifest_path: Path, cache_dir: Path, config: Dict) -> pd.DataFrame:
+    cache_dir = Path(cache_dir)
+    cache_dir.mkdir(parents=True, exist_ok=True)
+    out_path = cache_dir / f"resnet2d_mil_{_hash_file(manifest_path)}_{_hash_config(config)}.npz"
+    if not out_path.exists():
+        raise FileNotFoundError(f"ResNet2D MIL embeddings not found at {out_path}. Run scripts/build_resnet2d_mil_embeddings.py to generate them.")
+    data = np.load(out_path, allow_pickle=True)
+    df = pd.DataFrame({"subject_id": data["subject_id"], "session": data["session"], "label": data["label"]})
+    df["mri_mil"] = list(data["embeddings"])
+    return df

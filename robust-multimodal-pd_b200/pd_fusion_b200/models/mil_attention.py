@@ -1,0 +1,151 @@
+"""MIL (gated-)attention pooling head (reference: models/mil_attention.py).
+
+`MILAttentionNet` keeps the reference's parameter names so its `state_dict` is the weight-interchange format
+(SURVEY.md A.6).  Inference (`predict_proba`) runs ALL bags in one launch of pdf_mil_forward instead of the
+reference's per-bag B=1 loop with a `.cpu()` per bag (mil_attention.py:169-177).  Training stays host-side torch
+autograd on the CUDA device (device-native head training is a "next" row).
+"""
+from __future__ import annotations
+
+from typing import List, Optional
+
+import numpy as np
+import torch
+import torch.nn as nn
+
+from ..heads import MilHead
+from ..utils.torch_utils import get_torch_device
+from .base import BaseModel
+
+
+class MILAttentionNet(nn.Module):
+    def __init__(self, input_dim: int, hidden_dim: int, attn_dim: int, dropout: float = 0.3, gated: bool = False):
+        super().__init__()
+        self.gated = gated
+        self.instance = nn.Sequential(nn.Linear(input_dim, hidden_dim), nn.ReLU(), nn.Dropout(dropout))
+        if gated:
+            self.attn_v = nn.Sequential(nn.Linear(hidden_dim, attn_dim), nn.Tanh())
+            self.attn_u = nn.Sequential(nn.Linear(hidden_dim, attn_dim), nn.Sigmoid())
+            self.attn_w = nn.Linear(attn_dim, 1)
+        else:
+            self.attn = nn.Sequential(nn.Linear(hidden_dim, attn_dim), nn.Tanh(), nn.Linear(attn_dim, 1))
+        self.classifier = nn.Sequential(nn.Linear(hidden_dim, 1), nn.Sigmoid())
+
+    def forward(self, x: torch.Tensor, mask: Optional[torch.Tensor] = None) -> torch.Tensor:
+        """Training-time (autograd) forward; x [B, L, D], mask [B, L]."""
+        h = self.instance(x)
+        s = (self.attn_w(self.attn_v(h) * self.attn_u(h)) if self.gated else self.attn(h)).squeeze(-1)
+        if mask is not None:
+            s = s.masked_fill(mask == 0, -1e9)
+        a = torch.softmax(s, dim=1)
+        return self.classifier((a.unsqueeze(-1) * h).sum(dim=1)).squeeze(-1)
+
+
+def _pad_bags(bags):
+    """Zero-pads bags [L_i, D] to [n, Lmax, D] + {0,1} mask [n, Lmax] (reference: mil_attention.py:54-63)."""
+    lmax = max(b.shape[0] for b in bags)
+    X = np.zeros((len(bags), lmax, bags[0].shape[1]), dtype=np.float32)
+    M = np.zeros((len(bags), lmax), dtype=np.float32)
+    for i, b in enumerate(bags):
+        X[i, : b.shape[0]] = b
+        M[i, : b.shape[0]] = 1.0
+    return X, M
+
+
+class MilAttentionModel(BaseModel):
+    def __init__(self, input_dim: int, params: dict):
+        self.params = params or {}
+        p = self.params
+        self.gated = bool(p.get("gated", False))
+        self.missing_prob = float(p.get("missing_prob", 0.5))
+        self.model = MILAttentionNet(input_dim, int(p.get("hidden_dim", 128)), int(p.get("attn_dim", 64)),
+                                     float(p.get("dropout", 0.3)), gated=self.gated)
+        self.optimizer = torch.optim.Adam(self.model.parameters(), lr=float(p.get("lr", 1e-3)),
+                                          weight_decay=float(p.get("weight_decay", 0.0)))
+        self.criterion = nn.BCELoss(reduction="none")
+        self.pos_weight = float(p["pos_weight"]) if (p.get("class_weight") != "balanced" and p.get("pos_weight") is not None) else None
+        self._head: Optional[MilHead] = None
+
+    # -- training: torch autograd on the device (not the accelerated path) -----------------------
+    def train(self, bags, y, val_data=None):
+        X, M = _pad_bags(bags)
+        dev = get_torch_device()
+        self.model.to(dev)
+        Xt, Mt, yt = torch.from_numpy(X).to(dev), torch.from_numpy(M).to(dev), torch.as_tensor(np.asarray(y), dtype=torch.float32, device=dev)
+        p = self.params
+        bs, epochs = int(p.get("batch_size", 16)), int(p.get("epochs", 30))
+        clip, patience = p.get("max_grad_norm"), int(p.get("early_stopping_patience", 0))
+        if self.pos_weight is None and p.get("class_weight") == "balanced":
+            pos, neg = float((yt == 1).sum()), float((yt == 0).sum())
+            if pos > 0:
+                self.pos_weight = neg / pos
+        best_auc, best_state, bad = -1.0, None, 0
+        for _ in range(epochs):
+            self.model.train()
+            order = torch.randperm(len(Xt), device="cpu").to(dev)
+            for i in range(0, len(order), bs):
+                sel = order[i:i + bs]
+                loss = self.criterion(self.model(Xt[sel], Mt[sel]), yt[sel])
+                if self.pos_weight is not None:
+                    loss = loss * torch.where(yt[sel] >= 0.5, self.pos_weight, 1.0)
+                loss = loss.mean()
+                self.optimizer.zero_grad()
+                loss.backward()
+                if clip:
+                    torch.nn.utils.clip_grad_norm_(self.model.parameters(), float(clip))
+                self.optimizer.step()
+            self._head = None
+            if val_data is not None and patience > 0:
+                from sklearn.metrics import roc_auc_score
+                try:
+                    auc = float(roc_auc_score(val_data[1], self.predict_proba(val_data[0])))
+                except Exception:
+                    auc = -1.0
+                if auc > best_auc:
+                    best_auc, bad = auc, 0
+                    best_state = {k: v.detach().clone() for k, v in self.model.state_dict().items()}
+                else:
+                    bad += 1
+                    if bad >= patience:
+                        break
+        if best_state is not None:
+            self.model.load_state_dict(best_state)
+        self._head = None
+
+    # -- inference: one launch over all bags ------------------------------------------------------
+    def _get_head(self) -> MilHead:
+        if self._head is None:
+            self._head = MilHead(self.model.state_dict(), self.gated, self.missing_prob, device=get_torch_device())
+        return self._head
+
+    def invalidate(self):
+        """Call after mutating `self.model` weights in place (load_state_dict etc.)."""
+        self._head = None
+
+    def predict_proba(self, bags: List[Optional[np.ndarray]], masks=None) -> np.ndarray:
+        mri = masks["mri"] if isinstance(masks, dict) and "mri" in masks else None
+        n = len(bags)
+        live = [i for i, b in enumerate(bags) if b is not None and not (mri is not None and mri[i] == 0)]
+        out = np.full(n, self.missing_prob, dtype=np.float64)
+        if not live:
+            return out
+        head = self._get_head()
+        lmax = max(bags[i].shape[0] for i in live)
+        X = np.zeros((len(live), lmax, head.D), dtype=np.float32)
+        lens = np.zeros(len(live), dtype=np.int32)
+        for j, i in enumerate(live):
+            b = np.asarray(bags[i], dtype=np.float32)
+            X[j, : b.shape[0]] = b
+            lens[j] = b.shape[0]
+        prob = head.forward(torch.from_numpy(X).to(head.device), torch.from_numpy(lens).to(head.device))
+        out[live] = prob.cpu().numpy().astype(np.float64)
+        return out
+
+    def save(self, path):
+        torch.save(self.model.state_dict(), path)
+
+    @classmethod
+    def load(cls, path, input_dim, params):
+        inst = cls(input_dim, params)
+        inst.model.load_state_dict(torch.load(path, map_location="cpu", weights_only=True))
+        return inst

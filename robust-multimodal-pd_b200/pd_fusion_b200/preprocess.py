@@ -98,6 +98,17 @@ class VolumePreprocessor:
                                                       _lib.stream_ptr()), "pdf_select_bounds_indices")
         return self.lohi[:B], self.indices[:B], self.nslices[:B]
 
+    def select_raw(self, vol: torch.Tensor):
+        """Indices of `_select_slices` on an already-normalised volume: extent test is voxel > 0 (no re-normalisation)."""
+        B = self._check_raw(vol)
+        self.resample(vol)                      # in_shape == target_shape: identity zoom, gathers plane maxima
+        self.cfg.extent_raw = 1
+        try:
+            _, idx, ns = self.select(B)
+        finally:
+            self.cfg.extent_raw = 0
+        return idx, ns
+
     def gather(self, B: int) -> torch.Tensor:
         _lib.check(self.lib.pdf_gather_resize_normalize(C.byref(self.cfg), B, self.zoomed.data_ptr(), self.workspace.data_ptr(),
                                                         self.lohi.data_ptr(), self.indices.data_ptr(), self.nslices.data_ptr(),

@@ -1,0 +1,131 @@
+"""Host-side logic (no GPU): scenario masks vs the reference's golden masks, feature bookkeeping, sharding,
+the drop-in cache-name contract, NIfTI decode, FLOP accounting."""
+import gzip
+import json
+import struct
+
+import numpy as np
+import pandas as pd
+import pytest
+
+from oracle import oracle as O
+from pd_fusion_b200.backbone import ResNet2D, conv_list, flops_per_image
+from pd_fusion_b200.data import feature_utils as FU
+from pd_fusion_b200.data.missingness import apply_missingness_scenario, get_modality_mask_matrix, scenario_mask_tensor
+from pd_fusion_b200.data.preprocess import preprocess_features
+from pd_fusion_b200.parallel import shard_range
+from pd_fusion_b200.synthetic import synthetic_table
+
+
+def test_masks_bit_exact_vs_reference(golden):
+    g = golden("heads")
+    dims = json.loads(str(g["table/dims"]))
+    df, masks = synthetic_table(int(g["table/n"]), dims, seed=42, mask_seed=7)
+    scen = json.loads(str(g["scenarios"]))["scenarios"]
+    np.random.seed(11)
+    mk, per = scenario_mask_tensor(df, scen, masks, O.MODALITIES)
+    assert mk.dtype == np.uint8 and np.array_equal(mk, g["masks_seed11"])
+    np.random.seed(11)
+    seq = np.stack([get_modality_mask_matrix(apply_missingness_scenario(df, sc, masks)) for sc in scen])
+    assert np.array_equal(seq.astype(np.uint8), g["masks_seed11"])
+    # a modality that is not in the mask dict is a no-op; the input dict is never mutated
+    before = {k: v.copy() for k, v in masks.items()}
+    out = apply_missingness_scenario(df, {"name": "x", "drop_modalities": ["nope", "mri"]}, masks)
+    assert all(np.array_equal(before[k], masks[k]) for k in masks) and out["mri"].sum() == 0
+
+
+def test_feature_bookkeeping():
+    df, _ = synthetic_table(10, {"clinical": 3, "datspect": 2, "mri": 4})
+    cols = FU.get_all_feature_cols(df)
+    assert cols[:3] == ["clinical_f0", "clinical_f1", "clinical_f2"] and len(cols) == 9
+    sl = FU.get_feature_slices(cols)
+    assert sl["mri"] == [5, 6, 7, 8]
+    X, _, sc = preprocess_features(df, cols)
+    Xm = FU.apply_masks_to_matrix(X, {"mri": np.array([0] * 5 + [1] * 5)}, cols)
+    assert np.all(Xm[:5, 5:] == 0) and np.array_equal(Xm[5:], X[5:]) and np.array_equal(Xm[:, :5], X[:, :5])
+    X2, _, _ = preprocess_features(df, cols, None, sc)
+    assert np.array_equal(X, X2)
+
+
+@pytest.mark.parametrize("n,ws", [(10, 4), (5, 4), (0, 2), (8, 8), (10000, 8), (3, 1)])
+def test_shard_ranges_tile_rows_in_order(n, ws):
+    spans = [shard_range(n, r, ws) for r in range(ws)]
+    flat = [i for a, b in spans for i in range(a, b)]
+    assert flat == list(range(n))
+    per = -(-n // ws) if n else 0
+    assert all(b - a <= per for a, b in spans)
+
+
+def test_cache_name_contract(golden):
+    from pd_fusion_b200.data.openneuro_features import _hash_config
+    g = golden("scripts")
+    for tag, prefix in (("c2", "resnet2d_"), ("mil", "resnet2d_mil_")):
+        cfg = json.loads(str(g[f"{tag}/json"]))["config"]
+        name = [str(f) for f in g[f"{tag}/files"] if str(f).endswith(".json")][0]
+        assert name.endswith(f"_{_hash_config(cfg)}.json") and name.startswith(prefix)
+
+
+def test_nifti_reader_roundtrip(tmp_path):
+    from pd_fusion_b200.data.openneuro_features import _read_volume_host
+    vol = (np.arange(5 * 4 * 3, dtype=np.int16).reshape(5, 4, 3) - 7)
+    hdr = bytearray(352)
+    struct.pack_into("<i", hdr, 0, 348)
+    struct.pack_into("<8h", hdr, 40, 3, 5, 4, 3, 1, 1, 1, 1)
+    struct.pack_into("<h", hdr, 70, 4)
+    struct.pack_into("<h", hdr, 72, 16)
+    struct.pack_into("<f", hdr, 108, 352.0)
+    struct.pack_into("<2f", hdr, 112, 2.0, 1.5)
+    p = tmp_path / "v.nii.gz"
+    with gzip.open(p, "wb") as f:
+        f.write(bytes(hdr) + vol.tobytes(order="F"))
+    got = _read_volume_host(p)
+    assert got.dtype == np.float32 and got.shape == (5, 4, 3) and np.array_equal(got, (vol * 2.0 + 1.5).astype(np.float32))
+    np.save(tmp_path / "v.npy", vol.astype(np.float64))
+    assert np.array_equal(_read_volume_host(tmp_path / "v.npy"), vol.astype(np.float32))
+
+
+def test_flop_accounting_matches_survey():
+    assert int(flops_per_image("resnet18")) == 3627122688 and int(flops_per_image("resnet50")) == 8174272512
+    assert int(flops_per_image("resnet18") - flops_per_image("resnet18", folded_stem=True)) == 157351936
+    assert len(conv_list("resnet18")) == 20 and len(conv_list("resnet50")) == 53
+
+
+def test_resnet2d_matches_torchvision_init():
+    import torch
+    tv = pytest.importorskip("torchvision")
+    for arch in ("resnet18", "resnet50"):
+        torch.manual_seed(1234)
+        a = ResNet2D(arch).state_dict()
+        torch.manual_seed(1234)
+        b = getattr(tv.models, arch)(weights=None).state_dict()
+        assert list(a) == list(b) and all(torch.equal(a[k], b[k]) for k in b)
+
+
+def test_evaluate_dispatch_with_a_stub_model():
+    """evaluate_model's dispatch on the type of prep_info and its scenario/RNG order, with a model that needs no GPU."""
+    from pd_fusion_b200.evaluation.evaluate import evaluate_model, predict_proba_for_scenario
+
+    class Stub:
+        def __init__(self):
+            self.calls = []
+
+        def predict_proba(self, X, masks=None):
+            self.calls.append({k: np.array(v) for k, v in masks.items()})
+            return 1.0 / (1.0 + np.exp(-np.nan_to_num(X).sum(axis=1)))
+
+    dims = {"clinical": 3, "datspect": 2, "mri": 4}
+    df, masks = synthetic_table(64, dims)
+    cols = FU.get_all_feature_cols(df)
+    _, _, sc = preprocess_features(df, cols)
+    cfg = {"scenarios": [{"name": "full", "drop_modalities": []}, {"name": "half", "drop_modalities": ["mri"], "drop_rate": 0.5},
+                         {"name": "r1", "type": "random", "n_drop": 1}]}
+    m = Stub()
+    np.random.seed(5)
+    res = evaluate_model(m, df, masks, (None, sc, cols), cfg)
+    assert list(res) == ["full", "half", "r1"] and set(res["full"]) == {"roc_auc", "pr_auc", "balanced_accuracy", "f1", "brier_score", "ece"}
+    np.random.seed(5)
+    want = [O.apply_missingness_scenario(len(df), s, masks) for s in cfg["scenarios"]]
+    for got, w in zip(m.calls, want):
+        assert all(np.array_equal(got[k], w[k]) for k in w)
+    y, p = predict_proba_for_scenario(m, df, masks, (None, sc, cols), cfg["scenarios"][0])
+    assert len(y) == len(p) == 64

@@ -137,7 +137,7 @@ __global__ void avgpool_kernel(const T* __restrict__ in, float* __restrict__ out
   out[(size_t)n * C + c] = s / (float)HW;
 }
 
-// 7x7 stride-2 pad-3 patch matrix of a one-channel bf16 image: row = output pixel, col = r*7+s (zero padded to kpad)
+// 7x7 stride-2 pad-3 patch matrix of a one-channel bf16 image: row = output pixel, col = r*8+s (s=7 and r>=7 columns are zero)
 __global__ void stem_im2col_kernel(const __nv_bfloat16* __restrict__ in, __nv_bfloat16* __restrict__ out, int N, int H, int W,
                                    int Ho, int Wo, int kpad) {
   const int chunks = kpad / 8;
@@ -154,8 +154,8 @@ __global__ void stem_im2col_kernel(const __nv_bfloat16* __restrict__ in, __nv_bf
     for (int e = 0; e < 8; ++e) {
       const int k = ch * 8 + e;
       __nv_bfloat16 x = __float2bfloat16(0.f);
-      if (k < 49) {
-        const int r = k / 7, s = k - r * 7;
+      const int r = k >> 3, s = k & 7;          // K index = r*8 + s (s = 7 / r = 7 are zero columns), as stem_tc.cu
+      if (r < 7 && s < 7) {
         const int ih = p * 2 - 3 + r, iw = q * 2 - 3 + s;
         if (ih >= 0 && ih < H && iw >= 0 && iw < W) x = img[(size_t)ih * W + iw];
       }

@@ -10,6 +10,7 @@
 //
 // Reference call sites: data/openneuro_features.py:22-32, 121-151, 250-255 (see include/pdfusion_b200.h).
 #include "common.cuh"
+#include "tc_common.cuh"
 
 namespace pdf {
 
@@ -104,86 +105,236 @@ __device__ __forceinline__ double scrub(float v) {  // np.nan_to_num(nan=0, posi
   return isfinite(v) ? (double)v : 0.0;
 }
 
-__global__ void __launch_bounds__(1024)
+// One tile = output plane i, TJ consecutive output rows j, all k.  The 2 x nr input rows the tile touches
+// ([x0|x1][ylo..yhi][0..Z)) are contiguous in HBM per plane: they are streamed in once with 16-byte loads,
+// scrubbed, widened to float64 and parked in shared memory; every output voxel then reads its 8 taps from
+// shared memory.  Blocks are persistent over tiles so the histogram / plane-maximum partials are flushed once.
+__global__ void __launch_bounds__(256)
 resample_kernel(const float* __restrict__ raw, float* __restrict__ zoomed, SubjState* __restrict__ states,
-                const ZoomTables* __restrict__ tabs, int X, int Y, int Z, int T0, int T1, int T2, int rows_per_block) {
-  __shared__ uint32_t s_hist[kH0];
-  __shared__ uint32_t s_imax[kPlaneMax];
-  __shared__ uint32_t s_jmax[kPlaneMax];
+                const ZoomTables* __restrict__ tabs, int X, int Y, int Z, int T0, int T1, int T2, int TJ, int NR) {
+  extern __shared__ __align__(16) unsigned char sm_raw[];
+  double* s_in = reinterpret_cast<double*>(sm_raw);                      // [2][NR][Z]
+  uint32_t* s_hist = reinterpret_cast<uint32_t*>(s_in + 2 * (((size_t)NR * Z + 1) & ~(size_t)1));
+  uint32_t* s_imax = s_hist + kH0;
+  uint32_t* s_jmax = s_imax + T0;
   const int b = blockIdx.y;
-  const int tid = threadIdx.x;
-  for (int i = tid; i < kH0; i += blockDim.x) s_hist[i] = 0;
-  for (int i = tid; i < kPlaneMax; i += blockDim.x) { s_imax[i] = 0; s_jmax[i] = 0; }
+  const int tid = threadIdx.x, nthr = blockDim.x;
+  for (int i = tid; i < kH0 + T0 + T1; i += nthr) s_hist[i] = 0;        // hist, imax, jmax are contiguous
   __syncthreads();
 
   SubjState* st = states + b;
   const float* rb = raw + (size_t)b * X * Y * Z;
   float* zb = zoomed + (size_t)b * T0 * T1 * T2;
-  const int nrows = T0 * T1;
-  const int row0 = blockIdx.x * rows_per_block;
-  const int row1 = min(row0 + rows_per_block, nrows);
-  uint32_t tmin = 0xffffffffu;
+  const int tiles_per_i = (T1 + TJ - 1) / TJ;
+  const int ntiles = T0 * tiles_per_i;
+  const int kchunks = (T2 + nthr - 1) / nthr;
+  const size_t plane = ((size_t)NR * Z + 1) & ~(size_t)1;   // even: keeps plane 1 16-byte aligned for double2 stores
+  uint32_t tmin = 0xffffffffu, kmax0 = 0;
 
-  const int kchunks = (T2 + blockDim.x - 1) / blockDim.x;
-  for (int kc = 0; kc < kchunks; ++kc) {
-    const int k = kc * blockDim.x + tid;
+  for (int tile = blockIdx.x; tile < ntiles; tile += gridDim.x) {
+    const int i = tile / tiles_per_i;
+    const int j0 = (tile - i * tiles_per_i) * TJ, j1 = min(j0 + TJ, T1);
+    const int ylo = tabs->i0[1][j0], yhi = tabs->i1[1][j1 - 1];
+    const int n = (yhi - ylo + 1) * Z;
+#pragma unroll
+    for (int a = 0; a < 2; ++a) {
+      const int xa = a ? tabs->i1[0][i] : tabs->i0[0][i];
+      const float* src = rb + ((size_t)xa * Y + ylo) * Z;
+      double* dst = s_in + a * plane;
+      if (((reinterpret_cast<uintptr_t>(src) & 15) == 0) && (n & 3) == 0) {
+        const float4* s4 = reinterpret_cast<const float4*>(src);
+        for (int q = tid; q < (n >> 2); q += nthr) {
+          const float4 v = __ldg(s4 + q);
+          reinterpret_cast<double2*>(dst)[2 * q] = make_double2(scrub(v.x), scrub(v.y));
+          reinterpret_cast<double2*>(dst)[2 * q + 1] = make_double2(scrub(v.z), scrub(v.w));
+        }
+      } else {
+        for (int q = tid; q < n; q += nthr) dst[q] = scrub(__ldg(src + q));
+      }
+    }
+    __syncthreads();
+    const double wx0 = tabs->w0[0][i], wx1 = tabs->w1[0][i];
+    for (int kc = 0; kc < kchunks; ++kc) {
+      const int k = kc * nthr + tid;
+      const bool act = k < T2;
+      int z0 = 0, z1 = 0;
+      double wz0 = 0.0, wz1 = 0.0;
+      if (act) { z0 = tabs->i0[2][k]; z1 = tabs->i1[2][k]; wz0 = tabs->w0[2][k]; wz1 = tabs->w1[2][k]; }
+      uint32_t tile_max = 0;
+      for (int j = j0; j < j1; ++j) {
+        uint32_t key = 0;
+        if (act) {
+          const int y0 = tabs->i0[1][j] - ylo, y1 = tabs->i1[1][j] - ylo;
+          const double wy0 = tabs->w0[1][j], wy1 = tabs->w1[1][j];
+          const double* r00 = s_in + (size_t)y0 * Z;
+          const double* r01 = s_in + (size_t)y1 * Z;
+          const double* r10 = r00 + plane;
+          const double* r11 = r01 + plane;
+          // scipy NI_ZoomShift order: t += ((v*wx)*wy)*wz, taps in (x,y,z) lexicographic order, no FMA contraction
+          double t = 0.0;
+          t = __dadd_rn(t, __dmul_rn(__dmul_rn(__dmul_rn(r00[z0], wx0), wy0), wz0));
+          t = __dadd_rn(t, __dmul_rn(__dmul_rn(__dmul_rn(r00[z1], wx0), wy0), wz1));
+          t = __dadd_rn(t, __dmul_rn(__dmul_rn(__dmul_rn(r01[z0], wx0), wy1), wz0));
+          t = __dadd_rn(t, __dmul_rn(__dmul_rn(__dmul_rn(r01[z1], wx0), wy1), wz1));
+          t = __dadd_rn(t, __dmul_rn(__dmul_rn(__dmul_rn(r10[z0], wx1), wy0), wz0));
+          t = __dadd_rn(t, __dmul_rn(__dmul_rn(__dmul_rn(r10[z1], wx1), wy0), wz1));
+          t = __dadd_rn(t, __dmul_rn(__dmul_rn(__dmul_rn(r11[z0], wx1), wy1), wz0));
+          t = __dadd_rn(t, __dmul_rn(__dmul_rn(__dmul_rn(r11[z1], wx1), wy1), wz1));
+          const float out = __double2float_rn(t);
+          zb[((size_t)i * T1 + j) * T2 + k] = out;
+          key = float_to_ordered(out);
+          tile_max = max(tile_max, key);
+          tmin = min(tmin, key);
+          if (out > 0.0f) atomicAdd(&s_hist[__float_as_uint(out) >> 19], 1u);
+        }
+        const uint32_t wmax = __reduce_max_sync(0xffffffffu, key);
+        if ((tid & 31) == 0 && wmax != 0) atomicMax(&s_jmax[j], wmax);
+      }
+      if (kchunks == 1) kmax0 = max(kmax0, tile_max);
+      else if (act && tile_max != 0) atomicMax(&st->plane_max[2][k], tile_max);
+      const uint32_t imx = __reduce_max_sync(0xffffffffu, tile_max);
+      if ((tid & 31) == 0 && imx != 0) atomicMax(&s_imax[i], imx);
+    }
+    __syncthreads();
+  }
+  if (kchunks == 1 && tid < T2 && kmax0 != 0) atomicMax(&st->plane_max[2][tid], kmax0);
+  const uint32_t wmin = __reduce_min_sync(0xffffffffu, tmin);
+  if ((tid & 31) == 0 && wmin != 0xffffffffu) atomicMin(&st->gmin_key, wmin);
+  __syncthreads();
+  for (int i = tid; i < kH0; i += nthr) {
+    const uint32_t c = s_hist[i];
+    if (c) atomicAdd(&st->hist0[i], c);
+  }
+  for (int i = tid; i < T0; i += nthr) if (s_imax[i]) atomicMax(&st->plane_max[0][i], s_imax[i]);
+  for (int i = tid; i < T1; i += nthr) if (s_jmax[i]) atomicMax(&st->plane_max[1][i], s_jmax[i]);
+}
+
+// Same tile decomposition, but the input rows are streamed by the bulk-copy engine (cp.async.bulk, the 1-D TMA
+// path) into a ring of shared-memory stages while the compute warps work on earlier tiles: warp 0 is the producer
+// (one lane issues two bulk copies per tile and arms the stage's mbarrier with the byte count), the other warps
+// consume.  Needs 16-byte aligned rows (Z % 4 == 0).  Compute threads: [half][k], half = row parity inside the tile.
+constexpr int kResStages = 4;
+
+__device__ __forceinline__ void bulk_load(uint32_t dst, const void* src, uint32_t bytes, uint32_t bar) {
+  asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
+               ::"r"(dst), "l"(reinterpret_cast<uint64_t>(src)), "r"(bytes), "r"(bar) : "memory");
+}
+__device__ __forceinline__ void mbar_arrive(uint32_t bar) {
+  asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(bar) : "memory");
+}
+__device__ __forceinline__ double scrub_bits(float v) {   // nan/inf -> 0, else widen
+  return (fabsf(v) < INFINITY) ? (double)v : 0.0;
+}
+
+__global__ void __launch_bounds__(352)
+resample_tma_kernel(const float* __restrict__ raw, float* __restrict__ zoomed, SubjState* __restrict__ states,
+                    const ZoomTables* __restrict__ tabs, int X, int Y, int Z, int T0, int T1, int T2, int TJ, int NR, int KT) {
+  extern __shared__ __align__(16) unsigned char sm_raw[];
+  const uint32_t stage_bytes = (uint32_t)(2 * NR * Z * 4);
+  float* s_stage = reinterpret_cast<float*>(sm_raw);
+  uint32_t* s_hist = reinterpret_cast<uint32_t*>(sm_raw + (size_t)kResStages * stage_bytes);
+  uint32_t* s_imax = s_hist + kH0;
+  uint32_t* s_jmax = s_imax + T0;
+  uint64_t* s_bar = reinterpret_cast<uint64_t*>(sm_raw + (((size_t)kResStages * stage_bytes + (size_t)(kH0 + T0 + T1) * 4 + 7) & ~(size_t)7));
+  const uint32_t bar_full = smem_u32(s_bar), bar_empty = bar_full + kResStages * 8;
+  const int b = blockIdx.y;
+  const int tid = threadIdx.x, nthr = blockDim.x;
+  const int n_cwarps = (nthr - 32) / 32;
+  for (int i = tid; i < kH0 + T0 + T1; i += nthr) s_hist[i] = 0;
+  if (tid == 0) {
+    for (int s = 0; s < kResStages; ++s) { mbar_init(bar_full + s * 8, 1); mbar_init(bar_empty + s * 8, n_cwarps); }
+    fence_barrier_init();
+  }
+  __syncthreads();
+
+  SubjState* st = states + b;
+  const float* rb = raw + (size_t)b * X * Y * Z;
+  float* zb = zoomed + (size_t)b * T0 * T1 * T2;
+  const int tiles_per_i = (T1 + TJ - 1) / TJ;
+  const int ntiles = T0 * tiles_per_i;
+  const int plane = NR * Z;
+
+  if (tid < 32) {
+    if (tid == 0) {
+      int it = 0;
+      for (int tile = blockIdx.x; tile < ntiles; tile += gridDim.x, ++it) {
+        const int stage = it % kResStages;
+        const uint32_t phase = (uint32_t)(it / kResStages) & 1u;
+        const int i = tile / tiles_per_i;
+        const int j0 = (tile - i * tiles_per_i) * TJ, j1 = min(j0 + TJ, T1);
+        const int ylo = tabs->i0[1][j0], yhi = tabs->i1[1][j1 - 1];
+        const uint32_t bytes = (uint32_t)((yhi - ylo + 1) * Z * 4);
+        mbar_wait(bar_empty + stage * 8, phase ^ 1u);
+        mbar_expect_tx(bar_full + stage * 8, 2 * bytes);
+        const uint32_t dst = smem_u32(s_stage) + stage * stage_bytes;
+        bulk_load(dst, rb + ((size_t)tabs->i0[0][i] * Y + ylo) * Z, bytes, bar_full + stage * 8);
+        bulk_load(dst + plane * 4, rb + ((size_t)tabs->i1[0][i] * Y + ylo) * Z, bytes, bar_full + stage * 8);
+      }
+    }
+  } else {
+    const int ct = tid - 32;
+    const int half = ct / KT, k = ct - half * KT;
     const bool act = k < T2;
     int z0 = 0, z1 = 0;
     double wz0 = 0.0, wz1 = 0.0;
     if (act) { z0 = tabs->i0[2][k]; z1 = tabs->i1[2][k]; wz0 = tabs->w0[2][k]; wz1 = tabs->w1[2][k]; }
-    uint32_t kmax = 0;
-    for (int row = row0; row < row1; ++row) {
-      const int i = row / T1, j = row - i * T1;
-      uint32_t key = 0;
-      if (act) {
-        const int x0 = tabs->i0[0][i], x1 = tabs->i1[0][i];
-        const int y0 = tabs->i0[1][j], y1 = tabs->i1[1][j];
-        const double wx0 = tabs->w0[0][i], wx1 = tabs->w1[0][i];
-        const double wy0 = tabs->w0[1][j], wy1 = tabs->w1[1][j];
-        const float* p00 = rb + ((size_t)x0 * Y + y0) * Z;
-        const float* p01 = rb + ((size_t)x0 * Y + y1) * Z;
-        const float* p10 = rb + ((size_t)x1 * Y + y0) * Z;
-        const float* p11 = rb + ((size_t)x1 * Y + y1) * Z;
-        const double v000 = scrub(__ldg(p00 + z0)), v001 = scrub(__ldg(p00 + z1));
-        const double v010 = scrub(__ldg(p01 + z0)), v011 = scrub(__ldg(p01 + z1));
-        const double v100 = scrub(__ldg(p10 + z0)), v101 = scrub(__ldg(p10 + z1));
-        const double v110 = scrub(__ldg(p11 + z0)), v111 = scrub(__ldg(p11 + z1));
-        // scipy NI_ZoomShift order: t += ((v*wx)*wy)*wz, taps in (x,y,z) lexicographic order, no FMA
-        double t = 0.0;
-        t = __dadd_rn(t, __dmul_rn(__dmul_rn(__dmul_rn(v000, wx0), wy0), wz0));
-        t = __dadd_rn(t, __dmul_rn(__dmul_rn(__dmul_rn(v001, wx0), wy0), wz1));
-        t = __dadd_rn(t, __dmul_rn(__dmul_rn(__dmul_rn(v010, wx0), wy1), wz0));
-        t = __dadd_rn(t, __dmul_rn(__dmul_rn(__dmul_rn(v011, wx0), wy1), wz1));
-        t = __dadd_rn(t, __dmul_rn(__dmul_rn(__dmul_rn(v100, wx1), wy0), wz0));
-        t = __dadd_rn(t, __dmul_rn(__dmul_rn(__dmul_rn(v101, wx1), wy0), wz1));
-        t = __dadd_rn(t, __dmul_rn(__dmul_rn(__dmul_rn(v110, wx1), wy1), wz0));
-        t = __dadd_rn(t, __dmul_rn(__dmul_rn(__dmul_rn(v111, wx1), wy1), wz1));
-        const float out = __double2float_rn(t);
-        zb[(size_t)row * T2 + k] = out;
-        key = float_to_ordered(out);
-        kmax = max(kmax, key);
-        tmin = min(tmin, key);
-        if (out > 0.0f) atomicAdd(&s_hist[__float_as_uint(out) >> 19], 1u);
+    uint32_t tmin = 0xffffffffu, kmax = 0;
+    int it = 0;
+    for (int tile = blockIdx.x; tile < ntiles; tile += gridDim.x, ++it) {
+      const int stage = it % kResStages;
+      const uint32_t phase = (uint32_t)(it / kResStages) & 1u;
+      const int i = tile / tiles_per_i;
+      const int j0 = (tile - i * tiles_per_i) * TJ, j1 = min(j0 + TJ, T1);
+      const int ylo = tabs->i0[1][j0];
+      const double wx0 = tabs->w0[0][i], wx1 = tabs->w1[0][i];
+      const float* sp = s_stage + (size_t)stage * (stage_bytes / 4);
+      mbar_wait(bar_full + stage * 8, phase);
+      uint32_t tile_max = 0;
+      for (int j = j0 + half; j < j1; j += 2) {
+        uint32_t key = 0;
+        if (act) {
+          const int y0 = tabs->i0[1][j] - ylo, y1 = tabs->i1[1][j] - ylo;
+          const double wy0 = tabs->w0[1][j], wy1 = tabs->w1[1][j];
+          const float* r00 = sp + y0 * Z;
+          const float* r01 = sp + y1 * Z;
+          const float* r10 = r00 + plane;
+          const float* r11 = r01 + plane;
+          double t = 0.0;
+          t = __dadd_rn(t, __dmul_rn(__dmul_rn(__dmul_rn(scrub_bits(r00[z0]), wx0), wy0), wz0));
+          t = __dadd_rn(t, __dmul_rn(__dmul_rn(__dmul_rn(scrub_bits(r00[z1]), wx0), wy0), wz1));
+          t = __dadd_rn(t, __dmul_rn(__dmul_rn(__dmul_rn(scrub_bits(r01[z0]), wx0), wy1), wz0));
+          t = __dadd_rn(t, __dmul_rn(__dmul_rn(__dmul_rn(scrub_bits(r01[z1]), wx0), wy1), wz1));
+          t = __dadd_rn(t, __dmul_rn(__dmul_rn(__dmul_rn(scrub_bits(r10[z0]), wx1), wy0), wz0));
+          t = __dadd_rn(t, __dmul_rn(__dmul_rn(__dmul_rn(scrub_bits(r10[z1]), wx1), wy0), wz1));
+          t = __dadd_rn(t, __dmul_rn(__dmul_rn(__dmul_rn(scrub_bits(r11[z0]), wx1), wy1), wz0));
+          t = __dadd_rn(t, __dmul_rn(__dmul_rn(__dmul_rn(scrub_bits(r11[z1]), wx1), wy1), wz1));
+          const float out = __double2float_rn(t);
+          zb[((size_t)i * T1 + j) * T2 + k] = out;
+          key = float_to_ordered(out);
+          tile_max = max(tile_max, key);
+          tmin = min(tmin, key);
+          if (out > 0.0f) atomicAdd(&s_hist[__float_as_uint(out) >> 19], 1u);
+        }
+        const uint32_t wmax = __reduce_max_sync(0xffffffffu, key);
+        if ((tid & 31) == 0 && wmax != 0) atomicMax(&s_jmax[j], wmax);
       }
-      const uint32_t wmax = __reduce_max_sync(0xffffffffu, key);
-      if ((tid & 31) == 0 && wmax != 0) {
-        atomicMax(&s_imax[i], wmax);
-        atomicMax(&s_jmax[j], wmax);
-      }
+      __syncwarp();
+      if ((tid & 31) == 0) mbar_arrive(bar_empty + stage * 8);    // this warp is done reading the stage
+      kmax = max(kmax, tile_max);
+      const uint32_t imx = __reduce_max_sync(0xffffffffu, tile_max);
+      if ((tid & 31) == 0 && imx != 0) atomicMax(&s_imax[i], imx);
     }
     if (act && kmax != 0) atomicMax(&st->plane_max[2][k], kmax);
+    const uint32_t wmin = __reduce_min_sync(0xffffffffu, tmin);
+    if ((tid & 31) == 0 && wmin != 0xffffffffu) atomicMin(&st->gmin_key, wmin);
   }
-  const uint32_t wmin = __reduce_min_sync(0xffffffffu, tmin);
-  if ((tid & 31) == 0 && wmin != 0xffffffffu) atomicMin(&st->gmin_key, wmin);
   __syncthreads();
-  for (int i = tid; i < kH0; i += blockDim.x) {
+  for (int i = tid; i < kH0; i += nthr) {
     const uint32_t c = s_hist[i];
     if (c) atomicAdd(&st->hist0[i], c);
   }
-  for (int i = tid; i < kPlaneMax; i += blockDim.x) {
-    if (s_imax[i]) atomicMax(&st->plane_max[0][i], s_imax[i]);
-    if (s_jmax[i]) atomicMax(&st->plane_max[1][i], s_jmax[i]);
-  }
+  for (int i = tid; i < T0; i += nthr) if (s_imax[i]) atomicMax(&st->plane_max[0][i], s_imax[i]);
+  for (int i = tid; i < T1; i += nthr) if (s_jmax[i]) atomicMax(&st->plane_max[1][i], s_jmax[i]);
 }
 
 // ------------------------------------------------------------------------------------------------------
@@ -451,7 +602,8 @@ struct ResizeArgs {
   int axes[PDF_MAX_AXES];
   int counts[PDF_MAX_AXES];
   int lmax, S, cnt2;
-  float mean[3], stdv[3];
+  float mean[3], inv_std[3];
+  float scale_sq;   // T/S when the slice is square (the usual cubic target), hoisted out of the kernel
 };
 
 template <int MODE>
@@ -482,30 +634,32 @@ resize_kernel(const float* __restrict__ zoomed, const float* __restrict__ planes
   else if (axis == 1) { src = zoomed + (size_t)b * T0 * T1 * T2 + (size_t)idx * T2; H = T0; W = T2; rs = (size_t)T1 * T2; }
   else { src = planes + ((size_t)b * ra.cnt2 + off2 + t) * T0 * T1; H = T0; W = T1; rs = T1; }
   const float* l4 = lohi + 4 * (size_t)b;
-  const float lo = l4[0], hi = l4[1], den = l4[2];
+  const float lo = l4[0], hi = l4[1];
+  const float inv_den = __frcp_rn(l4[2]);          // network input is a 1e-5-tolerance quantity: reciprocal multiply
   const int oy = pix / S, ox = pix - oy * S;
   // ATen area_pixel_compute_source_index(align_corners=False): (dst + 0.5) * (in/out) - 0.5, clamped at 0
-  const float sh = __fdiv_rn((float)H, (float)S), sw = __fdiv_rn((float)W, (float)S);
+  const float sh = (H == W) ? ra.scale_sq : __fdiv_rn((float)H, (float)S);
+  const float sw = (H == W) ? ra.scale_sq : __fdiv_rn((float)W, (float)S);
   const float fy = fmaxf(__fsub_rn(__fmul_rn(__fadd_rn((float)oy, 0.5f), sh), 0.5f), 0.0f);
   const float fx = fmaxf(__fsub_rn(__fmul_rn(__fadd_rn((float)ox, 0.5f), sw), 0.5f), 0.0f);
   const int y0 = min((int)fy, H - 1), x0 = min((int)fx, W - 1);
   const int y1 = min(y0 + 1, H - 1), x1 = min(x0 + 1, W - 1);
   const float wy1 = __fsub_rn(fy, (float)y0), wx1 = __fsub_rn(fx, (float)x0);
   const float wy0 = __fsub_rn(1.0f, wy1), wx0 = __fsub_rn(1.0f, wx1);
-  const float v00 = normalise(__ldg(src + y0 * rs + x0), lo, hi, den);
-  const float v01 = normalise(__ldg(src + y0 * rs + x1), lo, hi, den);
-  const float v10 = normalise(__ldg(src + y1 * rs + x0), lo, hi, den);
-  const float v11 = normalise(__ldg(src + y1 * rs + x1), lo, hi, den);
+  const float v00 = (fminf(fmaxf(__ldg(src + y0 * rs + x0), lo), hi) - lo) * inv_den;
+  const float v01 = (fminf(fmaxf(__ldg(src + y0 * rs + x1), lo), hi) - lo) * inv_den;
+  const float v10 = (fminf(fmaxf(__ldg(src + y1 * rs + x0), lo), hi) - lo) * inv_den;
+  const float v11 = (fminf(fmaxf(__ldg(src + y1 * rs + x1), lo), hi) - lo) * inv_den;
   const float top = __fadd_rn(__fmul_rn(wx0, v00), __fmul_rn(wx1, v01));
   const float bot = __fadd_rn(__fmul_rn(wx0, v10), __fmul_rn(wx1, v11));
   const float r = __fadd_rn(__fmul_rn(wy0, top), __fmul_rn(wy1, bot));
   if (MODE == PDF_OUT_BF16_C1) {
-    reinterpret_cast<__nv_bfloat16*>(out)[opix] = __float2bfloat16(__fdiv_rn(__fsub_rn(r, ra.mean[0]), ra.stdv[0]));
+    reinterpret_cast<__nv_bfloat16*>(out)[opix] = __float2bfloat16((r - ra.mean[0]) * ra.inv_std[0]);
   } else {
     float* o = reinterpret_cast<float*>(out) + opix * 3;
-    o[0] = __fdiv_rn(__fsub_rn(r, ra.mean[0]), ra.stdv[0]);
-    o[1] = __fdiv_rn(__fsub_rn(r, ra.mean[1]), ra.stdv[1]);
-    o[2] = __fdiv_rn(__fsub_rn(r, ra.mean[2]), ra.stdv[2]);
+    o[0] = (r - ra.mean[0]) * ra.inv_std[0];
+    o[1] = (r - ra.mean[1]) * ra.inv_std[1];
+    o[2] = (r - ra.mean[2]) * ra.inv_std[2];
   }
 }
 
@@ -532,14 +686,53 @@ extern "C" int pdf_resample_stats(const pdf_preproc_cfg* cfg, int batch, const f
   const int tmax = max(max(T0, T1), max(T2, batch));
   init_tables_kernel<<<ceil_div(tmax, 256), 256, 0, s>>>(w.tabs, w.st, batch, X, Y, Z, T0, T1, T2);
   PDF_CHECK_LAUNCH();
-  const int threads = min(1024, (T2 + 31) / 32 * 32);
-  const int nrows = T0 * T1;
-  // ~2 waves of blocks over the chip for the whole batch, but at least 8 rows per block
-  int blocks_per_subject = max(1, min(nrows / 8, ceil_div(num_sms() * 12, batch)));
-  const int rows_per_block = ceil_div(nrows, blocks_per_subject);
-  blocks_per_subject = ceil_div(nrows, rows_per_block);
-  resample_kernel<<<dim3(blocks_per_subject, batch), threads, 0, s>>>(d_raw, d_zoomed, w.st, w.tabs, X, Y, Z, T0, T1, T2,
-                                                                      rows_per_block);
+  const double ystep = (double)(Y - 1) / (double)(T1 - 1);
+  const size_t fixed = (size_t)(kH0 + T0 + T1) * sizeof(uint32_t);
+  const int KT = (T2 + 31) / 32 * 32;
+  const bool tma_ok = (Z % 4 == 0) && ((reinterpret_cast<uintptr_t>(d_raw) & 15) == 0) && KT <= 160 && T1 >= 2;
+  if (tma_ok) {
+    // bulk-copy pipeline: 8 output rows per tile, kResStages stages of 2 x NR x Z floats
+    int TJ = 8, NR = 0;
+    size_t smem = 0;
+    for (; TJ >= 2; TJ >>= 1) {
+      NR = (int)((TJ - 1) * ystep) + 3;
+      smem = (size_t)kResStages * 2 * NR * Z * 4 + fixed + 8 + 2 * kResStages * 8 + 128;
+      if (smem <= 110 * 1024) break;
+    }
+    if (TJ >= 2 && smem <= 200 * 1024) {
+      static size_t configured = 0;
+      if (smem > configured) {
+        PDF_CHECK_CUDA(cudaFuncSetAttribute(resample_tma_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        configured = smem;
+      }
+      const int ntiles = T0 * ceil_div(T1, TJ);
+      const int per_sm = max(1, min(4, (int)((220 * 1024) / (smem + 1024))));
+      const int blocks_per_subject = max(1, min(ntiles, ceil_div(num_sms() * per_sm, batch)));
+      resample_tma_kernel<<<dim3(blocks_per_subject, batch), 32 + 2 * KT, smem, s>>>(d_raw, d_zoomed, w.st, w.tabs, X, Y, Z, T0, T1,
+                                                                                     T2, TJ, NR, KT);
+      PDF_CHECK_LAUNCH();
+      return PDF_OK;
+    }
+  }
+  const int threads = min(256, (T2 + 31) / 32 * 32);
+  // rows per tile: as many as fit the shared-memory staging buffer (2 planes x NR input rows x Z doubles)
+  int TJ = 8, NR = 0;
+  size_t smem = 0;
+  for (; TJ >= 1; TJ >>= 1) {
+    NR = (int)((TJ - 1) * ystep) + 3;
+    smem = 2 * (((size_t)NR * Z + 1) & ~(size_t)1) * sizeof(double) + fixed;
+    if (smem <= 72 * 1024 || TJ == 1) break;
+  }
+  PDF_REQUIRE(smem <= 200 * 1024, "pdf_resample_stats: volume rows too long for the shared-memory staging buffer (Z=%d)", Z);
+  static size_t configured = 0;
+  if (smem > configured) {
+    PDF_CHECK_CUDA(cudaFuncSetAttribute(resample_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    configured = smem;
+  }
+  const int ntiles = T0 * ceil_div(T1, TJ);
+  const int per_sm = max(1, min(8, (int)((220 * 1024) / (smem + 1024))));
+  const int blocks_per_subject = max(1, min(ntiles, ceil_div(num_sms() * per_sm, batch)));
+  resample_kernel<<<dim3(blocks_per_subject, batch), threads, smem, s>>>(d_raw, d_zoomed, w.st, w.tabs, X, Y, Z, T0, T1, T2, TJ, NR);
   PDF_CHECK_LAUNCH();
   return PDF_OK;
 }
@@ -592,7 +785,8 @@ extern "C" int pdf_gather_resize_normalize(const pdf_preproc_cfg* cfg, int batch
   ra.n_axes = cfg->n_axes;
   ra.S = cfg->input_size;
   ra.cnt2 = count_axis2(cfg);
-  for (int i = 0; i < 3; ++i) { ra.T[i] = cfg->out_shape[i]; ra.mean[i] = cfg->mean[i]; ra.stdv[i] = cfg->std[i]; }
+  for (int i = 0; i < 3; ++i) { ra.T[i] = cfg->out_shape[i]; ra.mean[i] = cfg->mean[i]; ra.inv_std[i] = 1.0f / cfg->std[i]; }
+  ra.scale_sq = (float)cfg->out_shape[0] / (float)ra.S;
   for (int a = 0; a < PDF_MAX_AXES; ++a) {
     ra.axes[a] = a < cfg->n_axes ? cfg->axes[a] : 0;
     ra.counts[a] = a < cfg->n_axes ? cfg->counts[a] : 0;

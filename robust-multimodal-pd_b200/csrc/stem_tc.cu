@@ -2,7 +2,7 @@
 // max-pool in ONE kernel.  Per CTA: a 7x7 tile of pooled pixels <- 15x15 conv pixels <- 35x35 input patch.
 //
 //   1. input patch (bf16, zero padded) -> shared memory
-//   2. the 225 x 64 im2col matrix (49 taps + 15 zero columns) is BUILT in shared memory in the K-major
+//   2. the 225 x 64 im2col matrix (K = r*8+s: 49 taps + 15 zero columns) is BUILT in shared memory in the K-major
 //      SWIZZLE_128B layout the tensor core reads (never touches HBM); weights [64 x 64] likewise
 //   3. 2 x 4 tcgen05.mma (M=128, N=64, K=16) -> two f32 accumulators in TMEM
 //   4. epilogue: tcgen05.ld -> +bias, ReLU -> bf16 conv tile in shared memory (overlays the A matrix)
@@ -24,7 +24,7 @@ constexpr int kConvPix = kCT * kCT;  // 225 valid rows of the 256-row A matrix
 
 struct StemParams {
   const __nv_bfloat16* in;    // [n, S, S]
-  const __nv_bfloat16* w;     // [64, 64]  (cout, tap; taps >= 49 are zero)
+  const __nv_bfloat16* w;     // [64, 64]  (cout, r*8+s; s = 7 and r = 7 columns are zero)
   const float* bias;          // [64]
   __nv_bfloat16* out;         // [n, P, P, 64]
   int S, H1, P, tiles;
@@ -69,25 +69,17 @@ stem_fused_kernel(const StemParams p) {
     *reinterpret_cast<uint4*>(sW + r * 128 + ((c ^ (r & 7)) << 4)) = v;
   }
   __syncthreads();
-  // 2b. im2col rows
+  // 2b. im2col rows.  K index = r*8 + s (s = 7 is a zero column, r = 7 a zero chunk): chunk c of row m is the 7 taps of
+  //     filter row c, i.e. 8 consecutive bf16 of the patch starting at an even column -> four aligned 32-bit loads.
   for (int i = tid; i < 256 * 8; i += 256) {
     const int m = i >> 3, c = i & 7;
-    __align__(16) __nv_bfloat16 v[8];
-#pragma unroll
-    for (int e = 0; e < 8; ++e) v[e] = __float2bfloat16(0.f);
-    if (m < kConvPix) {
+    uint4 v = make_uint4(0u, 0u, 0u, 0u);
+    if (m < kConvPix && c < 7) {
       const int cy = m / kCT, cx = m - cy * kCT;
-      const __nv_bfloat16* src = sIn + (2 * cy) * kITP + 2 * cx;
-#pragma unroll
-      for (int e = 0; e < 8; ++e) {
-        const int k = c * 8 + e;
-        if (k < 49) {
-          const int r = k / 7, s = k - r * 7;
-          v[e] = src[r * kITP + s];
-        }
-      }
+      const uint32_t* src = reinterpret_cast<const uint32_t*>(sIn + (2 * cy + c) * kITP + 2 * cx);
+      v = make_uint4(src[0], src[1], src[2], src[3] & 0x0000ffffu);
     }
-    *reinterpret_cast<uint4*>(sA + m * 128 + ((c ^ (m & 7)) << 4)) = *reinterpret_cast<const uint4*>(v);
+    *reinterpret_cast<uint4*>(sA + m * 128 + ((c ^ (m & 7)) << 4)) = v;
   }
   fence_proxy_async();          // generic-proxy smem writes -> visible to the tensor core (async proxy)
   tc_fence_before();

@@ -201,8 +201,9 @@ class ResNetEncoder:
             wf = w * scale.view(-1, 1, 1, 1)
             if cv["role"] == "stem":
                 w1 = wf.sum(dim=1)                                      # [64, 7, 7]: 3 identical channels folded
-                mat = torch.zeros(w1.shape[0], 64, dtype=torch.float64)
-                mat[:, :49] = w1.reshape(w1.shape[0], 49)
+                mat = torch.zeros(w1.shape[0], 8, 8, dtype=torch.float64)      # K index = r*8 + s (stem_tc.cu)
+                mat[:, :7, :7] = w1
+                mat = mat.reshape(w1.shape[0], 64)
                 return self._dev(mat.to(torch.bfloat16)), None, self._dev(shift.float())
             return self._dev(wf.permute(0, 2, 3, 1).to(torch.bfloat16)), None, self._dev(shift.float())   # [K,R,S,C]
         return self._dev(w.permute(2, 3, 1, 0).float()), self._dev(scale.float()), self._dev(shift.float())  # [R,S,C,K]

@@ -61,6 +61,45 @@ class EmbeddingPipeline:
                                            _lib.stream_ptr()), "pdf_slice_mean")
         return EmbedResult(emb[:B], self.mean_out[:B], res.indices, res.nslices)
 
+    def embed_host(self, host_batches, out_bags: bool = False):
+        """End-to-end path for volumes that live in (pinned) HOST memory: iterates over `host_batches` (tensors
+        [B, X, Y, Z] f32), overlapping the H2D copy of batch i+1 (copy stream, second device buffer) with the kernels
+        of batch i, and returns a list of host tensors (slice-mean embeddings [B, D], or the bags [B, L, D])."""
+        main = torch.cuda.current_stream(self.device)
+        if not hasattr(self, "_copy_stream"):
+            self._copy_stream = torch.cuda.Stream(self.device)
+            self._raw = [torch.empty((self.max_subjects,) + self.pre.in_shape, dtype=torch.float32, device=self.device) for _ in range(2)]
+            self._ev_copy = [torch.cuda.Event() for _ in range(2)]
+            self._ev_free = [torch.cuda.Event() for _ in range(2)]
+        cs = self._copy_stream
+        batches = list(host_batches)
+        outs = []
+
+        def start_copy(i):
+            slot = i & 1
+            with torch.cuda.stream(cs):
+                cs.wait_event(self._ev_free[slot])
+                self._raw[slot][: batches[i].shape[0]].copy_(batches[i], non_blocking=True)
+                self._ev_copy[slot].record(cs)
+
+        for ev in self._ev_free:
+            ev.record(main)
+        if batches:
+            start_copy(0)
+        for i, hb in enumerate(batches):
+            slot, B = i & 1, int(hb.shape[0])
+            if i + 1 < len(batches):
+                start_copy(i + 1)
+            main.wait_event(self._ev_copy[slot])
+            res = self.embed(self._raw[slot][:B])
+            self._ev_free[slot].record(main)
+            src = res.embeddings if out_bags else res.mean
+            host = torch.empty(src.shape, dtype=torch.float32).pin_memory()
+            host.copy_(src, non_blocking=True)
+            outs.append(host)
+        main.synchronize()
+        return outs
+
     def algorithmic_bytes_per_subject(self) -> int:
         return self.pre.algorithmic_bytes()
 

@@ -275,6 +275,21 @@ static int encode_im2col(TensorMapBlob* out, const pdf_op& op) {
   return PDF_OK;
 }
 
+// NHWC activation as a 4-D tiled map whose box is NR full padded rows (W+2 columns) of one image, 64 channels
+static int encode_halo(TensorMapBlob* out, const pdf_op& op, int Wp, int NR) {
+  const cuuint64_t dims[4] = {(cuuint64_t)op.c, (cuuint64_t)op.w, (cuuint64_t)op.h, (cuuint64_t)op.n};
+  const cuuint64_t strides[3] = {(cuuint64_t)op.c * 2, (cuuint64_t)op.w * op.c * 2, (cuuint64_t)op.h * op.w * op.c * 2};
+  const cuuint32_t box[4] = {(cuuint32_t)kBlockK, (cuuint32_t)Wp, (cuuint32_t)NR, 1};
+  const cuuint32_t estr[4] = {1, 1, 1, 1};
+  CUresult r = g_encode_tiled(reinterpret_cast<CUtensorMap*>(out), CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 4, const_cast<void*>(op.d_in), dims,
+                              strides, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B,
+                              CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  PDF_REQUIRE(r == CUDA_SUCCESS, "cuTensorMapEncodeTiled(4d halo) failed (%d) nhwc=%d,%d,%d,%d box=%d,%d", (int)r, op.n, op.h, op.w, op.c, Wp, NR);
+  return PDF_OK;
+}
+
+static bool g_disable_halo = false;
+
 int prepare_conv_tc(const pdf_op& op, TcConv* tc) {
   if (int rc = load_driver_entry_points()) return rc;
   PDF_REQUIRE(op.c % kBlockK == 0, "bf16 conv: Cin (%d) must be a multiple of 64", op.c);
@@ -290,6 +305,14 @@ int prepare_conv_tc(const pdf_op& op, TcConv* tc) {
   tc->Cout = op.k; tc->Ho = op.ho; tc->Wo = op.wo; tc->stride = op.stride; tc->pad = op.pad; tc->R = op.r; tc->S = op.s;
   tc->cchunks = op.c / kBlockK;
   tc->relu = op.relu; tc->bias = op.d_bias; tc->residual = op.d_residual; tc->out = op.d_out; tc->out_f32 = op.out_f32;
+  tc->n_images = op.n;
+  tc->halo = (!g_disable_halo && !op.out_f32 && op.d_bias && halo_eligible(op)) ? 1 : 0;
+  if (tc->halo) {
+    tc->halo_wp = op.w + 2;
+    tc->halo_nr = (tc->halo_wp - 1 + 255) / tc->halo_wp + 3;
+    if (int rc = encode_halo(&tc->tmap_a, op, tc->halo_wp, tc->halo_nr)) return rc;
+    return encode_2d(&tc->tmap_b, op.d_weight, (uint64_t)op.k, (uint64_t)op.r * op.s * op.c, 64);
+  }
   if (tc->im2col) {
     if (int rc = encode_im2col(&tc->tmap_a, op)) return rc;
   } else {
@@ -318,6 +341,7 @@ static int launch_tc(const TcConv& tc, cudaStream_t s) {
 }
 
 int launch_conv_tc(const TcConv& tc, cudaStream_t s) {
+  if (tc.halo) return launch_conv3x3_halo(tc, s);
   switch (tc.block_n) {
     case 256: return launch_tc<256, 4>(tc, s);
     case 128: return launch_tc<128, 3>(tc, s);   // 96 KB/CTA -> two CTAs per SM
@@ -356,5 +380,11 @@ extern "C" int pdf_selftest_umma_shift(int N, int shift, int mode, const void* d
   umma_shift_kernel<64><<<1, 128, smem, as_stream(stream)>>>(*reinterpret_cast<const CUtensorMap*>(&ta),
                                                              *reinterpret_cast<const CUtensorMap*>(&tb), shift, mode, d_c);
   PDF_CHECK_LAUNCH();
+  return PDF_OK;
+}
+
+/* test hook: 1 = route 3x3 s1 64->64 convs through the generic im2col kernel (A/B comparison of the halo kernel) */
+extern "C" int pdf_debug_disable_halo(int disable) {
+  pdf::g_disable_halo = disable != 0;
   return PDF_OK;
 }

@@ -22,9 +22,13 @@ struct TcConv {
   const void* residual;   // bf16 [M, Cout]
   void* out;              // bf16 [M, Cout] or f32 when out_f32
   int out_f32;
+  int halo;               // 1: halo-resident 3x3 kernel (conv3x3_tc.cu); tmap_a is then a 4-D tiled map
+  int halo_wp, halo_nr, n_images;
 };
 
 int prepare_conv_tc(const pdf_op& op, TcConv* out);
 int launch_conv_tc(const TcConv& tc, cudaStream_t s);
+bool halo_eligible(const pdf_op& op);
+int launch_conv3x3_halo(const TcConv& tc, cudaStream_t s);
 
 }  // namespace pdf

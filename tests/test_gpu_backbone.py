@@ -146,3 +146,38 @@ def test_umma_shifted_descriptor_probe():
             f.write(f"mode {mode}: " + " ".join(f"{s}:{'ok' if v else 'BAD'}" for (m, s), v in res.items() if m == mode) + "\n")
     print(open("gpurun_out/umma_shift_probe.txt").read())
     assert res[(0, 0)] and res[(0, 8)] and res[(0, 128)]      # 1024-byte aligned starts must work
+
+
+@pytest.mark.parametrize("n,h,res", [(3, 56, True), (2, 28, False), (5, 17, True), (1, 9, False), (40, 56, True)])
+def test_halo_conv_matches_im2col_conv(n, h, res):
+    """conv3x3_c64_kernel (halo loaded once, 9 shifted descriptors, resident weights, persistent CTAs) vs the generic
+    im2col-TMA kernel on the same bf16 data."""
+    import ctypes as C
+    lib = _lib.load()
+    g = torch.Generator().manual_seed(n * 100 + h)
+    x = (torch.randn(n, h, h, 64, generator=g) * 0.5).to(torch.bfloat16).cuda()
+    w = (torch.randn(64, 3, 3, 64, generator=g) / 24.0).to(torch.bfloat16).cuda()
+    bias = torch.randn(64, generator=g).cuda()
+    resid = (torch.randn(n, h, h, 64, generator=g) * 0.5).to(torch.bfloat16).cuda() if res else None
+    outs = []
+    for disable in (0, 1):
+        lib.pdf_debug_disable_halo(disable)
+        out = torch.full((n, h, h, 64), float("nan"), dtype=torch.bfloat16, device="cuda")
+        ops = (_lib.Op * 1)()
+        o = ops[0]
+        o.kind, o.precision = _lib.OP_CONV, _lib.PREC_BF16
+        o.n, o.h, o.w, o.c, o.k, o.r, o.s, o.stride, o.pad, o.ho, o.wo, o.relu = n, h, h, 64, 64, 3, 3, 1, 1, h, h, 1
+        o.d_in, o.d_weight, o.d_bias, o.d_out = x.data_ptr(), w.data_ptr(), bias.data_ptr(), out.data_ptr()
+        o.d_residual = resid.data_ptr() if res else None
+        plan = C.c_void_p()
+        try:
+            _lib.check(lib.pdf_plan_create(C.byref(plan), ops, 1))
+            _lib.check(lib.pdf_plan_run(plan, _lib.stream_ptr()))
+            torch.cuda.synchronize()
+        finally:
+            lib.pdf_debug_disable_halo(0)
+        lib.pdf_plan_destroy(plan)
+        outs.append(out.float().cpu())
+    assert not torch.isnan(outs[0]).any()
+    err = (outs[0] - outs[1]).abs().max().item()
+    assert err <= 1e-2 * max(1.0, outs[1].abs().max().item()), err

@@ -116,19 +116,31 @@ conv3x3_c64_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_cons
       const uint32_t accphase = (uint32_t)(it >> 1) & 1u;
       const int n = tile / p.tiles_per_image;
       const int m0 = (tile - n * p.tiles_per_image) * kHaloBM;
-      mbar_wait(bar_accfull + 8 * acc, accphase);
-      tc_fence_after();
-#pragma unroll 1
+      // residual rows of both halves are fetched BEFORE waiting on the accumulator: their latency hides behind the MMAs
+      uint4 res[2][8];
+      bool valid[2];
+      size_t obase[2];
+#pragma unroll
       for (int half = 0; half < 2; ++half) {
         const int m = m0 + half * 128 + quad * 32 + lane;
         const int pp = m / p.Wp, qq = m - pp * p.Wp;
-        const bool valid = pp < p.H && qq < p.W;
-        const size_t o = (((size_t)n * p.H + pp) * p.W + qq) * 64;
+        valid[half] = pp < p.H && qq < p.W;
+        obase[half] = (((size_t)n * p.H + pp) * p.W + qq) * 64;
+        if (p.residual && valid[half]) {
+          const uint4* rp = reinterpret_cast<const uint4*>(p.residual + obase[half]);
+#pragma unroll
+          for (int i = 0; i < 8; ++i) res[half][i] = __ldg(rp + i);
+        }
+      }
+      mbar_wait(bar_accfull + 8 * acc, accphase);
+      tc_fence_after();
+#pragma unroll
+      for (int half = 0; half < 2; ++half) {
 #pragma unroll
         for (int c0 = 0; c0 < 64; c0 += 32) {
           uint32_t v[32];
           tmem_ld32(tmem_base + ((uint32_t)(quad * 32) << 16) + (uint32_t)(acc * 128 + half * 64 + c0), v);
-          if (valid) {
+          if (valid[half]) {
             float f[32];
 #pragma unroll
             for (int i = 0; i < 32; i += 4) {
@@ -137,10 +149,9 @@ conv3x3_c64_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_cons
               f[i + 2] = __uint_as_float(v[i + 2]) + b.z; f[i + 3] = __uint_as_float(v[i + 3]) + b.w;
             }
             if (p.residual) {
-              const uint4* rp = reinterpret_cast<const uint4*>(p.residual + o + c0);
 #pragma unroll
               for (int i = 0; i < 4; ++i) {
-                const uint4 r = __ldg(rp + i);
+                const uint4 r = res[half][(c0 >> 3) + i];
                 const __nv_bfloat162* h = reinterpret_cast<const __nv_bfloat162*>(&r);
 #pragma unroll
                 for (int j = 0; j < 4; ++j) {
@@ -154,7 +165,7 @@ conv3x3_c64_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_cons
 #pragma unroll
               for (int i = 0; i < 32; ++i) f[i] = fmaxf(f[i], 0.f);
             }
-            uint4* op = reinterpret_cast<uint4*>(p.out + o + c0);
+            uint4* op = reinterpret_cast<uint4*>(p.out + obase[half] + c0);
 #pragma unroll
             for (int i = 0; i < 4; ++i) {
               uint4 ov;

@@ -299,15 +299,22 @@ resample_tma_kernel(const float* __restrict__ raw, float* __restrict__ zoomed, S
           const float* r01 = sp + y1 * Z;
           const float* r10 = r00 + plane;
           const float* r11 = r01 + plane;
+          const float f000 = r00[z0], f001 = r00[z1], f010 = r01[z0], f011 = r01[z1];
+          const float f100 = r10[z0], f101 = r10[z1], f110 = r11[z0], f111 = r11[z1];
+          // background fast path: eight (+-)0 taps give exactly +0.0 in scipy's sum, no float64 work needed
+          const uint32_t any = (__float_as_uint(f000) | __float_as_uint(f001) | __float_as_uint(f010) | __float_as_uint(f011) |
+                                __float_as_uint(f100) | __float_as_uint(f101) | __float_as_uint(f110) | __float_as_uint(f111)) & 0x7fffffffu;
           double t = 0.0;
-          t = __dadd_rn(t, __dmul_rn(__dmul_rn(__dmul_rn(scrub_bits(r00[z0]), wx0), wy0), wz0));
-          t = __dadd_rn(t, __dmul_rn(__dmul_rn(__dmul_rn(scrub_bits(r00[z1]), wx0), wy0), wz1));
-          t = __dadd_rn(t, __dmul_rn(__dmul_rn(__dmul_rn(scrub_bits(r01[z0]), wx0), wy1), wz0));
-          t = __dadd_rn(t, __dmul_rn(__dmul_rn(__dmul_rn(scrub_bits(r01[z1]), wx0), wy1), wz1));
-          t = __dadd_rn(t, __dmul_rn(__dmul_rn(__dmul_rn(scrub_bits(r10[z0]), wx1), wy0), wz0));
-          t = __dadd_rn(t, __dmul_rn(__dmul_rn(__dmul_rn(scrub_bits(r10[z1]), wx1), wy0), wz1));
-          t = __dadd_rn(t, __dmul_rn(__dmul_rn(__dmul_rn(scrub_bits(r11[z0]), wx1), wy1), wz0));
-          t = __dadd_rn(t, __dmul_rn(__dmul_rn(__dmul_rn(scrub_bits(r11[z1]), wx1), wy1), wz1));
+          if (any != 0) {
+            t = __dadd_rn(t, __dmul_rn(__dmul_rn(__dmul_rn(scrub_bits(f000), wx0), wy0), wz0));
+            t = __dadd_rn(t, __dmul_rn(__dmul_rn(__dmul_rn(scrub_bits(f001), wx0), wy0), wz1));
+            t = __dadd_rn(t, __dmul_rn(__dmul_rn(__dmul_rn(scrub_bits(f010), wx0), wy1), wz0));
+            t = __dadd_rn(t, __dmul_rn(__dmul_rn(__dmul_rn(scrub_bits(f011), wx0), wy1), wz1));
+            t = __dadd_rn(t, __dmul_rn(__dmul_rn(__dmul_rn(scrub_bits(f100), wx1), wy0), wz0));
+            t = __dadd_rn(t, __dmul_rn(__dmul_rn(__dmul_rn(scrub_bits(f101), wx1), wy0), wz1));
+            t = __dadd_rn(t, __dmul_rn(__dmul_rn(__dmul_rn(scrub_bits(f110), wx1), wy1), wz0));
+            t = __dadd_rn(t, __dmul_rn(__dmul_rn(__dmul_rn(scrub_bits(f111), wx1), wy1), wz1));
+          }
           const float out = __double2float_rn(t);
           zb[((size_t)i * T1 + j) * T2 + k] = out;
           key = float_to_ordered(out);
@@ -707,7 +714,8 @@ extern "C" int pdf_resample_stats(const pdf_preproc_cfg* cfg, int batch, const f
       }
       const int ntiles = T0 * ceil_div(T1, TJ);
       const int per_sm = max(1, min(4, (int)((220 * 1024) / (smem + 1024))));
-      const int blocks_per_subject = max(1, min(ntiles, ceil_div(num_sms() * per_sm, batch)));
+      // one resident wave: never more blocks than the chip holds at once (a second partial wave would double the time)
+      const int blocks_per_subject = max(1, min(ntiles, (num_sms() * per_sm) / batch));
       resample_tma_kernel<<<dim3(blocks_per_subject, batch), 32 + 2 * KT, smem, s>>>(d_raw, d_zoomed, w.st, w.tabs, X, Y, Z, T0, T1,
                                                                                      T2, TJ, NR, KT);
       PDF_CHECK_LAUNCH();

@@ -22,40 +22,49 @@ struct TcParams {
   void* out;
 };
 
-template <int BLOCK_N, int STAGES>
+template <int BLOCK_N, int STAGES, int MT>
 struct SmemLayout {
   static constexpr int kBBytes = BLOCK_N * kBlockK * 2;
-  static constexpr int kStage = kABytes + kBBytes;
+  static constexpr int kStage = MT * kABytes + kBBytes;
   static constexpr int kBarOff = STAGES * kStage;
-  static constexpr int kTotal = kBarOff + (2 * STAGES + 1) * 8 + 8;
-  static constexpr int kDynamic = kTotal + 1024;  // slack for manual 1024-byte alignment
+  static constexpr int kNumBars = 2 * STAGES + 4;               // full/empty ring + acc_full[2] + acc_empty[2]
+  static constexpr int kTotal = kBarOff + kNumBars * 8 + 8;
+  static constexpr int kDynamic = kTotal + 1024;                // slack for manual 1024-byte alignment
+  static constexpr int kAccCols = MT * BLOCK_N;                 // TMEM columns of one accumulator set
+  static_assert(2 * kAccCols <= 512, "two accumulator sets must fit the 512 TMEM columns");
 };
 
-template <int BLOCK_N, int STAGES>
+// Persistent, warp-specialised implicit-GEMM convolution.
+//   MT   128-row M sub-tiles per tile (each with its own accumulator) sharing one B tile per k-block
+//   two TMEM accumulator sets: the epilogue of tile t overlaps the TMA/MMA mainloop of tile t+1; the smem ring keeps
+//   running across tiles.  Tiles are assigned round-robin (tile = blockIdx.x + i*gridDim.x), m fastest inside an n-tile
+//   so that neighbouring CTAs share the weight tile in L2.
+template <int BLOCK_N, int STAGES, int MT>
 __global__ void __launch_bounds__(192)
 conv_tc_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant__ CUtensorMap tmap_b, const TcParams p) {
-  using L = SmemLayout<BLOCK_N, STAGES>;
+  using L = SmemLayout<BLOCK_N, STAGES, MT>;
   extern __shared__ uint8_t smem_raw[];
   const uint32_t raw_addr = smem_u32(smem_raw);
   const uint32_t base = (raw_addr + 1023u) & ~1023u;          // SWIZZLE_128B tiles need 1024-byte alignment
   uint8_t* smem = smem_raw + (base - raw_addr);
   const uint32_t bar_full = base + L::kBarOff;
   const uint32_t bar_empty = bar_full + STAGES * 8;
-  const uint32_t bar_acc = bar_empty + STAGES * 8;
-  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(smem + L::kBarOff + (2 * STAGES + 1) * 8);
+  const uint32_t bar_accfull = bar_empty + STAGES * 8;
+  const uint32_t bar_accempty = bar_accfull + 16;
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(smem + L::kBarOff + L::kNumBars * 8);
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  const int m0 = blockIdx.x * kBlockM;
-  const int n0 = blockIdx.y * BLOCK_N;
+  const int m_tiles = (p.M_total + kBlockM * MT - 1) / (kBlockM * MT);
+  const int total_tiles = m_tiles * (p.Cout / BLOCK_N);
 
   if (threadIdx.x == 0) {
     prefetch_tmap(&tmap_a);
     prefetch_tmap(&tmap_b);
     for (int s = 0; s < STAGES; ++s) { mbar_init(bar_full + s * 8, 1); mbar_init(bar_empty + s * 8, 1); }
-    mbar_init(bar_acc, 1);
+    for (int a = 0; a < 2; ++a) { mbar_init(bar_accfull + a * 8, 1); mbar_init(bar_accempty + a * 8, 4); }
     fence_barrier_init();
   }
-  if (warp == 1) tmem_alloc(smem_u32(tmem_slot), BLOCK_N);
+  if (warp == 1) tmem_alloc(smem_u32(tmem_slot), 2 * L::kAccCols);
   tc_fence_before();
   __syncthreads();
   tc_fence_after();
@@ -63,110 +72,158 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant
 
   if (warp == 0) {
     if (lane == 0) {
-      int n_img = 0, w0 = 0, h0 = 0;
-      if (p.im2col) {
-        const int hw = p.Ho * p.Wo;
-        n_img = m0 / hw;
-        const int rem = m0 - n_img * hw;
-        const int pp = rem / p.Wo, qq = rem - pp * p.Wo;
-        w0 = qq * p.stride - p.pad;
-        h0 = pp * p.stride - p.pad;
-      }
-      for (int kb = 0; kb < p.num_kb; ++kb) {
-        const int stage = kb % STAGES;
-        const uint32_t phase = (uint32_t)(kb / STAGES) & 1u;
-        mbar_wait(bar_empty + stage * 8, phase ^ 1u);
-        mbar_expect_tx(bar_full + stage * 8, L::kStage);
-        const uint32_t sa = base + stage * L::kStage, sb = sa + kABytes;
-        if (p.im2col) {
-          const int tap = kb / p.cchunks, cc = kb - tap * p.cchunks;
-          const int r = tap / p.S, s = tap - r * p.S;
-          tma_load_im2col_4d(sa, &tmap_a, bar_full + stage * 8, cc * kBlockK, w0, h0, n_img, (uint16_t)s, (uint16_t)r);
-        } else {
-          tma_load_2d(sa, &tmap_a, bar_full + stage * 8, kb * kBlockK, m0);
+      uint32_t g = 0;   // k-block counter across tiles (ring position)
+      for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
+        const int nt = tile / m_tiles, mtile = tile - nt * m_tiles;
+        const int m0 = mtile * (kBlockM * MT), n0 = nt * BLOCK_N;
+        const int n_sub = min(MT, (p.M_total - m0 + kBlockM - 1) / kBlockM);
+        int n_img[MT], w0[MT], h0[MT];
+#pragma unroll
+        for (int mt = 0; mt < MT; ++mt) {
+          n_img[mt] = w0[mt] = h0[mt] = 0;
+          if (p.im2col) {
+            const int ms = m0 + mt * kBlockM;
+            const int hw = p.Ho * p.Wo;
+            n_img[mt] = ms / hw;
+            const int rem = ms - n_img[mt] * hw;
+            const int pp = rem / p.Wo, qq = rem - pp * p.Wo;
+            w0[mt] = qq * p.stride - p.pad;
+            h0[mt] = pp * p.stride - p.pad;
+          }
         }
-        tma_load_2d(sb, &tmap_b, bar_full + stage * 8, kb * kBlockK, n0);
+        const uint32_t tx_bytes = (uint32_t)(n_sub * kABytes + L::kBBytes);
+        int tap = 0, cc = 0, r = 0, s = 0;
+        for (int kb = 0; kb < p.num_kb; ++kb, ++g) {
+          const uint32_t stage = g % STAGES, phase = (g / STAGES) & 1u;
+          mbar_wait(bar_empty + stage * 8, phase ^ 1u);
+          mbar_expect_tx(bar_full + stage * 8, tx_bytes);
+          const uint32_t sa = base + stage * L::kStage, sb = sa + MT * kABytes;
+#pragma unroll
+          for (int mt = 0; mt < MT; ++mt) {
+            if (mt < n_sub) {
+              if (p.im2col)
+                tma_load_im2col_4d(sa + mt * kABytes, &tmap_a, bar_full + stage * 8, cc * kBlockK, w0[mt], h0[mt], n_img[mt],
+                                   (uint16_t)s, (uint16_t)r);
+              else
+                tma_load_2d(sa + mt * kABytes, &tmap_a, bar_full + stage * 8, kb * kBlockK, m0 + mt * kBlockM);
+            }
+          }
+          tma_load_2d(sb, &tmap_b, bar_full + stage * 8, kb * kBlockK, n0);
+          if (++cc == p.cchunks) { cc = 0; ++tap; if (++s == p.S) { s = 0; ++r; } }
+        }
       }
     }
   } else if (warp == 1) {
     if (lane == 0) {
       constexpr uint32_t idesc = make_idesc(BLOCK_N);
-      for (int kb = 0; kb < p.num_kb; ++kb) {
-        const int stage = kb % STAGES;
-        const uint32_t phase = (uint32_t)(kb / STAGES) & 1u;
-        mbar_wait(bar_full + stage * 8, phase);
+      uint32_t g = 0;
+      int it = 0;
+      for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x, ++it) {
+        const int mtile = tile % m_tiles;
+        const int m0 = mtile * (kBlockM * MT);
+        const int n_sub = min(MT, (p.M_total - m0 + kBlockM - 1) / kBlockM);
+        const int acc = it & 1;
+        mbar_wait(bar_accempty + acc * 8, ((uint32_t)(it >> 1) & 1u) ^ 1u);   // epilogue drained this accumulator set
         tc_fence_after();
-        const uint32_t sa = base + stage * L::kStage, sb = sa + kABytes;
+        const uint32_t d0 = tmem_base + (uint32_t)(acc * L::kAccCols);
+        for (int kb = 0; kb < p.num_kb; ++kb, ++g) {
+          const uint32_t stage = g % STAGES, phase = (g / STAGES) & 1u;
+          mbar_wait(bar_full + stage * 8, phase);
+          tc_fence_after();
+          const uint32_t sa = base + stage * L::kStage, sb = sa + MT * kABytes;
 #pragma unroll
-        for (int k = 0; k < kBlockK / 16; ++k) {
-          // advance 16 bf16 = 32 bytes inside the 128-byte swizzle row
-          umma_f16(tmem_base, make_smem_desc(sa + k * 32), make_smem_desc(sb + k * 32), idesc, (kb | k) != 0 ? 1u : 0u);
+          for (int mt = 0; mt < MT; ++mt) {
+            if (mt < n_sub) {
+#pragma unroll
+              for (int k = 0; k < kBlockK / 16; ++k)   // advance 16 bf16 = 32 bytes inside the 128-byte swizzle row
+                umma_f16(d0 + mt * BLOCK_N, make_smem_desc(sa + mt * kABytes + k * 32), make_smem_desc(sb + k * 32), idesc,
+                         (kb | k) != 0 ? 1u : 0u);
+            }
+          }
+          umma_commit(bar_empty + stage * 8);   // frees the smem slot once these MMAs have read it
         }
-        umma_commit(bar_empty + stage * 8);   // frees the smem slot once these MMAs have read it
+        umma_commit(bar_accfull + acc * 8);     // accumulators of this tile complete
       }
-      umma_commit(bar_acc);                   // accumulator complete
     }
   } else {
-    const int quad = warp & 3;                // TMEM lanes [32*quad, 32*quad+32) belong to this warp
+    const int quad = warp & 3;                  // TMEM lanes [32*quad, 32*quad+32) belong to this warp
     const int row = quad * 32 + lane;
-    const int m = m0 + row;
-    mbar_wait(bar_acc, 0);
-    tc_fence_after();
+    int it = 0;
+    for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x, ++it) {
+      const int nt = tile / m_tiles, mtile = tile - nt * m_tiles;
+      const int m0 = mtile * (kBlockM * MT), n0 = nt * BLOCK_N;
+      const int n_sub = min(MT, (p.M_total - m0 + kBlockM - 1) / kBlockM);
+      const int acc = it & 1;
+      mbar_wait(bar_accfull + acc * 8, (uint32_t)(it >> 1) & 1u);
+      tc_fence_after();
 #pragma unroll 1
-    for (int c0 = 0; c0 < BLOCK_N; c0 += 32) {
-      uint32_t v[32];
-      tmem_ld32(tmem_base + ((uint32_t)(quad * 32) << 16) + (uint32_t)c0, v);
-      if (m < p.M_total) {
-        const int col = n0 + c0;
-        float f[32];
+      for (int mt = 0; mt < n_sub; ++mt) {
+        const int m = m0 + mt * kBlockM + row;
+        const bool mvalid = m < p.M_total;
+#pragma unroll 1
+        for (int c0 = 0; c0 < BLOCK_N; c0 += 32) {
+          const int col = n0 + c0;
+          uint4 res[4];
+          if (p.residual && mvalid) {             // issue the residual loads before the TMEM read so both latencies overlap
+            const uint4* rp = reinterpret_cast<const uint4*>(p.residual + (size_t)m * p.Cout + col);
 #pragma unroll
-        for (int i = 0; i < 32; ++i) f[i] = __uint_as_float(v[i]);
-        if (p.bias) {
-#pragma unroll
-          for (int i = 0; i < 32; i += 4) {
-            const float4 b = __ldg(reinterpret_cast<const float4*>(p.bias + col + i));
-            f[i] += b.x; f[i + 1] += b.y; f[i + 2] += b.z; f[i + 3] += b.w;
+            for (int i = 0; i < 4; ++i) res[i] = __ldg(rp + i);
           }
-        }
-        if (p.residual) {
-          const uint4* rp = reinterpret_cast<const uint4*>(p.residual + (size_t)m * p.Cout + col);
+          uint32_t v[32];
+          tmem_ld32(tmem_base + ((uint32_t)(quad * 32) << 16) + (uint32_t)(acc * L::kAccCols + mt * BLOCK_N + c0), v);
+          if (mvalid) {
+            float f[32];
 #pragma unroll
-          for (int i = 0; i < 4; ++i) {
-            const uint4 r = __ldg(rp + i);
-            const __nv_bfloat162* h = reinterpret_cast<const __nv_bfloat162*>(&r);
+            for (int i = 0; i < 32; ++i) f[i] = __uint_as_float(v[i]);
+            if (p.bias) {
 #pragma unroll
-            for (int j = 0; j < 4; ++j) {
-              const float2 x = __bfloat1622float2(h[j]);
-              f[i * 8 + j * 2] += x.x;
-              f[i * 8 + j * 2 + 1] += x.y;
+              for (int i = 0; i < 32; i += 4) {
+                const float4 b = __ldg(reinterpret_cast<const float4*>(p.bias + col + i));
+                f[i] += b.x; f[i + 1] += b.y; f[i + 2] += b.z; f[i + 3] += b.w;
+              }
+            }
+            if (p.residual) {
+#pragma unroll
+              for (int i = 0; i < 4; ++i) {
+                const __nv_bfloat162* h = reinterpret_cast<const __nv_bfloat162*>(&res[i]);
+#pragma unroll
+                for (int j = 0; j < 4; ++j) {
+                  const float2 x = __bfloat1622float2(h[j]);
+                  f[i * 8 + j * 2] += x.x;
+                  f[i * 8 + j * 2 + 1] += x.y;
+                }
+              }
+            }
+            if (p.relu) {
+#pragma unroll
+              for (int i = 0; i < 32; ++i) f[i] = fmaxf(f[i], 0.f);
+            }
+            if (p.out_f32) {
+              float4* op = reinterpret_cast<float4*>(reinterpret_cast<float*>(p.out) + (size_t)m * p.Cout + col);
+#pragma unroll
+              for (int i = 0; i < 8; ++i) op[i] = make_float4(f[4 * i], f[4 * i + 1], f[4 * i + 2], f[4 * i + 3]);
+            } else {
+              uint4* op = reinterpret_cast<uint4*>(reinterpret_cast<__nv_bfloat16*>(p.out) + (size_t)m * p.Cout + col);
+#pragma unroll
+              for (int i = 0; i < 4; ++i) {
+                uint4 o;
+                __nv_bfloat162* h = reinterpret_cast<__nv_bfloat162*>(&o);
+#pragma unroll
+                for (int j = 0; j < 4; ++j) h[j] = __floats2bfloat162_rn(f[i * 8 + j * 2], f[i * 8 + j * 2 + 1]);
+                op[i] = o;
+              }
             }
           }
         }
-        if (p.relu) {
-#pragma unroll
-          for (int i = 0; i < 32; ++i) f[i] = fmaxf(f[i], 0.f);
-        }
-        if (p.out_f32) {
-          float4* op = reinterpret_cast<float4*>(reinterpret_cast<float*>(p.out) + (size_t)m * p.Cout + col);
-#pragma unroll
-          for (int i = 0; i < 8; ++i) op[i] = make_float4(f[4 * i], f[4 * i + 1], f[4 * i + 2], f[4 * i + 3]);
-        } else {
-          uint4* op = reinterpret_cast<uint4*>(reinterpret_cast<__nv_bfloat16*>(p.out) + (size_t)m * p.Cout + col);
-#pragma unroll
-          for (int i = 0; i < 4; ++i) {
-            uint4 o;
-            __nv_bfloat162* h = reinterpret_cast<__nv_bfloat162*>(&o);
-#pragma unroll
-            for (int j = 0; j < 4; ++j) h[j] = __floats2bfloat162_rn(f[i * 8 + j * 2], f[i * 8 + j * 2 + 1]);
-            op[i] = o;
-          }
-        }
       }
+      tc_fence_before();
+      __syncwarp();
+      if (lane == 0) asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(bar_accempty + acc * 8) : "memory");
     }
   }
   tc_fence_before();
   __syncthreads();
-  if (warp == 1) tmem_dealloc(tmem_base, BLOCK_N);
+  if (warp == 1) tmem_dealloc(tmem_base, 2 * L::kAccCols);
 }
 
 // Probe kernel: A (256 x 64) resident in smem, MMA reads rows [shift, shift+128) through a shifted descriptor.
@@ -321,31 +378,38 @@ int prepare_conv_tc(const pdf_op& op, TcConv* tc) {
   return encode_2d(&tc->tmap_b, op.d_weight, (uint64_t)op.k, (uint64_t)op.r * op.s * op.c, (uint32_t)tc->block_n);
 }
 
-template <int BLOCK_N, int STAGES>
+template <int BLOCK_N, int STAGES, int MT>
 static int launch_tc(const TcConv& tc, cudaStream_t s) {
-  using L = SmemLayout<BLOCK_N, STAGES>;
+  using L = SmemLayout<BLOCK_N, STAGES, MT>;
   static bool configured = false;
   if (!configured) {
-    PDF_CHECK_CUDA(cudaFuncSetAttribute(conv_tc_kernel<BLOCK_N, STAGES>, cudaFuncAttributeMaxDynamicSharedMemorySize, L::kDynamic));
+    PDF_CHECK_CUDA(cudaFuncSetAttribute(conv_tc_kernel<BLOCK_N, STAGES, MT>, cudaFuncAttributeMaxDynamicSharedMemorySize, L::kDynamic));
     configured = true;
   }
   TcParams p;
   p.M_total = tc.M_total; p.Cout = tc.Cout; p.Ho = tc.Ho; p.Wo = tc.Wo; p.stride = tc.stride; p.pad = tc.pad; p.S = tc.S;
   p.cchunks = tc.cchunks; p.num_kb = tc.R * tc.S * tc.cchunks; p.relu = tc.relu; p.im2col = tc.im2col; p.out_f32 = tc.out_f32;
   p.bias = tc.bias; p.residual = reinterpret_cast<const __nv_bfloat16*>(tc.residual); p.out = tc.out;
-  dim3 grid(ceil_div(tc.M_total, kBlockM), tc.Cout / BLOCK_N);
-  conv_tc_kernel<BLOCK_N, STAGES><<<grid, 192, L::kDynamic, s>>>(*reinterpret_cast<const CUtensorMap*>(&tc.tmap_a),
-                                                                 *reinterpret_cast<const CUtensorMap*>(&tc.tmap_b), p);
+  const int total_tiles = ceil_div(tc.M_total, kBlockM * MT) * (tc.Cout / BLOCK_N);
+  const int ctas_per_sm = max(1, min(2, (int)((225 * 1024) / L::kDynamic)));
+  const int grid = max(1, min(total_tiles, num_sms() * ctas_per_sm));
+  conv_tc_kernel<BLOCK_N, STAGES, MT><<<grid, 192, L::kDynamic, s>>>(*reinterpret_cast<const CUtensorMap*>(&tc.tmap_a),
+                                                                     *reinterpret_cast<const CUtensorMap*>(&tc.tmap_b), p);
   PDF_CHECK_LAUNCH();
   return PDF_OK;
 }
 
 int launch_conv_tc(const TcConv& tc, cudaStream_t s) {
   if (tc.halo) return launch_conv3x3_halo(tc, s);
+  // two 128-row sub-tiles per CTA when the mainloop is long enough to amortise the single-tile prologue/epilogue and
+  // there are still >= 1.5 waves of CTAs
+  // N=128 tiles pair two 128-row sub-tiles per B tile when there is enough work for every SM
+  const long tiles2 = (long)ceil_div(tc.M_total, 2 * kBlockM) * (tc.Cout / tc.block_n);
+  const bool pair = tiles2 >= 2L * num_sms();
   switch (tc.block_n) {
-    case 256: return launch_tc<256, 4>(tc, s);
-    case 128: return launch_tc<128, 3>(tc, s);   // 96 KB/CTA -> two CTAs per SM
-    case 64: return launch_tc<64, 4>(tc, s);     // 96 KB/CTA -> two CTAs per SM
+    case 256: return launch_tc<256, 4, 1>(tc, s);                                        // 2 x 256 TMEM columns
+    case 128: return pair ? launch_tc<128, 4, 2>(tc, s) : launch_tc<128, 3, 1>(tc, s);
+    case 64: return pair ? launch_tc<64, 4, 2>(tc, s) : launch_tc<64, 4, 1>(tc, s);
   }
   set_error("launch_conv_tc: bad block_n %d", tc.block_n);
   return PDF_ERR_ARG;

@@ -80,6 +80,11 @@ conv3x3_c64_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_cons
   } else if (warp == 1) {
     if (lane == 0) {
       constexpr uint32_t idesc = make_idesc(64);
+      // one thread issues 72 MMAs of only 32 tensor-cycles each per tile: descriptor arithmetic must stay at ~1 add per MMA
+      uint32_t tap_off[9];
+#pragma unroll
+      for (int t = 0; t < 9; ++t) tap_off[t] = (uint32_t)((t / 3) * p.Wp + (t % 3)) * 8u;   // rows -> 16-byte units
+      const uint32_t w_lo = smem_desc_lo(s_w);
       mbar_wait(bar_w, 0);
       int it = 0;
       for (int tile = blockIdx.x; tile < p.total_tiles; tile += gridDim.x, ++it) {
@@ -91,17 +96,16 @@ conv3x3_c64_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_cons
         mbar_wait(bar_accempty + 8 * acc, accphase ^ 1u);      // epilogue has drained this accumulator set
         mbar_wait(bar_afull + 8 * stage, phase);
         tc_fence_after();
-        const uint32_t a0 = s_a + stage * a_bytes;
-#pragma unroll 1
+        const uint32_t a_lo = smem_desc_lo(s_a + stage * a_bytes) + (uint32_t)off0 * 8u;
+#pragma unroll
         for (int half = 0; half < 2; ++half) {
           const uint32_t d = tmem_base + (uint32_t)(acc * 128 + half * 64);
-#pragma unroll 1
+#pragma unroll
           for (int t = 0; t < 9; ++t) {
-            const int r = t / 3, s = t - r * 3;
-            const uint32_t arow = a0 + (uint32_t)(off0 + half * 128 + r * p.Wp + s) * 128u;
 #pragma unroll
             for (int k = 0; k < 4; ++k)
-              umma_f16(d, make_smem_desc(arow + k * 32), make_smem_desc(s_w + t * 8192 + k * 32), idesc, (t | k) != 0 ? 1u : 0u);
+              umma_f16_lo(d, a_lo + tap_off[t] + (uint32_t)(half * 128 * 8 + k * 2), w_lo + (uint32_t)(t * 512 + k * 2), idesc,
+                          (t | k) != 0 ? 1u : 0u);
           }
         }
         umma_commit(bar_aempty + 8 * stage);

@@ -130,14 +130,14 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant
           const uint32_t stage = g % STAGES, phase = (g / STAGES) & 1u;
           mbar_wait(bar_full + stage * 8, phase);
           tc_fence_after();
-          const uint32_t sa = base + stage * L::kStage, sb = sa + MT * kABytes;
+          const uint32_t a_lo = smem_desc_lo(base + stage * L::kStage), b_lo = a_lo + (uint32_t)(MT * kABytes / 16);
 #pragma unroll
           for (int mt = 0; mt < MT; ++mt) {
             if (mt < n_sub) {
 #pragma unroll
-              for (int k = 0; k < kBlockK / 16; ++k)   // advance 16 bf16 = 32 bytes inside the 128-byte swizzle row
-                umma_f16(d0 + mt * BLOCK_N, make_smem_desc(sa + mt * kABytes + k * 32), make_smem_desc(sb + k * 32), idesc,
-                         (kb | k) != 0 ? 1u : 0u);
+              for (int k = 0; k < kBlockK / 16; ++k)   // advance 16 bf16 = 32 bytes (2 x 16-byte units) inside the swizzle row
+                umma_f16_lo(d0 + mt * BLOCK_N, a_lo + (uint32_t)(mt * kABytes / 16 + k * 2), b_lo + (uint32_t)(k * 2), idesc,
+                            (kb | k) != 0 ? 1u : 0u);
             }
           }
           umma_commit(bar_empty + stage * 8);   // frees the smem slot once these MMAs have read it

@@ -54,23 +54,51 @@ def measured_peaks():
 
 
 class ClockSampler:
-    """nvidia-smi clocks / throttle reasons sampled DURING the timed region."""
+    """SM clock / throttle reasons sampled DURING the timed region (NVML; nvidia-smi as a fallback)."""
     Q = "clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown," \
         "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap"
+    BITS = {"hw_slowdown": 0x8, "hw_thermal_slowdown": 0x40, "sw_thermal_slowdown": 0x20, "sw_power_cap": 0x4}
 
     def __init__(self, index: int):
-        self.index, self.rows, self._stop, self._t = index, [], threading.Event(), None
+        self.index, self.sm, self.mx, self.reasons, self._stop, self._t = index, [], [], set(), threading.Event(), None
+        self.nvml = None
+        try:
+            import pynvml
+            pynvml.nvmlInit()
+            self.nvml = pynvml
+            self.h = pynvml.nvmlDeviceGetHandleByIndex(index)
+        except Exception:
+            self.nvml = None
+
+    def _sample_nvml(self):
+        n = self.nvml
+        self.sm.append(float(n.nvmlDeviceGetClockInfo(self.h, n.NVML_CLOCK_SM)))
+        self.mx.append(float(n.nvmlDeviceGetMaxClockInfo(self.h, n.NVML_CLOCK_SM)))
+        try:
+            r = n.nvmlDeviceGetCurrentClocksEventReasons(self.h)
+        except Exception:
+            r = n.nvmlDeviceGetCurrentClocksThrottleReasons(self.h)
+        for name, bit in self.BITS.items():
+            if r & bit:
+                self.reasons.add(name)
+
+    def _sample_smi(self):
+        out = subprocess.run(["nvidia-smi", "-i", str(self.index), f"--query-gpu={self.Q}", "--format=csv,noheader,nounits"],
+                             capture_output=True, text=True, timeout=5).stdout.strip()
+        if out:
+            r = [c.strip() for c in out.splitlines()[0].split(",")]
+            self.sm.append(float(r[0])); self.mx.append(float(r[1]))
+            for name, v in zip(["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"], r[3:7]):
+                if v.lower().startswith("active"):
+                    self.reasons.add(name)
 
     def _loop(self):
         while not self._stop.is_set():
             try:
-                out = subprocess.run(["nvidia-smi", "-i", str(self.index), f"--query-gpu={self.Q}", "--format=csv,noheader,nounits"],
-                                     capture_output=True, text=True, timeout=5).stdout.strip()
-                if out:
-                    self.rows.append([c.strip() for c in out.splitlines()[0].split(",")])
+                self._sample_nvml() if self.nvml else self._sample_smi()
             except Exception:
                 pass
-            self._stop.wait(0.2)
+            self._stop.wait(0.02 if self.nvml else 0.2)
 
     def __enter__(self):
         self._t = threading.Thread(target=self._loop, daemon=True)
@@ -82,17 +110,8 @@ class ClockSampler:
         self._t.join(timeout=6)
 
     def summary(self):
-        sm, mx, reasons = [], [], set()
-        for r in self.rows:
-            try:
-                sm.append(float(r[0])); mx.append(float(r[1]))
-            except Exception:
-                continue
-            for name, v in zip(["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"], r[3:7]):
-                if v.lower().startswith("active"):
-                    reasons.add(name)
-        return {"sm_mhz": float(np.median(sm)) if sm else None, "sm_max_mhz": max(mx) if mx else None,
-                "reasons": sorted(reasons), "samples": len(sm)}
+        return {"sm_mhz": float(np.median(self.sm)) if self.sm else None, "sm_max_mhz": max(self.mx) if self.mx else None,
+                "reasons": sorted(self.reasons), "samples": len(self.sm), "source": "nvml" if self.nvml else "nvidia-smi"}
 
 
 def host_pool(n: int):
@@ -141,8 +160,8 @@ def run_reference(args, wl):
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
-    ap.add_argument("--steps", type=int, default=10)
-    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--steps", type=int, default=100)
+    ap.add_argument("--warmup", type=int, default=5)
     ap.add_argument("--workload", default="c2", choices=sorted(WORKLOADS))
     ap.add_argument("--subjects", type=int, default=32, help="subjects per step per GPU")
     ap.add_argument("--pool", type=int, default=4, help="distinct synthetic volumes cycled by subject index")

@@ -25,7 +25,9 @@ def init_distributed(backend: str | None = None) -> Tuple[int, int, int]:
             backend = "nccl" if torch.cuda.is_available() else "gloo"
         if backend == "nccl":
             torch.cuda.set_device(local_rank)
-        torch.distributed.init_process_group(backend=backend, rank=rank, world_size=ws)
+            torch.distributed.init_process_group(backend=backend, rank=rank, world_size=ws, device_id=torch.device("cuda", local_rank))
+        else:
+            torch.distributed.init_process_group(backend=backend, rank=rank, world_size=ws)
     return rank, local_rank, ws
 
 

@@ -378,6 +378,12 @@ int prepare_conv_tc(const pdf_op& op, TcConv* tc) {
   return encode_2d(&tc->tmap_b, op.d_weight, (uint64_t)op.k, (uint64_t)op.r * op.s * op.c, (uint32_t)tc->block_n);
 }
 
+int prepare_stem_tc(const pdf_op& op, TcConv* tc) {
+  if (int rc = load_driver_entry_points()) return rc;
+  PDF_REQUIRE((reinterpret_cast<uintptr_t>(op.d_weight) & 15) == 0, "fused stem: weight pointer must be 16-byte aligned");
+  return encode_2d(&tc->tmap_b, op.d_weight, 64, 64, 64);
+}
+
 template <int BLOCK_N, int STAGES, int MT>
 static int launch_tc(const TcConv& tc, cudaStream_t s) {
   using L = SmemLayout<BLOCK_N, STAGES, MT>;

@@ -8,7 +8,7 @@ int launch_conv_f32(const pdf_op& op, cudaStream_t s);
 int launch_maxpool(const pdf_op& op, cudaStream_t s);
 int launch_avgpool(const pdf_op& op, cudaStream_t s);
 int launch_stem_im2col(const pdf_op& op, cudaStream_t s);
-int launch_stem_fused(const pdf_op& op, cudaStream_t s);
+
 
 // tcgen05 path: one prepared launch per bf16 conv op (tensor maps are 128-byte opaque blobs)
 struct alignas(64) TensorMapBlob { unsigned char bytes[128]; };
@@ -27,6 +27,8 @@ struct TcConv {
 };
 
 int prepare_conv_tc(const pdf_op& op, TcConv* out);
+int prepare_stem_tc(const pdf_op& op, TcConv* out);   // encodes the [64 x 64] weight map into out->tmap_b
+int launch_stem_fused(const pdf_op& op, const TensorMapBlob& tmap_w, cudaStream_t s);
 int launch_conv_tc(const TcConv& tc, cudaStream_t s);
 bool halo_eligible(const pdf_op& op);
 int launch_conv3x3_halo(const TcConv& tc, cudaStream_t s);

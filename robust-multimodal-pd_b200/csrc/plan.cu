@@ -50,6 +50,7 @@ extern "C" int pdf_plan_create(pdf_plan** out, const pdf_op* ops, int n_ops) {
   for (int i = 0; i < n_ops; ++i) {
     const pdf_op& op = plan->ops[i];
     int rc = validate_op(op, i);
+    if (rc == PDF_OK && op.kind == PDF_OP_STEM_FUSED) rc = prepare_stem_tc(op, &plan->tc[i]);
     if (rc == PDF_OK && op.kind == PDF_OP_STEM_FUSED) plan->flops += 2.0 * op.n * ((op.h - 1) / 2 + 1) * ((op.w - 1) / 2 + 1) * 64.0 * 49.0;
     if (rc == PDF_OK && op.kind == PDF_OP_CONV) {
       plan->flops += 2.0 * op.n * op.ho * op.wo * (double)op.k * op.r * op.s * op.c;
@@ -72,7 +73,7 @@ extern "C" int pdf_plan_run_range(const pdf_plan* plan, int first, int count, pd
       case PDF_OP_MAXPOOL: rc = launch_maxpool(op, s); break;
       case PDF_OP_AVGPOOL: rc = launch_avgpool(op, s); break;
       case PDF_OP_STEM_IM2COL: rc = launch_stem_im2col(op, s); break;
-      case PDF_OP_STEM_FUSED: rc = launch_stem_fused(op, s); break;
+      case PDF_OP_STEM_FUSED: rc = launch_stem_fused(op, plan->tc[i].tmap_b, s); break;
     }
     if (rc != PDF_OK) return rc;
   }

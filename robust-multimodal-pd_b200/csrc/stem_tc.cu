@@ -31,17 +31,16 @@ struct StemParams {
 };
 
 __global__ void __launch_bounds__(256)
-stem_fused_kernel(const StemParams p) {
+stem_fused_kernel(const __grid_constant__ CUtensorMap tmap_w, const StemParams p) {
   // [ A: 256 rows x 128 B | W: 64 rows x 128 B | input patch | barrier, tmem slot ]
   extern __shared__ uint8_t smem_raw[];
   const uint32_t raw_addr = smem_u32(smem_raw);
   const uint32_t base = (raw_addr + 1023u) & ~1023u;
   uint8_t* smem = smem_raw + (base - raw_addr);
   uint8_t* sA = smem;
-  uint8_t* sW = smem + 256 * 128;
   __nv_bfloat16* sIn = reinterpret_cast<__nv_bfloat16*>(smem + 256 * 128 + 64 * 128);
   const uint32_t bar = base + 256 * 128 + 64 * 128 + ((kIT * kITP * 2 + 15) & ~15);
-  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(smem + (bar - base) + 8);
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(smem + (bar - base) + 32);
 
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
   const int n = blockIdx.y;
@@ -50,7 +49,15 @@ stem_fused_kernel(const StemParams p) {
   const int cy0 = 2 * tp0 - 1, cx0 = 2 * tq0 - 1;    // conv-tile origin (may be -1)
   const int iy0 = 2 * cy0 - 3, ix0 = 2 * cx0 - 3;    // input-patch origin
 
-  if (tid == 0) { mbar_init(bar, 1); fence_barrier_init(); }
+  const uint32_t bar_w = bar + 16;
+  if (tid == 0) {
+    mbar_init(bar, 1);
+    mbar_init(bar_w, 1);
+    fence_barrier_init();
+    // weights [64 x 64] bf16 -> 128B-swizzled K-major rows, written by the TMA unit (one instruction per CTA)
+    mbar_expect_tx(bar_w, 64 * 128);
+    tma_load_2d(base + 256 * 128, &tmap_w, bar_w, 0, 0);
+  }
   if (warp == 1) tmem_alloc(smem_u32(tmem_slot), 128);
 
   // 1. input patch.  Patch column 0 is global x = ix0 (odd), so columns 1.. pair up into 4-byte aligned global words:
@@ -82,24 +89,25 @@ stem_fused_kernel(const StemParams p) {
       if (x + 1 < kIT) sIn16[y * kITP + x + 1] = hi16;
     }
   }
-  // 2a. weights -> swizzled K-major rows (16-byte chunk c of row r lives at chunk c ^ (r & 7))
-  for (int i = tid; i < 64 * 8; i += 256) {
-    const int r = i >> 3, c = i & 7;
-    const uint4 v = __ldg(reinterpret_cast<const uint4*>(p.w) + i);
-    *reinterpret_cast<uint4*>(sW + r * 128 + ((c ^ (r & 7)) << 4)) = v;
-  }
   __syncthreads();
   // 2b. im2col rows.  K index = r*8 + s (s = 7 is a zero column, r = 7 a zero chunk): chunk c of row m is the 7 taps of
   //     filter row c, i.e. 8 consecutive bf16 of the patch starting at an even column -> four aligned 32-bit loads.
-  for (int i = tid; i < 256 * 8; i += 256) {
-    const int m = i >> 3, c = i & 7;
-    uint4 v = make_uint4(0u, 0u, 0u, 0u);
-    if (m < kConvPix && c < 7) {
-      const int cy = m / kCT, cx = m - cy * kCT;
-      const uint32_t* src = reinterpret_cast<const uint32_t*>(sIn + (2 * cy + c) * kITP + 2 * cx);
-      v = make_uint4(src[0], src[1], src[2], src[3] & 0x0000ffffu);
+  {
+    const int c = tid & 7;                      // chunk (= filter row) is fixed per thread; rows advance by 32 per step
+    int m = tid >> 3;
+    int cy = m / kCT, cx = m - cy * kCT;
+    const uint32_t cmask = (c < 7) ? 0xffffffffu : 0u;
+#pragma unroll
+    for (int it = 0; it < 8; ++it) {
+      uint4 v = make_uint4(0u, 0u, 0u, 0u);
+      if (m < kConvPix) {
+        const uint32_t* src = reinterpret_cast<const uint32_t*>(sIn + (2 * cy + (c < 7 ? c : 0)) * kITP + 2 * cx);
+        v = make_uint4(src[0] & cmask, src[1] & cmask, src[2] & cmask, src[3] & 0x0000ffffu & cmask);
+      }
+      *reinterpret_cast<uint4*>(sA + m * 128 + ((c ^ (m & 7)) << 4)) = v;
+      m += 32; cy += 2; cx += 2;
+      if (cx >= kCT) { cx -= kCT; ++cy; }
     }
-    *reinterpret_cast<uint4*>(sA + m * 128 + ((c ^ (m & 7)) << 4)) = v;
   }
   fence_proxy_async();          // generic-proxy smem writes -> visible to the tensor core (async proxy)
   tc_fence_before();
@@ -111,6 +119,8 @@ stem_fused_kernel(const StemParams p) {
   if (tid == 0) {
     constexpr uint32_t idesc = make_idesc(64);
     const uint32_t a0 = base, w0 = base + 256 * 128;
+    mbar_wait(bar_w, 0);
+    tc_fence_after();
 #pragma unroll
     for (int mt = 0; mt < 2; ++mt)
 #pragma unroll
@@ -133,20 +143,18 @@ stem_fused_kernel(const StemParams p) {
       uint32_t v[32];
       tmem_ld32(tmem_base + ((uint32_t)(quad * 32) << 16) + (uint32_t)(mt * 64 + c0), v);
       if (m < kConvPix) {
+        const uint32_t keep = inside ? 0xffffffffu : 0u;       // out-of-image conv pixels must not win the max-pool
 #pragma unroll
         for (int i = 0; i < 4; ++i) {
+          const float4 b0 = __ldg(reinterpret_cast<const float4*>(p.bias + c0 + i * 8));
+          const float4 b1 = __ldg(reinterpret_cast<const float4*>(p.bias + c0 + i * 8 + 4));
           uint4 o;
           __nv_bfloat162* h = reinterpret_cast<__nv_bfloat162*>(&o);
-#pragma unroll
-          for (int j = 0; j < 4; ++j) {
-            const int ch = c0 + i * 8 + j * 2;
-            float a = 0.f, b = 0.f;
-            if (inside) {
-              a = fmaxf(__uint_as_float(v[i * 8 + j * 2]) + __ldg(p.bias + ch), 0.f);
-              b = fmaxf(__uint_as_float(v[i * 8 + j * 2 + 1]) + __ldg(p.bias + ch + 1), 0.f);
-            }
-            h[j] = __floats2bfloat162_rn(a, b);
-          }
+          h[0] = __floats2bfloat162_rn(fmaxf(__uint_as_float(v[i * 8 + 0]) + b0.x, 0.f), fmaxf(__uint_as_float(v[i * 8 + 1]) + b0.y, 0.f));
+          h[1] = __floats2bfloat162_rn(fmaxf(__uint_as_float(v[i * 8 + 2]) + b0.z, 0.f), fmaxf(__uint_as_float(v[i * 8 + 3]) + b0.w, 0.f));
+          h[2] = __floats2bfloat162_rn(fmaxf(__uint_as_float(v[i * 8 + 4]) + b1.x, 0.f), fmaxf(__uint_as_float(v[i * 8 + 5]) + b1.y, 0.f));
+          h[3] = __floats2bfloat162_rn(fmaxf(__uint_as_float(v[i * 8 + 6]) + b1.z, 0.f), fmaxf(__uint_as_float(v[i * 8 + 7]) + b1.w, 0.f));
+          o.x &= keep; o.y &= keep; o.z &= keep; o.w &= keep;
           const int chunk = (c0 >> 3) + i;
           *reinterpret_cast<uint4*>(sA + m * 128 + ((chunk ^ (m & 7)) << 4)) = o;
         }
@@ -184,9 +192,9 @@ stem_fused_kernel(const StemParams p) {
   }
 }
 
-constexpr int kStemSmem = 256 * 128 + 64 * 128 + ((kIT * kITP * 2 + 15) & ~15) + 16 + 1024;
+constexpr int kStemSmem = 256 * 128 + 64 * 128 + ((kIT * kITP * 2 + 15) & ~15) + 48 + 1024;
 
-int launch_stem_fused(const pdf_op& op, cudaStream_t s) {
+int launch_stem_fused(const pdf_op& op, const TensorMapBlob& tmap_w, cudaStream_t s) {
   static bool configured = false;
   if (!configured) {
     PDF_CHECK_CUDA(cudaFuncSetAttribute(stem_fused_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kStemSmem));
@@ -202,7 +210,7 @@ int launch_stem_fused(const pdf_op& op, cudaStream_t s) {
   p.P = op.ho;
   p.tiles = ceil_div(p.P, kTP);
   dim3 grid(p.tiles * p.tiles, op.n);
-  stem_fused_kernel<<<grid, 256, kStemSmem, s>>>(p);
+  stem_fused_kernel<<<grid, 256, kStemSmem, s>>>(*reinterpret_cast<const CUtensorMap*>(&tmap_w), p);
   PDF_CHECK_LAUNCH();
   return PDF_OK;
 }

@@ -20,6 +20,7 @@ namespace pdf {
 
 constexpr int kHaloBM = 256;       // output positions (padded-row space) per tile
 constexpr int kHaloStages = 2;
+constexpr int kPrefetchAhead = 2;   // tiles warmed in L2 beyond the ones resident in shared memory
 
 struct HaloParams {
   int H, W, Wp, NR, tiles_per_image, total_tiles, relu;
@@ -58,9 +59,26 @@ conv3x3_c64_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_cons
   const uint32_t tmem_base = *tmem_slot;
 
   if (warp == 0) {
-    if (lane == 0) {
+    if (elect_one()) {
       mbar_expect_tx(bar_w, 9 * 8192);
       for (int t = 0; t < 9; ++t) tma_load_2d(s_w + t * 8192, &tmap_w, bar_w, t * 64, 0);
+      // Warm L2 for the tile kPrefetchAhead iterations ahead (halo rows, and the residual rows its epilogue will read):
+      // the shared-memory ring is only two stages deep, so without this every halo load pays the full HBM latency.
+      auto prefetch_tile = [&](int tile) {
+        if (tile >= p.total_tiles) return;
+        const int n = tile / p.tiles_per_image;
+        const int m0 = (tile - n * p.tiles_per_image) * kHaloBM;
+        const int p_lo = m0 / p.Wp;
+        asm volatile("cp.async.bulk.prefetch.tensor.4d.L2.global.tile [%0, {%1, %2, %3, %4}];"
+                     ::"l"(reinterpret_cast<uint64_t>(&tmap_a)), "r"(0), "r"(-1), "r"(p_lo - 1), "r"(n) : "memory");
+        if (p.residual) {
+          const int p_hi = min(p.H - 1, (m0 + kHaloBM - 1) / p.Wp);
+          const __nv_bfloat16* r0 = p.residual + (((size_t)n * p.H + p_lo) * p.W) * 64;
+          const uint32_t bytes = (uint32_t)(p_hi - p_lo + 1) * (uint32_t)p.W * 128u;
+          asm volatile("cp.async.bulk.prefetch.L2.global [%0], %1;" ::"l"(reinterpret_cast<uint64_t>(r0)), "r"(bytes) : "memory");
+        }
+      };
+      for (int a = kHaloStages; a < kHaloStages + kPrefetchAhead; ++a) prefetch_tile(blockIdx.x + a * gridDim.x);
       int it = 0;
       for (int tile = blockIdx.x; tile < p.total_tiles; tile += gridDim.x, ++it) {
         const int stage = it % kHaloStages;
@@ -68,6 +86,7 @@ conv3x3_c64_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_cons
         const int n = tile / p.tiles_per_image;
         const int m0 = (tile - n * p.tiles_per_image) * kHaloBM;
         const int p_lo = m0 / p.Wp;
+        prefetch_tile(tile + (kHaloStages + kPrefetchAhead) * gridDim.x);
         mbar_wait(bar_aempty + 8 * stage, phase ^ 1u);
         mbar_expect_tx(bar_afull + 8 * stage, (uint32_t)(p.NR * p.Wp * 128));
         asm volatile(
@@ -78,7 +97,7 @@ conv3x3_c64_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_cons
       }
     }
   } else if (warp == 1) {
-    if (lane == 0) {
+    if (elect_one()) {
       constexpr uint32_t idesc = make_idesc(64);
       // one thread issues 72 MMAs of only 32 tensor-cycles each per tile: descriptor arithmetic must stay at ~1 add per MMA
       uint32_t tap_off[9];

@@ -71,7 +71,7 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant
   const uint32_t tmem_base = *tmem_slot;
 
   if (warp == 0) {
-    if (lane == 0) {
+    if (elect_one()) {
       uint32_t g = 0;   // k-block counter across tiles (ring position)
       for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
         const int nt = tile / m_tiles, mtile = tile - nt * m_tiles;
@@ -114,7 +114,7 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant
       }
     }
   } else if (warp == 1) {
-    if (lane == 0) {
+    if (elect_one()) {
       constexpr uint32_t idesc = make_idesc(BLOCK_N);
       uint32_t g = 0;
       int it = 0;

@@ -226,7 +226,25 @@ __device__ __forceinline__ double scrub_bits(float v) {   // nan/inf -> 0, else 
   return (fabsf(v) < INFINITY) ? (double)v : 0.0;
 }
 
-__global__ void __launch_bounds__(352)
+// Per-row constants of the y axis, staged in shared memory once per block: two 16-byte loads per output row instead of
+// four table loads from global memory plus the address arithmetic around them.
+struct __align__(16) JEntry {
+  int y0b, y1b;        // byte offset (y * Z * 4) of the two input rows
+  int pad0, pad1;
+  double w0, w1;
+};
+
+__device__ __forceinline__ float lds_f32(uint32_t addr) {
+  float v;
+  asm volatile("ld.shared.f32 %0, [%1];" : "=f"(v) : "r"(addr));
+  return v;
+}
+__device__ __forceinline__ uint32_t key_of(float f) { return float_to_ordered(f); }
+
+// NEED_JMAX: plane maxima along axis 1 are only needed when axis 1 is one of the slicing axes; they cost a warp
+// reduction + shared atomic per output row, so the common axis-2 / axis-0 configurations skip them.
+template <bool NEED_JMAX>
+__global__ void __launch_bounds__(352, 2)
 resample_tma_kernel(const float* __restrict__ raw, float* __restrict__ zoomed, SubjState* __restrict__ states,
                     const ZoomTables* __restrict__ tabs, int X, int Y, int Z, int T0, int T1, int T2, int TJ, int NR, int KT) {
   extern __shared__ __align__(16) unsigned char sm_raw[];
@@ -235,12 +253,21 @@ resample_tma_kernel(const float* __restrict__ raw, float* __restrict__ zoomed, S
   uint32_t* s_hist = reinterpret_cast<uint32_t*>(sm_raw + (size_t)kResStages * stage_bytes);
   uint32_t* s_imax = s_hist + kH0;
   uint32_t* s_jmax = s_imax + T0;
-  uint64_t* s_bar = reinterpret_cast<uint64_t*>(sm_raw + (((size_t)kResStages * stage_bytes + (size_t)(kH0 + T0 + T1) * 4 + 7) & ~(size_t)7));
+  size_t off = ((size_t)kResStages * stage_bytes + (size_t)(kH0 + T0 + T1) * 4 + 15) & ~(size_t)15;
+  JEntry* s_jtab = reinterpret_cast<JEntry*>(sm_raw + off);
+  off += (size_t)T1 * sizeof(JEntry);
+  uint64_t* s_bar = reinterpret_cast<uint64_t*>(sm_raw + off);
   const uint32_t bar_full = smem_u32(s_bar), bar_empty = bar_full + kResStages * 8;
   const int b = blockIdx.y;
   const int tid = threadIdx.x, nthr = blockDim.x;
   const int n_cwarps = (nthr - 32) / 32;
   for (int i = tid; i < kH0 + T0 + T1; i += nthr) s_hist[i] = 0;
+  for (int j = tid; j < T1; j += nthr) {
+    JEntry e;
+    e.y0b = tabs->i0[1][j] * Z * 4; e.y1b = tabs->i1[1][j] * Z * 4; e.pad0 = e.pad1 = 0;
+    e.w0 = tabs->w0[1][j]; e.w1 = tabs->w1[1][j];
+    s_jtab[j] = e;
+  }
   if (tid == 0) {
     for (int s = 0; s < kResStages; ++s) { mbar_init(bar_full + s * 8, 1); mbar_init(bar_empty + s * 8, n_cwarps); }
     fence_barrier_init();
@@ -253,9 +280,12 @@ resample_tma_kernel(const float* __restrict__ raw, float* __restrict__ zoomed, S
   const int tiles_per_i = (T1 + TJ - 1) / TJ;
   const int ntiles = T0 * tiles_per_i;
   const int plane = NR * Z;
+  // warp-uniform role / row bookkeeping (the shuffle tells the compiler so: it can live in uniform registers)
+  const int warp = __shfl_sync(0xffffffffu, tid >> 5, 0);
+  const int lane = tid & 31;
 
-  if (tid < 32) {
-    if (tid == 0) {
+  if (warp == 0) {
+    if (elect_one()) {
       int it = 0;
       for (int tile = blockIdx.x; tile < ntiles; tile += gridDim.x, ++it) {
         const int stage = it % kResStages;
@@ -272,68 +302,79 @@ resample_tma_kernel(const float* __restrict__ raw, float* __restrict__ zoomed, S
       }
     }
   } else {
-    const int ct = tid - 32;
-    const int half = ct / KT, k = ct - half * KT;
+    const int wph = KT >> 5;                       // compute warps per row half
+    const int cw = warp - 1;
+    const int half = cw / wph;
+    const int k = (cw - half * wph) * 32 + lane;
     const bool act = k < T2;
-    int z0 = 0, z1 = 0;
+    uint32_t z0b = 0, z1b = 0;
     double wz0 = 0.0, wz1 = 0.0;
-    if (act) { z0 = tabs->i0[2][k]; z1 = tabs->i1[2][k]; wz0 = tabs->w0[2][k]; wz1 = tabs->w1[2][k]; }
-    uint32_t tmin = 0xffffffffu, kmax = 0;
+    if (act) { z0b = (uint32_t)tabs->i0[2][k] * 4u; z1b = (uint32_t)tabs->i1[2][k] * 4u; wz0 = tabs->w0[2][k]; wz1 = tabs->w1[2][k]; }
+    const uint32_t planeb = (uint32_t)plane * 4u;
+    const uint32_t stage0 = smem_u32(s_stage);
+    float vmin = INFINITY, kmaxf = -INFINITY;
     int it = 0;
     for (int tile = blockIdx.x; tile < ntiles; tile += gridDim.x, ++it) {
       const int stage = it % kResStages;
       const uint32_t phase = (uint32_t)(it / kResStages) & 1u;
       const int i = tile / tiles_per_i;
       const int j0 = (tile - i * tiles_per_i) * TJ, j1 = min(j0 + TJ, T1);
-      const int ylo = tabs->i0[1][j0];
       const double wx0 = tabs->w0[0][i], wx1 = tabs->w1[0][i];
-      const float* sp = s_stage + (size_t)stage * (stage_bytes / 4);
+      const uint32_t sbase = stage0 + (uint32_t)stage * stage_bytes - (uint32_t)s_jtab[j0].y0b;
+      float* op = zb + ((size_t)i * T1 + (j0 + half)) * T2 + k;
       mbar_wait(bar_full + stage * 8, phase);
-      uint32_t tile_max = 0;
-      for (int j = j0 + half; j < j1; j += 2) {
-        uint32_t key = 0;
-        if (act) {
-          const int y0 = tabs->i0[1][j] - ylo, y1 = tabs->i1[1][j] - ylo;
-          const double wy0 = tabs->w0[1][j], wy1 = tabs->w1[1][j];
-          const float* r00 = sp + y0 * Z;
-          const float* r01 = sp + y1 * Z;
-          const float* r10 = r00 + plane;
-          const float* r11 = r01 + plane;
-          const float f000 = r00[z0], f001 = r00[z1], f010 = r01[z0], f011 = r01[z1];
-          const float f100 = r10[z0], f101 = r10[z1], f110 = r11[z0], f111 = r11[z1];
-          // background fast path: eight (+-)0 taps give exactly +0.0 in scipy's sum, no float64 work needed
-          const uint32_t any = (__float_as_uint(f000) | __float_as_uint(f001) | __float_as_uint(f010) | __float_as_uint(f011) |
-                                __float_as_uint(f100) | __float_as_uint(f101) | __float_as_uint(f110) | __float_as_uint(f111)) & 0x7fffffffu;
-          double t = 0.0;
-          if (any != 0) {
-            t = __dadd_rn(t, __dmul_rn(__dmul_rn(__dmul_rn(scrub_bits(f000), wx0), wy0), wz0));
-            t = __dadd_rn(t, __dmul_rn(__dmul_rn(__dmul_rn(scrub_bits(f001), wx0), wy0), wz1));
-            t = __dadd_rn(t, __dmul_rn(__dmul_rn(__dmul_rn(scrub_bits(f010), wx0), wy1), wz0));
-            t = __dadd_rn(t, __dmul_rn(__dmul_rn(__dmul_rn(scrub_bits(f011), wx0), wy1), wz1));
-            t = __dadd_rn(t, __dmul_rn(__dmul_rn(__dmul_rn(scrub_bits(f100), wx1), wy0), wz0));
-            t = __dadd_rn(t, __dmul_rn(__dmul_rn(__dmul_rn(scrub_bits(f101), wx1), wy0), wz1));
-            t = __dadd_rn(t, __dmul_rn(__dmul_rn(__dmul_rn(scrub_bits(f110), wx1), wy1), wz0));
-            t = __dadd_rn(t, __dmul_rn(__dmul_rn(__dmul_rn(scrub_bits(f111), wx1), wy1), wz1));
+      float tmaxf = -INFINITY;
+#pragma unroll 2
+      for (int j = j0 + half; j < j1; j += 2, op += 2 * (size_t)T2) {
+        const JEntry e = s_jtab[j];
+        const uint32_t r0 = sbase + (uint32_t)e.y0b, r1 = sbase + (uint32_t)e.y1b;
+        const float f000 = lds_f32(r0 + z0b), f001 = lds_f32(r0 + z1b), f010 = lds_f32(r1 + z0b), f011 = lds_f32(r1 + z1b);
+        const float f100 = lds_f32(r0 + planeb + z0b), f101 = lds_f32(r0 + planeb + z1b);
+        const float f110 = lds_f32(r1 + planeb + z0b), f111 = lds_f32(r1 + planeb + z1b);
+        const uint32_t orall = __float_as_uint(f000) | __float_as_uint(f001) | __float_as_uint(f010) | __float_as_uint(f011) |
+                               __float_as_uint(f100) | __float_as_uint(f101) | __float_as_uint(f110) | __float_as_uint(f111);
+        // background fast path: eight (+-)0 taps give exactly +0.0 in scipy's sum, no float64 work needed
+        double t = 0.0;
+        if ((orall & 0x7fffffffu) != 0u) {
+          double d000, d001, d010, d011, d100, d101, d110, d111;
+          if ((orall & 0x7f800000u) != 0x7f800000u) {     // no tap can be NaN/Inf (their exponent bits would survive the OR)
+            d000 = (double)f000; d001 = (double)f001; d010 = (double)f010; d011 = (double)f011;
+            d100 = (double)f100; d101 = (double)f101; d110 = (double)f110; d111 = (double)f111;
+          } else {
+            d000 = scrub_bits(f000); d001 = scrub_bits(f001); d010 = scrub_bits(f010); d011 = scrub_bits(f011);
+            d100 = scrub_bits(f100); d101 = scrub_bits(f101); d110 = scrub_bits(f110); d111 = scrub_bits(f111);
           }
-          const float out = __double2float_rn(t);
-          zb[((size_t)i * T1 + j) * T2 + k] = out;
-          key = float_to_ordered(out);
-          tile_max = max(tile_max, key);
-          tmin = min(tmin, key);
+          // scipy NI_ZoomShift order: t += ((v*wx)*wy)*wz, taps in (x,y,z) lexicographic order, no FMA contraction
+          t = __dadd_rn(t, __dmul_rn(__dmul_rn(__dmul_rn(d000, wx0), e.w0), wz0));
+          t = __dadd_rn(t, __dmul_rn(__dmul_rn(__dmul_rn(d001, wx0), e.w0), wz1));
+          t = __dadd_rn(t, __dmul_rn(__dmul_rn(__dmul_rn(d010, wx0), e.w1), wz0));
+          t = __dadd_rn(t, __dmul_rn(__dmul_rn(__dmul_rn(d011, wx0), e.w1), wz1));
+          t = __dadd_rn(t, __dmul_rn(__dmul_rn(__dmul_rn(d100, wx1), e.w0), wz0));
+          t = __dadd_rn(t, __dmul_rn(__dmul_rn(__dmul_rn(d101, wx1), e.w0), wz1));
+          t = __dadd_rn(t, __dmul_rn(__dmul_rn(__dmul_rn(d110, wx1), e.w1), wz0));
+          t = __dadd_rn(t, __dmul_rn(__dmul_rn(__dmul_rn(d111, wx1), e.w1), wz1));
+        }
+        const float out = __double2float_rn(t);
+        if (act) {
+          *op = out;
+          tmaxf = fmaxf(tmaxf, out);
+          vmin = fminf(vmin, out);
           if (out > 0.0f) atomicAdd(&s_hist[__float_as_uint(out) >> 19], 1u);
         }
-        const uint32_t wmax = __reduce_max_sync(0xffffffffu, key);
-        if ((tid & 31) == 0 && wmax != 0) atomicMax(&s_jmax[j], wmax);
+        if (NEED_JMAX) {
+          const uint32_t wmax = __reduce_max_sync(0xffffffffu, act ? key_of(out) : 0u);
+          if (lane == 0 && wmax != 0) atomicMax(&s_jmax[j], wmax);
+        }
       }
       __syncwarp();
-      if ((tid & 31) == 0) mbar_arrive(bar_empty + stage * 8);    // this warp is done reading the stage
-      kmax = max(kmax, tile_max);
-      const uint32_t imx = __reduce_max_sync(0xffffffffu, tile_max);
-      if ((tid & 31) == 0 && imx != 0) atomicMax(&s_imax[i], imx);
+      if (lane == 0) mbar_arrive(bar_empty + stage * 8);    // this warp is done reading the stage
+      kmaxf = fmaxf(kmaxf, tmaxf);
+      const uint32_t imx = __reduce_max_sync(0xffffffffu, tmaxf == -INFINITY ? 0u : key_of(tmaxf));
+      if (lane == 0 && imx != 0) atomicMax(&s_imax[i], imx);
     }
-    if (act && kmax != 0) atomicMax(&st->plane_max[2][k], kmax);
-    const uint32_t wmin = __reduce_min_sync(0xffffffffu, tmin);
-    if ((tid & 31) == 0 && wmin != 0xffffffffu) atomicMin(&st->gmin_key, wmin);
+    if (act && kmaxf != -INFINITY) atomicMax(&st->plane_max[2][k], key_of(kmaxf));
+    const uint32_t wmin = __reduce_min_sync(0xffffffffu, vmin == INFINITY ? 0xffffffffu : key_of(vmin));
+    if (lane == 0 && wmin != 0xffffffffu) atomicMin(&st->gmin_key, wmin);
   }
   __syncthreads();
   for (int i = tid; i < kH0; i += nthr) {
@@ -341,7 +382,8 @@ resample_tma_kernel(const float* __restrict__ raw, float* __restrict__ zoomed, S
     if (c) atomicAdd(&st->hist0[i], c);
   }
   for (int i = tid; i < T0; i += nthr) if (s_imax[i]) atomicMax(&st->plane_max[0][i], s_imax[i]);
-  for (int i = tid; i < T1; i += nthr) if (s_jmax[i]) atomicMax(&st->plane_max[1][i], s_jmax[i]);
+  if (NEED_JMAX)
+    for (int i = tid; i < T1; i += nthr) if (s_jmax[i]) atomicMax(&st->plane_max[1][i], s_jmax[i]);
 }
 
 // ------------------------------------------------------------------------------------------------------
@@ -722,21 +764,28 @@ extern "C" int pdf_resample_stats(const pdf_preproc_cfg* cfg, int batch, const f
     size_t smem = 0;
     for (; TJ >= 2; TJ >>= 1) {
       NR = (int)((TJ - 1) * ystep) + 3;
-      smem = (size_t)kResStages * 2 * NR * Z * 4 + fixed + 8 + 2 * kResStages * 8 + 128;
+      smem = (size_t)kResStages * 2 * NR * Z * 4 + fixed + 16 + (size_t)T1 * 32 + 2 * kResStages * 8 + 128;
       if (smem <= 110 * 1024) break;
     }
     if (TJ >= 2 && smem <= 200 * 1024) {
-      static size_t configured = 0;
-      if (smem > configured) {
-        PDF_CHECK_CUDA(cudaFuncSetAttribute(resample_tma_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-        configured = smem;
+      bool need_jmax = false;
+      for (int a = 0; a < cfg->n_axes; ++a) need_jmax |= cfg->axes[a] == 1;
+      static size_t configured[2] = {0, 0};
+      if (smem > configured[need_jmax]) {
+        if (need_jmax) PDF_CHECK_CUDA(cudaFuncSetAttribute(resample_tma_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        else PDF_CHECK_CUDA(cudaFuncSetAttribute(resample_tma_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        configured[need_jmax] = smem;
       }
       const int ntiles = T0 * ceil_div(T1, TJ);
       const int per_sm = max(1, min(4, (int)((220 * 1024) / (smem + 1024))));
       // one resident wave: never more blocks than the chip holds at once (a second partial wave would double the time)
       const int blocks_per_subject = max(1, min(ntiles, (num_sms() * per_sm) / batch));
-      resample_tma_kernel<<<dim3(blocks_per_subject, batch), 32 + 2 * KT, smem, s>>>(d_raw, d_zoomed, w.st, w.tabs, X, Y, Z, T0, T1,
-                                                                                     T2, TJ, NR, KT);
+      if (need_jmax)
+        resample_tma_kernel<true><<<dim3(blocks_per_subject, batch), 32 + 2 * KT, smem, s>>>(d_raw, d_zoomed, w.st, w.tabs, X, Y, Z, T0,
+                                                                                           T1, T2, TJ, NR, KT);
+      else
+        resample_tma_kernel<false><<<dim3(blocks_per_subject, batch), 32 + 2 * KT, smem, s>>>(d_raw, d_zoomed, w.st, w.tabs, X, Y, Z, T0,
+                                                                                            T1, T2, TJ, NR, KT);
       PDF_CHECK_LAUNCH();
       return PDF_OK;
     }

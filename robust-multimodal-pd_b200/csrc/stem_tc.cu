@@ -50,7 +50,7 @@ stem_fused_kernel(const __grid_constant__ CUtensorMap tmap_w, const StemParams p
   const int iy0 = 2 * cy0 - 3, ix0 = 2 * cx0 - 3;    // input-patch origin
 
   const uint32_t bar_w = bar + 16;
-  if (tid == 0) {
+  if (warp == 0 && elect_one()) {
     mbar_init(bar, 1);
     mbar_init(bar_w, 1);
     fence_barrier_init();
@@ -116,7 +116,7 @@ stem_fused_kernel(const __grid_constant__ CUtensorMap tmap_w, const StemParams p
   const uint32_t tmem_base = *tmem_slot;
 
   // 3. MMAs
-  if (tid == 0) {
+  if (warp == 0 && elect_one()) {
     constexpr uint32_t idesc = make_idesc(64);
     const uint32_t a0 = base, w0 = base + 256 * 128;
     mbar_wait(bar_w, 0);

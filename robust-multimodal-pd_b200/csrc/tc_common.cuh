@@ -14,6 +14,14 @@ constexpr uint32_t kSpinLimit = 1u << 26;        // turns a protocol bug into a 
 // ---------------------------------------------------------------------------------------- PTX wrappers
 __device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
 
+// exactly one lane of a converged warp gets true; ptxas then knows the guarded code runs in a single thread and emits the
+// uniform-datapath instructions (UTCHMMA / UTMALDG / UTCBAR) without a per-instruction ELECT retry loop
+__device__ __forceinline__ bool elect_one() {
+  uint32_t pred;
+  asm volatile("{\n\t.reg .pred p;\n\telect.sync _|p, 0xffffffff;\n\tselp.u32 %0, 1, 0, p;\n\t}" : "=r"(pred));
+  return pred != 0;
+}
+
 __device__ __forceinline__ void mbar_init(uint32_t bar, uint32_t count) {
   asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(bar), "r"(count));
 }

@@ -8,6 +8,7 @@ ResNet18/50 state_dict loads unchanged.
 from __future__ import annotations
 
 import ctypes as C
+import os
 from typing import Dict, List, Tuple
 
 import torch
@@ -162,6 +163,132 @@ def flops_per_image(arch: str, input_size: int = 224, folded_stem: bool = False)
     return total
 
 
+def lower_resnet(arch: str, n: int, S: int, bf16: bool, fused_stem: bool, chunks: List[int]):
+    """The network as a flat, ordered list of ops over symbolic buffers.
+
+    Returns (ops, extents, final_hw): ops = [(name, fields, refs, weight_name)], where refs maps the pointer fields
+    d_in / d_out / d_residual to (buffer, byte offset); extents = bytes each buffer must hold.  Buffers: "input",
+    "output", o0..o4 (stage outputs of the chunk being consumed), s0..s3 (scratch inside a stage).
+
+    chunks[k] = images per launch of stage k (0 = stem, 1..4 = residual stages).  The op list is depth-first: a
+    stage-k chunk is preceded by the stage-(k-1) chunks that produce its input, so the big early tensors are consumed
+    while they are still in L2."""
+    kind, _, _ = RESNET_SPECS[arch]
+    prec = _lib.PREC_BF16 if bf16 else _lib.PREC_F32
+    esz = 2 if bf16 else 4
+    exp = 1 if kind == "basic" else 4
+    h1 = (S + 6 - 7) // 2 + 1
+    h2 = (h1 + 2 - 3) // 2 + 1
+    in_bytes = S * S * 2 if bf16 else S * S * 3 * 4
+    # stage geometry: spatial size and channels of each stage's OUTPUT (stage 0 = stem + maxpool)
+    hw, ch = [h2], [64]
+    for k in range(1, 5):
+        hw.append(hw[-1] if k == 1 else (hw[-1] + 2 - 3) // 2 + 1)
+        ch.append(_PLANES[k - 1] * exp)
+
+    convs = conv_list(arch)
+    stage_blocks: List[List[Dict[str, dict]]] = [[] for _ in range(5)]
+    for cv in convs[1:]:
+        k, bi = int(cv["block"][5]), int(cv["block"].split(".")[1])
+        while len(stage_blocks[k]) <= bi:
+            stage_blocks[k].append({})
+        stage_blocks[k][bi][cv["role"]] = cv
+
+    extents: Dict[str, int] = {}
+    ops: List[tuple] = []
+    scratch = ("s0", "s1", "s2", "s3")
+
+    def ref(buf, off, nbytes):
+        extents[buf] = max(extents.get(buf, 0), off + nbytes)
+        return (buf, off)
+
+    def add(name, refs, wname=None, **kw):
+        ops.append((name, kw, refs, wname))
+
+    def out_bytes(k, count, final=False):
+        return count * hw[k] * hw[k] * ch[k] * (4 if (final and bf16) else esz)
+
+    def emit_stem(start, count, dst):
+        src = ref("input", start * in_bytes, count * in_bytes)
+        if bf16 and fused_stem:
+            # conv1 + bn1 + relu + maxpool in one kernel (stem_tc.cu): the patch matrix never leaves shared memory
+            add("stem.fused", dict(d_in=src, d_out=dst), "conv1", kind=_lib.OP_STEM_FUSED, precision=prec, n=count, h=S, w=S, c=1,
+                k=64, r=7, s=7, stride=2, pad=3, ho=h2, wo=h2, relu=1)
+            return
+        conv_out = ref("s0", 0, count * h1 * h1 * 64 * esz)
+        if bf16:
+            col = ref("s1", 0, count * h1 * h1 * 64 * esz)
+            add("stem.im2col", dict(d_in=src, d_out=col), None, kind=_lib.OP_STEM_IM2COL, precision=prec, n=count, h=S, w=S, c=1, k=64,
+                r=7, s=7, stride=2, pad=3, ho=h1, wo=h1)
+            add("conv1", dict(d_in=col, d_out=conv_out), "conv1", kind=_lib.OP_CONV, precision=prec, n=count, h=h1, w=h1, c=64, k=64,
+                r=1, s=1, stride=1, pad=0, ho=h1, wo=h1, relu=1)
+        else:
+            add("conv1", dict(d_in=src, d_out=conv_out), "conv1", kind=_lib.OP_CONV, precision=prec, n=count, h=S, w=S, c=3, k=64, r=7,
+                s=7, stride=2, pad=3, ho=h1, wo=h1, relu=1)
+        add("maxpool", dict(d_in=conv_out, d_out=dst), None, kind=_lib.OP_MAXPOOL, precision=prec, n=count, h=h1, w=h1, c=64, ho=h2,
+            wo=h2)
+
+    def emit_stage(k, count, src, dst):
+        """All blocks of residual stage k over `count` images: src = stage k-1 output, dst = stage k output."""
+        x, x_h, x_c = src, hw[k - 1], ch[k - 1]
+        blocks = stage_blocks[k]
+        free = list(scratch)
+        for bi, cvs in enumerate(blocks):
+            last_block = bi == len(blocks) - 1
+            idn, idn_slot = x, None
+            if "down" in cvs:
+                cv = cvs["down"]
+                idn_slot = free.pop(0)
+                idn = ref(idn_slot, 0, out_bytes(k, count))
+                add(cv["name"], dict(d_in=x, d_out=idn), cv["name"], kind=_lib.OP_CONV, precision=prec, n=count, h=x_h, w=x_h, c=x_c,
+                    k=cv["cout"], r=1, s=1, stride=cv["stride"], pad=0, ho=hw[k], wo=hw[k], relu=0)
+            t, t_h, t_c, t_slot = x, x_h, x_c, None
+            seq = [cvs["a"]] + ([cvs["b"]] if "b" in cvs else []) + [cvs["last"]]
+            for cv in seq:
+                ho = (t_h + 2 * cv["pad"] - cv["k"]) // cv["stride"] + 1
+                is_last = cv["role"] == "last"
+                final = is_last and last_block and k == 4
+                if is_last and last_block:
+                    o, o_slot = dst, None
+                else:
+                    o_slot = free.pop(0)
+                    o = ref(o_slot, 0, count * ho * ho * cv["cout"] * esz)
+                refs = dict(d_in=t, d_out=o)
+                if is_last:
+                    refs["d_residual"] = idn
+                add(cv["name"], refs, cv["name"], kind=_lib.OP_CONV, precision=prec, n=count, h=t_h, w=t_h, c=t_c, k=cv["cout"],
+                    r=cv["k"], s=cv["k"], stride=cv["stride"], pad=cv["pad"], ho=ho, wo=ho, relu=1,
+                    out_f32=1 if (final and bf16) else 0)
+                if t_slot is not None:
+                    free.append(t_slot)
+                t, t_h, t_c, t_slot = o, ho, cv["cout"], o_slot
+            if idn_slot is not None:
+                free.append(idn_slot)
+            if x[0] in scratch:
+                free.append(x[0])
+            x, x_h, x_c = t, t_h, t_c
+
+    def emit(k, start, count, dst):
+        """Produce the stage-k output of images [start, start+count) at `dst`, depth-first over the earlier stages."""
+        if k == 0:
+            emit_stem(start, count, dst)
+            return
+        below = f"o{k - 1}"                       # holds the stage k-1 output of this chunk only
+        per = hw[k - 1] * hw[k - 1] * ch[k - 1] * esz
+        for s0 in range(0, count, chunks[k - 1]):
+            cnt = min(chunks[k - 1], count - s0)
+            emit(k - 1, start + s0, cnt, ref(below, s0 * per, cnt * per))
+        emit_stage(k, count, (below, 0), dst)
+
+    per4 = out_bytes(4, 1, final=True)
+    for s0 in range(0, n, chunks[4]):
+        cnt = min(chunks[4], n - s0)
+        emit(4, s0, cnt, ref("o4", s0 * per4, cnt * per4))
+    add("avgpool", dict(d_in=("o4", 0), d_out=ref("output", 0, n * ch[4] * 4)), None, kind=_lib.OP_AVGPOOL, precision=prec, n=n,
+        h=hw[4], w=hw[4], c=ch[4], out_f32=1 if bf16 else 0)
+    return ops, extents, hw[4]
+
+
 class ResNetEncoder:
     """Runs `n_images` slices [n, S, S] through the backbone and returns [n, D] f32 embeddings.
 
@@ -171,7 +298,8 @@ class ResNetEncoder:
     """
 
     def __init__(self, state_dict: Dict[str, torch.Tensor], n_images: int, input_size: int = 224,
-                 precision: str = "bf16", arch: str | None = None, device=None, fused_stem: bool = True):
+                 precision: str = "bf16", arch: str | None = None, device=None, fused_stem: bool = True,
+                 front_chunk: int | None = None):
         _lib.require_cuda()
         self.lib = _lib.load()
         self.device = torch.device(device if device is not None else f"cuda:{torch.cuda.current_device()}")
@@ -184,6 +312,11 @@ class ResNetEncoder:
         self.bf16 = precision == "bf16"
         self.precision = precision
         self.fused_stem = bool(fused_stem)
+        env_chunk = os.environ.get("PDFUSION_B200_CHUNKS")          # "c1" or "c1,c2,c3,c4" (tuning hook)
+        if front_chunk is None and env_chunk:
+            vals = [int(v) for v in env_chunk.split(",")]
+            front_chunk = vals[0] if len(vals) == 1 else vals
+        self.front_chunk = front_chunk
         sd = {k: v.detach().to("cpu") for k, v in state_dict.items()}
         self._keep: List[torch.Tensor] = []     # device tensors referenced by the plan
         self._build(sd)
@@ -209,114 +342,65 @@ class ResNetEncoder:
         return self._dev(w.permute(2, 3, 1, 0).float()), self._dev(scale.float()), self._dev(shift.float())  # [R,S,C,K]
 
     # -- op list ---------------------------------------------------------------------------------
+    def _chunk_sizes(self, h2: int, esz: int) -> List[int]:
+        """Images per launch for the stem (index 0) and the four residual stages (1..4).
+
+        `front_chunk` (or PDFUSION_B200_CHUNKS) turns on depth-first execution: a stage-k chunk is preceded by the
+        stage-(k-1) chunks that produce its input, so early-stage tensors can be consumed from L2.  Measured on B200
+        (gpurun_out/sweep_chunks.txt, C2, 768 slices) it LOSES 10-30 %: the 56x56 layers are bound by the
+        shared-memory operand feed of the N=64 MMAs, not by HBM, and every extra launch costs a prologue and a tail.
+        The default is therefore one launch per layer over the whole batch."""
+        if isinstance(self.front_chunk, (list, tuple)):          # explicit per-stage sizes (stages 1..4)
+            c = [max(1, min(self.n, int(v))) for v in self.front_chunk]
+            c = (c + [self.n] * 4)[:4]
+            return [c[0]] + c
+        if self.front_chunk is not None:
+            c1 = max(1, min(self.n, int(self.front_chunk)))
+            c = [c1, c1]
+            for _ in range(3):
+                c.append(min(self.n, c[-1] * 2))
+            c[4] = self.n
+            return c
+        return [self.n] * 5
+
     def _build(self, sd):
         n, S = self.n, self.S
-        prec = _lib.PREC_BF16 if self.bf16 else _lib.PREC_F32
         esz = 2 if self.bf16 else 4
-        dt = torch.bfloat16 if self.bf16 else torch.float32
         h1 = (S + 6 - 7) // 2 + 1
         h2 = (h1 + 2 - 3) // 2 + 1
-        exp = 1 if self.kind == "basic" else 4
-        max_elems = max(n * h1 * h1 * 64, n * h2 * h2 * 64 * exp)
-        slot_bytes = max_elems * esz
-        hf = h2
-        for _ in range(3):
-            hf = (hf + 2 - 3) // 2 + 1
-        slot_bytes = max(slot_bytes, n * hf * hf * self.emb_dim * 4)
-        self.slots = [torch.empty(slot_bytes, dtype=torch.uint8, device=self.device) for _ in range(5)]
-        free = list(range(5))
         if self.bf16:
             self.input = torch.empty((n, S, S), dtype=torch.bfloat16, device=self.device)
         else:
             self.input = torch.empty((n, S, S, 3), dtype=torch.float32, device=self.device)
         self.output = torch.empty((n, self.emb_dim), dtype=torch.float32, device=self.device)
-        ops: List[_lib.Op] = []
+        self.chunks = self._chunk_sizes(h2, esz)
+        ops, extents, self.final_hw = lower_resnet(self.arch, n, S, self.bf16, self.fused_stem, self.chunks)
+        weights = {cv["name"]: self._conv_weights(sd, cv) for cv in conv_list(self.arch)}
+
+        self.buffers = {name: torch.empty(nbytes, dtype=torch.uint8, device=self.device) for name, nbytes in extents.items()
+                        if name not in ("input", "output")}
+        base = {name: t.data_ptr() for name, t in self.buffers.items()}
+        base["input"] = self.input.data_ptr()
+        base["output"] = self.output.data_ptr()
+        cops: List[_lib.Op] = []
         self.op_names: List[str] = []
-
-        def add(name, **kw):
+        for name, kw, refs, wname in ops:
             op = _lib.Op()
-            for k, v in kw.items():
-                setattr(op, k, v)
-            ops.append(op)
+            for key, v in kw.items():
+                setattr(op, key, v)
+            for key, (buf, off) in refs.items():
+                setattr(op, key, base[buf] + off)
+            if wname is not None:
+                w, sc, b = weights[wname]
+                op.d_weight, op.d_scale, op.d_bias = w.data_ptr(), _lib.ptr(sc), b.data_ptr()
+            cops.append(op)
             self.op_names.append(name)
-
-        def sp(i):
-            return self.slots[i].data_ptr()
-
-        convs = conv_list(self.arch)
-        # ---- stem
-        stem = convs[0]
-        w, sc, b = self._conv_weights(sd, stem)
-        if self.bf16 and self.fused_stem:
-            # conv1 + bn1 + relu + maxpool in one kernel (stem_tc.cu): the patch matrix never leaves shared memory
-            s_pool = free.pop(0)
-            add("stem.fused", kind=_lib.OP_STEM_FUSED, precision=prec, n=n, h=S, w=S, c=1, k=64, r=7, s=7, stride=2, pad=3,
-                ho=h2, wo=h2, relu=1, d_in=self.input.data_ptr(), d_weight=w.data_ptr(), d_bias=b.data_ptr(), d_out=sp(s_pool))
-        else:
-            s_out = free.pop(0)
-            if self.bf16:
-                s_col = free.pop(0)
-                add("stem.im2col", kind=_lib.OP_STEM_IM2COL, precision=prec, n=n, h=S, w=S, c=1, k=64, r=7, s=7, stride=2, pad=3,
-                    ho=h1, wo=h1, d_in=self.input.data_ptr(), d_out=sp(s_col))
-                add("conv1", kind=_lib.OP_CONV, precision=prec, n=n, h=h1, w=h1, c=64, k=64, r=1, s=1, stride=1, pad=0, ho=h1, wo=h1,
-                    relu=1, d_in=sp(s_col), d_weight=w.data_ptr(), d_bias=b.data_ptr(), d_out=sp(s_out))
-                free.append(s_col)
-            else:
-                add("conv1", kind=_lib.OP_CONV, precision=prec, n=n, h=S, w=S, c=3, k=64, r=7, s=7, stride=2, pad=3, ho=h1, wo=h1,
-                    relu=1, d_in=self.input.data_ptr(), d_weight=w.data_ptr(), d_scale=sc.data_ptr(), d_bias=b.data_ptr(), d_out=sp(s_out))
-            s_pool = free.pop(0)
-            add("maxpool", kind=_lib.OP_MAXPOOL, precision=prec, n=n, h=h1, w=h1, c=64, ho=h2, wo=h2, d_in=sp(s_out), d_out=sp(s_pool))
-            free.append(s_out)
-        cur, cur_h, cur_c = s_pool, h2, 64
-        # ---- residual stages
-        blocks: Dict[str, List[dict]] = {}
-        order: List[str] = []
-        for cv in convs[1:]:
-            if cv["block"] not in blocks:
-                blocks[cv["block"]] = []
-                order.append(cv["block"])
-            blocks[cv["block"]].append(cv)
-        last_block = order[-1]
-        for bname in order:
-            cvs = {cv["role"]: cv for cv in blocks[bname]}
-            x_slot, x_h, x_c = cur, cur_h, cur_c
-            idn_slot = x_slot
-            if "down" in cvs:
-                cv = cvs["down"]
-                ho = (x_h + 2 * cv["pad"] - cv["k"]) // cv["stride"] + 1
-                w, sc, b = self._conv_weights(sd, cv)
-                idn_slot = free.pop(0)
-                add(cv["name"], kind=_lib.OP_CONV, precision=prec, n=n, h=x_h, w=x_h, c=x_c, k=cv["cout"], r=1, s=1, stride=cv["stride"],
-                    pad=0, ho=ho, wo=ho, relu=0, d_in=sp(x_slot), d_weight=w.data_ptr(), d_scale=_lib.ptr(sc), d_bias=b.data_ptr(),
-                    d_out=sp(idn_slot))
-            t_slot, t_h, t_c = x_slot, x_h, x_c
-            seq = [cvs["a"]] + ([cvs["b"]] if "b" in cvs else []) + [cvs["last"]]
-            for cv in seq:
-                ho = (t_h + 2 * cv["pad"] - cv["k"]) // cv["stride"] + 1
-                w, sc, b = self._conv_weights(sd, cv)
-                o_slot = free.pop(0)
-                is_last = cv["role"] == "last"
-                final = is_last and bname == last_block
-                add(cv["name"], kind=_lib.OP_CONV, precision=prec, n=n, h=t_h, w=t_h, c=t_c, k=cv["cout"], r=cv["k"], s=cv["k"],
-                    stride=cv["stride"], pad=cv["pad"], ho=ho, wo=ho, relu=1, out_f32=1 if (final and self.bf16) else 0,
-                    d_in=sp(t_slot), d_weight=w.data_ptr(), d_scale=_lib.ptr(sc), d_bias=b.data_ptr(),
-                    d_residual=sp(idn_slot) if is_last else None, d_out=sp(o_slot))
-                if t_slot != x_slot:
-                    free.append(t_slot)
-                t_slot, t_h, t_c = o_slot, ho, cv["cout"]
-            if idn_slot != x_slot:
-                free.append(idn_slot)
-            free.append(x_slot)
-            cur, cur_h, cur_c = t_slot, t_h, t_c
-        add("avgpool", kind=_lib.OP_AVGPOOL, precision=prec, n=n, h=cur_h, w=cur_h, c=cur_c, out_f32=1 if self.bf16 else 0,
-            d_in=sp(cur), d_out=self.output.data_ptr())
-        self.final_hw = cur_h
-        arr = (_lib.Op * len(ops))(*ops)
+        arr = (_lib.Op * len(cops))(*cops)
         plan = C.c_void_p()
-        _lib.check(self.lib.pdf_plan_create(C.byref(plan), arr, len(ops)), "pdf_plan_create")
+        _lib.check(self.lib.pdf_plan_create(C.byref(plan), arr, len(cops)), "pdf_plan_create")
         self.plan = plan
-        self.n_ops = len(ops)
-        self.ops = ops
+        self.n_ops = len(cops)
+        self.ops = cops
 
     def __del__(self):
         try:

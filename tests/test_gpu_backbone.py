@@ -119,9 +119,24 @@ def test_fused_stem_equals_unfused(S, n):
         hp = ((S - 1) // 2 + 1 + 2 - 3) // 2 + 1
         first_conv = enc.ops[n_stem]           # the pooled stem output is the input of the first residual conv
         assert first_conv.h == hp
-        slot = [sl for sl in enc.slots if sl.data_ptr() == first_conv.d_in][0]
+        slot = enc.buffers["o0"]                # stage-0 (stem + maxpool) output of the first chunk
+        assert slot.data_ptr() == first_conv.d_in
         outs.append(slot[: n * hp * hp * 64 * 2].view(torch.bfloat16).clone())
     assert torch.equal(outs[0], outs[1])
+
+
+@pytest.mark.parametrize("arch,n,chunks", [("resnet18", 7, [2, 3, 4, 7]), ("resnet50", 5, [1, 2, 2, 4])])
+def test_chunked_front_is_bit_identical(arch, n, chunks):
+    """Depth-first chunking only changes WHICH images a launch covers, never the arithmetic of an output element."""
+    sd = _sd(arch)
+    S = 96
+    x = (torch.rand(n, S, S, generator=torch.Generator().manual_seed(n)) * 2 - 1).to(torch.bfloat16).cuda()
+    outs = []
+    for fc in (chunks, [n, n, n, n]):
+        enc = ResNetEncoder(sd, n, S, precision="bf16", front_chunk=fc)
+        outs.append(enc.forward(x).clone())
+        torch.cuda.synchronize()
+    assert torch.isfinite(outs[0]).all() and torch.equal(outs[0], outs[1])
 
 
 def test_umma_shifted_descriptor_probe():

@@ -129,3 +129,94 @@ def test_evaluate_dispatch_with_a_stub_model():
         assert all(np.array_equal(got[k], w[k]) for k in w)
     y, p = predict_proba_for_scenario(m, df, masks, (None, sc, cols), cfg["scenarios"][0])
     assert len(y) == len(p) == 64
+
+
+@pytest.mark.parametrize("arch,chunks", [("resnet18", [2, 2, 3, 4, 5]), ("resnet18", [5, 5, 5, 5, 5]), ("resnet50", [1, 1, 2, 4, 3])])
+def test_lowered_op_list_computes_the_network(arch, chunks):
+    """The depth-first, chunked op list (backbone.lower_resnet) is executed by a tiny CPU interpreter over byte buffers
+    and must reproduce torch's forward of the same state_dict: checks buffer wiring, chunk offsets and scratch reuse
+    (the kernels themselves are checked on the GPU)."""
+    import torch
+    import torch.nn.functional as F
+
+    from pd_fusion_b200 import _lib
+    from pd_fusion_b200.backbone import lower_resnet
+
+    n, S = 5, 32
+    torch.manual_seed(5)
+    net = ResNet2D(arch).eval()
+    with torch.no_grad():           # make BN non-trivial
+        for m in net.modules():
+            if isinstance(m, torch.nn.BatchNorm2d):
+                m.running_mean.normal_(0, 0.1); m.running_var.uniform_(0.5, 1.5); m.weight.uniform_(0.5, 1.5); m.bias.normal_(0, 0.1)
+    sd = net.state_dict()
+    ops, extents, _ = lower_resnet(arch, n, S, bf16=False, fused_stem=False, chunks=chunks)
+    bufs = {k: np.zeros(v, dtype=np.uint8) for k, v in extents.items()}
+    x = torch.randn(n, 3, S, S)
+    bufs["input"][:] = np.frombuffer(x.permute(0, 2, 3, 1).contiguous().numpy().tobytes(), dtype=np.uint8)
+
+    def view(ref, shape):
+        buf, off = ref
+        cnt = int(np.prod(shape))
+        return bufs[buf][off:off + 4 * cnt].view(np.float32).reshape(shape)
+
+    bn = {cv["name"]: cv["bn"] for cv in conv_list(arch)}
+    for name, f, refs, wname in ops:
+        k = f["kind"]
+        xin = torch.from_numpy(view(refs["d_in"], (f["n"], f["h"], f["w"], f["c"])).copy()).permute(0, 3, 1, 2)
+        if k == _lib.OP_CONV:
+            w = sd[wname + ".weight"]
+            g, b, mu, var = (sd[bn[wname] + s] for s in (".weight", ".bias", ".running_mean", ".running_var"))
+            y = F.conv2d(xin, w, stride=f["stride"], padding=f["pad"])
+            sc = g / torch.sqrt(var + 1e-5)
+            y = y * sc.view(1, -1, 1, 1) + (b - mu * sc).view(1, -1, 1, 1)
+            if "d_residual" in refs:
+                y = y + torch.from_numpy(view(refs["d_residual"], (f["n"], f["ho"], f["wo"], f["k"])).copy()).permute(0, 3, 1, 2)
+            if f["relu"]:
+                y = torch.relu(y)
+            view(refs["d_out"], (f["n"], f["ho"], f["wo"], f["k"]))[:] = y.permute(0, 2, 3, 1).numpy()
+        elif k == _lib.OP_MAXPOOL:
+            y = F.max_pool2d(xin, 3, 2, 1)
+            view(refs["d_out"], (f["n"], f["ho"], f["wo"], f["c"]))[:] = y.permute(0, 2, 3, 1).numpy()
+        elif k == _lib.OP_AVGPOOL:
+            view(refs["d_out"], (f["n"], f["c"]))[:] = xin.mean(dim=(2, 3)).numpy()
+        else:
+            raise AssertionError(k)
+    net.fc = torch.nn.Identity()
+    with torch.no_grad():
+        ref = net(x).numpy()
+    out = bufs["output"].view(np.float32).reshape(n, -1)
+    assert np.abs(out - ref).max() <= 1e-4 * max(1.0, np.abs(ref).max())
+
+
+def test_lowering_bf16_buffers_are_written_before_read():
+    """Structural check of the bf16 / fused-stem op list: every byte an op reads was written by an earlier op."""
+    from pd_fusion_b200.backbone import lower_resnet
+    for arch in ("resnet18", "resnet50"):
+        for fused in (True, False):
+            n, S = 7, 64
+            ops, extents, _ = lower_resnet(arch, n, S, bf16=True, fused_stem=fused, chunks=[2, 2, 4, 4, 7])
+            written = {k: np.zeros(v, dtype=bool) for k, v in extents.items()}
+            written["input"][:] = True
+            for name, f, refs, _ in ops:
+                esz = 2
+                in_elems = f["n"] * f["h"] * f["w"] * f["c"]
+                if f["kind"] == 2 and f.get("out_f32"):
+                    in_bytes = in_elems * 4
+                else:
+                    in_bytes = in_elems * esz
+                buf, off = refs["d_in"]
+                assert written[buf][off:off + in_bytes].all(), (arch, fused, name, "input not produced")
+                if "d_residual" in refs:
+                    rb, ro = refs["d_residual"]
+                    assert written[rb][ro:ro + f["n"] * f["ho"] * f["wo"] * f["k"] * esz].all(), (arch, name, "residual")
+                ob, oo = refs["d_out"]
+                if f["kind"] == 2:
+                    nbytes = f["n"] * f["c"] * 4
+                elif f["kind"] in (1,):
+                    nbytes = f["n"] * f["ho"] * f["wo"] * f["c"] * esz
+                else:
+                    nbytes = f["n"] * f["ho"] * f["wo"] * f["k"] * (4 if f.get("out_f32") else esz)
+                assert (ob, oo) != refs["d_in"] and oo + nbytes <= extents[ob]
+                written[ob][oo:oo + nbytes] = True
+            assert written["output"].all()

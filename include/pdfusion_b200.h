@@ -214,6 +214,11 @@ int pdf_selftest_umma(int M, int N, int K, const void* d_a_bf16, const void* d_b
  * operand reuse a halo-resident 3x3 convolution needs. */
 int pdf_selftest_umma_shift(int N, int shift, int mode, const void* d_a_bf16, const void* d_b_bf16, float* d_c, pdf_stream_t stream);
 
+/* Probe: tensor-pipe rate of back-to-back shared-memory-operand MMAs (M=128, N in {64,128,256}, K=16) with resident
+ * operands; `iters` x 36 MMAs per CTA, `grid` CTAs; mode bit 0 = walk the halo conv's 9 row-shifted A windows.
+ * d_cycles[grid] receives the SM-clock cycles each CTA took (profiles/r01_umma_rate.txt). */
+int pdf_selftest_umma_rate(int N, int iters, int mode, int grid, unsigned long long* d_cycles, pdf_stream_t stream);
+
 /* Test hook: disable != 0 makes later pdf_plan_create calls route 3x3/s1 64->64 convolutions through the generic
  * im2col kernel instead of the halo-resident kernel (A/B parity of the two tensor-core kernels). */
 int pdf_debug_disable_halo(int disable);

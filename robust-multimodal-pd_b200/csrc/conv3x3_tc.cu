@@ -42,6 +42,8 @@ conv3x3_c64_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_cons
   const uint32_t bar_w = bar0, bar_afull = bar0 + 8, bar_aempty = bar_afull + 8 * kHaloStages;
   const uint32_t bar_accfull = bar_aempty + 8 * kHaloStages, bar_accempty = bar_accfull + 16;
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(smem + (bar_accempty + 16 - base));
+  float4* s_bias4 = reinterpret_cast<float4*>(smem + (bar0 + 96 - base));               // 64 f32, broadcast reads in the epilogue
+  if (threadIdx.x < 16) s_bias4[threadIdx.x] = __ldg(reinterpret_cast<const float4*>(p.bias) + threadIdx.x);
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   if (threadIdx.x == 0) {
@@ -139,8 +141,9 @@ conv3x3_c64_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_cons
       const uint32_t accphase = (uint32_t)(it >> 1) & 1u;
       const int n = tile / p.tiles_per_image;
       const int m0 = (tile - n * p.tiles_per_image) * kHaloBM;
-      // residual rows of both halves are fetched BEFORE waiting on the accumulator: their latency hides behind the MMAs
-      uint4 res[2][8];
+      // residual rows of both halves are fetched BEFORE waiting on the accumulator: their latency hides behind the MMAs.
+      // Each thread owns one output row (128 bytes): 256-bit accesses move it as four full sectors.
+      uint32_t res[2][4][8];
       bool valid[2];
       size_t obase[2];
 #pragma unroll
@@ -150,9 +153,8 @@ conv3x3_c64_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_cons
         valid[half] = pp < p.H && qq < p.W;
         obase[half] = (((size_t)n * p.H + pp) * p.W + qq) * 64;
         if (p.residual && valid[half]) {
-          const uint4* rp = reinterpret_cast<const uint4*>(p.residual + obase[half]);
 #pragma unroll
-          for (int i = 0; i < 8; ++i) res[half][i] = __ldg(rp + i);
+          for (int i = 0; i < 4; ++i) ldg256_nc(p.residual + obase[half] + i * 16, res[half][i]);
         }
       }
       mbar_wait(bar_accfull + 8 * acc, accphase);
@@ -167,20 +169,18 @@ conv3x3_c64_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_cons
             float f[32];
 #pragma unroll
             for (int i = 0; i < 32; i += 4) {
-              const float4 b = __ldg(reinterpret_cast<const float4*>(p.bias + c0 + i));
+              const float4 b = s_bias4[(c0 + i) >> 2];
               f[i] = __uint_as_float(v[i]) + b.x; f[i + 1] = __uint_as_float(v[i + 1]) + b.y;
               f[i + 2] = __uint_as_float(v[i + 2]) + b.z; f[i + 3] = __uint_as_float(v[i + 3]) + b.w;
             }
             if (p.residual) {
 #pragma unroll
-              for (int i = 0; i < 4; ++i) {
-                const uint4 r = res[half][(c0 >> 3) + i];
-                const __nv_bfloat162* h = reinterpret_cast<const __nv_bfloat162*>(&r);
+              for (int i = 0; i < 2; ++i) {
 #pragma unroll
-                for (int j = 0; j < 4; ++j) {
-                  const float2 x = __bfloat1622float2(h[j]);
-                  f[i * 8 + j * 2] += x.x;
-                  f[i * 8 + j * 2 + 1] += x.y;
+                for (int j = 0; j < 8; ++j) {
+                  const uint32_t w = res[half][(c0 >> 4) + i][j];
+                  f[i * 16 + j * 2] += bf16_lo(w);
+                  f[i * 16 + j * 2 + 1] += bf16_hi(w);
                 }
               }
             }
@@ -188,15 +188,13 @@ conv3x3_c64_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_cons
 #pragma unroll
               for (int i = 0; i < 32; ++i) f[i] = fmaxf(f[i], 0.f);
             }
-            uint4* op = reinterpret_cast<uint4*>(p.out + obase[half] + c0);
+            __nv_bfloat16* op = p.out + obase[half] + c0;
 #pragma unroll
-            for (int i = 0; i < 4; ++i) {
-              uint4 ov;
-              __nv_bfloat162* h = reinterpret_cast<__nv_bfloat162*>(&ov);
-#pragma unroll
-              for (int j = 0; j < 4; ++j) h[j] = __floats2bfloat162_rn(f[i * 8 + j * 2], f[i * 8 + j * 2 + 1]);
-              op[i] = ov;
-            }
+            for (int i = 0; i < 2; ++i)
+              stg256(op + i * 16, pack_bf16x2(f[i * 16 + 0], f[i * 16 + 1]), pack_bf16x2(f[i * 16 + 2], f[i * 16 + 3]),
+                     pack_bf16x2(f[i * 16 + 4], f[i * 16 + 5]), pack_bf16x2(f[i * 16 + 6], f[i * 16 + 7]),
+                     pack_bf16x2(f[i * 16 + 8], f[i * 16 + 9]), pack_bf16x2(f[i * 16 + 10], f[i * 16 + 11]),
+                     pack_bf16x2(f[i * 16 + 12], f[i * 16 + 13]), pack_bf16x2(f[i * 16 + 14], f[i * 16 + 15]));
           }
         }
       }
@@ -212,7 +210,7 @@ conv3x3_c64_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_cons
 
 int halo_smem_bytes(int NR, int Wp) {
   const int a_bytes = (NR * Wp * 128 + 1023) & ~1023;
-  return 9 * 8192 + kHaloStages * a_bytes + 8 * (1 + 2 * kHaloStages + 4) + 16 + 1024;
+  return 9 * 8192 + kHaloStages * a_bytes + 8 * (1 + 2 * kHaloStages + 4) + 32 + 256 + 1024;
 }
 
 bool halo_eligible(const pdf_op& op) {

@@ -163,11 +163,11 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant
 #pragma unroll 1
         for (int c0 = 0; c0 < BLOCK_N; c0 += 32) {
           const int col = n0 + c0;
-          uint4 res[4];
+          uint32_t res[2][8];
           if (p.residual && mvalid) {             // issue the residual loads before the TMEM read so both latencies overlap
-            const uint4* rp = reinterpret_cast<const uint4*>(p.residual + (size_t)m * p.Cout + col);
-#pragma unroll
-            for (int i = 0; i < 4; ++i) res[i] = __ldg(rp + i);
+            const __nv_bfloat16* rp = p.residual + (size_t)m * p.Cout + col;
+            ldg256_nc(rp, res[0]);
+            ldg256_nc(rp + 16, res[1]);
           }
           uint32_t v[32];
           tmem_ld32(tmem_base + ((uint32_t)(quad * 32) << 16) + (uint32_t)(acc * L::kAccCols + mt * BLOCK_N + c0), v);
@@ -184,13 +184,11 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant
             }
             if (p.residual) {
 #pragma unroll
-              for (int i = 0; i < 4; ++i) {
-                const __nv_bfloat162* h = reinterpret_cast<const __nv_bfloat162*>(&res[i]);
+              for (int i = 0; i < 2; ++i) {
 #pragma unroll
-                for (int j = 0; j < 4; ++j) {
-                  const float2 x = __bfloat1622float2(h[j]);
-                  f[i * 8 + j * 2] += x.x;
-                  f[i * 8 + j * 2 + 1] += x.y;
+                for (int j = 0; j < 8; ++j) {
+                  f[i * 16 + j * 2] += bf16_lo(res[i][j]);
+                  f[i * 16 + j * 2 + 1] += bf16_hi(res[i][j]);
                 }
               }
             }
@@ -199,19 +197,20 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant
               for (int i = 0; i < 32; ++i) f[i] = fmaxf(f[i], 0.f);
             }
             if (p.out_f32) {
-              float4* op = reinterpret_cast<float4*>(reinterpret_cast<float*>(p.out) + (size_t)m * p.Cout + col);
+              float* op = reinterpret_cast<float*>(p.out) + (size_t)m * p.Cout + col;
 #pragma unroll
-              for (int i = 0; i < 8; ++i) op[i] = make_float4(f[4 * i], f[4 * i + 1], f[4 * i + 2], f[4 * i + 3]);
+              for (int i = 0; i < 4; ++i)
+                stg256(op + i * 8, __float_as_uint(f[8 * i]), __float_as_uint(f[8 * i + 1]), __float_as_uint(f[8 * i + 2]),
+                       __float_as_uint(f[8 * i + 3]), __float_as_uint(f[8 * i + 4]), __float_as_uint(f[8 * i + 5]),
+                       __float_as_uint(f[8 * i + 6]), __float_as_uint(f[8 * i + 7]));
             } else {
-              uint4* op = reinterpret_cast<uint4*>(reinterpret_cast<__nv_bfloat16*>(p.out) + (size_t)m * p.Cout + col);
+              __nv_bfloat16* op = reinterpret_cast<__nv_bfloat16*>(p.out) + (size_t)m * p.Cout + col;
 #pragma unroll
-              for (int i = 0; i < 4; ++i) {
-                uint4 o;
-                __nv_bfloat162* h = reinterpret_cast<__nv_bfloat162*>(&o);
-#pragma unroll
-                for (int j = 0; j < 4; ++j) h[j] = __floats2bfloat162_rn(f[i * 8 + j * 2], f[i * 8 + j * 2 + 1]);
-                op[i] = o;
-              }
+              for (int i = 0; i < 2; ++i)
+                stg256(op + i * 16, pack_bf16x2(f[i * 16 + 0], f[i * 16 + 1]), pack_bf16x2(f[i * 16 + 2], f[i * 16 + 3]),
+                       pack_bf16x2(f[i * 16 + 4], f[i * 16 + 5]), pack_bf16x2(f[i * 16 + 6], f[i * 16 + 7]),
+                       pack_bf16x2(f[i * 16 + 8], f[i * 16 + 9]), pack_bf16x2(f[i * 16 + 10], f[i * 16 + 11]),
+                       pack_bf16x2(f[i * 16 + 12], f[i * 16 + 13]), pack_bf16x2(f[i * 16 + 14], f[i * 16 + 15]));
             }
           }
         }
@@ -269,6 +268,47 @@ umma_shift_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_const
   tc_fence_before();
   __syncthreads();
   if (warp == 1) tmem_dealloc(tmem_base, BLOCK_N);
+}
+
+// Probe kernel: tensor-pipe rate of back-to-back SS MMAs (M=128, N, K=16) on resident operands.  mode bit 0: the A
+// descriptor walks 9 row-shifted windows (the halo conv's access pattern) instead of one tile; out[cta] = cycles.
+template <int BLOCK_N>
+__global__ void __launch_bounds__(128)
+umma_rate_kernel(int iters, int mode, unsigned long long* __restrict__ out) {
+  extern __shared__ uint8_t smem_raw[];
+  const uint32_t raw_addr = smem_u32(smem_raw);
+  const uint32_t base = (raw_addr + 1023u) & ~1023u;
+  uint8_t* smem = smem_raw + (base - raw_addr);
+  const uint32_t sa = base, sb = base + 3 * kABytes, bar = sb + BLOCK_N * 128;
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(smem + 3 * kABytes + BLOCK_N * 128 + 16);
+  const int warp = threadIdx.x >> 5;
+  for (uint32_t i = threadIdx.x; i < (3 * kABytes + BLOCK_N * 128) / 4; i += blockDim.x) reinterpret_cast<uint32_t*>(smem)[i] = 0x3c003c00u;
+  if (threadIdx.x == 0) { mbar_init(bar, 1); fence_barrier_init(); }
+  if (warp == 1) tmem_alloc(smem_u32(tmem_slot), BLOCK_N < 32 ? 32 : BLOCK_N);
+  fence_proxy_async();
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_slot;
+  if (warp == 0 && elect_one()) {
+    constexpr uint32_t idesc = make_idesc(BLOCK_N);
+    const uint32_t a_lo = smem_desc_lo(sa), b_lo = smem_desc_lo(sb);
+    const long long t0 = clock64();
+    for (int i = 0; i < iters; ++i) {
+#pragma unroll
+      for (int t = 0; t < 9; ++t) {
+        const uint32_t shift = (mode & 1) ? (uint32_t)((t / 3) * 58 + (t % 3)) * 8u : 0u;
+#pragma unroll
+        for (int k = 0; k < 4; ++k) umma_f16_lo(tmem_base, a_lo + shift + k * 2, b_lo + k * 2, idesc, 1u);
+      }
+    }
+    umma_commit(bar);
+    mbar_wait(bar, 0);
+    out[blockIdx.x] = (unsigned long long)(clock64() - t0);
+  }
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 1) tmem_dealloc(tmem_base, BLOCK_N < 32 ? 32 : BLOCK_N);
 }
 
 // ---------------------------------------------------------------------------------------- host side
@@ -456,5 +496,25 @@ extern "C" int pdf_selftest_umma_shift(int N, int shift, int mode, const void* d
 /* test hook: 1 = route 3x3 s1 64->64 convs through the generic im2col kernel (A/B comparison of the halo kernel) */
 extern "C" int pdf_debug_disable_halo(int disable) {
   pdf::g_disable_halo = disable != 0;
+  return PDF_OK;
+}
+
+/* probe: cycles for `iters` x 36 back-to-back MMAs (M=128, N, K=16) per CTA, one CTA per SM; d_cycles[grid] */
+extern "C" int pdf_selftest_umma_rate(int N, int iters, int mode, int grid, unsigned long long* d_cycles, pdf_stream_t stream) {
+  using namespace pdf;
+  PDF_REQUIRE((N == 64 || N == 128 || N == 256) && iters > 0 && grid > 0 && d_cycles, "pdf_selftest_umma_rate: bad arguments");
+  const int smem = 3 * kABytes + N * 128 + 64 + 1024;
+  cudaStream_t s = as_stream(stream);
+  if (N == 64) {
+    PDF_CHECK_CUDA(cudaFuncSetAttribute(umma_rate_kernel<64>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
+    umma_rate_kernel<64><<<grid, 128, smem, s>>>(iters, mode, d_cycles);
+  } else if (N == 128) {
+    PDF_CHECK_CUDA(cudaFuncSetAttribute(umma_rate_kernel<128>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
+    umma_rate_kernel<128><<<grid, 128, smem, s>>>(iters, mode, d_cycles);
+  } else {
+    PDF_CHECK_CUDA(cudaFuncSetAttribute(umma_rate_kernel<256>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
+    umma_rate_kernel<256><<<grid, 128, smem, s>>>(iters, mode, d_cycles);
+  }
+  PDF_CHECK_LAUNCH();
   return PDF_OK;
 }

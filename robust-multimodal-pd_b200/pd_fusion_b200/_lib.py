@@ -105,6 +105,7 @@ PROTOTYPES = {
     "pdf_moe_sweep": (C.c_int, [C.POINTER(Moe), C.c_int, C.c_int, C.POINTER(_P), _P, _P, _P]),
     "pdf_selftest_umma": (C.c_int, [C.c_int, C.c_int, C.c_int, _P, _P, _P, _P]),
     "pdf_selftest_umma_shift": (C.c_int, [C.c_int, C.c_int, C.c_int, _P, _P, _P, _P]),
+    "pdf_selftest_umma_rate": (C.c_int, [C.c_int, C.c_int, C.c_int, C.c_int, _P, _P]),
     "pdf_debug_disable_halo": (C.c_int, [C.c_int]),
 }
 

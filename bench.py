@@ -242,7 +242,7 @@ def main():
         pipe.enc.forward(None)
 
     def pre_only():
-        pipe.pre.run(raw, net_input=pipe.enc.input.view(pipe.pre.net_input.shape))
+        pipe.pre.run(raw, net_input=pipe._net_input)
 
     for _ in range(2):
         enc_only(); pre_only()

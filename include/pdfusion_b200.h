@@ -63,6 +63,14 @@ typedef struct {
 /* output layouts of pdf_gather_resize_normalize */
 #define PDF_OUT_BF16_C1 0 /* [B, L, S, S]    bf16, one channel (requires channel-uniform mean/std) */
 #define PDF_OUT_F32_NHWC3 1 /* [B, L, S, S, 3] f32,  exact 3-channel input of the reference */
+#define PDF_OUT_BF16_C1_PAD 2 /* [B, L, rows, pitch] bf16, one channel, image origin at (PDF_STEM_PAD_LO, PDF_STEM_PAD_LO) of a
+                                 zero border (pdf_stem_padded_dims); the caller zeroes the buffer ONCE, the kernel only writes
+                                 the image (and zeros into border pixels that share an 8-byte group with it).  Input layout of
+                                 PDF_OP_STEM_FUSED. */
+#define PDF_STEM_PAD_LO 5
+
+/* pitch (elements per row, multiple of 8) and row count of the padded stem input of an S x S image */
+int pdf_stem_padded_dims(int S, int* pitch, int* rows);
 
 /* bytes of device workspace pdf_preproc_* needs for `batch` subjects (histograms, plane maxima,
  * per-subject select state, interpolation tables). */
@@ -107,7 +115,9 @@ int pdf_normalize_volume(int batch, size_t voxels, const float* d_zoomed, const 
 #define PDF_OP_MAXPOOL 1     /* 3x3 stride 2 pad 1 */
 #define PDF_OP_AVGPOOL 2     /* global average over H*W -> [N, C] f32 */
 #define PDF_OP_STEM_IM2COL 3 /* [N,H,W] bf16 one-channel image -> [N*Ho*Wo, kpad] bf16 patch matrix (7x7 s2 p3) */
-#define PDF_OP_STEM_FUSED 4  /* [N,H,W] bf16 image -> conv 7x7 s2 p3 (64 ch) + bias + ReLU + maxpool 3x3 s2 p1 -> [N,ho,wo,64] bf16, one kernel */
+#define PDF_OP_STEM_FUSED 4  /* zero-padded [N,rows,pitch] bf16 image (PDF_OUT_BF16_C1_PAD; h = w = S) -> conv 7x7 s2 p3 (64 ch) + bias
+                                + ReLU + maxpool 3x3 s2 p1 -> [N,ho,wo,64] bf16, one kernel.  d_weight: [128][128] bf16, row v*64+c,
+                                column t*8+s = w[c][t-4v][s] (BN folded, 3 input channels summed), zero elsewhere */
 
 #define PDF_PREC_F32 0  /* CUDA-core FFMA path, 1e-5 parity */
 #define PDF_PREC_BF16 1 /* tcgen05/TMEM path, bf16 operands, f32 accumulate */

@@ -421,7 +421,20 @@ int prepare_conv_tc(const pdf_op& op, TcConv* tc) {
 int prepare_stem_tc(const pdf_op& op, TcConv* tc) {
   if (int rc = load_driver_entry_points()) return rc;
   PDF_REQUIRE((reinterpret_cast<uintptr_t>(op.d_weight) & 15) == 0, "fused stem: weight pointer must be 16-byte aligned");
-  return encode_2d(&tc->tmap_b, op.d_weight, 64, 64, 64);
+  if (int rc = encode_2d(&tc->tmap_b, op.d_weight, 128, 128, 128)) return rc;   // [2 variants x 64 channels, K = 96 padded to 128]
+  // zero-padded one-channel images [n, rows, pitch]: box = one 39 x 40 patch, no swizzle (stem_tc.cu)
+  int pitch = 0, rows = 0;
+  if (int rc = pdf_stem_padded_dims(op.h, &pitch, &rows)) return rc;
+  PDF_REQUIRE((reinterpret_cast<uintptr_t>(op.d_in) & 15) == 0, "fused stem: input pointer must be 16-byte aligned");
+  const cuuint64_t dims[3] = {(cuuint64_t)pitch, (cuuint64_t)rows, (cuuint64_t)op.n};
+  const cuuint64_t strides[2] = {(cuuint64_t)pitch * 2, (cuuint64_t)pitch * rows * 2};
+  const cuuint32_t box[3] = {40, 39, 1};
+  const cuuint32_t estr[3] = {1, 1, 1};
+  CUresult r = g_encode_tiled(reinterpret_cast<CUtensorMap*>(&tc->tmap_a), CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 3, const_cast<void*>(op.d_in),
+                              dims, strides, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_NONE,
+                              CU_TENSOR_MAP_L2_PROMOTION_L2_128B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  PDF_REQUIRE(r == CUDA_SUCCESS, "cuTensorMapEncodeTiled(stem patch) failed (%d) n=%d rows=%d pitch=%d", (int)r, op.n, rows, pitch);
+  return PDF_OK;
 }
 
 template <int BLOCK_N, int STAGES, int MT>

@@ -27,8 +27,8 @@ struct TcConv {
 };
 
 int prepare_conv_tc(const pdf_op& op, TcConv* out);
-int prepare_stem_tc(const pdf_op& op, TcConv* out);   // encodes the [64 x 64] weight map into out->tmap_b
-int launch_stem_fused(const pdf_op& op, const TensorMapBlob& tmap_w, cudaStream_t s);
+int prepare_stem_tc(const pdf_op& op, TcConv* out);   // weight map -> out->tmap_b, padded-image patch map -> out->tmap_a
+int launch_stem_fused(const pdf_op& op, const TensorMapBlob& tmap_w, const TensorMapBlob& tmap_in, cudaStream_t s);
 int launch_conv_tc(const TcConv& tc, cudaStream_t s);
 bool halo_eligible(const pdf_op& op);
 int launch_conv3x3_halo(const TcConv& tc, cudaStream_t s);

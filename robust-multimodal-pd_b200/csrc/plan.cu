@@ -73,7 +73,7 @@ extern "C" int pdf_plan_run_range(const pdf_plan* plan, int first, int count, pd
       case PDF_OP_MAXPOOL: rc = launch_maxpool(op, s); break;
       case PDF_OP_AVGPOOL: rc = launch_avgpool(op, s); break;
       case PDF_OP_STEM_IM2COL: rc = launch_stem_im2col(op, s); break;
-      case PDF_OP_STEM_FUSED: rc = launch_stem_fused(op, plan->tc[i].tmap_b, s); break;
+      case PDF_OP_STEM_FUSED: rc = launch_stem_fused(op, plan->tc[i].tmap_b, plan->tc[i].tmap_a, s); break;
     }
     if (rc != PDF_OK) return rc;
   }

@@ -651,6 +651,7 @@ struct ResizeArgs {
   int axes[PDF_MAX_AXES];
   int counts[PDF_MAX_AXES];
   int lmax, S, cnt2;
+  int pitch, rows;  // PDF_OUT_BF16_C1_PAD geometry
   float mean[3], inv_std[3];
   float scale_sq;   // T/S when the slice is square (the usual cubic target), hoisted out of the kernel
 };
@@ -664,17 +665,20 @@ resize_kernel(const float* __restrict__ zoomed, const float* __restrict__ planes
               const int32_t* __restrict__ indices, const int32_t* __restrict__ nslices, void* __restrict__ out, ResizeArgs ra) {
   const int b = blockIdx.z, l = blockIdx.y;
   const int S = ra.S;
-  const int gpr = (S + 3) >> 2;                         // 4-pixel groups per output row
+  constexpr bool PAD = MODE == PDF_OUT_BF16_C1_PAD;
+  const int gpr = PAD ? (ra.pitch >> 2) : ((S + 3) >> 2);   // 4-pixel groups per output row
   const int g = blockIdx.x * blockDim.x + threadIdx.x;
   if (g >= gpr * S) return;
-  const int oy = g / gpr, ox0 = (g - oy * gpr) * 4;
-  const int npx = min(4, S - ox0);
+  const int oy = g / gpr;
+  const int ox0 = (g - oy * gpr) * 4 - (PAD ? PDF_STEM_PAD_LO : 0);   // first image column of the group (may be < 0 when padded)
+  const int npx = PAD ? 4 : min(4, S - ox0);
   // locate the axis group of slot l
   int a = 0, t = l, off2 = 0;
   while (a < ra.n_axes - 1 && t >= ra.counts[a]) { if (ra.axes[a] == 2) off2 += ra.counts[a]; t -= ra.counts[a]; ++a; }
   const int axis = ra.axes[a];
   const bool valid = t < nslices[(size_t)b * ra.n_axes + a];
-  const size_t opix = ((size_t)b * ra.lmax + l) * S * S + (size_t)oy * S + ox0;
+  const size_t opix = PAD ? (((size_t)b * ra.lmax + l) * ra.rows + oy + PDF_STEM_PAD_LO) * ra.pitch + (size_t)(ox0 + PDF_STEM_PAD_LO)
+                          : ((size_t)b * ra.lmax + l) * S * S + (size_t)oy * S + ox0;
   float r[4] = {0.f, 0.f, 0.f, 0.f};
   if (valid) {
     const int idx = indices[(size_t)b * ra.lmax + l];
@@ -698,7 +702,7 @@ resize_kernel(const float* __restrict__ zoomed, const float* __restrict__ planes
     const float* row1 = src + y1 * rs;
 #pragma unroll
     for (int j = 0; j < 4; ++j) {
-      const int ox = min(ox0 + j, S - 1);
+      const int ox = min(max(ox0 + j, 0), S - 1);
       const float fx = fmaxf(__fsub_rn(__fmul_rn(__fadd_rn((float)ox, 0.5f), sw), 0.5f), 0.0f);
       const int x0 = min((int)fx, W - 1), x1 = min(x0 + 1, W - 1);
       const float wx1 = __fsub_rn(fx, (float)x0), wx0 = __fsub_rn(1.0f, wx1);
@@ -709,11 +713,14 @@ resize_kernel(const float* __restrict__ zoomed, const float* __restrict__ planes
       r[j] = (__fadd_rn(__fmul_rn(wy0, top), __fmul_rn(wy1, bot)) - lo) * inv_den;
     }
   }
-  if (MODE == PDF_OUT_BF16_C1) {
+  if (MODE == PDF_OUT_BF16_C1 || PAD) {
     __nv_bfloat16* o = reinterpret_cast<__nv_bfloat16*>(out) + opix;
     __nv_bfloat16 h[4];
 #pragma unroll
-    for (int j = 0; j < 4; ++j) h[j] = __float2bfloat16(valid ? (r[j] - ra.mean[0]) * ra.inv_std[0] : 0.0f);
+    for (int j = 0; j < 4; ++j) {
+      const bool inb = !PAD || (ox0 + j >= 0 && ox0 + j < S);      // border pixels of a padded group stay exactly 0
+      h[j] = __float2bfloat16((valid && inb) ? (r[j] - ra.mean[0]) * ra.inv_std[0] : 0.0f);
+    }
     if (npx == 4 && ((reinterpret_cast<uintptr_t>(o) & 7) == 0)) {
       uint2 pk;
       pk.x = (uint32_t)__bfloat16_as_ushort(h[0]) | ((uint32_t)__bfloat16_as_ushort(h[1]) << 16);
@@ -849,8 +856,9 @@ extern "C" int pdf_gather_resize_normalize(const pdf_preproc_cfg* cfg, int batch
                                               void* d_out, int out_mode, pdf_stream_t stream) {
   if (int rc = validate(cfg, batch)) return rc;
   PDF_REQUIRE(d_zoomed && d_workspace && d_lohi && d_indices && d_nslices && d_out, "pdf_gather_resize_normalize: null device pointer");
-  PDF_REQUIRE(out_mode == PDF_OUT_BF16_C1 || out_mode == PDF_OUT_F32_NHWC3, "pdf_gather_resize_normalize: bad out_mode");
-  if (out_mode == PDF_OUT_BF16_C1) {
+  PDF_REQUIRE(out_mode == PDF_OUT_BF16_C1 || out_mode == PDF_OUT_F32_NHWC3 || out_mode == PDF_OUT_BF16_C1_PAD,
+              "pdf_gather_resize_normalize: bad out_mode");
+  if (out_mode != PDF_OUT_F32_NHWC3) {
     PDF_REQUIRE(cfg->mean[0] == cfg->mean[1] && cfg->mean[1] == cfg->mean[2] && cfg->std[0] == cfg->std[1] && cfg->std[1] == cfg->std[2],
                 "PDF_OUT_BF16_C1 needs channel-uniform mean/std");
   }
@@ -880,8 +888,15 @@ extern "C" int pdf_gather_resize_normalize(const pdf_preproc_cfg* cfg, int batch
     }
     off += cfg->counts[a];
   }
-  const dim3 grid(ceil_div((long long)ra.S * ((ra.S + 3) / 4), 256), ra.lmax, batch);
-  if (out_mode == PDF_OUT_BF16_C1)
+  ra.pitch = ra.rows = 0;
+  if (out_mode == PDF_OUT_BF16_C1_PAD) {
+    if (int rc = pdf_stem_padded_dims(ra.S, &ra.pitch, &ra.rows)) return rc;
+  }
+  const int groups = out_mode == PDF_OUT_BF16_C1_PAD ? ra.pitch / 4 : (ra.S + 3) / 4;
+  const dim3 grid(ceil_div((long long)ra.S * groups, 256), ra.lmax, batch);
+  if (out_mode == PDF_OUT_BF16_C1_PAD)
+    resize_kernel<PDF_OUT_BF16_C1_PAD><<<grid, 256, 0, s>>>(d_zoomed, w.planes, d_lohi, d_indices, d_nslices, d_out, ra);
+  else if (out_mode == PDF_OUT_BF16_C1)
     resize_kernel<PDF_OUT_BF16_C1><<<grid, 256, 0, s>>>(d_zoomed, w.planes, d_lohi, d_indices, d_nslices, d_out, ra);
   else
     resize_kernel<PDF_OUT_F32_NHWC3><<<grid, 256, 0, s>>>(d_zoomed, w.planes, d_lohi, d_indices, d_nslices, d_out, ra);

@@ -1,200 +1,287 @@
 // K2 stem, fused: 7x7 stride-2 pad-3 convolution (one folded input channel) + bias + ReLU + 3x3 stride-2 pad-1
-// max-pool in ONE kernel.  Per CTA: a 7x7 tile of pooled pixels <- 15x15 conv pixels <- 35x35 input patch.
+// max-pool in ONE persistent, warp-specialised kernel.
 //
-//   1. input patch (bf16, zero padded) -> shared memory
-//   2. the 225 x 64 im2col matrix (K = r*8+s: 49 taps + 15 zero columns) is BUILT in shared memory in the K-major
-//      SWIZZLE_128B layout the tensor core reads (never touches HBM); weights [64 x 64] likewise
-//   3. 2 x 4 tcgen05.mma (M=128, N=64, K=16) -> two f32 accumulators in TMEM
-//   4. epilogue: tcgen05.ld -> +bias, ReLU -> bf16 conv tile in shared memory (overlays the A matrix)
-//   5. 3x3/2 max over the conv tile -> [n, P, P, 64] bf16 NHWC
+// The GEMM is TRANSPOSED so that the max-pool needs no shared-memory round trip:
 //
-// HBM traffic per image: S*S*2 bytes in (+halo re-reads from L2), P*P*64*2 bytes out -- the unfused sequence
-// (stem_im2col_kernel -> conv_tc_kernel -> maxpool_kernel) moves ~6.8 MB per 224x224 image instead of 0.5 MB.
+//   D[lane = (variant v, channel c), column = site n]  =  Wa[128 x 96]  *  B[192 x 96]^T       (tcgen05, f32 in TMEM)
+//
+//   * a tile is 8 x 7 pooled pixels  <-  17 x 15 conv pixels  <-  a 39 x 35 input patch;
+//   * site n = ((i*3+u)*16 + cx), i = 0..3, u = 0..2, cx = 0..14: its B row holds the 11 patch rows (8 pixels each:
+//     K = t*8 + s, t = 0..10, s = 0..7) that cover conv row 4i+u (variant 0, filter rows at t = 0..6) AND conv row
+//     4i+u+2 (variant 1, the same filter shifted down by 4 patch rows, t = 4..10) of conv column cx;
+//   * lane v*64+c therefore owns, as TMEM COLUMNS, every conv pixel of channel c that the pooled rows 2i+v need:
+//     the 3x3/2 max-pool, bias, ReLU and the bf16 conversion are plain register arithmetic on tcgen05.ld results,
+//     and all 128 lanes do useful work.
+//
+//   warps 0..3   epilogue: tcgen05.ld -> vertical/horizontal max -> +bias, ReLU -> bf16 NHWC store
+//   warp  4      TMA load of the weights, tcgen05.mma issue (6 x M128 N192 K16 per tile), TMEM alloc
+//   warps 5..12  build the B matrix (im2col) in shared memory, 128B-swizzled K-major, from the patch; double buffered
+//                against the MMAs; two TMEM accumulators overlap epilogue and MMA
+//   warp  13     TMA producer: the 39 x 40 input patch of tile t+4 lands in a 4-stage ring while tile t is built
+//
+// The input image is read from a zero-PADDED buffer (origin at row/column 5, see pdf_stem_padded_dims): the patch
+// origin is then (4*pp0, 4*pq0) >= 0 and every 8-pixel chunk of the staged patch is a 4-byte aligned shared-memory read.
+// HBM traffic per image: the padded bf16 image in, P*P*64 bf16 out.
 // Replaces conv1/bn1/relu/maxpool of torchvision's ResNet (`model(batch)`, data/openneuro_features.py:260).
 #include "tc_common.cuh"
 #include "ops.cuh"
 
 namespace pdf {
 
-constexpr int kTP = 7;             // pooled tile side
-constexpr int kCT = 2 * kTP + 1;   // conv tile side (15)
-constexpr int kIT = 2 * kCT + 5;   // input patch side (35)
-constexpr int kITP = kIT + 1;      // padded row pitch
-constexpr int kConvPix = kCT * kCT;  // 225 valid rows of the 256-row A matrix
+constexpr int kPR = 8, kPQ = 7;                  // pooled tile: rows x columns
+constexpr int kPatchRows = 4 * kPR + 7;          // 39
+constexpr int kConvCols = 2 * kPQ + 1;           // 15
+constexpr int kSites = 12 * 16;                  // 192 B rows
+constexpr int kStemBBlock = kSites * 128;        // one 64-wide K block of B
+constexpr int kStemBStage = 2 * kStemBBlock;
+constexpr int kStemABlock = 128 * 128;
+constexpr int kStemABytes = 2 * kStemABlock;
+constexpr int kStemWarps = 14;
+constexpr int kStemBuilders = 8 * 32;
+constexpr int kPatchCols = 40;                   // 35 needed (+4 when the box start is rounded down to 16 bytes); 80-byte rows
+constexpr int kPatchStages = 4;
+constexpr int kPatchStage = (kPatchRows * kPatchCols * 2 + 127) / 128 * 128;
+constexpr int kStemSmem = kStemABytes + 2 * kStemBStage + kPatchStages * kPatchStage + 256 + 1024;
 
 struct StemParams {
-  const __nv_bfloat16* in;    // [n, S, S]
-  const __nv_bfloat16* w;     // [64, 64]  (cout, r*8+s; s = 7 and r = 7 columns are zero)
+  const __nv_bfloat16* in;    // padded [n, rows, pitch]
   const float* bias;          // [64]
   __nv_bfloat16* out;         // [n, P, P, 64]
-  int S, H1, P, tiles;
+  int pitch, rows, H1, P, tiles_x, tiles_per_image, total_tiles;
 };
 
-__global__ void __launch_bounds__(256)
-stem_fused_kernel(const __grid_constant__ CUtensorMap tmap_w, const StemParams p) {
-  // [ A: 256 rows x 128 B | W: 64 rows x 128 B | input patch | barrier, tmem slot ]
+__device__ __forceinline__ void tmem_ld16_nowait(uint32_t taddr, uint32_t (&v)[16]) {
+  asm volatile(
+      "tcgen05.ld.sync.aligned.32x32b.x16.b32 {%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15}, [%16];"
+      : "=r"(v[0]), "=r"(v[1]), "=r"(v[2]), "=r"(v[3]), "=r"(v[4]), "=r"(v[5]), "=r"(v[6]), "=r"(v[7]), "=r"(v[8]), "=r"(v[9]),
+        "=r"(v[10]), "=r"(v[11]), "=r"(v[12]), "=r"(v[13]), "=r"(v[14]), "=r"(v[15])
+      : "r"(taddr));
+}
+__device__ __forceinline__ void tmem_wait_ld() { asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory"); }
+__device__ __forceinline__ void mbar_arrive_cta(uint32_t bar) {
+  asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(bar) : "memory");
+}
+
+__global__ void __launch_bounds__(kStemWarps * 32, 1)
+stem_fused_kernel(const __grid_constant__ CUtensorMap tmap_w, const __grid_constant__ CUtensorMap tmap_in, const StemParams p) {
   extern __shared__ uint8_t smem_raw[];
   const uint32_t raw_addr = smem_u32(smem_raw);
   const uint32_t base = (raw_addr + 1023u) & ~1023u;
   uint8_t* smem = smem_raw + (base - raw_addr);
-  uint8_t* sA = smem;
-  __nv_bfloat16* sIn = reinterpret_cast<__nv_bfloat16*>(smem + 256 * 128 + 64 * 128);
-  const uint32_t bar = base + 256 * 128 + 64 * 128 + ((kIT * kITP * 2 + 15) & ~15);
-  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(smem + (bar - base) + 32);
+  const uint32_t sA = base, sB = base + kStemABytes;
+  const uint32_t sP = sB + 2 * kStemBStage;
+  const uint32_t bar0 = sP + kPatchStages * kPatchStage;
+  const uint32_t bar_w = bar0, bar_bfull = bar0 + 8, bar_bempty = bar0 + 24, bar_accfull = bar0 + 40, bar_accempty = bar0 + 56;
+  const uint32_t bar_pfull = bar0 + 72, bar_pempty = bar_pfull + 8 * kPatchStages;
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(smem + (bar0 - base) + 72 + 16 * kPatchStages);
 
-  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
-  const int n = blockIdx.y;
-  const int ty = blockIdx.x / p.tiles, tx = blockIdx.x - ty * p.tiles;
-  const int tp0 = ty * kTP, tq0 = tx * kTP;          // pooled-tile origin
-  const int cy0 = 2 * tp0 - 1, cx0 = 2 * tq0 - 1;    // conv-tile origin (may be -1)
-  const int iy0 = 2 * cy0 - 3, ix0 = 2 * cx0 - 3;    // input-patch origin
+  const int tid = threadIdx.x, lane = tid & 31;
+  const int warp = __shfl_sync(0xffffffffu, tid >> 5, 0);
 
-  const uint32_t bar_w = bar + 16;
-  if (warp == 0 && elect_one()) {
-    mbar_init(bar, 1);
-    mbar_init(bar_w, 1);
-    fence_barrier_init();
-    // weights [64 x 64] bf16 -> 128B-swizzled K-major rows, written by the TMA unit (one instruction per CTA)
-    mbar_expect_tx(bar_w, 64 * 128);
-    tma_load_2d(base + 256 * 128, &tmap_w, bar_w, 0, 0);
-  }
-  if (warp == 1) tmem_alloc(smem_u32(tmem_slot), 128);
-
-  // 1. input patch.  Patch column 0 is global x = ix0 (odd), so columns 1.. pair up into 4-byte aligned global words:
-  //    one 2-byte load for column 0 and 17 word loads per row instead of 35 scalar loads.
-  const __nv_bfloat16* img = p.in + (size_t)n * p.S * p.S;
-  const unsigned short* img16 = reinterpret_cast<const unsigned short*>(img);
-  unsigned short* sIn16 = reinterpret_cast<unsigned short*>(sIn);
-  const bool even = (p.S & 1) == 0;
-  for (int i = tid; i < kIT * 18; i += 256) {
-    const int y = i / 18, k = i - y * 18;
-    const int gy = iy0 + y;
-    const bool rowin = gy >= 0 && gy < p.S;
-    if (k == 0) {
-      sIn16[y * kITP] = (rowin && ix0 >= 0 && ix0 < p.S) ? img16[(size_t)gy * p.S + ix0] : (unsigned short)0;
-    } else {
-      const int x = 2 * k - 1, gx = ix0 + x;              // gx is even
-      unsigned short lo16 = 0, hi16 = 0;
-      if (rowin) {
-        if (even && gx >= 0 && gx + 1 < p.S) {
-          const uint32_t w = *reinterpret_cast<const uint32_t*>(img16 + (size_t)gy * p.S + gx);
-          lo16 = (unsigned short)(w & 0xffffu);
-          hi16 = (unsigned short)(w >> 16);
-        } else {
-          if (gx >= 0 && gx < p.S) lo16 = img16[(size_t)gy * p.S + gx];
-          if (gx + 1 >= 0 && gx + 1 < p.S) hi16 = img16[(size_t)gy * p.S + gx + 1];
-        }
+  if (warp == 4) {
+    if (elect_one()) {
+      prefetch_tmap(&tmap_w);
+      mbar_init(bar_w, 1);
+      for (int s = 0; s < 2; ++s) {
+        mbar_init(bar_bfull + 8 * s, 8);       // one arrive per builder warp
+        mbar_init(bar_bempty + 8 * s, 1);      // tcgen05.commit
+        mbar_init(bar_accfull + 8 * s, 1);     // tcgen05.commit
+        mbar_init(bar_accempty + 8 * s, 4);    // one arrive per epilogue warp
       }
-      sIn16[y * kITP + x] = lo16;
-      if (x + 1 < kIT) sIn16[y * kITP + x + 1] = hi16;
+      for (int s = 0; s < kPatchStages; ++s) { mbar_init(bar_pfull + 8 * s, 1); mbar_init(bar_pempty + 8 * s, 8); }
+      fence_barrier_init();
+      mbar_expect_tx(bar_w, kStemABytes);
+      tma_load_2d(sA, &tmap_w, bar_w, 0, 0);
+      tma_load_2d(sA + kStemABlock, &tmap_w, bar_w, 64, 0);
     }
+    __syncwarp();
+    tmem_alloc(smem_u32(tmem_slot), 512);
   }
-  __syncthreads();
-  // 2b. im2col rows.  K index = r*8 + s (s = 7 is a zero column, r = 7 a zero chunk): chunk c of row m is the 7 taps of
-  //     filter row c, i.e. 8 consecutive bf16 of the patch starting at an even column -> four aligned 32-bit loads.
-  {
-    const int c = tid & 7;                      // chunk (= filter row) is fixed per thread; rows advance by 32 per step
-    int m = tid >> 3;
-    int cy = m / kCT, cx = m - cy * kCT;
-    const uint32_t cmask = (c < 7) ? 0xffffffffu : 0u;
-#pragma unroll
-    for (int it = 0; it < 8; ++it) {
-      uint4 v = make_uint4(0u, 0u, 0u, 0u);
-      if (m < kConvPix) {
-        const uint32_t* src = reinterpret_cast<const uint32_t*>(sIn + (2 * cy + (c < 7 ? c : 0)) * kITP + 2 * cx);
-        v = make_uint4(src[0] & cmask, src[1] & cmask, src[2] & cmask, src[3] & 0x0000ffffu & cmask);
-      }
-      *reinterpret_cast<uint4*>(sA + m * 128 + ((c ^ (m & 7)) << 4)) = v;
-      m += 32; cy += 2; cx += 2;
-      if (cx >= kCT) { cx -= kCT; ++cy; }
-    }
-  }
-  fence_proxy_async();          // generic-proxy smem writes -> visible to the tensor core (async proxy)
+  // B rows of the unused column slot (cx = 15) and the K padding (t = 11) are never written by the builders: they only
+  // have to be finite, so both stages are zeroed once
+  for (int i = tid; i < 2 * kStemBStage / 16; i += kStemWarps * 32)
+    reinterpret_cast<uint4*>(smem + kStemABytes)[i] = make_uint4(0u, 0u, 0u, 0u);
+  fence_proxy_async();
   tc_fence_before();
   __syncthreads();
   tc_fence_after();
   const uint32_t tmem_base = *tmem_slot;
 
-  // 3. MMAs
-  if (warp == 0 && elect_one()) {
-    constexpr uint32_t idesc = make_idesc(64);
-    const uint32_t a0 = base, w0 = base + 256 * 128;
-    mbar_wait(bar_w, 0);
-    tc_fence_after();
+  if (warp < 4) {
+    // ------------------------------------------------------------------------------------------ epilogue
+    const int v = warp >> 1, c = (warp & 1) * 32 + lane;
+    const float bias_c = __ldg(p.bias + c);
+    const uint32_t tlane = tmem_base + ((uint32_t)(warp * 32) << 16);
+    int it = 0;
+    for (int tile = blockIdx.x; tile < p.total_tiles; tile += gridDim.x, ++it) {
+      const int stage = it & 1;
+      const uint32_t phase = (uint32_t)(it >> 1) & 1u;
+      const int n = tile / p.tiles_per_image, rem = tile - n * p.tiles_per_image;
+      const int ty = rem / p.tiles_x, tx = rem - ty * p.tiles_x;
+      const int pp0 = ty * kPR, pq0 = tx * kPQ;
+      const int cy0 = 2 * pp0 - 1, cx0 = 2 * pq0 - 1;
+      const bool col_edge = cx0 < 0 || cx0 + kConvCols > p.H1;
+      const size_t orow_stride = (size_t)p.P * 64;
+      __nv_bfloat16* otile = p.out + (((size_t)n * p.P + pp0 + v) * p.P + pq0) * 64 + c;
+      mbar_wait(bar_accfull + 8 * stage, phase);
+      tc_fence_after();
 #pragma unroll
-    for (int mt = 0; mt < 2; ++mt)
-#pragma unroll
-      for (int k = 0; k < 4; ++k)
-        umma_f16(tmem_base + mt * 64, make_smem_desc(a0 + mt * kABytes + k * 32), make_smem_desc(w0 + k * 32), idesc, k != 0 ? 1u : 0u);
-    umma_commit(bar);
-  }
-  mbar_wait(bar, 0);
-  tc_fence_after();
-
-  // 4. epilogue: conv tile (bias, ReLU, bf16) -> shared memory over the A matrix; out-of-image conv pixels -> 0
-  {
-    const int quad = warp & 3, mt = warp >> 2;
-    const int m = mt * 128 + quad * 32 + lane;
-    const int cy = m / kCT, cx = m - cy * kCT;
-    const int gy = cy0 + cy, gx = cx0 + cx;
-    const bool inside = m < kConvPix && gy >= 0 && gy < p.H1 && gx >= 0 && gx < p.H1;
-#pragma unroll
-    for (int c0 = 0; c0 < 64; c0 += 32) {
-      uint32_t v[32];
-      tmem_ld32(tmem_base + ((uint32_t)(quad * 32) << 16) + (uint32_t)(mt * 64 + c0), v);
-      if (m < kConvPix) {
-        const uint32_t keep = inside ? 0xffffffffu : 0u;       // out-of-image conv pixels must not win the max-pool
-#pragma unroll
-        for (int i = 0; i < 4; ++i) {
-          const float4 b0 = __ldg(reinterpret_cast<const float4*>(p.bias + c0 + i * 8));
-          const float4 b1 = __ldg(reinterpret_cast<const float4*>(p.bias + c0 + i * 8 + 4));
-          uint4 o;
-          __nv_bfloat162* h = reinterpret_cast<__nv_bfloat162*>(&o);
-          h[0] = __floats2bfloat162_rn(fmaxf(__uint_as_float(v[i * 8 + 0]) + b0.x, 0.f), fmaxf(__uint_as_float(v[i * 8 + 1]) + b0.y, 0.f));
-          h[1] = __floats2bfloat162_rn(fmaxf(__uint_as_float(v[i * 8 + 2]) + b0.z, 0.f), fmaxf(__uint_as_float(v[i * 8 + 3]) + b0.w, 0.f));
-          h[2] = __floats2bfloat162_rn(fmaxf(__uint_as_float(v[i * 8 + 4]) + b1.x, 0.f), fmaxf(__uint_as_float(v[i * 8 + 5]) + b1.y, 0.f));
-          h[3] = __floats2bfloat162_rn(fmaxf(__uint_as_float(v[i * 8 + 6]) + b1.z, 0.f), fmaxf(__uint_as_float(v[i * 8 + 7]) + b1.w, 0.f));
-          o.x &= keep; o.y &= keep; o.z &= keep; o.w &= keep;
-          const int chunk = (c0 >> 3) + i;
-          *reinterpret_cast<uint4*>(sA + m * 128 + ((chunk ^ (m & 7)) << 4)) = o;
+      for (int i = 0; i < 4; ++i) {
+        uint32_t r0[16], r1[16], r2[16];
+        const uint32_t col = (uint32_t)(stage * 256 + i * 48);
+        tmem_ld16_nowait(tlane + col, r0);
+        tmem_ld16_nowait(tlane + col + 16, r1);
+        tmem_ld16_nowait(tlane + col + 32, r2);
+        tmem_wait_ld();
+        if (i == 3) {                                  // accumulator fully read: hand it back to the MMA warp
+          tc_fence_before();
+          __syncwarp();
+          if (lane == 0) mbar_arrive_cta(bar_accempty + 8 * stage);
         }
+        const int pr = pp0 + 2 * i + v;
+        if (pr >= p.P) continue;
+        const int cy = cy0 + 4 * i + 2 * v;            // conv rows cy, cy+1, cy+2; the middle one (2*pr) is always valid
+        const bool top = cy >= 0, bot = cy + 2 < p.H1;
+        float m[16];
+#pragma unroll
+        for (int k = 0; k < kConvCols; ++k) {
+          float x = __uint_as_float(r1[k]);
+          if (top) x = fmaxf(x, __uint_as_float(r0[k]));
+          if (bot) x = fmaxf(x, __uint_as_float(r2[k]));
+          m[k] = x;
+        }
+        if (col_edge) {
+#pragma unroll
+          for (int k = 0; k < kConvCols; ++k)
+            if (cx0 + k < 0 || cx0 + k >= p.H1) m[k] = -INFINITY;
+        }
+        __nv_bfloat16* orow = otile + (size_t)(2 * i) * orow_stride;
+#pragma unroll
+        for (int j = 0; j < kPQ; ++j) {
+          const float h = fmaxf(fmaxf(m[2 * j], m[2 * j + 1]), m[2 * j + 2]);
+          if (pq0 + j < p.P) orow[j * 64] = __float2bfloat16(fmaxf(h + bias_c, 0.f));
+        }
+      }
+    }
+  } else if (warp == 4) {
+    // ------------------------------------------------------------------------------------------ MMA issue
+    if (elect_one()) {
+      constexpr uint32_t idesc = make_idesc(kSites);
+      const uint32_t a_lo = smem_desc_lo(sA);
+      mbar_wait(bar_w, 0);
+      int it = 0;
+      for (int tile = blockIdx.x; tile < p.total_tiles; tile += gridDim.x, ++it) {
+        const int stage = it & 1;
+        const uint32_t phase = (uint32_t)(it >> 1) & 1u;
+        mbar_wait(bar_accempty + 8 * stage, phase ^ 1u);
+        mbar_wait(bar_bfull + 8 * stage, phase);
+        tc_fence_after();
+        const uint32_t b_lo = smem_desc_lo(sB + stage * kStemBStage);
+        const uint32_t d = tmem_base + (uint32_t)(stage * 256);
+#pragma unroll
+        for (int ks = 0; ks < 6; ++ks)
+          umma_f16_lo(d, a_lo + (uint32_t)((ks >> 2) * (kStemABlock / 16) + (ks & 3) * 2),
+                      b_lo + (uint32_t)((ks >> 2) * (kStemBBlock / 16) + (ks & 3) * 2), idesc, ks != 0 ? 1u : 0u);
+        umma_commit(bar_bempty + 8 * stage);
+        umma_commit(bar_accfull + 8 * stage);
+      }
+    }
+  } else if (warp < 13) {
+    // ------------------------------------------------------------------------------------------ B builders
+    // The (patch row, conv column) chunks a thread copies, and the B rows each one lands in, are the same for every tile:
+    // the offsets are computed once and live in registers.
+    const int bt = tid - 5 * 32;
+    int ld_off[3];
+    uint32_t st_off[3][6];
+#pragma unroll
+    for (int k = 0; k < 3; ++k) {
+      const int idx = bt + k * kStemBuilders;
+      const bool have = idx < kPatchRows * kConvCols;
+      const int y = idx / kConvCols, cx = idx - y * kConvCols;
+      ld_off[k] = have ? y * (kPatchCols * 2) + cx * 4 : -1;
+      const int q0 = y >> 1, tpar = y & 1;
+#pragma unroll
+      for (int j = 0; j < 6; ++j) {
+        const int q = q0 - j, t = tpar + 2 * j;      // conv row q (sites exist for q % 4 != 3) sees patch row y as its t-th row
+        const bool ok = have && q >= 0 && q <= 14 && (q & 3) != 3 && t <= 10;
+        const int site = ((q >> 2) * 3 + (q & 3)) * 16 + cx;
+        st_off[k][j] = ok ? (uint32_t)((t >> 3) * kStemBBlock + site * 128 + (((t & 7) ^ (cx & 7)) << 4)) : 0xffffffffu;
+      }
+    }
+    int it = 0;
+    for (int tile = blockIdx.x; tile < p.total_tiles; tile += gridDim.x, ++it) {
+      const int stage = it & 1, ps = it % kPatchStages;
+      const uint32_t phase = (uint32_t)(it >> 1) & 1u, pphase = (uint32_t)(it / kPatchStages) & 1u;
+      const int tx = (tile % p.tiles_per_image) % p.tiles_x;
+      const uint32_t pbase = sP + (uint32_t)ps * kPatchStage + (uint32_t)(((4 * tx * kPQ) & 7) * 2);   // see the TMA producer
+      const uint32_t bbase = sB + (uint32_t)stage * kStemBStage;
+      mbar_wait(bar_pfull + 8 * ps, pphase);
+      mbar_wait(bar_bempty + 8 * stage, phase ^ 1u);
+#pragma unroll
+      for (int k = 0; k < 3; ++k) {
+        if (ld_off[k] >= 0) {
+          const uint32_t a = pbase + (uint32_t)ld_off[k];
+          uint32_t v0, v1, v2, v3;
+          asm volatile("ld.shared.b32 %0, [%1];" : "=r"(v0) : "r"(a));
+          asm volatile("ld.shared.b32 %0, [%1+4];" : "=r"(v1) : "r"(a));
+          asm volatile("ld.shared.b32 %0, [%1+8];" : "=r"(v2) : "r"(a));
+          asm volatile("ld.shared.b32 %0, [%1+12];" : "=r"(v3) : "r"(a));
+#pragma unroll
+          for (int j = 0; j < 6; ++j)
+            if (st_off[k][j] != 0xffffffffu)
+              asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(bbase + st_off[k][j]), "r"(v0), "r"(v1), "r"(v2), "r"(v3) : "memory");
+        }
+      }
+      fence_proxy_async();          // generic-proxy smem writes -> visible to the tensor core (async proxy)
+      __syncwarp();
+      if (lane == 0) {
+        mbar_arrive_cta(bar_bfull + 8 * stage);
+        mbar_arrive_cta(bar_pempty + 8 * ps);
+      }
+    }
+  } else {
+    // ------------------------------------------------------------------------------------------ patch TMA producer
+    if (elect_one()) {
+      prefetch_tmap(&tmap_in);
+      int it = 0;
+      for (int tile = blockIdx.x; tile < p.total_tiles; tile += gridDim.x, ++it) {
+        const int ps = it % kPatchStages;
+        const uint32_t pphase = (uint32_t)(it / kPatchStages) & 1u;
+        const int n = tile / p.tiles_per_image, rem = tile - n * p.tiles_per_image;
+        const int ty = rem / p.tiles_x, tx = rem - ty * p.tiles_x;
+        mbar_wait(bar_pempty + 8 * ps, pphase ^ 1u);
+        mbar_expect_tx(bar_pfull + 8 * ps, kPatchRows * kPatchCols * 2);
+        // padded coordinates of the patch origin: image row 4*pp0-5 -> padded row 4*pp0, likewise for columns.  A TMA box must
+        // start on a 16-byte boundary of the innermost dimension (profiles/r01_tma_probe.txt): the column is rounded down to
+        // a multiple of 8 pixels and the builders skip the 0 or 4 extra pixels
+        asm volatile("cp.async.bulk.tensor.3d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, %5}], [%2];"
+                     ::"r"(sP + (uint32_t)ps * kPatchStage), "l"(reinterpret_cast<uint64_t>(&tmap_in)), "r"(bar_pfull + 8 * ps),
+                       "r"((4 * tx * kPQ) & ~7), "r"(4 * ty * kPR), "r"(n) : "memory");
       }
     }
   }
   tc_fence_before();
   __syncthreads();
-  if (warp == 1) tmem_dealloc(tmem_base, 128);
-
-  // 5. 3x3 stride-2 max-pool over the conv tile (values are >= 0 after ReLU, so padding/out-of-image = 0 is neutral)
-  for (int i = tid; i < kTP * kTP * 8; i += 256) {
-    const int c = i & 7, px = i >> 3;
-    const int pp = px / kTP, pq = px - pp * kTP;
-    const int gp = tp0 + pp, gq = tq0 + pq;
-    if (gp >= p.P || gq >= p.P) continue;
-    __nv_bfloat162 mx[4];
-#pragma unroll
-    for (int j = 0; j < 4; ++j) mx[j] = __floats2bfloat162_rn(0.f, 0.f);
-#pragma unroll
-    for (int dy = 0; dy < 3; ++dy)
-#pragma unroll
-      for (int dx = 0; dx < 3; ++dx) {
-        const int m = (2 * pp + dy) * kCT + 2 * pq + dx;
-        const uint4 v = *reinterpret_cast<const uint4*>(sA + m * 128 + ((c ^ (m & 7)) << 4));
-        const __nv_bfloat162* h = reinterpret_cast<const __nv_bfloat162*>(&v);
-#pragma unroll
-        for (int j = 0; j < 4; ++j) mx[j] = __hmax2(mx[j], h[j]);
-      }
-    uint4 o;
-    __nv_bfloat162* ho = reinterpret_cast<__nv_bfloat162*>(&o);
-#pragma unroll
-    for (int j = 0; j < 4; ++j) ho[j] = mx[j];
-    *reinterpret_cast<uint4*>(p.out + (((size_t)n * p.P + gp) * p.P + gq) * 64 + c * 8) = o;
-  }
+  if (warp == 4) tmem_dealloc(tmem_base, 512);
 }
 
-constexpr int kStemSmem = 256 * 128 + 64 * 128 + ((kIT * kITP * 2 + 15) & ~15) + 48 + 1024;
+}  // namespace pdf
 
-int launch_stem_fused(const pdf_op& op, const TensorMapBlob& tmap_w, cudaStream_t s) {
+/* geometry of the zero-padded one-channel stem input for an S x S image (include/pdfusion_b200.h) */
+extern "C" int pdf_stem_padded_dims(int S, int* pitch, int* rows) {
+  using namespace pdf;
+  PDF_REQUIRE(S >= 8 && pitch && rows, "pdf_stem_padded_dims: bad arguments");
+  const int H1 = (S + 6 - 7) / 2 + 1, P = (H1 + 2 - 3) / 2 + 1;
+  const int pq0max = kPQ * (ceil_div(P, kPQ) - 1), pp0max = kPR * (ceil_div(P, kPR) - 1);
+  const int cols = max(S + PDF_STEM_PAD_LO, 4 * pq0max + 2 * (kConvCols - 1) + 8);
+  *pitch = (cols + 7) / 8 * 8;
+  *rows = max(S + PDF_STEM_PAD_LO, 4 * pp0max + kPatchRows);
+  return PDF_OK;
+}
+
+namespace pdf {
+
+int launch_stem_fused(const pdf_op& op, const TensorMapBlob& tmap_w, const TensorMapBlob& tmap_in, cudaStream_t s) {
   static bool configured = false;
   if (!configured) {
     PDF_CHECK_CUDA(cudaFuncSetAttribute(stem_fused_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kStemSmem));
@@ -202,15 +289,17 @@ int launch_stem_fused(const pdf_op& op, const TensorMapBlob& tmap_w, cudaStream_
   }
   StemParams p;
   p.in = reinterpret_cast<const __nv_bfloat16*>(op.d_in);
-  p.w = reinterpret_cast<const __nv_bfloat16*>(op.d_weight);
   p.bias = op.d_bias;
   p.out = reinterpret_cast<__nv_bfloat16*>(op.d_out);
-  p.S = op.h;
+  if (int rc = pdf_stem_padded_dims(op.h, &p.pitch, &p.rows)) return rc;
   p.H1 = (op.h + 6 - 7) / 2 + 1;
   p.P = op.ho;
-  p.tiles = ceil_div(p.P, kTP);
-  dim3 grid(p.tiles * p.tiles, op.n);
-  stem_fused_kernel<<<grid, 256, kStemSmem, s>>>(*reinterpret_cast<const CUtensorMap*>(&tmap_w), p);
+  p.tiles_x = ceil_div(p.P, kPQ);
+  p.tiles_per_image = p.tiles_x * ceil_div(p.P, kPR);
+  p.total_tiles = p.tiles_per_image * op.n;
+  const int grid = max(1, min(p.total_tiles, num_sms()));
+  stem_fused_kernel<<<grid, kStemWarps * 32, kStemSmem, s>>>(*reinterpret_cast<const CUtensorMap*>(&tmap_w),
+                                                             *reinterpret_cast<const CUtensorMap*>(&tmap_in), p);
   PDF_CHECK_LAUNCH();
   return PDF_OK;
 }

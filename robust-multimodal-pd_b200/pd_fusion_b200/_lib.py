@@ -18,6 +18,8 @@ PDF_MAX_MODS = 8
 
 OUT_BF16_C1 = 0
 OUT_F32_NHWC3 = 1
+OUT_BF16_C1_PAD = 2
+STEM_PAD_LO = 5
 
 OP_CONV, OP_MAXPOOL, OP_AVGPOOL, OP_STEM_IM2COL, OP_STEM_FUSED = 0, 1, 2, 3, 4
 PREC_F32, PREC_BF16 = 0, 1
@@ -92,6 +94,7 @@ PROTOTYPES = {
     "pdf_gather_resize_normalize": (C.c_int, [C.POINTER(PreprocCfg), C.c_int, _P, _P, _P, _P, _P, _P, C.c_int, _P]),
     "pdf_preprocess": (C.c_int, [C.POINTER(PreprocCfg), C.c_int, _P, _P, _P, _P, _P, _P, _P, C.c_int, _P]),
     "pdf_normalize_volume": (C.c_int, [C.c_int, C.c_size_t, _P, _P, _P, _P]),
+    "pdf_stem_padded_dims": (C.c_int, [C.c_int, C.POINTER(C.c_int), C.POINTER(C.c_int)]),
     "pdf_plan_create": (C.c_int, [C.POINTER(_P), C.POINTER(Op), C.c_int]),
     "pdf_plan_run": (C.c_int, [_P, _P]),
     "pdf_plan_run_range": (C.c_int, [_P, C.c_int, C.c_int, _P]),
@@ -145,6 +148,13 @@ def require_cuda():
 
     if not torch.cuda.is_available():
         raise PdfusionError("pd_fusion_b200 needs a CUDA device (sm_100a); there is no CPU fallback.")
+
+
+def stem_padded_dims(S: int):
+    """(pitch, rows) of the zero-padded one-channel stem input of an S x S image (image origin at STEM_PAD_LO)."""
+    pitch, rows = C.c_int(), C.c_int()
+    check(load().pdf_stem_padded_dims(int(S), C.byref(pitch), C.byref(rows)), "pdf_stem_padded_dims")
+    return pitch.value, rows.value
 
 
 def ptr(t) -> int:

@@ -163,7 +163,7 @@ def flops_per_image(arch: str, input_size: int = 224, folded_stem: bool = False)
     return total
 
 
-def lower_resnet(arch: str, n: int, S: int, bf16: bool, fused_stem: bool, chunks: List[int]):
+def lower_resnet(arch: str, n: int, S: int, bf16: bool, fused_stem: bool, chunks: List[int], in_bytes: int | None = None):
     """The network as a flat, ordered list of ops over symbolic buffers.
 
     Returns (ops, extents, final_hw): ops = [(name, fields, refs, weight_name)], where refs maps the pointer fields
@@ -179,7 +179,8 @@ def lower_resnet(arch: str, n: int, S: int, bf16: bool, fused_stem: bool, chunks
     exp = 1 if kind == "basic" else 4
     h1 = (S + 6 - 7) // 2 + 1
     h2 = (h1 + 2 - 3) // 2 + 1
-    in_bytes = S * S * 2 if bf16 else S * S * 3 * 4
+    if in_bytes is None:                      # bytes of one input image (the fused stem reads a zero-padded image)
+        in_bytes = S * S * 2 if bf16 else S * S * 3 * 4
     # stage geometry: spatial size and channels of each stage's OUTPUT (stage 0 = stem + maxpool)
     hw, ch = [h2], [64]
     for k in range(1, 5):
@@ -334,9 +335,16 @@ class ResNetEncoder:
             wf = w * scale.view(-1, 1, 1, 1)
             if cv["role"] == "stem":
                 w1 = wf.sum(dim=1)                                      # [64, 7, 7]: 3 identical channels folded
-                mat = torch.zeros(w1.shape[0], 8, 8, dtype=torch.float64)      # K index = r*8 + s (stem_tc.cu)
-                mat[:, :7, :7] = w1
-                mat = mat.reshape(w1.shape[0], 64)
+                if self.fused_stem:
+                    # stem_tc.cu: row v*64+c, K index t*8+s holds w[c][t-4v][s] (variant 1 = the filter 4 patch rows lower)
+                    mat = torch.zeros(2, 64, 16, 8, dtype=torch.float64)
+                    mat[0, :, 0:7, :7] = w1
+                    mat[1, :, 4:11, :7] = w1
+                    mat = mat.reshape(128, 128)
+                else:
+                    mat = torch.zeros(w1.shape[0], 8, 8, dtype=torch.float64)  # im2col kernel: K index = r*8 + s
+                    mat[:, :7, :7] = w1
+                    mat = mat.reshape(w1.shape[0], 64)
                 return self._dev(mat.to(torch.bfloat16)), None, self._dev(shift.float())
             return self._dev(wf.permute(0, 2, 3, 1).to(torch.bfloat16)), None, self._dev(shift.float())   # [K,R,S,C]
         return self._dev(w.permute(2, 3, 1, 0).float()), self._dev(scale.float()), self._dev(shift.float())  # [R,S,C,K]
@@ -368,19 +376,29 @@ class ResNetEncoder:
         esz = 2 if self.bf16 else 4
         h1 = (S + 6 - 7) // 2 + 1
         h2 = (h1 + 2 - 3) // 2 + 1
-        if self.bf16:
+        self.input_padded = None
+        if self.bf16 and self.fused_stem:
+            # zero-padded one-channel images (border written once, here); `input` is the S x S interior view
+            pitch, rows = _lib.stem_padded_dims(S)
+            self.input_padded = torch.zeros((n, rows, pitch), dtype=torch.bfloat16, device=self.device)
+            lo = _lib.STEM_PAD_LO
+            self.input = self.input_padded[:, lo:lo + S, lo:lo + S]
+            in_bytes = rows * pitch * 2
+        elif self.bf16:
             self.input = torch.empty((n, S, S), dtype=torch.bfloat16, device=self.device)
+            in_bytes = S * S * 2
         else:
             self.input = torch.empty((n, S, S, 3), dtype=torch.float32, device=self.device)
+            in_bytes = S * S * 3 * 4
         self.output = torch.empty((n, self.emb_dim), dtype=torch.float32, device=self.device)
         self.chunks = self._chunk_sizes(h2, esz)
-        ops, extents, self.final_hw = lower_resnet(self.arch, n, S, self.bf16, self.fused_stem, self.chunks)
+        ops, extents, self.final_hw = lower_resnet(self.arch, n, S, self.bf16, self.fused_stem, self.chunks, in_bytes)
         weights = {cv["name"]: self._conv_weights(sd, cv) for cv in conv_list(self.arch)}
 
         self.buffers = {name: torch.empty(nbytes, dtype=torch.uint8, device=self.device) for name, nbytes in extents.items()
                         if name not in ("input", "output")}
         base = {name: t.data_ptr() for name, t in self.buffers.items()}
-        base["input"] = self.input.data_ptr()
+        base["input"] = (self.input_padded if self.input_padded is not None else self.input).data_ptr()
         base["output"] = self.output.data_ptr()
         cops: List[_lib.Op] = []
         self.op_names: List[str] = []
@@ -423,7 +441,7 @@ class ResNetEncoder:
         """x: [n,S,S] bf16 (bf16 path) or [n,S,S,3] f32 (fp32 path); None = data already in self.input.
         Enqueues on the current stream, returns the (reused) output buffer [n, D] f32."""
         if x is not None and x.data_ptr() != self.input.data_ptr():
-            self.input.copy_(x.reshape(self.input.shape))
+            self.input.copy_(x.reshape(self.input.shape))      # (into the interior view when the input is padded)
         _lib.check(self.lib.pdf_plan_run(self.plan, _lib.stream_ptr()), "pdf_plan_run")
         return self.output
 

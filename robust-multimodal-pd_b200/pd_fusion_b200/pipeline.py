@@ -37,7 +37,7 @@ class EmbeddingPipeline:
         if precision == "bf16" and (len(set(float(m) for m in mean)) != 1 or len(set(float(s) for s in std)) != 1):
             raise ValueError("the bf16 path folds the three identical input channels and needs channel-uniform mean/std; "
                              "use precision='fp32' for per-channel statistics")
-        mode = _lib.OUT_BF16_C1 if precision == "bf16" else _lib.OUT_F32_NHWC3
+        mode = _lib.OUT_BF16_C1_PAD if precision == "bf16" else _lib.OUT_F32_NHWC3   # the fused stem reads a zero-padded image
         with torch.cuda.device(self.device):
             self.pre = VolumePreprocessor(in_shape, target_shape, axes, counts, input_size, mean, std, mode,
                                           self.max_subjects, self.device)
@@ -45,6 +45,10 @@ class EmbeddingPipeline:
             self.enc = ResNetEncoder(backbone_state_dict, self.max_subjects * self.L, input_size, precision,
                                      arch or detect_arch(backbone_state_dict), self.device)
             self.D = self.enc.emb_dim
+            # preprocessing writes straight into the encoder's input buffer
+            enc_in = self.enc.input_padded if self.enc.input_padded is not None else self.enc.input
+            self._net_input = enc_in.view(self.pre.net_input.shape)
+            self.pre.net_input = self._net_input
             self.mean_out = torch.empty((self.max_subjects, self.D), dtype=torch.float32, device=self.device)
             self.nvalid = torch.empty((self.max_subjects,), dtype=torch.int32, device=self.device)
 
@@ -54,7 +58,7 @@ class EmbeddingPipeline:
         B = int(raw.shape[0])
         if B < self.max_subjects:   # the encoder plan is built for max_subjects*L images: clear the unused tail
             self.enc.input[B * self.L:].zero_()
-        res = self.pre.run(raw, net_input=self.enc.input.view(self.pre.net_input.shape))
+        res = self.pre.run(raw, net_input=self._net_input)
         emb = self.enc.forward(None).view(self.max_subjects, self.L, self.D)
         self.nvalid[:B].copy_(res.nslices.sum(dim=1))
         _lib.check(self.lib.pdf_slice_mean(B, self.L, self.D, emb.data_ptr(), self.nvalid.data_ptr(), self.mean_out.data_ptr(),

@@ -18,7 +18,7 @@ from . import _lib
 
 @dataclass
 class PreprocResult:
-    net_input: torch.Tensor   # [B, L, S, S] bf16 or [B, L, S, S, 3] f32
+    net_input: torch.Tensor   # [B, L, S, S] bf16, [B, L, rows, pitch] bf16 (zero-padded) or [B, L, S, S, 3] f32
     zoomed: torch.Tensor      # [B, T0, T1, T2] f32 (resampled, un-normalised)
     lohi: torch.Tensor        # [B, 4] f32: lo, hi, denominator, has_positive
     indices: torch.Tensor     # [B, L] i32 (-1 in unused slots)
@@ -65,6 +65,9 @@ class VolumePreprocessor:
             self.nslices = torch.empty((B, len(self.axes)), dtype=torch.int32, device=self.device)
             if out_mode == _lib.OUT_BF16_C1:
                 self.net_input = torch.empty((B, self.lmax, S, S), dtype=torch.bfloat16, device=self.device)
+            elif out_mode == _lib.OUT_BF16_C1_PAD:
+                pitch, rows = _lib.stem_padded_dims(S)       # the border is zeroed here, once; the kernels only write the image
+                self.net_input = torch.zeros((B, self.lmax, rows, pitch), dtype=torch.bfloat16, device=self.device)
             else:
                 self.net_input = torch.empty((B, self.lmax, S, S, 3), dtype=torch.float32, device=self.device)
 
@@ -133,5 +136,5 @@ class VolumePreprocessor:
             dims = [T0, T1, T2]
             dims.pop(a)
             plane += 4 * c * dims[0] * dims[1]
-        b_out = 2 if self.out_mode == _lib.OUT_BF16_C1 else 12
+        b_out = 12 if self.out_mode == _lib.OUT_F32_NHWC3 else 2
         return 4 * X * Y * Z + 8 * T0 * T1 * T2 + plane + b_out * self.lmax * self.input_size ** 2

@@ -44,6 +44,14 @@ def test_argument_validation_without_gpu():
     assert rc == -1
 
 
+def test_stem_padded_dims_host_function():
+    # pure host arithmetic: 224 -> 56 x 56 pooled pixels in 7 x 8 tiles of 8 x 7; last patch ends at row 230 / column 231
+    assert _lib.stem_padded_dims(224) == (232, 231)
+    for S in (64, 70, 96, 128):
+        pitch, rows = _lib.stem_padded_dims(S)
+        assert pitch % 8 == 0 and pitch >= S + 5 and rows >= S + 5
+
+
 def test_no_cpu_fallback():
     import torch
     if torch.cuda.is_available():

@@ -85,6 +85,15 @@ def test_preproc_batch_and_bf16_output():
         assert np.array_equal(got[:len(idx[0])], idx[0]) and np.array_equal(got[5:5 + len(idx[1])], idx[1])
     a = res32.net_input[..., 0].to(torch.bfloat16)
     assert torch.equal(a, res16.net_input)
+    # zero-padded layout read by the fused stem: same pixels at origin (5, 5), exact zeros everywhere else
+    _, resp, _ = _run(raws, target, [0, 2], [5, 3], 48, _lib.OUT_BF16_C1_PAD)
+    lo = _lib.STEM_PAD_LO
+    pad = resp.net_input
+    assert pad.shape[2:] == tuple(reversed(_lib.stem_padded_dims(48)))
+    assert torch.equal(pad[:, :, lo:lo + 48, lo:lo + 48], res16.net_input)
+    border = pad.clone()
+    border[:, :, lo:lo + 48, lo:lo + 48] = 0
+    assert not border.any()
 
 
 def test_resample_property_full_size():

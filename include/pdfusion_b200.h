@@ -229,6 +229,10 @@ int pdf_selftest_umma_shift(int N, int shift, int mode, const void* d_a_bf16, co
  * d_cycles[grid] receives the SM-clock cycles each CTA took (profiles/r01_umma_rate.txt). */
 int pdf_selftest_umma_rate(int N, int iters, int mode, int grid, unsigned long long* d_cycles, pdf_stream_t stream);
 
+/* Debug hook: CTA 0 of the following PDF_OP_STEM_FUSED launches records clock64 stamps of its warp roles,
+ * [64 tiles][16 events] u64, into d_buf (NULL switches it off). */
+int pdf_debug_set_trace(unsigned long long* d_buf);
+
 /* Test hook: disable != 0 makes later pdf_plan_create calls route 3x3/s1 64->64 convolutions through the generic
  * im2col kernel instead of the halo-resident kernel (A/B parity of the two tensor-core kernels). */
 int pdf_debug_disable_halo(int disable);

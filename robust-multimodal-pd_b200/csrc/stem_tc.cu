@@ -15,9 +15,9 @@
 //
 //   warps 0..3   epilogue: tcgen05.ld -> vertical/horizontal max -> +bias, ReLU -> bf16 NHWC store
 //   warp  4      TMA load of the weights, tcgen05.mma issue (6 x M128 N192 K16 per tile), TMEM alloc
-//   warps 5..12  build the B matrix (im2col) in shared memory, 128B-swizzled K-major, from the patch; double buffered
+//   warps 5..14  build the B matrix (im2col) in shared memory, 128B-swizzled K-major, from the patch; a 3-stage ring
 //                against the MMAs; two TMEM accumulators overlap epilogue and MMA
-//   warp  13     TMA producer: the 39 x 40 input patch of tile t+4 lands in a 4-stage ring while tile t is built
+//   warp  15     TMA producer: the 39 x 40 input patch of tile t+4 lands in a 4-stage ring while tile t is built
 //
 // The input image is read from a zero-PADDED buffer (origin at row/column 5, see pdf_stem_padded_dims): the patch
 // origin is then (4*pp0, 4*pq0) >= 0 and every 8-pixel chunk of the staged patch is a 4-byte aligned shared-memory read.
@@ -36,18 +36,45 @@ constexpr int kStemBBlock = kSites * 128;        // one 64-wide K block of B
 constexpr int kStemBStage = 2 * kStemBBlock;
 constexpr int kStemABlock = 128 * 128;
 constexpr int kStemABytes = 2 * kStemABlock;
-constexpr int kStemWarps = 14;
-constexpr int kStemBuilders = 8 * 32;
+constexpr int kBuilderWarps = 10;                // 585 chunks over 320 threads: two rounds
+constexpr int kStemWarps = 4 + 1 + kBuilderWarps + 1;
+constexpr int kStemBuilders = kBuilderWarps * 32;
+constexpr int kBStages = 3;                      // B ring (the two TMEM accumulators bound the epilogue side)
 constexpr int kPatchCols = 40;                   // 35 needed (+4 when the box start is rounded down to 16 bytes); 80-byte rows
 constexpr int kPatchStages = 4;
 constexpr int kPatchStage = (kPatchRows * kPatchCols * 2 + 127) / 128 * 128;
-constexpr int kStemSmem = kStemABytes + 2 * kStemBStage + kPatchStages * kPatchStage + 256 + 1024;
+constexpr int kStemSmem = kStemABytes + kBStages * kStemBStage + kPatchStages * kPatchStage + 256 + 1024;
 
 struct StemParams {
   const __nv_bfloat16* in;    // padded [n, rows, pitch]
   const float* bias;          // [64]
   __nv_bfloat16* out;         // [n, P, P, 64]
-  int pitch, rows, H1, P, tiles_x, tiles_per_image, total_tiles;
+  int pitch, rows, H1, P, tiles_x, tiles_y, total_tiles;
+  unsigned long long* trace;  // debug: per-role clock64 stamps of CTA 0 (pdf_debug_set_trace), or NULL
+};
+
+// stamp slot: [it][event]; events 0-2 producer/builder, 3-5 MMA, 6-8 epilogue
+#define STEM_TRACE(ev) do { if (p.trace && blockIdx.x == 0 && it < 64 && (threadIdx.x & 31) == 0) p.trace[it * 16 + (ev)] = clock64(); } while (0)
+
+// (image, tile row, tile column) of the tiles blockIdx.x, blockIdx.x + gridDim.x, ... without a division per tile
+struct TileIter {
+  int n, ty, tx, dn, dty, dtx, tiles_x, tiles_y;
+  __device__ TileIter(int first, int stride, int tiles_x_, int tiles_y_) : tiles_x(tiles_x_), tiles_y(tiles_y_) {
+    const int per = tiles_x * tiles_y;
+    n = first / per;
+    int r = first - n * per;
+    ty = r / tiles_x;
+    tx = r - ty * tiles_x;
+    dn = stride / per;
+    r = stride - dn * per;
+    dty = r / tiles_x;
+    dtx = r - dty * tiles_x;
+  }
+  __device__ __forceinline__ void next() {
+    tx += dtx; ty += dty; n += dn;
+    if (tx >= tiles_x) { tx -= tiles_x; ++ty; }
+    if (ty >= tiles_y) { ty -= tiles_y; ++n; }
+  }
 };
 
 __device__ __forceinline__ void tmem_ld16_nowait(uint32_t taddr, uint32_t (&v)[16]) {
@@ -69,11 +96,11 @@ stem_fused_kernel(const __grid_constant__ CUtensorMap tmap_w, const __grid_const
   const uint32_t base = (raw_addr + 1023u) & ~1023u;
   uint8_t* smem = smem_raw + (base - raw_addr);
   const uint32_t sA = base, sB = base + kStemABytes;
-  const uint32_t sP = sB + 2 * kStemBStage;
+  const uint32_t sP = sB + kBStages * kStemBStage;
   const uint32_t bar0 = sP + kPatchStages * kPatchStage;
-  const uint32_t bar_w = bar0, bar_bfull = bar0 + 8, bar_bempty = bar0 + 24, bar_accfull = bar0 + 40, bar_accempty = bar0 + 56;
-  const uint32_t bar_pfull = bar0 + 72, bar_pempty = bar_pfull + 8 * kPatchStages;
-  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(smem + (bar0 - base) + 72 + 16 * kPatchStages);
+  const uint32_t bar_w = bar0, bar_bfull = bar0 + 8, bar_bempty = bar_bfull + 8 * kBStages, bar_accfull = bar_bempty + 8 * kBStages;
+  const uint32_t bar_accempty = bar_accfull + 16, bar_pfull = bar_accempty + 16, bar_pempty = bar_pfull + 8 * kPatchStages;
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(smem + (bar_pempty + 8 * kPatchStages - base));
 
   const int tid = threadIdx.x, lane = tid & 31;
   const int warp = __shfl_sync(0xffffffffu, tid >> 5, 0);
@@ -82,13 +109,15 @@ stem_fused_kernel(const __grid_constant__ CUtensorMap tmap_w, const __grid_const
     if (elect_one()) {
       prefetch_tmap(&tmap_w);
       mbar_init(bar_w, 1);
-      for (int s = 0; s < 2; ++s) {
-        mbar_init(bar_bfull + 8 * s, 8);       // one arrive per builder warp
-        mbar_init(bar_bempty + 8 * s, 1);      // tcgen05.commit
-        mbar_init(bar_accfull + 8 * s, 1);     // tcgen05.commit
-        mbar_init(bar_accempty + 8 * s, 4);    // one arrive per epilogue warp
+      for (int s = 0; s < kBStages; ++s) {
+        mbar_init(bar_bfull + 8 * s, kBuilderWarps);   // one arrive per builder warp
+        mbar_init(bar_bempty + 8 * s, 1);              // tcgen05.commit
       }
-      for (int s = 0; s < kPatchStages; ++s) { mbar_init(bar_pfull + 8 * s, 1); mbar_init(bar_pempty + 8 * s, 8); }
+      for (int s = 0; s < 2; ++s) {
+        mbar_init(bar_accfull + 8 * s, 1);             // tcgen05.commit
+        mbar_init(bar_accempty + 8 * s, 4);            // one arrive per epilogue warp
+      }
+      for (int s = 0; s < kPatchStages; ++s) { mbar_init(bar_pfull + 8 * s, 1); mbar_init(bar_pempty + 8 * s, kBuilderWarps); }
       fence_barrier_init();
       mbar_expect_tx(bar_w, kStemABytes);
       tma_load_2d(sA, &tmap_w, bar_w, 0, 0);
@@ -99,7 +128,7 @@ stem_fused_kernel(const __grid_constant__ CUtensorMap tmap_w, const __grid_const
   }
   // B rows of the unused column slot (cx = 15) and the K padding (t = 11) are never written by the builders: they only
   // have to be finite, so both stages are zeroed once
-  for (int i = tid; i < 2 * kStemBStage / 16; i += kStemWarps * 32)
+  for (int i = tid; i < kBStages * kStemBStage / 16; i += kStemWarps * 32)
     reinterpret_cast<uint4*>(smem + kStemABytes)[i] = make_uint4(0u, 0u, 0u, 0u);
   fence_proxy_async();
   tc_fence_before();
@@ -113,18 +142,21 @@ stem_fused_kernel(const __grid_constant__ CUtensorMap tmap_w, const __grid_const
     const float bias_c = __ldg(p.bias + c);
     const uint32_t tlane = tmem_base + ((uint32_t)(warp * 32) << 16);
     int it = 0;
-    for (int tile = blockIdx.x; tile < p.total_tiles; tile += gridDim.x, ++it) {
+    TileIter ti(blockIdx.x, gridDim.x, p.tiles_x, p.tiles_y);
+    for (int tile = blockIdx.x; tile < p.total_tiles; tile += gridDim.x, ++it, ti.next()) {
       const int stage = it & 1;
       const uint32_t phase = (uint32_t)(it >> 1) & 1u;
-      const int n = tile / p.tiles_per_image, rem = tile - n * p.tiles_per_image;
-      const int ty = rem / p.tiles_x, tx = rem - ty * p.tiles_x;
-      const int pp0 = ty * kPR, pq0 = tx * kPQ;
+      const int n = ti.n;
+      const int pp0 = ti.ty * kPR, pq0 = ti.tx * kPQ;
       const int cy0 = 2 * pp0 - 1, cx0 = 2 * pq0 - 1;
       const bool col_edge = cx0 < 0 || cx0 + kConvCols > p.H1;
       const size_t orow_stride = (size_t)p.P * 64;
       __nv_bfloat16* otile = p.out + (((size_t)n * p.P + pp0 + v) * p.P + pq0) * 64 + c;
       mbar_wait(bar_accfull + 8 * stage, phase);
+      if (warp == 0) STEM_TRACE(6);
       tc_fence_after();
+      // tcgen05.ld moves only ~64-100 B/clk per SM (gpurun_out/stem_trace.txt): reading the 96 KB accumulator is the longest
+      // stage of this kernel; issuing the loads further ahead (a register double buffer) was measured slower.
 #pragma unroll
       for (int i = 0; i < 4; ++i) {
         uint32_t r0[16], r1[16], r2[16];
@@ -137,6 +169,7 @@ stem_fused_kernel(const __grid_constant__ CUtensorMap tmap_w, const __grid_const
           tc_fence_before();
           __syncwarp();
           if (lane == 0) mbar_arrive_cta(bar_accempty + 8 * stage);
+          if (warp == 0) STEM_TRACE(7);
         }
         const int pr = pp0 + 2 * i + v;
         if (pr >= p.P) continue;
@@ -162,6 +195,7 @@ stem_fused_kernel(const __grid_constant__ CUtensorMap tmap_w, const __grid_const
           if (pq0 + j < p.P) orow[j * 64] = __float2bfloat16(fmaxf(h + bias_c, 0.f));
         }
       }
+      if (warp == 0) STEM_TRACE(8);
     }
   } else if (warp == 4) {
     // ------------------------------------------------------------------------------------------ MMA issue
@@ -171,30 +205,34 @@ stem_fused_kernel(const __grid_constant__ CUtensorMap tmap_w, const __grid_const
       mbar_wait(bar_w, 0);
       int it = 0;
       for (int tile = blockIdx.x; tile < p.total_tiles; tile += gridDim.x, ++it) {
-        const int stage = it & 1;
-        const uint32_t phase = (uint32_t)(it >> 1) & 1u;
-        mbar_wait(bar_accempty + 8 * stage, phase ^ 1u);
-        mbar_wait(bar_bfull + 8 * stage, phase);
+        const int acc = it & 1, bs = it % kBStages;
+        const uint32_t phase = (uint32_t)(it >> 1) & 1u, bphase = (uint32_t)(it / kBStages) & 1u;
+        mbar_wait(bar_accempty + 8 * acc, phase ^ 1u);
+        STEM_TRACE(3);
+        mbar_wait(bar_bfull + 8 * bs, bphase);
+        STEM_TRACE(4);
         tc_fence_after();
-        const uint32_t b_lo = smem_desc_lo(sB + stage * kStemBStage);
-        const uint32_t d = tmem_base + (uint32_t)(stage * 256);
+        const uint32_t b_lo = smem_desc_lo(sB + bs * kStemBStage);
+        const uint32_t d = tmem_base + (uint32_t)(acc * 256);
 #pragma unroll
         for (int ks = 0; ks < 6; ++ks)
           umma_f16_lo(d, a_lo + (uint32_t)((ks >> 2) * (kStemABlock / 16) + (ks & 3) * 2),
                       b_lo + (uint32_t)((ks >> 2) * (kStemBBlock / 16) + (ks & 3) * 2), idesc, ks != 0 ? 1u : 0u);
-        umma_commit(bar_bempty + 8 * stage);
-        umma_commit(bar_accfull + 8 * stage);
+        umma_commit(bar_bempty + 8 * bs);
+        umma_commit(bar_accfull + 8 * acc);
+        STEM_TRACE(5);
       }
     }
-  } else if (warp < 13) {
+  } else if (warp < 5 + kBuilderWarps) {
     // ------------------------------------------------------------------------------------------ B builders
     // The (patch row, conv column) chunks a thread copies, and the B rows each one lands in, are the same for every tile:
     // the offsets are computed once and live in registers.
     const int bt = tid - 5 * 32;
-    int ld_off[3];
-    uint32_t st_off[3][6];
+    constexpr int kRounds = (kPatchRows * kConvCols + kStemBuilders - 1) / kStemBuilders;
+    int ld_off[kRounds];
+    uint32_t st_off[kRounds][6];
 #pragma unroll
-    for (int k = 0; k < 3; ++k) {
+    for (int k = 0; k < kRounds; ++k) {
       const int idx = bt + k * kStemBuilders;
       const bool have = idx < kPatchRows * kConvCols;
       const int y = idx / kConvCols, cx = idx - y * kConvCols;
@@ -209,16 +247,18 @@ stem_fused_kernel(const __grid_constant__ CUtensorMap tmap_w, const __grid_const
       }
     }
     int it = 0;
-    for (int tile = blockIdx.x; tile < p.total_tiles; tile += gridDim.x, ++it) {
-      const int stage = it & 1, ps = it % kPatchStages;
-      const uint32_t phase = (uint32_t)(it >> 1) & 1u, pphase = (uint32_t)(it / kPatchStages) & 1u;
-      const int tx = (tile % p.tiles_per_image) % p.tiles_x;
-      const uint32_t pbase = sP + (uint32_t)ps * kPatchStage + (uint32_t)(((4 * tx * kPQ) & 7) * 2);   // see the TMA producer
+    TileIter ti(blockIdx.x, gridDim.x, p.tiles_x, p.tiles_y);
+    for (int tile = blockIdx.x; tile < p.total_tiles; tile += gridDim.x, ++it, ti.next()) {
+      const int stage = it % kBStages, ps = it % kPatchStages;
+      const uint32_t phase = (uint32_t)(it / kBStages) & 1u, pphase = (uint32_t)(it / kPatchStages) & 1u;
+      const uint32_t pbase = sP + (uint32_t)ps * kPatchStage + (uint32_t)(((4 * ti.tx * kPQ) & 7) * 2);   // see the TMA producer
       const uint32_t bbase = sB + (uint32_t)stage * kStemBStage;
       mbar_wait(bar_pfull + 8 * ps, pphase);
+      if (warp == 5) STEM_TRACE(0);
       mbar_wait(bar_bempty + 8 * stage, phase ^ 1u);
+      if (warp == 5) STEM_TRACE(1);
 #pragma unroll
-      for (int k = 0; k < 3; ++k) {
+      for (int k = 0; k < kRounds; ++k) {
         if (ld_off[k] >= 0) {
           const uint32_t a = pbase + (uint32_t)ld_off[k];
           uint32_t v0, v1, v2, v3;
@@ -238,17 +278,18 @@ stem_fused_kernel(const __grid_constant__ CUtensorMap tmap_w, const __grid_const
         mbar_arrive_cta(bar_bfull + 8 * stage);
         mbar_arrive_cta(bar_pempty + 8 * ps);
       }
+      if (warp == 5) STEM_TRACE(2);
     }
   } else {
     // ------------------------------------------------------------------------------------------ patch TMA producer
     if (elect_one()) {
       prefetch_tmap(&tmap_in);
       int it = 0;
-      for (int tile = blockIdx.x; tile < p.total_tiles; tile += gridDim.x, ++it) {
+      TileIter ti(blockIdx.x, gridDim.x, p.tiles_x, p.tiles_y);
+      for (int tile = blockIdx.x; tile < p.total_tiles; tile += gridDim.x, ++it, ti.next()) {
         const int ps = it % kPatchStages;
         const uint32_t pphase = (uint32_t)(it / kPatchStages) & 1u;
-        const int n = tile / p.tiles_per_image, rem = tile - n * p.tiles_per_image;
-        const int ty = rem / p.tiles_x, tx = rem - ty * p.tiles_x;
+        const int n = ti.n, ty = ti.ty, tx = ti.tx;
         mbar_wait(bar_pempty + 8 * ps, pphase ^ 1u);
         mbar_expect_tx(bar_pfull + 8 * ps, kPatchRows * kPatchCols * 2);
         // padded coordinates of the patch origin: image row 4*pp0-5 -> padded row 4*pp0, likewise for columns.  A TMA box must
@@ -279,6 +320,13 @@ extern "C" int pdf_stem_padded_dims(int S, int* pitch, int* rows) {
   return PDF_OK;
 }
 
+static unsigned long long* g_stem_trace = nullptr;
+/* debug hook: CTA 0 of the next fused-stem launches writes clock64 stamps [64 tiles][16 events] into d_buf (NULL = off) */
+extern "C" int pdf_debug_set_trace(unsigned long long* d_buf) {
+  g_stem_trace = d_buf;
+  return PDF_OK;
+}
+
 namespace pdf {
 
 int launch_stem_fused(const pdf_op& op, const TensorMapBlob& tmap_w, const TensorMapBlob& tmap_in, cudaStream_t s) {
@@ -295,8 +343,9 @@ int launch_stem_fused(const pdf_op& op, const TensorMapBlob& tmap_w, const Tenso
   p.H1 = (op.h + 6 - 7) / 2 + 1;
   p.P = op.ho;
   p.tiles_x = ceil_div(p.P, kPQ);
-  p.tiles_per_image = p.tiles_x * ceil_div(p.P, kPR);
-  p.total_tiles = p.tiles_per_image * op.n;
+  p.tiles_y = ceil_div(p.P, kPR);
+  p.total_tiles = p.tiles_x * p.tiles_y * op.n;
+  p.trace = g_stem_trace;
   const int grid = max(1, min(p.total_tiles, num_sms()));
   stem_fused_kernel<<<grid, kStemWarps * 32, kStemSmem, s>>>(*reinterpret_cast<const CUtensorMap*>(&tmap_w),
                                                              *reinterpret_cast<const CUtensorMap*>(&tmap_in), p);

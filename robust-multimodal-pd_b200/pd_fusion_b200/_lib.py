@@ -109,6 +109,7 @@ PROTOTYPES = {
     "pdf_selftest_umma": (C.c_int, [C.c_int, C.c_int, C.c_int, _P, _P, _P, _P]),
     "pdf_selftest_umma_shift": (C.c_int, [C.c_int, C.c_int, C.c_int, _P, _P, _P, _P]),
     "pdf_selftest_umma_rate": (C.c_int, [C.c_int, C.c_int, C.c_int, C.c_int, _P, _P]),
+    "pdf_debug_set_trace": (C.c_int, [_P]),
     "pdf_debug_disable_halo": (C.c_int, [C.c_int]),
 }
 

@@ -64,8 +64,8 @@ conv3x3_c64_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_cons
     if (elect_one()) {
       mbar_expect_tx(bar_w, 9 * 8192);
       for (int t = 0; t < 9; ++t) tma_load_2d(s_w + t * 8192, &tmap_w, bar_w, t * 64, 0);
-      // Warm L2 for the tile kPrefetchAhead iterations ahead (halo rows, and the residual rows its epilogue will read):
-      // the shared-memory ring is only two stages deep, so without this every halo load pays the full HBM latency.
+      // Warm L2 with the halo rows of the tile kPrefetchAhead iterations ahead: the shared-memory ring is only two stages deep.
+      // (Prefetching the residual rows the same way was measured to DOUBLE their DRAM traffic -- profiles/r01_ncu_conv_b32.txt.)
       auto prefetch_tile = [&](int tile) {
         if (tile >= p.total_tiles) return;
         const int n = tile / p.tiles_per_image;
@@ -73,12 +73,6 @@ conv3x3_c64_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_cons
         const int p_lo = m0 / p.Wp;
         asm volatile("cp.async.bulk.prefetch.tensor.4d.L2.global.tile [%0, {%1, %2, %3, %4}];"
                      ::"l"(reinterpret_cast<uint64_t>(&tmap_a)), "r"(0), "r"(-1), "r"(p_lo - 1), "r"(n) : "memory");
-        if (p.residual) {
-          const int p_hi = min(p.H - 1, (m0 + kHaloBM - 1) / p.Wp);
-          const __nv_bfloat16* r0 = p.residual + (((size_t)n * p.H + p_lo) * p.W) * 64;
-          const uint32_t bytes = (uint32_t)(p_hi - p_lo + 1) * (uint32_t)p.W * 128u;
-          asm volatile("cp.async.bulk.prefetch.L2.global [%0], %1;" ::"l"(reinterpret_cast<uint64_t>(r0)), "r"(bytes) : "memory");
-        }
       };
       for (int a = kHaloStages; a < kHaloStages + kPrefetchAhead; ++a) prefetch_tile(blockIdx.x + a * gridDim.x);
       int it = 0;

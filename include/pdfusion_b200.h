@@ -102,6 +102,31 @@ int pdf_preprocess(const pdf_preproc_cfg* cfg, int batch, const float* d_raw, fl
                    float* d_lohi, int32_t* d_indices, int32_t* d_nslices, void* d_out, int out_mode,
                    pdf_stream_t stream);
 
+/* ------------------------------------------------------------------------------------------
+ * a6 -- test-time augmentation (`tta > 1`): data/openneuro_features.py:166-178,235-248 and
+ * scripts/build_resnet2d_mil_embeddings.py:124-146.  The random draws (angle, translation, scale, shift and the
+ * N(0, sigma) field) are made ON THE HOST with the reference's exact numpy calls and passed in as data; the
+ * affine resampling, intensity map, noise add and clip run here.
+ * ------------------------------------------------------------------------------------------ */
+typedef struct {
+  double rot[4];    /* row-major 2x2 matrix handed to scipy.ndimage.affine_transform */
+  double offset[2]; /* its offset = center - rot @ center + translate */
+  float scale;      /* 1 + U(-intensity_scale, intensity_scale), rounded to float32 as numpy does */
+  float shift;
+} pdf_tta_params;
+
+/* `_select_slices` of the normalised volume for every requested axis group, concatenated: d_slices [B, Lmax, H, W] f32
+ * (slots beyond d_nslices are zero).  All groups must share one slice shape. */
+int pdf_gather_slices(const pdf_preproc_cfg* cfg, int batch, const float* d_zoomed, const float* d_lohi,
+                      const int32_t* d_indices, const int32_t* d_nslices, float* d_slices, pdf_stream_t stream);
+/* one augmentation pass: d_params [B]; d_noise [B, L, H, W] f64 or NULL (noise_std == 0); d_out [B, L, H, W] f32.
+ * affine_only != 0: stop after the affine resampling (`_apply_affine_2d` itself: no intensity map, noise or clip). */
+int pdf_tta_augment(int batch, int L, int H, int W, const float* d_slices, const pdf_tta_params* d_params,
+                    const double* d_noise, int affine_only, float* d_out, pdf_stream_t stream);
+/* bilinear resize (align_corners=False) + (x-mean)/std of ready-made slices in [0,1] -> network input in `out_mode` layout */
+int pdf_resize_slices(int batch, int L, int H, int W, int input_size, const float* mean, const float* std,
+                      const float* d_slices, void* d_out, int out_mode, pdf_stream_t stream);
+
 /* normalised volume itself (parity helper for _normalize_volume_for_resnet): d_zoomed -> d_norm */
 int pdf_normalize_volume(int batch, size_t voxels, const float* d_zoomed, const float* d_lohi, float* d_norm,
                          pdf_stream_t stream);

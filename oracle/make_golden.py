@@ -208,6 +208,73 @@ def gold_scripts():
     print("scripts.npz", {k: out[k] for k in ("c2/files", "mil/files")})
 
 
+def gold_tta():
+    """Test-time augmentation: the reference's `_apply_affine_2d` on its own, the augmented slice stacks of its `tta > 1`
+    loop (the loop body is inline script code, restated here with the reference's helper and the SAME numpy calls, then
+    checked against the embeddings the unmodified MIL script writes), and that script's output.  Run with PYTHONHASHSEED=0."""
+    out = {}
+    rng = np.random.default_rng(5)
+    # 1. _apply_affine_2d alone
+    for k, (H, W, ang, tr) in enumerate([(160, 160, 4.2, (3.5, -6.25)), (37, 52, -8.0, (0.0, 0.0)), (32, 32, 0.0, (0.0, 0.0)), (48, 40, 2.5, (-2.4, 2.0))]):
+        img = rng.random((H, W)).astype(np.float32)
+        img[: H // 6] = 0
+        out[f"affine/{k}/img"] = img
+        out[f"affine/{k}/angle"], out[f"affine/{k}/translate"] = np.float64(ang), np.array(tr, dtype=np.float64)
+        out[f"affine/{k}/out"] = of._apply_affine_2d(img, ang, np.array(tr, dtype=np.float64))
+    out["affine/n"] = np.array(4)
+    # 2. the MIL script with --tta 2 on two small subjects
+    targs = dict(max_rotation_deg=8.0, max_translation=0.05, intensity_scale=0.1, intensity_shift=0.1, noise_std=0.02)
+    with tempfile.TemporaryDirectory() as td:
+        td = Path(td)
+        manifest = write_synthetic_manifest(td / "vols", 2, shape=(48, 40, 36))
+        args = ["--backbone", "resnet18", "--target-shape", "32", "32", "32", "--slice-axes", "0", "2", "--slice-counts", "3", "2",
+                "--input-size", "64", "--batch-size", "4", "--tta", "2", "--max-rotation-deg", "8.0", "--noise-std", "0.02"]
+        od = td / "out"
+        argv = sys.argv
+        sys.argv = ["build_resnet2d_mil_embeddings.py", "--manifest", str(manifest), "--out-dir", str(od)] + args
+        try:
+            runpy.run_path(str(REF / "scripts" / "build_resnet2d_mil_embeddings.py"), run_name="__main__")
+        finally:
+            sys.argv = argv
+        npz = [p for p in od.iterdir() if p.suffix == ".npz"][0]
+        d = np.load(npz, allow_pickle=True)
+        out["script/emb"] = d["embeddings"]
+        out["script/argv"] = np.array(args)
+        out["script/files"] = np.array(sorted(p.name for p in od.iterdir()))
+        import pandas as pd
+        df = pd.read_csv(manifest)
+        seeds = [abs(hash(str(s))) % (2 ** 32) for s in df["subject_id"]]
+        out["script/seeds"] = np.array(seeds, dtype=np.int64)
+        out["script/subject_ids"] = np.array([str(s) for s in df["subject_id"]])
+        model, _, _ = of._build_resnet_backbone("resnet18")
+        model.eval()
+        for b, row in df.iterrows():
+            vol = of._normalize_volume_for_resnet(of._load_volume(Path(row["t1wbrain_path"]), target_shape=(32, 32, 32)))
+            sl = np.concatenate([of._select_slices(vol, 0, 3), of._select_slices(vol, 2, 2)], axis=0)
+            r = np.random.default_rng(seeds[b])
+            acc = None
+            for p_ in range(2):
+                aug = sl.copy()
+                angle = r.uniform(-targs["max_rotation_deg"], targs["max_rotation_deg"])
+                translate = r.uniform(-targs["max_translation"], targs["max_translation"], size=2)
+                translate = translate * np.array([aug.shape[1], aug.shape[2]])
+                for i in range(aug.shape[0]):
+                    aug[i] = of._apply_affine_2d(aug[i], angle, translate)
+                scale = 1.0 + r.uniform(-targs["intensity_scale"], targs["intensity_scale"])
+                shift = r.uniform(-targs["intensity_shift"], targs["intensity_shift"])
+                aug = aug * scale + shift
+                aug = aug + r.normal(0.0, targs["noise_std"], size=aug.shape)
+                aug = np.clip(aug, 0.0, 1.0).astype(np.float32, copy=False)
+                out[f"script/aug/{b}/{p_}"] = aug
+                with torch.no_grad():
+                    emb = model(ref_input_tensor(aug, 64)).numpy()
+                acc = emb if acc is None else acc + emb
+            assert np.allclose(acc / 2, d["embeddings"][b], rtol=0, atol=1e-5), "restated TTA loop disagrees with the reference script"
+        out["script/targs"] = np.array(json.dumps(targs))
+    np.savez_compressed(GOLD / "tta.npz", **out)
+    print("tta.npz", out["script/emb"].shape, seeds)
+
+
 def _sd_np(sd):
     return {k: v.detach().cpu().numpy() for k, v in sd.items()}
 
@@ -308,7 +375,7 @@ def gold_heads():
 
 if __name__ == "__main__":
     GOLD.mkdir(parents=True, exist_ok=True)
-    which = sys.argv[1:] or ["preproc", "embed", "scripts", "heads"]
+    which = sys.argv[1:] or ["preproc", "embed", "scripts", "heads", "tta"]
     os.environ.setdefault("PYTHONHASHSEED", "0")
     for w in which:
         globals()[f"gold_{w}"]()

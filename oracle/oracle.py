@@ -15,6 +15,7 @@ versions installed here in brackets) is restated from its published algorithm:
   * numpy.percentile / linspace      [numpy 2.3.5]   -> `percentile_linear`, `linspace_indices`
   * torch F.interpolate(bilinear)    [torch 2.11.0]  -> `bilinear_resize`
   * torchvision resnet18/50          [tv 0.26.0]     -> `resnet_forward` (torch fp32 functional ops)
+  * scipy.ndimage.affine_transform(order=1, mode="constant")  [scipy 1.18.1]  -> `affine_transform_linear`
 Integer/index work is numpy; floating-point contractions use torch fp32 on the CPU.
 """
 from __future__ import annotations
@@ -251,6 +252,82 @@ def embed_subject(raw: np.ndarray, sd, arch: str, target_shape=(160, 160, 160), 
     x = torch.from_numpy(slices_to_input(sl, input_size, mean, std))
     emb = resnet_forward(sd, arch, x, batch_size).numpy()
     return idx, emb
+
+
+# ----------------------------------------------------------------------------------------
+# a6  test-time augmentation (data/openneuro_features.py:166-178, 231-248; scripts/build_resnet2d_mil_embeddings.py:120-139)
+# ----------------------------------------------------------------------------------------
+def affine_transform_linear(img: np.ndarray, matrix: np.ndarray, offset: np.ndarray) -> np.ndarray:
+    """scipy.ndimage.affine_transform(img, matrix, offset, order=1, mode="constant", cval=0) for a 2-D float32 image:
+    input coordinate = offset + matrix @ (oy, ox) accumulated left to right in float64; a point whose coordinate leaves
+    [0, len-1] on either axis is 0; otherwise the 4 taps are summed as ((v * wy) * wx) in row-major tap order (a tap
+    index one past the edge -- only reachable with weight 0 -- reads cval) and rounded once to float32."""
+    H, W = img.shape
+    oy, ox = np.meshgrid(np.arange(H, dtype=np.float64), np.arange(W, dtype=np.float64), indexing="ij")
+    c0 = (offset[0] + oy * matrix[0, 0]) + ox * matrix[0, 1]
+    c1 = (offset[1] + oy * matrix[1, 0]) + ox * matrix[1, 1]
+    inside = (c0 >= 0) & (c0 <= H - 1) & (c1 >= 0) & (c1 <= W - 1)
+    f0, f1 = np.floor(c0), np.floor(c1)
+    y, x = c0 - f0, c1 - f1
+    i0 = np.clip(f0.astype(np.int64), 0, H - 1)
+    j0 = np.clip(f1.astype(np.int64), 0, W - 1)
+    v = img.astype(np.float64)
+
+    def tap(ii, jj):
+        ok = (ii < H) & (jj < W)
+        return np.where(ok, v[np.minimum(ii, H - 1), np.minimum(jj, W - 1)], 0.0)
+
+    t = np.zeros_like(c0)
+    t = t + (tap(i0, j0) * (1 - y)) * (1 - x)
+    t = t + (tap(i0, j0 + 1) * (1 - y)) * x
+    t = t + (tap(i0 + 1, j0) * y) * (1 - x)
+    t = t + (tap(i0 + 1, j0 + 1) * y) * x
+    return np.where(inside, t, 0.0).astype(img.dtype)
+
+
+def apply_affine_2d(slice_2d: np.ndarray, angle_deg: float, translate: np.ndarray) -> np.ndarray:
+    """`_apply_affine_2d` (openneuro_features.py:166-178)."""
+    theta = np.deg2rad(angle_deg)
+    rot = np.array([[np.cos(theta), -np.sin(theta)], [np.sin(theta), np.cos(theta)]])
+    center = np.array(slice_2d.shape) / 2.0
+    offset = center - rot @ center + translate
+    return affine_transform_linear(slice_2d, rot, offset)
+
+
+def tta_passes(slices: np.ndarray, seed: int, n_pass: int, max_rotation_deg=5.0, max_translation=0.05, intensity_scale=0.1,
+               intensity_shift=0.1, noise_std=0.01) -> List[np.ndarray]:
+    """The augmented float32 slice stacks of the `tta > 1` loop, one per pass, drawing from ONE Generator(seed) in the
+    reference's order (angle, translate[2], scale, shift, noise field); cast to float32 as the MIL script does (:139)."""
+    rng = np.random.default_rng(seed)
+    out = []
+    for _ in range(n_pass):
+        aug = slices.copy()
+        angle = rng.uniform(-max_rotation_deg, max_rotation_deg)
+        translate = rng.uniform(-max_translation, max_translation, size=2)
+        translate = translate * np.array([aug.shape[1], aug.shape[2]])
+        for i in range(aug.shape[0]):
+            aug[i] = apply_affine_2d(aug[i], angle, translate)
+        scale = 1.0 + rng.uniform(-intensity_scale, intensity_scale)
+        shift = rng.uniform(-intensity_shift, intensity_shift)
+        aug = aug * scale + shift                      # float32 array, weak python scalars: stays float32 (NEP 50)
+        if noise_std > 0:
+            aug = aug + rng.normal(0.0, noise_std, size=aug.shape)    # float64 from here
+        aug = np.clip(aug, 0.0, 1.0)
+        out.append(aug.astype(np.float32, copy=False))
+    return out
+
+
+def embed_subject_tta(raw: np.ndarray, sd, arch: str, seed: int, n_pass: int, tta_kwargs: Dict, target_shape=(160, 160, 160),
+                      axes=(2,), counts=(24,), input_size: int = 224, batch_size: int = 32):
+    """`tta > 1` path: per-slice embeddings averaged over the passes [L, D] f32."""
+    import torch
+
+    _, idx, sl = preprocess_subject(raw, target_shape, axes, counts)
+    acc = None
+    for aug in tta_passes(sl, seed, n_pass, **tta_kwargs):
+        emb = resnet_forward(sd, arch, torch.from_numpy(slices_to_input(aug, input_size)), batch_size).numpy()
+        acc = emb if acc is None else acc + emb
+    return idx, acc / max(1, n_pass)
 
 
 # ----------------------------------------------------------------------------------------

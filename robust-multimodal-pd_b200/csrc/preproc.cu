@@ -652,6 +652,7 @@ struct ResizeArgs {
   int counts[PDF_MAX_AXES];
   int lmax, S, cnt2;
   int pitch, rows;  // PDF_OUT_BF16_C1_PAD geometry
+  int ready;        // 1: `planes` holds ready-made normalised slices [B, lmax, T0, T1] (pdf_resize_slices): no clip / min-max
   float mean[3], inv_std[3];
   float scale_sq;   // T/S when the slice is square (the usual cubic target), hoisted out of the kernel
 };
@@ -676,12 +677,12 @@ resize_kernel(const float* __restrict__ zoomed, const float* __restrict__ planes
   int a = 0, t = l, off2 = 0;
   while (a < ra.n_axes - 1 && t >= ra.counts[a]) { if (ra.axes[a] == 2) off2 += ra.counts[a]; t -= ra.counts[a]; ++a; }
   const int axis = ra.axes[a];
-  const bool valid = t < nslices[(size_t)b * ra.n_axes + a];
+  const bool valid = ra.ready ? true : t < nslices[(size_t)b * ra.n_axes + a];
   const size_t opix = PAD ? (((size_t)b * ra.lmax + l) * ra.rows + oy + PDF_STEM_PAD_LO) * ra.pitch + (size_t)(ox0 + PDF_STEM_PAD_LO)
                           : ((size_t)b * ra.lmax + l) * S * S + (size_t)oy * S + ox0;
   float r[4] = {0.f, 0.f, 0.f, 0.f};
   if (valid) {
-    const int idx = indices[(size_t)b * ra.lmax + l];
+    const int idx = ra.ready ? 0 : indices[(size_t)b * ra.lmax + l];
     const int T0 = ra.T[0], T1 = ra.T[1], T2 = ra.T[2];
     const float* src;
     int H, W;
@@ -690,8 +691,8 @@ resize_kernel(const float* __restrict__ zoomed, const float* __restrict__ planes
     else if (axis == 1) { src = zoomed + (size_t)b * T0 * T1 * T2 + (size_t)idx * T2; H = T0; W = T2; rs = (size_t)T1 * T2; }
     else { src = planes + ((size_t)b * ra.cnt2 + off2 + t) * T0 * T1; H = T0; W = T1; rs = T1; }
     const float* l4 = lohi + 4 * (size_t)b;
-    const float lo = l4[0], hi = l4[1];
-    const float inv_den = __frcp_rn(l4[2]);
+    const float lo = ra.ready ? 0.0f : l4[0], hi = ra.ready ? 1.0f : l4[1];       // ready slices already lie in [0, 1]
+    const float inv_den = ra.ready ? 1.0f : __frcp_rn(l4[2]);
     // ATen area_pixel_compute_source_index(align_corners=False): (dst + 0.5) * (in/out) - 0.5, clamped at 0
     const float sh = (H == W) ? ra.scale_sq : __fdiv_rn((float)H, (float)S);
     const float sw = (H == W) ? ra.scale_sq : __fdiv_rn((float)W, (float)S);
@@ -735,6 +736,77 @@ resize_kernel(const float* __restrict__ zoomed, const float* __restrict__ planes
 #pragma unroll
       for (int c = 0; c < 3; ++c) o[j * 3 + c] = valid ? (r[j] - ra.mean[c]) * ra.inv_std[c] : 0.0f;
     }
+  }
+}
+
+// normalised selected slices themselves ([B, Lmax, H, W] f32, `_select_slices` of the normalised volume): the input of
+// the test-time-augmentation path.  Axis 0 -> [n, Y, Z], axis 1 -> [n, X, Z], axis 2 -> [n, X, Y].
+__global__ void gather_slices_kernel(const float* __restrict__ zoomed, const float* __restrict__ lohi, const int32_t* __restrict__ indices,
+                                     const int32_t* __restrict__ nslices, float* __restrict__ out, FinalizeArgs fa, int H, int W) {
+  const int b = blockIdx.z, l = blockIdx.y;
+  int a = 0, t = l;
+  while (a < fa.n_axes - 1 && t >= fa.counts[a]) { t -= fa.counts[a]; ++a; }
+  const int axis = fa.axes[a];
+  const bool valid = t < nslices[(size_t)b * fa.n_axes + a];
+  const int idx = valid ? indices[(size_t)b * fa.lmax + l] : 0;
+  const int T1 = fa.T[1], T2 = fa.T[2];
+  const float* zb = zoomed + (size_t)b * fa.T[0] * T1 * T2;
+  const float* l4 = lohi + 4 * (size_t)b;
+  const float lo = l4[0], hi = l4[1], den = l4[2];
+  float* ob = out + ((size_t)b * fa.lmax + l) * H * W;
+  for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < H * W; i += gridDim.x * blockDim.x) {
+    float v = 0.0f;
+    if (valid) {
+      const int y = i / W, x = i - y * W;
+      const size_t src = axis == 0 ? ((size_t)idx * T1 + y) * T2 + x : axis == 1 ? ((size_t)y * T1 + idx) * T2 + x : ((size_t)y * T1 + x) * T2 + idx;
+      v = normalise(__ldg(zb + src), lo, hi, den);
+    }
+    ob[i] = v;
+  }
+}
+
+// a6, one augmentation pass: scipy.ndimage.affine_transform(order=1, mode="constant", cval=0) of every slice with the
+// subject's matrix/offset (float64 coordinates and weights, taps accumulated as ((v*wy)*wx) row-major, one rounding to
+// f32), then x*scale+shift in float32, + noise in float64 (when given), clip to [0,1], float32
+// (data/openneuro_features.py:166-178, 237-248; scripts/build_resnet2d_mil_embeddings.py:126-139).
+__global__ void tta_kernel(const float* __restrict__ slices, const pdf_tta_params* __restrict__ params, const double* __restrict__ noise,
+                           float* __restrict__ out, int L, int H, int W, int affine_only) {
+  const int b = blockIdx.z, l = blockIdx.y;
+  const pdf_tta_params pr = params[b];
+  const size_t base = ((size_t)b * L + l) * H * W;
+  const float* img = slices + base;
+  for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < H * W; i += gridDim.x * blockDim.x) {
+    const int oy = i / W, ox = i - oy * W;
+    const double c0 = __dadd_rn(__dadd_rn(pr.offset[0], __dmul_rn((double)oy, pr.rot[0])), __dmul_rn((double)ox, pr.rot[1]));
+    const double c1 = __dadd_rn(__dadd_rn(pr.offset[1], __dmul_rn((double)oy, pr.rot[2])), __dmul_rn((double)ox, pr.rot[3]));
+    float a = 0.0f;
+    if (c0 >= 0.0 && c0 <= (double)(H - 1) && c1 >= 0.0 && c1 <= (double)(W - 1)) {
+      const double f0 = floor(c0), f1 = floor(c1);
+      const double y = __dsub_rn(c0, f0), x = __dsub_rn(c1, f1);
+      const int i0 = (int)f0, j0 = (int)f1;
+      const bool i1ok = i0 + 1 < H, j1ok = j0 + 1 < W;
+      const double wy0 = __dsub_rn(1.0, y), wx0 = __dsub_rn(1.0, x);
+      const double v00 = (double)img[i0 * W + j0];
+      const double v01 = j1ok ? (double)img[i0 * W + j0 + 1] : 0.0;
+      const double v10 = i1ok ? (double)img[(i0 + 1) * W + j0] : 0.0;
+      const double v11 = (i1ok && j1ok) ? (double)img[(i0 + 1) * W + j0 + 1] : 0.0;
+      double t = 0.0;
+      t = __dadd_rn(t, __dmul_rn(__dmul_rn(v00, wy0), wx0));
+      t = __dadd_rn(t, __dmul_rn(__dmul_rn(v01, wy0), x));
+      t = __dadd_rn(t, __dmul_rn(__dmul_rn(v10, y), wx0));
+      t = __dadd_rn(t, __dmul_rn(__dmul_rn(v11, y), x));
+      a = __double2float_rn(t);
+    }
+    if (affine_only) { out[base + i] = a; continue; }      // `_apply_affine_2d` alone
+    a = __fadd_rn(__fmul_rn(a, pr.scale), pr.shift);
+    float r;
+    if (noise) {
+      const double d = __dadd_rn((double)a, noise[base + i]);
+      r = __double2float_rn(fmin(fmax(d, 0.0), 1.0));
+    } else {
+      r = fminf(fmaxf(a, 0.0f), 1.0f);
+    }
+    out[base + i] = r;
   }
 }
 
@@ -889,6 +961,7 @@ extern "C" int pdf_gather_resize_normalize(const pdf_preproc_cfg* cfg, int batch
     off += cfg->counts[a];
   }
   ra.pitch = ra.rows = 0;
+  ra.ready = 0;
   if (out_mode == PDF_OUT_BF16_C1_PAD) {
     if (int rc = pdf_stem_padded_dims(ra.S, &ra.pitch, &ra.rows)) return rc;
   }
@@ -917,6 +990,67 @@ extern "C" int pdf_normalize_volume(int batch, size_t voxels, const float* d_zoo
   PDF_REQUIRE(batch > 0 && voxels > 0 && d_zoomed && d_lohi && d_norm, "pdf_normalize_volume: bad arguments");
   const int blocks = max(1, min((int)((voxels + 255) / 256), 2048));
   normalize_kernel<<<dim3(blocks, batch), 256, 0, as_stream(stream)>>>(d_zoomed, d_lohi, d_norm, voxels);
+  PDF_CHECK_LAUNCH();
+  return PDF_OK;
+}
+
+extern "C" int pdf_gather_slices(const pdf_preproc_cfg* cfg, int batch, const float* d_zoomed, const float* d_lohi,
+                                 const int32_t* d_indices, const int32_t* d_nslices, float* d_slices, pdf_stream_t stream) {
+  if (int rc = validate(cfg, batch)) return rc;
+  PDF_REQUIRE(d_zoomed && d_lohi && d_indices && d_nslices && d_slices, "pdf_gather_slices: null device pointer");
+  FinalizeArgs fa;
+  fa.lmax = 0; fa.n_axes = cfg->n_axes; fa.extent_raw = 0;
+  for (int i = 0; i < 3; ++i) fa.T[i] = cfg->out_shape[i];
+  int H = -1, W = -1;
+  for (int a = 0; a < PDF_MAX_AXES; ++a) {
+    fa.axes[a] = a < cfg->n_axes ? cfg->axes[a] : 0;
+    fa.counts[a] = a < cfg->n_axes ? cfg->counts[a] : 0;
+    fa.lmax += fa.counts[a];
+    if (a < cfg->n_axes) {
+      const int h = cfg->out_shape[fa.axes[a] == 0 ? 1 : 0], w = cfg->out_shape[fa.axes[a] == 2 ? 1 : 2];
+      PDF_REQUIRE(H < 0 || (H == h && W == w), "pdf_gather_slices: all slice groups must share one slice shape (the reference concatenates them)");
+      H = h; W = w;
+    }
+  }
+  const int xb = max(1, min(ceil_div((long long)H * W, 256 * 4), 64));
+  gather_slices_kernel<<<dim3(xb, fa.lmax, batch), 256, 0, as_stream(stream)>>>(d_zoomed, d_lohi, d_indices, d_nslices, d_slices, fa, H, W);
+  PDF_CHECK_LAUNCH();
+  return PDF_OK;
+}
+
+extern "C" int pdf_tta_augment(int batch, int L, int H, int W, const float* d_slices, const pdf_tta_params* d_params,
+                               const double* d_noise, int affine_only, float* d_out, pdf_stream_t stream) {
+  PDF_REQUIRE(batch > 0 && L > 0 && H > 0 && W > 0 && d_slices && d_params && d_out, "pdf_tta_augment: bad arguments");
+  const int xb = max(1, min(ceil_div((long long)H * W, 256 * 2), 64));
+  tta_kernel<<<dim3(xb, L, batch), 256, 0, as_stream(stream)>>>(d_slices, d_params, d_noise, d_out, L, H, W, affine_only);
+  PDF_CHECK_LAUNCH();
+  return PDF_OK;
+}
+
+extern "C" int pdf_resize_slices(int batch, int L, int H, int W, int input_size, const float* mean, const float* std,
+                                 const float* d_slices, void* d_out, int out_mode, pdf_stream_t stream) {
+  PDF_REQUIRE(batch > 0 && L > 0 && H >= 2 && W >= 2 && input_size >= 1 && mean && std && d_slices && d_out, "pdf_resize_slices: bad arguments");
+  PDF_REQUIRE(out_mode == PDF_OUT_BF16_C1 || out_mode == PDF_OUT_F32_NHWC3 || out_mode == PDF_OUT_BF16_C1_PAD, "pdf_resize_slices: bad out_mode");
+  if (out_mode != PDF_OUT_F32_NHWC3)
+    PDF_REQUIRE(mean[0] == mean[1] && mean[1] == mean[2] && std[0] == std[1] && std[1] == std[2], "one-channel output needs channel-uniform mean/std");
+  ResizeArgs ra;
+  memset(&ra, 0, sizeof(ra));
+  ra.ready = 1; ra.n_axes = 1; ra.axes[0] = 2; ra.counts[0] = L; ra.lmax = L; ra.cnt2 = L; ra.S = input_size;
+  ra.T[0] = H; ra.T[1] = W; ra.T[2] = 1;
+  for (int i = 0; i < 3; ++i) { ra.mean[i] = mean[i]; ra.inv_std[i] = 1.0f / std[i]; }
+  ra.scale_sq = (float)H / (float)ra.S;
+  if (out_mode == PDF_OUT_BF16_C1_PAD) {
+    if (int rc = pdf_stem_padded_dims(ra.S, &ra.pitch, &ra.rows)) return rc;
+  }
+  const int groups = out_mode == PDF_OUT_BF16_C1_PAD ? ra.pitch / 4 : (ra.S + 3) / 4;
+  const dim3 grid(ceil_div((long long)ra.S * groups, 256), L, batch);
+  cudaStream_t s = as_stream(stream);
+  if (out_mode == PDF_OUT_BF16_C1_PAD)
+    resize_kernel<PDF_OUT_BF16_C1_PAD><<<grid, 256, 0, s>>>(nullptr, d_slices, nullptr, nullptr, nullptr, d_out, ra);
+  else if (out_mode == PDF_OUT_BF16_C1)
+    resize_kernel<PDF_OUT_BF16_C1><<<grid, 256, 0, s>>>(nullptr, d_slices, nullptr, nullptr, nullptr, d_out, ra);
+  else
+    resize_kernel<PDF_OUT_F32_NHWC3><<<grid, 256, 0, s>>>(nullptr, d_slices, nullptr, nullptr, nullptr, d_out, ra);
   PDF_CHECK_LAUNCH();
   return PDF_OK;
 }

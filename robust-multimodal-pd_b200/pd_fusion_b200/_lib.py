@@ -39,6 +39,10 @@ class PreprocCfg(C.Structure):
     ]
 
 
+class TtaParams(C.Structure):
+    _fields_ = [("rot", C.c_double * 4), ("offset", C.c_double * 2), ("scale", C.c_float), ("shift", C.c_float)]
+
+
 class Op(C.Structure):
     _fields_ = [
         ("kind", C.c_int32), ("precision", C.c_int32),
@@ -93,6 +97,9 @@ PROTOTYPES = {
     "pdf_select_bounds_indices": (C.c_int, [C.POINTER(PreprocCfg), C.c_int, _P, _P, _P, _P, _P, _P]),
     "pdf_gather_resize_normalize": (C.c_int, [C.POINTER(PreprocCfg), C.c_int, _P, _P, _P, _P, _P, _P, C.c_int, _P]),
     "pdf_preprocess": (C.c_int, [C.POINTER(PreprocCfg), C.c_int, _P, _P, _P, _P, _P, _P, _P, C.c_int, _P]),
+    "pdf_gather_slices": (C.c_int, [C.POINTER(PreprocCfg), C.c_int, _P, _P, _P, _P, _P, _P]),
+    "pdf_tta_augment": (C.c_int, [C.c_int, C.c_int, C.c_int, C.c_int, _P, _P, _P, C.c_int, _P, _P]),
+    "pdf_resize_slices": (C.c_int, [C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, C.POINTER(C.c_float), C.POINTER(C.c_float), _P, _P, C.c_int, _P]),
     "pdf_normalize_volume": (C.c_int, [C.c_int, C.c_size_t, _P, _P, _P, _P]),
     "pdf_stem_padded_dims": (C.c_int, [C.c_int, C.POINTER(C.c_int), C.POINTER(C.c_int)]),
     "pdf_plan_create": (C.c_int, [C.POINTER(_P), C.POINTER(Op), C.c_int]),

@@ -140,7 +140,16 @@ def _build_resnet_backbone(backbone: str, pretrained: bool = True):
 
 
 def _apply_affine_2d(slice_2d: np.ndarray, angle_deg: float, translate: np.ndarray) -> np.ndarray:
-    raise NotImplementedError("test-time augmentation (tta > 1) is not implemented on the B200 path yet (SURVEY.md 8a row a6)")
+    """Rotation about the slice centre + translation, bilinear, zero outside (reference: openneuro_features.py:166-178;
+    scipy.ndimage.affine_transform order 1, mode "constant") -- `pdf_tta_augment` with affine_only on the device."""
+    from .tta import TtaDraw, affine_matrix, params_bytes
+    img = np.ascontiguousarray(slice_2d, dtype=np.float32)
+    rot, offset = affine_matrix(img.shape, angle_deg, np.asarray(translate, dtype=np.float64))
+    pre = _preprocessor((8, 8, 8), (8, 8, 8))           # any instance: only its library handle and device are used
+    dev = pre.device
+    params = torch.from_numpy(params_bytes([TtaDraw(rot, offset, 1.0, 0.0, None)])).to(dev)
+    out = pre.tta_augment(torch.from_numpy(img[None, None]).to(dev), params, None, affine_only=True)
+    return out[0, 0].cpu().numpy().astype(slice_2d.dtype, copy=False)
 
 
 # ---------------------------------------------------------------------------------------------------
@@ -153,12 +162,17 @@ def _mean_std(weights) -> Tuple[List[float], List[float]]:
 
 
 def embed_manifest(df: pd.DataFrame, backbone: str, target_shape: Sequence[int], axes: Sequence[int], counts: Sequence[int],
-                   input_size: int, tta: int = 1) -> Tuple[np.ndarray, np.ndarray]:
+                   input_size: int, tta: int = 1, tta_cfg: Dict | None = None, tta_seeds: Sequence[int] | None = None
+                   ) -> Tuple[np.ndarray, np.ndarray]:
     """Per-slice embeddings [S, L, D] f32 and slice-mean embeddings [S, D] f32 for every manifest row, in row order.
     Subjects are processed in device batches; under torchrun each rank embeds its contiguous shard of rows and the
     table is assembled with an all-gather."""
-    if int(tta) > 1:
-        raise NotImplementedError("tta > 1 is not implemented on the B200 path yet (SURVEY.md 8a row a6)")
+    from .tta import subject_seed, tta_config
+    tta = int(tta)
+    tta_cfg = tta_config(tta_cfg or {})
+    if tta > 1 and tta_seeds is None:                   # the reference's per-subject Generator seed (process-salted hash)
+        ids = df["subject_id"].tolist() if "subject_id" in df.columns else [""] * len(df)
+        tta_seeds = [subject_seed(s) for s in ids]
     rank, local_rank, ws = world()
     dev = torch.device("cuda", local_rank)
     torch.cuda.set_device(dev)
@@ -191,7 +205,10 @@ def embed_manifest(df: pd.DataFrame, backbone: str, target_shape: Sequence[int],
             pipes[first.shape] = EmbeddingPipeline(sd, first.shape, target_shape, axes, counts, input_size, precision, bsz,
                                                    mean, std, "resnet50" if backbone == "resnet50" else "resnet18", dev)
         raw = torch.from_numpy(np.stack(batch)).pin_memory().to(dev, non_blocking=True)
-        res = pipes[first.shape].embed(raw)
+        if tta > 1:
+            res = pipes[first.shape].embed_tta(raw, [tta_seeds[k] for k in range(i, j)], tta, tta_cfg)
+        else:
+            res = pipes[first.shape].embed(raw)
         emb[i - lo:j - lo].copy_(res.embeddings)
         avg[i - lo:j - lo].copy_(res.mean)
         nsl[i - lo:j - lo].copy_(res.nslices.sum(dim=1))
@@ -224,7 +241,7 @@ def build_resnet2d_embeddings(manifest_path: Path, cache_dir: Path, config: Dict
     df = pd.read_csv(manifest_path)
     _, avg = embed_manifest(df, config.get("backbone", "resnet18"), tuple(config.get("target_shape", (160, 160, 160))),
                             [int(config.get("slice_axis", 2))], [int(config.get("slice_count", 24))],
-                            int(config.get("input_size", 224)), int(config.get("tta", 1)))
+                            int(config.get("input_size", 224)), int(config.get("tta", 1)), config)
     cols = {"subject_id": df["subject_id"].values, "session": df["session"].values, "label": df["label"].astype(int).values}
     emb64 = avg.astype(np.float64)                      # the reference stores python floats -> float64 columns
     cols.update({f"mri_resnet_{k}": emb64[:, k] for k in range(emb64.shape[1])})
@@ -242,7 +259,7 @@ def build_resnet2d_mil_embeddings(manifest_path: Path, out_dir: Path, cfg: Dict,
     out_path = out_dir / f"resnet2d_mil_{_hash_file(manifest_path)}_{_hash_config(cfg)}.npz"
     df = pd.read_csv(manifest_path)
     emb, _ = embed_manifest(df, cfg["backbone"], tuple(cfg["target_shape"]), list(axes), list(counts), int(cfg["input_size"]),
-                            int(cfg.get("tta", 1)))
+                            int(cfg.get("tta", 1)), cfg)
     if embed_manifest.short_bags is not None:
         row, n = embed_manifest.short_bags
         raise ValueError(f"all input arrays must have the same shape: subject row {row} has {n} slices, expected {emb.shape[1]}")

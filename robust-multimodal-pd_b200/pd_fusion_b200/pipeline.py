@@ -65,6 +65,48 @@ class EmbeddingPipeline:
                                            _lib.stream_ptr()), "pdf_slice_mean")
         return EmbedResult(emb[:B], self.mean_out[:B], res.indices, res.nslices)
 
+    def embed_tta(self, raw: torch.Tensor, seeds, n_pass: int, tta_cfg: Dict) -> EmbedResult:
+        """`tta > 1` path of the builders (data/openneuro_features.py:235-265): every pass re-augments the selected slices
+        (affine, intensity, noise, clip), runs the backbone, and the per-slice / slice-mean embeddings are averaged over the
+        passes.  seeds[b] seeds subject b's numpy Generator (the reference: abs(hash(str(subject_id))) % 2**32)."""
+        import numpy as np
+
+        from .data.tta import draw_passes, params_bytes
+
+        B = int(raw.shape[0])
+        self.pre.resample(raw)
+        _, indices, nslices = self.pre.select(B)
+        slices = self.pre.gather_slices(B)
+        H, W = self.pre.slice_shape()
+        ns = nslices.cpu().numpy()                          # the noise field's shape depends on the slices actually found
+        counts = self.pre.counts
+        draws = [draw_passes(int(seeds[b]), n_pass, int(ns[b].sum()), (H, W), tta_cfg) for b in range(B)]
+        emb_sum = torch.zeros((B, self.L, self.D), dtype=torch.float32, device=self.device)
+        mean_sum = torch.zeros((B, self.D), dtype=torch.float32, device=self.device)
+        self.nvalid[:B].copy_(nslices.sum(dim=1))
+        if B < self.max_subjects:
+            self.enc.input[B * self.L:].zero_()
+        for p in range(n_pass):
+            params = torch.from_numpy(params_bytes([draws[b][p] for b in range(B)])).to(self.device)
+            noise = None
+            if draws[0][p].noise is not None:
+                host = np.zeros((B, self.L, H, W), dtype=np.float64)
+                for b in range(B):
+                    k, off = 0, 0
+                    for a, c in enumerate(counts):              # valid slices are the first ns[b, a] slots of each axis group
+                        n = int(ns[b, a])
+                        host[b, off:off + n] = draws[b][p].noise[k:k + n]
+                        k, off = k + n, off + c
+                noise = torch.from_numpy(host).to(self.device)
+            aug = self.pre.tta_augment(slices, params, noise)
+            self.pre.resize_slices(aug, out=self._net_input)
+            emb = self.enc.forward(None).view(self.max_subjects, self.L, self.D)
+            _lib.check(self.lib.pdf_slice_mean(B, self.L, self.D, emb.data_ptr(), self.nvalid.data_ptr(), self.mean_out.data_ptr(),
+                                               _lib.stream_ptr()), "pdf_slice_mean")
+            emb_sum += emb[:B]
+            mean_sum += self.mean_out[:B]
+        return EmbedResult(emb_sum / float(n_pass), mean_sum / float(n_pass), indices, nslices)
+
     def embed_host(self, host_batches, out_bags: bool = False):
         """End-to-end path for volumes that live in (pinned) HOST memory: iterates over `host_batches` (tensors
         [B, X, Y, Z] f32), overlapping the H2D copy of batch i+1 (copy stream, second device buffer) with the kernels

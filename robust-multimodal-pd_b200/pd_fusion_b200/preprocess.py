@@ -119,6 +119,46 @@ class VolumePreprocessor:
                    "pdf_gather_resize_normalize")
         return self.net_input[:B]
 
+    # ---- test-time augmentation (a6): slices -> affine/intensity/noise/clip -> network input
+    def slice_shape(self):
+        """(H, W) of the selected slices; every axis group must agree (the reference concatenates them)."""
+        shapes = set()
+        for a in self.axes:
+            dims = list(self.target_shape)
+            dims.pop(a)
+            shapes.add(tuple(dims))
+        if len(shapes) != 1:
+            raise ValueError("slice groups of different shapes cannot be concatenated (the reference needs a cubic target_shape)")
+        return shapes.pop()
+
+    def gather_slices(self, B: int) -> torch.Tensor:
+        """`_select_slices` of the normalised volume, all axis groups concatenated: [B, L, H, W] f32 (after select())."""
+        H, W = self.slice_shape()
+        if getattr(self, "_slices", None) is None:
+            self._slices = torch.empty((self.max_batch, self.lmax, H, W), dtype=torch.float32, device=self.device)
+        _lib.check(self.lib.pdf_gather_slices(C.byref(self.cfg), B, self.zoomed.data_ptr(), self.lohi.data_ptr(), self.indices.data_ptr(),
+                                              self.nslices.data_ptr(), self._slices.data_ptr(), _lib.stream_ptr()), "pdf_gather_slices")
+        return self._slices[:B]
+
+    def tta_augment(self, slices: torch.Tensor, params: torch.Tensor, noise: torch.Tensor | None, affine_only: bool = False) -> torch.Tensor:
+        """One augmentation pass.  slices [B, L, H, W] f32; params = pdf_tta_params bytes of the B subjects on the device;
+        noise [B, L, H, W] f64 on the device or None."""
+        B, L, H, W = (int(v) for v in slices.shape)
+        out = torch.empty_like(slices)
+        _lib.check(self.lib.pdf_tta_augment(B, L, H, W, slices.data_ptr(), params.data_ptr(), _lib.ptr(noise), int(affine_only),
+                                            out.data_ptr(), _lib.stream_ptr()), "pdf_tta_augment")
+        return out
+
+    def resize_slices(self, slices: torch.Tensor, out: torch.Tensor | None = None) -> torch.Tensor:
+        """Bilinear resize + (x-mean)/std of ready-made [0,1] slices into the network-input layout of this preprocessor."""
+        B, L, H, W = (int(v) for v in slices.shape)
+        out = self.net_input if out is None else out
+        mean = (C.c_float * 3)(*[float(v) for v in self.cfg.mean])
+        std = (C.c_float * 3)(*[float(v) for v in self.cfg.std])
+        _lib.check(self.lib.pdf_resize_slices(B, L, H, W, self.input_size, mean, std, slices.data_ptr(), out.data_ptr(), self.out_mode,
+                                              _lib.stream_ptr()), "pdf_resize_slices")
+        return out[:B]
+
     def normalized_volume(self, B: int) -> torch.Tensor:
         """`_normalize_volume_for_resnet` output itself (parity helper)."""
         out = torch.empty_like(self.zoomed[:B])

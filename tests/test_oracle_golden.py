@@ -131,3 +131,37 @@ def test_moddrop_and_moe_probs(golden):
             Xd[m] = _robust_scale(df[cm].values) * mk[:, i:i + 1]
         p = O.moe_predict_proba(sdm, Xd, mk.astype(np.float32))
         np.testing.assert_allclose(p, g["moe/probs"][s], atol=2e-6, rtol=0)
+
+
+def test_tta_affine_and_passes_bit_exact(golden):
+    """a6: scipy.ndimage.affine_transform (order 1, constant) restated bit for bit, and the augmented slice stacks of the
+    reference's `tta > 1` loop reproduced from the stored per-subject seeds."""
+    g = golden("tta")
+    for k in range(int(g["affine/n"])):
+        got = O.apply_affine_2d(g[f"affine/{k}/img"], float(g[f"affine/{k}/angle"]), g[f"affine/{k}/translate"])
+        assert np.array_equal(got.view(np.uint32), g[f"affine/{k}/out"].view(np.uint32)), k
+    targs = json.loads(str(g["script/targs"]))
+    from pd_fusion_b200.synthetic import write_synthetic_manifest  # noqa: F401  (same generator the fixture used)
+    for b, seed in enumerate(g["script/seeds"]):
+        raw = synthetic_volume(b, (48, 40, 36))
+        _, _, sl = O.preprocess_subject(raw, (32, 32, 32), [0, 2], [3, 2])
+        for p, aug in enumerate(O.tta_passes(sl, int(seed), 2, **targs)):
+            want = g[f"script/aug/{b}/{p}"]
+            assert aug.dtype == np.float32 and np.array_equal(aug.view(np.uint32), want.view(np.uint32)), (b, p)
+
+
+def test_product_tta_draws_match_oracle(golden):
+    """The product's host-side draw logic (pd_fusion_b200/data/tta.py) consumes the Generator exactly like the reference:
+    feeding its draws through the oracle's arithmetic reproduces the reference's augmented slices."""
+    from pd_fusion_b200.data.tta import draw_passes, params_bytes, tta_config
+    g = golden("tta")
+    targs = tta_config(json.loads(str(g["script/targs"])))
+    raw = synthetic_volume(0, (48, 40, 36))
+    _, _, sl = O.preprocess_subject(raw, (32, 32, 32), [0, 2], [3, 2])
+    draws = draw_passes(int(g["script/seeds"][0]), 2, sl.shape[0], sl.shape[1:], targs)
+    for p, d in enumerate(draws):
+        aug = np.stack([O.affine_transform_linear(s, d.rot, d.offset) for s in sl])
+        aug = aug * np.float32(d.scale) + np.float32(d.shift)
+        aug = np.clip(aug + d.noise, 0.0, 1.0).astype(np.float32)
+        assert np.array_equal(aug.view(np.uint32), g[f"script/aug/0/{p}"].view(np.uint32)), p
+    assert params_bytes([draws[0], draws[1]]).size == 2 * 56

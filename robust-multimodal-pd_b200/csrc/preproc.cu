@@ -603,7 +603,17 @@ hist_kernel(const float* __restrict__ zoomed, SubjState* __restrict__ states, si
   const float4* z4 = reinterpret_cast<const float4*>(zb);
   const bool aligned = ((reinterpret_cast<uintptr_t>(zb) & 15) == 0);
   if (aligned) {
-    for (size_t i = (size_t)blockIdx.x * 256 + tid; i < n4; i += (size_t)gridDim.x * 256) {
+    // four independent 16-byte loads in flight per thread: the pass is latency-bound otherwise (one load per iteration)
+    const size_t stride = (size_t)gridDim.x * 256;
+    size_t i = (size_t)blockIdx.x * 256 + tid;
+    for (; i + 3 * stride < n4; i += 4 * stride) {
+      const float4 a = __ldcs(z4 + i), b = __ldcs(z4 + i + stride), c = __ldcs(z4 + i + 2 * stride), d = __ldcs(z4 + i + 3 * stride);
+      visit(a.x); visit(a.y); visit(a.z); visit(a.w);
+      visit(b.x); visit(b.y); visit(b.z); visit(b.w);
+      visit(c.x); visit(c.y); visit(c.z); visit(c.w);
+      visit(d.x); visit(d.y); visit(d.z); visit(d.w);
+    }
+    for (; i < n4; i += stride) {
       const float4 v = z4[i];
       visit(v.x); visit(v.y); visit(v.z); visit(v.w);
     }
@@ -735,6 +745,85 @@ resize_kernel(const float* __restrict__ zoomed, const float* __restrict__ planes
     for (int j = 0; j < npx; ++j) {
 #pragma unroll
       for (int c = 0; c < 3; ++c) o[j * 3 + c] = valid ? (r[j] - ra.mean[c]) * ra.inv_std[c] : 0.0f;
+    }
+  }
+}
+
+// bf16 outputs: a thread owns four adjacent output columns for a band of rows, so the horizontal source indices and
+// weights are computed once and stay in registers; per pixel only the four loads, the clips and the blend remain
+// (the generic kernel above spends ~110 instructions per pixel, mostly on index arithmetic).
+// block (64, 4): x = column group (4 pixels), y = row lane; grid (row bands of kBandRows, slices, subjects).
+constexpr int kBandRows = 32;
+template <int MODE>
+__global__ void __launch_bounds__(256)
+resize_band_kernel(const float* __restrict__ zoomed, const float* __restrict__ planes, const float* __restrict__ lohi,
+                   const int32_t* __restrict__ indices, const int32_t* __restrict__ nslices, __nv_bfloat16* __restrict__ out, ResizeArgs ra) {
+  constexpr bool PAD = MODE == PDF_OUT_BF16_C1_PAD;
+  const int b = blockIdx.z, l = blockIdx.y;
+  const int S = ra.S;
+  const int gpr = PAD ? (ra.pitch >> 2) : ((S + 3) >> 2);
+  const int cg = threadIdx.x;
+  if (cg >= gpr) return;
+  const int ox0 = cg * 4 - (PAD ? PDF_STEM_PAD_LO : 0);
+  int a = 0, t = l, off2 = 0;
+  while (a < ra.n_axes - 1 && t >= ra.counts[a]) { if (ra.axes[a] == 2) off2 += ra.counts[a]; t -= ra.counts[a]; ++a; }
+  const int axis = ra.axes[a];
+  const bool valid = ra.ready ? true : t < nslices[(size_t)b * ra.n_axes + a];
+  const int idx = (ra.ready || !valid) ? 0 : indices[(size_t)b * ra.lmax + l];
+  const int T0 = ra.T[0], T1 = ra.T[1], T2 = ra.T[2];
+  const float* src;
+  int H, W;
+  size_t rs;
+  if (axis == 0) { src = zoomed + ((size_t)b * T0 + idx) * T1 * T2; H = T1; W = T2; rs = T2; }
+  else if (axis == 1) { src = zoomed + (size_t)b * T0 * T1 * T2 + (size_t)idx * T2; H = T0; W = T2; rs = (size_t)T1 * T2; }
+  else { src = planes + ((size_t)b * ra.cnt2 + off2 + t) * T0 * T1; H = T0; W = T1; rs = T1; }
+  float lo = 0.0f, hi = 1.0f, inv_den = 1.0f;                 // ready slices already lie in [0, 1]
+  if (!ra.ready && valid) { const float* l4 = lohi + 4 * (size_t)b; lo = l4[0]; hi = l4[1]; inv_den = __frcp_rn(l4[2]); }
+  // ATen area_pixel_compute_source_index(align_corners=False): (dst + 0.5) * (in/out) - 0.5, clamped at 0
+  const float sh = (H == W) ? ra.scale_sq : __fdiv_rn((float)H, (float)S);
+  const float sw = (H == W) ? ra.scale_sq : __fdiv_rn((float)W, (float)S);
+  int x0[4], x1[4];
+  float wx0[4], wx1[4];
+  bool inb[4];
+#pragma unroll
+  for (int j = 0; j < 4; ++j) {
+    inb[j] = ox0 + j >= 0 && ox0 + j < S;
+    const int ox = min(max(ox0 + j, 0), S - 1);
+    const float fx = fmaxf(__fsub_rn(__fmul_rn(__fadd_rn((float)ox, 0.5f), sw), 0.5f), 0.0f);
+    x0[j] = min((int)fx, W - 1);
+    x1[j] = min(x0[j] + 1, W - 1);
+    wx1[j] = __fsub_rn(fx, (float)x0[j]);
+    wx0[j] = __fsub_rn(1.0f, wx1[j]);
+  }
+  const float m0 = ra.mean[0], is0 = ra.inv_std[0];
+  const int oy_end = min(S, (int)(blockIdx.x + 1) * kBandRows);
+  for (int oy = blockIdx.x * kBandRows + threadIdx.y; oy < oy_end; oy += 4) {
+    const float fy = fmaxf(__fsub_rn(__fmul_rn(__fadd_rn((float)oy, 0.5f), sh), 0.5f), 0.0f);
+    const int y0 = min((int)fy, H - 1), y1 = min(y0 + 1, H - 1);
+    const float wy1 = __fsub_rn(fy, (float)y0), wy0 = __fsub_rn(1.0f, wy1);
+    const float* row0 = src + y0 * rs;
+    const float* row1 = src + y1 * rs;
+    uint32_t h[4];
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+      float r = 0.0f;
+      if (valid && inb[j]) {
+        const float v00 = fminf(fmaxf(__ldg(row0 + x0[j]), lo), hi), v01 = fminf(fmaxf(__ldg(row0 + x1[j]), lo), hi);
+        const float v10 = fminf(fmaxf(__ldg(row1 + x0[j]), lo), hi), v11 = fminf(fmaxf(__ldg(row1 + x1[j]), lo), hi);
+        const float top = __fadd_rn(__fmul_rn(wx0[j], v00), __fmul_rn(wx1[j], v01));
+        const float bot = __fadd_rn(__fmul_rn(wx0[j], v10), __fmul_rn(wx1[j], v11));
+        const float nrm = __fmul_rn(__fsub_rn(__fadd_rn(__fmul_rn(wy0, top), __fmul_rn(wy1, bot)), lo), inv_den);
+        r = __fmul_rn(__fsub_rn(nrm, m0), is0);     // same roundings as the f32 layout: no fused multiply-add
+      }
+      h[j] = (uint32_t)__bfloat16_as_ushort(__float2bfloat16(r));
+    }
+    const size_t opix = PAD ? (((size_t)b * ra.lmax + l) * ra.rows + oy + PDF_STEM_PAD_LO) * ra.pitch + (size_t)(cg * 4)
+                            : ((size_t)b * ra.lmax + l) * S * S + (size_t)oy * S + ox0;
+    __nv_bfloat16* o = out + opix;
+    if ((PAD || ox0 + 4 <= S) && ((reinterpret_cast<uintptr_t>(o) & 7) == 0)) {
+      *reinterpret_cast<uint2*>(o) = make_uint2(h[0] | (h[1] << 16), h[2] | (h[3] << 16));
+    } else {
+      for (int j = 0; j < 4 && ox0 + j < S; ++j) o[j] = __ushort_as_bfloat16((unsigned short)h[j]);
     }
   }
 }
@@ -923,6 +1012,22 @@ extern "C" int pdf_select_bounds_indices(const pdf_preproc_cfg* cfg, int batch, 
   return PDF_OK;
 }
 
+namespace pdf {
+// bf16 layouts go through the banded kernel when a row of column groups fits one block row (64 groups = 256 pixels)
+static bool launch_resize_band(const ResizeArgs& ra, int out_mode, int batch, const float* d_zoomed, const float* planes, const float* d_lohi,
+                               const int32_t* d_indices, const int32_t* d_nslices, void* d_out, cudaStream_t s) {
+  const int groups = out_mode == PDF_OUT_BF16_C1_PAD ? ra.pitch / 4 : (ra.S + 3) / 4;
+  if (out_mode == PDF_OUT_F32_NHWC3 || groups > 64) return false;
+  const dim3 grid(ceil_div(ra.S, kBandRows), ra.lmax, batch), block(64, 4);
+  __nv_bfloat16* o = reinterpret_cast<__nv_bfloat16*>(d_out);
+  if (out_mode == PDF_OUT_BF16_C1_PAD)
+    resize_band_kernel<PDF_OUT_BF16_C1_PAD><<<grid, block, 0, s>>>(d_zoomed, planes, d_lohi, d_indices, d_nslices, o, ra);
+  else
+    resize_band_kernel<PDF_OUT_BF16_C1><<<grid, block, 0, s>>>(d_zoomed, planes, d_lohi, d_indices, d_nslices, o, ra);
+  return true;
+}
+}  // namespace pdf
+
 extern "C" int pdf_gather_resize_normalize(const pdf_preproc_cfg* cfg, int batch, const float* d_zoomed, void* d_workspace,
                                               const float* d_lohi, const int32_t* d_indices, const int32_t* d_nslices,
                                               void* d_out, int out_mode, pdf_stream_t stream) {
@@ -964,6 +1069,10 @@ extern "C" int pdf_gather_resize_normalize(const pdf_preproc_cfg* cfg, int batch
   ra.ready = 0;
   if (out_mode == PDF_OUT_BF16_C1_PAD) {
     if (int rc = pdf_stem_padded_dims(ra.S, &ra.pitch, &ra.rows)) return rc;
+  }
+  if (launch_resize_band(ra, out_mode, batch, d_zoomed, w.planes, d_lohi, d_indices, d_nslices, d_out, s)) {
+    PDF_CHECK_LAUNCH();
+    return PDF_OK;
   }
   const int groups = out_mode == PDF_OUT_BF16_C1_PAD ? ra.pitch / 4 : (ra.S + 3) / 4;
   const dim3 grid(ceil_div((long long)ra.S * groups, 256), ra.lmax, batch);
@@ -1042,9 +1151,13 @@ extern "C" int pdf_resize_slices(int batch, int L, int H, int W, int input_size,
   if (out_mode == PDF_OUT_BF16_C1_PAD) {
     if (int rc = pdf_stem_padded_dims(ra.S, &ra.pitch, &ra.rows)) return rc;
   }
+  cudaStream_t s = as_stream(stream);
+  if (launch_resize_band(ra, out_mode, batch, nullptr, d_slices, nullptr, nullptr, nullptr, d_out, s)) {
+    PDF_CHECK_LAUNCH();
+    return PDF_OK;
+  }
   const int groups = out_mode == PDF_OUT_BF16_C1_PAD ? ra.pitch / 4 : (ra.S + 3) / 4;
   const dim3 grid(ceil_div((long long)ra.S * groups, 256), L, batch);
-  cudaStream_t s = as_stream(stream);
   if (out_mode == PDF_OUT_BF16_C1_PAD)
     resize_kernel<PDF_OUT_BF16_C1_PAD><<<grid, 256, 0, s>>>(nullptr, d_slices, nullptr, nullptr, nullptr, d_out, ra);
   else if (out_mode == PDF_OUT_BF16_C1)

@@ -142,7 +142,12 @@ int pdf_normalize_volume(int batch, size_t voxels, const float* d_zoomed, const 
 #define PDF_OP_STEM_IM2COL 3 /* [N,H,W] bf16 one-channel image -> [N*Ho*Wo, kpad] bf16 patch matrix (7x7 s2 p3) */
 #define PDF_OP_STEM_FUSED 4  /* zero-padded [N,rows,pitch] bf16 image (PDF_OUT_BF16_C1_PAD; h = w = S) -> conv 7x7 s2 p3 (64 ch) + bias
                                 + ReLU + maxpool 3x3 s2 p1 -> [N,ho,wo,64] bf16, one kernel.  d_weight: [128][128] bf16, row v*64+c,
-                                column t*8+s = w[c][t-4v][s] (BN folded, 3 input channels summed), zero elsewhere */
+                                column t*8+s = w[c][t-4v][s] (BN folded, 3 input channels summed), zero elsewhere.
+                                d_scale: NULL, or a border-correction blob for inputs whose (x-mean)/std is PER CHANNEL (the one
+                                channel fed to the kernel is then (x-mean_avg)/std_avg and the per-channel offsets become a bias that
+                                depends on how much of the 7x7 window lies inside the image):
+                                  int32 n_classes, int32 h1, int32 cls[h1], float delta[n_classes][n_classes][64]
+                                delta[cls[row]][cls[col]][k] is added to channel k of conv pixel (row, col); class 0 = interior */
 
 #define PDF_PREC_F32 0  /* CUDA-core FFMA path, 1e-5 parity */
 #define PDF_PREC_BF16 1 /* tcgen05/TMEM path, bf16 operands, f32 accumulate */

@@ -48,6 +48,7 @@ constexpr int kStemSmem = kStemABytes + kBStages * kStemBStage + kPatchStages * 
 struct StemParams {
   const __nv_bfloat16* in;    // padded [n, rows, pitch]
   const float* bias;          // [64]
+  const int* border;          // NULL, or the border-correction blob of pdf_op.d_scale (see include/pdfusion_b200.h)
   __nv_bfloat16* out;         // [n, P, P, 64]
   int pitch, rows, H1, P, tiles_x, tiles_y, total_tiles;
   unsigned long long* trace;  // debug: per-role clock64 stamps of CTA 0 (pdf_debug_set_trace), or NULL
@@ -140,6 +141,10 @@ stem_fused_kernel(const __grid_constant__ CUtensorMap tmap_w, const __grid_const
     // ------------------------------------------------------------------------------------------ epilogue
     const int v = warp >> 1, c = (warp & 1) * 32 + lane;
     const float bias_c = __ldg(p.bias + c);
+    // per-channel input statistics: conv pixels whose 7x7 window leaves the image need a class-dependent bias correction
+    const int nc = p.border ? p.border[0] : 0;
+    const int* cls = p.border + 2;
+    const float* delta = reinterpret_cast<const float*>(p.border + 2 + p.H1) + c;
     const uint32_t tlane = tmem_base + ((uint32_t)(warp * 32) << 16);
     int it = 0;
     TileIter ti(blockIdx.x, gridDim.x, p.tiles_x, p.tiles_y);
@@ -150,6 +155,8 @@ stem_fused_kernel(const __grid_constant__ CUtensorMap tmap_w, const __grid_const
       const int pp0 = ti.ty * kPR, pq0 = ti.tx * kPQ;
       const int cy0 = 2 * pp0 - 1, cx0 = 2 * pq0 - 1;
       const bool col_edge = cx0 < 0 || cx0 + kConvCols > p.H1;
+      bool fix = false;
+      if (nc) fix = (cls[max(cy0, 0)] | cls[min(cy0 + 4 * kPR / 2, p.H1 - 1)] | cls[max(cx0, 0)] | cls[min(cx0 + kConvCols - 1, p.H1 - 1)]) != 0;
       const size_t orow_stride = (size_t)p.P * 64;
       __nv_bfloat16* otile = p.out + (((size_t)n * p.P + pp0 + v) * p.P + pq0) * 64 + c;
       mbar_wait(bar_accfull + 8 * stage, phase);
@@ -175,6 +182,20 @@ stem_fused_kernel(const __grid_constant__ CUtensorMap tmap_w, const __grid_const
         if (pr >= p.P) continue;
         const int cy = cy0 + 4 * i + 2 * v;            // conv rows cy, cy+1, cy+2; the middle one (2*pr) is always valid
         const bool top = cy >= 0, bot = cy + 2 < p.H1;
+        if (fix) {                                     // (uniform branch: border tiles of a per-channel-normalised input only)
+          auto correct = [&](uint32_t (&r)[16], int row) {
+            if (row < 0 || row >= p.H1) return;
+            const int rc = cls[row];
+#pragma unroll
+            for (int k = 0; k < kConvCols; ++k) {
+              const int cx = cx0 + k;
+              if (cx < 0 || cx >= p.H1) continue;
+              const int cc = cls[cx];
+              if (rc | cc) r[k] = __float_as_uint(__uint_as_float(r[k]) + __ldg(delta + (rc * nc + cc) * 64));
+            }
+          };
+          correct(r0, cy); correct(r1, cy + 1); correct(r2, cy + 2);
+        }
         float m[16];
 #pragma unroll
         for (int k = 0; k < kConvCols; ++k) {
@@ -338,6 +359,7 @@ int launch_stem_fused(const pdf_op& op, const TensorMapBlob& tmap_w, const Tenso
   StemParams p;
   p.in = reinterpret_cast<const __nv_bfloat16*>(op.d_in);
   p.bias = op.d_bias;
+  p.border = reinterpret_cast<const int*>(op.d_scale);
   p.out = reinterpret_cast<__nv_bfloat16*>(op.d_out);
   if (int rc = pdf_stem_padded_dims(op.h, &p.pitch, &p.rows)) return rc;
   p.H1 = (op.h + 6 - 7) / 2 + 1;

@@ -300,7 +300,7 @@ class ResNetEncoder:
 
     def __init__(self, state_dict: Dict[str, torch.Tensor], n_images: int, input_size: int = 224,
                  precision: str = "bf16", arch: str | None = None, device=None, fused_stem: bool = True,
-                 front_chunk: int | None = None):
+                 front_chunk: int | None = None, mean=(0.5, 0.5, 0.5), std=(0.5, 0.5, 0.5)):
         _lib.require_cuda()
         self.lib = _lib.load()
         self.device = torch.device(device if device is not None else f"cuda:{torch.cuda.current_device()}")
@@ -313,6 +313,14 @@ class ResNetEncoder:
         self.bf16 = precision == "bf16"
         self.precision = precision
         self.fused_stem = bool(fused_stem)
+        # (x-mean)/std of the reference's 3-channel input.  The bf16 path feeds ONE channel u = (x-mean_avg)/std_avg
+        # (`input_mean_std`) and folds the per-channel differences into the stem weights and a border-dependent bias.
+        self.mean = [float(m) for m in mean]
+        self.std = [float(v) for v in std]
+        self.input_mean_std = (sum(self.mean) / 3.0, sum(self.std) / 3.0)
+        uniform = len(set(self.mean)) == 1 and len(set(self.std)) == 1
+        if self.bf16 and not uniform and not self.fused_stem:
+            raise ValueError("per-channel mean/std on the bf16 path needs the fused stem")
         env_chunk = os.environ.get("PDFUSION_B200_CHUNKS")          # "c1" or "c1,c2,c3,c4" (tuning hook)
         if front_chunk is None and env_chunk:
             vals = [int(v) for v in env_chunk.split(",")]
@@ -334,7 +342,37 @@ class ResNetEncoder:
         if self.bf16:
             wf = w * scale.view(-1, 1, 1, 1)
             if cv["role"] == "stem":
-                w1 = wf.sum(dim=1)                                      # [64, 7, 7]: 3 identical channels folded
+                # the three input channels are the same image: xn_c = a_c*u + b_c with u = (x-mean_avg)/std_avg
+                m_avg, s_avg = self.input_mean_std
+                a = torch.tensor([s_avg / sc_ for sc_ in self.std], dtype=torch.float64)
+                bco = torch.tensor([(m_avg - mc) / sc_ for mc, sc_ in zip(self.mean, self.std)], dtype=torch.float64)
+                w1 = (wf * a.view(1, 3, 1, 1)).sum(dim=1)               # [64, 7, 7]: channels folded
+                border = None
+                if bool((bco != 0).any()):
+                    # sum_c w[k,c,t] * b_c over the taps INSIDE the image is a bias that depends on the conv pixel's border
+                    # class; `shift` takes the interior value, the blob the differences (stem_tc.cu, pdf_op.d_scale)
+                    wb = (wf * bco.view(1, 3, 1, 1)).sum(dim=1)         # [64, 7, 7]
+                    S = self.S
+                    h1 = (S + 6 - 7) // 2 + 1
+                    masks, cls = [], []
+                    for cy in range(h1):
+                        mk = tuple(0 <= 2 * cy - 3 + r < S for r in range(7))
+                        if mk not in masks:
+                            masks.append(mk)
+                        cls.append(masks.index(mk))
+                    full = tuple([True] * 7)
+                    if masks[0] != full:                               # class 0 must be the interior class
+                        j = masks.index(full)
+                        masks[0], masks[j] = masks[j], masks[0]
+                        cls = [j if c == 0 else (0 if c == j else c) for c in cls]
+                    nc = len(masks)
+                    mt = torch.tensor(masks, dtype=torch.float64)      # [nc, 7]
+                    inside = torch.einsum("krs,ar,bs->abk", wb, mt, mt)  # [nc, nc, 64]
+                    delta = inside - inside[0, 0]
+                    shift = shift + inside[0, 0]
+                    blob = torch.cat([torch.tensor([nc, h1] + cls, dtype=torch.int32).view(torch.uint8),
+                                      delta.float().contiguous().view(-1).view(torch.uint8)])
+                    border = self._dev(blob)
                 if self.fused_stem:
                     # stem_tc.cu: row v*64+c, K index t*8+s holds w[c][t-4v][s] (variant 1 = the filter 4 patch rows lower)
                     mat = torch.zeros(2, 64, 16, 8, dtype=torch.float64)
@@ -345,7 +383,7 @@ class ResNetEncoder:
                     mat = torch.zeros(w1.shape[0], 8, 8, dtype=torch.float64)  # im2col kernel: K index = r*8 + s
                     mat[:, :7, :7] = w1
                     mat = mat.reshape(w1.shape[0], 64)
-                return self._dev(mat.to(torch.bfloat16)), None, self._dev(shift.float())
+                return self._dev(mat.to(torch.bfloat16)), border, self._dev(shift.float())
             return self._dev(wf.permute(0, 2, 3, 1).to(torch.bfloat16)), None, self._dev(shift.float())   # [K,R,S,C]
         return self._dev(w.permute(2, 3, 1, 0).float()), self._dev(scale.float()), self._dev(shift.float())  # [R,S,C,K]
 

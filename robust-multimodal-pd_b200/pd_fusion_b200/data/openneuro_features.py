@@ -180,8 +180,6 @@ def embed_manifest(df: pd.DataFrame, backbone: str, target_shape: Sequence[int],
     bsz = max(1, int(os.environ.get("PD_FUSION_B200_SUBJECT_BATCH", "8")))
     model, emb_dim, weights = _build_resnet_backbone(backbone)
     mean, std = _mean_std(weights)
-    if precision == "bf16" and (len(set(mean)) != 1 or len(set(std)) != 1):
-        precision = "fp32"     # per-channel ImageNet statistics: the one-channel stem fold does not apply
     sd = {k: v for k, v in model.state_dict().items() if not k.startswith("fc.")}
     L = int(sum(counts))
     n_rows = len(df)

@@ -34,16 +34,17 @@ class EmbeddingPipeline:
         self.device = torch.device(device if device is not None else f"cuda:{torch.cuda.current_device()}")
         self.max_subjects = int(max_subjects)
         self.precision = precision
-        if precision == "bf16" and (len(set(float(m) for m in mean)) != 1 or len(set(float(s) for s in std)) != 1):
-            raise ValueError("the bf16 path folds the three identical input channels and needs channel-uniform mean/std; "
-                             "use precision='fp32' for per-channel statistics")
         mode = _lib.OUT_BF16_C1_PAD if precision == "bf16" else _lib.OUT_F32_NHWC3   # the fused stem reads a zero-padded image
         with torch.cuda.device(self.device):
+            L = int(sum(counts))
+            self.enc = ResNetEncoder(backbone_state_dict, self.max_subjects * L, input_size, precision,
+                                     arch or detect_arch(backbone_state_dict), self.device, mean=mean, std=std)
+            if precision == "bf16":      # one channel, normalised with the channel-averaged statistics (backbone.py folds the rest)
+                m_avg, s_avg = self.enc.input_mean_std
+                mean, std = (m_avg,) * 3, (s_avg,) * 3
             self.pre = VolumePreprocessor(in_shape, target_shape, axes, counts, input_size, mean, std, mode,
                                           self.max_subjects, self.device)
             self.L = self.pre.lmax
-            self.enc = ResNetEncoder(backbone_state_dict, self.max_subjects * self.L, input_size, precision,
-                                     arch or detect_arch(backbone_state_dict), self.device)
             self.D = self.enc.emb_dim
             # preprocessing writes straight into the encoder's input buffer
             enc_in = self.enc.input_padded if self.enc.input_padded is not None else self.enc.input

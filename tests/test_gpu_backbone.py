@@ -66,6 +66,33 @@ def test_bf16_encoder_vs_reference(golden, case):
     assert rel.max() < 1e-2, rel                            # north_star: bf16 path within 1e-2 (norm-wise, per slice)
 
 
+@pytest.mark.parametrize("S,n", [(224, 4), (64, 6), (70, 3)])
+def test_bf16_encoder_with_per_channel_statistics(S, n):
+    """ImageNet mean/std (what pretrained torchvision weights bring): the tcgen05 path feeds ONE channel normalised with the
+    channel-averaged statistics; per-channel scale goes into the stem weights, the per-channel offset into a bias that
+    depends on how much of the 7x7 window is inside the image.  Checked against the oracle on the true 3-channel input."""
+    mean, std = (0.485, 0.456, 0.406), (0.229, 0.224, 0.225)
+    sd = _sd("resnet18")
+    g = torch.Generator().manual_seed(S + n)
+    x = torch.rand(n, S, S, generator=g)                                      # slices in [0, 1]
+    x[:, : S // 3] *= 0.02                                                    # dark background up to the border
+    enc = ResNetEncoder(sd, n, S, precision="bf16", mean=mean, std=std)
+    m_avg, s_avg = enc.input_mean_std
+    enc.input.copy_(((x - m_avg) / s_avg).to(torch.bfloat16))
+    out = enc.forward(None).clone()
+    torch.cuda.synchronize()
+    x3 = torch.stack([(x - m) / s_ for m, s_ in zip(mean, std)], dim=1)        # [n,3,S,S] f32, the reference's input
+    ref = O.resnet_forward(sd, "resnet18", x3).numpy()
+    emb = out.cpu().numpy()
+    rel = np.linalg.norm(emb - ref, axis=1) / np.linalg.norm(ref, axis=1)
+    assert rel.max() < 1e-2, rel
+    # the correction matters: without the border blob the same weights must be measurably worse at small sizes
+    enc32 = ResNetEncoder(sd, n, S, precision="fp32", mean=mean, std=std)
+    out32 = enc32.forward(x3.permute(0, 2, 3, 1).contiguous().cuda()).cpu().numpy()
+    rel32 = np.linalg.norm(out32 - ref, axis=1) / np.linalg.norm(ref, axis=1)
+    assert rel32.max() < 1e-5, rel32
+
+
 def test_bf16_layers_vs_fp32_layers():
     """Layer-by-layer: every bf16 tcgen05 conv (im2col TMA, strides, padding, residual epilogue) against the
     FP32 CUDA-core conv of the same layer fed with the SAME (bf16-rounded) input."""

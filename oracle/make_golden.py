@@ -275,6 +275,34 @@ def gold_tta():
     print("tta.npz", out["script/emb"].shape, seeds)
 
 
+def gold_ft():
+    """`MilAttentionFineTuneModel.predict_proba` of the reference (eval mode, no TTA) on path bags, a ready slice-array bag,
+    a None bag and a masked-out bag; resnet18 backbone from the seeded builder, head weights stored."""
+    from pd_fusion.models.mil_attention_finetune import MilAttentionFineTuneModel
+    out = {}
+    params = dict(backbone="resnet18", target_shape=(32, 32, 32), slice_axes=[0, 2], slice_counts=[3, 2], input_size=64, slice_batch_size=4,
+                  hidden_dim=32, attn_dim=16, gated=True, pretrained=True, missing_prob=0.37)
+    with tempfile.TemporaryDirectory() as td:
+        td = Path(td)
+        manifest = write_synthetic_manifest(td / "vols", 3, shape=(48, 40, 36))
+        import pandas as pd
+        paths = pd.read_csv(manifest)["t1wbrain_path"].tolist()
+        torch.manual_seed(HEAD_SEED)
+        m = MilAttentionFineTuneModel(params)          # backbone: patched builder -> manual_seed(1234); then the head is created
+        rng = np.random.default_rng(3)
+        arr_bag = rng.random((4, 32, 32)).astype(np.float32)
+        bags = [paths[0], paths[1], None, arr_bag, paths[2]]
+        masks = {"mri": np.array([1, 1, 1, 1, 0])}
+        out["prob"] = np.asarray(m.predict_proba(bags, masks=masks), dtype=np.float64)
+        out["arr_bag"] = arr_bag
+        out["params"] = np.array(json.dumps(params))
+        for k, v in _sd_np(m.attn.state_dict()).items():
+            out[f"attn/{k}"] = v
+        out["backbone_fingerprint"] = weight_fingerprint(m.backbone.state_dict())
+    np.savez_compressed(GOLD / "ft.npz", **out)
+    print("ft.npz", out["prob"])
+
+
 def _sd_np(sd):
     return {k: v.detach().cpu().numpy() for k, v in sd.items()}
 
@@ -375,7 +403,7 @@ def gold_heads():
 
 if __name__ == "__main__":
     GOLD.mkdir(parents=True, exist_ok=True)
-    which = sys.argv[1:] or ["preproc", "embed", "scripts", "heads", "tta"]
+    which = sys.argv[1:] or ["preproc", "embed", "scripts", "heads", "tta", "ft"]
     os.environ.setdefault("PYTHONHASHSEED", "0")
     for w in which:
         globals()[f"gold_{w}"]()

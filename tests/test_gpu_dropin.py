@@ -160,3 +160,33 @@ def test_model_api_and_evaluate_sweep(golden):
     y, pp = predict_proba_for_scenario(mil, dfm, {"clinical": np.zeros(6, int), "datspect": np.zeros(6, int), "mri": np.ones(6, int)},
                                        ("mil", "mri_mil"), {"name": "no_mri", "drop_modalities": ["mri"]})
     assert np.all(pp == 0.5) and len(y) == 6
+
+
+@pytest.mark.parametrize("precision,tol", [("fp32", 2e-5), ("bf16", 2e-3)])
+def test_finetune_model_predict_proba_matches_reference(golden, tmp_path, seeded_backbone, monkeypatch, precision, tol):
+    """a13, inference: volume paths / slice-array / None / masked bags through the native pipeline + one MIL launch,
+    against probabilities the reference's MilAttentionFineTuneModel produced with the same weights."""
+    from pd_fusion_b200.models.mil_attention_finetune import MilAttentionFineTuneModel
+    g = golden("ft")
+    monkeypatch.setenv("PD_FUSION_B200_PRECISION", precision)
+    params = json.loads(str(g["params"]))
+    manifest = write_synthetic_manifest(tmp_path / "vols", 3, shape=(48, 40, 36))
+    paths = pd.read_csv(manifest)["t1wbrain_path"].tolist()
+    m = MilAttentionFineTuneModel(params)
+    m.attn.load_state_dict({k[5:]: torch.from_numpy(g[k]) for k in g.files if k.startswith("attn/")})
+    m.invalidate()
+    bags = [paths[0], paths[1], None, g["arr_bag"], paths[2]]
+    prob = m.predict_proba(bags, masks={"mri": np.array([1, 1, 1, 1, 0])})
+    assert prob.shape == (5,) and prob[2] == params["missing_prob"] and prob[4] == params["missing_prob"]
+    assert np.abs(prob - g["prob"]).max() < tol, (prob, g["prob"])
+    # save / load round trip keeps the reference's checkpoint layout
+    m.save(tmp_path / "ft.pt")
+    state = torch.load(tmp_path / "ft.pt", map_location="cpu", weights_only=True)
+    assert set(state) == {"backbone", "attn"} and "layer1.0.conv1.weight" in state["backbone"]
+    m2 = MilAttentionFineTuneModel.load(tmp_path / "ft.pt", params)
+    assert np.abs(m2.predict_proba(bags[:2]) - prob[:2]).max() < 1e-6
+    # one short training run changes the head and the native path picks the new weights up
+    torch.manual_seed(0); np.random.seed(0)
+    m.params.update(epochs=1, freeze_backbone_epochs=5, batch_size=2)
+    m.train([paths[0], paths[1], g["arr_bag"]], np.array([1, 0, 1]))
+    assert np.abs(m.predict_proba(bags[:2]) - prob[:2]).max() > 1e-6

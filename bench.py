@@ -168,6 +168,7 @@ def main():
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
     ap.add_argument("--cpu-subjects", type=int, default=8, help="bounded CPU-baseline sample (subjects)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-overlap", action="store_true", help="run preprocessing and convolutions of consecutive batches on one stream")
     args = ap.parse_args()
     wl = WORKLOADS[args.workload]
     if args.impl == "reference":
@@ -201,10 +202,20 @@ def main():
     host_out = torch.empty(table.shape, dtype=torch.float32).pin_memory()
     torch.cuda.synchronize()
 
+    overlap = not args.no_overlap
+    if overlap:
+        pipe.enable_overlap()
+
     def step_device():
-        res = pipe.embed(raw)
-        table.copy_(res.embeddings if args.workload == "c3" else res.mean)
-        return all_gather_rows(table, B * ws) if ws > 1 else table
+        if not overlap:
+            res = pipe.embed(raw)
+            table.copy_(res.embeddings if args.workload == "c3" else res.mean)
+            return all_gather_rows(table, B * ws) if ws > 1 else table
+        # preprocessing of this batch overlaps the convolutions of the previous one (two streams, two encoder instances)
+        res = pipe.embed_overlapped(raw)
+        with torch.cuda.stream(pipe.conv_stream):
+            table.copy_(res.embeddings if args.workload == "c3" else res.mean)
+            return all_gather_rows(table, B * ws) if ws > 1 else table
 
     host_batches = [pinned] * args.steps
 
@@ -219,8 +230,12 @@ def main():
         barrier(); torch.cuda.synchronize()
         e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
         e0.record()
+        if overlap:
+            pipe.overlap_begin()
         for _ in range(steps):
             fn()
+        if overlap:
+            pipe.overlap_end()
         e1.record()
         torch.cuda.synchronize(); barrier()
         ms = torch.tensor([e0.elapsed_time(e1)], device=dev)
@@ -270,7 +285,8 @@ def main():
         "config": {"workload": wl["name"], "backbone": wl["arch"], "slices": L, "subjects_per_step_per_gpu": B,
                    "volume": list(IN_SHAPE), "target": list(TARGET), "input_size": INPUT_SIZE, "volume_pool": args.pool,
                    "l2": "inputs larger than L2 (%.1f GB of volumes per step)" % (B * 4 * np.prod(IN_SHAPE) / 1e9),
-                   "parallelism": f"subjects sharded x{ws}, all-gather of the embedding table" if ws > 1 else "1 GPU"},
+                   "parallelism": f"subjects sharded x{ws}, all-gather of the embedding table" if ws > 1 else "1 GPU",
+                   "streams": "preprocessing of batch i+1 overlaps the conv stack of batch i (2 streams)" if overlap else "one stream"},
         "clocks": clk.summary(),
         "e2e": {"value": e2e, "unit": UNIT, "h2d_bytes_per_step": int(pinned.numel() * 4), "d2h_bytes_per_step": int(host_out.numel() * 4), "overlap": "H2D of batch i+1 on a copy stream overlaps the kernels of batch i", "timer": "host wall clock around K steps, device synchronised on both sides",
                 "ms_per_step": ms_e2e / args.steps},

@@ -34,6 +34,8 @@ class EmbeddingPipeline:
         self.device = torch.device(device if device is not None else f"cuda:{torch.cuda.current_device()}")
         self.max_subjects = int(max_subjects)
         self.precision = precision
+        self._ctor = dict(sd=backbone_state_dict, input_size=input_size, arch=arch or detect_arch(backbone_state_dict), mean=mean, std=std)
+        self._ov = None
         mode = _lib.OUT_BF16_C1_PAD if precision == "bf16" else _lib.OUT_F32_NHWC3   # the fused stem reads a zero-padded image
         with torch.cuda.device(self.device):
             L = int(sum(counts))
@@ -65,6 +67,75 @@ class EmbeddingPipeline:
         _lib.check(self.lib.pdf_slice_mean(B, self.L, self.D, emb.data_ptr(), self.nvalid.data_ptr(), self.mean_out.data_ptr(),
                                            _lib.stream_ptr()), "pdf_slice_mean")
         return EmbedResult(emb[:B], self.mean_out[:B], res.indices, res.nslices)
+
+    # ---- cross-batch overlap: preprocessing of batch i+1 (CUDA cores, HBM streaming) runs on its own stream next to the
+    #      tensor-core conv stack of batch i.  Two encoder instances alternate so that a batch's network input is never
+    #      overwritten while its convolutions still read it.
+    def enable_overlap(self):
+        if self._ov is not None:
+            return
+        c = self._ctor
+        with torch.cuda.device(self.device):
+            enc2 = ResNetEncoder(c["sd"], self.max_subjects * self.L, c["input_size"], self.precision, c["arch"], self.device,
+                                 mean=c["mean"], std=c["std"])
+            encs = [self.enc, enc2]
+            ins = [(e.input_padded if e.input_padded is not None else e.input).view(self.pre.net_input.shape) for e in encs]
+            B, L = self.max_subjects, self.L
+            self._ov = dict(
+                encs=encs, ins=ins, turn=0,
+                pre_stream=torch.cuda.Stream(self.device), conv_stream=torch.cuda.Stream(self.device),
+                pre_done=[torch.cuda.Event() for _ in range(2)], slot_free=[torch.cuda.Event() for _ in range(2)],
+                mean=[torch.empty((B, self.D), dtype=torch.float32, device=self.device) for _ in range(2)],
+                nvalid=[torch.empty((B,), dtype=torch.int32, device=self.device) for _ in range(2)],
+                indices=[torch.empty((B, L), dtype=torch.int32, device=self.device) for _ in range(2)],
+                nslices=[torch.empty((B, len(self.pre.axes)), dtype=torch.int32, device=self.device) for _ in range(2)])
+            cur = torch.cuda.current_stream(self.device)
+            for ev in self._ov["slot_free"]:
+                ev.record(cur)
+
+    @property
+    def conv_stream(self):
+        return self._ov["conv_stream"]
+
+    def overlap_begin(self):
+        """The two worker streams start after everything already enqueued on the current stream."""
+        cur = torch.cuda.current_stream(self.device)
+        self._ov["pre_stream"].wait_stream(cur)
+        self._ov["conv_stream"].wait_stream(cur)
+
+    def overlap_end(self):
+        """The current stream continues after everything the worker streams were given."""
+        cur = torch.cuda.current_stream(self.device)
+        cur.wait_stream(self._ov["pre_stream"])
+        cur.wait_stream(self._ov["conv_stream"])
+
+    def embed_overlapped(self, raw: torch.Tensor) -> EmbedResult:
+        """Like embed(), but preprocessing is enqueued on the preprocessing stream and the encoder on the convolution
+        stream: consecutive calls overlap.  The returned tensors are produced on `conv_stream` and stay valid until the
+        call after next (two result slots); bracket a sequence of calls with overlap_begin() / overlap_end()."""
+        self.enable_overlap()
+        ov = self._ov
+        s = ov["turn"] & 1
+        ov["turn"] += 1
+        B = int(raw.shape[0])
+        enc = ov["encs"][s]
+        P, Cs = ov["pre_stream"], ov["conv_stream"]
+        with torch.cuda.stream(P):
+            P.wait_event(ov["slot_free"][s])                  # the convolutions of the batch before last have consumed this input
+            if B < self.max_subjects:
+                enc.input[B * self.L:].zero_()
+            res = self.pre.run(raw, net_input=ov["ins"][s])
+            ov["indices"][s][:B].copy_(res.indices)
+            ov["nslices"][s][:B].copy_(res.nslices)
+            ov["nvalid"][s][:B].copy_(res.nslices.sum(dim=1))
+            ov["pre_done"][s].record(P)
+        with torch.cuda.stream(Cs):
+            Cs.wait_event(ov["pre_done"][s])
+            emb = enc.forward(None).view(self.max_subjects, self.L, self.D)
+            _lib.check(self.lib.pdf_slice_mean(B, self.L, self.D, emb.data_ptr(), ov["nvalid"][s].data_ptr(), ov["mean"][s].data_ptr(),
+                                               _lib.stream_ptr()), "pdf_slice_mean")
+            ov["slot_free"][s].record(Cs)
+        return EmbedResult(emb[:B], ov["mean"][s][:B], ov["indices"][s][:B], ov["nslices"][s][:B])
 
     def embed_tta(self, raw: torch.Tensor, seeds, n_pass: int, tta_cfg: Dict) -> EmbedResult:
         """`tta > 1` path of the builders (data/openneuro_features.py:235-265): every pass re-augments the selected slices

@@ -77,3 +77,30 @@ def test_builders_with_tta_match_reference_script(golden, tmp_path, monkeypatch,
     assert emb.shape == want.shape and rel.max() < tol, rel
     rel_avg = np.linalg.norm(avg - want.mean(axis=1), axis=1) / np.linalg.norm(want.mean(axis=1), axis=1)
     assert rel_avg.max() < tol
+
+
+def test_overlapped_pipeline_equals_serial():
+    """Two-stream execution (preprocessing of batch i+1 next to the convolutions of batch i, alternating encoder instances)
+    returns exactly what the single-stream path returns, batch after batch."""
+    from pd_fusion_b200.pipeline import EmbeddingPipeline
+    torch.manual_seed(1234)
+    sd = {k: v for k, v in ResNet2D("resnet18").state_dict().items() if not k.startswith("fc.")}
+    shape, target = (48, 40, 36), (32, 32, 32)
+    pipe = EmbeddingPipeline(sd, shape, target, [0, 2], [3, 2], 64, precision="bf16", max_subjects=3)
+    batches = [torch.from_numpy(np.stack([synthetic_volume(10 * k + b, shape) for b in range(3 if k != 2 else 2)])).cuda() for k in range(5)]
+    want = []
+    for raw in batches:
+        r = pipe.embed(raw)
+        torch.cuda.synchronize()
+        want.append((r.embeddings.clone(), r.mean.clone(), r.indices.clone()))
+    pipe.overlap_begin() if pipe._ov else pipe.enable_overlap()
+    pipe.overlap_begin()
+    got = []
+    for raw in batches:
+        r = pipe.embed_overlapped(raw)
+        with torch.cuda.stream(pipe.conv_stream):
+            got.append((r.embeddings.clone(), r.mean.clone(), r.indices.clone()))
+    pipe.overlap_end()
+    torch.cuda.synchronize()
+    for (e0, m0, i0), (e1, m1, i1) in zip(want, got):
+        assert torch.equal(e0, e1) and torch.equal(m0, m1) and torch.equal(i0, i1)

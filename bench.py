@@ -41,7 +41,7 @@ WORKLOADS = {
     "c3": dict(arch="resnet50", axes=[2], counts=[48], batch_size=16, name="configs/openneuro_ds001907_resnet2d_mil.yaml"),
 }
 IN_SHAPE, TARGET, INPUT_SIZE = (256, 256, 176), (160, 160, 160), 224
-METRIC, UNIT = "mri_subjects_per_sec_resnet2d_embed", "subjects/s"
+METRIC, UNIT = "mri_subjects_per_sec_resnet2d_embed_fuse", "subjects/s"
 
 
 def measured_peaks():
@@ -128,9 +128,25 @@ def cpu_reference_rate(wl, n_subjects: int, pool):
     torch.set_num_threads(cores)
     torch.manual_seed(1234)
     sd = {k: v for k, v in ResNet2D(wl["arch"]).state_dict().items() if not k.startswith("fc.")}
+    # the fuse half: the config's head under the 7 scenario masks, per subject as evaluate_model would (tiny next to the backbone)
+    torch.manual_seed(4321)
+    D = 2048 if wl["arch"] == "resnet50" else 512
+    if wl["arch"] == "resnet18":
+        from pd_fusion_b200.models.fusion_moddrop import ModalityDropoutNet
+        dims = {"clinical": 0, "datspect": 0, "mri": D}
+        hsd = {k: v.numpy() for k, v in ModalityDropoutNet(dims, [256, 128, 64], 0.3).state_dict().items()}
+    else:
+        from pd_fusion_b200.models.mil_attention import MILAttentionNet
+        hsd = {k: v.numpy() for k, v in MILAttentionNet(D, 256, 128, 0.2, gated=True).state_dict().items()}
+    mri_masks = [1, 1, 0, 1, 0, 0, 1]                       # one subject's mri availability under the 7 scenarios (fixed draw)
     t0 = time.perf_counter()
     for i in range(n_subjects):
-        O.embed_subject(pool[i % len(pool)], sd, wl["arch"], TARGET, wl["axes"], wl["counts"], INPUT_SIZE, wl["batch_size"])
+        _, emb = O.embed_subject(pool[i % len(pool)], sd, wl["arch"], TARGET, wl["axes"], wl["counts"], INPUT_SIZE, wl["batch_size"])
+        for m in mri_masks:
+            if wl["arch"] == "resnet18":
+                O.moddrop_predict_proba(hsd, dims, emb.mean(axis=0, keepdims=True), {"clinical": np.zeros(1), "datspect": np.zeros(1), "mri": np.array([m])})
+            else:
+                O.mil_predict_proba(hsd, [emb], True, {"mri": np.array([m])})
     dt = time.perf_counter() - t0
     return n_subjects / dt, cores, dt
 
@@ -206,16 +222,59 @@ def main():
     if overlap:
         pipe.enable_overlap()
 
+    # --- the "fuse" half of the metric: the config's head evaluated under EVERY scenario mask of
+    #     configs/eval_missingness_openneuro_ds001907.yaml in one masked-forward launch over the batch's embeddings
+    #     (evaluation/evaluate.py:18-97 loops scenarios and subjects).  Masks are drawn on the host by the reference's
+    #     rule (global numpy RNG), once; weights are random-init (seed 4321).
+    import pandas as pd
+    from pd_fusion_b200.data.missingness import scenario_mask_tensor
+    from pd_fusion_b200.heads import MilHead, ModDropSweep
+    scenarios = [{"name": "full_observation", "drop_modalities": []},
+                 {"name": "mri_missing_25", "drop_modalities": ["mri"], "drop_rate": 0.25},
+                 {"name": "mri_missing_50", "drop_modalities": ["mri"], "drop_rate": 0.50},
+                 {"name": "mri_missing_75", "drop_modalities": ["mri"], "drop_rate": 0.75},
+                 {"name": "mri_missing_100", "drop_modalities": ["mri"]},
+                 {"name": "random_1_drop", "n_drop": 1, "type": "random"},
+                 {"name": "random_2_drop", "n_drop": 2, "type": "random"}]
+    mods = ["clinical", "datspect", "mri"]
+    base = {"clinical": np.zeros(B, dtype=int), "datspect": np.zeros(B, dtype=int), "mri": np.ones(B, dtype=int)}   # openneuro_ds001907.py:77-81
+    np.random.seed(11 + rank)
+    mask_np, _ = scenario_mask_tensor(pd.DataFrame({"subject_id": np.arange(B)}), scenarios, base, mods)
+    masks = torch.from_numpy(mask_np).to(dev)                                  # u8 [S, B, 3]
+    S_scen = len(scenarios)
+    torch.manual_seed(4321)
+    if args.workload == "c2":
+        from pd_fusion_b200.models.fusion_moddrop import ModalityDropoutNet
+        dims = {"clinical": 0, "datspect": 0, "mri": D}
+        head = ModDropSweep(ModalityDropoutNet(dims, [256, 128, 64], 0.3).state_dict(), dims, device=dev)
+    else:
+        from pd_fusion_b200.models.mil_attention import MILAttentionNet
+        head = MilHead(MILAttentionNet(D, 256, 128, 0.2, gated=True).state_dict(), True, 0.5, device=dev)
+        mri_col = masks[:, :, 2].contiguous()
+    probs = torch.empty((B, S_scen), dtype=torch.float32, device=dev)
+
+    def fuse(res):
+        """probabilities [B, S] of the batch under every scenario"""
+        if args.workload == "c2":
+            probs.copy_(head.forward(res.mean, masks).t())
+        else:                                   # MIL: a masked-out bag has length 0 (-> missing_prob); one launch per scenario set
+            lens = (mri_col * L).to(torch.int32)                     # [S, B]
+            bags = res.embeddings.unsqueeze(0).expand(S_scen, B, L, D).reshape(S_scen * B, L, D).contiguous()
+            probs.copy_(head.forward(bags, lens.reshape(-1)).view(S_scen, B).t())
+        return probs
+
     def step_device():
         if not overlap:
             res = pipe.embed(raw)
             table.copy_(res.embeddings if args.workload == "c3" else res.mean)
-            return all_gather_rows(table, B * ws) if ws > 1 else table
+            pr = fuse(res)
+            return (all_gather_rows(table, B * ws), all_gather_rows(pr, B * ws)) if ws > 1 else (table, pr)
         # preprocessing of this batch overlaps the convolutions of the previous one (two streams, two encoder instances)
         res = pipe.embed_overlapped(raw)
         with torch.cuda.stream(pipe.conv_stream):
             table.copy_(res.embeddings if args.workload == "c3" else res.mean)
-            return all_gather_rows(table, B * ws) if ws > 1 else table
+            pr = fuse(res)
+            return (all_gather_rows(table, B * ws), all_gather_rows(pr, B * ws)) if ws > 1 else (table, pr)
 
     host_batches = [pinned] * args.steps
 
@@ -286,6 +345,8 @@ def main():
                    "volume": list(IN_SHAPE), "target": list(TARGET), "input_size": INPUT_SIZE, "volume_pool": args.pool,
                    "l2": "inputs larger than L2 (%.1f GB of volumes per step)" % (B * 4 * np.prod(IN_SHAPE) / 1e9),
                    "parallelism": f"subjects sharded x{ws}, all-gather of the embedding table" if ws > 1 else "1 GPU",
+                   "fuse": ("Fusion-ModDrop 512-256-128-64-1" if args.workload == "c2" else "gated MIL attention 2048-256-128") +
+                           f" under {S_scen} missingness scenarios, one launch",
                    "streams": "preprocessing of batch i+1 overlaps the conv stack of batch i (2 streams)" if overlap else "one stream"},
         "clocks": clk.summary(),
         "e2e": {"value": e2e, "unit": UNIT, "h2d_bytes_per_step": int(pinned.numel() * 4), "d2h_bytes_per_step": int(host_out.numel() * 4), "overlap": "H2D of batch i+1 on a copy stream overlaps the kernels of batch i", "timer": "host wall clock around K steps, device synchronised on both sides",

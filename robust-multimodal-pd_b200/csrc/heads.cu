@@ -153,7 +153,30 @@ mil_pool_kernel(const float* __restrict__ hbuf, const int32_t* __restrict__ lens
 // one dense layer evaluated by a warp: out[o] = act(sum_i W[o,i] in[i] + b[o]); in/out in shared memory
 __device__ __forceinline__ void warp_dense(const float* __restrict__ W, const float* __restrict__ b, int n_in, int n_out,
                                            const float* in, float* out, int relu, int lane) {
-  for (int o = 0; o < n_out; ++o) {
+  int o = 0;
+  for (; o + 4 <= n_out; o += 4) {          // four independent dot products in flight (same summation order per output)
+    const float* wr = W + (size_t)o * n_in;
+    float a0 = 0.f, a1 = 0.f, a2 = 0.f, a3 = 0.f;
+    for (int i = lane; i < n_in; i += 32) {
+      const float x = in[i];
+      a0 = fmaf(__ldg(wr + i), x, a0);
+      a1 = fmaf(__ldg(wr + n_in + i), x, a1);
+      a2 = fmaf(__ldg(wr + 2 * n_in + i), x, a2);
+      a3 = fmaf(__ldg(wr + 3 * n_in + i), x, a3);
+    }
+#pragma unroll
+    for (int s = 16; s; s >>= 1) {
+      a0 += __shfl_xor_sync(0xffffffffu, a0, s);
+      a1 += __shfl_xor_sync(0xffffffffu, a1, s);
+      a2 += __shfl_xor_sync(0xffffffffu, a2, s);
+      a3 += __shfl_xor_sync(0xffffffffu, a3, s);
+    }
+    if (lane < 4) {
+      const float v = (lane == 0 ? a0 : lane == 1 ? a1 : lane == 2 ? a2 : a3) + __ldg(b + o + lane);
+      out[o + lane] = relu ? fmaxf(v, 0.f) : v;
+    }
+  }
+  for (; o < n_out; ++o) {
     const float* wr = W + (size_t)o * n_in;
     float acc = 0.f;
     for (int i = lane; i < n_in; i += 32) acc = fmaf(__ldg(wr + i), in[i], acc);
@@ -177,8 +200,10 @@ moddrop_sweep_kernel(pdf_mlp net, const float* __restrict__ partials, const uint
   float* bufA = sm + (size_t)warp * 2 * maxw;
   float* bufB = bufA + maxw;
   const int M = net.n_mods;
-  for (int n = blockIdx.x * 8 + warp; n < N; n += gridDim.x * 8) {
-    for (int s = 0; s < S; ++s) {
+  // one warp per (scenario, subject) pair: a 32-subject batch under 7 scenarios still fills 28 blocks
+  for (long long pair = (long long)blockIdx.x * 8 + warp; pair < (long long)N * S; pair += (long long)gridDim.x * 8) {
+    {
+      const int s = (int)(pair / N), n = (int)(pair - (long long)s * N);
       const uint8_t* mk = masks + ((size_t)s * N + n) * M;
       const bool last0 = net.n_layers == 1;
       for (int i = lane; i < h1; i += 32) {
@@ -323,7 +348,7 @@ extern "C" int pdf_moddrop_sweep(const pdf_mlp* net, int n_subjects, int n_scena
   for (int l = 2; l <= net->n_layers; ++l) maxw = max(maxw, net->dims[l]);
   const size_t smem = (size_t)8 * 2 * maxw * sizeof(float);
   if (smem > 48 * 1024) PDF_CHECK_CUDA(cudaFuncSetAttribute(moddrop_sweep_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-  const int blocks = max(1, min(ceil_div(n_subjects, 8), num_sms() * 8));
+  const int blocks = max(1, min(ceil_div((long long)n_subjects * n_scenarios, 8), num_sms() * 8));
   moddrop_sweep_kernel<<<blocks, 256, smem, s>>>(*net, partials, d_masks, n_subjects, n_scenarios, d_prob);
   PDF_CHECK_LAUNCH();
   return PDF_OK;

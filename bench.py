@@ -280,9 +280,10 @@ def main():
 
     def run_e2e():
         # public host API: pinned host volumes -> (H2D overlapped with the previous batch's kernels) -> hot path -> D2H
-        outs = pipe.embed_host(host_batches, out_bags=(args.workload == "c3"))
+        outs = pipe.embed_host(host_batches, out_bags=(args.workload == "c3"), post=fuse)
         if ws > 1:
-            all_gather_rows(outs[-1].to(dev), B * ws)
+            all_gather_rows(outs[-1][0].to(dev), B * ws)
+            all_gather_rows(outs[-1][1].to(dev), B * ws)
         return outs
 
     def timed(fn, steps):
@@ -349,7 +350,7 @@ def main():
                            f" under {S_scen} missingness scenarios, one launch",
                    "streams": "preprocessing of batch i+1 overlaps the conv stack of batch i (2 streams)" if overlap else "one stream"},
         "clocks": clk.summary(),
-        "e2e": {"value": e2e, "unit": UNIT, "h2d_bytes_per_step": int(pinned.numel() * 4), "d2h_bytes_per_step": int(host_out.numel() * 4), "overlap": "H2D of batch i+1 on a copy stream overlaps the kernels of batch i", "timer": "host wall clock around K steps, device synchronised on both sides",
+        "e2e": {"value": e2e, "unit": UNIT, "h2d_bytes_per_step": int(pinned.numel() * 4), "d2h_bytes_per_step": int(host_out.numel() * 4 + B * S_scen * 4), "overlap": "H2D of batch i+1 on a copy stream overlaps the kernels of batch i", "timer": "host wall clock around K steps, device synchronised on both sides",
                 "ms_per_step": ms_e2e / args.steps},
         "gpu_launches": int(launches),
         "roofline": {"bound": "tensor", "kernel": "conv_tc_kernel (tcgen05 implicit-GEMM conv stack, all launches of one step)",

@@ -179,10 +179,12 @@ class EmbeddingPipeline:
             mean_sum += self.mean_out[:B]
         return EmbedResult(emb_sum / float(n_pass), mean_sum / float(n_pass), indices, nslices)
 
-    def embed_host(self, host_batches, out_bags: bool = False):
+    def embed_host(self, host_batches, out_bags: bool = False, post=None):
         """End-to-end path for volumes that live in (pinned) HOST memory: iterates over `host_batches` (tensors
         [B, X, Y, Z] f32), overlapping the H2D copy of batch i+1 (copy stream, second device buffer) with the kernels
-        of batch i, and returns a list of host tensors (slice-mean embeddings [B, D], or the bags [B, L, D])."""
+        of batch i, and returns a list of host tensors (slice-mean embeddings [B, D], or the bags [B, L, D]).
+        `post(EmbedResult) -> device tensor` (e.g. the fusion head under the scenario masks) runs on each batch before the
+        read-back; its result is read back too and the list then holds (embeddings, post result) pairs."""
         main = torch.cuda.current_stream(self.device)
         if not hasattr(self, "_copy_stream"):
             self._copy_stream = torch.cuda.Stream(self.device)
@@ -214,7 +216,13 @@ class EmbeddingPipeline:
             src = res.embeddings if out_bags else res.mean
             host = torch.empty(src.shape, dtype=torch.float32).pin_memory()
             host.copy_(src, non_blocking=True)
-            outs.append(host)
+            if post is not None:
+                extra = post(res)
+                hx = torch.empty(extra.shape, dtype=extra.dtype).pin_memory()
+                hx.copy_(extra, non_blocking=True)
+                outs.append((host, hx))
+            else:
+                outs.append(host)
         main.synchronize()
         return outs
 

@@ -219,6 +219,7 @@ def main():
     torch.cuda.synchronize()
 
     overlap = not args.no_overlap
+    fuse_stream = torch.cuda.Stream(dev)
     if overlap:
         pipe.enable_overlap()
 
@@ -270,11 +271,15 @@ def main():
             pr = fuse(res)
             return (all_gather_rows(table, B * ws), all_gather_rows(pr, B * ws)) if ws > 1 else (table, pr)
         # preprocessing of this batch overlaps the convolutions of the previous one (two streams, two encoder instances)
+        # the fusion head (a few small latency-bound launches) and the gathers run on a third stream next to the next batch
         res = pipe.embed_overlapped(raw)
-        with torch.cuda.stream(pipe.conv_stream):
+        fuse_stream.wait_stream(pipe.conv_stream)
+        with torch.cuda.stream(fuse_stream):
             table.copy_(res.embeddings if args.workload == "c3" else res.mean)
             pr = fuse(res)
-            return (all_gather_rows(table, B * ws), all_gather_rows(pr, B * ws)) if ws > 1 else (table, pr)
+            out = (all_gather_rows(table, B * ws), all_gather_rows(pr, B * ws)) if ws > 1 else (table, pr)
+        pipe.hold_slot(fuse_stream)          # this batch's result slot may be reused only after the head has read it
+        return out
 
     host_batches = [pinned] * args.steps
 
@@ -292,10 +297,12 @@ def main():
         e0.record()
         if overlap:
             pipe.overlap_begin()
+            fuse_stream.wait_stream(torch.cuda.current_stream())
         for _ in range(steps):
             fn()
         if overlap:
             pipe.overlap_end()
+            torch.cuda.current_stream().wait_stream(fuse_stream)
         e1.record()
         torch.cuda.synchronize(); barrier()
         ms = torch.tensor([e0.elapsed_time(e1)], device=dev)

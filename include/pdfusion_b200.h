@@ -259,6 +259,11 @@ int pdf_selftest_umma_shift(int N, int shift, int mode, const void* d_a_bf16, co
  * d_cycles[grid] receives the SM-clock cycles each CTA took (profiles/r01_umma_rate.txt). */
 int pdf_selftest_umma_rate(int N, int iters, int mode, int grid, unsigned long long* d_cycles, pdf_stream_t stream);
 
+/* Tuning / test hook: enable != 0 routes Cout >= 128 layers with enough tiles through the CTA-pair kernel
+ * (tcgen05.mma.cta_group::2, csrc/conv_tc2.cu).  Off by default: measured equal (N=256) or slower (N=128) than the single-CTA
+ * kernel on the ResNet shapes. */
+int pdf_debug_enable_pair(int enable);
+
 /* Debug hook: CTA 0 of the following PDF_OP_STEM_FUSED launches records clock64 stamps of its warp roles,
  * [64 tiles][16 events] u64, into d_buf (NULL switches it off). */
 int pdf_debug_set_trace(unsigned long long* d_buf);

@@ -415,6 +415,9 @@ int prepare_conv_tc(const pdf_op& op, TcConv* tc) {
   } else {
     if (int rc = encode_2d(&tc->tmap_a, op.d_in, (uint64_t)tc->M_total, (uint64_t)op.c, kBlockM)) return rc;
   }
+  if (tc->block_n >= 128) {   // one CTA's half of the weight tile, for the cta_group::2 pair kernel
+    if (int rc = encode_2d(&tc->tmap_b2, op.d_weight, (uint64_t)op.k, (uint64_t)op.r * op.s * op.c, (uint32_t)tc->block_n / 2)) return rc;
+  }
   return encode_2d(&tc->tmap_b, op.d_weight, (uint64_t)op.k, (uint64_t)op.r * op.s * op.c, (uint32_t)tc->block_n);
 }
 
@@ -460,6 +463,7 @@ static int launch_tc(const TcConv& tc, cudaStream_t s) {
 
 int launch_conv_tc(const TcConv& tc, cudaStream_t s) {
   if (tc.halo) return launch_conv3x3_halo(tc, s);
+  if (pair_eligible(tc)) return launch_conv_tc2(tc, s);      // cta_group::2: two SMs per 256-row tile (conv_tc2.cu)
   // two 128-row sub-tiles per CTA when the mainloop is long enough to amortise the single-tile prologue/epilogue and
   // there are still >= 1.5 waves of CTAs
   // N=128 tiles pair two 128-row sub-tiles per B tile when there is enough work for every SM

@@ -15,6 +15,7 @@ struct alignas(64) TensorMapBlob { unsigned char bytes[128]; };
 
 struct TcConv {
   TensorMapBlob tmap_a, tmap_b;
+  TensorMapBlob tmap_b2;   // weight map with a [BLOCK_N/2 x 64] box (one CTA's half of B in the CTA-pair kernel)
   int block_n;      // 64 | 128 | 256
   int im2col;       // 1: A through im2col-mode TMA, 0: plain 2D tile of the [M, C] matrix (1x1 stride-1)
   int M_total, Cout, Ho, Wo, stride, pad, R, S, cchunks, relu;
@@ -30,6 +31,8 @@ int prepare_conv_tc(const pdf_op& op, TcConv* out);
 int prepare_stem_tc(const pdf_op& op, TcConv* out);   // weight map -> out->tmap_b, padded-image patch map -> out->tmap_a
 int launch_stem_fused(const pdf_op& op, const TensorMapBlob& tmap_w, const TensorMapBlob& tmap_in, cudaStream_t s);
 int launch_conv_tc(const TcConv& tc, cudaStream_t s);
+bool pair_eligible(const TcConv& tc);
+int launch_conv_tc2(const TcConv& tc, cudaStream_t s);   // cta_group::2 pair kernel (conv_tc2.cu)
 bool halo_eligible(const pdf_op& op);
 int launch_conv3x3_halo(const TcConv& tc, cudaStream_t s);
 

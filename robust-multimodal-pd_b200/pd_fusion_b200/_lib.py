@@ -117,6 +117,7 @@ PROTOTYPES = {
     "pdf_selftest_umma_shift": (C.c_int, [C.c_int, C.c_int, C.c_int, _P, _P, _P, _P]),
     "pdf_selftest_umma_rate": (C.c_int, [C.c_int, C.c_int, C.c_int, C.c_int, _P, _P]),
     "pdf_debug_set_trace": (C.c_int, [_P]),
+    "pdf_debug_enable_pair": (C.c_int, [C.c_int]),
     "pdf_debug_disable_halo": (C.c_int, [C.c_int]),
 }
 
@@ -141,6 +142,8 @@ def load():
         fn = getattr(lib, name)
         fn.restype = res
         fn.argtypes = args
+    if os.environ.get("PDFUSION_B200_PAIR"):             # tuning hook: CTA-pair (cta_group::2) kernel for Cout >= 128 layers
+        lib.pdf_debug_enable_pair(1)
     _lib = lib
     return lib
 

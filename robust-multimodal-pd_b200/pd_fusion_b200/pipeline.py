@@ -109,6 +109,13 @@ class EmbeddingPipeline:
         cur.wait_stream(self._ov["pre_stream"])
         cur.wait_stream(self._ov["conv_stream"])
 
+    def hold_slot(self, stream) -> None:
+        """Consumers that read the latest embed_overlapped() result on ANOTHER stream call this after enqueueing their reads:
+        the result slot (encoder output, slice means, indices) is then not reused before `stream` got there."""
+        ov = self._ov
+        s = (ov["turn"] - 1) & 1
+        ov["slot_free"][s].record(stream)
+
     def embed_overlapped(self, raw: torch.Tensor) -> EmbedResult:
         """Like embed(), but preprocessing is enqueued on the preprocessing stream and the encoder on the convolution
         stream: consecutive calls overlap.  The returned tensors are produced on `conv_stream` and stay valid until the

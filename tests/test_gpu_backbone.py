@@ -18,16 +18,20 @@ def _sd(arch):
     return {k: v for k, v in ResNet2D(arch).state_dict().items() if not k.startswith("fc.")}
 
 
-@pytest.mark.parametrize("M,N,K", [(128, 64, 64), (300, 128, 192), (1000, 256, 576), (77, 512, 128)])
+@pytest.mark.parametrize("M,N,K", [(128, 64, 64), (300, 128, 192), (1000, 256, 576), (77, 512, 128),
+                                   (20480, 256, 192), (19001, 128, 576), (9600, 512, 128), (40000, 256, 64)])   # last four: CTA-pair kernel
 def test_umma_selftest(M, N, K):
-    """TMA (2D, 128B swizzle) -> tcgen05.mma (TMEM accumulator) -> tcgen05.ld against an f32 matmul of the same bf16 data."""
+    """TMA (2D, 128B swizzle) -> tcgen05.mma (TMEM accumulator) -> tcgen05.ld against an f32 matmul of the same bf16 data.
+    The large cases also run through the CTA-pair kernel (tcgen05.mma.cta_group::2, multicast commit, remote arrives)."""
     lib = _lib.load()
+    lib.pdf_debug_enable_pair(1 if M >= 9600 else 0)
     g = torch.Generator(device="cpu").manual_seed(M * 7 + N)
     a = torch.randn(M, K, generator=g).to(torch.bfloat16).cuda()
     b = torch.randn(N, K, generator=g).to(torch.bfloat16).cuda()
     c = torch.full((M, N), float("nan"), dtype=torch.float32, device="cuda")
     _lib.check(lib.pdf_selftest_umma(M, N, K, a.data_ptr(), b.data_ptr(), c.data_ptr(), _lib.stream_ptr()))
     torch.cuda.synchronize()
+    lib.pdf_debug_enable_pair(0)
     ref = a.float().cpu().double() @ b.float().cpu().double().T
     err = (c.cpu().double() - ref).abs().max().item()
     assert err < 1e-3 * max(1.0, ref.abs().max().item()), err

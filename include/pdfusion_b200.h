@@ -142,7 +142,8 @@ int pdf_normalize_volume(int batch, size_t voxels, const float* d_zoomed, const 
 #define PDF_OP_STEM_IM2COL 3 /* [N,H,W] bf16 one-channel image -> [N*Ho*Wo, kpad] bf16 patch matrix (7x7 s2 p3) */
 #define PDF_OP_STEM_FUSED 4  /* zero-padded [N,rows,pitch] bf16 image (PDF_OUT_BF16_C1_PAD; h = w = S) -> conv 7x7 s2 p3 (64 ch) + bias
                                 + ReLU + maxpool 3x3 s2 p1 -> [N,ho,wo,64] bf16, one kernel.  d_weight: [128][128] bf16, row v*64+c,
-                                column t*8+s = w[c][t-4v][s] (BN folded, 3 input channels summed), zero elsewhere.
+                                column t*8+s = w[c][t-4v][s] (BN folded, 3 input channels summed), columns 88 and 89 = the bias of channel c split
+                                into two bf16 terms (they multiply a constant 1; d_bias is not read), zero elsewhere.
                                 d_scale: NULL, or a border-correction blob for inputs whose (x-mean)/std is PER CHANNEL (the one
                                 channel fed to the kernel is then (x-mean_avg)/std_avg and the per-channel offsets become a bias that
                                 depends on how much of the 7x7 window lies inside the image):
@@ -263,6 +264,10 @@ int pdf_selftest_umma_rate(int N, int iters, int mode, int grid, unsigned long l
  * (tcgen05.mma.cta_group::2, csrc/conv_tc2.cu).  Off by default: measured equal (N=256) or slower (N=128) than the single-CTA
  * kernel on the ResNet shapes. */
 int pdf_debug_enable_pair(int enable);
+
+/* Tuning hook: pdf_preprocess works through the batch in sub-batches of `subjects` volumes (0 = the whole batch at once) so that
+ * one sub-batch's resampled volumes stay L2-resident across the histogram passes and the plane gather.  Results are identical. */
+int pdf_debug_set_pre_chunk(int subjects);
 
 /* Debug hook: CTA 0 of the following PDF_OP_STEM_FUSED launches records clock64 stamps of its warp roles,
  * [64 tiles][16 events] u64, into d_buf (NULL switches it off). */

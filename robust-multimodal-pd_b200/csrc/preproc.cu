@@ -903,6 +903,8 @@ __global__ void tta_kernel(const float* __restrict__ slices, const pdf_tta_param
 
 using namespace pdf;
 
+static int g_pre_chunk = 0;   // subjects per pdf_preprocess sub-batch (0 = whole batch); pdf_debug_set_pre_chunk
+
 extern "C" size_t pdf_preproc_workspace_bytes(const pdf_preproc_cfg* cfg, int batch) {
   if (!cfg || batch <= 0) return 0;
   size_t n = align_up(sizeof(ZoomTables), 256) + align_up(sizeof(SubjState) * (size_t)batch, 256);
@@ -1089,9 +1091,39 @@ extern "C" int pdf_gather_resize_normalize(const pdf_preproc_cfg* cfg, int batch
 extern "C" int pdf_preprocess(const pdf_preproc_cfg* cfg, int batch, const float* d_raw, float* d_zoomed, void* d_workspace,
                               float* d_lohi, int32_t* d_indices, int32_t* d_nslices, void* d_out, int out_mode,
                               pdf_stream_t stream) {
-  if (int rc = pdf_resample_stats(cfg, batch, d_raw, d_zoomed, d_workspace, stream)) return rc;
-  if (int rc = pdf_select_bounds_indices(cfg, batch, d_zoomed, d_workspace, d_lohi, d_indices, d_nslices, stream)) return rc;
-  return pdf_gather_resize_normalize(cfg, batch, d_zoomed, d_workspace, d_lohi, d_indices, d_nslices, d_out, out_mode, stream);
+  if (int rc = validate(cfg, batch)) return rc;
+  // Sub-batches: the resampled volumes of one sub-batch (8.4 MB each at 128^3) stay L2-resident between the resample kernel,
+  // the two refinement-histogram passes and the plane gather, instead of streaming B x 8.4 MB through HBM four times.
+  const int chunk = (g_pre_chunk > 0 && g_pre_chunk < batch) ? g_pre_chunk : batch;
+  int lmax = 0;
+  for (int a = 0; a < cfg->n_axes; ++a) lmax += cfg->counts[a];
+  const size_t S = (size_t)cfg->input_size;
+  size_t out_bytes = (size_t)lmax * S * S * (out_mode == PDF_OUT_F32_NHWC3 ? 12 : 2);
+  if (out_mode == PDF_OUT_BF16_C1_PAD) {
+    int pitch = 0, rows = 0;
+    if (int rc = pdf_stem_padded_dims(cfg->input_size, &pitch, &rows)) return rc;
+    out_bytes = (size_t)lmax * rows * pitch * 2;
+  }
+  const size_t vin = (size_t)cfg->in_shape[0] * cfg->in_shape[1] * cfg->in_shape[2];
+  const size_t vout = (size_t)cfg->out_shape[0] * cfg->out_shape[1] * cfg->out_shape[2];
+  for (int b0 = 0; b0 < batch; b0 += chunk) {
+    const int nb = min(chunk, batch - b0);
+    const float* raw = d_raw + (size_t)b0 * vin;
+    float* zoomed = d_zoomed + (size_t)b0 * vout;
+    float* lohi = d_lohi + 4 * (size_t)b0;
+    int32_t* indices = d_indices + (size_t)b0 * lmax;
+    int32_t* nslices = d_nslices + (size_t)b0 * cfg->n_axes;
+    void* out = reinterpret_cast<char*>(d_out) + (size_t)b0 * out_bytes;
+    if (int rc = pdf_resample_stats(cfg, nb, raw, zoomed, d_workspace, stream)) return rc;
+    if (int rc = pdf_select_bounds_indices(cfg, nb, zoomed, d_workspace, lohi, indices, nslices, stream)) return rc;
+    if (int rc = pdf_gather_resize_normalize(cfg, nb, zoomed, d_workspace, lohi, indices, nslices, out, out_mode, stream)) return rc;
+  }
+  return PDF_OK;
+}
+
+extern "C" int pdf_debug_set_pre_chunk(int subjects) {
+  g_pre_chunk = subjects > 0 ? subjects : 0;
+  return PDF_OK;
 }
 
 extern "C" int pdf_normalize_volume(int batch, size_t voxels, const float* d_zoomed, const float* d_lohi, float* d_norm,

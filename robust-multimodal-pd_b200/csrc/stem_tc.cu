@@ -13,11 +13,12 @@
 //     the 3x3/2 max-pool, bias, ReLU and the bf16 conversion are plain register arithmetic on tcgen05.ld results,
 //     and all 128 lanes do useful work.
 //
-//   warps 0..3   epilogue: tcgen05.ld -> vertical/horizontal max -> +bias, ReLU -> bf16 NHWC store
-//   warp  4      TMA load of the weights, tcgen05.mma issue (6 x M128 N192 K16 per tile), TMEM alloc
-//   warps 5..14  build the B matrix (im2col) in shared memory, 128B-swizzled K-major, from the patch; a 3-stage ring
+//   warps 0..E-1 epilogue (E = kEpiWarps, 4 or 8): tcgen05.ld -> 3x3 max -> ReLU -> bf16 NHWC store.  With E = 8 two warps share
+//                a TMEM lane quarter (warp w and w+4 both own lanes 32*(w%4)..+31) and take half of the accumulator's columns each
+//   warp  E      TMA load of the weights, tcgen05.mma issue (6 x M128 N192 K16 per tile), TMEM alloc
+//   next 10      build the B matrix (im2col) in shared memory, 128B-swizzled K-major, from the patch; a 3-stage ring
 //                against the MMAs; two TMEM accumulators overlap epilogue and MMA
-//   warp  15     TMA producer: the 39 x 40 input patch of tile t+4 lands in a 4-stage ring while tile t is built
+//   last warp    TMA producer: the 39 x 40 input patch of tile t+4 lands in a 4-stage ring while tile t is built
 //
 // The input image is read from a zero-PADDED buffer (origin at row/column 5, see pdf_stem_padded_dims): the patch
 // origin is then (4*pp0, 4*pq0) >= 0 and every 8-pixel chunk of the staged patch is a 4-byte aligned shared-memory read.
@@ -37,7 +38,12 @@ constexpr int kStemBStage = 2 * kStemBBlock;
 constexpr int kStemABlock = 128 * 128;
 constexpr int kStemABytes = 2 * kStemABlock;
 constexpr int kBuilderWarps = 10;                // 585 chunks over 320 threads: two rounds
-constexpr int kStemWarps = 4 + 1 + kBuilderWarps + 1;
+#ifndef STEM_EPI_WARPS
+#define STEM_EPI_WARPS 8
+#endif
+constexpr int kEpiWarps = STEM_EPI_WARPS;
+constexpr int kEpiGroups = 16 / kEpiWarps;        // row groups (of 4) per epilogue warp
+constexpr int kStemWarps = kEpiWarps + 1 + kBuilderWarps + 1;
 constexpr int kStemBuilders = kBuilderWarps * 32;
 constexpr int kBStages = 3;                      // B ring (the two TMEM accumulators bound the epilogue side)
 constexpr int kPatchCols = 40;                   // 35 needed (+4 when the box start is rounded down to 16 bytes); 80-byte rows
@@ -47,14 +53,13 @@ constexpr int kStemSmem = kStemABytes + kBStages * kStemBStage + kPatchStages * 
 
 struct StemParams {
   const __nv_bfloat16* in;    // padded [n, rows, pitch]
-  const float* bias;          // [64]
   const int* border;          // NULL, or the border-correction blob of pdf_op.d_scale (see include/pdfusion_b200.h)
   __nv_bfloat16* out;         // [n, P, P, 64]
   int pitch, rows, H1, P, tiles_x, tiles_y, total_tiles;
   unsigned long long* trace;  // debug: per-role clock64 stamps of CTA 0 (pdf_debug_set_trace), or NULL
 };
 
-// stamp slot: [it][event]; events 0-2 producer/builder, 3-5 MMA, 6-8 epilogue
+// stamp slot: [it][event]; events 0-2 builder, 3-5 MMA, 6-8 epilogue, 9-13 inside the epilogue of warp 0
 #define STEM_TRACE(ev) do { if (p.trace && blockIdx.x == 0 && it < 64 && (threadIdx.x & 31) == 0) p.trace[it * 16 + (ev)] = clock64(); } while (0)
 
 // (image, tile row, tile column) of the tiles blockIdx.x, blockIdx.x + gridDim.x, ... without a division per tile
@@ -85,11 +90,20 @@ __device__ __forceinline__ void tmem_ld16_nowait(uint32_t taddr, uint32_t (&v)[1
         "=r"(v[10]), "=r"(v[11]), "=r"(v[12]), "=r"(v[13]), "=r"(v[14]), "=r"(v[15])
       : "r"(taddr));
 }
+// max(x, 0) rounded to bf16 in one instruction (cvt.rn.relu)
+__device__ __forceinline__ __nv_bfloat16 relu_bf16(float x) {
+  uint32_t r;
+  asm("cvt.rn.relu.bf16x2.f32 %0, %1, %1;" : "=r"(r) : "f"(x));
+  return __ushort_as_bfloat16((unsigned short)(r & 0xffffu));
+}
 __device__ __forceinline__ void tmem_wait_ld() { asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory"); }
 __device__ __forceinline__ void mbar_arrive_cta(uint32_t bar) {
   asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(bar) : "memory");
 }
 
+// FIX: the input was normalised with per-channel statistics, border conv pixels get a class-dependent bias correction
+// (p.border).  A separate instantiation keeps the ~3000 instructions of that path out of the common kernel.
+template <bool FIX>
 __global__ void __launch_bounds__(kStemWarps * 32, 1)
 stem_fused_kernel(const __grid_constant__ CUtensorMap tmap_w, const __grid_constant__ CUtensorMap tmap_in, const StemParams p) {
   extern __shared__ uint8_t smem_raw[];
@@ -106,7 +120,7 @@ stem_fused_kernel(const __grid_constant__ CUtensorMap tmap_w, const __grid_const
   const int tid = threadIdx.x, lane = tid & 31;
   const int warp = __shfl_sync(0xffffffffu, tid >> 5, 0);
 
-  if (warp == 4) {
+  if (warp == kEpiWarps) {
     if (elect_one()) {
       prefetch_tmap(&tmap_w);
       mbar_init(bar_w, 1);
@@ -116,7 +130,7 @@ stem_fused_kernel(const __grid_constant__ CUtensorMap tmap_w, const __grid_const
       }
       for (int s = 0; s < 2; ++s) {
         mbar_init(bar_accfull + 8 * s, 1);             // tcgen05.commit
-        mbar_init(bar_accempty + 8 * s, 4);            // one arrive per epilogue warp
+        mbar_init(bar_accempty + 8 * s, kEpiWarps);    // one arrive per epilogue warp
       }
       for (int s = 0; s < kPatchStages; ++s) { mbar_init(bar_pfull + 8 * s, 1); mbar_init(bar_pempty + 8 * s, kBuilderWarps); }
       fence_barrier_init();
@@ -131,21 +145,28 @@ stem_fused_kernel(const __grid_constant__ CUtensorMap tmap_w, const __grid_const
   // have to be finite, so both stages are zeroed once
   for (int i = tid; i < kBStages * kStemBStage / 16; i += kStemWarps * 32)
     reinterpret_cast<uint4*>(smem + kStemABytes)[i] = make_uint4(0u, 0u, 0u, 0u);
+  __syncthreads();
+  // K slots 88 and 89 (t = 11, s = 0, 1) of every B row hold the constant 1: the weight matrix carries the bias there (split
+  // into two bf16 terms), so the tensor core adds it and the epilogue has no per-pixel bias add
+  for (int i = tid; i < kBStages * kSites; i += kStemWarps * 32) {
+    const int stage = i / kSites, site = i - stage * kSites;
+    *reinterpret_cast<uint32_t*>(smem + kStemABytes + stage * kStemBStage + kStemBBlock + site * 128 + ((3 ^ (site & 7)) << 4)) = 0x3F803F80u;
+  }
   fence_proxy_async();
   tc_fence_before();
   __syncthreads();
   tc_fence_after();
   const uint32_t tmem_base = *tmem_slot;
 
-  if (warp < 4) {
+  if (warp < kEpiWarps) {
     // ------------------------------------------------------------------------------------------ epilogue
-    const int v = warp >> 1, c = (warp & 1) * 32 + lane;
-    const float bias_c = __ldg(p.bias + c);
+    const int quarter = warp & 3, half = warp >> 2;     // TMEM lane quarter (fixed by warp % 4), column half of the accumulator
+    const int v = quarter >> 1, c = (quarter & 1) * 32 + lane;
     // per-channel input statistics: conv pixels whose 7x7 window leaves the image need a class-dependent bias correction
-    const int nc = p.border ? p.border[0] : 0;
+    const int nc = FIX ? p.border[0] : 0;
     const int* cls = p.border + 2;
     const float* delta = reinterpret_cast<const float*>(p.border + 2 + p.H1) + c;
-    const uint32_t tlane = tmem_base + ((uint32_t)(warp * 32) << 16);
+    const uint32_t tlane = tmem_base + ((uint32_t)(quarter * 32) << 16);
     int it = 0;
     TileIter ti(blockIdx.x, gridDim.x, p.tiles_x, p.tiles_y);
     for (int tile = blockIdx.x; tile < p.total_tiles; tile += gridDim.x, ++it, ti.next()) {
@@ -156,7 +177,7 @@ stem_fused_kernel(const __grid_constant__ CUtensorMap tmap_w, const __grid_const
       const int cy0 = 2 * pp0 - 1, cx0 = 2 * pq0 - 1;
       const bool col_edge = cx0 < 0 || cx0 + kConvCols > p.H1;
       bool fix = false;
-      if (nc) fix = (cls[max(cy0, 0)] | cls[min(cy0 + 4 * kPR / 2, p.H1 - 1)] | cls[max(cx0, 0)] | cls[min(cx0 + kConvCols - 1, p.H1 - 1)]) != 0;
+      if (FIX) fix = (cls[max(cy0, 0)] | cls[min(cy0 + 4 * kPR / 2, p.H1 - 1)] | cls[max(cx0, 0)] | cls[min(cx0 + kConvCols - 1, p.H1 - 1)]) != 0;
       const size_t orow_stride = (size_t)p.P * 64;
       __nv_bfloat16* otile = p.out + (((size_t)n * p.P + pp0 + v) * p.P + pq0) * 64 + c;
       mbar_wait(bar_accfull + 8 * stage, phase);
@@ -165,14 +186,16 @@ stem_fused_kernel(const __grid_constant__ CUtensorMap tmap_w, const __grid_const
       // tcgen05.ld moves only ~64-100 B/clk per SM (gpurun_out/stem_trace.txt): reading the 96 KB accumulator is the longest
       // stage of this kernel; issuing the loads further ahead (a register double buffer) was measured slower.
 #pragma unroll
-      for (int i = 0; i < 4; ++i) {
+      for (int ii = 0; ii < kEpiGroups; ++ii) {
+        const int i = kEpiGroups * half + ii;
         uint32_t r0[16], r1[16], r2[16];
         const uint32_t col = (uint32_t)(stage * 256 + i * 48);
         tmem_ld16_nowait(tlane + col, r0);
         tmem_ld16_nowait(tlane + col + 16, r1);
         tmem_ld16_nowait(tlane + col + 32, r2);
         tmem_wait_ld();
-        if (i == 3) {                                  // accumulator fully read: hand it back to the MMA warp
+        if (warp == 0) STEM_TRACE(9 + ii);
+        if (ii == kEpiGroups - 1) {                    // this warp's share is read: hand it back to the MMA warp
           tc_fence_before();
           __syncwarp();
           if (lane == 0) mbar_arrive_cta(bar_accempty + 8 * stage);
@@ -182,7 +205,7 @@ stem_fused_kernel(const __grid_constant__ CUtensorMap tmap_w, const __grid_const
         if (pr >= p.P) continue;
         const int cy = cy0 + 4 * i + 2 * v;            // conv rows cy, cy+1, cy+2; the middle one (2*pr) is always valid
         const bool top = cy >= 0, bot = cy + 2 < p.H1;
-        if (fix) {                                     // (uniform branch: border tiles of a per-channel-normalised input only)
+        if (FIX && fix) {                              // (uniform branch: border tiles of a per-channel-normalised input only)
           auto correct = [&](uint32_t (&r)[16], int row) {
             if (row < 0 || row >= p.H1) return;
             const int rc = cls[row];
@@ -196,29 +219,36 @@ stem_fused_kernel(const __grid_constant__ CUtensorMap tmap_w, const __grid_const
           };
           correct(r0, cy); correct(r1, cy + 1); correct(r2, cy + 2);
         }
-        float m[16];
-#pragma unroll
-        for (int k = 0; k < kConvCols; ++k) {
-          float x = __uint_as_float(r1[k]);
-          if (top) x = fmaxf(x, __uint_as_float(r0[k]));
-          if (bot) x = fmaxf(x, __uint_as_float(r2[k]));
-          m[k] = x;
-        }
-        if (col_edge) {
-#pragma unroll
-          for (int k = 0; k < kConvCols; ++k)
-            if (cx0 + k < 0 || cx0 + k >= p.H1) m[k] = -INFINITY;
-        }
         __nv_bfloat16* orow = otile + (size_t)(2 * i) * orow_stride;
+        float m[16];
+        if (top && bot && !col_edge) {                 // interior rows of interior tile columns: 3-input maxima, ReLU in the convert
 #pragma unroll
-        for (int j = 0; j < kPQ; ++j) {
-          const float h = fmaxf(fmaxf(m[2 * j], m[2 * j + 1]), m[2 * j + 2]);
-          if (pq0 + j < p.P) orow[j * 64] = __float2bfloat16(fmaxf(h + bias_c, 0.f));
+          for (int k = 0; k < kConvCols; ++k) m[k] = fmaxf(fmaxf(__uint_as_float(r0[k]), __uint_as_float(r1[k])), __uint_as_float(r2[k]));
+#pragma unroll
+          for (int j = 0; j < kPQ; ++j)
+            orow[j * 64] = relu_bf16(fmaxf(fmaxf(m[2 * j], m[2 * j + 1]), m[2 * j + 2]));
+        } else {
+#pragma unroll
+          for (int k = 0; k < kConvCols; ++k) {
+            float x = __uint_as_float(r1[k]);
+            if (top) x = fmaxf(x, __uint_as_float(r0[k]));
+            if (bot) x = fmaxf(x, __uint_as_float(r2[k]));
+            m[k] = x;
+          }
+          if (col_edge) {
+#pragma unroll
+            for (int k = 0; k < kConvCols; ++k)
+              if (cx0 + k < 0 || cx0 + k >= p.H1) m[k] = -INFINITY;
+          }
+#pragma unroll
+          for (int j = 0; j < kPQ; ++j)
+            if (pq0 + j < p.P) orow[j * 64] = relu_bf16(fmaxf(fmaxf(m[2 * j], m[2 * j + 1]), m[2 * j + 2]));
         }
+        if (ii == 0 && warp == 0) STEM_TRACE(13);
       }
       if (warp == 0) STEM_TRACE(8);
     }
-  } else if (warp == 4) {
+  } else if (warp == kEpiWarps) {
     // ------------------------------------------------------------------------------------------ MMA issue
     if (elect_one()) {
       constexpr uint32_t idesc = make_idesc(kSites);
@@ -244,11 +274,11 @@ stem_fused_kernel(const __grid_constant__ CUtensorMap tmap_w, const __grid_const
         STEM_TRACE(5);
       }
     }
-  } else if (warp < 5 + kBuilderWarps) {
+  } else if (warp < kEpiWarps + 1 + kBuilderWarps) {
     // ------------------------------------------------------------------------------------------ B builders
     // The (patch row, conv column) chunks a thread copies, and the B rows each one lands in, are the same for every tile:
     // the offsets are computed once and live in registers.
-    const int bt = tid - 5 * 32;
+    const int bt = tid - (kEpiWarps + 1) * 32;
     constexpr int kRounds = (kPatchRows * kConvCols + kStemBuilders - 1) / kStemBuilders;
     int ld_off[kRounds];
     uint32_t st_off[kRounds][6];
@@ -275,9 +305,9 @@ stem_fused_kernel(const __grid_constant__ CUtensorMap tmap_w, const __grid_const
       const uint32_t pbase = sP + (uint32_t)ps * kPatchStage + (uint32_t)(((4 * ti.tx * kPQ) & 7) * 2);   // see the TMA producer
       const uint32_t bbase = sB + (uint32_t)stage * kStemBStage;
       mbar_wait(bar_pfull + 8 * ps, pphase);
-      if (warp == 5) STEM_TRACE(0);
+      if (warp == kEpiWarps + 1) STEM_TRACE(0);
       mbar_wait(bar_bempty + 8 * stage, phase ^ 1u);
-      if (warp == 5) STEM_TRACE(1);
+      if (warp == kEpiWarps + 1) STEM_TRACE(1);
 #pragma unroll
       for (int k = 0; k < kRounds; ++k) {
         if (ld_off[k] >= 0) {
@@ -299,7 +329,7 @@ stem_fused_kernel(const __grid_constant__ CUtensorMap tmap_w, const __grid_const
         mbar_arrive_cta(bar_bfull + 8 * stage);
         mbar_arrive_cta(bar_pempty + 8 * ps);
       }
-      if (warp == 5) STEM_TRACE(2);
+      if (warp == kEpiWarps + 1) STEM_TRACE(2);
     }
   } else {
     // ------------------------------------------------------------------------------------------ patch TMA producer
@@ -324,7 +354,7 @@ stem_fused_kernel(const __grid_constant__ CUtensorMap tmap_w, const __grid_const
   }
   tc_fence_before();
   __syncthreads();
-  if (warp == 4) tmem_dealloc(tmem_base, 512);
+  if (warp == kEpiWarps) tmem_dealloc(tmem_base, 512);
 }
 
 }  // namespace pdf
@@ -353,12 +383,12 @@ namespace pdf {
 int launch_stem_fused(const pdf_op& op, const TensorMapBlob& tmap_w, const TensorMapBlob& tmap_in, cudaStream_t s) {
   static bool configured = false;
   if (!configured) {
-    PDF_CHECK_CUDA(cudaFuncSetAttribute(stem_fused_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kStemSmem));
+    PDF_CHECK_CUDA(cudaFuncSetAttribute(stem_fused_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, kStemSmem));
+    PDF_CHECK_CUDA(cudaFuncSetAttribute(stem_fused_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, kStemSmem));
     configured = true;
   }
   StemParams p;
   p.in = reinterpret_cast<const __nv_bfloat16*>(op.d_in);
-  p.bias = op.d_bias;
   p.border = reinterpret_cast<const int*>(op.d_scale);
   p.out = reinterpret_cast<__nv_bfloat16*>(op.d_out);
   if (int rc = pdf_stem_padded_dims(op.h, &p.pitch, &p.rows)) return rc;
@@ -369,8 +399,10 @@ int launch_stem_fused(const pdf_op& op, const TensorMapBlob& tmap_w, const Tenso
   p.total_tiles = p.tiles_x * p.tiles_y * op.n;
   p.trace = g_stem_trace;
   const int grid = max(1, min(p.total_tiles, num_sms()));
-  stem_fused_kernel<<<grid, kStemWarps * 32, kStemSmem, s>>>(*reinterpret_cast<const CUtensorMap*>(&tmap_w),
-                                                             *reinterpret_cast<const CUtensorMap*>(&tmap_in), p);
+  const CUtensorMap& tw = *reinterpret_cast<const CUtensorMap*>(&tmap_w);
+  const CUtensorMap& ti = *reinterpret_cast<const CUtensorMap*>(&tmap_in);
+  if (p.border) stem_fused_kernel<true><<<grid, kStemWarps * 32, kStemSmem, s>>>(tw, ti, p);
+  else stem_fused_kernel<false><<<grid, kStemWarps * 32, kStemSmem, s>>>(tw, ti, p);
   PDF_CHECK_LAUNCH();
   return PDF_OK;
 }

@@ -118,6 +118,7 @@ PROTOTYPES = {
     "pdf_selftest_umma_rate": (C.c_int, [C.c_int, C.c_int, C.c_int, C.c_int, _P, _P]),
     "pdf_debug_set_trace": (C.c_int, [_P]),
     "pdf_debug_enable_pair": (C.c_int, [C.c_int]),
+    "pdf_debug_set_pre_chunk": (C.c_int, [C.c_int]),
     "pdf_debug_disable_halo": (C.c_int, [C.c_int]),
 }
 
@@ -144,6 +145,8 @@ def load():
         fn.argtypes = args
     if os.environ.get("PDFUSION_B200_PAIR"):             # tuning hook: CTA-pair (cta_group::2) kernel for Cout >= 128 layers
         lib.pdf_debug_enable_pair(1)
+    if os.environ.get("PDFUSION_B200_PRE_CHUNK"):        # tuning hook: subjects per preprocessing sub-batch (L2 residency)
+        lib.pdf_debug_set_pre_chunk(int(os.environ["PDFUSION_B200_PRE_CHUNK"]))
     _lib = lib
     return lib
 

@@ -378,6 +378,11 @@ class ResNetEncoder:
                     mat = torch.zeros(2, 64, 16, 8, dtype=torch.float64)
                     mat[0, :, 0:7, :7] = w1
                     mat[1, :, 4:11, :7] = w1
+                    # K slots 88, 89 (t = 11, s = 0, 1) multiply a constant 1 in the kernel's B matrix: the bias rides through the
+                    # tensor core as two bf16 terms (hi + lo, relative error 2^-17)
+                    hi = shift.to(torch.bfloat16).double()
+                    mat[:, :, 11, 0] = hi
+                    mat[:, :, 11, 1] = shift - hi
                     mat = mat.reshape(128, 128)
                 else:
                     mat = torch.zeros(w1.shape[0], 8, 8, dtype=torch.float64)  # im2col kernel: K index = r*8 + s

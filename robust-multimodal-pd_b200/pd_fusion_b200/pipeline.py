@@ -6,6 +6,7 @@ every subject of the batch is resampled, normalised, sliced and encoded by the s
 """
 from __future__ import annotations
 
+import os
 from dataclasses import dataclass
 from typing import Dict, Sequence
 
@@ -81,9 +82,11 @@ class EmbeddingPipeline:
             encs = [self.enc, enc2]
             ins = [(e.input_padded if e.input_padded is not None else e.input).view(self.pre.net_input.shape) for e in encs]
             B, L = self.max_subjects, self.L
+            prio = os.environ.get("PDFUSION_B200_PRIO", "")          # tuning hook: which of the two streams the block scheduler prefers
             self._ov = dict(
                 encs=encs, ins=ins, turn=0,
-                pre_stream=torch.cuda.Stream(self.device), conv_stream=torch.cuda.Stream(self.device),
+                pre_stream=torch.cuda.Stream(self.device, priority=-1 if prio == "pre" else 0),
+                conv_stream=torch.cuda.Stream(self.device, priority=-1 if prio == "conv" else 0),
                 pre_done=[torch.cuda.Event() for _ in range(2)], slot_free=[torch.cuda.Event() for _ in range(2)],
                 mean=[torch.empty((B, self.D), dtype=torch.float32, device=self.device) for _ in range(2)],
                 nvalid=[torch.empty((B,), dtype=torch.int32, device=self.device) for _ in range(2)],

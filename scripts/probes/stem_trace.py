@@ -30,3 +30,9 @@ d = (t[5:40, :9] - t[4:39, :9]).float().mean(dim=0)
 print("mean period per event:", [round(float(x)) for x in d])
 print("builder work (bempty->done):", float((t[4:40, 2] - t[4:40, 1]).float().mean()), " mma (bfull->commit):", float((t[4:40, 5] - t[4:40, 4]).float().mean()),
       " epilogue (accfull->done):", float((t[4:40, 8] - t[4:40, 6]).float().mean()), " commit->accfull seen:", float((t[4:40, 6] - t[4:40, 5]).float().mean()))
+
+# inside the epilogue (warp 0): accfull -> loads of row group i landed (ld0..ld3), end of group 0's arithmetic and stores (g0done)
+print("tile   ld0-accfull  g0done-ld0  ld1-g0done  ld2-ld1  ld3-ld2  done-ld3")
+for it in range(4, 20):
+    r = [int(x) for x in t[it]]
+    print(f"{it:4d} {r[9]-r[6]:10d} {r[13]-r[9]:10d} {r[10]-r[13]:10d} {r[11]-r[10]:10d} {r[12]-r[11]:10d} {r[8]-r[12]:10d}")

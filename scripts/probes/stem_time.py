@@ -1,5 +1,5 @@
 """GPU probe: device time of single encoder ops in isolation (CUDA events over many launches).
-usage: stem_time.py [first_op last_op]   (default 0 1 = the fused stem); PDFUSION_B200_LIB selects the library build."""
+usage: stem_time.py [first_op count]   (default 0 1 = the fused stem); PDFUSION_B200_LIB selects the library build."""
 import sys
 from pathlib import Path
 sys.path.insert(0, str(Path(__file__).resolve().parents[2] / "robust-multimodal-pd_b200"))

@@ -260,10 +260,13 @@ int pdf_selftest_umma_shift(int N, int shift, int mode, const void* d_a_bf16, co
  * d_cycles[grid] receives the SM-clock cycles each CTA took (profiles/r01_umma_rate.txt). */
 int pdf_selftest_umma_rate(int N, int iters, int mode, int grid, unsigned long long* d_cycles, pdf_stream_t stream);
 
-/* Tuning / test hook: enable != 0 routes Cout >= 128 layers with enough tiles through the CTA-pair kernel
- * (tcgen05.mma.cta_group::2, csrc/conv_tc2.cu).  Off by default: measured equal (N=256) or slower (N=128) than the single-CTA
- * kernel on the ResNet shapes. */
+/* Tuning / test hook for the CTA-pair kernel (tcgen05.mma.cta_group::2, csrc/conv_tc2.cu): 0 = never, 1 = every eligible
+ * Cout >= 128 layer, 2 (default) = only 3x3 layers with 256-wide tiles, where it wins under the power cap. */
 int pdf_debug_enable_pair(int enable);
+
+/* Tuning / test hook: enable == 0 launches the tcgen05 kernels without programmatic dependent launch (default: on -- the prologue
+ * of each convolution kernel overlaps the tail of its predecessor; results are identical). */
+int pdf_debug_enable_pdl(int enable);
 
 /* Tuning hook: pdf_preprocess works through the batch in sub-batches of `subjects` volumes (0 = the whole batch at once) so that
  * one sub-batch's resampled volumes stay L2-resident across the histogram passes and the plane gather.  Results are identical. */

@@ -16,6 +16,9 @@ void set_error(const char* fmt, ...) {
   va_end(ap);
 }
 
+static std::atomic<bool> g_pdl{true};
+bool pdl_enabled() { return g_pdl.load(std::memory_order_relaxed); }
+
 void count_launch(int n) { g_launches.fetch_add((uint64_t)n, std::memory_order_relaxed); }
 
 int num_sms() {
@@ -31,5 +34,9 @@ int num_sms() {
 }  // namespace pdf
 
 extern "C" int pdf_version(void) { return 100; }
+extern "C" int pdf_debug_enable_pdl(int enable) {
+  pdf::g_pdl.store(enable != 0, std::memory_order_relaxed);
+  return PDF_OK;
+}
 extern "C" const char* pdf_last_error(void) { return pdf::g_error; }
 extern "C" uint64_t pdf_launch_count(void) { return pdf::g_launches.load(std::memory_order_relaxed); }

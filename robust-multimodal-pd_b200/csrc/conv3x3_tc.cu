@@ -59,6 +59,8 @@ conv3x3_c64_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_cons
   __syncthreads();
   tc_fence_after();
   const uint32_t tmem_base = *tmem_slot;
+  pdl_launch_dependents();   // see common.cuh: the successor's prologue overlaps this kernel's tail,
+  pdl_wait();                // activations are touched only after the predecessor has completed
 
   if (warp == 0) {
     if (elect_one()) {
@@ -228,8 +230,8 @@ int launch_conv3x3_halo(const TcConv& tc, cudaStream_t s) {
   p.relu = tc.relu; p.bias = tc.bias; p.residual = reinterpret_cast<const __nv_bfloat16*>(tc.residual);
   p.out = reinterpret_cast<__nv_bfloat16*>(tc.out);
   const int grid = min(p.total_tiles, num_sms());
-  conv3x3_c64_kernel<<<grid, 192, smem, s>>>(*reinterpret_cast<const CUtensorMap*>(&tc.tmap_a),
-                                             *reinterpret_cast<const CUtensorMap*>(&tc.tmap_b), p);
+  PDF_CHECK_CUDA(launch_pdl(conv3x3_c64_kernel, dim3(grid), dim3(192), (size_t)smem, s,
+                            *reinterpret_cast<const CUtensorMap*>(&tc.tmap_a), *reinterpret_cast<const CUtensorMap*>(&tc.tmap_b), p));
   PDF_CHECK_LAUNCH();
   return PDF_OK;
 }

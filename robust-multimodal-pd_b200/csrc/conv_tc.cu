@@ -69,6 +69,8 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant
   __syncthreads();
   tc_fence_after();
   const uint32_t tmem_base = *tmem_slot;
+  pdl_launch_dependents();   // the next kernel's prologue may overlap this kernel's tail ...
+  pdl_wait();                // ... and this one touches activations only after its predecessor has completed
 
   if (warp == 0) {
     if (elect_one()) {
@@ -467,8 +469,8 @@ static int launch_tc(const TcConv& tc, cudaStream_t s) {
   const int total_tiles = ceil_div(tc.M_total, kBlockM * MT) * (tc.Cout / BLOCK_N);
   const int ctas_per_sm = max(1, min(2, (int)((225 * 1024) / L::kDynamic)));
   const int grid = max(1, min(total_tiles, num_sms() * ctas_per_sm));
-  conv_tc_kernel<BLOCK_N, STAGES, MT><<<grid, 192, L::kDynamic, s>>>(*reinterpret_cast<const CUtensorMap*>(&tc.tmap_a),
-                                                                     *reinterpret_cast<const CUtensorMap*>(&tc.tmap_b), p);
+  PDF_CHECK_CUDA(launch_pdl(conv_tc_kernel<BLOCK_N, STAGES, MT>, dim3(grid), dim3(192), (size_t)L::kDynamic, s,
+                            *reinterpret_cast<const CUtensorMap*>(&tc.tmap_a), *reinterpret_cast<const CUtensorMap*>(&tc.tmap_b), p));
   PDF_CHECK_LAUNCH();
   return PDF_OK;
 }

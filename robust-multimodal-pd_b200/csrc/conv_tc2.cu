@@ -243,14 +243,17 @@ conv_tc2_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constan
   if (warp == 1) tmem_dealloc_2sm(tmem_base, 2 * BLOCK_N);
 }
 
-// Measured on B200 (C2, 768 slices; gpurun_out/launches_pair.csv): N=256 layers run at the same speed as the single-CTA kernel
-// (both ~85-90 % of the measured cuBLAS peak), N=128 layers are 25-40 % SLOWER than the single-CTA kernel with two M sub-tiles
-// per B tile.  The pair kernel is therefore opt-in (pdf_debug_enable_pair / PDFUSION_B200_PAIR=1).
-static bool g_enable_pair = false;
+// Measured on B200 (C2, 768 slices).  One launch at a time under ncu (profiles/r01_launches_pair_kernel.csv) the 256-wide 3x3
+// layers take the same time as the single-CTA kernel and the 128-wide layers are 25-40 % SLOWER than the single-CTA kernel with
+// two M sub-tiles per B tile.  Back to back, however, the conv stack runs into the 1000 W power cap (SM clock 1.4-1.55 GHz,
+// profiles/r01_stack_power.txt): there the pair kernel, which reads half of the B operand from shared memory per CTA, lets
+// layers 3-4 clock ~60 MHz higher and finish 5 % sooner.  Default: pairs for the 256-wide 3x3 layers only.
+static int g_pair_mode = 2;     // 0 off, 1 every eligible Cout >= 128 layer, 2 only 3x3 layers with 256-wide tiles
 
 bool pair_eligible(const TcConv& tc) {
-  if (!g_enable_pair || tc.halo) return false;
+  if (!g_pair_mode || tc.halo) return false;
   if (tc.block_n != 256 && tc.block_n != 128) return false;
+  if (g_pair_mode == 2 && (tc.block_n != 256 || tc.R * tc.S == 1)) return false;
   const long tiles = (long)ceil_div(tc.M_total, 2 * kBlockM) * (tc.Cout / tc.block_n);
   return tiles >= num_sms() / 2;          // at least one tile per CTA pair
 }
@@ -282,8 +285,9 @@ int launch_conv_tc2(const TcConv& tc, cudaStream_t s) {
 
 }  // namespace pdf
 
-/* tuning / test hook: 1 = route eligible Cout >= 128 layers through the CTA-pair (cta_group::2) kernel */
+/* tuning / test hook: 1 = route eligible Cout >= 128 layers through the CTA-pair (cta_group::2) kernel, 2 = only the 3x3 layers with
+ * 256-wide tiles, 0 = off */
 extern "C" int pdf_debug_enable_pair(int enable) {
-  pdf::g_enable_pair = enable != 0;
+  pdf::g_pair_mode = enable;
   return PDF_OK;
 }

@@ -157,6 +157,8 @@ stem_fused_kernel(const __grid_constant__ CUtensorMap tmap_w, const __grid_const
   __syncthreads();
   tc_fence_after();
   const uint32_t tmem_base = *tmem_slot;
+  pdl_launch_dependents();   // see common.cuh: the successor's prologue overlaps this kernel's tail,
+  pdl_wait();                // the image is read (and the output written) only after the predecessor has completed
 
   if (warp < kEpiWarps) {
     // ------------------------------------------------------------------------------------------ epilogue
@@ -401,8 +403,8 @@ int launch_stem_fused(const pdf_op& op, const TensorMapBlob& tmap_w, const Tenso
   const int grid = max(1, min(p.total_tiles, num_sms()));
   const CUtensorMap& tw = *reinterpret_cast<const CUtensorMap*>(&tmap_w);
   const CUtensorMap& ti = *reinterpret_cast<const CUtensorMap*>(&tmap_in);
-  if (p.border) stem_fused_kernel<true><<<grid, kStemWarps * 32, kStemSmem, s>>>(tw, ti, p);
-  else stem_fused_kernel<false><<<grid, kStemWarps * 32, kStemSmem, s>>>(tw, ti, p);
+  if (p.border) PDF_CHECK_CUDA(launch_pdl(stem_fused_kernel<true>, dim3(grid), dim3(kStemWarps * 32), (size_t)kStemSmem, s, tw, ti, p));
+  else PDF_CHECK_CUDA(launch_pdl(stem_fused_kernel<false>, dim3(grid), dim3(kStemWarps * 32), (size_t)kStemSmem, s, tw, ti, p));
   PDF_CHECK_LAUNCH();
   return PDF_OK;
 }

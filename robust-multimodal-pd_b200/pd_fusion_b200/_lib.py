@@ -119,6 +119,7 @@ PROTOTYPES = {
     "pdf_debug_set_trace": (C.c_int, [_P]),
     "pdf_debug_enable_pair": (C.c_int, [C.c_int]),
     "pdf_debug_set_pre_chunk": (C.c_int, [C.c_int]),
+    "pdf_debug_enable_pdl": (C.c_int, [C.c_int]),
     "pdf_debug_disable_halo": (C.c_int, [C.c_int]),
 }
 
@@ -144,7 +145,9 @@ def load():
         fn.restype = res
         fn.argtypes = args
     if os.environ.get("PDFUSION_B200_PAIR"):             # tuning hook: CTA-pair (cta_group::2) kernel for Cout >= 128 layers
-        lib.pdf_debug_enable_pair(1)
+        lib.pdf_debug_enable_pair(int(os.environ["PDFUSION_B200_PAIR"]))
+    if os.environ.get("PDFUSION_B200_NO_PDL"):           # tuning hook: plain stream-ordered launches
+        lib.pdf_debug_enable_pdl(0)
     if os.environ.get("PDFUSION_B200_PRE_CHUNK"):        # tuning hook: subjects per preprocessing sub-batch (L2 residency)
         lib.pdf_debug_set_pre_chunk(int(os.environ["PDFUSION_B200_PRE_CHUNK"]))
     _lib = lib

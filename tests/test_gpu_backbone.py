@@ -31,7 +31,7 @@ def test_umma_selftest(M, N, K):
     c = torch.full((M, N), float("nan"), dtype=torch.float32, device="cuda")
     _lib.check(lib.pdf_selftest_umma(M, N, K, a.data_ptr(), b.data_ptr(), c.data_ptr(), _lib.stream_ptr()))
     torch.cuda.synchronize()
-    lib.pdf_debug_enable_pair(0)
+    lib.pdf_debug_enable_pair(2)
     ref = a.float().cpu().double() @ b.float().cpu().double().T
     err = (c.cpu().double() - ref).abs().max().item()
     assert err < 1e-3 * max(1.0, ref.abs().max().item()), err

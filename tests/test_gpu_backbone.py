@@ -170,6 +170,32 @@ def test_chunked_front_is_bit_identical(arch, n, chunks):
     assert torch.isfinite(outs[0]).all() and torch.equal(outs[0], outs[1])
 
 
+def test_pair_kernel_matches_single_cta_kernel():
+    """The CTA-pair conv kernel (cta_group::2, M = 256 across two SMs) accumulates the same K steps in the same order as the
+    single-CTA kernel: a network large enough to route layers 3-4 through it gives the same embeddings as with pairs off; and
+    with programmatic dependent launch off."""
+    lib = _lib.load()
+    sd = _sd("resnet18")
+    n, S = 400, 224
+    x = (torch.rand(n, S, S, generator=torch.Generator().manual_seed(5)) * 2 - 1).to(torch.bfloat16).cuda()
+    outs = {}
+    try:
+        for mode, pdl in ((2, 1), (0, 1), (1, 1), (2, 0)):
+            lib.pdf_debug_enable_pair(mode)
+            lib.pdf_debug_enable_pdl(pdl)
+            enc = ResNetEncoder(sd, n, S, precision="bf16")
+            outs[(mode, pdl)] = enc.forward(x).clone()
+            torch.cuda.synchronize()
+    finally:
+        lib.pdf_debug_enable_pair(2)
+        lib.pdf_debug_enable_pdl(1)
+    ref = outs[(0, 1)]
+    assert torch.isfinite(ref).all()
+    for key, o in outs.items():
+        err = (o - ref).abs().max().item()
+        assert err <= 1e-5 * ref.abs().max().item(), (key, err)
+
+
 def test_umma_shifted_descriptor_probe():
     """Records whether an MMA operand may start at an arbitrary 128-byte row of a resident, 128B-swizzled tile --
     the precondition for halo-resident 3x3 convolutions.  Result goes to gpurun_out/umma_shift_probe.txt."""

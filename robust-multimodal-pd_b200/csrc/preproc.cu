@@ -28,7 +28,8 @@ struct SubjState {
   uint32_t prefix[kNQ];              // high bits of the answer found so far (0xffffffff = no query)
   uint32_t rank[kNQ];                // residual rank inside the current bucket
   float gamma[2];                    // numpy gamma for q=1 / q=99
-  uint32_t pad[3];
+  uint32_t n_cand;                   // voxels sharing a level-0 bucket with a query (appended to the candidate list by hist<1>)
+  uint32_t pad[2];
 };
 
 struct ZoomTables {                  // lives at the head of the workspace
@@ -41,8 +42,15 @@ struct ZoomTables {                  // lives at the head of the workspace
 struct Workspace {
   ZoomTables* tabs;
   SubjState* st;
-  float* planes;  // [B][L2z][T0][T1]
+  float* planes;   // [B][L2z][T0][T1]
+  uint32_t* cand;  // [B][cand_cap] bit patterns of the level-2 candidates
+  size_t cand_cap;
 };
+
+// candidate list capacity per subject: a quarter of the volume; denser buckets fall back to a full second scan
+static size_t cand_capacity(const pdf_preproc_cfg* cfg) {
+  return ((size_t)cfg->out_shape[0] * cfg->out_shape[1] * cfg->out_shape[2] / 4 + 63) & ~(size_t)63;
+}
 
 static size_t align_up(size_t x, size_t a) { return (x + a - 1) / a * a; }
 
@@ -61,6 +69,9 @@ static Workspace carve(const pdf_preproc_cfg* cfg, int batch, void* ws) {
   w.st = reinterpret_cast<SubjState*>(p);
   p += align_up(sizeof(SubjState) * (size_t)batch, 256);
   w.planes = reinterpret_cast<float*>(p);
+  p += align_up((size_t)batch * count_axis2(cfg) * cfg->out_shape[0] * cfg->out_shape[1] * sizeof(float), 256);
+  w.cand = reinterpret_cast<uint32_t*>(p);
+  w.cand_cap = cand_capacity(cfg);
   return w;
 }
 
@@ -574,9 +585,13 @@ scan_kernel(SubjState* __restrict__ states, FinalizeArgs fa, float* __restrict__
   }
 }
 
+// LEVEL 1 scans the resampled volume: 11-bit histograms inside the four level-0 buckets, and every voxel of those buckets is
+// appended to the subject's candidate list (one global atomic per warp and 512 voxels).  LEVEL 2 then builds the 8-bit
+// histograms from the list -- a few per cent of the volume -- instead of streaming the volume from HBM a third time; a list that
+// overflowed its capacity (a quarter of the volume: near-constant images) falls back to the full scan.
 template <int LEVEL>
 __global__ void __launch_bounds__(256)
-hist_kernel(const float* __restrict__ zoomed, SubjState* __restrict__ states, size_t voxels) {
+hist_kernel(const float* __restrict__ zoomed, SubjState* __restrict__ states, size_t voxels, uint32_t* __restrict__ cand, size_t cand_cap) {
   constexpr int NB = (LEVEL == 1) ? kH1 : kH2;
   __shared__ uint32_t s_hist[kNQ][NB];
   __shared__ uint32_t s_prefix[kNQ];
@@ -588,38 +603,81 @@ hist_kernel(const float* __restrict__ zoomed, SubjState* __restrict__ states, si
   __syncthreads();
   const uint32_t p0 = s_prefix[0], p1 = s_prefix[1], p2 = s_prefix[2], p3 = s_prefix[3];
   const float* zb = zoomed + (size_t)blockIdx.y * voxels;
-  auto visit = [&](float v) {
-    if (v > 0.0f) {
-      const uint32_t bits = __float_as_uint(v);
-      const uint32_t hi = (LEVEL == 1) ? (bits >> 19) : (bits >> 8);
-      const uint32_t bin = (LEVEL == 1) ? ((bits >> 8) & 0x7ffu) : (bits & 0xffu);
-      if (hi == p0) atomicAdd(&s_hist[0][bin], 1u);
-      if (hi == p1) atomicAdd(&s_hist[1][bin], 1u);
-      if (hi == p2) atomicAdd(&s_hist[2][bin], 1u);
-      if (hi == p3) atomicAdd(&s_hist[3][bin], 1u);
-    }
+  uint32_t* cb = cand + (size_t)blockIdx.y * cand_cap;
+  // returns true when the voxel lies in one of the four queried buckets
+  auto visit_bits = [&](uint32_t bits) -> bool {
+    const uint32_t hi = (LEVEL == 1) ? (bits >> 19) : (bits >> 8);
+    const uint32_t bin = (LEVEL == 1) ? ((bits >> 8) & 0x7ffu) : (bits & 0xffu);
+    const bool m0 = hi == p0, m1 = hi == p1, m2 = hi == p2, m3 = hi == p3;
+    if (m0) atomicAdd(&s_hist[0][bin], 1u);
+    if (m1) atomicAdd(&s_hist[1][bin], 1u);
+    if (m2) atomicAdd(&s_hist[2][bin], 1u);
+    if (m3) atomicAdd(&s_hist[3][bin], 1u);
+    return m0 | m1 | m2 | m3;
   };
-  const size_t n4 = voxels / 4;
-  const float4* z4 = reinterpret_cast<const float4*>(zb);
-  const bool aligned = ((reinterpret_cast<uintptr_t>(zb) & 15) == 0);
-  if (aligned) {
-    // four independent 16-byte loads in flight per thread: the pass is latency-bound otherwise (one load per iteration)
-    const size_t stride = (size_t)gridDim.x * 256;
-    size_t i = (size_t)blockIdx.x * 256 + tid;
-    for (; i + 3 * stride < n4; i += 4 * stride) {
-      const float4 a = __ldcs(z4 + i), b = __ldcs(z4 + i + stride), c = __ldcs(z4 + i + 2 * stride), d = __ldcs(z4 + i + 3 * stride);
-      visit(a.x); visit(a.y); visit(a.z); visit(a.w);
-      visit(b.x); visit(b.y); visit(b.z); visit(b.w);
-      visit(c.x); visit(c.y); visit(c.z); visit(c.w);
-      visit(d.x); visit(d.y); visit(d.z); visit(d.w);
+  auto visit = [&](float v) -> bool { return v > 0.0f ? visit_bits(__float_as_uint(v)) : false; };
+  bool from_list = false;
+  if (LEVEL == 2) {
+    const size_t n_list = st->n_cand;
+    from_list = n_list <= cand_cap;
+    if (from_list)
+      for (size_t i = (size_t)blockIdx.x * 256 + tid; i < n_list; i += (size_t)gridDim.x * 256) visit_bits(__ldcs(cb + i));
+  }
+  if (!from_list) {
+    const size_t n4 = voxels / 4;
+    const float4* z4 = reinterpret_cast<const float4*>(zb);
+    const bool aligned = ((reinterpret_cast<uintptr_t>(zb) & 15) == 0);
+    const int lane = tid & 31;
+    if (aligned) {
+      // four independent 16-byte loads in flight per thread: the pass is latency-bound otherwise (one load per iteration)
+      const size_t stride = (size_t)gridDim.x * 256;
+      const size_t n_iter = (n4 + 4 * stride - 1) / (4 * stride);           // uniform trip count: the warp scan below needs all lanes
+      size_t i = (size_t)blockIdx.x * 256 + tid;
+      for (size_t it = 0; it < n_iter; ++it, i += 4 * stride) {
+        float4 q[4];
+#pragma unroll
+        for (int u = 0; u < 4; ++u) q[u] = (i + u * stride < n4) ? __ldcs(z4 + i + u * stride) : make_float4(0.f, 0.f, 0.f, 0.f);
+        uint32_t mine = 0;                                                   // bit u*4+e: element e of load u is a candidate
+#pragma unroll
+        for (int u = 0; u < 4; ++u) {
+          if (visit(q[u].x)) mine |= 1u << (u * 4);
+          if (visit(q[u].y)) mine |= 2u << (u * 4);
+          if (visit(q[u].z)) mine |= 4u << (u * 4);
+          if (visit(q[u].w)) mine |= 8u << (u * 4);
+        }
+        if (LEVEL == 1) {
+          const uint32_t cnt = __popc(mine);
+          uint32_t incl = cnt;
+#pragma unroll
+          for (int o = 1; o < 32; o <<= 1) {
+            const uint32_t nb = __shfl_up_sync(0xffffffffu, incl, o);
+            if (lane >= o) incl += nb;
+          }
+          const uint32_t total = __shfl_sync(0xffffffffu, incl, 31);
+          if (total) {
+            uint32_t base = 0;
+            if (lane == 31) base = atomicAdd(&st->n_cand, total);
+            base = __shfl_sync(0xffffffffu, base, 31);
+            size_t pos = (size_t)base + incl - cnt;
+#pragma unroll
+            for (int u = 0; u < 4; ++u) {
+              const float e[4] = {q[u].x, q[u].y, q[u].z, q[u].w};
+#pragma unroll
+              for (int k = 0; k < 4; ++k)
+                if (mine & (1u << (u * 4 + k))) { if (pos < cand_cap) cb[pos] = __float_as_uint(e[k]); ++pos; }
+            }
+          }
+        }
+      }
+      // scalar tail (voxels % 4): too few to matter, appended one by one
+      for (size_t t = n4 * 4 + (size_t)blockIdx.x * 256 + tid; t < voxels; t += (size_t)gridDim.x * 256) {
+        if (visit(zb[t]) && LEVEL == 1) { const uint32_t pos = atomicAdd(&st->n_cand, 1u); if (pos < cand_cap) cb[pos] = __float_as_uint(zb[t]); }
+      }
+    } else {
+      for (size_t t = (size_t)blockIdx.x * 256 + tid; t < voxels; t += (size_t)gridDim.x * 256) {
+        if (visit(zb[t]) && LEVEL == 1) { const uint32_t pos = atomicAdd(&st->n_cand, 1u); if (pos < cand_cap) cb[pos] = __float_as_uint(zb[t]); }
+      }
     }
-    for (; i < n4; i += stride) {
-      const float4 v = z4[i];
-      visit(v.x); visit(v.y); visit(v.z); visit(v.w);
-    }
-    for (size_t i = n4 * 4 + (size_t)blockIdx.x * 256 + tid; i < voxels; i += (size_t)gridDim.x * 256) visit(zb[i]);
-  } else {
-    for (size_t i = (size_t)blockIdx.x * 256 + tid; i < voxels; i += (size_t)gridDim.x * 256) visit(zb[i]);
   }
   __syncthreads();
   for (int i = tid; i < kNQ * NB; i += 256) {
@@ -908,7 +966,8 @@ static int g_pre_chunk = 0;   // subjects per pdf_preprocess sub-batch (0 = whol
 extern "C" size_t pdf_preproc_workspace_bytes(const pdf_preproc_cfg* cfg, int batch) {
   if (!cfg || batch <= 0) return 0;
   size_t n = align_up(sizeof(ZoomTables), 256) + align_up(sizeof(SubjState) * (size_t)batch, 256);
-  n += (size_t)batch * count_axis2(cfg) * cfg->out_shape[0] * cfg->out_shape[1] * sizeof(float);
+  n += align_up((size_t)batch * count_axis2(cfg) * cfg->out_shape[0] * cfg->out_shape[1] * sizeof(float), 256);
+  n += (size_t)batch * cand_capacity(cfg) * sizeof(uint32_t);
   return n + 256;
 }
 
@@ -1003,11 +1062,11 @@ extern "C" int pdf_select_bounds_indices(const pdf_preproc_cfg* cfg, int batch, 
   const int hblocks = max(1, min((int)(voxels / 4 / 256 / 4) + 1, ceil_div(num_sms() * 8, batch)));
   scan_kernel<0><<<batch, 256, 0, s>>>(w.st, fa, d_lohi, d_indices, d_nslices);
   PDF_CHECK_LAUNCH();
-  hist_kernel<1><<<dim3(hblocks, batch), 256, 0, s>>>(d_zoomed, w.st, voxels);
+  hist_kernel<1><<<dim3(hblocks, batch), 256, 0, s>>>(d_zoomed, w.st, voxels, w.cand, w.cand_cap);
   PDF_CHECK_LAUNCH();
   scan_kernel<1><<<batch, 256, 0, s>>>(w.st, fa, d_lohi, d_indices, d_nslices);
   PDF_CHECK_LAUNCH();
-  hist_kernel<2><<<dim3(hblocks, batch), 256, 0, s>>>(d_zoomed, w.st, voxels);
+  hist_kernel<2><<<dim3(hblocks, batch), 256, 0, s>>>(d_zoomed, w.st, voxels, w.cand, w.cand_cap);
   PDF_CHECK_LAUNCH();
   scan_kernel<2><<<batch, 256, 0, s>>>(w.st, fa, d_lohi, d_indices, d_nslices);
   PDF_CHECK_LAUNCH();

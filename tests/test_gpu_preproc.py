@@ -73,6 +73,30 @@ def test_preproc_degenerate(golden, case):
     assert np.array_equal(res.indices[0].cpu().numpy()[:len(want)], want)
 
 
+@pytest.mark.parametrize("kind", ["two_levels", "constant", "narrow"])
+def test_percentiles_when_candidates_overflow_the_list(kind):
+    """The refinement keeps a candidate list of the voxels that share a coarse bucket with a queried order statistic (a quarter
+    of the volume at most).  Volumes whose positive voxels crowd into one or two buckets overflow it and must take the
+    full-scan fallback with the same bit-exact percentiles."""
+    rng = np.random.default_rng(7)
+    shape = (40, 40, 40)
+    if kind == "two_levels":
+        raw = rng.choice(np.array([0.0, 100.0, 100.5], np.float32), size=shape, p=[0.2, 0.5, 0.3]).astype(np.float32)
+    elif kind == "constant":
+        raw = np.full(shape, 37.25, np.float32)
+    else:
+        raw = (1000.0 + rng.random(shape) * 1e-2).astype(np.float32)          # all positives inside one 13-bit bucket
+    raws = [raw, synthetic_volume(3, shape, 1e-4)]                              # an ordinary subject next to it in the batch
+    pre, res, norm = _run(raws, shape, [2], [6], 32, _lib.OUT_F32_NHWC3)       # identity zoom
+    for b, r in enumerate(raws):
+        zoom = O.load_volume(r, shape)
+        lo, hi = O.percentile_bounds(zoom)
+        got = res.lohi[b].cpu().numpy()
+        assert got[0] == lo and got[1] == hi, (kind, b, got[:2], lo, hi)
+        ref_norm = O.normalize_volume_for_resnet(zoom)
+        assert np.array_equal(norm[b].cpu().numpy().view(np.uint32), ref_norm.view(np.uint32))
+
+
 def test_preproc_batch_and_bf16_output():
     """Several subjects in one launch; bf16 one-channel output equals the rounded f32 output."""
     shape, target = (40, 36, 44), (32, 32, 32)

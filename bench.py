@@ -184,7 +184,10 @@ def main():
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
     ap.add_argument("--cpu-subjects", type=int, default=8, help="bounded CPU-baseline sample (subjects)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
-    ap.add_argument("--no-overlap", action="store_true", help="run preprocessing and convolutions of consecutive batches on one stream")
+    ap.add_argument("--overlap", action="store_true",
+                    help="software-pipeline preprocessing of batch i+1 next to the convolutions of batch i on two streams (measured 2 %% SLOWER "
+                         "than one stream since the conv stack is power-capped: profiles/r01_ab_overlap.txt)")
+    ap.add_argument("--no-overlap", action="store_true", help="(default) one stream")
     args = ap.parse_args()
     wl = WORKLOADS[args.workload]
     if args.impl == "reference":
@@ -218,7 +221,7 @@ def main():
     host_out = torch.empty(table.shape, dtype=torch.float32).pin_memory()
     torch.cuda.synchronize()
 
-    overlap = not args.no_overlap
+    overlap = args.overlap and not args.no_overlap
     fuse_stream = torch.cuda.Stream(dev)
     if overlap:
         pipe.enable_overlap()
@@ -254,24 +257,31 @@ def main():
         mri_col = masks[:, :, 2].contiguous()
     probs = torch.empty((B, S_scen), dtype=torch.float32, device=dev)
 
-    def fuse(res):
-        """probabilities [B, S] of the batch under every scenario"""
+    def fuse(res, emb=None):
+        """probabilities [B, S] of the batch under every scenario (emb: a stable copy of the embeddings to read instead of res)"""
         if args.workload == "c2":
-            probs.copy_(head.forward(res.mean, masks).t())
+            probs.copy_(head.forward(res.mean if emb is None else emb, masks).t())
         else:                                   # MIL: a masked-out bag has length 0 (-> missing_prob); one launch per scenario set
             lens = (mri_col * L).to(torch.int32)                     # [S, B]
-            bags = res.embeddings.unsqueeze(0).expand(S_scen, B, L, D).reshape(S_scen * B, L, D).contiguous()
+            e = res.embeddings if emb is None else emb
+            bags = e.unsqueeze(0).expand(S_scen, B, L, D).reshape(S_scen * B, L, D).contiguous()
             probs.copy_(head.forward(bags, lens.reshape(-1)).view(S_scen, B).t())
         return probs
 
     def step_device():
+        # The fusion head (a few small latency-bound launches) and the gathers run on a side stream, next to the preprocessing of
+        # the following batch; they read `table`, this step's copy of the embeddings.
+        cur = torch.cuda.current_stream()
         if not overlap:
             res = pipe.embed(raw)
+            cur.wait_stream(fuse_stream)         # the previous step's head has finished reading `table` (long ago)
             table.copy_(res.embeddings if args.workload == "c3" else res.mean)
-            pr = fuse(res)
-            return (all_gather_rows(table, B * ws), all_gather_rows(pr, B * ws)) if ws > 1 else (table, pr)
-        # preprocessing of this batch overlaps the convolutions of the previous one (two streams, two encoder instances)
-        # the fusion head (a few small latency-bound launches) and the gathers run on a third stream next to the next batch
+            fuse_stream.wait_stream(cur)
+            with torch.cuda.stream(fuse_stream):
+                pr = fuse(res, table)
+                return (all_gather_rows(table, B * ws), all_gather_rows(pr, B * ws)) if ws > 1 else (table, pr)
+        # --overlap: preprocessing of this batch additionally overlaps the convolutions of the previous one (two streams, two
+        # encoder instances)
         res = pipe.embed_overlapped(raw)
         fuse_stream.wait_stream(pipe.conv_stream)
         with torch.cuda.stream(fuse_stream):
@@ -297,12 +307,12 @@ def main():
         e0.record()
         if overlap:
             pipe.overlap_begin()
-            fuse_stream.wait_stream(torch.cuda.current_stream())
+        fuse_stream.wait_stream(torch.cuda.current_stream())
         for _ in range(steps):
             fn()
         if overlap:
             pipe.overlap_end()
-            torch.cuda.current_stream().wait_stream(fuse_stream)
+        torch.cuda.current_stream().wait_stream(fuse_stream)
         e1.record()
         torch.cuda.synchronize(); barrier()
         ms = torch.tensor([e0.elapsed_time(e1)], device=dev)
@@ -355,7 +365,8 @@ def main():
                    "parallelism": f"subjects sharded x{ws}, all-gather of the embedding table" if ws > 1 else "1 GPU",
                    "fuse": ("Fusion-ModDrop 512-256-128-64-1" if args.workload == "c2" else "gated MIL attention 2048-256-128") +
                            f" under {S_scen} missingness scenarios, one launch",
-                   "streams": "preprocessing of batch i+1 overlaps the conv stack of batch i (2 streams)" if overlap else "one stream"},
+                   "streams": ("preprocessing of batch i+1 overlaps the conv stack of batch i (2 streams); " if overlap else "preprocessing + conv stack on one stream; ") +
+                              "fusion head and gathers on a side stream next to the following batch"},
         "clocks": clk.summary(),
         "e2e": {"value": e2e, "unit": UNIT, "h2d_bytes_per_step": int(pinned.numel() * 4), "d2h_bytes_per_step": int(host_out.numel() * 4 + B * S_scen * 4), "overlap": "H2D of batch i+1 on a copy stream overlaps the kernels of batch i", "timer": "host wall clock around K steps, device synchronised on both sides",
                 "ms_per_step": ms_e2e / args.steps},

@@ -589,6 +589,8 @@ scan_kernel(SubjState* __restrict__ states, FinalizeArgs fa, float* __restrict__
 // appended to the subject's candidate list (one global atomic per warp and 512 voxels).  LEVEL 2 then builds the 8-bit
 // histograms from the list -- a few per cent of the volume -- instead of streaming the volume from HBM a third time; a list that
 // overflowed its capacity (a quarter of the volume: near-constant images) falls back to the full scan.
+constexpr uint32_t kCandChunk = 512;   // = candidates one warp can find per iteration (32 lanes x 16 voxels)
+
 template <int LEVEL>
 __global__ void __launch_bounds__(256)
 hist_kernel(const float* __restrict__ zoomed, SubjState* __restrict__ states, size_t voxels, uint32_t* __restrict__ cand, size_t cand_cap) {
@@ -628,6 +630,7 @@ hist_kernel(const float* __restrict__ zoomed, SubjState* __restrict__ states, si
     const float4* z4 = reinterpret_cast<const float4*>(zb);
     const bool aligned = ((reinterpret_cast<uintptr_t>(zb) & 15) == 0);
     const int lane = tid & 31;
+    uint32_t cur = 0, left = 0;                                             // this warp's current chunk of the candidate list
     if (aligned) {
       // four independent 16-byte loads in flight per thread: the pass is latency-bound otherwise (one load per iteration)
       const size_t stride = (size_t)gridDim.x * 256;
@@ -640,12 +643,15 @@ hist_kernel(const float* __restrict__ zoomed, SubjState* __restrict__ states, si
         uint32_t mine = 0;                                                   // bit u*4+e: element e of load u is a candidate
 #pragma unroll
         for (int u = 0; u < 4; ++u) {
-          if (visit(q[u].x)) mine |= 1u << (u * 4);
-          if (visit(q[u].y)) mine |= 2u << (u * 4);
-          if (visit(q[u].z)) mine |= 4u << (u * 4);
-          if (visit(q[u].w)) mine |= 8u << (u * 4);
+          // background (three quarters of a head volume) is skipped four voxels at a time, mostly by whole warps
+          if (fmaxf(fmaxf(q[u].x, q[u].y), fmaxf(q[u].z, q[u].w)) > 0.0f) {
+            if (visit(q[u].x)) mine |= 1u << (u * 4);
+            if (visit(q[u].y)) mine |= 2u << (u * 4);
+            if (visit(q[u].z)) mine |= 4u << (u * 4);
+            if (visit(q[u].w)) mine |= 8u << (u * 4);
+          }
         }
-        if (LEVEL == 1) {
+        if (LEVEL == 1 && __any_sync(0xffffffffu, mine != 0u)) {
           const uint32_t cnt = __popc(mine);
           uint32_t incl = cnt;
 #pragma unroll
@@ -653,21 +659,35 @@ hist_kernel(const float* __restrict__ zoomed, SubjState* __restrict__ states, si
             const uint32_t nb = __shfl_up_sync(0xffffffffu, incl, o);
             if (lane >= o) incl += nb;
           }
-          const uint32_t total = __shfl_sync(0xffffffffu, incl, 31);
+          const uint32_t total = __shfl_sync(0xffffffffu, incl, 31);       // <= 512 = kCandChunk
           if (total) {
-            uint32_t base = 0;
-            if (lane == 31) base = atomicAdd(&st->n_cand, total);
-            base = __shfl_sync(0xffffffffu, base, 31);
-            size_t pos = (size_t)base + incl - cnt;
+            // list space is reserved a chunk at a time per warp (one same-address atomic per 512 entries, not per iteration);
+            // an iteration's candidates fill the rest of the current chunk and spill into the new one
+            uint32_t fresh = 0;
+            if (total > left) {
+              if (lane == 0) fresh = atomicAdd(&st->n_cand, kCandChunk);
+              fresh = __shfl_sync(0xffffffffu, fresh, 0);
+            }
+            uint32_t r = incl - cnt;
 #pragma unroll
             for (int u = 0; u < 4; ++u) {
               const float e[4] = {q[u].x, q[u].y, q[u].z, q[u].w};
 #pragma unroll
               for (int k = 0; k < 4; ++k)
-                if (mine & (1u << (u * 4 + k))) { if (pos < cand_cap) cb[pos] = __float_as_uint(e[k]); ++pos; }
+                if (mine & (1u << (u * 4 + k))) {
+                  const size_t pos = (r < left) ? (size_t)cur + r : (size_t)fresh + (r - left);
+                  if (pos < cand_cap) cb[pos] = __float_as_uint(e[k]);
+                  ++r;
+                }
             }
+            if (total > left) { cur = fresh + (total - left); left = kCandChunk - (total - left); }
+            else { cur += total; left -= total; }
           }
         }
+      }
+      if (LEVEL == 1) {                                                    // unused rest of the warp's last chunk: sentinels
+        for (uint32_t k = lane; k < left; k += 32)
+          if ((size_t)cur + k < cand_cap) cb[cur + k] = 0xffffffffu;       // sign bit set: never equals a (positive) prefix
       }
       // scalar tail (voxels % 4): too few to matter, appended one by one
       for (size_t t = n4 * 4 + (size_t)blockIdx.x * 256 + tid; t < voxels; t += (size_t)gridDim.x * 256) {

@@ -22,13 +22,16 @@ struct TcParams {
   void* out;
 };
 
+constexpr int kBiasMax = 2048;
+
 template <int BLOCK_N, int STAGES, int MT>
 struct SmemLayout {
   static constexpr int kBBytes = BLOCK_N * kBlockK * 2;
   static constexpr int kStage = MT * kABytes + kBBytes;
   static constexpr int kBarOff = STAGES * kStage;
   static constexpr int kNumBars = 2 * STAGES + 4;               // full/empty ring + acc_full[2] + acc_empty[2]
-  static constexpr int kTotal = kBarOff + kNumBars * 8 + 8;
+  static constexpr int kBiasOff = kBarOff + kNumBars * 8 + 16;   // f32 bias of every output channel (Cout <= kBiasMax), staged once
+  static constexpr int kTotal = kBiasOff + kBiasMax * 4;
   static constexpr int kDynamic = kTotal + 1024;                // slack for manual 1024-byte alignment
   static constexpr int kAccCols = MT * BLOCK_N;                 // TMEM columns of one accumulator set
   static_assert(2 * kAccCols <= 512, "two accumulator sets must fit the 512 TMEM columns");
@@ -56,6 +59,12 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int m_tiles = (p.M_total + kBlockM * MT - 1) / (kBlockM * MT);
   const int total_tiles = m_tiles * (p.Cout / BLOCK_N);
+  // The bias vector lives in shared memory: a global load per 32-column chunk put one L2 latency on the epilogue's critical path,
+  // which is the whole run time of the short-K (1x1 downsample) launches.  (Weights: not produced by the predecessor kernel.)
+  float* s_bias = reinterpret_cast<float*>(smem + L::kBiasOff);
+  const bool bias_staged = p.bias != nullptr && p.Cout <= kBiasMax;
+  if (bias_staged)
+    for (int i = threadIdx.x; i < p.Cout; i += blockDim.x) s_bias[i] = __ldg(p.bias + i);
 
   if (threadIdx.x == 0) {
     prefetch_tmap(&tmap_a);
@@ -192,7 +201,8 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant
             if (p.bias) {
 #pragma unroll
               for (int i = 0; i < 32; i += 4) {
-                const float4 b = __ldg(reinterpret_cast<const float4*>(p.bias + col + i));
+                const float4 b = bias_staged ? *reinterpret_cast<const float4*>(s_bias + col + i)
+                                             : __ldg(reinterpret_cast<const float4*>(p.bias + col + i));
                 f[i] += b.x; f[i + 1] += b.y; f[i + 2] += b.z; f[i + 3] += b.w;
               }
             }

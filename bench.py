@@ -190,6 +190,7 @@ def main():
                     help="software-pipeline preprocessing of batch i+1 next to the convolutions of batch i on two streams (measured 2 %% SLOWER "
                          "than one stream since the conv stack is power-capped: profiles/r01_ab_overlap.txt)")
     ap.add_argument("--no-overlap", action="store_true", help="(default) one stream")
+    ap.add_argument("--no-stored-e2e", action="store_true", help="skip the second end-to-end leg (int16 stored voxels decoded on the device)")
     args = ap.parse_args()
     wl = WORKLOADS[args.workload]
     if args.impl == "reference":
@@ -357,6 +358,29 @@ def main():
     ms_e2e = float(ms_e2e_t.item())
     e2e = ws * B * args.steps / (ms_e2e / 1e3)
 
+    # --- the same end-to-end call fed the voxels AS AN int16 NIfTI STORES THEM (x fastest): half the PCIe bytes, decode
+    #     (float64 scaling rule, cast, transpose) on the device -- SURVEY.md 8f rank 1.  Values are the pool volumes rounded to
+    #     integers (NaN/Inf -> 0), so this is reported next to `e2e`, not instead of it.
+    e2e_i16 = None
+    if not args.no_stored_e2e:
+        pinned_i16 = torch.empty((B, int(np.prod(IN_SHAPE))), dtype=torch.int16).pin_memory()
+        for i in range(B):
+            v = np.nan_to_num(pool[(rank * B + i) % len(pool)], nan=0.0, posinf=0.0, neginf=0.0)
+            pinned_i16[i].copy_(torch.from_numpy(np.clip(np.round(v), -32768, 32767).astype(np.int16).reshape(-1, order="F")))
+        stored_batches = [pinned_i16] * args.steps
+        stored_desc = (4, 1, 1.0, 0.0)
+        pipe.embed_host(stored_batches[:2], out_bags=(args.workload == "c3"), post=fuse, stored=stored_desc)
+        barrier(); torch.cuda.synchronize()
+        t0 = time.perf_counter()
+        pipe.embed_host(stored_batches, out_bags=(args.workload == "c3"), post=fuse, stored=stored_desc)
+        torch.cuda.synchronize(); barrier()
+        t_i16 = torch.tensor([(time.perf_counter() - t0) * 1e3], device=dev)
+        if ws > 1:
+            torch.distributed.all_reduce(t_i16, op=torch.distributed.ReduceOp.MAX)
+        e2e_i16 = {"value": ws * B * args.steps / (float(t_i16.item()) / 1e3), "unit": UNIT, "h2d_bytes_per_step": int(pinned_i16.numel() * 2),
+                   "ms_per_step": float(t_i16.item()) / args.steps,
+                   "input": "voxels as an int16 NIfTI stores them (Fortran order); float64 scaling rule, cast and transpose on the device"}
+
     line = {
         "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": ws, "steps": args.steps, "warmup": max(args.warmup, 3),
         "ms_per_step": ms / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
@@ -372,6 +396,7 @@ def main():
         "clocks": clk.summary(),
         "e2e": {"value": e2e, "unit": UNIT, "h2d_bytes_per_step": int(pinned.numel() * 4), "d2h_bytes_per_step": int(host_out.numel() * 4 + B * S_scen * 4), "overlap": "H2D of batch i+1 on a copy stream overlaps the kernels of batch i", "timer": "host wall clock around K steps, device synchronised on both sides",
                 "ms_per_step": ms_e2e / args.steps},
+        "e2e_stored_int16": e2e_i16,
         "gpu_launches": int(launches),
         "roofline": {"bound": "tensor", "kernel": "conv_tc_kernel (tcgen05 implicit-GEMM conv stack, all launches of one step)",
                      "achieved": tf, "peak": peaks["tf"], "unit": "TFLOP/s", "frac": tf / peaks["tf"],

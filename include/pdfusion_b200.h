@@ -127,6 +127,13 @@ int pdf_tta_augment(int batch, int L, int H, int W, const float* d_slices, const
 int pdf_resize_slices(int batch, int L, int H, int W, int input_size, const float* mean, const float* std,
                       const float* d_slices, void* d_out, int out_mode, pdf_stream_t stream);
 
+/* Stored NIfTI-1 voxels -> the float32 array `nib.load(p).get_fdata().astype(np.float32)` gives the reference
+ * (data/openneuro_features.py:24-25), on the device: float64(raw) [* slope + inter when nibabel would scale] -> float32, written
+ * C-order [B, X, Y, Z].  nifti_datatype: 2 u8, 4 i16, 8 i32, 16 f32, 64 f64, 256 i8, 512 u16, 768 u32.  fortran_order != 0: the
+ * source is x-fastest as in the file (tiled transpose), else already C-order.  d_src / d_dst must not overlap. */
+int pdf_decode_volume(int batch, int nifti_datatype, int X, int Y, int Z, int fortran_order, double slope, double inter,
+                      const void* d_src, float* d_dst, pdf_stream_t stream);
+
 /* normalised volume itself (parity helper for _normalize_volume_for_resnet): d_zoomed -> d_norm */
 int pdf_normalize_volume(int batch, size_t voxels, const float* d_zoomed, const float* d_lohi, float* d_norm,
                          pdf_stream_t stream);

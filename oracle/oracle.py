@@ -65,6 +65,19 @@ def zoom_trilinear(vol: np.ndarray, target_shape: Sequence[int]) -> np.ndarray:
     return out.astype(np.float32)
 
 
+def decode_stored_voxels(voxels: np.ndarray, shape, fortran: bool, slope: float = 1.0, inter: float = 0.0) -> np.ndarray:
+    """`nib.load(p).get_fdata().astype(np.float32)` (openneuro_features.py:24-25) from the stored voxels.
+
+    nibabel is NOT installed here and is not vendored by the reference (pyproject.toml lists the bare name): this restates
+    nibabel 5.x's published behaviour -- `get_fdata()` returns float64; the array proxy applies `arr * scl_slope + scl_inter`
+    (two float64 operations) unless the slope is 0 / non-finite or (slope, inter) == (1, 0); a non-finite inter counts as 0;
+    data are Fortran-ordered in the file.  PARITY UNPINNED for this one function (no nibabel to run, no reference fixture)."""
+    data = np.asarray(voxels).reshape(tuple(shape), order="F" if fortran else "C").astype(np.float64)
+    if slope != 0 and np.isfinite(slope) and not (slope == 1.0 and inter == 0.0):
+        data = data * np.float64(slope) + np.float64(inter if np.isfinite(inter) else 0.0)
+    return np.ascontiguousarray(data.astype(np.float32))
+
+
 def load_volume(data: np.ndarray, target_shape=(160, 160, 160)) -> np.ndarray:
     """openneuro_features.py:25-31 minus the nibabel decode (out of scope)."""
     d = np.asarray(data).astype(np.float32)

@@ -977,6 +977,90 @@ __global__ void tta_kernel(const float* __restrict__ slices, const pdf_tta_param
   }
 }
 
+// ------------------------------------------------------------------------------------------------------
+// Voxel decode on the device: the stored voxels of a NIfTI-1 image (any integer or float type, Fortran
+// order: x fastest) -> what `nib.load(p).get_fdata().astype(np.float32)` hands the reference (data/openneuro_features.py:24-25):
+// float64(raw) [* scl_slope + scl_inter, two roundings, no FMA] -> float32, laid out C-order [X][Y][Z] as the resample kernel
+// reads it.  An int16 volume then crosses PCIe at half the bytes of the float32 array the reference would upload.
+template <typename T>
+__device__ __forceinline__ float decode_one(T v, bool scale, double slope, double inter) {
+  double d = (double)v;
+  if (scale) d = __dadd_rn(__dmul_rn(d, slope), inter);
+  return __double2float_rn(d);
+}
+
+// Fortran-order source: a 32 (x) by 32 (z) tile is transposed through shared memory so that both the reads (x fastest) and the
+// writes (z fastest) are coalesced.  grid (ceil(X/32), ceil(Z/32), Y * batch), block (32, 8).
+template <typename T>
+__global__ void __launch_bounds__(256)
+decode_fortran_kernel(const T* __restrict__ src, float* __restrict__ dst, int X, int Y, int Z, bool scale, double slope, double inter) {
+  __shared__ float tile[32][33];
+  const int b = blockIdx.z / Y, y = blockIdx.z - b * Y;
+  const int x0 = blockIdx.x * 32, z0 = blockIdx.y * 32;
+  const T* sb = src + (size_t)b * X * Y * Z;
+  float* db = dst + (size_t)b * X * Y * Z;
+#pragma unroll
+  for (int k = 0; k < 32; k += 8) {
+    const int x = x0 + threadIdx.x, z = z0 + threadIdx.y + k;
+    if (x < X && z < Z) tile[threadIdx.y + k][threadIdx.x] = decode_one(sb[(size_t)x + (size_t)X * (y + (size_t)Y * z)], scale, slope, inter);
+  }
+  __syncthreads();
+#pragma unroll
+  for (int k = 0; k < 32; k += 8) {
+    const int x = x0 + threadIdx.y + k, z = z0 + threadIdx.x;
+    if (x < X && z < Z) db[((size_t)x * Y + y) * Z + z] = tile[threadIdx.x][threadIdx.y + k];
+  }
+}
+
+template <typename T>
+__global__ void __launch_bounds__(256)
+decode_linear_kernel(const T* __restrict__ src, float* __restrict__ dst, size_t n, bool scale, double slope, double inter) {
+  for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (size_t)gridDim.x * blockDim.x)
+    dst[i] = decode_one(src[i], scale, slope, inter);
+}
+
+template <typename T>
+static int launch_decode(int batch, int X, int Y, int Z, int fortran, bool scale, double slope, double inter, const void* src,
+                         float* dst, cudaStream_t s) {
+  if (fortran) {
+    const dim3 grid(ceil_div(X, 32), ceil_div(Z, 32), Y * batch);
+    decode_fortran_kernel<T><<<grid, dim3(32, 8), 0, s>>>(reinterpret_cast<const T*>(src), dst, X, Y, Z, scale, slope, inter);
+  } else {
+    const size_t n = (size_t)batch * X * Y * Z;
+    const int blocks = (int)min((size_t)num_sms() * 16, (n + 255) / 256);
+    decode_linear_kernel<T><<<max(1, blocks), 256, 0, s>>>(reinterpret_cast<const T*>(src), dst, n, scale, slope, inter);
+  }
+  PDF_CHECK_LAUNCH();
+  return PDF_OK;
+}
+
+}  // namespace pdf
+
+using namespace pdf;
+
+extern "C" int pdf_decode_volume(int batch, int nifti_datatype, int X, int Y, int Z, int fortran_order, double slope, double inter,
+                                 const void* d_src, float* d_dst, pdf_stream_t stream) {
+  PDF_REQUIRE(batch > 0 && X > 0 && Y > 0 && Z > 0 && d_src && d_dst, "pdf_decode_volume: bad arguments");
+  PDF_REQUIRE((long long)Y * batch <= 65535, "pdf_decode_volume: Y * batch exceeds the grid limit");
+  // nibabel applies the scaling only when scl_slope is finite and non-zero and (slope, inter) != (1, 0)
+  const bool scale = slope != 0.0 && isfinite(slope) && !(slope == 1.0 && inter == 0.0);
+  if (!isfinite(inter)) inter = 0.0;
+  cudaStream_t s = as_stream(stream);
+  switch (nifti_datatype) {
+    case 2: return launch_decode<uint8_t>(batch, X, Y, Z, fortran_order, scale, slope, inter, d_src, d_dst, s);
+    case 4: return launch_decode<int16_t>(batch, X, Y, Z, fortran_order, scale, slope, inter, d_src, d_dst, s);
+    case 8: return launch_decode<int32_t>(batch, X, Y, Z, fortran_order, scale, slope, inter, d_src, d_dst, s);
+    case 16: return launch_decode<float>(batch, X, Y, Z, fortran_order, scale, slope, inter, d_src, d_dst, s);
+    case 64: return launch_decode<double>(batch, X, Y, Z, fortran_order, scale, slope, inter, d_src, d_dst, s);
+    case 256: return launch_decode<int8_t>(batch, X, Y, Z, fortran_order, scale, slope, inter, d_src, d_dst, s);
+    case 512: return launch_decode<uint16_t>(batch, X, Y, Z, fortran_order, scale, slope, inter, d_src, d_dst, s);
+    case 768: return launch_decode<uint32_t>(batch, X, Y, Z, fortran_order, scale, slope, inter, d_src, d_dst, s);
+    default: break;
+  }
+  PDF_REQUIRE(false, "pdf_decode_volume: unsupported NIfTI datatype %d", nifti_datatype);
+}
+
+namespace pdf {
 }  // namespace pdf
 
 using namespace pdf;

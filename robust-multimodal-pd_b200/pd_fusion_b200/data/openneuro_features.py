@@ -48,7 +48,29 @@ def _hash_config(cfg: Dict) -> str:
 _NIFTI_DTYPES = {2: "u1", 4: "i2", 8: "i4", 16: "f4", 64: "f8", 256: "i1", 512: "u2", 768: "u4", 1024: "i8", 1280: "u8"}
 
 
-def _read_nifti(path: Path) -> np.ndarray:
+_NP_TO_NIFTI = {"uint8": 2, "int16": 4, "int32": 8, "float32": 16, "float64": 64, "int8": 256, "uint16": 512, "uint32": 768}
+
+
+class StoredVolume:
+    """Voxels as they are stored, plus what is needed to turn them into the reference's float32 array on the device
+    (`pdf_decode_volume`): NIfTI datatype code, [X, Y, Z], storage order, scl_slope / scl_inter."""
+    __slots__ = ("voxels", "code", "shape", "fortran", "slope", "inter")
+
+    def __init__(self, voxels, code, shape, fortran, slope=1.0, inter=0.0):
+        self.voxels, self.code, self.shape, self.fortran, self.slope, self.inter = voxels, int(code), tuple(shape), bool(fortran), float(slope), float(inter)
+
+    def key(self):
+        return (self.code, self.shape, self.fortran, self.slope, self.inter)
+
+    def to_float32(self) -> np.ndarray:
+        """Host restatement of `get_fdata().astype(np.float32)` (C-order [X, Y, Z]); the batched path decodes on the device."""
+        data = self.voxels.reshape(self.shape, order="F" if self.fortran else "C").astype(np.float64)
+        if self.slope != 0 and np.isfinite(self.slope) and not (self.slope == 1.0 and self.inter == 0.0):
+            data = data * self.slope + (self.inter if np.isfinite(self.inter) else 0.0)
+        return np.ascontiguousarray(data.astype(np.float32))
+
+
+def _read_nifti_stored(path: Path) -> StoredVolume:
     raw = gzip.open(path, "rb").read() if str(path).endswith(".gz") else Path(path).read_bytes()
     end = "<" if struct.unpack("<i", raw[:4])[0] == 348 else ">"
     if struct.unpack(end + "i", raw[:4])[0] != 348:
@@ -59,13 +81,35 @@ def _read_nifti(path: Path) -> np.ndarray:
     slope, inter = struct.unpack(end + "2f", raw[112:120])
     if datatype not in _NIFTI_DTYPES:
         raise ValueError(f"{path}: unsupported NIfTI datatype {datatype}")
-    shape = tuple(int(d) for d in dim[1:1 + dim[0]])
+    shape = [int(d) for d in dim[1:1 + dim[0]]]
+    while len(shape) > 3 and shape[-1] == 1:
+        shape.pop()
+    if len(shape) != 3:
+        raise ValueError(f"{path}: expected a 3-D volume, got shape {shape}")
     arr = np.frombuffer(raw, dtype=np.dtype(end + _NIFTI_DTYPES[datatype]), count=int(np.prod(shape)), offset=vox_offset)
-    data = arr.reshape(shape, order="F").astype(np.float64)           # get_fdata(): float64 with scaling applied
-    if slope != 0 and np.isfinite(slope) and not (slope == 1.0 and inter == 0.0):
-        data = data * slope + inter
-    while data.ndim > 3 and data.shape[-1] == 1:
-        data = data[..., 0]
+    if end == ">":
+        arr = arr.astype(arr.dtype.newbyteorder("<"))             # the device kernel reads native (little-endian) voxels
+    if datatype in (1024, 1280):                                   # 64-bit integers: no device decode, go through float64 on the host
+        arr, datatype = arr.astype(np.float64), 64
+    return StoredVolume(arr, datatype, shape, True, slope, inter)
+
+
+def _read_volume_stored(path) -> StoredVolume:
+    p = str(path)
+    if p.endswith(".npy"):
+        data = np.load(p)
+        if data.dtype.name not in _NP_TO_NIFTI:
+            data = data.astype(np.float32)
+        return StoredVolume(np.ascontiguousarray(data).reshape(-1), _NP_TO_NIFTI[data.dtype.name], data.shape, False)
+    return _read_nifti_stored(Path(p))
+
+
+def _read_nifti(path: Path) -> np.ndarray:
+    """float64 array as `get_fdata()` returns it (host path)."""
+    v = _read_nifti_stored(path)
+    data = v.voxels.reshape(v.shape, order="F").astype(np.float64)
+    if v.slope != 0 and np.isfinite(v.slope) and not (v.slope == 1.0 and v.inter == 0.0):
+        data = data * v.slope + (v.inter if np.isfinite(v.inter) else 0.0)
     return data
 
 
@@ -74,6 +118,20 @@ def _read_volume_host(path) -> np.ndarray:
     p = str(path)
     data = np.load(p) if p.endswith(".npy") else _read_nifti(Path(p))
     return np.ascontiguousarray(data.astype(np.float32))
+
+
+def _decode_on_device(batch, dev) -> torch.Tensor:
+    """Stored voxels of same-keyed volumes -> float32 [B, X, Y, Z] on `dev`: the upload carries the file's bytes (half of the
+    float32 array for the usual int16 T1 image), `pdf_decode_volume` does the float64 scaling, the cast and the transpose."""
+    v0 = batch[0]
+    host = torch.from_numpy(np.stack([b.voxels for b in batch]).view(np.uint8)).pin_memory()       # bytes as stored
+    src = host.to(dev, non_blocking=True)
+    out = torch.empty((len(batch),) + v0.shape, dtype=torch.float32, device=dev)
+    lib = _lib.load()
+    _lib.check(lib.pdf_decode_volume(len(batch), v0.code, v0.shape[0], v0.shape[1], v0.shape[2], int(v0.fortran), v0.slope, v0.inter,
+                                     src.data_ptr(), out.data_ptr(), _lib.stream_ptr()), "pdf_decode_volume")
+    src.record_stream(torch.cuda.current_stream(dev))
+    return out
 
 
 # ---------------------------------------------------------------------------------------------------
@@ -191,18 +249,18 @@ def embed_manifest(df: pd.DataFrame, backbone: str, target_shape: Sequence[int],
     paths = df["t1wbrain_path"].tolist()
     i = lo
     while i < hi:
-        first = _read_volume_host(paths[i])
+        first = _read_volume_stored(paths[i])
         batch, j = [first], i + 1
         while j < hi and len(batch) < bsz:
-            nxt = _read_volume_host(paths[j])
-            if nxt.shape != first.shape:
+            nxt = _read_volume_stored(paths[j])
+            if nxt.key() != first.key():                 # same shape, stored type and scaling: one decode launch
                 break
             batch.append(nxt)
             j += 1
         if first.shape not in pipes:
             pipes[first.shape] = EmbeddingPipeline(sd, first.shape, target_shape, axes, counts, input_size, precision, bsz,
                                                    mean, std, "resnet50" if backbone == "resnet50" else "resnet18", dev)
-        raw = torch.from_numpy(np.stack(batch)).pin_memory().to(dev, non_blocking=True)
+        raw = _decode_on_device(batch, dev)
         if tta > 1:
             res = pipes[first.shape].embed_tta(raw, [tta_seeds[k] for k in range(i, j)], tta, tta_cfg)
         else:

@@ -82,6 +82,29 @@ def test_nifti_reader_roundtrip(tmp_path):
     assert got.dtype == np.float32 and got.shape == (5, 4, 3) and np.array_equal(got, (vol * 2.0 + 1.5).astype(np.float32))
     np.save(tmp_path / "v.npy", vol.astype(np.float64))
     assert np.array_equal(_read_volume_host(tmp_path / "v.npy"), vol.astype(np.float32))
+    # the stored form (what the batched builders upload and decode on the device) describes the same array
+    from oracle import oracle as O
+    from pd_fusion_b200.data.openneuro_features import _read_volume_stored
+    sv = _read_volume_stored(p)
+    assert (sv.code, sv.shape, sv.fortran, sv.slope, sv.inter) == (4, (5, 4, 3), True, 2.0, 1.5) and sv.voxels.dtype == np.int16
+    assert np.array_equal(sv.to_float32(), got)
+    assert np.array_equal(O.decode_stored_voxels(sv.voxels, sv.shape, sv.fortran, sv.slope, sv.inter), got)
+    sn = _read_volume_stored(tmp_path / "v.npy")
+    assert (sn.code, sn.fortran) == (64, False) and np.array_equal(sn.to_float32(), vol.astype(np.float32))
+    # big-endian file, slope 0 (= "no scaling" in NIfTI)
+    be = bytearray(352)
+    struct.pack_into(">i", be, 0, 348)
+    struct.pack_into(">8h", be, 40, 3, 5, 4, 3, 1, 1, 1, 1)
+    struct.pack_into(">h", be, 70, 512)
+    struct.pack_into(">h", be, 72, 16)
+    struct.pack_into(">f", be, 108, 352.0)
+    struct.pack_into(">2f", be, 112, 0.0, 9.0)
+    u16 = (np.arange(60, dtype=np.uint16) * 1000).reshape(5, 4, 3)
+    pb = tmp_path / "be.nii"
+    pb.write_bytes(bytes(be) + u16.astype(">u2").tobytes(order="F"))
+    sb = _read_volume_stored(pb)
+    assert sb.code == 512 and sb.voxels.dtype == np.dtype("<u2") and np.array_equal(sb.to_float32(), u16.astype(np.float32))
+    assert np.array_equal(_read_volume_host(pb), u16.astype(np.float32))
 
 
 def test_flop_accounting_matches_survey():

@@ -33,6 +33,7 @@ def _voxels(dtype, n, rng):
 @pytest.mark.parametrize("fortran", [True, False])
 @pytest.mark.parametrize("slope,inter", [(1.0, 0.0), (0.0, 5.0), (0.0123456789, -3.25), (float("nan"), 1.0)])
 def test_decode_matches_oracle(dtype, fortran, slope, inter):
+    slope, inter = float(np.float32(slope)), float(np.float32(inter))          # the header stores float32
     rng = np.random.default_rng(len(dtype) + int(fortran))
     B, shape = 3, (37, 21, 45)                                   # nothing a multiple of the 32 x 32 transpose tile
     vox = np.stack([_voxels(dtype, int(np.prod(shape)), rng) for _ in range(B)])
@@ -43,7 +44,7 @@ def test_decode_matches_oracle(dtype, fortran, slope, inter):
     torch.cuda.synchronize()
     got = out.cpu().numpy()
     for b in range(B):
-        ref = O.decode_stored_voxels(vox[b], shape, fortran, np.float32(slope), np.float32(inter))
+        ref = O.decode_stored_voxels(vox[b], shape, fortran, slope, inter)
         nan = np.isnan(ref)                                       # NaN payloads are not part of the contract (nan_to_num zeroes them next)
         assert np.array_equal(np.isnan(got[b]), nan), (dtype, fortran, slope, inter, b)
         assert np.array_equal(got[b][~nan].view(np.uint32), ref[~nan].view(np.uint32)), (dtype, fortran, slope, inter, b)

@@ -97,6 +97,26 @@ def test_percentiles_when_candidates_overflow_the_list(kind):
         assert np.array_equal(norm[b].cpu().numpy().view(np.uint32), ref_norm.view(np.uint32))
 
 
+def test_resample_extreme_values_bit_exact():
+    """The resample kernel widens float32 to float64 and narrows the sum back with integer instructions on the common path:
+    subnormals, signed zeros, huge magnitudes, results that underflow to float32 subnormals and NaN/Inf must still match the
+    float64 reference bit for bit."""
+    rng = np.random.default_rng(11)
+    shape, target = (24, 28, 32), (17, 19, 23)
+    mag = np.float32(10.0) ** rng.uniform(-44, 38, size=shape).astype(np.float32)        # down into the subnormal range
+    raw = (mag * rng.choice(np.array([-1.0, 1.0], np.float32), size=shape)).astype(np.float32)
+    raw[rng.random(shape) < 0.15] = 0.0
+    raw[rng.random(shape) < 0.05] = -0.0
+    raw[rng.random(shape) < 0.01] = np.nan
+    raw[rng.random(shape) < 0.01] = np.inf
+    raw[0, 0, :4] = np.array([1e-45, 1.17549435e-38, 3.4028235e38, -3.4028235e38], np.float32)
+    with np.errstate(all="ignore"):
+        ref = O.load_volume(raw, target)
+    pre = VolumePreprocessor(shape, target, [2], [4], 32, out_mode=_lib.OUT_F32_NHWC3, max_batch=1)
+    got = pre.resample(torch.from_numpy(raw[None]).cuda())[0].cpu().numpy()
+    assert np.array_equal(got.view(np.uint32), ref.view(np.uint32))
+
+
 def test_preproc_batch_and_bf16_output():
     """Several subjects in one launch; bf16 one-channel output equals the rounded f32 output."""
     shape, target = (40, 36, 44), (32, 32, 32)

@@ -544,6 +544,7 @@ extern "C" int pdf_debug_disable_halo(int disable) {
 extern "C" int pdf_selftest_umma_rate(int N, int iters, int mode, int grid, unsigned long long* d_cycles, pdf_stream_t stream) {
   using namespace pdf;
   PDF_REQUIRE((N == 64 || N == 128 || N == 256) && iters > 0 && grid > 0 && d_cycles, "pdf_selftest_umma_rate: bad arguments");
+  if (mode & 2) return launch_umma2_rate(N, iters, mode & 1, max(1, grid / 2), d_cycles, as_stream(stream));   // CTA pairs (cta_group::2)
   const int smem = 3 * kABytes + N * 128 + 64 + 1024;
   cudaStream_t s = as_stream(stream);
   if (N == 64) {

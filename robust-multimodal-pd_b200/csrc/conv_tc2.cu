@@ -278,6 +278,67 @@ static int launch_tc2(const TcConv& tc, cudaStream_t s) {
   return PDF_OK;
 }
 
+// Probe: back-to-back tcgen05.mma.cta_group::2 (M = 256 over the pair, N, K = 16) from shared memory, the pair counterpart of
+// umma_rate_kernel: each CTA holds its 128 A rows and N/2 B rows.  out[pair] = cycles (leader clock).
+template <int BLOCK_N>
+__global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(128)
+umma2_rate_kernel(int iters, int mode, unsigned long long* __restrict__ out) {
+  extern __shared__ uint8_t smem_raw[];
+  const uint32_t raw_addr = smem_u32(smem_raw);
+  const uint32_t base = (raw_addr + 1023u) & ~1023u;
+  uint8_t* smem = smem_raw + (base - raw_addr);
+  const uint32_t sa = base, sb = base + 3 * kABytes, bar = sb + BLOCK_N * 64;
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(smem + 3 * kABytes + BLOCK_N * 64 + 16);
+  const int warp = threadIdx.x >> 5;
+  const bool leader = cluster_ctarank() == 0;
+  for (uint32_t i = threadIdx.x; i < (3 * kABytes + BLOCK_N * 64) / 4; i += blockDim.x) reinterpret_cast<uint32_t*>(smem)[i] = 0x3c003c00u;
+  if (threadIdx.x == 0) { mbar_init(bar, 1); fence_barrier_init(); }
+  if (warp == 1) tmem_alloc_2sm(smem_u32(tmem_slot), BLOCK_N < 32 ? 32 : BLOCK_N);
+  fence_proxy_async();
+  tc_fence_before();
+  __syncthreads();
+  cluster_sync_all();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_slot;
+  if (leader && warp == 0 && elect_one()) {
+    constexpr uint32_t idesc = make_idesc_m256(BLOCK_N);
+    const uint32_t a_lo = smem_desc_lo(sa), b_lo = smem_desc_lo(sb);
+    const long long t0 = clock64();
+    for (int i = 0; i < iters; ++i) {
+#pragma unroll
+      for (int t = 0; t < 9; ++t) {
+        const uint32_t shift = (mode & 1) ? (uint32_t)((t / 3) * 58 + (t % 3)) * 8u : 0u;
+#pragma unroll
+        for (int k = 0; k < 4; ++k) umma2_f16_lo(tmem_base, a_lo + shift + k * 2, b_lo + k * 2, idesc, 1u);
+      }
+    }
+    umma2_commit_mc(bar);
+    mbar_wait(bar, 0);
+    out[blockIdx.x >> 1] = (unsigned long long)(clock64() - t0);
+  }
+  if (!leader && warp == 0 && elect_one()) mbar_wait(bar, 0);      // the multicast commit arrives here too
+  tc_fence_before();
+  __syncthreads();
+  cluster_sync_all();
+  if (warp == 1) tmem_dealloc_2sm(tmem_base, BLOCK_N < 32 ? 32 : BLOCK_N);
+}
+
+int launch_umma2_rate(int N, int iters, int mode, int pairs, unsigned long long* d_cycles, cudaStream_t s) {
+  const int smem = 3 * kABytes + N * 64 + 64 + 1024;
+  if (N == 64) {
+    PDF_CHECK_CUDA(cudaFuncSetAttribute(umma2_rate_kernel<64>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
+    umma2_rate_kernel<64><<<2 * pairs, 128, smem, s>>>(iters, mode, d_cycles);
+  } else if (N == 128) {
+    PDF_CHECK_CUDA(cudaFuncSetAttribute(umma2_rate_kernel<128>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
+    umma2_rate_kernel<128><<<2 * pairs, 128, smem, s>>>(iters, mode, d_cycles);
+  } else {
+    PDF_CHECK_CUDA(cudaFuncSetAttribute(umma2_rate_kernel<256>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
+    umma2_rate_kernel<256><<<2 * pairs, 128, smem, s>>>(iters, mode, d_cycles);
+  }
+  PDF_CHECK_LAUNCH();
+  return PDF_OK;
+}
+
 int launch_conv_tc2(const TcConv& tc, cudaStream_t s) {
   if (tc.block_n == 256) return launch_tc2<256, 6>(tc, s);
   return launch_tc2<128, 8>(tc, s);

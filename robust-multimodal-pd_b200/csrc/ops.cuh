@@ -33,6 +33,7 @@ int launch_stem_fused(const pdf_op& op, const TensorMapBlob& tmap_w, const Tenso
 int launch_conv_tc(const TcConv& tc, cudaStream_t s);
 bool pair_eligible(const TcConv& tc);
 int launch_conv_tc2(const TcConv& tc, cudaStream_t s);   // cta_group::2 pair kernel (conv_tc2.cu)
+int launch_umma2_rate(int N, int iters, int mode, int pairs, unsigned long long* d_cycles, cudaStream_t s);   // probe
 bool halo_eligible(const pdf_op& op);
 int launch_conv3x3_halo(const TcConv& tc, cudaStream_t s);
 

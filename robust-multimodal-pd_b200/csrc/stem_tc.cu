@@ -60,7 +60,12 @@ struct StemParams {
 };
 
 // stamp slot: [it][event]; events 0-2 builder, 3-5 MMA, 6-8 epilogue, 9-13 inside the epilogue of warp 0
+// (compiled in only with -DPDF_STEM_TRACE: `make EXTRA=-DPDF_STEM_TRACE`; the stamps cost ~25 instructions per tile and warp)
+#ifdef PDF_STEM_TRACE
 #define STEM_TRACE(ev) do { if (p.trace && blockIdx.x == 0 && it < 64 && (threadIdx.x & 31) == 0) p.trace[it * 16 + (ev)] = clock64(); } while (0)
+#else
+#define STEM_TRACE(ev) do { } while (0)
+#endif
 
 // (image, tile row, tile column) of the tiles blockIdx.x, blockIdx.x + gridDim.x, ... without a division per tile
 struct TileIter {

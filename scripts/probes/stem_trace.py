@@ -1,4 +1,5 @@
-"""GPU probe: per-role timeline of CTA 0 of the fused stem kernel (cycles relative to the first stamp)."""
+"""GPU probe: per-role timeline of CTA 0 of the fused stem kernel (cycles relative to the first stamp).
+Needs a library built with the stamps compiled in: make -C robust-multimodal-pd_b200/csrc -B build/stem_tc.o EXTRA=-DPDF_STEM_TRACE && make -C ..."""
 import sys
 from pathlib import Path
 sys.path.insert(0, str(Path(__file__).resolve().parents[2] / "robust-multimodal-pd_b200"))

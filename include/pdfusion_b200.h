@@ -275,6 +275,10 @@ int pdf_debug_enable_pair(int enable);
  * of each convolution kernel overlaps the tail of its predecessor; results are identical). */
 int pdf_debug_enable_pdl(int enable);
 
+/* Timing probe for the generic tcgen05 conv kernel -- outputs are garbage while it is set.  bit 0: the epilogue only hands the
+ * accumulator back (no TMEM read, no stores); bit 1: the MMA issuer skips the MMAs (TMA ring and commits still run); 0 = normal. */
+int pdf_debug_set_conv_probe(int mode);
+
 /* Tuning hook: pdf_preprocess works through the batch in sub-batches of `subjects` volumes (0 = the whole batch at once) so that
  * one sub-batch's resampled volumes stay L2-resident across the histogram passes and the plane gather.  Results are identical. */
 int pdf_debug_set_pre_chunk(int subjects);

@@ -15,8 +15,11 @@
 
 namespace pdf {
 
+static int g_conv_probe = 0;   // pdf_debug_set_conv_probe
+
 struct TcParams {
   int M_total, Cout, Ho, Wo, stride, pad, S, cchunks, num_kb, relu, im2col, out_f32;
+  int probe;            // timing probe (pdf_debug_set_conv_probe): bit 0 = epilogue only hands the accumulator back, bit 1 = no MMAs
   const float* bias;
   const __nv_bfloat16* residual;
   void* out;
@@ -145,6 +148,7 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant
 #pragma unroll
           for (int mt = 0; mt < MT; ++mt) {
             if (mt < n_sub) {
+              if (p.probe & 2) continue;
 #pragma unroll
               for (int k = 0; k < kBlockK / 16; ++k)   // advance 16 bf16 = 32 bytes (2 x 16-byte units) inside the swizzle row
                 umma_f16_lo(d0 + mt * BLOCK_N, a_lo + (uint32_t)(mt * kABytes / 16 + k * 2), b_lo + (uint32_t)(k * 2), idesc,
@@ -187,7 +191,7 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant
 #pragma unroll
       for (int ch = 0; ch < MT * kCPT; ++ch) {
         const int mt = ch / kCPT, c0 = (ch - mt * kCPT) * 32;
-        if (mt >= n_sub) continue;
+        if (mt >= n_sub || (p.probe & 1)) continue;
         const int m = m0 + mt * kBlockM + row;
         const bool mvalid = m < p.M_total;
         {
@@ -476,6 +480,7 @@ static int launch_tc(const TcConv& tc, cudaStream_t s) {
   p.M_total = tc.M_total; p.Cout = tc.Cout; p.Ho = tc.Ho; p.Wo = tc.Wo; p.stride = tc.stride; p.pad = tc.pad; p.S = tc.S;
   p.cchunks = tc.cchunks; p.num_kb = tc.R * tc.S * tc.cchunks; p.relu = tc.relu; p.im2col = tc.im2col; p.out_f32 = tc.out_f32;
   p.bias = tc.bias; p.residual = reinterpret_cast<const __nv_bfloat16*>(tc.residual); p.out = tc.out;
+  p.probe = g_conv_probe;
   const int total_tiles = ceil_div(tc.M_total, kBlockM * MT) * (tc.Cout / BLOCK_N);
   const int ctas_per_sm = max(1, min(2, (int)((225 * 1024) / L::kDynamic)));
   const int grid = max(1, min(total_tiles, num_sms() * ctas_per_sm));
@@ -537,6 +542,13 @@ extern "C" int pdf_selftest_umma_shift(int N, int shift, int mode, const void* d
 /* test hook: 1 = route 3x3 s1 64->64 convs through the generic im2col kernel (A/B comparison of the halo kernel) */
 extern "C" int pdf_debug_disable_halo(int disable) {
   pdf::g_disable_halo = disable != 0;
+  return PDF_OK;
+}
+
+/* timing probe for conv_tc_kernel (results are garbage while set): bit 0 = the epilogue only hands the accumulator back,
+ * bit 1 = the MMA issuer skips the MMAs (TMA ring and commits still run); 0 = normal */
+extern "C" int pdf_debug_set_conv_probe(int mode) {
+  pdf::g_conv_probe = mode;
   return PDF_OK;
 }
 

@@ -121,6 +121,7 @@ PROTOTYPES = {
     "pdf_debug_enable_pair": (C.c_int, [C.c_int]),
     "pdf_debug_set_pre_chunk": (C.c_int, [C.c_int]),
     "pdf_debug_enable_pdl": (C.c_int, [C.c_int]),
+    "pdf_debug_set_conv_probe": (C.c_int, [C.c_int]),
     "pdf_debug_disable_halo": (C.c_int, [C.c_int]),
 }
 
@@ -147,6 +148,8 @@ def load():
         fn.argtypes = args
     if os.environ.get("PDFUSION_B200_PAIR"):             # tuning hook: CTA-pair (cta_group::2) kernel for Cout >= 128 layers
         lib.pdf_debug_enable_pair(int(os.environ["PDFUSION_B200_PAIR"]))
+    if os.environ.get("PDFUSION_B200_CONV_PROBE"):       # timing probe (garbage outputs): see pdf_debug_set_conv_probe
+        lib.pdf_debug_set_conv_probe(int(os.environ["PDFUSION_B200_CONV_PROBE"]))
     if os.environ.get("PDFUSION_B200_NO_PDL"):           # tuning hook: plain stream-ordered launches
         lib.pdf_debug_enable_pdl(0)
     if os.environ.get("PDFUSION_B200_PRE_CHUNK"):        # tuning hook: subjects per preprocessing sub-batch (L2 residency)

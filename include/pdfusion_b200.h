@@ -175,6 +175,12 @@ typedef struct {
   const float* d_bias;    /* per-channel bias / BN shift (NULL = 0) */
   const void* d_residual; /* same layout/dtype as the (bf16|f32) output, or NULL */
   void* d_out;
+  /* bf16 PDF_OP_CONV only, all three NULL otherwise: a 1x1 convolution of the SAME input with the same stride and Cout (a ResNet
+   * BasicBlock's downsample next to its 3x3 pad-1 conv1 -- torchvision resnet.py BasicBlock.forward) computed in the same launch from
+   * the centre-tap tiles.  d_weight2 [K][C] bf16 (BN folded), d_bias2 [K] f32 or NULL, d_out2 [N,ho,wo,K] bf16 (no ReLU). */
+  const void* d_weight2;
+  const float* d_bias2;
+  void* d_out2;
 } pdf_op;
 
 typedef struct pdf_plan pdf_plan; /* opaque: validated ops + pre-encoded TMA descriptors */

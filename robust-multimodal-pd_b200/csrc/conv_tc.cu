@@ -19,6 +19,9 @@ static int g_conv_probe = 0;   // pdf_debug_set_conv_probe
 
 struct TcParams {
   int M_total, Cout, Ho, Wo, stride, pad, S, cchunks, num_kb, relu, im2col, out_f32;
+  int num_kb2;          // DUAL: k-blocks (= Cin/64) of the fused 1x1 convolution that shares the centre-tap A tiles
+  const float* bias2;   // DUAL: its bias, and its bf16 output [M, Cout] (no ReLU, no residual)
+  void* out2;
   int probe;            // timing probe (pdf_debug_set_conv_probe): bit 0 = epilogue only hands the accumulator back, bit 1 = no MMAs
   const float* bias;
   const __nv_bfloat16* residual;
@@ -27,16 +30,17 @@ struct TcParams {
 
 constexpr int kBiasMax = 2048;
 
-template <int BLOCK_N, int STAGES, int MT>
+template <int BLOCK_N, int STAGES, int MT, bool DUAL = false>
 struct SmemLayout {
   static constexpr int kBBytes = BLOCK_N * kBlockK * 2;
   static constexpr int kStage = MT * kABytes + kBBytes;
   static constexpr int kBarOff = STAGES * kStage;
   static constexpr int kNumBars = 2 * STAGES + 4;               // full/empty ring + acc_full[2] + acc_empty[2]
   static constexpr int kBiasOff = kBarOff + kNumBars * 8 + 16;   // f32 bias of every output channel (Cout <= kBiasMax), staged once
-  static constexpr int kTotal = kBiasOff + kBiasMax * 4;
+  static constexpr int kTotal = kBiasOff + (DUAL ? 2 : 1) * kBiasMax * 4;
   static constexpr int kDynamic = kTotal + 1024;                // slack for manual 1024-byte alignment
-  static constexpr int kAccCols = MT * BLOCK_N;                 // TMEM columns of one accumulator set
+  static constexpr int kAccCols = (DUAL ? 2 : 1) * MT * BLOCK_N;   // TMEM columns of one accumulator set (DUAL: main | fused 1x1)
+  static_assert(!DUAL || MT == 1, "the dual kernel uses one 128-row sub-tile per tile");
   static_assert(2 * kAccCols <= 512, "two accumulator sets must fit the 512 TMEM columns");
 };
 
@@ -45,10 +49,15 @@ struct SmemLayout {
 //   two TMEM accumulator sets: the epilogue of tile t overlaps the TMA/MMA mainloop of tile t+1; the smem ring keeps
 //   running across tiles.  Tiles are assigned round-robin (tile = blockIdx.x + i*gridDim.x), m fastest inside an n-tile
 //   so that neighbouring CTAs share the weight tile in L2.
-template <int BLOCK_N, int STAGES, int MT>
+//   DUAL a ResNet BasicBlock's 1x1 stride-s downsample convolution reads exactly the centre-tap A tiles of the block's 3x3 stride-s
+//        conv1: both are computed in one launch -- after the 9*Cin/64 k-blocks of the 3x3 the centre-tap tiles are loaded once
+//        more against the 1x1 weights (tmap_b2) into a second accumulator, and the epilogue writes both outputs.  The separate
+//        downsample launches were pure epilogue (profiles/r01_conv_probe.txt); here their stores hide under the next tile.
+template <int BLOCK_N, int STAGES, int MT, bool DUAL = false>
 __global__ void __launch_bounds__(192)
-conv_tc_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant__ CUtensorMap tmap_b, const TcParams p) {
-  using L = SmemLayout<BLOCK_N, STAGES, MT>;
+conv_tc_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant__ CUtensorMap tmap_b,
+               const __grid_constant__ CUtensorMap tmap_b2, const TcParams p) {
+  using L = SmemLayout<BLOCK_N, STAGES, MT, DUAL>;
   extern __shared__ uint8_t smem_raw[];
   const uint32_t raw_addr = smem_u32(smem_raw);
   const uint32_t base = (raw_addr + 1023u) & ~1023u;          // SWIZZLE_128B tiles need 1024-byte alignment
@@ -68,10 +77,13 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant
   const bool bias_staged = p.bias != nullptr && p.Cout <= kBiasMax;
   if (bias_staged)
     for (int i = threadIdx.x; i < p.Cout; i += blockDim.x) s_bias[i] = __ldg(p.bias + i);
+  if (DUAL)
+    for (int i = threadIdx.x; i < p.Cout; i += blockDim.x) s_bias[kBiasMax + i] = p.bias2 ? __ldg(p.bias2 + i) : 0.f;
 
   if (threadIdx.x == 0) {
     prefetch_tmap(&tmap_a);
     prefetch_tmap(&tmap_b);
+    if (DUAL) prefetch_tmap(&tmap_b2);
     for (int s = 0; s < STAGES; ++s) { mbar_init(bar_full + s * 8, 1); mbar_init(bar_empty + s * 8, 1); }
     for (int a = 0; a < 2; ++a) { mbar_init(bar_accfull + a * 8, 1); mbar_init(bar_accempty + a * 8, 4); }
     fence_barrier_init();
@@ -125,6 +137,16 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant
           tma_load_2d(sb, &tmap_b, bar_full + stage * 8, kb * kBlockK, n0);
           if (++cc == p.cchunks) { cc = 0; ++tap; if (++s == p.S) { s = 0; ++r; } }
         }
+        if (DUAL) {   // centre tap (offset = pad in both directions) once more, against the 1x1 weights
+          for (int kb = 0; kb < p.num_kb2; ++kb, ++g) {
+            const uint32_t stage = g % STAGES, phase = (g / STAGES) & 1u;
+            mbar_wait(bar_empty + stage * 8, phase ^ 1u);
+            mbar_expect_tx(bar_full + stage * 8, tx_bytes);
+            const uint32_t sa = base + stage * L::kStage, sb = sa + MT * kABytes;
+            tma_load_im2col_4d(sa, &tmap_a, bar_full + stage * 8, kb * kBlockK, w0[0], h0[0], n_img[0], (uint16_t)p.pad, (uint16_t)p.pad);
+            tma_load_2d(sb, &tmap_b2, bar_full + stage * 8, kb * kBlockK, n0);
+          }
+        }
       }
     }
   } else if (warp == 1) {
@@ -156,6 +178,18 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant
             }
           }
           umma_commit(bar_empty + stage * 8);   // frees the smem slot once these MMAs have read it
+        }
+        if (DUAL) {
+          for (int kb = 0; kb < p.num_kb2; ++kb, ++g) {
+            const uint32_t stage = g % STAGES, phase = (g / STAGES) & 1u;
+            mbar_wait(bar_full + stage * 8, phase);
+            tc_fence_after();
+            const uint32_t a_lo = smem_desc_lo(base + stage * L::kStage), b_lo = a_lo + (uint32_t)(MT * kABytes / 16);
+#pragma unroll
+            for (int k = 0; k < kBlockK / 16; ++k)
+              umma_f16_lo(d0 + MT * BLOCK_N, a_lo + (uint32_t)(k * 2), b_lo + (uint32_t)(k * 2), idesc, (kb | k) != 0 ? 1u : 0u);
+            umma_commit(bar_empty + stage * 8);
+          }
         }
         umma_commit(bar_accfull + acc * 8);     // accumulators of this tile complete
       }
@@ -240,6 +274,31 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant
                        pack_bf16x2(f[i * 16 + 8], f[i * 16 + 9]), pack_bf16x2(f[i * 16 + 10], f[i * 16 + 11]),
                        pack_bf16x2(f[i * 16 + 12], f[i * 16 + 13]), pack_bf16x2(f[i * 16 + 14], f[i * 16 + 15]));
             }
+          }
+        }
+      }
+      if (DUAL && !(p.probe & 1)) {                 // second accumulator: the fused 1x1 convolution (+bias, no ReLU) -> out2
+        const int m = m0 + row;
+#pragma unroll
+        for (int c0 = 0; c0 < BLOCK_N; c0 += 32) {
+          const int col = n0 + c0;
+          uint32_t v[32];
+          tmem_ld32(tmem_base + ((uint32_t)(quad * 32) << 16) + (uint32_t)(acc * L::kAccCols + MT * BLOCK_N + c0), v);   // (whole warp)
+          if (m < p.M_total) {
+            float f[32];
+#pragma unroll
+            for (int i = 0; i < 32; i += 4) {
+              const float4 b = *reinterpret_cast<const float4*>(s_bias + kBiasMax + col + i);
+              f[i] = __uint_as_float(v[i]) + b.x; f[i + 1] = __uint_as_float(v[i + 1]) + b.y;
+              f[i + 2] = __uint_as_float(v[i + 2]) + b.z; f[i + 3] = __uint_as_float(v[i + 3]) + b.w;
+            }
+            __nv_bfloat16* op = reinterpret_cast<__nv_bfloat16*>(p.out2) + (size_t)m * p.Cout + col;
+#pragma unroll
+            for (int i = 0; i < 2; ++i)
+              stg256(op + i * 16, pack_bf16x2(f[i * 16 + 0], f[i * 16 + 1]), pack_bf16x2(f[i * 16 + 2], f[i * 16 + 3]),
+                     pack_bf16x2(f[i * 16 + 4], f[i * 16 + 5]), pack_bf16x2(f[i * 16 + 6], f[i * 16 + 7]),
+                     pack_bf16x2(f[i * 16 + 8], f[i * 16 + 9]), pack_bf16x2(f[i * 16 + 10], f[i * 16 + 11]),
+                     pack_bf16x2(f[i * 16 + 12], f[i * 16 + 13]), pack_bf16x2(f[i * 16 + 14], f[i * 16 + 15]));
           }
         }
       }
@@ -431,6 +490,20 @@ int prepare_conv_tc(const pdf_op& op, TcConv* tc) {
   tc->cchunks = op.c / kBlockK;
   tc->relu = op.relu; tc->bias = op.d_bias; tc->residual = op.d_residual; tc->out = op.d_out; tc->out_f32 = op.out_f32;
   tc->n_images = op.n;
+  tc->dual = 0;
+  if (op.d_weight2) {   // fused 1x1 downsample (ResNet BasicBlock): see conv_tc_kernel<..., DUAL>
+    PDF_REQUIRE(op.r == 3 && op.s == 3 && op.pad == 1 && op.k % 128 == 0 && op.k <= kBiasMax && op.d_out2 && !op.out_f32 && !op.d_residual,
+                "bf16 conv: a fused 1x1 convolution needs a 3x3 pad-1 host conv with Cout %% 128 == 0, bf16 output, no residual");
+    PDF_REQUIRE((reinterpret_cast<uintptr_t>(op.d_weight2) & 15) == 0 && (reinterpret_cast<uintptr_t>(op.d_out2) & 31) == 0,
+                "bf16 conv: fused 1x1 pointers must be aligned");
+    tc->dual = 1;
+    tc->block_n = 128;
+    tc->bias2 = op.d_bias2;
+    tc->out2 = op.d_out2;
+    if (int rc = encode_im2col(&tc->tmap_a, op)) return rc;
+    if (int rc = encode_2d(&tc->tmap_ds, op.d_weight2, (uint64_t)op.k, (uint64_t)op.c, 128)) return rc;
+    return encode_2d(&tc->tmap_b, op.d_weight, (uint64_t)op.k, (uint64_t)op.r * op.s * op.c, 128);
+  }
   tc->halo = (!g_disable_halo && !op.out_f32 && op.d_bias && halo_eligible(op)) ? 1 : 0;
   if (tc->halo) {
     tc->halo_wp = op.w + 2;
@@ -468,29 +541,33 @@ int prepare_stem_tc(const pdf_op& op, TcConv* tc) {
   return PDF_OK;
 }
 
-template <int BLOCK_N, int STAGES, int MT>
+template <int BLOCK_N, int STAGES, int MT, bool DUAL = false>
 static int launch_tc(const TcConv& tc, cudaStream_t s) {
-  using L = SmemLayout<BLOCK_N, STAGES, MT>;
+  using L = SmemLayout<BLOCK_N, STAGES, MT, DUAL>;
   static bool configured = false;
   if (!configured) {
-    PDF_CHECK_CUDA(cudaFuncSetAttribute(conv_tc_kernel<BLOCK_N, STAGES, MT>, cudaFuncAttributeMaxDynamicSharedMemorySize, L::kDynamic));
+    PDF_CHECK_CUDA(cudaFuncSetAttribute(conv_tc_kernel<BLOCK_N, STAGES, MT, DUAL>, cudaFuncAttributeMaxDynamicSharedMemorySize, L::kDynamic));
     configured = true;
   }
   TcParams p;
   p.M_total = tc.M_total; p.Cout = tc.Cout; p.Ho = tc.Ho; p.Wo = tc.Wo; p.stride = tc.stride; p.pad = tc.pad; p.S = tc.S;
   p.cchunks = tc.cchunks; p.num_kb = tc.R * tc.S * tc.cchunks; p.relu = tc.relu; p.im2col = tc.im2col; p.out_f32 = tc.out_f32;
   p.bias = tc.bias; p.residual = reinterpret_cast<const __nv_bfloat16*>(tc.residual); p.out = tc.out;
+  p.num_kb2 = DUAL ? tc.cchunks : 0; p.bias2 = DUAL ? tc.bias2 : nullptr; p.out2 = DUAL ? tc.out2 : nullptr;
   p.probe = g_conv_probe;
   const int total_tiles = ceil_div(tc.M_total, kBlockM * MT) * (tc.Cout / BLOCK_N);
   const int ctas_per_sm = max(1, min(2, (int)((225 * 1024) / L::kDynamic)));
   const int grid = max(1, min(total_tiles, num_sms() * ctas_per_sm));
-  PDF_CHECK_CUDA(launch_pdl(conv_tc_kernel<BLOCK_N, STAGES, MT>, dim3(grid), dim3(192), (size_t)L::kDynamic, s,
-                            *reinterpret_cast<const CUtensorMap*>(&tc.tmap_a), *reinterpret_cast<const CUtensorMap*>(&tc.tmap_b), p));
+  const CUtensorMap& ta = *reinterpret_cast<const CUtensorMap*>(&tc.tmap_a);
+  const CUtensorMap& tb = *reinterpret_cast<const CUtensorMap*>(&tc.tmap_b);
+  const CUtensorMap& tb2 = DUAL ? *reinterpret_cast<const CUtensorMap*>(&tc.tmap_ds) : tb;
+  PDF_CHECK_CUDA(launch_pdl(conv_tc_kernel<BLOCK_N, STAGES, MT, DUAL>, dim3(grid), dim3(192), (size_t)L::kDynamic, s, ta, tb, tb2, p));
   PDF_CHECK_LAUNCH();
   return PDF_OK;
 }
 
 int launch_conv_tc(const TcConv& tc, cudaStream_t s) {
+  if (tc.dual) return launch_tc<128, 6, 1, true>(tc, s);     // 3x3 conv + the block's 1x1 downsample in one launch
   if (tc.halo) return launch_conv3x3_halo(tc, s);
   if (pair_eligible(tc)) return launch_conv_tc2(tc, s);      // cta_group::2: two SMs per 256-row tile (conv_tc2.cu)
   // two 128-row sub-tiles per CTA when the mainloop is long enough to amortise the single-tile prologue/epilogue and

@@ -16,6 +16,10 @@ struct alignas(64) TensorMapBlob { unsigned char bytes[128]; };
 struct TcConv {
   TensorMapBlob tmap_a, tmap_b;
   TensorMapBlob tmap_b2;   // weight map with a [BLOCK_N/2 x 64] box (one CTA's half of B in the CTA-pair kernel)
+  TensorMapBlob tmap_ds;   // dual kernel: weights [Cout, Cin] of the fused 1x1 convolution
+  int dual;                // 1: the launch also computes that 1x1 convolution of the same input (centre-tap tiles) into out2
+  const float* bias2;
+  void* out2;
   int block_n;      // 64 | 128 | 256
   int im2col;       // 1: A through im2col-mode TMA, 0: plain 2D tile of the [M, C] matrix (1x1 stride-1)
   int M_total, Cout, Ho, Wo, stride, pad, R, S, cchunks, relu;

@@ -54,6 +54,13 @@ extern "C" int pdf_plan_create(pdf_plan** out, const pdf_op* ops, int n_ops) {
     if (rc == PDF_OK && op.kind == PDF_OP_STEM_FUSED) plan->flops += 2.0 * op.n * ((op.h - 1) / 2 + 1) * ((op.w - 1) / 2 + 1) * 64.0 * 49.0;
     if (rc == PDF_OK && op.kind == PDF_OP_CONV) {
       plan->flops += 2.0 * op.n * op.ho * op.wo * (double)op.k * op.r * op.s * op.c;
+      if (op.d_weight2) {
+        plan->flops += 2.0 * op.n * op.ho * op.wo * (double)op.k * op.c;
+        if (op.precision != PDF_PREC_BF16) {
+          set_error("op %d: a fused 1x1 convolution exists on the bf16 path only", i);
+          rc = PDF_ERR_ARG;
+        }
+      }
       if (op.precision == PDF_PREC_BF16) rc = prepare_conv_tc(op, &plan->tc[i]);
     }
     if (rc != PDF_OK) { delete plan; return rc; }

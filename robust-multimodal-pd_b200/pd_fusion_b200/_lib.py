@@ -53,6 +53,7 @@ class Op(C.Structure):
         ("relu", C.c_int32), ("out_f32", C.c_int32),
         ("d_in", C.c_void_p), ("d_weight", C.c_void_p), ("d_scale", C.c_void_p), ("d_bias", C.c_void_p),
         ("d_residual", C.c_void_p), ("d_out", C.c_void_p),
+        ("d_weight2", C.c_void_p), ("d_bias2", C.c_void_p), ("d_out2", C.c_void_p),
     ]
 
 

@@ -9,7 +9,7 @@ from __future__ import annotations
 
 import ctypes as C
 import os
-from typing import Dict, List, Tuple
+from typing import Dict, List, Sequence, Tuple
 
 import torch
 import torch.nn as nn
@@ -163,12 +163,20 @@ def flops_per_image(arch: str, input_size: int = 224, folded_stem: bool = False)
     return total
 
 
-def lower_resnet(arch: str, n: int, S: int, bf16: bool, fused_stem: bool, chunks: List[int], in_bytes: int | None = None):
+# measured (profiles/r01_op_times_dual.txt): stage 2 -21 us, stage 3 -6 us, stage 4 +15 us (its 128-wide tiles re-read A four times)
+DEFAULT_DUAL_STAGES = (2, 3)
+
+
+def lower_resnet(arch: str, n: int, S: int, bf16: bool, fused_stem: bool, chunks: List[int], in_bytes: int | None = None,
+                 dual_stages: Sequence[int] = ()):
     """The network as a flat, ordered list of ops over symbolic buffers.
 
     Returns (ops, extents, final_hw): ops = [(name, fields, refs, weight_name)], where refs maps the pointer fields
     d_in / d_out / d_residual to (buffer, byte offset); extents = bytes each buffer must hold.  Buffers: "input",
     "output", o0..o4 (stage outputs of the chunk being consumed), s0..s3 (scratch inside a stage).
+
+    dual_stages: residual stages (2..4) of a BasicBlock network whose first block computes its 1x1 downsample INSIDE the 3x3 conv1
+    launch (bf16 path; the conv op then carries `_weight2` = the downsample's weight name and a `d_out2` reference).
 
     chunks[k] = images per launch of stage k (0 = stem, 1..4 = residual stages).  The op list is depth-first: a
     stage-k chunk is preceded by the stage-(k-1) chunks that produce its input, so the big early tensors are consumed
@@ -237,12 +245,18 @@ def lower_resnet(arch: str, n: int, S: int, bf16: bool, fused_stem: bool, chunks
         for bi, cvs in enumerate(blocks):
             last_block = bi == len(blocks) - 1
             idn, idn_slot = x, None
+            fuse_down = None
             if "down" in cvs:
                 cv = cvs["down"]
                 idn_slot = free.pop(0)
                 idn = ref(idn_slot, 0, out_bytes(k, count))
-                add(cv["name"], dict(d_in=x, d_out=idn), cv["name"], kind=_lib.OP_CONV, precision=prec, n=count, h=x_h, w=x_h, c=x_c,
-                    k=cv["cout"], r=1, s=1, stride=cv["stride"], pad=0, ho=hw[k], wo=hw[k], relu=0)
+                a = cvs["a"]
+                if (bf16 and kind == "basic" and k in dual_stages and a["k"] == 3 and a["pad"] == 1 and a["stride"] == cv["stride"]
+                        and a["cout"] == cv["cout"] and cv["cout"] % 128 == 0):
+                    fuse_down = cv["name"]                 # computed by conv1's launch from its centre-tap tiles
+                else:
+                    add(cv["name"], dict(d_in=x, d_out=idn), cv["name"], kind=_lib.OP_CONV, precision=prec, n=count, h=x_h, w=x_h, c=x_c,
+                        k=cv["cout"], r=1, s=1, stride=cv["stride"], pad=0, ho=hw[k], wo=hw[k], relu=0)
             t, t_h, t_c, t_slot = x, x_h, x_c, None
             seq = [cvs["a"]] + ([cvs["b"]] if "b" in cvs else []) + [cvs["last"]]
             for cv in seq:
@@ -257,9 +271,13 @@ def lower_resnet(arch: str, n: int, S: int, bf16: bool, fused_stem: bool, chunks
                 refs = dict(d_in=t, d_out=o)
                 if is_last:
                     refs["d_residual"] = idn
+                extra = {}
+                if fuse_down is not None and cv["role"] == "a":
+                    refs["d_out2"] = idn
+                    extra["_weight2"] = fuse_down
                 add(cv["name"], refs, cv["name"], kind=_lib.OP_CONV, precision=prec, n=count, h=t_h, w=t_h, c=t_c, k=cv["cout"],
                     r=cv["k"], s=cv["k"], stride=cv["stride"], pad=cv["pad"], ho=ho, wo=ho, relu=1,
-                    out_f32=1 if (final and bf16) else 0)
+                    out_f32=1 if (final and bf16) else 0, **extra)
                 if t_slot is not None:
                     free.append(t_slot)
                 t, t_h, t_c, t_slot = o, ho, cv["cout"], o_slot
@@ -326,6 +344,9 @@ class ResNetEncoder:
             vals = [int(v) for v in env_chunk.split(",")]
             front_chunk = vals[0] if len(vals) == 1 else vals
         self.front_chunk = front_chunk
+        # residual stages whose 1x1 downsample is computed inside conv1's launch (BasicBlock networks, bf16 path)
+        env_dual = os.environ.get("PDFUSION_B200_DUAL")               # tuning hook: "" = none, "2,3,4" = those stages
+        self.dual_stages = tuple(int(v) for v in env_dual.split(",") if v) if env_dual is not None else DEFAULT_DUAL_STAGES
         sd = {k: v.detach().to("cpu") for k, v in state_dict.items()}
         self._keep: List[torch.Tensor] = []     # device tensors referenced by the plan
         self._build(sd)
@@ -435,7 +456,7 @@ class ResNetEncoder:
             in_bytes = S * S * 3 * 4
         self.output = torch.empty((n, self.emb_dim), dtype=torch.float32, device=self.device)
         self.chunks = self._chunk_sizes(h2, esz)
-        ops, extents, self.final_hw = lower_resnet(self.arch, n, S, self.bf16, self.fused_stem, self.chunks, in_bytes)
+        ops, extents, self.final_hw = lower_resnet(self.arch, n, S, self.bf16, self.fused_stem, self.chunks, in_bytes, self.dual_stages)
         weights = {cv["name"]: self._conv_weights(sd, cv) for cv in conv_list(self.arch)}
 
         self.buffers = {name: torch.empty(nbytes, dtype=torch.uint8, device=self.device) for name, nbytes in extents.items()
@@ -447,8 +468,13 @@ class ResNetEncoder:
         self.op_names: List[str] = []
         for name, kw, refs, wname in ops:
             op = _lib.Op()
+            kw = dict(kw)
+            wname2 = kw.pop("_weight2", None)
             for key, v in kw.items():
                 setattr(op, key, v)
+            if wname2 is not None:
+                w2, _, b2 = weights[wname2]
+                op.d_weight2, op.d_bias2 = w2.data_ptr(), b2.data_ptr()
             for key, (buf, off) in refs.items():
                 setattr(op, key, base[buf] + off)
             if wname is not None:

@@ -196,6 +196,26 @@ def test_pair_kernel_matches_single_cta_kernel():
         assert err <= 1e-5 * ref.abs().max().item(), (key, err)
 
 
+@pytest.mark.parametrize("n,S", [(7, 96), (40, 224), (3, 70)])
+def test_fused_downsample_equals_separate_launches(monkeypatch, n, S):
+    """resnet18's three 1x1 stride-2 downsample convolutions are computed inside the 3x3 stride-2 conv1 launch of their block
+    (same centre-tap A tiles, second TMEM accumulator): the embeddings equal those of the separate launches."""
+    sd = _sd("resnet18")
+    x = (torch.rand(n, S, S, generator=torch.Generator().manual_seed(n)) * 2 - 1).to(torch.bfloat16).cuda()
+    outs = []
+    for dual in ("2,3,4", "", "3"):
+        monkeypatch.setenv("PDFUSION_B200_DUAL", dual)
+        enc = ResNetEncoder(sd, n, S, precision="bf16")
+        assert enc.dual_stages == tuple(int(v) for v in dual.split(",") if v)
+        assert ("layer2.0.downsample.0" in enc.op_names) == (2 not in enc.dual_stages)
+        outs.append(enc.forward(x).clone())
+        torch.cuda.synchronize()
+    ref = outs[1]
+    assert torch.isfinite(ref).all()
+    for o in (outs[0], outs[2]):
+        assert (o - ref).abs().max().item() <= 1e-5 * ref.abs().max().item()
+
+
 def test_umma_shifted_descriptor_probe():
     """Records whether an MMA operand may start at an arbitrary 128-byte row of a resident, 128B-swizzled tile --
     the precondition for halo-resident 3x3 convolutions.  Result goes to gpurun_out/umma_shift_probe.txt."""

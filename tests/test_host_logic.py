@@ -213,33 +213,43 @@ def test_lowered_op_list_computes_the_network(arch, chunks):
 
 
 def test_lowering_bf16_buffers_are_written_before_read():
-    """Structural check of the bf16 / fused-stem op list: every byte an op reads was written by an earlier op."""
+    """Structural check of the bf16 / fused-stem op list: every byte an op reads was written by an earlier op -- also when the
+    BasicBlock downsample convolutions are computed inside conv1's launch (`dual_stages`)."""
     from pd_fusion_b200.backbone import lower_resnet
     for arch in ("resnet18", "resnet50"):
         for fused in (True, False):
-            n, S = 7, 64
-            ops, extents, _ = lower_resnet(arch, n, S, bf16=True, fused_stem=fused, chunks=[2, 2, 4, 4, 7])
-            written = {k: np.zeros(v, dtype=bool) for k, v in extents.items()}
-            written["input"][:] = True
-            for name, f, refs, _ in ops:
-                esz = 2
-                in_elems = f["n"] * f["h"] * f["w"] * f["c"]
-                if f["kind"] == 2 and f.get("out_f32"):
-                    in_bytes = in_elems * 4
-                else:
-                    in_bytes = in_elems * esz
-                buf, off = refs["d_in"]
-                assert written[buf][off:off + in_bytes].all(), (arch, fused, name, "input not produced")
-                if "d_residual" in refs:
-                    rb, ro = refs["d_residual"]
-                    assert written[rb][ro:ro + f["n"] * f["ho"] * f["wo"] * f["k"] * esz].all(), (arch, name, "residual")
-                ob, oo = refs["d_out"]
-                if f["kind"] == 2:
-                    nbytes = f["n"] * f["c"] * 4
-                elif f["kind"] in (1,):
-                    nbytes = f["n"] * f["ho"] * f["wo"] * f["c"] * esz
-                else:
-                    nbytes = f["n"] * f["ho"] * f["wo"] * f["k"] * (4 if f.get("out_f32") else esz)
-                assert (ob, oo) != refs["d_in"] and oo + nbytes <= extents[ob]
-                written[ob][oo:oo + nbytes] = True
-            assert written["output"].all()
+            for dual in ((), (2, 3, 4)):
+                n, S = 7, 64
+                ops, extents, _ = lower_resnet(arch, n, S, bf16=True, fused_stem=fused, chunks=[2, 2, 4, 4, 7], dual_stages=dual)
+                n_down = sum("downsample" in o[0] for o in ops)
+                n_dual = sum("_weight2" in o[1] for o in ops)
+                if arch == "resnet18" and dual:          # BasicBlock: the three downsample convs ride inside conv1
+                    assert n_down == 0 and n_dual > 0 and all("d_out2" in o[2] for o in ops if "_weight2" in o[1])
+                else:                                    # Bottleneck blocks (stride on conv2) cannot share tiles: nothing fused
+                    assert n_dual == 0 and n_down > 0
+                written = {k: np.zeros(v, dtype=bool) for k, v in extents.items()}
+                written["input"][:] = True
+                for name, f, refs, _ in ops:
+                    esz = 2
+                    in_elems = f["n"] * f["h"] * f["w"] * f["c"]
+                    in_bytes = in_elems * (4 if (f["kind"] == 2 and f.get("out_f32")) else esz)
+                    buf, off = refs["d_in"]
+                    assert written[buf][off:off + in_bytes].all(), (arch, fused, name, "input not produced")
+                    if "d_residual" in refs:
+                        rb, ro = refs["d_residual"]
+                        assert written[rb][ro:ro + f["n"] * f["ho"] * f["wo"] * f["k"] * esz].all(), (arch, name, "residual")
+                    ob, oo = refs["d_out"]
+                    if f["kind"] == 2:
+                        nbytes = f["n"] * f["c"] * 4
+                    elif f["kind"] in (1,):
+                        nbytes = f["n"] * f["ho"] * f["wo"] * f["c"] * esz
+                    else:
+                        nbytes = f["n"] * f["ho"] * f["wo"] * f["k"] * (4 if f.get("out_f32") else esz)
+                    assert (ob, oo) != refs["d_in"] and oo + nbytes <= extents[ob]
+                    written[ob][oo:oo + nbytes] = True
+                    if "d_out2" in refs:
+                        b2, o2 = refs["d_out2"]
+                        n2 = f["n"] * f["ho"] * f["wo"] * f["k"] * esz
+                        assert (b2, o2) not in (refs["d_in"], refs["d_out"]) and o2 + n2 <= extents[b2]
+                        written[b2][o2:o2 + n2] = True
+                assert written["output"].all()

@@ -274,7 +274,8 @@ int pdf_selftest_umma_shift(int N, int shift, int mode, const void* d_a_bf16, co
 int pdf_selftest_umma_rate(int N, int iters, int mode, int grid, unsigned long long* d_cycles, pdf_stream_t stream);
 
 /* Tuning / test hook for the CTA-pair kernel (tcgen05.mma.cta_group::2, csrc/conv_tc2.cu): 0 = never, 1 = every eligible
- * Cout >= 128 layer, 2 (default) = only 3x3 layers with 256-wide tiles, where it wins under the power cap. */
+ * Cout >= 128 layer, 2 (default) = only 3x3 layers with 256-wide tiles, where it wins under the power cap,
+ * 3 = 2 plus the resident-weights variant on 128-channel 3x3 layers (measured slower). */
 int pdf_debug_enable_pair(int enable);
 
 /* Tuning / test hook: enable == 0 launches the tcgen05 kernels without programmatic dependent launch (default: on -- the prologue

@@ -71,20 +71,32 @@ __host__ __device__ constexpr uint32_t make_idesc_m256(int n) {
   return (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(n >> 3) << 17) | ((uint32_t)(256 >> 4) << 24);
 }
 
-template <int BLOCK_N, int STAGES>
+constexpr int kBiasMax2 = 2048;
+
+constexpr int kResidentKb = 18;     // BRES: k-blocks of weights kept in shared memory (3x3 x 128 input channels)
+
+// BRES: the layer has ONE n-tile (Cout == BLOCK_N), so every tile multiplies by the same weights: each CTA of the pair keeps its
+// half of them resident (kResidentKb x (BLOCK_N/2) x 128 B = 144 KB at N = 128) and only the activations stream through the
+// ring.  The generic kernels re-fetch the weights for every tile, a third of the L2 -> shared-memory traffic that bounds the
+// 128-channel layers (profiles/r01_conv_probe.txt).  MEASURED SLOWER (profiles/r01_op_times_resident_weights.txt: 187-192 us against
+// 152-173 us for the single-CTA kernel with two M sub-tiles): next to 144 KB of weights only 64 KB of activations are in flight
+// per CTA.  Kept as pair mode 3 (opt-in), parity-tested.
+template <int BLOCK_N, int STAGES, bool BRES = false>
 struct Smem2 {
   static constexpr int kBHalf = (BLOCK_N / 2) * kBlockK * 2;
-  static constexpr int kStage = kABytes + kBHalf;
-  static constexpr int kBarOff = STAGES * kStage;
-  static constexpr int kNumBars = 2 * STAGES + 4;
-  static constexpr int kDynamic = kBarOff + kNumBars * 8 + 16 + 1024;
+  static constexpr int kStage = kABytes + (BRES ? 0 : kBHalf);
+  static constexpr int kResOff = STAGES * kStage;                 // resident weights (BRES)
+  static constexpr int kBarOff = kResOff + (BRES ? kResidentKb * kBHalf : 0);
+  static constexpr int kNumBars = 2 * STAGES + 5;                 // full/empty ring, acc_full[2], acc_empty[2], weights
+  static constexpr int kBiasOff = (kBarOff + kNumBars * 8 + 16 + 15) & ~15;   // f32 bias of every output channel (Cout <= kBiasMax2), staged once
+  static constexpr int kDynamic = kBiasOff + kBiasMax2 * 4 + 1024;
   static_assert(2 * BLOCK_N <= 512, "two accumulator sets must fit the 512 TMEM columns");
 };
 
-template <int BLOCK_N, int STAGES>
+template <int BLOCK_N, int STAGES, bool BRES = false>
 __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(192)
 conv_tc2_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant__ CUtensorMap tmap_b, const Tc2Params p) {
-  using L = Smem2<BLOCK_N, STAGES>;
+  using L = Smem2<BLOCK_N, STAGES, BRES>;
   extern __shared__ uint8_t smem_raw[];
   const uint32_t raw_addr = smem_u32(smem_raw);
   const uint32_t base = (raw_addr + 1023u) & ~1023u;
@@ -93,6 +105,7 @@ conv_tc2_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constan
   const uint32_t bar_empty = bar_full + STAGES * 8;
   const uint32_t bar_accfull = bar_empty + STAGES * 8;
   const uint32_t bar_accempty = bar_accfull + 16;
+  const uint32_t bar_w = bar_accempty + 16;
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(smem + L::kBarOff + L::kNumBars * 8);
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
@@ -101,12 +114,17 @@ conv_tc2_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constan
   const int pair = blockIdx.x >> 1, npairs = gridDim.x >> 1;
   const int m_tiles = (p.M_total + 2 * kBlockM - 1) / (2 * kBlockM);
   const int total_tiles = m_tiles * (p.Cout / BLOCK_N);
+  float* s_bias = reinterpret_cast<float*>(smem + L::kBiasOff);    // as in conv_tc_kernel: no global load per chunk in the epilogue
+  const bool bias_staged = p.bias != nullptr && p.Cout <= kBiasMax2;
+  if (bias_staged)
+    for (int i = threadIdx.x; i < p.Cout; i += blockDim.x) s_bias[i] = __ldg(p.bias + i);
 
   if (threadIdx.x == 0) {
     prefetch_tmap(&tmap_a);
     prefetch_tmap(&tmap_b);
     for (int s = 0; s < STAGES; ++s) { mbar_init(bar_full + s * 8, 1); mbar_init(bar_empty + s * 8, 1); }
     for (int a = 0; a < 2; ++a) { mbar_init(bar_accfull + a * 8, 1); mbar_init(bar_accempty + a * 8, 8); }   // 4 epilogue warps x 2 CTAs
+    mbar_init(bar_w, 1);
     fence_barrier_init();
   }
   if (warp == 1) tmem_alloc_2sm(smem_u32(tmem_slot), 2 * BLOCK_N);
@@ -118,6 +136,12 @@ conv_tc2_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constan
 
   if (warp == 0) {
     if (elect_one()) {
+      if (BRES) {   // this CTA's half of every weight k-block, once; all bytes of the pair are counted on the leader's barrier
+        const uint32_t w_leader = bar_w & kPeerBitMask;
+        if (leader) mbar_expect_tx(bar_w, 2u * (uint32_t)(p.num_kb * L::kBHalf));
+        for (int kb = 0; kb < p.num_kb; ++kb)
+          tma2_load_2d(base + L::kResOff + kb * L::kBHalf, &tmap_b, w_leader, kb * kBlockK, (int)rank * (BLOCK_N / 2));
+      }
       uint32_t g = 0;
       for (int tile = pair; tile < total_tiles; tile += npairs) {
         const int nt = tile / m_tiles, mtile = tile - nt * m_tiles;
@@ -141,7 +165,7 @@ conv_tc2_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constan
           const uint32_t sa = base + stage * L::kStage, sb = sa + kABytes;
           if (p.im2col) tma2_load_im2col_4d(sa, &tmap_a, full_leader, cc * kBlockK, w0, h0, n_img, (uint16_t)s, (uint16_t)r);
           else tma2_load_2d(sa, &tmap_a, full_leader, kb * kBlockK, ms);
-          tma2_load_2d(sb, &tmap_b, full_leader, kb * kBlockK, n0);
+          if (!BRES) tma2_load_2d(sb, &tmap_b, full_leader, kb * kBlockK, n0);
           if (++cc == p.cchunks) { cc = 0; if (++s == p.S) { s = 0; ++r; } }
         }
       }
@@ -151,6 +175,8 @@ conv_tc2_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constan
       constexpr uint32_t idesc = make_idesc_m256(BLOCK_N);
       uint32_t g = 0;
       int it = 0;
+      if (BRES) mbar_wait(bar_w, 0);               // both halves of the resident weights have landed
+      const uint32_t w_lo = smem_desc_lo(base + L::kResOff);
       for (int tile = pair; tile < total_tiles; tile += npairs, ++it) {
         const int acc = it & 1;
         mbar_wait(bar_accempty + acc * 8, ((uint32_t)(it >> 1) & 1u) ^ 1u);   // both CTAs' epilogues drained this accumulator set
@@ -160,7 +186,8 @@ conv_tc2_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constan
           const uint32_t stage = g % STAGES, phase = (g / STAGES) & 1u;
           mbar_wait(bar_full + stage * 8, phase);
           tc_fence_after();
-          const uint32_t a_lo = smem_desc_lo(base + stage * L::kStage), b_lo = a_lo + (uint32_t)(kABytes / 16);
+          const uint32_t a_lo = smem_desc_lo(base + stage * L::kStage);
+          const uint32_t b_lo = BRES ? w_lo + (uint32_t)(kb * (L::kBHalf / 16)) : a_lo + (uint32_t)(kABytes / 16);
 #pragma unroll
           for (int k = 0; k < kBlockK / 16; ++k)
             umma2_f16_lo(d0, a_lo + (uint32_t)(k * 2), b_lo + (uint32_t)(k * 2), idesc, (kb | k) != 0 ? 1u : 0u);
@@ -180,17 +207,23 @@ conv_tc2_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constan
       const int n0 = nt * BLOCK_N;
       const int acc = it & 1;
       const bool mvalid = m < p.M_total;
+      // the whole row's residual is in registers before the wait for the accumulator (see conv_tc_kernel)
+      constexpr int kChunks = BLOCK_N / 32;
+      uint32_t res[kChunks][2][8];
+      if (p.residual && mvalid) {
+#pragma unroll
+        for (int ch = 0; ch < kChunks; ++ch) {
+          const __nv_bfloat16* rp = p.residual + (size_t)m * p.Cout + n0 + ch * 32;
+          ldg256_nc(rp, res[ch][0]);
+          ldg256_nc(rp + 16, res[ch][1]);
+        }
+      }
       mbar_wait(bar_accfull + acc * 8, (uint32_t)(it >> 1) & 1u);
       tc_fence_after();
-#pragma unroll 1
-      for (int c0 = 0; c0 < BLOCK_N; c0 += 32) {
+#pragma unroll
+      for (int ch = 0; ch < kChunks; ++ch) {
+        const int c0 = ch * 32;
         const int col = n0 + c0;
-        uint32_t res[2][8];
-        if (p.residual && mvalid) {
-          const __nv_bfloat16* rp = p.residual + (size_t)m * p.Cout + col;
-          ldg256_nc(rp, res[0]);
-          ldg256_nc(rp + 16, res[1]);
-        }
         uint32_t v[32];
         tmem_ld32(tmem_base + ((uint32_t)(quad * 32) << 16) + (uint32_t)(acc * BLOCK_N + c0), v);
         if (mvalid) {
@@ -200,7 +233,8 @@ conv_tc2_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constan
           if (p.bias) {
 #pragma unroll
             for (int i = 0; i < 32; i += 4) {
-              const float4 b = __ldg(reinterpret_cast<const float4*>(p.bias + col + i));
+              const float4 b = bias_staged ? *reinterpret_cast<const float4*>(s_bias + col + i)
+                                           : __ldg(reinterpret_cast<const float4*>(p.bias + col + i));
               f[i] += b.x; f[i + 1] += b.y; f[i + 2] += b.z; f[i + 3] += b.w;
             }
           }
@@ -208,7 +242,7 @@ conv_tc2_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constan
 #pragma unroll
             for (int i = 0; i < 2; ++i)
 #pragma unroll
-              for (int j = 0; j < 8; ++j) { f[i * 16 + j * 2] += bf16_lo(res[i][j]); f[i * 16 + j * 2 + 1] += bf16_hi(res[i][j]); }
+              for (int j = 0; j < 8; ++j) { f[i * 16 + j * 2] += bf16_lo(res[ch][i][j]); f[i * 16 + j * 2 + 1] += bf16_hi(res[ch][i][j]); }
           }
           if (p.relu) {
 #pragma unroll
@@ -248,22 +282,24 @@ conv_tc2_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constan
 // two M sub-tiles per B tile.  Back to back, however, the conv stack runs into the 1000 W power cap (SM clock 1.4-1.55 GHz,
 // profiles/r01_stack_power.txt): there the pair kernel, which reads half of the B operand from shared memory per CTA, lets
 // layers 3-4 clock ~60 MHz higher and finish 5 % sooner.  Default: pairs for the 256-wide 3x3 layers only.
-static int g_pair_mode = 2;     // 0 off, 1 every eligible Cout >= 128 layer, 2 only 3x3 layers with 256-wide tiles
+static int g_pair_mode = 2;     // 0 off, 1 every eligible Cout >= 128 layer, 2 only 3x3 layers with 256-wide tiles, 3 = 2 + resident weights at N = 128
 
 bool pair_eligible(const TcConv& tc) {
   if (!g_pair_mode || tc.halo) return false;
   if (tc.block_n != 256 && tc.block_n != 128) return false;
   if (g_pair_mode == 2 && (tc.block_n != 256 || tc.R * tc.S == 1)) return false;
+  if (g_pair_mode == 3 && tc.block_n != 256 && !(tc.R * tc.S == 9 && tc.block_n == 128 && tc.Cout == 128 && tc.R * tc.S * tc.cchunks <= kResidentKb)) return false;
+  if (g_pair_mode == 3 && tc.block_n == 256 && tc.R * tc.S == 1) return false;
   const long tiles = (long)ceil_div(tc.M_total, 2 * kBlockM) * (tc.Cout / tc.block_n);
   return tiles >= num_sms() / 2;          // at least one tile per CTA pair
 }
 
-template <int BLOCK_N, int STAGES>
+template <int BLOCK_N, int STAGES, bool BRES = false>
 static int launch_tc2(const TcConv& tc, cudaStream_t s) {
-  using L = Smem2<BLOCK_N, STAGES>;
+  using L = Smem2<BLOCK_N, STAGES, BRES>;
   static bool configured = false;
   if (!configured) {
-    PDF_CHECK_CUDA(cudaFuncSetAttribute(conv_tc2_kernel<BLOCK_N, STAGES>, cudaFuncAttributeMaxDynamicSharedMemorySize, L::kDynamic));
+    PDF_CHECK_CUDA(cudaFuncSetAttribute(conv_tc2_kernel<BLOCK_N, STAGES, BRES>, cudaFuncAttributeMaxDynamicSharedMemorySize, L::kDynamic));
     configured = true;
   }
   Tc2Params p;
@@ -272,8 +308,8 @@ static int launch_tc2(const TcConv& tc, cudaStream_t s) {
   p.bias = tc.bias; p.residual = reinterpret_cast<const __nv_bfloat16*>(tc.residual); p.out = tc.out;
   const int total_tiles = ceil_div(tc.M_total, 2 * kBlockM) * (tc.Cout / BLOCK_N);
   const int pairs = max(1, min(total_tiles, num_sms() / 2));
-  conv_tc2_kernel<BLOCK_N, STAGES><<<2 * pairs, 192, L::kDynamic, s>>>(*reinterpret_cast<const CUtensorMap*>(&tc.tmap_a),
-                                                                       *reinterpret_cast<const CUtensorMap*>(&tc.tmap_b2), p);
+  conv_tc2_kernel<BLOCK_N, STAGES, BRES><<<2 * pairs, 192, L::kDynamic, s>>>(*reinterpret_cast<const CUtensorMap*>(&tc.tmap_a),
+                                                                             *reinterpret_cast<const CUtensorMap*>(&tc.tmap_b2), p);
   PDF_CHECK_LAUNCH();
   return PDF_OK;
 }
@@ -339,8 +375,13 @@ int launch_umma2_rate(int N, int iters, int mode, int pairs, unsigned long long*
   return PDF_OK;
 }
 
+static bool resident_eligible(const TcConv& tc) {      // one n-tile, all weight k-blocks fit next to the activation ring
+  return tc.block_n == 128 && tc.Cout == 128 && tc.R * tc.S * tc.cchunks <= kResidentKb;
+}
+
 int launch_conv_tc2(const TcConv& tc, cudaStream_t s) {
   if (tc.block_n == 256) return launch_tc2<256, 6>(tc, s);
+  if (g_pair_mode == 3 && resident_eligible(tc)) return launch_tc2<128, 4, true>(tc, s);
   return launch_tc2<128, 8>(tc, s);
 }
 

@@ -180,7 +180,7 @@ def test_pair_kernel_matches_single_cta_kernel():
     x = (torch.rand(n, S, S, generator=torch.Generator().manual_seed(5)) * 2 - 1).to(torch.bfloat16).cuda()
     outs = {}
     try:
-        for mode, pdl in ((2, 1), (0, 1), (1, 1), (2, 0)):
+        for mode, pdl in ((2, 1), (0, 1), (1, 1), (2, 0), (3, 1)):       # 3 = + resident-weight pairs on the 128-channel 3x3 layers
             lib.pdf_debug_enable_pair(mode)
             lib.pdf_debug_enable_pdl(pdl)
             enc = ResNetEncoder(sd, n, S, precision="bf16")

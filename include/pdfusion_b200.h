@@ -282,6 +282,11 @@ int pdf_debug_enable_pair(int enable);
  * of each convolution kernel overlaps the tail of its predecessor; results are identical). */
 int pdf_debug_enable_pdl(int enable);
 
+/* Tuning / test hook for the horizontally-shared 3x3 stride-1 kernel (csrc/conv3x3_hs.cu: one activation tile per filter row serves its
+ * three taps): 0 = off, 1 (default) = eligible layers with Cout == 128 and enough tiles for every SM, 2 = every such layer with
+ * Cout % 128 == 0, 3 = 2 whatever the size (tests).  Read when a plan is created. */
+int pdf_debug_set_hs_mode(int mode);
+
 /* Timing probe for the generic tcgen05 conv kernel -- outputs are garbage while it is set.  bit 0: the epilogue only hands the
  * accumulator back (no TMEM read, no stores); bit 1: the MMA issuer skips the MMAs (TMA ring and commits still run); 0 = normal. */
 int pdf_debug_set_conv_probe(int mode);

@@ -439,15 +439,17 @@ static int encode_2d(TensorMapBlob* out, const void* ptr, uint64_t rows, uint64_
   return PDF_OK;
 }
 
-static int encode_im2col(TensorMapBlob* out, const pdf_op& op) {
+// extra_w: widen the base-pixel bounding box by that many columns on the right (conv3x3_hs.cu traverses W + 2 positions per row);
+// pixels: positions per load
+static int encode_im2col(TensorMapBlob* out, const pdf_op& op, int extra_w = 0, int pixels = kBlockM) {
   const cuuint64_t dims[4] = {(cuuint64_t)op.c, (cuuint64_t)op.w, (cuuint64_t)op.h, (cuuint64_t)op.n};
   const cuuint64_t strides[3] = {(cuuint64_t)op.c * 2, (cuuint64_t)op.w * op.c * 2, (cuuint64_t)op.h * op.w * op.c * 2};
   // bounding box of the filter's base pixel: lower = -pad, upper = pad - (filter-1)   [W, H] order as CUTLASS passes them
   const int lower[2] = {-op.pad, -op.pad};
-  const int upper[2] = {op.pad - (op.s - 1), op.pad - (op.r - 1)};
+  const int upper[2] = {op.pad - (op.s - 1) + extra_w, op.pad - (op.r - 1)};
   const cuuint32_t estr[4] = {1, (cuuint32_t)op.stride, (cuuint32_t)op.stride, 1};
   CUresult r = g_encode_im2col(reinterpret_cast<CUtensorMap*>(out), CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 4, const_cast<void*>(op.d_in),
-                               dims, strides, lower, upper, (cuuint32_t)kBlockK, (cuuint32_t)kBlockM, estr,
+                               dims, strides, lower, upper, (cuuint32_t)kBlockK, (cuuint32_t)pixels, estr,
                                CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
                                CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
   PDF_REQUIRE(r == CUDA_SUCCESS, "cuTensorMapEncodeIm2col failed (%d) nhwc=%d,%d,%d,%d rs=%d,%d stride=%d pad=%d", (int)r, op.n,
@@ -502,6 +504,12 @@ int prepare_conv_tc(const pdf_op& op, TcConv* tc) {
     tc->out2 = op.d_out2;
     if (int rc = encode_im2col(&tc->tmap_a, op)) return rc;
     if (int rc = encode_2d(&tc->tmap_ds, op.d_weight2, (uint64_t)op.k, (uint64_t)op.c, 128)) return rc;
+    return encode_2d(&tc->tmap_b, op.d_weight, (uint64_t)op.k, (uint64_t)op.r * op.s * op.c, 128);
+  }
+  tc->hs = 0;
+  if (hs_eligible(op)) {   // 3x3 stride-1: one activation tile per filter row serves its three taps (conv3x3_hs.cu)
+    tc->hs = 1;
+    if (int rc = encode_im2col(&tc->tmap_a, op, 2, kBlockM + 2)) return rc;
     return encode_2d(&tc->tmap_b, op.d_weight, (uint64_t)op.k, (uint64_t)op.r * op.s * op.c, 128);
   }
   tc->halo = (!g_disable_halo && !op.out_f32 && op.d_bias && halo_eligible(op)) ? 1 : 0;
@@ -568,6 +576,7 @@ static int launch_tc(const TcConv& tc, cudaStream_t s) {
 
 int launch_conv_tc(const TcConv& tc, cudaStream_t s) {
   if (tc.dual) return launch_tc<128, 6, 1, true>(tc, s);     // 3x3 conv + the block's 1x1 downsample in one launch
+  if (tc.hs) return launch_conv3x3_hs(tc, s);                // 3x3 stride-1: horizontal taps share one activation tile
   if (tc.halo) return launch_conv3x3_halo(tc, s);
   if (pair_eligible(tc)) return launch_conv_tc2(tc, s);      // cta_group::2: two SMs per 256-row tile (conv_tc2.cu)
   // two 128-row sub-tiles per CTA when the mainloop is long enough to amortise the single-tile prologue/epilogue and

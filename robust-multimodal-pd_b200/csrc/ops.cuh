@@ -27,6 +27,7 @@ struct TcConv {
   const void* residual;   // bf16 [M, Cout]
   void* out;              // bf16 [M, Cout] or f32 when out_f32
   int out_f32;
+  int hs;                 // 1: horizontally-shared 3x3 stride-1 kernel (conv3x3_hs.cu); tmap_a traverses W+2 positions per row
   int halo;               // 1: halo-resident 3x3 kernel (conv3x3_tc.cu); tmap_a is then a 4-D tiled map
   int halo_wp, halo_nr, n_images;
 };
@@ -39,6 +40,8 @@ bool pair_eligible(const TcConv& tc);
 int launch_conv_tc2(const TcConv& tc, cudaStream_t s);   // cta_group::2 pair kernel (conv_tc2.cu)
 int launch_umma2_rate(int N, int iters, int mode, int pairs, unsigned long long* d_cycles, cudaStream_t s);   // probe
 bool halo_eligible(const pdf_op& op);
+bool hs_eligible(const pdf_op& op);
+int launch_conv3x3_hs(const TcConv& tc, cudaStream_t s);
 int launch_conv3x3_halo(const TcConv& tc, cudaStream_t s);
 
 }  // namespace pdf

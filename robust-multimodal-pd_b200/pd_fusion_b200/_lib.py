@@ -123,6 +123,7 @@ PROTOTYPES = {
     "pdf_debug_set_pre_chunk": (C.c_int, [C.c_int]),
     "pdf_debug_enable_pdl": (C.c_int, [C.c_int]),
     "pdf_debug_set_conv_probe": (C.c_int, [C.c_int]),
+    "pdf_debug_set_hs_mode": (C.c_int, [C.c_int]),
     "pdf_debug_disable_halo": (C.c_int, [C.c_int]),
 }
 
@@ -149,6 +150,8 @@ def load():
         fn.argtypes = args
     if os.environ.get("PDFUSION_B200_PAIR"):             # tuning hook: CTA-pair (cta_group::2) kernel for Cout >= 128 layers
         lib.pdf_debug_enable_pair(int(os.environ["PDFUSION_B200_PAIR"]))
+    if os.environ.get("PDFUSION_B200_HS") is not None:   # tuning hook: horizontally-shared 3x3 kernel (0 off, 1 Cout == 128, 2 all)
+        lib.pdf_debug_set_hs_mode(int(os.environ["PDFUSION_B200_HS"]))
     if os.environ.get("PDFUSION_B200_CONV_PROBE"):       # timing probe (garbage outputs): see pdf_debug_set_conv_probe
         lib.pdf_debug_set_conv_probe(int(os.environ["PDFUSION_B200_CONV_PROBE"]))
     if os.environ.get("PDFUSION_B200_NO_PDL"):           # tuning hook: plain stream-ordered launches

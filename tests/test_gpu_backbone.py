@@ -216,6 +216,68 @@ def test_fused_downsample_equals_separate_launches(monkeypatch, n, S):
         assert (o - ref).abs().max().item() <= 1e-5 * ref.abs().max().item()
 
 
+def test_horizontally_shared_conv_equals_generic():
+    """conv3x3_hs.cu: one im2col tile of W+2 positions per filter row serves the three horizontal taps through shifted MMA
+    descriptors (A fetched 3x instead of 9x).  Same K order per output element as the generic kernel: the embeddings agree with
+    the kernel off, on for the 128-channel layers, and on for every eligible layer."""
+    lib = _lib.load()
+    sd = _sd("resnet18")
+    n, S = 200, 224
+    x = (torch.rand(n, S, S, generator=torch.Generator().manual_seed(9)) * 2 - 1).to(torch.bfloat16).cuda()
+    outs = {}
+    try:
+        for mode in (0, 1, 2):
+            lib.pdf_debug_set_hs_mode(mode)
+            enc = ResNetEncoder(sd, n, S, precision="bf16")
+            outs[mode] = enc.forward(x).clone()
+            torch.cuda.synchronize()
+    finally:
+        lib.pdf_debug_set_hs_mode(1)
+    ref = outs[0]
+    assert torch.isfinite(ref).all()
+    for mode in (1, 2):
+        # the taps are accumulated in (row, channel chunk, column) order instead of (row, column, channel chunk): f32 sums differ in the
+        # last bits and a few bf16 activations round the other way -- far inside the 1e-2 contract, far outside what a wrong tap would do
+        rel = ((outs[mode] - ref).norm(dim=1) / ref.norm(dim=1)).max().item()
+        assert rel < 2e-3, (mode, rel)
+
+
+@pytest.mark.parametrize("n,h,c,k,res", [(2, 6, 64, 128, False), (3, 28, 128, 128, True), (7, 14, 256, 256, True), (9, 7, 128, 512, False),
+                                         (40, 28, 128, 128, True)])
+def test_horizontally_shared_conv_single_layer(n, h, c, k, res):
+    """One 3x3 stride-1 layer through conv3x3_hs.cu against an f32 convolution of the same bf16 data (bias, residual, ReLU; one and
+    several n-tiles; tiles that run through image rows and images; more tiles than CTAs)."""
+    import ctypes as C
+    lib = _lib.load()
+    g = torch.Generator().manual_seed(n * 100 + h)
+    x = (torch.randn(n, h, h, c, generator=g) * 0.5).to(torch.bfloat16).cuda()
+    w = (torch.randn(k, 3, 3, c, generator=g) / (3.0 * c ** 0.5)).to(torch.bfloat16).cuda()
+    bias = torch.randn(k, generator=g).cuda()
+    resid = (torch.randn(n, h, h, k, generator=g) * 0.5).to(torch.bfloat16).cuda() if res else None
+    ref = torch.nn.functional.conv2d(x.float().permute(0, 3, 1, 2), w.float().permute(0, 3, 1, 2), bias, padding=1).permute(0, 2, 3, 1)
+    if res:
+        ref = ref + resid.float()
+    ref = torch.relu(ref)
+    out = torch.full((n, h, h, k), float("nan"), dtype=torch.bfloat16, device="cuda")
+    ops = (_lib.Op * 1)()
+    o = ops[0]
+    o.kind, o.precision = _lib.OP_CONV, _lib.PREC_BF16
+    o.n, o.h, o.w, o.c, o.k, o.r, o.s, o.stride, o.pad, o.ho, o.wo, o.relu = n, h, h, c, k, 3, 3, 1, 1, h, h, 1
+    o.d_in, o.d_weight, o.d_bias, o.d_out = x.data_ptr(), w.data_ptr(), bias.data_ptr(), out.data_ptr()
+    o.d_residual = resid.data_ptr() if res else None
+    plan = C.c_void_p()
+    lib.pdf_debug_set_hs_mode(3)                       # every eligible layer, whatever its size
+    try:
+        _lib.check(lib.pdf_plan_create(C.byref(plan), ops, 1))
+        _lib.check(lib.pdf_plan_run(plan, _lib.stream_ptr()))
+        torch.cuda.synchronize()
+    finally:
+        lib.pdf_debug_set_hs_mode(1)
+    lib.pdf_plan_destroy(plan)
+    err = (out.float() - ref).abs().max().item()
+    assert not torch.isnan(out.float()).any() and err <= 2e-2 * max(1.0, ref.abs().max().item()), err
+
+
 def test_umma_shifted_descriptor_probe():
     """Records whether an MMA operand may start at an arbitrary 128-byte row of a resident, 128B-swizzled tile --
     the precondition for halo-resident 3x3 convolutions.  Result goes to gpurun_out/umma_shift_probe.txt."""

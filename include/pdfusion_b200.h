@@ -288,7 +288,8 @@ int pdf_debug_enable_pdl(int enable);
 int pdf_debug_set_hs_mode(int mode);
 
 /* Timing probe for the generic tcgen05 conv kernel -- outputs are garbage while it is set.  bit 0: the epilogue only hands the
- * accumulator back (no TMEM read, no stores); bit 1: the MMA issuer skips the MMAs (TMA ring and commits still run); 0 = normal. */
+ * accumulator back (no TMEM read, no stores); bit 1: the MMA issuer skips the MMAs (TMA ring and commits still run); bit 2: the
+ * epilogue runs without its global stores; 0 = normal. */
 int pdf_debug_set_conv_probe(int mode);
 
 /* Tuning hook: pdf_preprocess works through the batch in sub-batches of `subjects` volumes (0 = the whole batch at once) so that

@@ -8,11 +8,12 @@ from pd_fusion_b200 import _lib
 from pd_fusion_b200.backbone import ResNet2D, ResNetEncoder
 
 a, b = (int(sys.argv[1]), int(sys.argv[2])) if len(sys.argv) > 2 else (0, 1)
+arch = sys.argv[3] if len(sys.argv) > 3 else "resnet18"
 lib = _lib.load()
 torch.manual_seed(1234)
-sd = {k: v for k, v in ResNet2D("resnet18").state_dict().items() if not k.startswith("fc.")}
+sd = {k: v for k, v in ResNet2D(arch).state_dict().items() if not k.startswith("fc.")}
 n = 768
-enc = ResNetEncoder(sd, n, 224, precision="bf16")
+enc = ResNetEncoder(sd, n, 224, precision="bf16", arch=arch)
 enc.input.copy_((torch.rand(n, 224, 224, device="cuda") * 2 - 1).to(torch.bfloat16))
 enc.forward(None)
 torch.cuda.synchronize()
@@ -25,4 +26,4 @@ for rep in range(5):
     e1.record()
     torch.cuda.synchronize()
     best.append(e0.elapsed_time(e1) / 50 * 1e3)
-print(f"ops [{a},{b}): {min(best):.1f} us best, {sorted(best)[2]:.1f} us median of 5 x 50 launches")
+print(f"{arch} {enc.op_names[a]} ops [{a},+{b}): {min(best):.1f} us best, {sorted(best)[2]:.1f} us median of 5 x 50 launches")

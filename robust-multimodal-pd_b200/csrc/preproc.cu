@@ -734,15 +734,19 @@ __global__ void normalize_kernel(const float* __restrict__ zoomed, const float* 
 // axis-2 planes: vol[:, :, idx] has stride T2 between neighbours; copy the selected planes into a compact
 // [B][L2][T0*T1] buffer (coalesced writes) so the resize kernel reads rows.
 __global__ void extract_planes_kernel(const float* __restrict__ zoomed, const int32_t* __restrict__ indices, int lmax,
-                                      int off2, int cnt2, float* __restrict__ planes, int T0, int T1, int T2) {
+                                      int off2, int cnt2, float* __restrict__ planes, int T0, int T1, int T2,
+                                      const float* __restrict__ lohi) {
   const int b = blockIdx.z, l = blockIdx.y;
   const int idx = indices[(size_t)b * lmax + off2 + l];
   if (idx < 0) return;
   const size_t n = (size_t)T0 * T1;
   const float* zb = zoomed + (size_t)b * n * T2 + idx;
   float* pb = planes + ((size_t)b * cnt2 + l) * n;
+  // the p1/p99 clip of `_normalize_volume_for_resnet` is applied here, once per voxel: the resize kernel would otherwise clip each
+  // voxel once per output pixel that taps it (~8x); this kernel is HBM-bound and does it for free
+  const float lo = lohi[4 * (size_t)b], hi = lohi[4 * (size_t)b + 1];
   for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (size_t)gridDim.x * blockDim.x)
-    pb[i] = __ldg(zb + i * T2);
+    pb[i] = fminf(fmaxf(__ldg(zb + i * T2), lo), hi);
 }
 
 struct ResizeArgs {
@@ -844,7 +848,8 @@ resize_kernel(const float* __restrict__ zoomed, const float* __restrict__ planes
 // (the generic kernel above spends ~110 instructions per pixel, mostly on index arithmetic).
 // block (64, 4): x = column group (4 pixels), y = row lane; grid (row bands of kBandRows, slices, subjects).
 constexpr int kBandRows = 32;
-template <int MODE>
+// PRECLIP: every slot reads pre-clipped axis-2 planes (extract_planes_kernel), so the four taps need no clip here.
+template <int MODE, bool PRECLIP>
 __global__ void __launch_bounds__(256)
 resize_band_kernel(const float* __restrict__ zoomed, const float* __restrict__ planes, const float* __restrict__ lohi,
                    const int32_t* __restrict__ indices, const int32_t* __restrict__ nslices, __nv_bfloat16* __restrict__ out, ResizeArgs ra) {
@@ -898,8 +903,11 @@ resize_band_kernel(const float* __restrict__ zoomed, const float* __restrict__ p
     for (int j = 0; j < 4; ++j) {
       float r = 0.0f;
       if (valid && inb[j]) {
-        const float v00 = fminf(fmaxf(__ldg(row0 + x0[j]), lo), hi), v01 = fminf(fmaxf(__ldg(row0 + x1[j]), lo), hi);
-        const float v10 = fminf(fmaxf(__ldg(row1 + x0[j]), lo), hi), v11 = fminf(fmaxf(__ldg(row1 + x1[j]), lo), hi);
+        float v00 = __ldg(row0 + x0[j]), v01 = __ldg(row0 + x1[j]), v10 = __ldg(row1 + x0[j]), v11 = __ldg(row1 + x1[j]);
+        if (!PRECLIP) {
+          v00 = fminf(fmaxf(v00, lo), hi); v01 = fminf(fmaxf(v01, lo), hi);
+          v10 = fminf(fmaxf(v10, lo), hi); v11 = fminf(fmaxf(v11, lo), hi);
+        }
         const float top = __fadd_rn(__fmul_rn(wx0[j], v00), __fmul_rn(wx1[j], v01));
         const float bot = __fadd_rn(__fmul_rn(wx0[j], v10), __fmul_rn(wx1[j], v11));
         const float nrm = __fmul_rn(__fsub_rn(__fadd_rn(__fmul_rn(wy0, top), __fmul_rn(wy1, bot)), lo), inv_den);
@@ -1197,10 +1205,15 @@ static bool launch_resize_band(const ResizeArgs& ra, int out_mode, int batch, co
   if (out_mode == PDF_OUT_F32_NHWC3 || groups > 64) return false;
   const dim3 grid(ceil_div(ra.S, kBandRows), ra.lmax, batch), block(64, 4);
   __nv_bfloat16* o = reinterpret_cast<__nv_bfloat16*>(d_out);
-  if (out_mode == PDF_OUT_BF16_C1_PAD)
-    resize_band_kernel<PDF_OUT_BF16_C1_PAD><<<grid, block, 0, s>>>(d_zoomed, planes, d_lohi, d_indices, d_nslices, o, ra);
-  else
-    resize_band_kernel<PDF_OUT_BF16_C1><<<grid, block, 0, s>>>(d_zoomed, planes, d_lohi, d_indices, d_nslices, o, ra);
+  bool preclip = !ra.ready;                      // all slots on axis 2: their planes were clipped by extract_planes_kernel
+  for (int a = 0; a < ra.n_axes; ++a) preclip = preclip && ra.axes[a] == 2;
+  if (out_mode == PDF_OUT_BF16_C1_PAD) {
+    if (preclip) resize_band_kernel<PDF_OUT_BF16_C1_PAD, true><<<grid, block, 0, s>>>(d_zoomed, planes, d_lohi, d_indices, d_nslices, o, ra);
+    else resize_band_kernel<PDF_OUT_BF16_C1_PAD, false><<<grid, block, 0, s>>>(d_zoomed, planes, d_lohi, d_indices, d_nslices, o, ra);
+  } else {
+    if (preclip) resize_band_kernel<PDF_OUT_BF16_C1, true><<<grid, block, 0, s>>>(d_zoomed, planes, d_lohi, d_indices, d_nslices, o, ra);
+    else resize_band_kernel<PDF_OUT_BF16_C1, false><<<grid, block, 0, s>>>(d_zoomed, planes, d_lohi, d_indices, d_nslices, o, ra);
+  }
   return true;
 }
 }  // namespace pdf
@@ -1236,7 +1249,7 @@ extern "C" int pdf_gather_resize_normalize(const pdf_preproc_cfg* cfg, int batch
     if (cfg->axes[a] == 2) {
       const int xb = max(1, min(ceil_div((long long)T0 * T1, 256 * 4), 64));
       extract_planes_kernel<<<dim3(xb, cfg->counts[a], batch), 256, 0, s>>>(d_zoomed, d_indices, ra.lmax, off, ra.cnt2,
-                                                                            w.planes + (size_t)off2 * T0 * T1, T0, T1, T2);
+                                                                            w.planes + (size_t)off2 * T0 * T1, T0, T1, T2, d_lohi);
       PDF_CHECK_LAUNCH();
       off2 += cfg->counts[a];
     }

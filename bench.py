@@ -42,8 +42,8 @@ WORKLOADS = {
 }
 IN_SHAPE, TARGET, INPUT_SIZE = (256, 256, 176), (160, 160, 160), 224
 METRIC, UNIT = "mri_subjects_per_sec_resnet2d_embed_fuse", "subjects/s"
-# DRAM bytes moved by the tcgen05 conv launches of ONE step, measured with ncu --set full (profiles/r01_ncu_full_conv_final.txt)
-CONV_DRAM_BYTES = {("c2", 32): 6487.6e6}
+# DRAM bytes moved by the tcgen05 conv launches of ONE step, measured with ncu --set full (profiles/r01_ncu_full_step_final.txt)
+CONV_DRAM_BYTES = {("c2", 32): 6538.8e6}
 
 
 def measured_peaks():
@@ -402,7 +402,7 @@ def main():
                      "achieved": tf, "peak": peaks["tf"], "unit": "TFLOP/s", "frac": tf / peaks["tf"],
                      "traffic": CONV_DRAM_BYTES.get((args.workload, B)),
                      "traffic_source": "dram__bytes_read.sum + dram__bytes_write.sum over the conv launches of one step, ncu --set full "
-                                       "(profiles/r01_ncu_full_conv_final.txt); null for configurations that were not captured",
+                                       "(profiles/r01_ncu_full_step_final.txt); null for configurations that were not captured",
                      "peak_source": peaks["src"] + " burst bf16 (the stack runs into the 1000 W power cap at 1.4-1.55 GHz SM clock, "
                                                    "profiles/r01_stack_power.txt, which is the regime of the sustained figure)",
                      "frac_sustained": tf / peaks["tf_sustained"], "peak_sustained": peaks["tf_sustained"],

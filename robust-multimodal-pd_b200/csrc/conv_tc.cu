@@ -8,6 +8,9 @@
 //   warp 1 (one lane)  tcgen05.mma cta_group::1 kind::f16, M=128, N=BLOCK_N, K=16 x4 per stage, accumulator in TMEM
 //   warps 2..5         epilogue: tcgen05.ld 32x32b -> +bias (+residual) (ReLU) -> bf16 (or f32) NHWC store
 //
+// Relatives: conv3x3_tc.cu (64-channel 3x3, halo resident), conv3x3_hs.cu (3x3 stride 1, horizontal taps share a tile),
+// conv_tc2.cu (CTA pairs, cta_group::2), the DUAL instantiation below (3x3 + the block's 1x1 downsample in one launch).
+//
 // Replaces the cuDNN/oneDNN convolutions torchvision's ResNet issues from `model(batch)`
 // (data/openneuro_features.py:260, scripts/build_resnet2d_mil_embeddings.py:152).
 #include "tc_common.cuh"

@@ -1,12 +1,16 @@
 // K1: raw T1 volume -> network input, batched over subjects, HBM-bound.
 //
-//   resample_kernel        nan/inf scrub + trilinear zoom in float64 (scipy order, one f32 rounding)
-//                          + level-0 radix histogram of positive voxels + per-plane maxima (3 axes) + global min
+//   decode_*_kernel        stored NIfTI voxels (any type, x-fastest) -> float32 C-order, nibabel's float64 scaling rule
+//   resample_tma_kernel    nan/inf scrub + trilinear zoom in float64 (scipy order, one f32 rounding), input rows streamed by
+//   (resample_kernel)      cp.async.bulk; + level-0 radix histogram of positive voxels + per-plane maxima (3 axes) + global min
 //   scan_kernel<0|1|2>     per subject: locate the bucket of each of the 4 order statistics numpy.percentile needs
-//   hist_kernel<1|2>       refinement histograms (11 then 8 bits) over the resampled volume
+//   hist_kernel<1>         11-bit refinement histograms over the resampled volume + compaction of the candidate voxels
+//   hist_kernel<2>         8-bit refinement from the candidate list (full scan only when the list overflowed)
 //   finalize (in scan<2>)  numpy lerp -> lo/hi, extents from plane maxima, np.linspace(...).astype(int) indices
-//   extract_planes_kernel  axis-2 planes (stride-T2 gather) -> compact [L2][T0][T1]
-//   resize_kernel          clip/min-max + bilinear (align_corners=False) + (x-mean)/std -> bf16 C1 or f32 NHWC3
+//   extract_planes_kernel  axis-2 planes (stride-T2 gather), clipped to [lo, hi] -> compact [L2][T0][T1]
+//   resize_band_kernel     (clip) + bilinear (align_corners=False) + min-max + (x-mean)/std -> bf16 one channel (padded for the stem)
+//   resize_kernel          the same for the f32 NHWC3 layout and odd sizes
+//   gather_slices / tta    slices themselves and their test-time augmentation (a6)
 //
 // Reference call sites: data/openneuro_features.py:22-32, 121-151, 250-255 (see include/pdfusion_b200.h).
 #include "common.cuh"

@@ -10,8 +10,8 @@
 //     K = t*8 + s, t = 0..10, s = 0..7) that cover conv row 4i+u (variant 0, filter rows at t = 0..6) AND conv row
 //     4i+u+2 (variant 1, the same filter shifted down by 4 patch rows, t = 4..10) of conv column cx;
 //   * lane v*64+c therefore owns, as TMEM COLUMNS, every conv pixel of channel c that the pooled rows 2i+v need:
-//     the 3x3/2 max-pool, bias, ReLU and the bf16 conversion are plain register arithmetic on tcgen05.ld results,
-//     and all 128 lanes do useful work.
+//     the 3x3/2 max-pool, ReLU and the bf16 conversion are plain register arithmetic on tcgen05.ld results, and all 128 lanes
+//     do useful work.  The bias is added by the tensor core: K slots 88/89 of every B row hold 1, the weights carry hi + lo terms.
 //
 //   warps 0..E-1 epilogue (E = kEpiWarps, 4 or 8): tcgen05.ld -> 3x3 max -> ReLU -> bf16 NHWC store.  With E = 8 two warps share
 //                a TMEM lane quarter (warp w and w+4 both own lanes 32*(w%4)..+31) and take half of the accumulator's columns each

@@ -465,6 +465,8 @@ template <int LEVEL>
 __global__ void __launch_bounds__(256)
 scan_kernel(SubjState* __restrict__ states, FinalizeArgs fa, float* __restrict__ lohi, int32_t* __restrict__ indices,
             int32_t* __restrict__ nslices) {
+  pdl_launch_dependents();   // programmatic dependent launch (common.cuh): scheduled under the predecessor's tail,
+  pdl_wait();                // nothing is read before the predecessor has completed
   __shared__ uint32_t s_scan[8];
   __shared__ uint32_t s_bin[kNQ], s_res[kNQ];
   __shared__ float s_lohi[3];
@@ -604,6 +606,8 @@ hist_kernel(const float* __restrict__ zoomed, SubjState* __restrict__ states, si
   constexpr int NB = (LEVEL == 1) ? kH1 : kH2;
   __shared__ uint32_t s_hist[kNQ][NB];
   __shared__ uint32_t s_prefix[kNQ];
+  pdl_launch_dependents();   // programmatic dependent launch (common.cuh): scheduled under the predecessor's tail,
+  pdl_wait();                // nothing is read before the predecessor has completed
   SubjState* st = states + blockIdx.y;
   if (st->n_pos == 0) return;
   const int tid = threadIdx.x;
@@ -740,6 +744,8 @@ __global__ void normalize_kernel(const float* __restrict__ zoomed, const float* 
 __global__ void extract_planes_kernel(const float* __restrict__ zoomed, const int32_t* __restrict__ indices, int lmax,
                                       int off2, int cnt2, float* __restrict__ planes, int T0, int T1, int T2,
                                       const float* __restrict__ lohi) {
+  pdl_launch_dependents();   // programmatic dependent launch (common.cuh): scheduled under the predecessor's tail,
+  pdl_wait();                // nothing is read before the predecessor has completed
   const int b = blockIdx.z, l = blockIdx.y;
   const int idx = indices[(size_t)b * lmax + off2 + l];
   if (idx < 0) return;
@@ -858,6 +864,8 @@ __global__ void __launch_bounds__(256)
 resize_band_kernel(const float* __restrict__ zoomed, const float* __restrict__ planes, const float* __restrict__ lohi,
                    const int32_t* __restrict__ indices, const int32_t* __restrict__ nslices, __nv_bfloat16* __restrict__ out, ResizeArgs ra) {
   constexpr bool PAD = MODE == PDF_OUT_BF16_C1_PAD;
+  pdl_launch_dependents();   // programmatic dependent launch (common.cuh): scheduled under the predecessor's tail,
+  pdl_wait();                // nothing is read before the predecessor has completed
   const int b = blockIdx.z, l = blockIdx.y;
   const int S = ra.S;
   const int gpr = PAD ? (ra.pitch >> 2) : ((S + 3) >> 2);
@@ -1188,15 +1196,15 @@ extern "C" int pdf_select_bounds_indices(const pdf_preproc_cfg* cfg, int batch, 
   }
   const size_t voxels = (size_t)cfg->out_shape[0] * cfg->out_shape[1] * cfg->out_shape[2];
   const int hblocks = max(1, min((int)(voxels / 4 / 256 / 4) + 1, ceil_div(num_sms() * 8, batch)));
-  scan_kernel<0><<<batch, 256, 0, s>>>(w.st, fa, d_lohi, d_indices, d_nslices);
+  PDF_CHECK_CUDA(launch_pdl(scan_kernel<0>, dim3(batch), dim3(256), 0, s, w.st, fa, d_lohi, d_indices, d_nslices));
   PDF_CHECK_LAUNCH();
-  hist_kernel<1><<<dim3(hblocks, batch), 256, 0, s>>>(d_zoomed, w.st, voxels, w.cand, w.cand_cap);
+  PDF_CHECK_CUDA(launch_pdl(hist_kernel<1>, dim3(hblocks, batch), dim3(256), 0, s, d_zoomed, w.st, voxels, w.cand, w.cand_cap));
   PDF_CHECK_LAUNCH();
-  scan_kernel<1><<<batch, 256, 0, s>>>(w.st, fa, d_lohi, d_indices, d_nslices);
+  PDF_CHECK_CUDA(launch_pdl(scan_kernel<1>, dim3(batch), dim3(256), 0, s, w.st, fa, d_lohi, d_indices, d_nslices));
   PDF_CHECK_LAUNCH();
-  hist_kernel<2><<<dim3(hblocks, batch), 256, 0, s>>>(d_zoomed, w.st, voxels, w.cand, w.cand_cap);
+  PDF_CHECK_CUDA(launch_pdl(hist_kernel<2>, dim3(hblocks, batch), dim3(256), 0, s, d_zoomed, w.st, voxels, w.cand, w.cand_cap));
   PDF_CHECK_LAUNCH();
-  scan_kernel<2><<<batch, 256, 0, s>>>(w.st, fa, d_lohi, d_indices, d_nslices);
+  PDF_CHECK_CUDA(launch_pdl(scan_kernel<2>, dim3(batch), dim3(256), 0, s, w.st, fa, d_lohi, d_indices, d_nslices));
   PDF_CHECK_LAUNCH();
   return PDF_OK;
 }
@@ -1252,6 +1260,8 @@ extern "C" int pdf_gather_resize_normalize(const pdf_preproc_cfg* cfg, int batch
   for (int a = 0; a < cfg->n_axes; ++a) {
     if (cfg->axes[a] == 2) {
       const int xb = max(1, min(ceil_div((long long)T0 * T1, 256 * 4), 64));
+      // (plain launch: with programmatic dependent launch the next kernel's blocks would sit on the SMs waiting while this
+      //  multi-wave grid still has blocks to place -- measured 220 -> 403 us for gather + resize)
       extract_planes_kernel<<<dim3(xb, cfg->counts[a], batch), 256, 0, s>>>(d_zoomed, d_indices, ra.lmax, off, ra.cnt2,
                                                                             w.planes + (size_t)off2 * T0 * T1, T0, T1, T2, d_lohi);
       PDF_CHECK_LAUNCH();

@@ -120,6 +120,35 @@ def _read_volume_host(path) -> np.ndarray:
     return np.ascontiguousarray(data.astype(np.float32))
 
 
+class _ReadAhead:
+    """Volumes of manifest rows [lo, hi) read by a small thread pool, `window` rows ahead of the consumer (file I/O and zlib
+    release the GIL; the reference reads serially through nibabel, `data/openneuro_features.py:23-27`).  get(j) returns row j's
+    StoredVolume, blocking until it is there; release(i, j) drops rows [i, j) once they are on the device."""
+
+    def __init__(self, paths, lo: int, hi: int, window: int):
+        from concurrent.futures import ThreadPoolExecutor
+        self.paths, self.hi, self.window = paths, hi, max(1, int(window))
+        n_threads = max(1, int(os.environ.get("PD_FUSION_B200_IO_THREADS", "4")))
+        self.pool = ThreadPoolExecutor(max_workers=n_threads, thread_name_prefix="pdf-read")
+        self.futures: Dict[int, object] = {}
+        self.next = lo
+
+    def _fill(self, upto: int) -> None:
+        while self.next < min(self.hi, upto):
+            self.futures[self.next] = self.pool.submit(_read_volume_stored, self.paths[self.next])
+            self.next += 1
+
+    def get(self, j: int) -> "StoredVolume":
+        self._fill(j + self.window)
+        return self.futures[j].result()                  # a reader's exception (missing file, bad header) surfaces here
+
+    def release(self, i: int, j: int) -> None:
+        for k in range(i, j):
+            self.futures.pop(k, None)
+        if self.next >= self.hi and not self.futures:
+            self.pool.shutdown(wait=False)
+
+
 def _decode_on_device(batch, dev) -> torch.Tensor:
     """Stored voxels of same-keyed volumes -> float32 [B, X, Y, Z] on `dev`: the upload carries the file's bytes (half of the
     float32 array for the usual int16 T1 image), `pdf_decode_volume` does the float64 scaling, the cast and the transpose."""
@@ -247,16 +276,18 @@ def embed_manifest(df: pd.DataFrame, backbone: str, target_shape: Sequence[int],
     nsl = torch.zeros((hi - lo,), dtype=torch.int32, device=dev)
     pipes: Dict[tuple, EmbeddingPipeline] = {}
     paths = df["t1wbrain_path"].tolist()
+    reader = _ReadAhead(paths, lo, hi, window=2 * bsz)     # files are read and gunzipped by worker threads, ahead of the GPU
     i = lo
     while i < hi:
-        first = _read_volume_stored(paths[i])
+        first = reader.get(i)
         batch, j = [first], i + 1
         while j < hi and len(batch) < bsz:
-            nxt = _read_volume_stored(paths[j])
+            nxt = reader.get(j)
             if nxt.key() != first.key():                 # same shape, stored type and scaling: one decode launch
                 break
             batch.append(nxt)
             j += 1
+        reader.release(i, j)
         if first.shape not in pipes:
             pipes[first.shape] = EmbeddingPipeline(sd, first.shape, target_shape, axes, counts, input_size, precision, bsz,
                                                    mean, std, "resnet50" if backbone == "resnet50" else "resnet18", dev)

@@ -107,6 +107,30 @@ def test_nifti_reader_roundtrip(tmp_path):
     assert np.array_equal(_read_volume_host(pb), u16.astype(np.float32))
 
 
+def test_read_ahead_keeps_manifest_order_and_surfaces_errors(tmp_path):
+    """The builders read volume files with worker threads, a window ahead of the GPU: rows come back in manifest order whatever
+    the completion order, released rows are dropped, and a reader's exception reaches the caller (as the reference's would)."""
+    from pd_fusion_b200.data.openneuro_features import _ReadAhead
+    paths = []
+    for i in range(9):
+        p = tmp_path / f"v{i}.npy"
+        np.save(p, (np.arange(24, dtype=np.float32) + i).reshape(2, 3, 4))
+        paths.append(str(p))
+    r = _ReadAhead(paths, 2, 9, window=3)
+    seen, i = [], 2
+    while i < 9:
+        j = min(i + 2, 9)
+        peek = r.get(j) if j < 9 else None            # the batching loop peeks at the first row of the next batch ...
+        seen += [float(r.get(k).voxels[0]) for k in range(i, j)]
+        r.release(i, j)
+        assert peek is None or r.get(j) is peek       # ... and finds the same object when that batch starts
+        i = j
+    assert seen == [2.0, 3.0, 4.0, 5.0, 6.0, 7.0, 8.0] and not r.futures
+    bad = _ReadAhead(paths + [str(tmp_path / "missing.nii.gz")], 9, 10, window=2)
+    with pytest.raises(FileNotFoundError):
+        bad.get(9)
+
+
 def test_flop_accounting_matches_survey():
     assert int(flops_per_image("resnet18")) == 3627122688 and int(flops_per_image("resnet50")) == 8174272512
     assert int(flops_per_image("resnet18") - flops_per_image("resnet18", folded_stem=True)) == 157351936

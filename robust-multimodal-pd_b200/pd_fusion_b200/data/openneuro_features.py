@@ -27,6 +27,7 @@ from ..backbone import RESNET_SPECS, ResNet2D
 from ..parallel import all_gather_rows, shard_range, world
 from ..pipeline import EmbeddingPipeline
 from ..preprocess import VolumePreprocessor
+from ..utils.npz_writer import savez_compressed_parallel
 
 
 def _hash_file(path: Path) -> str:
@@ -351,8 +352,9 @@ def build_resnet2d_mil_embeddings(manifest_path: Path, out_dir: Path, cfg: Dict,
         row, n = embed_manifest.short_bags
         raise ValueError(f"all input arrays must have the same shape: subject row {row} has {n} slices, expected {emb.shape[1]}")
     if world()[0] == 0:
-        np.savez_compressed(out_path, embeddings=emb.astype(np.float32), subject_id=df["subject_id"].values,
-                            session=df["session"].values, label=df["label"].values)
+        # same npz as np.savez_compressed (scripts/build_resnet2d_mil_embeddings.py:162-168), deflated by a thread pool
+        savez_compressed_parallel(out_path, embeddings=emb.astype(np.float32), subject_id=df["subject_id"].values,
+                                  session=df["session"].values, label=df["label"].values)
     return out_path
 
 

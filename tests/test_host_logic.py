@@ -131,6 +131,29 @@ def test_read_ahead_keeps_manifest_order_and_surfaces_errors(tmp_path):
         bad.get(9)
 
 
+def test_parallel_npz_writer_is_read_back_like_numpys(tmp_path):
+    """The MIL cache is written by `savez_compressed_parallel` (deflate spread over threads, pigz-style): every reader sees what
+    np.savez_compressed would have written -- same members, dtypes, values (object arrays included), a sound ZIP."""
+    import zipfile
+    from pd_fusion_b200.utils import npz_writer
+    rng = np.random.default_rng(3)
+    emb = np.maximum(rng.standard_normal((37, 24, 512)).astype(np.float32), 0)            # 1.8 MB
+    big = rng.integers(0, 1000, size=(5, 1 << 20), dtype=np.int32)                      # 20 MB: several chunks ...
+    odd = rng.standard_normal(2 * (8 << 20) // 8 + 12345)                                # ... and one that ends mid-chunk
+    ids = np.array([f"sub-{i:05d}" for i in range(37)], dtype=object)
+    kw = dict(embeddings=emb, big=big, odd=odd, subject_id=ids, session=np.ones(37, dtype=int), label=np.arange(37) % 2, empty=np.zeros((0, 3)))
+    p = npz_writer.savez_compressed_parallel(tmp_path / "cache", threads=3, **kw)
+    assert p.name == "cache.npz" and zipfile.ZipFile(p).testzip() is None
+    np.savez_compressed(tmp_path / "ref.npz", **kw)
+    a, b = np.load(tmp_path / "ref.npz", allow_pickle=True), np.load(p, allow_pickle=True)
+    assert sorted(a.files) == sorted(b.files)
+    for k in a.files:
+        assert a[k].dtype == b[k].dtype and a[k].shape == b[k].shape and np.array_equal(a[k], b[k]), k
+    assert p.stat().st_size < 1.02 * (tmp_path / "ref.npz").stat().st_size              # independent chunks cost next to nothing
+    for m in zipfile.ZipFile(p).infolist():
+        assert m.compress_type == zipfile.ZIP_DEFLATED
+
+
 def test_flop_accounting_matches_survey():
     assert int(flops_per_image("resnet18")) == 3627122688 and int(flops_per_image("resnet50")) == 8174272512
     assert int(flops_per_image("resnet18") - flops_per_image("resnet18", folded_stem=True)) == 157351936

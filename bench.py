@@ -5,12 +5,16 @@
 
 A "step" = one pass of the hot path over one batch of B synthetic subjects per GPU:
 raw T1 volumes f32[256,256,176] resident in HBM -> resample 160^3 -> p1/p99 normalise -> slice select ->
-224x224 network input -> ResNet2D (bf16 tcgen05) -> per-slice embeddings (+ slice mean) [-> all-gather of the
-embedding table when N > 1].  Prints ONE JSON line (rank 0).
+224x224 network input -> ResNet2D (bf16 tcgen05) -> per-slice embeddings (+ slice mean) -> fusion head (ModDrop for c2, gated
+MIL attention for c3) under the 7 missing-modality scenarios of configs/eval_missingness_openneuro_ds001907.yaml [-> all-gather
+of the embedding table and of the per-scenario probabilities when N > 1].  Prints ONE JSON line (rank 0).
 
   value        device-resident throughput (inputs already in HBM), CUDA-event timed, max over ranks
-  e2e          same metric through the public host API (pinned host volumes -> H2D -> hot path -> D2H embeddings)
-  roofline     the dominant kernel family (tcgen05 implicit-GEMM convs): algorithmic FLOPs / CUDA-event time
+  e2e          same metric through the public host API (pinned float32 host volumes -> H2D -> hot path -> D2H results)
+  e2e_stored_int16  the same call fed the voxels as an int16 NIfTI stores them (decoded on the device): half the PCIe bytes
+  roofline     the dominant kernel family (tcgen05 implicit-GEMM convs): algorithmic FLOPs / CUDA-event time, against the burst
+               and the sustained measured bf16 peak, with the DRAM traffic of the same launches (ncu)
+  roofline_preproc  the preprocessing kernels against the measured copy bandwidth (SURVEY.md 8d algorithmic bytes)
   cpu_baseline the oracle port of the reference's CPU path on a bounded sample (rank 0, N = 1 only)
 
 `--impl reference` times the reference's own CPU implementation of the path (oracle port; /root/reference does

@@ -3,6 +3,7 @@ the drop-in cache-name contract, NIfTI decode, FLOP accounting."""
 import gzip
 import json
 import struct
+from pathlib import Path
 
 import numpy as np
 import pandas as pd
@@ -152,6 +153,22 @@ def test_parallel_npz_writer_is_read_back_like_numpys(tmp_path):
     assert p.stat().st_size < 1.02 * (tmp_path / "ref.npz").stat().st_size              # independent chunks cost next to nothing
     for m in zipfile.ZipFile(p).infolist():
         assert m.compress_type == zipfile.ZIP_DEFLATED
+
+
+def test_bench_reference_arm_contract():
+    """`bench.py --impl reference` needs no GPU (it times the reference's CPU path): one JSON line with the arm's keys."""
+    import subprocess
+    import sys
+    root = Path(__file__).resolve().parents[1]
+    out = subprocess.run([sys.executable, str(root / "bench.py"), "--impl", "reference", "--steps", "1", "--warmup", "0"],
+                         capture_output=True, text=True, timeout=600, cwd=root)
+    assert out.returncode == 0, out.stderr[-2000:]
+    line = json.loads(out.stdout.strip().splitlines()[-1])
+    assert line["impl"] == "reference" and line["metric"] == "mri_subjects_per_sec_resnet2d_embed_fuse" and line["unit"] == "subjects/s"
+    assert line["value"] > 0 and line["higher_is_better"] is True and line["n_gpus"] == 1 and line["steps"] == 1
+    assert line["cpu_baseline"]["kind"] == "port" and line["cpu_baseline"]["cores"] >= 1 and line["cpu_baseline"]["value"] == line["value"]
+    assert line["e2e"] == {"value": line["value"], "unit": "subjects/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}
+    assert line["config"]["workload"] == "configs/openneuro_ds001907_resnet2d.yaml"
 
 
 def test_flop_accounting_matches_survey():

@@ -181,11 +181,24 @@ typedef struct {
   const void* d_weight2;
   const float* d_bias2;
   void* d_out2;
+  /* bf16 1x1 PDF_OP_CONV only, all NULL / 0 otherwise: the NEXT 1x1 convolution, chained while the output tile is still on chip
+   * (a ResNet Bottleneck's conv3 + bn3 + add + relu followed by the next block's conv1 + bn1 + relu -- torchvision resnet.py
+   * Bottleneck.forward): d_out3 [N,ho,wo,k3] bf16 = relu(conv1x1(d_out, d_weight3) + d_bias3).  d_weight3 [k3][K] bf16 (BN folded),
+   * k3 in {64, 128, 256}, K % 128 == 0.  d_out is still written (it is the next block's residual). */
+  const void* d_weight3;
+  const float* d_bias3;
+  void* d_out3;
+  int32_t k3;
 } pdf_op;
 
 typedef struct pdf_plan pdf_plan; /* opaque: validated ops + pre-encoded TMA descriptors */
 
 /* validates shapes, encodes the CUtensorMaps of every bf16 conv (needs a CUDA context). */
+/* tuning / A-B hook for the pointwise kernel (conv_pw.cu): 0 = 1x1 convolutions stay on the generic kernel, 1 = default
+ * policy, 2 = every eligible 1x1 convolution.  Affects plans created afterwards. */
+int pdf_debug_set_pw(int mode);
+/* ring depth (2..6) and staging-buffer count (2..4) of conv_pw_kernel launches (the ring shrinks to what fits 227 KB) */
+int pdf_debug_set_pw_config(int stages, int staging_buffers);
 int pdf_plan_create(pdf_plan** out, const pdf_op* ops, int n_ops);
 int pdf_plan_run(const pdf_plan* plan, pdf_stream_t stream);
 /* runs ops [first, first+count) only (per-layer timing / debugging) */

@@ -1,0 +1,439 @@
+// K2 (bf16 path): pointwise (1x1) convolutions of the ResNet50 bottleneck, epilogue through shared memory.
+//
+//   Y[M, Cout] = relu?( X[M, Cin] * W[Cout, Cin]^T + bias (+ R[M, Cout]) )                 bf16 x bf16 -> f32 (TMEM) -> bf16
+//   optional chain:  T[M, N2] = relu( Y[M, Cout] * W3[N2, Cout]^T + bias3 )               (the NEXT block's 1x1 reduce conv)
+//
+// Why a second kernel next to conv_tc.cu: the bottleneck's expansion convs and downsamples have K = 64..512 and N = 256..2048,
+// i.e. a few hundred tensor-pipe cycles per 128 x 128 output tile against 64 KB of residual + output traffic -- they are bound
+// by how the EPILOGUE moves bytes.  conv_tc_kernel's row-per-lane global accesses (every lane of a warp in a different
+// 128-byte line) ran them at 2x their HBM floor (profiles/r01_op_times_resnet50.txt, r01_conv_probe_resnet50.txt).  Here
+//
+//   * the residual tile is fetched by TMA into a 128B-swizzled staging buffer, one unit ahead of the epilogue;
+//   * the epilogue warps read TMEM, add bias + residual (conflict-free 16-byte shared-memory accesses), apply ReLU and write
+//     the bf16 result IN PLACE into the staging buffer;
+//   * one thread hands the buffer to the TMA unit (cp.async.bulk.tensor store): full-line writes, no LSU involvement;
+//   * the same buffer -- it has exactly the K-major SWIZZLE_128B layout of an MMA A operand -- feeds the chained GEMM:
+//     the next block's 1x1 reduce convolution accumulates over the N-chunks of the tile in a third TMEM accumulator, so that
+//     conv never re-reads the (4x wider) block output from HBM: its launch disappears.
+//
+// Work unit = (128-row M tile, NC-column N chunk), N fastest: one CTA owns all chunks of its M tiles (persistent, round-robin).
+//   warp 0 (one lane)  TMA producer: residual tile of unit u | A/B k-blocks of unit u | chained-weight k-blocks of unit u-1
+//   warp 1 (one lane)  tcgen05.mma issuer: main GEMM of unit u, then the chained GEMM of unit u-1 (its Y tile is ready by then)
+//   warps 2..9         epilogue (two warps per TMEM lane quarter, alternating 32-column chunks)
+//
+// Replaces the cuDNN 1x1 convolutions + BatchNorm + add + ReLU torchvision's Bottleneck.forward issues from `model(batch)`
+// (scripts/build_resnet2d_mil_embeddings.py:148-156, data/openneuro_features.py:257-262).
+#include "tc_common.cuh"
+#include "ops.cuh"
+
+namespace pdf {
+
+static int g_pw_mode = 1;   // pdf_debug_set_pw: 0 = never, 1 = default policy, 2 = every eligible 1x1 convolution
+
+constexpr int kPwMaxStages = 6;     // ring depth and staging-buffer count are launch parameters (pdf_debug_set_pw_config)
+constexpr int kPwMaxRy = 4;         // staging buffers (residual in / output out / chained A operand)
+static int g_pw_stages = 0, g_pw_ry = 0;   // 0 = per-launch default (launch_pw)
+constexpr int kPwEpiWarps = 8;
+constexpr int kPwThreads = 64 + 32 * kPwEpiWarps;
+constexpr int kPwBiasMax = 2048;
+
+struct PwParams {
+  int M_total, Cout, K, n_chunks, m_tiles, relu, im2col, has_res;
+  int Ho, Wo, stride;           // im2col (strided 1x1) geometry
+  int N2;                       // chained output channels
+  int stages, nry;              // ring depth, staging buffers
+  const float* bias;
+  const float* bias3;
+  __nv_bfloat16* out3;
+};
+
+template <int NC>
+struct PwSmem {
+  static constexpr int kStageBytes = (NC == 128) ? 32768 : (kABytes + NC * 128);   // NC=128: A | B contiguous = one [256 x 64] chained-weight tile
+  static constexpr int kRyBytes = NC * 256;                                         // 128 rows x NC channels bf16 = NC/64 sub-tiles of 16 KB
+  // layout: ring [stages] | staging [nry] | barriers | TMEM slot | bias
+  static constexpr int kNumBars = 2 * kPwMaxStages + 4 + 3 * kPwMaxRy + 2;
+  static constexpr int kTail = kNumBars * 8 + 16 + 16 + (kPwBiasMax + 256) * 4;
+  static int dynamic_bytes(int stages, int nry) { return stages * kStageBytes + nry * kRyBytes + kTail + 1024; }
+};
+
+__device__ __forceinline__ void tma_store_2d(const void* tmap, uint32_t src, int c0, int c1) {
+  asm volatile("cp.async.bulk.tensor.2d.global.shared::cta.bulk_group [%0, {%2, %3}], [%1];"
+               ::"l"(reinterpret_cast<uint64_t>(tmap)), "r"(src), "r"(c0), "r"(c1) : "memory");
+}
+__device__ __forceinline__ void bulk_commit() { asm volatile("cp.async.bulk.commit_group;" ::: "memory"); }
+template <int N>
+__device__ __forceinline__ void bulk_wait_read() { asm volatile("cp.async.bulk.wait_group.read %0;" ::"n"(N) : "memory"); }
+__device__ __forceinline__ void bulk_wait_all() { asm volatile("cp.async.bulk.wait_group 0;" ::: "memory"); }
+__device__ __forceinline__ void mbar_arrive(uint32_t bar) { asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(bar) : "memory"); }
+__device__ __forceinline__ void epi_bar_sync() { asm volatile("bar.sync 1, %0;" ::"n"(32 * kPwEpiWarps) : "memory"); }
+__device__ __forceinline__ uint4 lds128(uint32_t a) {
+  uint4 v;
+  asm volatile("ld.shared.v4.b32 {%0,%1,%2,%3}, [%4];" : "=r"(v.x), "=r"(v.y), "=r"(v.z), "=r"(v.w) : "r"(a));
+  return v;
+}
+__device__ __forceinline__ void sts128(uint32_t a, uint4 v) {
+  asm volatile("st.shared.v4.b32 [%0], {%1,%2,%3,%4};" ::"r"(a), "r"(v.x), "r"(v.y), "r"(v.z), "r"(v.w) : "memory");
+}
+
+template <int NC, bool CHAIN>
+__global__ void __launch_bounds__(kPwThreads, 1)
+conv_pw_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant__ CUtensorMap tmap_b,
+               const __grid_constant__ CUtensorMap tmap_out, const __grid_constant__ CUtensorMap tmap_res,
+               const __grid_constant__ CUtensorMap tmap_w3, const PwParams p) {
+  using L = PwSmem<NC>;
+  constexpr int kSub = NC / 64;                   // 64-channel sub-tiles of a staging buffer
+  extern __shared__ uint8_t smem_raw[];
+  const uint32_t raw_addr = smem_u32(smem_raw);
+  const uint32_t base = (raw_addr + 1023u) & ~1023u;
+  uint8_t* smem = smem_raw + (base - raw_addr);
+  const int kPwStages = p.stages, kPwRy = p.nry;
+  const uint32_t s_ring = base, s_ry = base + (uint32_t)(kPwStages * L::kStageBytes);
+  const uint32_t bar_off = (uint32_t)(kPwStages * L::kStageBytes + kPwRy * L::kRyBytes);
+  const uint32_t bar_full = base + bar_off;
+  const uint32_t bar_empty = bar_full + 8 * kPwMaxStages;
+  const uint32_t bar_accfull = bar_empty + 8 * kPwMaxStages;
+  const uint32_t bar_accempty = bar_accfull + 16;
+  const uint32_t bar_resfull = bar_accempty + 16;
+  const uint32_t bar_ryfree = bar_resfull + 8 * kPwMaxRy;
+  const uint32_t bar_yready = bar_ryfree + 8 * kPwMaxRy;
+  const uint32_t bar_acc2full = bar_yready + 8 * kPwMaxRy;
+  const uint32_t bar_acc2empty = bar_acc2full + 8;
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(smem + bar_off + L::kNumBars * 8);
+  float* s_bias = reinterpret_cast<float*>(smem + bar_off + L::kNumBars * 8 + 16);
+  float* s_bias3 = s_bias + kPwBiasMax;
+
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  for (int i = threadIdx.x; i < p.Cout; i += blockDim.x) s_bias[i] = p.bias ? __ldg(p.bias + i) : 0.f;
+  if (CHAIN)
+    for (int i = threadIdx.x; i < p.N2; i += blockDim.x) s_bias3[i] = p.bias3 ? __ldg(p.bias3 + i) : 0.f;
+
+  if (threadIdx.x == 0) {
+    prefetch_tmap(&tmap_a); prefetch_tmap(&tmap_b); prefetch_tmap(&tmap_out);
+    if (p.has_res) prefetch_tmap(&tmap_res);
+    if (CHAIN) prefetch_tmap(&tmap_w3);
+    for (int s = 0; s < kPwStages; ++s) { mbar_init(bar_full + 8 * s, 1); mbar_init(bar_empty + 8 * s, 1); }
+    for (int a = 0; a < 2; ++a) { mbar_init(bar_accfull + 8 * a, 1); mbar_init(bar_accempty + 8 * a, kPwEpiWarps); }
+    for (int b = 0; b < kPwRy; ++b) {
+      mbar_init(bar_resfull + 8 * b, 1);
+      mbar_init(bar_ryfree + 8 * b, CHAIN ? 2 : 1);     // TMA store has read the buffer (+ the chained MMAs have)
+      mbar_init(bar_yready + 8 * b, 1);
+    }
+    mbar_init(bar_acc2full, 1);
+    mbar_init(bar_acc2empty, kPwEpiWarps);
+    fence_barrier_init();
+  }
+  constexpr uint32_t kTmemCols = CHAIN ? 512 : 2 * NC;
+  if (warp == 1) tmem_alloc(smem_u32(tmem_slot), kTmemCols);
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_slot;
+  const uint32_t tmem_acc2 = tmem_base + 2 * NC;
+  pdl_launch_dependents();
+  pdl_wait();
+
+  const int my_tiles = (p.m_tiles - (int)blockIdx.x + (int)gridDim.x - 1) / (int)gridDim.x;   // M tiles of this CTA
+  const int n_units = my_tiles * p.n_chunks;
+  const int num_kb = p.K / kBlockK;
+
+  if (warp == 0) {
+    if (elect_one()) {
+      uint32_t g = 0;
+      auto ring_wait = [&](uint32_t& stage) {
+        stage = g % kPwStages;
+        mbar_wait(bar_empty + 8 * stage, ((g / kPwStages) & 1u) ^ 1u);
+        ++g;
+      };
+      auto load_chain = [&](int v) {                // chained-weight k-blocks of unit v: W3[:, nc*NC + j*64 .. +64]
+        const int nc = v % p.n_chunks;
+        for (int j = 0; j < kSub; ++j) {
+          uint32_t stage;
+          ring_wait(stage);
+          mbar_expect_tx(bar_full + 8 * stage, (uint32_t)p.N2 * 128u);
+          tma_load_2d(s_ring + stage * L::kStageBytes + (p.N2 > 128 ? 0 : kABytes), &tmap_w3, bar_full + 8 * stage, nc * NC + j * 64, 0);
+        }
+      };
+      for (int u = 0; u < n_units; ++u) {
+        const int ti = u / p.n_chunks, nc = u - ti * p.n_chunks;
+        const int m0 = ((int)blockIdx.x + ti * (int)gridDim.x) * kBlockM, n0 = nc * NC;
+        if (p.has_res) {
+          const int b = u % kPwRy;
+          mbar_wait(bar_ryfree + 8 * b, (((uint32_t)(u / kPwRy)) & 1u) ^ 1u);
+          mbar_expect_tx(bar_resfull + 8 * b, (uint32_t)L::kRyBytes);
+          for (int s = 0; s < kSub; ++s) tma_load_2d(s_ry + b * L::kRyBytes + s * kABytes, &tmap_res, bar_resfull + 8 * b, n0 + s * 64, m0);
+        }
+        int n_img = 0, w0 = 0, h0 = 0;
+        if (p.im2col) {
+          const int hw = p.Ho * p.Wo;
+          n_img = m0 / hw;
+          const int rem = m0 - n_img * hw;
+          const int pp = rem / p.Wo, qq = rem - pp * p.Wo;
+          w0 = qq * p.stride; h0 = pp * p.stride;
+        }
+        for (int kb = 0; kb < num_kb; ++kb) {
+          uint32_t stage;
+          ring_wait(stage);
+          mbar_expect_tx(bar_full + 8 * stage, (uint32_t)(kABytes + NC * 128));
+          const uint32_t sa = s_ring + stage * L::kStageBytes;
+          if (p.im2col) tma_load_im2col_4d(sa, &tmap_a, bar_full + 8 * stage, kb * kBlockK, w0, h0, n_img, 0, 0);
+          else tma_load_2d(sa, &tmap_a, bar_full + 8 * stage, kb * kBlockK, m0);
+          tma_load_2d(sa + kABytes, &tmap_b, bar_full + 8 * stage, kb * kBlockK, n0);
+        }
+        if (CHAIN && u > 0) load_chain(u - 1);
+      }
+      if (CHAIN && n_units > 0) load_chain(n_units - 1);
+    }
+  } else if (warp == 1) {
+    if (elect_one()) {
+      constexpr uint32_t idesc = make_idesc(NC);
+      const uint32_t idesc2 = make_idesc(CHAIN ? p.N2 : NC);
+      uint32_t g = 0;
+      auto do_chain = [&](int v) {                  // acc2 (+)= Y tile of unit v (staging buffer) x chained weights
+        const int ti = v / p.n_chunks, nc = v - ti * p.n_chunks;
+        const int b = v % kPwRy;
+        if (nc == 0) { mbar_wait(bar_acc2empty, ((uint32_t)ti & 1u) ^ 1u); }
+        mbar_wait(bar_yready + 8 * b, ((uint32_t)(v / kPwRy)) & 1u);
+        tc_fence_after();
+        for (int j = 0; j < kSub; ++j, ++g) {
+          const uint32_t stage = g % kPwStages;
+          mbar_wait(bar_full + 8 * stage, (g / kPwStages) & 1u);
+          tc_fence_after();
+          const uint32_t a_lo = smem_desc_lo(s_ry + b * L::kRyBytes + j * kABytes);
+          const uint32_t b_lo = smem_desc_lo(s_ring + stage * L::kStageBytes + (p.N2 > 128 ? 0 : kABytes));
+#pragma unroll
+          for (int k = 0; k < kBlockK / 16; ++k)
+            umma_f16_lo(tmem_acc2, a_lo + (uint32_t)(k * 2), b_lo + (uint32_t)(k * 2), idesc2, (nc | j | k) != 0 ? 1u : 0u);
+          umma_commit(bar_empty + 8 * stage);
+        }
+        umma_commit(bar_ryfree + 8 * b);
+        if (nc == p.n_chunks - 1) umma_commit(bar_acc2full);
+      };
+      for (int u = 0; u < n_units; ++u) {
+        const int acc = u & 1;
+        mbar_wait(bar_accempty + 8 * acc, (((uint32_t)(u >> 1)) & 1u) ^ 1u);
+        tc_fence_after();
+        const uint32_t d0 = tmem_base + (uint32_t)(acc * NC);
+        for (int kb = 0; kb < num_kb; ++kb, ++g) {
+          const uint32_t stage = g % kPwStages;
+          mbar_wait(bar_full + 8 * stage, (g / kPwStages) & 1u);
+          tc_fence_after();
+          const uint32_t a_lo = smem_desc_lo(s_ring + stage * L::kStageBytes), b_lo = a_lo + (uint32_t)(kABytes / 16);
+#pragma unroll
+          for (int k = 0; k < kBlockK / 16; ++k)
+            umma_f16_lo(d0, a_lo + (uint32_t)(k * 2), b_lo + (uint32_t)(k * 2), idesc, (kb | k) != 0 ? 1u : 0u);
+          umma_commit(bar_empty + 8 * stage);
+        }
+        umma_commit(bar_accfull + 8 * acc);
+        if (CHAIN && u > 0) do_chain(u - 1);
+      }
+      if (CHAIN && n_units > 0) do_chain(n_units - 1);
+    }
+  } else {
+    const int ew = warp - 2;                        // 0..7
+    const int quad = warp & 3;                      // TMEM lane quarter this warp may read
+    const int half = ew >> 2;                       // which 32-column chunks (alternating) this warp handles
+    const int row = quad * 32 + lane;
+    const uint32_t row_off = (uint32_t)row * 128u;
+    const uint32_t sw = (uint32_t)(row & 7);
+    const bool leader = (ew == 0 && lane == 0);
+    constexpr int kChunks = NC / 32;
+
+    auto acc2_epilogue = [&](int ti) {              // chained conv output of M tile ti: relu(acc2 + bias3) -> out3 (bf16)
+      mbar_wait(bar_acc2full, (uint32_t)ti & 1u);
+      tc_fence_after();
+      const int m = ((int)blockIdx.x + ti * (int)gridDim.x) * kBlockM + row;
+      const int chunks2 = p.N2 / 32;
+      for (int ch = half; ch < chunks2; ch += 2) {
+        uint32_t v[32];
+        tmem_ld32(tmem_acc2 + ((uint32_t)(quad * 32) << 16) + (uint32_t)(ch * 32), v);
+        if (m < p.M_total) {
+          float f[32];
+#pragma unroll
+          for (int i = 0; i < 32; i += 4) {
+            const float4 b = *reinterpret_cast<const float4*>(s_bias3 + ch * 32 + i);
+            f[i] = fmaxf(__uint_as_float(v[i]) + b.x, 0.f); f[i + 1] = fmaxf(__uint_as_float(v[i + 1]) + b.y, 0.f);
+            f[i + 2] = fmaxf(__uint_as_float(v[i + 2]) + b.z, 0.f); f[i + 3] = fmaxf(__uint_as_float(v[i + 3]) + b.w, 0.f);
+          }
+          __nv_bfloat16* op = p.out3 + (size_t)m * p.N2 + ch * 32;
+#pragma unroll
+          for (int i = 0; i < 2; ++i)
+            stg256(op + i * 16, pack_bf16x2(f[i * 16 + 0], f[i * 16 + 1]), pack_bf16x2(f[i * 16 + 2], f[i * 16 + 3]),
+                   pack_bf16x2(f[i * 16 + 4], f[i * 16 + 5]), pack_bf16x2(f[i * 16 + 6], f[i * 16 + 7]),
+                   pack_bf16x2(f[i * 16 + 8], f[i * 16 + 9]), pack_bf16x2(f[i * 16 + 10], f[i * 16 + 11]),
+                   pack_bf16x2(f[i * 16 + 12], f[i * 16 + 13]), pack_bf16x2(f[i * 16 + 14], f[i * 16 + 15]));
+        }
+      }
+      tc_fence_before();
+      __syncwarp();
+      if (lane == 0) mbar_arrive(bar_acc2empty);
+    };
+
+    for (int u = 0; u < n_units; ++u) {
+      const int ti = u / p.n_chunks, nc = u - ti * p.n_chunks;
+      const int m0 = ((int)blockIdx.x + ti * (int)gridDim.x) * kBlockM, n0 = nc * NC;
+      const int b = u % kPwRy, acc = u & 1;
+      const uint32_t ry = s_ry + b * L::kRyBytes;
+      if (p.has_res) mbar_wait(bar_resfull + 8 * b, ((uint32_t)(u / kPwRy)) & 1u);
+      else mbar_wait(bar_ryfree + 8 * b, (((uint32_t)(u / kPwRy)) & 1u) ^ 1u);
+      mbar_wait(bar_accfull + 8 * acc, ((uint32_t)(u >> 1)) & 1u);
+      tc_fence_after();
+#pragma unroll
+      for (int ci = 0; ci < kChunks / 2; ++ci) {
+        const int ch = ci * 2 + half;
+        uint32_t v[32];
+        tmem_ld32(tmem_base + ((uint32_t)(quad * 32) << 16) + (uint32_t)(acc * NC + ch * 32), v);
+        const uint32_t sub = ry + (uint32_t)(ch >> 1) * kABytes + row_off;      // 64-channel sub-tile, this thread's 128-byte row
+        const float* bp = s_bias + n0 + ch * 32;
+#pragma unroll
+        for (int q = 0; q < 4; ++q) {                                          // 8 channels = one 16-byte unit
+          const uint32_t addr = sub + ((((uint32_t)((ch & 1) * 4 + q)) ^ sw) << 4);
+          const float4 b0 = *reinterpret_cast<const float4*>(bp + q * 8), b1 = *reinterpret_cast<const float4*>(bp + q * 8 + 4);
+          float f0 = __uint_as_float(v[q * 8 + 0]) + b0.x, f1 = __uint_as_float(v[q * 8 + 1]) + b0.y;
+          float f2 = __uint_as_float(v[q * 8 + 2]) + b0.z, f3 = __uint_as_float(v[q * 8 + 3]) + b0.w;
+          float f4 = __uint_as_float(v[q * 8 + 4]) + b1.x, f5 = __uint_as_float(v[q * 8 + 5]) + b1.y;
+          float f6 = __uint_as_float(v[q * 8 + 6]) + b1.z, f7 = __uint_as_float(v[q * 8 + 7]) + b1.w;
+          if (p.has_res) {
+            const uint4 r = lds128(addr);
+            f0 += bf16_lo(r.x); f1 += bf16_hi(r.x); f2 += bf16_lo(r.y); f3 += bf16_hi(r.y);
+            f4 += bf16_lo(r.z); f5 += bf16_hi(r.z); f6 += bf16_lo(r.w); f7 += bf16_hi(r.w);
+          }
+          if (p.relu) {
+            f0 = fmaxf(f0, 0.f); f1 = fmaxf(f1, 0.f); f2 = fmaxf(f2, 0.f); f3 = fmaxf(f3, 0.f);
+            f4 = fmaxf(f4, 0.f); f5 = fmaxf(f5, 0.f); f6 = fmaxf(f6, 0.f); f7 = fmaxf(f7, 0.f);
+          }
+          uint4 o;
+          o.x = pack_bf16x2(f0, f1); o.y = pack_bf16x2(f2, f3); o.z = pack_bf16x2(f4, f5); o.w = pack_bf16x2(f6, f7);
+          sts128(addr, o);
+        }
+      }
+      tc_fence_before();
+      __syncwarp();
+      if (lane == 0) mbar_arrive(bar_accempty + 8 * acc);        // the MMA issuer may overwrite this accumulator
+      if (leader && u > 0) {                                     // the PREVIOUS unit's store was issued a whole tile of arithmetic ago: it
+        bulk_wait_read<0>();                                     // has read its staging buffer -- hand the buffer back now (not after this
+        mbar_arrive(bar_ryfree + 8 * ((u - 1) % kPwRy));         // unit's store), the next residual tile streams in under the rest
+      }
+      fence_proxy_async();                                       // staging-buffer writes -> visible to the TMA unit / tensor core
+      epi_bar_sync();
+      if (leader) {
+#pragma unroll
+        for (int s = 0; s < kSub; ++s) tma_store_2d(&tmap_out, ry + s * kABytes, n0 + s * 64, m0);
+        bulk_commit();
+        if (CHAIN) mbar_arrive(bar_yready + 8 * b);
+      }
+      // the chained accumulator of the previous M tile is complete once the chained MMAs of its last chunk (issued after the
+      // main MMAs of THIS unit) have run
+      if (CHAIN && nc == 0 && ti > 0) acc2_epilogue(ti - 1);
+    }
+    if (CHAIN && my_tiles > 0) acc2_epilogue(my_tiles - 1);
+    if (leader) bulk_wait_all();
+  }
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 1) tmem_dealloc(tmem_base, kTmemCols);
+}
+
+// ---------------------------------------------------------------------------------------- host side
+bool pw_eligible(const pdf_op& op) {
+  if (g_pw_mode == 0) return false;
+  if (!(op.kind == PDF_OP_CONV && op.precision == PDF_PREC_BF16 && op.r == 1 && op.s == 1 && op.pad == 0 && !op.out_f32 && !op.d_weight2))
+    return false;
+  if (op.c % 64 != 0 || op.k % 64 != 0 || op.k > kPwBiasMax) return false;
+  if (op.d_weight3) return true;
+  if (g_pw_mode == 2) return true;
+  // default policy (profiles/r02_op_times_resnet50_pw*.txt): every N chunk of a tile re-streams the A tile, so long-K reduce
+  // convs and downsamples stay on conv_tc_kernel's 256-wide tiles; the epilogue-bound short-K launches come here
+  if (op.c <= 256) return true;
+  return op.d_residual != nullptr && op.c <= 512;
+}
+
+int prepare_conv_pw(const pdf_op& op, TcConv* tc) {
+  if (int rc = load_driver_entry_points()) return rc;
+  const int NC = (op.k % 128 == 0) ? 128 : 64;
+  PDF_REQUIRE((reinterpret_cast<uintptr_t>(op.d_in) & 15) == 0 && (reinterpret_cast<uintptr_t>(op.d_weight) & 15) == 0 &&
+              (reinterpret_cast<uintptr_t>(op.d_out) & 15) == 0 && (reinterpret_cast<uintptr_t>(op.d_residual) & 15) == 0,
+              "pointwise conv: pointers must be 16-byte aligned");
+  tc->pw = NC;
+  tc->Cin = op.c;
+  tc->M_total = op.n * op.ho * op.wo;
+  tc->Cout = op.k; tc->Ho = op.ho; tc->Wo = op.wo; tc->stride = op.stride; tc->pad = 0; tc->R = 1; tc->S = 1;
+  tc->cchunks = op.c / kBlockK;
+  tc->relu = op.relu; tc->bias = op.d_bias; tc->residual = op.d_residual; tc->out = op.d_out; tc->out_f32 = 0;
+  tc->n_images = op.n;
+  tc->im2col = op.stride != 1;
+  tc->k3 = 0; tc->bias3 = nullptr; tc->out3 = nullptr;
+  if (tc->im2col) {
+    if (int rc = encode_im2col(&tc->tmap_a, op)) return rc;
+  } else {
+    if (int rc = encode_2d(&tc->tmap_a, op.d_in, (uint64_t)tc->M_total, (uint64_t)op.c, kBlockM)) return rc;
+  }
+  if (int rc = encode_2d(&tc->tmap_b, op.d_weight, (uint64_t)op.k, (uint64_t)op.c, (uint32_t)NC)) return rc;
+  if (int rc = encode_2d(&tc->tmap_out, op.d_out, (uint64_t)tc->M_total, (uint64_t)op.k, kBlockM)) return rc;
+  if (op.d_residual)
+    if (int rc = encode_2d(&tc->tmap_res, op.d_residual, (uint64_t)tc->M_total, (uint64_t)op.k, kBlockM)) return rc;
+  if (op.d_weight3) {
+    PDF_REQUIRE(NC == 128 && (op.k3 == 64 || op.k3 == 128 || op.k3 == 256) && op.d_out3 &&
+                (reinterpret_cast<uintptr_t>(op.d_weight3) & 15) == 0 && (reinterpret_cast<uintptr_t>(op.d_out3) & 31) == 0,
+                "pointwise conv: a chained 1x1 convolution needs Cout %% 128 == 0, k3 in {64,128,256} and aligned pointers");
+    tc->k3 = op.k3; tc->bias3 = op.d_bias3; tc->out3 = op.d_out3;
+    if (int rc = encode_2d(&tc->tmap_w3, op.d_weight3, (uint64_t)op.k3, (uint64_t)op.k, (uint32_t)op.k3)) return rc;
+  }
+  return PDF_OK;
+}
+
+template <int NC, bool CHAIN>
+static int launch_pw(const TcConv& tc, cudaStream_t s) {
+  using L = PwSmem<NC>;
+  // measured (profiles/r02_pw_cfg.txt): launches that fetch a residual tile want the third staging buffer (the residual of unit
+  // u+1 streams in while unit u is still in its buffer), the others the fourth ring stage
+  const bool wants_staging = tc.residual != nullptr || CHAIN;
+  int stages = g_pw_stages ? g_pw_stages : (wants_staging ? 3 : 4), nry = g_pw_ry ? g_pw_ry : (wants_staging ? 3 : 2);
+  while (L::dynamic_bytes(stages, nry) > 227 * 1024 && stages > 2) --stages;
+  const int smem = L::dynamic_bytes(stages, nry);
+  static int configured = 0;
+  if (smem > configured) {
+    PDF_CHECK_CUDA(cudaFuncSetAttribute(conv_pw_kernel<NC, CHAIN>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
+    configured = smem;
+  }
+  PwParams p;
+  p.stages = stages; p.nry = nry;
+  p.M_total = tc.M_total; p.Cout = tc.Cout; p.K = tc.Cin; p.n_chunks = tc.Cout / NC; p.m_tiles = ceil_div(tc.M_total, kBlockM);
+  p.relu = tc.relu; p.im2col = tc.im2col; p.has_res = tc.residual != nullptr;
+  p.Ho = tc.Ho; p.Wo = tc.Wo; p.stride = tc.stride;
+  p.N2 = tc.k3; p.bias = tc.bias; p.bias3 = tc.bias3; p.out3 = reinterpret_cast<__nv_bfloat16*>(tc.out3);
+  const int grid = max(1, min(p.m_tiles, num_sms()));
+  const CUtensorMap& ta = *reinterpret_cast<const CUtensorMap*>(&tc.tmap_a);
+  const CUtensorMap& tb = *reinterpret_cast<const CUtensorMap*>(&tc.tmap_b);
+  const CUtensorMap& to = *reinterpret_cast<const CUtensorMap*>(&tc.tmap_out);
+  const CUtensorMap& tr = p.has_res ? *reinterpret_cast<const CUtensorMap*>(&tc.tmap_res) : to;
+  const CUtensorMap& tw = CHAIN ? *reinterpret_cast<const CUtensorMap*>(&tc.tmap_w3) : tb;
+  PDF_CHECK_CUDA(launch_pdl(conv_pw_kernel<NC, CHAIN>, dim3(grid), dim3(kPwThreads), (size_t)smem, s, ta, tb, to, tr, tw, p));
+  PDF_CHECK_LAUNCH();
+  return PDF_OK;
+}
+
+int launch_conv_pw(const TcConv& tc, cudaStream_t s) {
+  if (tc.pw == 128) return tc.k3 ? launch_pw<128, true>(tc, s) : launch_pw<128, false>(tc, s);
+  if (tc.pw == 64) return launch_pw<64, false>(tc, s);
+  set_error("launch_conv_pw: bad chunk width %d", tc.pw);
+  return PDF_ERR_ARG;
+}
+
+}  // namespace pdf
+
+/* tuning / A-B hook: 0 = 1x1 convolutions stay on conv_tc_kernel, 1 = default policy, 2 = every eligible 1x1 convolution uses
+ * conv_pw_kernel.  Takes effect for plans created afterwards. */
+extern "C" int pdf_debug_set_pw_config(int stages, int staging_buffers) {
+  if (stages == 0 && staging_buffers == 0) { pdf::g_pw_stages = pdf::g_pw_ry = 0; return PDF_OK; }   // back to the defaults
+  if (stages < 2 || stages > pdf::kPwMaxStages || staging_buffers < 2 || staging_buffers > pdf::kPwMaxRy) {
+    pdf::set_error("pdf_debug_set_pw_config: stages in [2,%d], staging buffers in [2,%d]", pdf::kPwMaxStages, pdf::kPwMaxRy);
+    return PDF_ERR_ARG;
+  }
+  pdf::g_pw_stages = stages; pdf::g_pw_ry = staging_buffers;
+  return PDF_OK;
+}
+extern "C" int pdf_debug_set_pw(int mode) {
+  pdf::g_pw_mode = mode;
+  return PDF_OK;
+}

@@ -448,7 +448,7 @@ typedef CUresult (*EncodeIm2colFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t
 static EncodeTiledFn g_encode_tiled = nullptr;
 static EncodeIm2colFn g_encode_im2col = nullptr;
 
-static int load_driver_entry_points() {
+int load_driver_entry_points() {
   if (g_encode_tiled && g_encode_im2col) return PDF_OK;
   PDF_CHECK_CUDA(cudaFree(0));  // make sure a context exists
   void* fn = nullptr;
@@ -464,7 +464,7 @@ static int load_driver_entry_points() {
 }
 
 // [rows, cols] row-major bf16 matrix, box = [box_rows x 64 cols], 128-byte swizzle
-static int encode_2d(TensorMapBlob* out, const void* ptr, uint64_t rows, uint64_t cols, uint32_t box_rows) {
+int encode_2d(TensorMapBlob* out, const void* ptr, uint64_t rows, uint64_t cols, uint32_t box_rows) {
   static_assert(sizeof(CUtensorMap) == sizeof(TensorMapBlob), "CUtensorMap is 128 bytes");
   const cuuint64_t dims[2] = {cols, rows};
   const cuuint64_t strides[1] = {cols * 2};
@@ -480,7 +480,7 @@ static int encode_2d(TensorMapBlob* out, const void* ptr, uint64_t rows, uint64_
 
 // extra_w: widen the base-pixel bounding box by that many columns on the right (conv3x3_hs.cu traverses W + 2 positions per row);
 // pixels: positions per load
-static int encode_im2col(TensorMapBlob* out, const pdf_op& op, int extra_w = 0, int pixels = kBlockM) {
+int encode_im2col(TensorMapBlob* out, const pdf_op& op, int extra_w, int pixels) {
   const cuuint64_t dims[4] = {(cuuint64_t)op.c, (cuuint64_t)op.w, (cuuint64_t)op.h, (cuuint64_t)op.n};
   const cuuint64_t strides[3] = {(cuuint64_t)op.c * 2, (cuuint64_t)op.w * op.c * 2, (cuuint64_t)op.h * op.w * op.c * 2};
   // bounding box of the filter's base pixel: lower = -pad, upper = pad - (filter-1)   [W, H] order as CUTLASS passes them
@@ -524,6 +524,9 @@ int prepare_conv_tc(const pdf_op& op, TcConv* tc) {
               "bf16 conv: inconsistent output size");
   PDF_REQUIRE((reinterpret_cast<uintptr_t>(op.d_in) & 15) == 0 && (reinterpret_cast<uintptr_t>(op.d_weight) & 15) == 0 &&
               (reinterpret_cast<uintptr_t>(op.d_out) & 15) == 0, "bf16 conv: pointers must be 16-byte aligned");
+  tc->pw = 0;
+  if (pw_eligible(op)) return prepare_conv_pw(op, tc);   // 1x1 convs whose epilogue goes through shared memory (conv_pw.cu)
+  PDF_REQUIRE(!op.d_weight3, "bf16 conv: a chained 1x1 convolution needs a 1x1 host convolution with bf16 output (conv_pw.cu)");
   tc->block_n = (op.k % 256 == 0) ? 256 : (op.k % 128 == 0 ? 128 : 64);
   tc->im2col = !(op.r == 1 && op.s == 1 && op.stride == 1 && op.pad == 0);
   tc->M_total = op.n * op.ho * op.wo;
@@ -614,6 +617,7 @@ static int launch_tc(const TcConv& tc, cudaStream_t s) {
 }
 
 int launch_conv_tc(const TcConv& tc, cudaStream_t s) {
+  if (tc.pw) return launch_conv_pw(tc, s);
   if (tc.dual) return launch_tc<128, 6, 1, true>(tc, s);     // 3x3 conv + the block's 1x1 downsample in one launch
   if (tc.hs) return launch_conv3x3_hs(tc, s);                // 3x3 stride-1: horizontal taps share one activation tile
   if (tc.halo) return launch_conv3x3_halo(tc, s);
@@ -644,6 +648,7 @@ extern "C" int pdf_selftest_umma(int M, int N, int K, const void* d_a_bf16, cons
   op.n = 1; op.h = 1; op.w = M; op.c = K; op.k = N; op.r = 1; op.s = 1; op.stride = 1; op.pad = 0; op.ho = 1; op.wo = M;
   op.relu = 0; op.out_f32 = 1; op.d_in = d_a_bf16; op.d_weight = d_b_bf16; op.d_out = d_c;
   TcConv tc;
+  memset(&tc, 0, sizeof(tc));
   if (int rc = prepare_conv_tc(op, &tc)) return rc;
   return launch_conv_tc(tc, as_stream(stream));
 }

@@ -30,8 +30,20 @@ struct TcConv {
   int hs;                 // 1: horizontally-shared 3x3 stride-1 kernel (conv3x3_hs.cu); tmap_a traverses W+2 positions per row
   int halo;               // 1: halo-resident 3x3 kernel (conv3x3_tc.cu); tmap_a is then a 4-D tiled map
   int halo_wp, halo_nr, n_images;
+  // pointwise kernel (conv_pw.cu): 1x1 convolution whose epilogue goes through shared memory (TMA residual load, TMA store),
+  // optionally chained with the NEXT 1x1 convolution (out3 = relu(out * W3^T + bias3)) while the output tile is still on chip
+  int pw;                  // 0 | NC (64 or 128): the launch goes to conv_pw_kernel<NC, ...>
+  int Cin;
+  TensorMapBlob tmap_out, tmap_res, tmap_w3;
+  int k3;                  // chained output channels (0 = no chain)
+  const float* bias3;
+  void* out3;
 };
 
+int load_driver_entry_points();
+// [rows, cols] row-major bf16 matrix, box = [box_rows x 64 cols], 128-byte swizzle
+int encode_2d(TensorMapBlob* out, const void* ptr, uint64_t rows, uint64_t cols, uint32_t box_rows);
+int encode_im2col(TensorMapBlob* out, const pdf_op& op, int extra_w = 0, int pixels = 128);
 int prepare_conv_tc(const pdf_op& op, TcConv* out);
 int prepare_stem_tc(const pdf_op& op, TcConv* out);   // weight map -> out->tmap_b, padded-image patch map -> out->tmap_a
 int launch_stem_fused(const pdf_op& op, const TensorMapBlob& tmap_w, const TensorMapBlob& tmap_in, cudaStream_t s);
@@ -43,5 +55,8 @@ bool halo_eligible(const pdf_op& op);
 bool hs_eligible(const pdf_op& op);
 int launch_conv3x3_hs(const TcConv& tc, cudaStream_t s);
 int launch_conv3x3_halo(const TcConv& tc, cudaStream_t s);
+bool pw_eligible(const pdf_op& op);
+int prepare_conv_pw(const pdf_op& op, TcConv* tc);
+int launch_conv_pw(const TcConv& tc, cudaStream_t s);
 
 }  // namespace pdf

@@ -61,7 +61,14 @@ extern "C" int pdf_plan_create(pdf_plan** out, const pdf_op* ops, int n_ops) {
           rc = PDF_ERR_ARG;
         }
       }
-      if (op.precision == PDF_PREC_BF16) rc = prepare_conv_tc(op, &plan->tc[i]);
+      if (op.d_weight3) {
+        plan->flops += 2.0 * op.n * op.ho * op.wo * (double)op.k3 * op.k;
+        if (op.precision != PDF_PREC_BF16) {
+          set_error("op %d: a chained 1x1 convolution exists on the bf16 path only", i);
+          rc = PDF_ERR_ARG;
+        }
+      }
+      if (rc == PDF_OK && op.precision == PDF_PREC_BF16) rc = prepare_conv_tc(op, &plan->tc[i]);
     }
     if (rc != PDF_OK) { delete plan; return rc; }
   }

@@ -54,6 +54,7 @@ class Op(C.Structure):
         ("d_in", C.c_void_p), ("d_weight", C.c_void_p), ("d_scale", C.c_void_p), ("d_bias", C.c_void_p),
         ("d_residual", C.c_void_p), ("d_out", C.c_void_p),
         ("d_weight2", C.c_void_p), ("d_bias2", C.c_void_p), ("d_out2", C.c_void_p),
+        ("d_weight3", C.c_void_p), ("d_bias3", C.c_void_p), ("d_out3", C.c_void_p), ("k3", C.c_int32),
     ]
 
 
@@ -125,6 +126,8 @@ PROTOTYPES = {
     "pdf_debug_set_conv_probe": (C.c_int, [C.c_int]),
     "pdf_debug_set_hs_mode": (C.c_int, [C.c_int]),
     "pdf_debug_disable_halo": (C.c_int, [C.c_int]),
+    "pdf_debug_set_pw": (C.c_int, [C.c_int]),
+    "pdf_debug_set_pw_config": (C.c_int, [C.c_int, C.c_int]),
 }
 
 _lib = None
@@ -154,6 +157,13 @@ def load():
         lib.pdf_debug_set_hs_mode(int(os.environ["PDFUSION_B200_HS"]))
     if os.environ.get("PDFUSION_B200_CONV_PROBE"):       # timing probe (garbage outputs): see pdf_debug_set_conv_probe
         lib.pdf_debug_set_conv_probe(int(os.environ["PDFUSION_B200_CONV_PROBE"]))
+    if os.environ.get("PDFUSION_B200_PW") is not None:   # tuning hook: pointwise kernel (0 off, 1 default policy, 2 every 1x1 conv)
+        lib.pdf_debug_set_pw(int(os.environ["PDFUSION_B200_PW"]))
+    if os.environ.get("PDFUSION_B200_PW_CFG"):           # tuning hook: "stages,staging_buffers" of the pointwise kernel
+        a, b = (int(v) for v in os.environ["PDFUSION_B200_PW_CFG"].split(","))
+        check_rc = lib.pdf_debug_set_pw_config(a, b)
+        if check_rc != 0:
+            raise PdfusionError("PDFUSION_B200_PW_CFG: " + lib.pdf_last_error().decode())
     if os.environ.get("PDFUSION_B200_NO_PDL"):           # tuning hook: plain stream-ordered launches
         lib.pdf_debug_enable_pdl(0)
     if os.environ.get("PDFUSION_B200_PRE_CHUNK"):        # tuning hook: subjects per preprocessing sub-batch (L2 residency)

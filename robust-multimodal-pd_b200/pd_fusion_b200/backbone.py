@@ -165,10 +165,13 @@ def flops_per_image(arch: str, input_size: int = 224, folded_stem: bool = False)
 
 # measured (profiles/r01_op_times_dual.txt): stage 2 -21 us, stage 3 -6 us, stage 4 +15 us (its 128-wide tiles re-read A four times)
 DEFAULT_DUAL_STAGES = (2, 3)
+# Bottleneck networks, bf16 path: residual stages whose conv3 launch also computes the NEXT block's conv1 (conv_pw.cu) -- the
+# chained accumulator needs planes <= 256 TMEM columns, i.e. stages 1..3
+DEFAULT_CHAIN_STAGES = (1, 2, 3)
 
 
 def lower_resnet(arch: str, n: int, S: int, bf16: bool, fused_stem: bool, chunks: List[int], in_bytes: int | None = None,
-                 dual_stages: Sequence[int] = ()):
+                 dual_stages: Sequence[int] = (), chain_stages: Sequence[int] = ()):
     """The network as a flat, ordered list of ops over symbolic buffers.
 
     Returns (ops, extents, final_hw): ops = [(name, fields, refs, weight_name)], where refs maps the pointer fields
@@ -177,6 +180,9 @@ def lower_resnet(arch: str, n: int, S: int, bf16: bool, fused_stem: bool, chunks
 
     dual_stages: residual stages (2..4) of a BasicBlock network whose first block computes its 1x1 downsample INSIDE the 3x3 conv1
     launch (bf16 path; the conv op then carries `_weight2` = the downsample's weight name and a `d_out2` reference).
+
+    chain_stages: residual stages (1..3) of a Bottleneck network whose conv3 launch also computes the next block's conv1 (the op
+    carries `_weight3` and a `d_out3` reference; that conv1 is not emitted).
 
     chunks[k] = images per launch of stage k (0 = stem, 1..4 = residual stages).  The op list is depth-first: a
     stage-k chunk is preceded by the stage-(k-1) chunks that produce its input, so the big early tensors are consumed
@@ -205,7 +211,7 @@ def lower_resnet(arch: str, n: int, S: int, bf16: bool, fused_stem: bool, chunks
 
     extents: Dict[str, int] = {}
     ops: List[tuple] = []
-    scratch = ("s0", "s1", "s2", "s3")
+    scratch = ("s0", "s1", "s2", "s3", "s4")
 
     def ref(buf, off, nbytes):
         extents[buf] = max(extents.get(buf, 0), off + nbytes)
@@ -242,6 +248,7 @@ def lower_resnet(arch: str, n: int, S: int, bf16: bool, fused_stem: bool, chunks
         x, x_h, x_c = src, hw[k - 1], ch[k - 1]
         blocks = stage_blocks[k]
         free = list(scratch)
+        chained = None
         for bi, cvs in enumerate(blocks):
             last_block = bi == len(blocks) - 1
             idn, idn_slot = x, None
@@ -259,6 +266,13 @@ def lower_resnet(arch: str, n: int, S: int, bf16: bool, fused_stem: bool, chunks
                         k=cv["cout"], r=1, s=1, stride=cv["stride"], pad=0, ho=hw[k], wo=hw[k], relu=0)
             t, t_h, t_c, t_slot = x, x_h, x_c, None
             seq = [cvs["a"]] + ([cvs["b"]] if "b" in cvs else []) + [cvs["last"]]
+            if chained is not None:                        # conv1 of this block was computed by the previous block's conv3 launch
+                t, t_h, t_c, t_slot = chained
+                seq = seq[1:]
+                chained = None
+            nxt = blocks[bi + 1]["a"] if not last_block else None
+            chain_next = (nxt is not None and bf16 and kind == "bottleneck" and k in chain_stages and nxt["k"] == 1 and nxt["stride"] == 1
+                          and nxt["cout"] in (64, 128, 256) and cvs["last"]["cout"] % 128 == 0)
             for cv in seq:
                 ho = (t_h + 2 * cv["pad"] - cv["k"]) // cv["stride"] + 1
                 is_last = cv["role"] == "last"
@@ -275,6 +289,12 @@ def lower_resnet(arch: str, n: int, S: int, bf16: bool, fused_stem: bool, chunks
                 if fuse_down is not None and cv["role"] == "a":
                     refs["d_out2"] = idn
                     extra["_weight2"] = fuse_down
+                if is_last and chain_next:
+                    c_slot = free.pop(0)
+                    refs["d_out3"] = ref(c_slot, 0, count * ho * ho * nxt["cout"] * esz)
+                    extra["_weight3"] = nxt["name"]
+                    extra["k3"] = nxt["cout"]
+                    chained = (refs["d_out3"], ho, nxt["cout"], c_slot)
                 add(cv["name"], refs, cv["name"], kind=_lib.OP_CONV, precision=prec, n=count, h=t_h, w=t_h, c=t_c, k=cv["cout"],
                     r=cv["k"], s=cv["k"], stride=cv["stride"], pad=cv["pad"], ho=ho, wo=ho, relu=1,
                     out_f32=1 if (final and bf16) else 0, **extra)
@@ -347,6 +367,8 @@ class ResNetEncoder:
         # residual stages whose 1x1 downsample is computed inside conv1's launch (BasicBlock networks, bf16 path)
         env_dual = os.environ.get("PDFUSION_B200_DUAL")               # tuning hook: "" = none, "2,3,4" = those stages
         self.dual_stages = tuple(int(v) for v in env_dual.split(",") if v) if env_dual is not None else DEFAULT_DUAL_STAGES
+        env_chain = os.environ.get("PDFUSION_B200_CHAIN")             # tuning hook: "" = none, "1,2" = those stages
+        self.chain_stages = tuple(int(v) for v in env_chain.split(",") if v) if env_chain is not None else DEFAULT_CHAIN_STAGES
         sd = {k: v.detach().to("cpu") for k, v in state_dict.items()}
         self._keep: List[torch.Tensor] = []     # device tensors referenced by the plan
         self._build(sd)
@@ -456,7 +478,8 @@ class ResNetEncoder:
             in_bytes = S * S * 3 * 4
         self.output = torch.empty((n, self.emb_dim), dtype=torch.float32, device=self.device)
         self.chunks = self._chunk_sizes(h2, esz)
-        ops, extents, self.final_hw = lower_resnet(self.arch, n, S, self.bf16, self.fused_stem, self.chunks, in_bytes, self.dual_stages)
+        ops, extents, self.final_hw = lower_resnet(self.arch, n, S, self.bf16, self.fused_stem, self.chunks, in_bytes, self.dual_stages,
+                                                     self.chain_stages)
         weights = {cv["name"]: self._conv_weights(sd, cv) for cv in conv_list(self.arch)}
 
         self.buffers = {name: torch.empty(nbytes, dtype=torch.uint8, device=self.device) for name, nbytes in extents.items()
@@ -470,11 +493,15 @@ class ResNetEncoder:
             op = _lib.Op()
             kw = dict(kw)
             wname2 = kw.pop("_weight2", None)
+            wname3 = kw.pop("_weight3", None)
             for key, v in kw.items():
                 setattr(op, key, v)
             if wname2 is not None:
                 w2, _, b2 = weights[wname2]
                 op.d_weight2, op.d_bias2 = w2.data_ptr(), b2.data_ptr()
+            if wname3 is not None:
+                w3, _, b3 = weights[wname3]
+                op.d_weight3, op.d_bias3 = w3.data_ptr(), b3.data_ptr()
             for key, (buf, off) in refs.items():
                 setattr(op, key, base[buf] + off)
             if wname is not None:

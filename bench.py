@@ -1,7 +1,10 @@
 #!/usr/bin/env python
 """bench.py -- MRI subjects/s of the imaging-embedding hot path on B200 (BASELINE.json metric).
 
-    python bench.py [--gpus N] [--steps K] [--warmup W] [--workload c2|c3] [--subjects B] [--impl b200|reference]
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--workload c3|c2] [--subjects B] [--impl b200|reference]
+
+The default workload is c3 = configs/openneuro_ds001907_resnet2d_mil.yaml (ResNet50, 48 slices, gated MIL attention): the
+configuration BASELINE.json's metric ("ResNet2D-MIL embed+fuse") is quoted on.
 
 A "step" = one pass of the hot path over one batch of B synthetic subjects per GPU:
 raw T1 volumes f32[256,256,176] resident in HBM -> resample 160^3 -> p1/p99 normalise -> slice select ->
@@ -12,9 +15,15 @@ of the embedding table and of the per-scenario probabilities when N > 1].  Print
   value        device-resident throughput (inputs already in HBM), CUDA-event timed, max over ranks
   e2e          same metric through the public host API (pinned float32 host volumes -> H2D -> hot path -> D2H results)
   e2e_stored_int16  the same call fed the voxels as an int16 NIfTI stores them (decoded on the device): half the PCIe bytes
-  roofline     the dominant kernel family (tcgen05 implicit-GEMM convs): algorithmic FLOPs / CUDA-event time, against the burst
-               and the sustained measured bf16 peak, with the DRAM traffic of the same launches (ncu)
-  roofline_preproc  the preprocessing kernels against the measured copy bandwidth (SURVEY.md 8d algorithmic bytes)
+  roofline     the dominant kernel family (tcgen05 implicit-GEMM convs): algorithmic FLOPs / CUDA-event time of the timed region
+               against the measured BURST bf16 peak, with the DRAM traffic of the same launches (ncu capture, profiles/)
+  sustained    >= 2 s of back-to-back steps / conv stacks (the regime of a 10 k-subject job: the board sits at its power cap):
+               subjects/s, and the conv stack's TFLOP/s against the measured SUSTAINED bf16 peak
+  roofline_preproc, roofline_preproc_dense  the preprocessing kernels against the measured copy bandwidth (SURVEY.md 8d
+               algorithmic bytes) on the synthetic brains (73 % exact-zero background, which the kernels skip) and on volumes
+               without background
+  roofline_mil the MIL head (projection + attention + pooling, all 7 scenarios) on a bag table larger than L2: 4*L*D+4 bytes per bag
+  heads        pdf_moddrop_sweep / pdf_moe_sweep at N = 10 000 and 1 000 000 subjects, bytes-based roofline
   cpu_baseline the oracle port of the reference's CPU path on a bounded sample (rank 0, N = 1 only)
 
 `--impl reference` times the reference's own CPU implementation of the path (oracle port; /root/reference does
@@ -46,8 +55,18 @@ WORKLOADS = {
 }
 IN_SHAPE, TARGET, INPUT_SIZE = (256, 256, 176), (160, 160, 160), 224
 METRIC, UNIT = "mri_subjects_per_sec_resnet2d_embed_fuse", "subjects/s"
-# DRAM bytes moved by the tcgen05 conv launches of ONE step, measured with ncu --set full (profiles/r01_ncu_full_step_final.txt)
-CONV_DRAM_BYTES = {("c2", 32): 6538.8e6}
+
+
+def conv_dram_traffic(workload: str, B: int):
+    """DRAM bytes moved by the conv launches of ONE step: dram__bytes_read.sum + dram__bytes_write.sum summed over the launches
+    of one `ncu --set full` capture of this command, written by scripts/ncu_traffic.py into profiles/conv_traffic.json (keyed
+    by workload and subjects per step, with the capture's date and source file).  None when that configuration was not captured."""
+    p = ROOT / "profiles" / "conv_traffic.json"
+    if not p.exists():
+        return None, None
+    d = json.loads(p.read_text())
+    e = d.get(f"{workload}_b{B}")
+    return (float(e["dram_bytes"]), e.get("source")) if e else (None, None)
 
 
 def measured_peaks():
@@ -125,6 +144,11 @@ def host_pool(n: int):
     return [synthetic_volume(i, IN_SHAPE) for i in range(n)]
 
 
+def dense_volume(index: int):
+    """A volume WITHOUT background: Gamma(4, 100) everywhere (no exact zeros for the kernels to skip)."""
+    return np.random.default_rng(5000 + index).gamma(4.0, 100.0, size=IN_SHAPE).astype(np.float32)
+
+
 def cpu_reference_rate(wl, n_subjects: int, pool):
     """The reference's CPU path (oracle port) on `n_subjects` subjects with every host thread."""
     import torch
@@ -179,12 +203,63 @@ def run_reference(args, wl):
     print(json.dumps(line), flush=True)
 
 
+def heads_leg(dev, peaks, timed):
+    """pdf_moddrop_sweep (C2 dims: mri 512 -> 256-128-64-1) and pdf_moe_sweep (C4 dims: mri 512 + clinical 10) under the 7 scenarios
+    of the ds001907 eval file and under the 8-mask power set, at N = 10 000 and 1 000 000 subjects.  Algorithmic bytes per subject
+    (SURVEY.md 8d): features once (4F) + S*M mask bytes + 4S probabilities.  The reference's evaluate_model loop (oracle port) is
+    timed next to the N = 10 000 ModDrop/MoE sweeps on the host."""
+    import torch
+    from oracle import oracle as O
+    from pd_fusion_b200.heads import ModDropSweep, MoeSweep
+    from pd_fusion_b200.models.fusion_moddrop import ModalityDropoutNet
+    from pd_fusion_b200.models.moe import MoENet
+    out = []
+    torch.manual_seed(4321)
+    dims_md = {"clinical": 0, "datspect": 0, "mri": 512}
+    md_sd = ModalityDropoutNet(dims_md, [256, 128, 64], 0.3).state_dict()
+    md = ModDropSweep(md_sd, dims_md, device=dev)
+    dims_moe = {"clinical": 10, "mri": 512}
+    moe_sd = MoENet(dims_moe, {"expert_hidden_dims": [32, 16], "router_hidden_dims": [16]}).state_dict()   # configs/model_moe.yaml
+    moe = MoeSweep(moe_sd, list(dims_moe), device=dev)
+    g = torch.Generator(device=dev).manual_seed(3)
+    for N in (10_000, 1_000_000):
+        X = torch.randn((N, 512), generator=g, device=dev)
+        Xc = torch.randn((N, 10), generator=g, device=dev)
+        for S, label in ((7, "7 scenarios"), (8, "8-mask power set")):
+            m3 = (torch.rand((S, N, 3), generator=g, device=dev) < 0.7).to(torch.uint8)
+            m2 = m3[:, :, 1:].contiguous()
+            reps = 20 if N <= 10_000 else 3
+            for name, fn, F, M in (("moddrop", lambda: md.forward(X, m3), 512, 3), ("moe", lambda: moe.forward({"clinical": Xc, "mri": X}, m2), 522, 2)):
+                fn(); fn()
+                ms = timed(fn, reps) / reps
+                nbytes = N * (4 * F + S * M + 4 * S)
+                rec = {"head": name, "N": N, "S": S, "masks": label, "ms": ms, "pairs_per_s": N * S / (ms / 1e3),
+                       "roofline": {"bound": "hbm", "achieved": nbytes / (ms / 1e3) / 1e9, "peak": peaks["hbm"], "unit": "GB/s",
+                                    "frac": nbytes / (ms / 1e3) / 1e9 / peaks["hbm"], "bytes_per_subject": 4 * F + S * M + 4 * S}}
+                if N == 10_000 and S == 7:      # the reference's per-scenario loop on the host cores (oracle port), same inputs
+                    Xh, mh = X.cpu().numpy(), m3.cpu().numpy()
+                    t0 = time.perf_counter()
+                    if name == "moddrop":
+                        sdn = {k: v.numpy() for k, v in md_sd.items()}
+                        for s_ in range(S):
+                            O.moddrop_predict_proba(sdn, dims_md, Xh, {m: mh[s_][:, i] for i, m in enumerate(O.MODALITIES)})
+                    else:
+                        sdn = {k: v.numpy() for k, v in moe_sd.items()}
+                        Xch, m2h = Xc.cpu().numpy(), m2.cpu().numpy()
+                        for s_ in range(S):
+                            O.moe_predict_proba(sdn, {"clinical": Xch * m2h[s_][:, :1], "mri": Xh * m2h[s_][:, 1:2]}, m2h[s_].astype(np.float32))
+                    rec["cpu_reference_ms"] = (time.perf_counter() - t0) * 1e3
+                out.append(rec)
+        del X, Xc
+    return out
+
+
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
     ap.add_argument("--steps", type=int, default=100)
     ap.add_argument("--warmup", type=int, default=5)
-    ap.add_argument("--workload", default="c2", choices=sorted(WORKLOADS))
+    ap.add_argument("--workload", default="c3", choices=sorted(WORKLOADS))
     ap.add_argument("--subjects", type=int, default=32, help="subjects per step per GPU")
     ap.add_argument("--pool", type=int, default=4, help="distinct synthetic volumes cycled by subject index")
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
@@ -195,6 +270,9 @@ def main():
                          "than one stream since the conv stack is power-capped: profiles/r01_ab_overlap.txt)")
     ap.add_argument("--no-overlap", action="store_true", help="(default) one stream")
     ap.add_argument("--no-stored-e2e", action="store_true", help="skip the second end-to-end leg (int16 stored voxels decoded on the device)")
+    ap.add_argument("--sustained-seconds", type=float, default=2.0, help="length of the sustained legs (0 = skip)")
+    ap.add_argument("--no-heads", action="store_true", help="skip the fusion-head legs (ModDrop / MoE sweeps at N = 1e4, 1e6)")
+    ap.add_argument("--mil-bags", type=int, default=2048, help="bags of the MIL roofline leg (c3)")
     args = ap.parse_args()
     wl = WORKLOADS[args.workload]
     if args.impl == "reference":
@@ -260,19 +338,19 @@ def main():
         head = ModDropSweep(ModalityDropoutNet(dims, [256, 128, 64], 0.3).state_dict(), dims, device=dev)
     else:
         from pd_fusion_b200.models.mil_attention import MILAttentionNet
-        head = MilHead(MILAttentionNet(D, 256, 128, 0.2, gated=True).state_dict(), True, 0.5, device=dev)
-        mri_col = masks[:, :, 2].contiguous()
+        head = MilHead(MILAttentionNet(D, 256, 128, 0.2, gated=True).state_dict(), True, 0.5, device=dev, precision="tf32")
+        mri_col = masks[:, :, 2].contiguous()                  # [S, B] u8: the bag is present under scenario s
+        full_len = torch.full((B,), L, dtype=torch.int32, device=dev)
+        probs_sb = torch.empty((S_scen, B), dtype=torch.float32, device=dev)
     probs = torch.empty((B, S_scen), dtype=torch.float32, device=dev)
 
     def fuse(res, emb=None):
         """probabilities [B, S] of the batch under every scenario (emb: a stable copy of the embeddings to read instead of res)"""
         if args.workload == "c2":
             probs.copy_(head.forward(res.mean if emb is None else emb, masks).t())
-        else:                                   # MIL: a masked-out bag has length 0 (-> missing_prob); one launch per scenario set
-            lens = (mri_col * L).to(torch.int32)                     # [S, B]
+        else:                                   # MIL: project + pool every bag ONCE, the scenario only selects missing_prob (pdf_mil_sweep)
             e = res.embeddings if emb is None else emb
-            bags = e.unsqueeze(0).expand(S_scen, B, L, D).reshape(S_scen * B, L, D).contiguous()
-            probs.copy_(head.forward(bags, lens.reshape(-1)).view(S_scen, B).t())
+            probs.copy_(head.sweep(e, full_len, mri_col, out=probs_sb).t())
         return probs
 
     def step_device():
@@ -351,6 +429,72 @@ def main():
     tf = flops / (ms_enc / 1e3) / 1e12
     gbs = pipe.algorithmic_bytes_per_subject() * B / (ms_pre / 1e3) / 1e9
 
+    # --- sustained regime: >= `sustained_seconds` of back-to-back work, clocks sampled throughout.  A 10 k-subject job runs
+    #     for seconds, not for the 0.1-0.5 s of the timed region above: the board settles at its power cap.
+    sustained = None
+    if args.sustained_seconds > 0:
+        n_step = max(args.steps, int(np.ceil(args.sustained_seconds * 1e3 / max(ms / args.steps, 1e-3))))
+        n_enc = max(args.steps, int(np.ceil(args.sustained_seconds * 1e3 / max(ms_enc, 1e-3))))
+        with ClockSampler(local_rank) as clk_s:
+            ms_s = timed(step_device, n_step)
+        with ClockSampler(local_rank) as clk_c:
+            ms_c = timed(enc_only, n_enc) / n_enc
+        tf_s = flops / (ms_c / 1e3) / 1e12
+        sustained = {"seconds": ms_s / 1e3, "steps": n_step, "value": ws * B * n_step / (ms_s / 1e3), "unit": UNIT,
+                     "ms_per_step": ms_s / n_step, "clocks": clk_s.summary(),
+                     "conv": {"achieved": tf_s, "peak": peaks["tf_sustained"], "unit": "TFLOP/s", "frac": tf_s / peaks["tf_sustained"],
+                              "ms": ms_c, "launches_timed": n_enc, "seconds": ms_c * n_enc / 1e3, "clocks": clk_c.summary(),
+                              "peak_source": peaks["src"] + " sustained bf16 (cuBLAS back to back for 4 s)"}}
+
+    # --- preprocessing on volumes WITHOUT background (the synthetic brains are ~73 % exact zeros, which the resample and select
+    #     kernels skip): same kernels, same algorithmic bytes
+    pool_d = [dense_volume(i) for i in range(2)]
+    raw_d = torch.empty_like(raw)
+    for i in range(B):
+        raw_d[i].copy_(torch.from_numpy(pool_d[i % 2]), non_blocking=False)
+
+    def pre_dense():
+        pipe.pre.run(raw_d, net_input=pipe._net_input)
+
+    for _ in range(2):
+        pre_dense()
+    ms_pre_d = timed(pre_dense, args.steps) / args.steps
+    gbs_d = pipe.algorithmic_bytes_per_subject() * B / (ms_pre_d / 1e3) / 1e9
+    del raw_d
+
+    # --- MIL head on a bag table larger than L2 (4*L*D + 4 bytes per bag): projection + attention (tcgen05
+    #     kind::tf32 on the f32 bags) + softmax-pool + classifier ONCE, all scenarios selected on the device
+    roofline_mil = None
+    if args.workload == "c3" and args.mil_bags > 0:
+        nb = args.mil_bags
+        g = torch.Generator(device=dev).manual_seed(7)
+        bag_tab = torch.randn((nb, L, D), generator=g, device=dev, dtype=torch.float32)
+        lens_tab = torch.full((nb,), L, dtype=torch.int32, device=dev)
+        live_tab = (torch.rand((S_scen, nb), generator=g, device=dev) < 0.6).to(torch.uint8)
+        out_tab = torch.empty((S_scen, nb), dtype=torch.float32, device=dev)
+
+        def mil_only():
+            head.sweep(bag_tab, lens_tab, live_tab, out=out_tab)
+
+        for _ in range(3):
+            mil_only()
+        l0 = _lib.launch_count()
+        mil_only()
+        mil_launches = _lib.launch_count() - l0
+        ms_mil = timed(mil_only, max(args.steps, 10)) / max(args.steps, 10)
+        b_mil = (4 * L * D + 4) * nb
+        gbs_mil = b_mil / (ms_mil / 1e3) / 1e9
+        roofline_mil = {"bound": "hbm", "kernel": "pdf_mil_sweep: gemm_tf32_kernel x2 (projection, attention scores) + mil_pool_kernel",
+                        "achieved": gbs_mil, "peak": peaks["hbm"], "unit": "GB/s", "frac": gbs_mil / peaks["hbm"], "ms": ms_mil,
+                        "bags": nb, "scenarios": S_scen, "launches": int(mil_launches), "bytes_per_bag": 4 * L * D + 4,
+                        "table_bytes": int(bag_tab.numel() * 4), "peak_source": peaks["src"]}
+        del bag_tab, out_tab
+
+    # --- fusion heads: every scenario in one call at N = 10 000 and 1 000 000 subjects
+    heads = None
+    if not args.no_heads and rank == 0:
+        heads = heads_leg(dev, peaks, timed)
+
     run_e2e()                                            # warm-up (allocates the second device buffer)
     barrier(); torch.cuda.synchronize()
     t0 = time.perf_counter()
@@ -385,6 +529,7 @@ def main():
                    "ms_per_step": float(t_i16.item()) / args.steps,
                    "input": "voxels as an int16 NIfTI stores them (Fortran order); float64 scaling rule, cast and transpose on the device"}
 
+    traffic, traffic_src = conv_dram_traffic(args.workload, B)
     line = {
         "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": ws, "steps": args.steps, "warmup": max(args.warmup, 3),
         "ms_per_step": ms / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
@@ -394,7 +539,7 @@ def main():
                    "l2": "inputs larger than L2 (%.1f GB of volumes per step)" % (B * 4 * np.prod(IN_SHAPE) / 1e9),
                    "parallelism": f"subjects sharded x{ws}, all-gather of the embedding table" if ws > 1 else "1 GPU",
                    "fuse": ("Fusion-ModDrop 512-256-128-64-1" if args.workload == "c2" else "gated MIL attention 2048-256-128") +
-                           f" under {S_scen} missingness scenarios, one launch",
+                           f" under {S_scen} missingness scenarios, " + ("one launch" if args.workload == "c2" else "one pdf_mil_sweep call (tf32 tensor path)"),
                    "streams": ("preprocessing of batch i+1 overlaps the conv stack of batch i (2 streams); " if overlap else "preprocessing + conv stack on one stream; ") +
                               "fusion head and gathers on a side stream next to the following batch"},
         "clocks": clk.summary(),
@@ -402,18 +547,23 @@ def main():
                 "ms_per_step": ms_e2e / args.steps},
         "e2e_stored_int16": e2e_i16,
         "gpu_launches": int(launches),
-        "roofline": {"bound": "tensor", "kernel": "conv_tc_kernel (tcgen05 implicit-GEMM conv stack, all launches of one step)",
+        "roofline": {"bound": "tensor", "kernel": "tcgen05 implicit-GEMM conv stack (stem_fused, conv3x3_c64, conv3x3_hs, conv_tc, conv_tc2, "
+                                                  "conv_pw kernels: all launches of one step)",
                      "achieved": tf, "peak": peaks["tf"], "unit": "TFLOP/s", "frac": tf / peaks["tf"],
-                     "traffic": CONV_DRAM_BYTES.get((args.workload, B)),
-                     "traffic_source": "dram__bytes_read.sum + dram__bytes_write.sum over the conv launches of one step, ncu --set full "
-                                       "(profiles/r01_ncu_full_step_final.txt); null for configurations that were not captured",
-                     "peak_source": peaks["src"] + " burst bf16 (the stack runs into the 1000 W power cap at 1.4-1.55 GHz SM clock, "
-                                                   "profiles/r01_stack_power.txt, which is the regime of the sustained figure)",
-                     "frac_sustained": tf / peaks["tf_sustained"], "peak_sustained": peaks["tf_sustained"],
+                     "traffic": traffic,
+                     "traffic_source": traffic_src or "no ncu --set full capture of this configuration in profiles/conv_traffic.json",
+                     "peak_source": peaks["src"] + " burst bf16 (numerator and denominator both from sub-second runs; the >= 2 s regime is "
+                                                   "under `sustained`)",
                      "ms": ms_enc, "flops_per_step": flops},
+        "sustained": sustained,
         "roofline_preproc": {"bound": "hbm", "kernel": "K1 resample/select/gather (all launches of one step)", "achieved": gbs,
                              "peak": peaks["hbm"], "unit": "GB/s", "frac": gbs / peaks["hbm"], "ms": ms_pre,
-                             "bytes_per_subject": pipe.algorithmic_bytes_per_subject(), "peak_source": peaks["src"]},
+                             "bytes_per_subject": pipe.algorithmic_bytes_per_subject(), "peak_source": peaks["src"],
+                             "input": "synthetic brains, ~73 % exact-zero background"},
+        "roofline_preproc_dense": {"bound": "hbm", "achieved": gbs_d, "peak": peaks["hbm"], "unit": "GB/s", "frac": gbs_d / peaks["hbm"],
+                                   "ms": ms_pre_d, "input": "Gamma(4,100) everywhere, no background"},
+        "roofline_mil": roofline_mil,
+        "heads": heads,
     }
     if rank == 0 and ws == 1 and not args.no_cpu_baseline:
         rate, cores, dt = cpu_reference_rate(wl, args.cpu_subjects, pool)

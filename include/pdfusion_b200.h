@@ -159,6 +159,7 @@ int pdf_normalize_volume(int batch, size_t voxels, const float* d_zoomed, const 
 
 #define PDF_PREC_F32 0  /* CUDA-core FFMA path, 1e-5 parity */
 #define PDF_PREC_BF16 1 /* tcgen05/TMEM path, bf16 operands, f32 accumulate */
+#define PDF_PREC_TF32 2 /* tcgen05/TMEM path on float32 operands (kind::tf32: 10-bit mantissa products, f32 accumulate): MIL head */
 
 typedef struct {
   int32_t kind;
@@ -228,6 +229,15 @@ typedef struct {
 } pdf_mil_weights;
 
 size_t pdf_mil_workspace_bytes(const pdf_mil_weights* w, int n_bags, int Lmax);
+/* The MIL head under EVERY scenario in one call (evaluation/evaluate.py:32-37 sets a bag to None where the scenario drops mri and
+ * calls predict_proba once per scenario; the bag's probability itself does not depend on the scenario): instance projection and
+ * attention layers ONCE over all bags, softmax-pool + classifier once per bag, then
+ *   d_prob[s, b] = (d_live[s, b] && d_len[b] > 0) ? p_b : missing_prob          d_live [n_scenarios, n_bags] u8 or NULL (all live).
+ * precision PDF_PREC_F32: FFMA GEMMs (<= 5e-6 vs the reference); PDF_PREC_TF32: both linear layers as tcgen05 kind::tf32 GEMMs on
+ * the f32 bags (needs H, (2)A in {64,128,256}, D % 32 == 0, H % 32 == 0, and for the gated head w_u == w_v + A*H, b_u == b_v + A,
+ * i.e. [W_v; W_u] packed as one matrix), attention scores computed in the GEMM epilogue. */
+int pdf_mil_sweep(const pdf_mil_weights* w, int n_bags, int Lmax, const float* d_bags, const int32_t* d_len, int n_scenarios,
+                  const uint8_t* d_live, int precision, void* d_workspace, float* d_prob, pdf_stream_t stream);
 int pdf_mil_forward(const pdf_mil_weights* w, int n_bags, int Lmax, const float* d_bags, const int32_t* d_len,
                     void* d_workspace, float* d_prob, pdf_stream_t stream);
 

@@ -3,6 +3,7 @@
 // pairs instead of the reference's per-bag and per-scenario Python loops
 // (models/mil_attention.py:169-177, evaluation/evaluate.py:18-97).
 #include "common.cuh"
+#include "ops.cuh"
 
 namespace pdf {
 
@@ -76,43 +77,47 @@ __device__ __forceinline__ float warp_sum(float v) {
 __device__ __forceinline__ float sigmoidf_(float x) { return 1.0f / (1.0f + expf(-x)); }
 
 // ------------------------------------------------------------------------------------------------------
-// MIL: one block per bag, h = ReLU(instance(x)) already in `hbuf`.
+// MIL pooling: one block per bag.  h = ReLU(instance(x)) [n_bags*Lmax, H] is in `hbuf`; the attention scores come either
+// ready-made (`scores`, tensor path: computed by the attention GEMM's epilogue) or as the pre-activations of the attention
+// layer(s) `vu` [n_bags*Lmax, NA] (FP32 path; NA = 2A gated: v | u, else A).  Masked softmax over the bag, weighted pool,
+// classifier, and the result is written for EVERY scenario: prob[s, bag] = live[s, bag] ? p : missing_prob -- the bag's
+// probability does not depend on the scenario, only its presence does (evaluation/evaluate.py:32-37).
 __global__ void __launch_bounds__(256)
-mil_pool_kernel(const float* __restrict__ hbuf, const int32_t* __restrict__ lens, int Lmax, pdf_mil_weights w,
+mil_pool_kernel(const float* __restrict__ hbuf, const float* __restrict__ vu, const float* __restrict__ scores,
+                const int32_t* __restrict__ lens, int Lmax, pdf_mil_weights w, int n_bags, int S, const uint8_t* __restrict__ live,
                 float* __restrict__ prob) {
   extern __shared__ float sm[];
   float* s_score = sm;                 // [Lmax]
-  float* s_h = sm + Lmax;              // [8][H] staging, then [H] pooled
   __shared__ float s_red[8];
   const int bag = blockIdx.x;
   const int len = min(lens[bag], Lmax);
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
   const int H = w.H, A = w.A;
-  if (len <= 0) {
-    if (tid == 0) prob[bag] = w.missing_prob;
+  bool any_live = len > 0;
+  if (any_live && live) {
+    any_live = false;
+    for (int s = 0; s < S; ++s) any_live |= live[(size_t)s * n_bags + bag] != 0;
+  }
+  if (!any_live) {
+    for (int s = tid; s < S; s += 256) prob[(size_t)s * n_bags + bag] = w.missing_prob;
     return;
   }
   const float* hb = hbuf + (size_t)bag * Lmax * H;
-  float* myh = s_h + warp * H;
-  for (int l = warp; l < len; l += 8) {
-    for (int i = lane; i < H; i += 32) myh[i] = hb[(size_t)l * H + i];
-    __syncwarp();
-    float sc = 0.f;
-    for (int a = 0; a < A; ++a) {
-      float dv = 0.f, du = 0.f;
-      const float* wv = w.w_v + (size_t)a * H;
-      for (int i = lane; i < H; i += 32) dv = fmaf(__ldg(wv + i), myh[i], dv);
-      if (w.gated) {
-        const float* wu = w.w_u + (size_t)a * H;
-        for (int i = lane; i < H; i += 32) du = fmaf(__ldg(wu + i), myh[i], du);
+  if (scores) {
+    for (int l = tid; l < len; l += 256) s_score[l] = scores[(size_t)bag * Lmax + l];
+  } else {
+    const int NA = w.gated ? 2 * A : A;
+    for (int l = warp; l < len; l += 8) {
+      const float* r = vu + ((size_t)bag * Lmax + l) * NA;
+      float sc = 0.f;
+      for (int a = lane; a < A; a += 32) {
+        float t = tanhf(r[a] + __ldg(w.b_v + a));
+        if (w.gated) t *= sigmoidf_(r[A + a] + __ldg(w.b_u + a));
+        sc = fmaf(__ldg(w.w_w + a), t, sc);
       }
-      dv = warp_sum(dv) + __ldg(w.b_v + a);
-      float t = tanhf(dv);
-      if (w.gated) { du = warp_sum(du) + __ldg(w.b_u + a); t *= sigmoidf_(du); }
-      sc = fmaf(__ldg(w.w_w + a), t, sc);
+      sc = warp_sum(sc);
+      if (lane == 0) s_score[l] = sc + __ldg(w.b_w);
     }
-    if (lane == 0) s_score[l] = sc + __ldg(w.b_w);
-    __syncwarp();
   }
   __syncthreads();
   // softmax over the valid instances (masked_fill(-1e9) on padding == exclusion)
@@ -142,11 +147,10 @@ mil_pool_kernel(const float* __restrict__ hbuf, const int32_t* __restrict__ lens
   z = warp_sum(z);
   if (lane == 0) s_red[warp] = z;
   __syncthreads();
-  if (tid == 0) {
-    float t = 0.f;
-    for (int i = 0; i < 8; ++i) t += s_red[i];
-    prob[bag] = sigmoidf_(t + __ldg(w.b_cls));
-  }
+  float t = 0.f;
+  for (int i = 0; i < 8; ++i) t += s_red[i];
+  const float pr = sigmoidf_(t + __ldg(w.b_cls));
+  for (int s = tid; s < S; s += 256) prob[(size_t)s * n_bags + bag] = (!live || live[(size_t)s * n_bags + bag]) ? pr : w.missing_prob;
 }
 
 // ------------------------------------------------------------------------------------------------------
@@ -300,25 +304,56 @@ using namespace pdf;
 
 extern "C" size_t pdf_mil_workspace_bytes(const pdf_mil_weights* w, int n_bags, int Lmax) {
   if (!w || n_bags <= 0 || Lmax <= 0) return 0;
-  return (size_t)n_bags * Lmax * w->H * sizeof(float) + 256;
+  const size_t rows = (size_t)n_bags * Lmax;
+  const size_t na = (size_t)(w->gated ? 2 * w->A : w->A);
+  // h [rows, H] | attention pre-activations [rows, NA] (FP32 path) or scores [rows] (tensor path)
+  return rows * w->H * sizeof(float) + rows * na * sizeof(float) + 512;
+}
+
+extern "C" int pdf_mil_sweep(const pdf_mil_weights* w, int n_bags, int Lmax, const float* d_bags, const int32_t* d_len,
+                             int n_scenarios, const uint8_t* d_live, int precision, void* d_workspace, float* d_prob,
+                             pdf_stream_t stream) {
+  PDF_REQUIRE(w && n_bags > 0 && Lmax > 0 && d_bags && d_len && d_workspace && d_prob && n_scenarios > 0, "pdf_mil_sweep: bad arguments");
+  PDF_REQUIRE(w->D > 0 && w->H > 0 && w->H <= 2048 && w->A > 0, "pdf_mil_sweep: bad dims");
+  PDF_REQUIRE(w->w_inst && w->b_inst && w->w_v && w->b_v && w->w_w && w->b_w && w->w_cls && w->b_cls && (!w->gated || (w->w_u && w->b_u)),
+              "pdf_mil_sweep: null weight pointer");
+  PDF_REQUIRE(precision == PDF_PREC_F32 || precision == PDF_PREC_TF32, "pdf_mil_sweep: precision must be PDF_PREC_F32 or PDF_PREC_TF32");
+  cudaStream_t s = as_stream(stream);
+  const int rows = n_bags * Lmax;
+  const int NA = w->gated ? 2 * w->A : w->A;
+  float* hbuf = reinterpret_cast<float*>(d_workspace);
+  float* abuf = hbuf + (((size_t)rows * w->H + 63) & ~(size_t)63);
+  const float* scores = nullptr;
+  const float* vu = nullptr;
+  if (precision == PDF_PREC_TF32) {
+    // both linear layers on the tensor cores (kind::tf32 on the f32 operands); the attention GEMM reads [W_v; W_u] as ONE [2A, H]
+    // matrix, so for the gated head w_u must directly follow w_v in memory (pd_fusion_b200/heads.py packs them)
+    PDF_REQUIRE(gemm_tf32_supported(w->H, w->D) && gemm_tf32_supported(NA, w->H),
+                "pdf_mil_sweep: the tensor path needs H and (2)A in {64,128,256}, D and H multiples of 32 (D=%d H=%d A=%d)", w->D, w->H, w->A);
+    PDF_REQUIRE(!w->gated || (w->w_u == w->w_v + (size_t)w->A * w->H && w->b_u == w->b_v + w->A),
+                "pdf_mil_sweep: the tensor path needs [w_v; w_u] and [b_v; b_u] contiguous");
+    if (int rc = launch_gemm_tf32(d_bags, w->w_inst, rows, w->H, w->D, 0, 0, 0, w->b_inst, nullptr, nullptr, hbuf, s)) return rc;
+    if (int rc = launch_gemm_tf32(hbuf, w->w_v, rows, NA, w->H, 1, w->gated, w->A, w->b_v, w->w_w, w->b_w, abuf, s)) return rc;
+    scores = abuf;
+  } else {
+    // instance projection for every (padded) instance of every bag at once: M = n_bags * Lmax, then the attention layer(s)
+    if (int rc = gemm_nt(d_bags, w->D, w->w_inst, w->D, hbuf, w->H, w->b_inst, rows, w->H, w->D, 1, s)) return rc;
+    if (int rc = gemm_nt(hbuf, w->H, w->w_v, w->H, abuf, NA, nullptr, rows, w->A, w->H, 0, s)) return rc;
+    if (w->gated)
+      if (int rc = gemm_nt(hbuf, w->H, w->w_u, w->H, abuf + w->A, NA, nullptr, rows, w->A, w->H, 0, s)) return rc;
+    vu = abuf;
+  }
+  const size_t smem = (size_t)Lmax * sizeof(float);
+  PDF_REQUIRE(smem <= 200 * 1024, "pdf_mil_sweep: bag too large for shared memory");
+  if (smem > 48 * 1024) PDF_CHECK_CUDA(cudaFuncSetAttribute(mil_pool_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+  mil_pool_kernel<<<n_bags, 256, smem, s>>>(hbuf, vu, scores, d_len, Lmax, *w, n_bags, n_scenarios, d_live, d_prob);
+  PDF_CHECK_LAUNCH();
+  return PDF_OK;
 }
 
 extern "C" int pdf_mil_forward(const pdf_mil_weights* w, int n_bags, int Lmax, const float* d_bags, const int32_t* d_len,
                                void* d_workspace, float* d_prob, pdf_stream_t stream) {
-  PDF_REQUIRE(w && n_bags > 0 && Lmax > 0 && d_bags && d_len && d_workspace && d_prob, "pdf_mil_forward: bad arguments");
-  PDF_REQUIRE(w->D > 0 && w->H > 0 && w->H <= 2048 && w->A > 0, "pdf_mil_forward: bad dims");
-  PDF_REQUIRE(w->w_inst && w->b_inst && w->w_v && w->b_v && w->w_w && w->b_w && w->w_cls && w->b_cls && (!w->gated || (w->w_u && w->b_u)),
-              "pdf_mil_forward: null weight pointer");
-  cudaStream_t s = as_stream(stream);
-  float* hbuf = reinterpret_cast<float*>(d_workspace);
-  // instance projection for every (padded) instance of every bag at once: M = n_bags * Lmax
-  if (int rc = gemm_nt(d_bags, w->D, w->w_inst, w->D, hbuf, w->H, w->b_inst, n_bags * Lmax, w->H, w->D, 1, s)) return rc;
-  const size_t smem = ((size_t)Lmax + 8 * (size_t)w->H) * sizeof(float);
-  PDF_REQUIRE(smem <= 200 * 1024, "pdf_mil_forward: bag too large for shared memory");
-  if (smem > 48 * 1024) PDF_CHECK_CUDA(cudaFuncSetAttribute(mil_pool_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-  mil_pool_kernel<<<n_bags, 256, smem, s>>>(hbuf, d_len, Lmax, *w, d_prob);
-  PDF_CHECK_LAUNCH();
-  return PDF_OK;
+  return pdf_mil_sweep(w, n_bags, Lmax, d_bags, d_len, 1, nullptr, PDF_PREC_F32, d_workspace, d_prob, stream);
 }
 
 extern "C" size_t pdf_moddrop_workspace_bytes(const pdf_mlp* net, int n_subjects) {

@@ -55,6 +55,10 @@ bool halo_eligible(const pdf_op& op);
 bool hs_eligible(const pdf_op& op);
 int launch_conv3x3_hs(const TcConv& tc, cudaStream_t s);
 int launch_conv3x3_halo(const TcConv& tc, cudaStream_t s);
+// tcgen05 kind::tf32 GEMM on f32 operands (mil_tc.cu): mode 0 out[M,N] = relu(A B^T + bias); mode 1 out[M] = attention score
+bool gemm_tf32_supported(int N, int K);
+int launch_gemm_tf32(const float* A, const float* B, int M, int N, int K, int mode, int gated, int A_dim, const float* bias,
+                     const float* w_w, const float* b_w, float* out, cudaStream_t s);
 bool pw_eligible(const pdf_op& op);
 int prepare_conv_pw(const pdf_op& op, TcConv* tc);
 int launch_conv_pw(const TcConv& tc, cudaStream_t s);

@@ -22,7 +22,7 @@ OUT_BF16_C1_PAD = 2
 STEM_PAD_LO = 5
 
 OP_CONV, OP_MAXPOOL, OP_AVGPOOL, OP_STEM_IM2COL, OP_STEM_FUSED = 0, 1, 2, 3, 4
-PREC_F32, PREC_BF16 = 0, 1
+PREC_F32, PREC_BF16, PREC_TF32 = 0, 1, 2
 
 
 class PreprocCfg(C.Structure):
@@ -113,6 +113,7 @@ PROTOTYPES = {
     "pdf_slice_mean": (C.c_int, [C.c_int, C.c_int, C.c_int, _P, _P, _P, _P]),
     "pdf_mil_workspace_bytes": (C.c_size_t, [C.POINTER(MilWeights), C.c_int, C.c_int]),
     "pdf_mil_forward": (C.c_int, [C.POINTER(MilWeights), C.c_int, C.c_int, _P, _P, _P, _P, _P]),
+    "pdf_mil_sweep": (C.c_int, [C.POINTER(MilWeights), C.c_int, C.c_int, _P, _P, C.c_int, _P, C.c_int, _P, _P, _P]),
     "pdf_moddrop_workspace_bytes": (C.c_size_t, [C.POINTER(Mlp), C.c_int]),
     "pdf_moddrop_sweep": (C.c_int, [C.POINTER(Mlp), C.c_int, C.c_int, _P, _P, _P, _P, _P]),
     "pdf_moe_sweep": (C.c_int, [C.POINTER(Moe), C.c_int, C.c_int, C.POINTER(_P), _P, _P, _P]),

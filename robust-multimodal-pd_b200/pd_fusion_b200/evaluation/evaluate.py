@@ -33,6 +33,12 @@ def _sweep_probs(model, df_test, mask_test, prep_info, scenarios: List[Dict]) ->
     if kind == "mil":
         _, per = scenario_mask_tensor(df_test, scenarios, mask_test, list(mask_test.keys()))
         bags = df_test[prep_info[1]].tolist()
+        if hasattr(model, "predict_proba_sweep") and all(b is None or isinstance(b, np.ndarray) for b in bags):
+            # one upload, one projection, one pooling pass for ALL scenarios (pdf_mil_sweep): the scenario only decides where
+            # missing_prob replaces the bag's probability
+            n = len(bags)
+            mri = np.stack([np.asarray(cur["mri"]) if "mri" in cur else np.ones(n, dtype=int) for cur in per])
+            return model.predict_proba_sweep(bags, mri), per
         probs = []
         for cur in per:   # the bag tensor is padded once per call; a missing bag never reaches the device
             b = [bag if m == 1 else None for bag, m in zip(bags, cur["mri"])] if "mri" in cur else bags

@@ -19,9 +19,13 @@ def _dev_f32(t, device) -> torch.Tensor:
 
 
 class MilHead:
-    """MILAttentionNet (models/mil_attention.py:10-51) in eval mode for a batch of padded bags."""
+    """MILAttentionNet (models/mil_attention.py:10-51) in eval mode for a batch of padded bags.
 
-    def __init__(self, state_dict: Dict[str, torch.Tensor], gated: bool, missing_prob: float = 0.5, device=None):
+    precision "fp32": FFMA GEMMs, <= 5e-6 against the reference; "tf32": both linear layers as tcgen05 kind::tf32 GEMMs on the
+    f32 bags (the throughput path; needs H, (2)A in {64,128,256} and D, H multiples of 32 -- `tensor_path_ok`)."""
+
+    def __init__(self, state_dict: Dict[str, torch.Tensor], gated: bool, missing_prob: float = 0.5, device=None,
+                 precision: str = "fp32"):
         _lib.require_cuda()
         self.lib = _lib.load()
         self.device = torch.device(device if device is not None else f"cuda:{torch.cuda.current_device()}")
@@ -33,8 +37,12 @@ class MilHead:
         w.w_inst, w.b_inst = g["instance.0.weight"].data_ptr(), g["instance.0.bias"].data_ptr()
         if gated:
             w.A = g["attn_v.0.weight"].shape[0]
-            w.w_v, w.b_v = g["attn_v.0.weight"].data_ptr(), g["attn_v.0.bias"].data_ptr()
-            w.w_u, w.b_u = g["attn_u.0.weight"].data_ptr(), g["attn_u.0.bias"].data_ptr()
+            # [W_v; W_u] and [b_v; b_u] packed: the tensor path runs both attention layers as ONE [2A, H] GEMM
+            g["_attn_vu.weight"] = torch.cat([g["attn_v.0.weight"], g["attn_u.0.weight"]], dim=0).contiguous()
+            g["_attn_vu.bias"] = torch.cat([g["attn_v.0.bias"], g["attn_u.0.bias"]], dim=0).contiguous()
+            esz = 4
+            w.w_v, w.b_v = g["_attn_vu.weight"].data_ptr(), g["_attn_vu.bias"].data_ptr()
+            w.w_u, w.b_u = w.w_v + int(w.A) * int(w.H) * esz, w.b_v + int(w.A) * esz
             w.w_w, w.b_w = g["attn_w.weight"].data_ptr(), g["attn_w.bias"].data_ptr()
         else:
             w.A = g["attn.0.weight"].shape[0]
@@ -45,18 +53,44 @@ class MilHead:
         w.missing_prob = float(missing_prob)
         self.w = w
         self.D = int(w.D)
+        na = int(w.A) * (2 if gated else 1)
+        self.tensor_path_ok = int(w.H) in (64, 128, 256) and na in (64, 128, 256) and self.D % 32 == 0 and int(w.H) % 32 == 0
+        if precision not in ("fp32", "tf32"):
+            raise ValueError("precision must be 'fp32' or 'tf32'")
+        if precision == "tf32" and not self.tensor_path_ok:
+            raise ValueError("the tf32 tensor path needs H and (2)A in {64,128,256}, D and H multiples of 32")
+        self.precision = precision
+        self._ws: Optional[torch.Tensor] = None
 
-    def forward(self, bags: torch.Tensor, lens: torch.Tensor) -> torch.Tensor:
-        """bags [n, Lmax, D] f32 cuda (zero padded), lens [n] i32 cuda (0 = missing) -> prob [n] f32."""
+    def _workspace(self, n: int, lmax: int, device) -> torch.Tensor:
+        need = int(self.lib.pdf_mil_workspace_bytes(C.byref(self.w), n, lmax))
+        if self._ws is None or self._ws.numel() < need or self._ws.device != device:
+            self._ws = torch.empty(need, dtype=torch.uint8, device=device)
+        return self._ws
+
+    def sweep(self, bags: torch.Tensor, lens: torch.Tensor, live: Optional[torch.Tensor] = None, n_scenarios: int = 1,
+              out: Optional[torch.Tensor] = None) -> torch.Tensor:
+        """bags [n, Lmax, D] f32 cuda (zero padded), lens [n] i32 (0 = no bag), live [S, n] u8 (1 = the bag is present under
+        scenario s; None = present everywhere) -> prob [S, n] f32: ONE projection + pooling pass for all scenarios."""
         if bags.dtype != torch.float32 or not bags.is_cuda or not bags.is_contiguous() or bags.shape[2] != self.D:
             raise ValueError("bags must be a contiguous float32 CUDA tensor [n, Lmax, D]")
         n, lmax = int(bags.shape[0]), int(bags.shape[1])
         lens = lens.to(device=bags.device, dtype=torch.int32).contiguous()
-        ws = torch.empty(self.lib.pdf_mil_workspace_bytes(C.byref(self.w), n, lmax), dtype=torch.uint8, device=bags.device)
-        prob = torch.empty(n, dtype=torch.float32, device=bags.device)
-        _lib.check(self.lib.pdf_mil_forward(C.byref(self.w), n, lmax, bags.data_ptr(), lens.data_ptr(), ws.data_ptr(),
-                                            prob.data_ptr(), _lib.stream_ptr()), "pdf_mil_forward")
+        if live is not None:
+            live = live.to(device=bags.device, dtype=torch.uint8).contiguous()
+            n_scenarios = int(live.shape[0])
+            if tuple(live.shape) != (n_scenarios, n):
+                raise ValueError("live must be [S, n]")
+        ws = self._workspace(n, lmax, bags.device)
+        prob = out if out is not None else torch.empty((n_scenarios, n), dtype=torch.float32, device=bags.device)
+        prec = _lib.PREC_TF32 if self.precision == "tf32" else _lib.PREC_F32
+        _lib.check(self.lib.pdf_mil_sweep(C.byref(self.w), n, lmax, bags.data_ptr(), lens.data_ptr(), n_scenarios, _lib.ptr(live), prec,
+                                          ws.data_ptr(), prob.data_ptr(), _lib.stream_ptr()), "pdf_mil_sweep")
         return prob
+
+    def forward(self, bags: torch.Tensor, lens: torch.Tensor) -> torch.Tensor:
+        """bags [n, Lmax, D] f32 cuda (zero padded), lens [n] i32 cuda (0 = missing) -> prob [n] f32."""
+        return self.sweep(bags, lens)[0]
 
 
 def _fill_mlp(m: "_lib.Mlp", weights: Sequence[torch.Tensor], biases: Sequence[torch.Tensor]) -> None:

@@ -64,6 +64,8 @@ class MilAttentionModel(BaseModel):
                                           weight_decay=float(p.get("weight_decay", 0.0)))
         self.criterion = nn.BCELoss(reduction="none")
         self.pos_weight = float(p["pos_weight"]) if (p.get("class_weight") != "balanced" and p.get("pos_weight") is not None) else None
+        # "fp32" (default: FFMA GEMMs, <= 5e-6 against the reference) | "tf32" (tcgen05 kind::tf32 projection, the throughput path)
+        self.precision = str(p.get("precision", "fp32"))
         self._head: Optional[MilHead] = None
 
     # -- training: torch autograd on the device (not the accelerated path) -----------------------
@@ -115,12 +117,25 @@ class MilAttentionModel(BaseModel):
     # -- inference: one launch over all bags ------------------------------------------------------
     def _get_head(self) -> MilHead:
         if self._head is None:
-            self._head = MilHead(self.model.state_dict(), self.gated, self.missing_prob, device=get_torch_device())
+            self._head = MilHead(self.model.state_dict(), self.gated, self.missing_prob, device=get_torch_device(),
+                                 precision=self.precision)
         return self._head
 
     def invalidate(self):
         """Call after mutating `self.model` weights in place (load_state_dict etc.)."""
         self._head = None
+
+    def _upload(self, bags, keep):
+        """Pads the bags listed in `keep` into one [n, Lmax, D] device tensor (once per call, whatever the number of scenarios)."""
+        head = self._get_head()
+        lmax = max(bags[i].shape[0] for i in keep)
+        X = np.zeros((len(keep), lmax, head.D), dtype=np.float32)
+        lens = np.zeros(len(keep), dtype=np.int32)
+        for j, i in enumerate(keep):
+            b = np.asarray(bags[i], dtype=np.float32)
+            X[j, : b.shape[0]] = b
+            lens[j] = b.shape[0]
+        return head, torch.from_numpy(X).to(head.device), torch.from_numpy(lens).to(head.device)
 
     def predict_proba(self, bags: List[Optional[np.ndarray]], masks=None) -> np.ndarray:
         mri = masks["mri"] if isinstance(masks, dict) and "mri" in masks else None
@@ -129,16 +144,26 @@ class MilAttentionModel(BaseModel):
         out = np.full(n, self.missing_prob, dtype=np.float64)
         if not live:
             return out
-        head = self._get_head()
-        lmax = max(bags[i].shape[0] for i in live)
-        X = np.zeros((len(live), lmax, head.D), dtype=np.float32)
-        lens = np.zeros(len(live), dtype=np.int32)
-        for j, i in enumerate(live):
-            b = np.asarray(bags[i], dtype=np.float32)
-            X[j, : b.shape[0]] = b
-            lens[j] = b.shape[0]
-        prob = head.forward(torch.from_numpy(X).to(head.device), torch.from_numpy(lens).to(head.device))
-        out[live] = prob.cpu().numpy().astype(np.float64)
+        head, X, lens = self._upload(bags, live)
+        out[live] = head.forward(X, lens).cpu().numpy().astype(np.float64)
+        return out
+
+    def predict_proba_sweep(self, bags: List[Optional[np.ndarray]], mri_masks: Optional[np.ndarray]) -> np.ndarray:
+        """All scenarios of evaluate_model at once (evaluation/evaluate.py:32-37 re-runs predict_proba per scenario with the
+        dropped bags set to None): mri_masks [S, N] {0,1} (None = one scenario, everything present) -> prob [S, N] float64.
+        Bags are padded and uploaded ONCE, projected and pooled ONCE; the scenario only selects missing_prob."""
+        n = len(bags)
+        S = 1 if mri_masks is None else int(np.asarray(mri_masks).shape[0])
+        out = np.full((S, n), self.missing_prob, dtype=np.float64)
+        have = [i for i, b in enumerate(bags) if b is not None]
+        if mri_masks is not None:
+            mm = np.asarray(mri_masks)
+            have = [i for i in have if mm[:, i].any()]              # a bag dropped by every scenario never reaches the device
+        if not have:
+            return out
+        head, X, lens = self._upload(bags, have)
+        live = None if mri_masks is None else torch.from_numpy(np.ascontiguousarray(np.asarray(mri_masks)[:, have] != 0).astype(np.uint8))
+        out[:, have] = head.sweep(X, lens, live, S).cpu().numpy().astype(np.float64)
         return out
 
     def save(self, path):

@@ -94,3 +94,67 @@ def test_every_mask_sweep_matches_oracle():
     for s in range(8):
         ref = O.moddrop_predict_proba(sdn, dims, X, {m: mk[s][:, i] for i, m in enumerate(O.MODALITIES)})
         np.testing.assert_allclose(p[s].cpu().numpy(), ref, atol=5e-6, rtol=0)
+
+
+def _mil_case(g, tag):
+    cfg = json.loads(str(g[f"{tag}/cfg"]))
+    sd = {k.split("/sd/")[1]: torch.from_numpy(g[k]) for k in g.files if k.startswith(f"{tag}/sd/")}
+    none = g[f"{tag}/none"]
+    bags = [None if none[i] else g[f"{tag}/bag{i}"] for i in range(len(none))]
+    return cfg, sd, bags, g[f"{tag}/mask_mri"], g[f"{tag}/prob"]
+
+
+@pytest.mark.parametrize("tag", ["mil_gated", "mil_plain", "mil_c3"])
+def test_mil_sweep_equals_per_scenario_reference(golden, tag):
+    """pdf_mil_sweep: ONE projection + pooling pass for all scenarios.  Scenario 0 is the golden mask (the reference's own
+    probabilities), the others are further drop patterns; each row must equal what the reference's per-scenario call returns
+    (its probability where the bag is live, missing_prob elsewhere) -- FP32 path, 5e-6."""
+    from pd_fusion_b200.models.mil_attention import MilAttentionModel
+    g = golden("heads")
+    cfg, sd, bags, mask, ref = _mil_case(g, tag)
+    n = len(bags)
+    params = {"hidden_dim": sd["instance.0.weight"].shape[0], "attn_dim": (sd["attn_v.0.weight"] if cfg["gated"] else sd["attn.0.weight"]).shape[0],
+              "gated": cfg["gated"], "missing_prob": 0.5}
+    model = MilAttentionModel(cfg["D"], params)
+    model.model.load_state_dict(sd)
+    model.invalidate()
+    rng = np.random.default_rng(3)
+    mm = np.stack([mask, np.ones(n, int), np.zeros(n, int), rng.integers(0, 2, n), rng.integers(0, 2, n)])
+    probs = model.predict_proba_sweep(bags, mm)
+    assert probs.shape == (5, n) and probs.dtype == np.float64
+    np.testing.assert_allclose(probs[0], ref, atol=5e-6, rtol=0)
+    full = model.predict_proba(bags, masks={"mri": np.ones(n, int)})
+    for s in range(5):
+        want = np.where((mm[s] != 0) & np.array([b is not None for b in bags]), full, 0.5)
+        np.testing.assert_allclose(probs[s], want, atol=1e-7, rtol=0)
+    assert np.all(probs[2] == 0.5)
+
+
+@pytest.mark.parametrize("D,H,A,gated,L", [(2048, 256, 128, True, 48), (2048, 256, 128, False, 72), (512, 128, 64, True, 24), (96, 64, 64, False, 5)])
+def test_mil_tensor_path(D, H, A, gated, L):
+    """tcgen05 kind::tf32 projection + attention GEMM (scores in the epilogue) against the FP32 path on ragged bags, several
+    row tiles per CTA.  TF32 products carry a 10-bit mantissa: probabilities agree to 2e-3 (typically 1e-4)."""
+    from pd_fusion_b200.models.mil_attention import MILAttentionNet
+    torch.manual_seed(D + H + L)
+    sd = MILAttentionNet(D, H, A, 0.2, gated=gated).state_dict()
+    n = 700 if D <= 512 else 67
+    rng = np.random.default_rng(L)
+    lens = rng.integers(1, L + 1, n).astype(np.int32)
+    lens[::9] = 0
+    X = rng.standard_normal((n, L, D)).astype(np.float32) * np.float32(1.5)
+    for i in range(n):
+        X[i, lens[i]:] = 0
+    live = rng.integers(0, 2, (7, n)).astype(np.uint8)
+    Xd, ld, lv = torch.from_numpy(X).cuda(), torch.from_numpy(lens).cuda(), torch.from_numpy(live).cuda()
+    p32 = MilHead(sd, gated, 0.37, precision="fp32").sweep(Xd, ld, lv)
+    ptf = MilHead(sd, gated, 0.37, precision="tf32").sweep(Xd, ld, lv)
+    torch.cuda.synchronize()
+    p32, ptf = p32.cpu().numpy(), ptf.cpu().numpy()
+    dead = (live == 0) | (lens[None, :] == 0)
+    assert np.all(ptf[dead] == np.float32(0.37)) and np.all(p32[dead] == np.float32(0.37))
+    assert p32[~dead].std() > 1e-3                        # the comparison is not between constants
+    np.testing.assert_allclose(ptf, p32, atol=2e-3, rtol=0)
+    # and the FP32 path against the oracle on a few bags
+    sdn = {k: v.numpy() for k, v in sd.items()}
+    ref = O.mil_predict_proba(sdn, [X[i, :lens[i]] if lens[i] else None for i in range(8)], gated, None, 0.37)
+    np.testing.assert_allclose(MilHead(sd, gated, 0.37).forward(Xd[:8].contiguous(), ld[:8]).cpu().numpy(), ref, atol=5e-6, rtol=0)

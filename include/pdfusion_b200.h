@@ -198,6 +198,8 @@ typedef struct pdf_plan pdf_plan; /* opaque: validated ops + pre-encoded TMA des
 /* tuning / A-B hook for the pointwise kernel (conv_pw.cu): 0 = 1x1 convolutions stay on the generic kernel, 1 = default
  * policy, 2 = every eligible 1x1 convolution.  Affects plans created afterwards. */
 int pdf_debug_set_pw(int mode);
+/* persistent kernels size their grids for `cap` SMs instead of the device's (0 = off): two streams can then share the GPU */
+int pdf_debug_set_sm_cap(int cap);
 /* ring depth (2..6) and staging-buffer count (2..4) of conv_pw_kernel launches (the ring shrinks to what fits 227 KB) */
 int pdf_debug_set_pw_config(int stages, int staging_buffers);
 int pdf_plan_create(pdf_plan** out, const pdf_op* ops, int n_ops);

@@ -21,7 +21,11 @@ bool pdl_enabled() { return g_pdl.load(std::memory_order_relaxed); }
 
 void count_launch(int n) { g_launches.fetch_add((uint64_t)n, std::memory_order_relaxed); }
 
+static std::atomic<int> g_sm_cap{0};
+
 int num_sms() {
+  const int cap = g_sm_cap.load(std::memory_order_relaxed);
+  if (cap > 0) return cap;
   static int sms = 0;
   if (sms == 0) {
     int dev = 0;
@@ -36,6 +40,11 @@ int num_sms() {
 extern "C" int pdf_version(void) { return 100; }
 extern "C" int pdf_debug_enable_pdl(int enable) {
   pdf::g_pdl.store(enable != 0, std::memory_order_relaxed);
+  return PDF_OK;
+}
+/* tuning hook: persistent kernels size their grids for `cap` SMs instead of the device's (0 = off): lets two streams share the GPU */
+extern "C" int pdf_debug_set_sm_cap(int cap) {
+  pdf::g_sm_cap.store(cap < 0 ? 0 : cap, std::memory_order_relaxed);
   return PDF_OK;
 }
 extern "C" const char* pdf_last_error(void) { return pdf::g_error; }

@@ -128,6 +128,7 @@ PROTOTYPES = {
     "pdf_debug_set_hs_mode": (C.c_int, [C.c_int]),
     "pdf_debug_disable_halo": (C.c_int, [C.c_int]),
     "pdf_debug_set_pw": (C.c_int, [C.c_int]),
+    "pdf_debug_set_sm_cap": (C.c_int, [C.c_int]),
     "pdf_debug_set_pw_config": (C.c_int, [C.c_int, C.c_int]),
 }
 

@@ -24,7 +24,7 @@ import torch
 
 from .. import _lib
 from ..backbone import RESNET_SPECS, ResNet2D
-from ..parallel import all_gather_rows, shard_range, world
+from ..parallel import all_gather_rows, barrier, init_distributed, shard_range, world
 from ..pipeline import EmbeddingPipeline
 from ..preprocess import VolumePreprocessor
 from ..utils.npz_writer import savez_compressed_parallel
@@ -261,7 +261,9 @@ def embed_manifest(df: pd.DataFrame, backbone: str, target_shape: Sequence[int],
     if tta > 1 and tta_seeds is None:                   # the reference's per-subject Generator seed (process-salted hash)
         ids = df["subject_id"].tolist() if "subject_id" in df.columns else [""] * len(df)
         tta_seeds = [subject_seed(s) for s in ids]
-    rank, local_rank, ws = world()
+    # a library caller under torchrun gets the same sharding as the CLIs: the process group is created here when the
+    # environment says WORLD_SIZE > 1 (all_gather_rows would otherwise silently return the local shard)
+    rank, local_rank, ws = init_distributed()
     dev = torch.device("cuda", local_rank)
     torch.cuda.set_device(dev)
     precision = os.environ.get("PD_FUSION_B200_PRECISION", "bf16")
@@ -304,6 +306,9 @@ def embed_manifest(df: pd.DataFrame, backbone: str, target_shape: Sequence[int],
     if ws > 1:
         emb, avg, nsl = all_gather_rows(emb, n_rows), all_gather_rows(avg, n_rows), all_gather_rows(nsl, n_rows)
     torch.cuda.synchronize()
+    if emb.shape[0] != n_rows or avg.shape[0] != n_rows:
+        raise RuntimeError(f"embedding table has {emb.shape[0]} rows for {n_rows} manifest rows (rank {rank} of {ws}): "
+                           "the shards were not gathered")
     nsl_h = nsl.cpu().numpy()
     if (nsl_h != L).any():
         bad = int(np.argmax(nsl_h != L))
@@ -334,8 +339,11 @@ def build_resnet2d_embeddings(manifest_path: Path, cache_dir: Path, config: Dict
     emb64 = avg.astype(np.float64)                      # the reference stores python floats -> float64 columns
     cols.update({f"mri_resnet_{k}": emb64[:, k] for k in range(emb64.shape[1])})
     emb_df = pd.DataFrame(cols)
-    if world()[0] == 0:
-        emb_df.to_parquet(out_path, index=False)
+    if world()[0] == 0:                                 # written under a temporary name and renamed: a reader never sees half a file
+        tmp = out_path.with_name(out_path.name + f".tmp{os.getpid()}")
+        emb_df.to_parquet(tmp, index=False)
+        os.replace(tmp, out_path)
+    barrier()                                           # every rank returns only once the cache file exists
     return emb_df
 
 
@@ -353,8 +361,11 @@ def build_resnet2d_mil_embeddings(manifest_path: Path, out_dir: Path, cfg: Dict,
         raise ValueError(f"all input arrays must have the same shape: subject row {row} has {n} slices, expected {emb.shape[1]}")
     if world()[0] == 0:
         # same npz as np.savez_compressed (scripts/build_resnet2d_mil_embeddings.py:162-168), deflated by a thread pool
-        savez_compressed_parallel(out_path, embeddings=emb.astype(np.float32), subject_id=df["subject_id"].values,
+        tmp = out_path.with_name(out_path.name + f".tmp{os.getpid()}.npz")
+        savez_compressed_parallel(tmp, embeddings=emb.astype(np.float32), subject_id=df["subject_id"].values,
                                   session=df["session"].values, label=df["label"].values)
+        os.replace(tmp, out_path)
+    barrier()
     return out_path
 
 
@@ -377,3 +388,27 @@ def load_resnet2d_mil_embeddings(manifest_path: Path, cache_dir: Path, config: D
     df = pd.DataFrame({"subject_id": data["subject_id"], "session": data["session"], "label": data["label"]})
     df["mri_mil"] = list(data["embeddings"])
     return df
+
+
+def load_cnn_embeddings(manifest_path: Path, cache_dir: Path, config: Dict) -> pd.DataFrame:
+    """Reader of the `cnn3d` cache (reference: data/openneuro_features.py:106-119); the builder of that feature mode
+    (scripts/build_cnn3d_embeddings.py, a 3-D conv auto-encoder) is outside the ResNet2D path and not rebuilt here."""
+    cache_dir = Path(cache_dir)
+    cache_dir.mkdir(parents=True, exist_ok=True)
+    out_path = cache_dir / f"embeddings_{_hash_file(manifest_path)}_{_hash_config(config)}.parquet"
+    if not out_path.exists():
+        raise FileNotFoundError(f"Embeddings not found at {out_path}. Run scripts/build_cnn3d_embeddings.py to generate them.")
+    return pd.read_parquet(out_path)
+
+
+def load_simple_features(manifest_path: Path, cache_dir: Path, config: Dict) -> pd.DataFrame:
+    """Reader of the `simple` (histogram / grid statistics) cache, `features_<mh>_<ch>.parquet` (reference:
+    data/openneuro_features.py:75-104).  The reference computes a missing cache on the fly on the CPU; that feature mode is
+    outside the ResNet2D path and this package has no CPU fallback, so a missing cache is an error."""
+    cache_dir = Path(cache_dir)
+    cache_dir.mkdir(parents=True, exist_ok=True)
+    out_path = cache_dir / f"features_{_hash_file(manifest_path)}_{_hash_config(config)}.parquet"
+    if not out_path.exists():
+        raise FileNotFoundError(f"Simple features not found at {out_path}: build them with the reference's load_simple_features "
+                                "(this feature mode is not part of the B200 path).")
+    return pd.read_parquet(out_path)

@@ -46,6 +46,10 @@ def _sweep_probs(model, df_test, mask_test, prep_info, scenarios: List[Dict]) ->
         return np.stack(probs), per
     if kind == "moe":
         mods = list(prep_info.keys())
+        if mods != sorted(mods):
+            # MoENet orders its experts by sorted(modality) while the reference's evaluate feeds the router in caller order
+            # (evaluation/evaluate.py:54-63): an unsorted prep_info would silently pair router outputs with the wrong experts
+            raise ValueError(f"MoE prep_info modalities must be in sorted order, got {mods}")
         masks, per = scenario_mask_tensor(df_test, scenarios, mask_test, mods)
         X = {m: preprocess_features(df_test, prep_info[m][2], prep_info[m][0], prep_info[m][1])[0] for m in mods}
         if hasattr(model, "predict_proba_sweep"):

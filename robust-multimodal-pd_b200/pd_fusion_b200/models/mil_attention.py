@@ -105,7 +105,10 @@ class MilAttentionModel(BaseModel):
                     auc = -1.0
                 if auc > best_auc:
                     best_auc, bad = auc, 0
-                    best_state = {k: v.detach().clone() for k, v in self.model.state_dict().items()}
+                    # the reference keeps `self.model.state_dict()` WITHOUT cloning (models/mil_attention.py:147): it aliases the
+                    # live parameters, so restoring it below is a no-op and the final weights are the last epoch's.  A drop-in
+                    # trains to the same weights; MilAttentionFineTuneModel keeps the same quirk.
+                    best_state = self.model.state_dict()
                 else:
                     bad += 1
                     if bad >= patience:

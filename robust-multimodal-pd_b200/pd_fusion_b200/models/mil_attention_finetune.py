@@ -115,20 +115,38 @@ class MilAttentionFineTuneModel(BaseModel):
         vol = onf._normalize_volume_for_resnet(onf._load_volume(bag, target_shape=self.target_shape))
         return np.concatenate([onf._select_slices(vol, a, c) for a, c in zip(self.axes, self.counts)], axis=0).astype(np.float32, copy=False)
 
+    def _capacity(self, longest: int) -> int:
+        """Images per encoder pass: a FIXED capacity (bag_batch_size bags of the nominal length, at least 256 images), so that ONE
+        encoder instance -- weights plus activation buffers -- serves every call whatever the number of live bags.  The reference
+        goes bag by bag in 16-slice chunks (mil_attention_finetune.py:141-150); memory here is bounded the same way."""
+        cap = int(os.environ.get("PD_FUSION_B200_FT_IMAGES", "0")) or max(256, self.bag_batch_size * int(sum(self.counts)))
+        return max(cap, int(longest))
+
     def _embed_slices(self, stacks: Sequence[torch.Tensor]) -> List[torch.Tensor]:
-        """Per-slice embeddings of ready slice stacks ([L_i, H, W] f32 CUDA tensors in [0,1]); one encoder pass."""
-        total = sum(int(s.shape[0]) for s in stacks)
-        enc = self._encoder(total)
+        """Per-slice embeddings of ready slice stacks ([L_i, H, W] f32 CUDA tensors in [0,1]): the bags go through ONE
+        fixed-capacity encoder in groups of whole bags, the unused tail of the input buffer zeroed (as EmbeddingPipeline.embed does)."""
+        cap = self._capacity(max(int(s.shape[0]) for s in stacks))
+        enc = self._encoder(cap)
         H, W = int(stacks[0].shape[1]), int(stacks[0].shape[2])
         pre = self._resizer(H, W)
-        allsl = torch.cat(list(stacks), dim=0).contiguous().view(1, total, H, W)
         dst = enc.input_padded if enc.input_padded is not None else enc.input
-        pre.resize_slices(allsl, out=dst.view((1, total) + tuple(dst.shape[1:])))
-        emb = enc.forward(None)
-        out, k = [], 0
-        for s in stacks:
-            out.append(emb[k:k + int(s.shape[0])])
-            k += int(s.shape[0])
+        out: List[torch.Tensor] = []
+        i = 0
+        while i < len(stacks):
+            j, total = i, 0
+            while j < len(stacks) and total + int(stacks[j].shape[0]) <= cap:
+                total += int(stacks[j].shape[0])
+                j += 1
+            allsl = torch.cat(list(stacks[i:j]), dim=0).contiguous().view(1, total, H, W)
+            pre.resize_slices(allsl, out=dst[:total].view((1, total) + tuple(dst.shape[1:])))
+            if total < cap:
+                enc.input[total:].zero_()
+            emb = enc.forward(None)[:total].clone()          # the encoder's output buffer is reused by the next group
+            k = 0
+            for s in stacks[i:j]:
+                out.append(emb[k:k + int(s.shape[0])])
+                k += int(s.shape[0])
+            i = j
         return out
 
     def _augment(self, stack: torch.Tensor, rng: np.random.Generator) -> torch.Tensor:
@@ -160,7 +178,10 @@ class MilAttentionFineTuneModel(BaseModel):
         head = self._head()
         rng = np.random.default_rng()
         for _ in range(passes):
-            cur = [self._augment(s, rng) for s in stacks] if self.tta_inference > 1 else stacks
+            # the reference augments inside _load_bag only when train_aug is on AND the bag is a path (ndarray bags return before
+            # the augmentation, mil_attention_finetune.py:114-125)
+            cur = [self._augment(s, rng) if (self.tta_inference > 1 and self.train_aug and not isinstance(bags[i], np.ndarray)) else s
+                   for s, i in zip(stacks, live)]
             embs = self._embed_slices(cur)
             lmax = max(int(e.shape[0]) for e in embs)
             X = torch.zeros((len(embs), lmax, self.emb_dim), dtype=torch.float32, device=self.device)

@@ -39,17 +39,36 @@ def shard_range(n_rows: int, rank: int, world_size: int) -> Tuple[int, int]:
     return start, min(n_rows, start + per)
 
 
-def all_gather_rows(local: torch.Tensor, n_rows_total: int) -> torch.Tensor:
+_GATHER_BUFFERS: dict = {}
+
+
+def all_gather_rows(local: torch.Tensor, n_rows_total: int, out: torch.Tensor | None = None) -> torch.Tensor:
     """Assembles the row-sharded table on every rank.  `local` holds this rank's shard_range rows (any trailing
-    dims).  Shards are padded to ceil(n/G) rows (NCCL all-gather needs equal sizes) and the pad is trimmed."""
+    dims).  Shards are padded to ceil(n/G) rows (NCCL all-gather needs equal sizes) and the pad is trimmed.
+    The staging shard and the gathered table are cached per (shape, dtype, device): a step loop that gathers the same
+    table every step allocates nothing (the result is overwritten by the next call with the same signature; pass `out` or
+    clone to keep it)."""
     if not (torch.distributed.is_available() and torch.distributed.is_initialized()):
         return local
     ws = torch.distributed.get_world_size()
     per = -(-n_rows_total // ws)
-    pad = torch.zeros((per,) + tuple(local.shape[1:]), dtype=local.dtype, device=local.device)
-    pad[: local.shape[0]].copy_(local)
-    out = torch.empty((ws * per,) + tuple(local.shape[1:]), dtype=local.dtype, device=local.device)
-    torch.distributed.all_gather_into_tensor(out, pad)
+    tail = tuple(local.shape[1:])
+    if local.shape[0] == per and local.is_contiguous():
+        src = local                                      # equal shards: gather straight from the caller's tensor
+    else:
+        key = ("pad", per, tail, local.dtype, local.device)
+        src = _GATHER_BUFFERS.get(key)
+        if src is None:
+            src = _GATHER_BUFFERS[key] = torch.zeros((per,) + tail, dtype=local.dtype, device=local.device)
+        src[: local.shape[0]].copy_(local)
+        if local.shape[0] < per:
+            src[local.shape[0]:].zero_()
+    if out is None:
+        key = ("out", ws * per, tail, local.dtype, local.device)
+        out = _GATHER_BUFFERS.get(key)
+        if out is None:
+            out = _GATHER_BUFFERS[key] = torch.empty((ws * per,) + tail, dtype=local.dtype, device=local.device)
+    torch.distributed.all_gather_into_tensor(out, src)
     return out[:n_rows_total]
 
 

@@ -168,7 +168,7 @@ def test_bench_reference_arm_contract():
     assert line["value"] > 0 and line["higher_is_better"] is True and line["n_gpus"] == 1 and line["steps"] == 1
     assert line["cpu_baseline"]["kind"] == "port" and line["cpu_baseline"]["cores"] >= 1 and line["cpu_baseline"]["value"] == line["value"]
     assert line["e2e"] == {"value": line["value"], "unit": "subjects/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}
-    assert line["config"]["workload"] == "configs/openneuro_ds001907_resnet2d.yaml"
+    assert line["config"]["workload"] == "configs/openneuro_ds001907_resnet2d_mil.yaml"      # the metric's own config is the default
 
 
 def test_flop_accounting_matches_survey():
@@ -317,3 +317,41 @@ def test_lowering_bf16_buffers_are_written_before_read():
                         assert (b2, o2) not in (refs["d_in"], refs["d_out"]) and o2 + n2 <= extents[b2]
                         written[b2][o2:o2 + n2] = True
                 assert written["output"].all()
+
+
+def test_load_openneuro_ds001907_modes(tmp_path, monkeypatch):
+    """Cache consumer (reference: data/openneuro_ds001907.py:17-82): env override of the manifest, feature_mode dispatch onto the
+    cache files the builders write, `diagnosis` from `label`, masks clinical = datspect = 0 and mri from the data."""
+    import pandas as pd
+    from pd_fusion_b200.data.openneuro_ds001907 import load_openneuro_ds001907
+    from pd_fusion_b200.data.openneuro_features import _hash_config, _hash_file
+    man = tmp_path / "m.csv"
+    pd.DataFrame({"subject_id": ["a", "b", "c"], "session": [1, 1, 2], "label": [0, 1, 1], "t1wbrain_path": ["x", "y", "z"]}).to_csv(man, index=False)
+    cfg = {"backbone": "resnet18", "slice_count": 4}
+    cache = tmp_path / "cache"
+    cache.mkdir()
+    # resnet2d: parquet with mri_resnet_* columns (one subject without features)
+    df = pd.DataFrame({"subject_id": ["a", "b", "c"], "session": [1, 1, 2], "label": [0, 1, 1],
+                       "mri_resnet_0": [0.1, np.nan, 0.3], "mri_resnet_1": [1.0, np.nan, 3.0]})
+    df.to_parquet(cache / f"resnet2d_{_hash_file(man)}_{_hash_config(cfg)}.parquet", index=False)
+    monkeypatch.setenv("PD_FUSION_DS001907_MANIFEST", str(man))
+    out, masks = load_openneuro_ds001907({"manifest_path": "does/not/exist.csv", "feature_mode": "resnet2d", "resnet2d_cache_dir": str(cache),
+                                          "resnet2d_config": cfg})
+    assert list(out["diagnosis"]) == [0, 1, 1]
+    assert masks["mri"].tolist() == [1, 0, 1] and masks["clinical"].tolist() == [0, 0, 0] and masks["datspect"].tolist() == [0, 0, 0]
+    # resnet2d_mil: npz with [S, L, D] bags
+    emb = np.arange(3 * 2 * 5, dtype=np.float32).reshape(3, 2, 5)
+    np.savez_compressed(cache / f"resnet2d_mil_{_hash_file(man)}_{_hash_config(cfg)}.npz", embeddings=emb,
+                        subject_id=np.array(["a", "b", "c"], dtype=object), session=np.array([1, 1, 2]), label=np.array([0, 1, 1]))
+    out, masks = load_openneuro_ds001907({"feature_mode": "resnet2d_mil", "resnet2d_cache_dir": str(cache), "resnet2d_config": cfg})
+    assert np.array_equal(out["mri_mil"][1], emb[1]) and masks["mri"].tolist() == [1, 1, 1]
+    # fine-tune mode: the manifest itself, paths in mri_mil
+    out, masks = load_openneuro_ds001907({"feature_mode": "resnet2d_mil_ft"})
+    assert list(out["mri_mil"]) == ["x", "y", "z"] and masks["mri"].tolist() == [1, 1, 1]
+    with pytest.raises(ValueError):
+        load_openneuro_ds001907({"feature_mode": "nope"})
+    with pytest.raises(FileNotFoundError):
+        load_openneuro_ds001907({"feature_mode": "cnn3d", "embedding_cache_dir": str(cache)})
+    monkeypatch.delenv("PD_FUSION_DS001907_MANIFEST")
+    with pytest.raises(FileNotFoundError):
+        load_openneuro_ds001907({"manifest_path": str(tmp_path / "missing.csv"), "feature_mode": "resnet2d"})

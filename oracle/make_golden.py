@@ -401,9 +401,81 @@ def gold_heads():
           "moe", json.loads(str(out["moe/metrics"]))["full_observation"]["roc_auc"])
 
 
+def gold_c45():
+    """BASELINE configs 4 and 5 at their full sizes.
+    C5: the UNMODIFIED MIL script on one synthetic 256x256x176 volume with resnet50, slice axes 0/1/2 x 24 (L = 72), --tta 2,
+        batch size 8, the augmentation amplitudes of configs/data_openneuro_ds001907_resnet2d_mil_multi.yaml.
+    C4: MoE over imaging (512) + clinical (10) features, N = 10 000 subjects, trained BY THE REFERENCE, its own evaluate_model sweep."""
+    out = {}
+    with tempfile.TemporaryDirectory() as td:
+        td = Path(td)
+        manifest = write_synthetic_manifest(td / "vols", 1, shape=(256, 256, 176), start=21)
+        args = ["--backbone", "resnet50", "--target-shape", "160", "160", "160", "--slice-axes", "0", "1", "2", "--slice-counts", "24", "24", "24",
+                "--input-size", "224", "--batch-size", "8", "--tta", "2", "--max-rotation-deg", "8.0", "--max-translation", "0.05",
+                "--intensity-scale", "0.1", "--intensity-shift", "0.1", "--noise-std", "0.02"]
+        od = td / "out"
+        argv = sys.argv
+        sys.argv = ["build_resnet2d_mil_embeddings.py", "--manifest", str(manifest), "--out-dir", str(od)] + args
+        try:
+            runpy.run_path(str(REF / "scripts" / "build_resnet2d_mil_embeddings.py"), run_name="__main__")
+        finally:
+            sys.argv = argv
+        d = np.load([p for p in od.iterdir() if p.suffix == ".npz"][0], allow_pickle=True)
+        import pandas as pd
+        df = pd.read_csv(manifest)
+        out["c5/emb"] = d["embeddings"].astype(np.float32)
+        out["c5/argv"] = np.array(args)
+        out["c5/seeds"] = np.array([abs(hash(str(s))) % (2 ** 32) for s in df["subject_id"]], dtype=np.int64)
+        out["c5/targs"] = np.array(json.dumps(dict(max_rotation_deg=8.0, max_translation=0.05, intensity_scale=0.1, intensity_shift=0.1, noise_std=0.02)))
+        print("c5", out["c5/emb"].shape, float(np.abs(out["c5/emb"]).mean()), out["c5/seeds"])
+
+    import yaml
+    scen_cfg = {"scenarios": yaml.safe_load((REF / "configs" / "eval_missingness.yaml").read_text())["scenarios"]}
+    out["c4/scenarios"] = np.array(json.dumps(scen_cfg))
+    dims = {"clinical": 10, "datspect": 0, "mri": 512}
+    N = 10000
+    df, masks = synthetic_table(N, dims, seed=44, mask_seed=9)
+    y = df["diagnosis"].values
+    from pd_fusion.data.preprocess import preprocess_features
+    mods = ["clinical", "mri"]
+    prep, Xd = {}, {}
+    for m in mods:
+        cols = [c for c in df.columns if c.startswith(m + "_")]
+        Xm, _, sc_m = preprocess_features(df, cols)
+        prep[m] = (None, sc_m, cols)
+        Xd[m] = torch.FloatTensor(Xm * masks[m].reshape(-1, 1))
+    mt = torch.FloatTensor(np.stack([masks[m] for m in mods], axis=1))
+    torch.manual_seed(HEAD_SEED)
+    params = yaml.safe_load((REF / "configs" / "model_moe.yaml").read_text())["params"]
+    params = dict(params, epochs=40)
+    moe = MoEModel({m: Xd[m].shape[1] for m in mods}, params)
+    moe.train(Xd, y, mt)
+    for k, v in _sd_np(moe.model.state_dict()).items():
+        out[f"c4/sd/{k}"] = v
+    masks2 = {m: masks[m] for m in mods}
+    np.random.seed(13)
+    res = evaluate_model(moe, df, masks2, prep, scen_cfg)
+    out["c4/metrics"] = np.array(json.dumps({k: {m: float(v) for m, v in d.items()} for k, d in res.items()}))
+    np.random.seed(13)
+    probs, mk = [], []
+    for sc in scen_cfg["scenarios"]:
+        cur = apply_missingness_scenario(df, sc, masks2)
+        Xs = {}
+        for m in mods:
+            Xm, _, _ = preprocess_features(df, prep[m][2], None, prep[m][1])
+            Xs[m] = torch.FloatTensor(Xm * cur[m].reshape(-1, 1))
+        probs.append(moe.predict_proba(Xs, torch.FloatTensor(np.stack([cur[m] for m in mods], axis=1))))
+        mk.append(np.stack([cur[m] for m in mods], axis=1))
+    out["c4/probs"] = np.stack(probs).astype(np.float32)
+    out["c4/masks_seed13"] = np.packbits(np.stack(mk).astype(np.uint8), axis=1)       # [S, ceil(N/8), M]
+    out["c4/n"], out["c4/dims"], out["c4/mods"] = np.array(N), np.array(json.dumps(dims)), np.array(mods)
+    np.savez_compressed(GOLD / "c45.npz", **out)
+    print("c45.npz moe auc", json.loads(str(out["c4/metrics"]))["full_observation"]["roc_auc"], out["c4/probs"].shape)
+
+
 if __name__ == "__main__":
     GOLD.mkdir(parents=True, exist_ok=True)
-    which = sys.argv[1:] or ["preproc", "embed", "scripts", "heads", "tta", "ft"]
+    which = sys.argv[1:] or ["preproc", "embed", "scripts", "heads", "tta", "ft", "c45"]
     os.environ.setdefault("PYTHONHASHSEED", "0")
     for w in which:
         globals()[f"gold_{w}"]()

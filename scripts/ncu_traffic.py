@@ -32,7 +32,8 @@ def main():
         if i is None:
             return 0.0
         v, u = num(r[i]), units[i].lower()
-        scale = {"gbyte": 1e9, "mbyte": 1e6, "kbyte": 1e3, "byte": 1.0, "msecond": 1e3, "usecond": 1.0, "nsecond": 1e-3, "second": 1e6}
+        scale = {"gbyte": 1e9, "mbyte": 1e6, "kbyte": 1e3, "byte": 1.0, "ms": 1e3, "us": 1.0, "ns": 1e-3, "s": 1e6,
+                 "msecond": 1e3, "usecond": 1.0, "nsecond": 1e-3, "second": 1e6}
         return v * scale.get(u, 1.0)
 
     lines = ["kernel | time us | dram read MB | dram write MB | dram throughput % | sm throughput % | tensor pipe % | regs"]

@@ -165,3 +165,26 @@ def test_product_tta_draws_match_oracle(golden):
         aug = np.clip(aug + d.noise, 0.0, 1.0).astype(np.float32)
         assert np.array_equal(aug.view(np.uint32), g[f"script/aug/0/{p}"].view(np.uint32)), p
     assert params_bytes([draws[0], draws[1]]).size == 2 * 56
+
+
+def test_oracle_moe_c4_dims_vs_reference(golden):
+    """The oracle's MoE restatement at BASELINE config 4's dims (512 + 10, N = 10 000) against the reference's own probabilities."""
+    import json
+    from pd_fusion_b200.synthetic import synthetic_table
+    g = golden("c45")
+    dims, N = json.loads(str(g["c4/dims"])), int(g["c4/n"])
+    df, _ = synthetic_table(N, dims, seed=44, mask_seed=9)
+    mods = [str(m) for m in g["c4/mods"]]
+    sd = {k.split("/sd/")[1]: g[k] for k in g.files if k.startswith("c4/sd/")}
+    masks = np.unpackbits(g["c4/masks_seed13"], axis=1)[:, :N, :]
+
+    def scale(X):
+        med = np.nanmedian(X, axis=0)
+        iqr = np.nanpercentile(X, 75, axis=0) - np.nanpercentile(X, 25, axis=0)
+        iqr[iqr == 0] = 1.0
+        return ((X - med) / iqr).astype(np.float32)
+    X = {m: scale(df[[c for c in df.columns if c.startswith(m + "_")]].values) for m in mods}
+    for s in (0, 2, 5):
+        mk = masks[s].astype(np.float32)
+        p = O.moe_predict_proba(sd, {m: X[m] * mk[:, i:i + 1] for i, m in enumerate(mods)}, mk)
+        np.testing.assert_allclose(p, g["c4/probs"][s], atol=5e-6, rtol=0)

@@ -244,6 +244,59 @@ int pdf_mil_forward(const pdf_mil_weights* w, int n_bags, int Lmax, const float*
                     void* d_workspace, float* d_prob, pdf_stream_t stream);
 
 /* ------------------------------------------------------------------------------------------
+ * K5 -- training (FP32, NHWC).  Replaces torch autograd under MilAttentionFineTuneModel.train / _forward_bags
+ * (models/mil_attention_finetune.py:135-162,164-253: backbone in TRAIN mode, BatchNorm statistics per 16-slice chunk, MIL head,
+ * BCE / focal loss, backward, clip_grad_norm_, Adam) and under the heads' train loops (models/mil_attention.py:88-155,
+ * fusion_moddrop.py:69-91, moe.py:60-70).  The host walks the layer list in reverse (pd_fusion_b200/training.py).
+ * ------------------------------------------------------------------------------------------ */
+/* C[M,N] (+)= act(sum_k A(i,k) B(k,j) + bias[j]); A(i,k) = A[i*a_rs + k*a_cs], B(k,j) = B[k*b_rs + j*b_cs]; act 1 = ReLU.
+ * One entry point for x W^T (forward), dy W (dgrad) and dy^T x (wgrad) of the linear layers. */
+int pdf_gemm_f32(int M, int N, int K, const float* A, long a_rs, long a_cs, const float* B, long b_rs, long b_cs, float* C, long c_rs,
+                 const float* bias, int act, int accumulate, pdf_stream_t stream);
+/* convolution backward; geometry from `op` (n,h,w,c,k,r,s,stride,pad,ho,wo), weights [R][S][C][K] f32 as the FP32 forward path:
+ * dgrad d_dx [n,h,w,c] (+)= conv^T(d_dy [n,ho,wo,k], w);  wgrad d_dw [R][S][C][K] += x^T * dy (accumulates: zero it first). */
+int pdf_conv_dgrad_f32(const pdf_op* op, const float* d_dy, const float* d_weight, float* d_dx, int accumulate, pdf_stream_t stream);
+int pdf_conv_wgrad_f32(const pdf_op* op, const float* d_x, const float* d_dy, float* d_dw, pdf_stream_t stream);
+/* train-mode BatchNorm over row groups of the [M, C] activation matrix: group g = rows [d_goff[g], d_goff[g+1]) (one 16-slice chunk of
+ * one bag).  forward: y = (x - mean_g) * invstd_g * gamma + beta (+ residual) (ReLU); saves mean, invstd (biased variance, eps inside)
+ * and the unbiased variance (for the running statistics) per (group, channel). */
+int pdf_bn_train_forward(int n_groups, const int32_t* d_goff, int C, const float* d_x, const float* d_gamma, const float* d_beta, float eps,
+                         const float* d_residual, int relu, float* d_y, float* d_mean, float* d_invstd, float* d_var_unbiased,
+                         pdf_stream_t stream);
+/* backward of the same: g = d_dy * (d_y > 0 if relu); d_dgamma += sum g*xhat, d_dbeta += sum g (accumulate over calls: zero first);
+ * d_dx = gamma*invstd*(g - mean_g(g) - xhat*mean_g(g*xhat)); d_dres (or NULL) (+)= g, the gradient of the residual branch.
+ * d_scratch: 2 * n_groups * C floats. */
+int pdf_bn_train_backward(int n_groups, const int32_t* d_goff, int C, const float* d_dy, const float* d_y, const float* d_x,
+                          const float* d_gamma, const float* d_mean, const float* d_invstd, int relu, float* d_scratch, float* d_dx,
+                          float* d_dres, int dres_accumulate, float* d_dgamma, float* d_dbeta, pdf_stream_t stream);
+/* running = (1-momentum)*running + momentum*batch, group after group (the reference forwards its chunks one at a time) */
+int pdf_bn_update_running(int n_groups, int C, const float* d_mean, const float* d_var_unbiased, float momentum, float* d_running_mean,
+                          float* d_running_var, pdf_stream_t stream);
+int pdf_maxpool_backward_f32(int n, int h, int w, int c, const float* d_x, const float* d_dy, float* d_dx, pdf_stream_t stream);
+int pdf_avgpool_backward_f32(int n, int hw, int c, const float* d_demb, float* d_dx, pdf_stream_t stream);
+/* MIL head, training: everything after the linear layers, forward AND backward, in one kernel (one block per bag).
+ * d_h [n_bags*Lmax, H] = dropout(relu(instance(x))); d_vu [n_bags*Lmax, NA] = attention pre-activations incl. bias (NA = 2A gated: v|u).
+ * Writes d_prob [n_bags], adds the batch-mean loss to d_loss[0], writes d_dh (pooling path only) and d_dvu, and ACCUMULATES the
+ * gradients of attn_w / classifier into the pdf_mil_train pointers.  loss_type 0: BCE * (pos_weight for y >= 0.5), 1: focal. */
+typedef struct {
+  int32_t loss_type;
+  float pos_weight, focal_gamma, focal_alpha; /* focal_alpha < 0: no alpha term */
+  float *d_w_w, *d_b_w, *d_w_cls, *d_b_cls;   /* gradient accumulators [A], [1], [H], [1] */
+} pdf_mil_train;
+int pdf_mil_pool_train(const pdf_mil_weights* w, const pdf_mil_train* t, int n_bags, int Lmax, const float* d_h, const float* d_vu,
+                       const int32_t* d_len, const float* d_target, float* d_prob, float* d_loss, float* d_dh, float* d_dvu,
+                       pdf_stream_t stream);
+int pdf_colsum_f32(int M, int N, const float* d_x, float* d_out, int accumulate, pdf_stream_t stream);
+/* in place: grad *= (act > 0) * mask   (ReLU + inverted-dropout backward; mask NULL = no dropout) */
+int pdf_relu_mask_backward(float* d_grad, const float* d_act, const float* d_mask, size_t n, pdf_stream_t stream);
+int pdf_mul_f32(float* d_x, const float* d_m, size_t n, pdf_stream_t stream);
+/* clip_grad_norm_ + Adam (torch.optim.Adam, L2-style weight decay): d_acc[0] += sum x^2; scale = min(1, max_norm/(norm+1e-6)) */
+int pdf_sumsq_f32(const float* d_x, size_t n, float* d_acc, pdf_stream_t stream);
+int pdf_clip_scale(const float* d_sumsq, float max_norm, float* d_out2, pdf_stream_t stream);
+int pdf_adam_step(float* d_param, const float* d_grad, float* d_m, float* d_v, size_t n, float lr, float beta1, float beta2, float eps,
+                  float weight_decay, int step, const float* d_grad_scale, pdf_stream_t stream);
+
+/* ------------------------------------------------------------------------------------------
  * K4a -- Fusion-ModDrop under every scenario mask in one launch.  Replaces the per-scenario
  * apply_masks_to_matrix + ModalityDropoutModel.predict_proba (data/feature_utils.py:49-61,
  * models/fusion_moddrop.py:93-114; loop at evaluation/evaluate.py:18-97).

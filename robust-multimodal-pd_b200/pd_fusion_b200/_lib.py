@@ -68,6 +68,13 @@ class MilWeights(C.Structure):
     ]
 
 
+class MilTrain(C.Structure):
+    _fields_ = [
+        ("loss_type", C.c_int32), ("pos_weight", C.c_float), ("focal_gamma", C.c_float), ("focal_alpha", C.c_float),
+        ("d_w_w", C.c_void_p), ("d_b_w", C.c_void_p), ("d_w_cls", C.c_void_p), ("d_b_cls", C.c_void_p),
+    ]
+
+
 class Mlp(C.Structure):
     _fields_ = [
         ("n_layers", C.c_int32),
@@ -117,6 +124,21 @@ PROTOTYPES = {
     "pdf_moddrop_workspace_bytes": (C.c_size_t, [C.POINTER(Mlp), C.c_int]),
     "pdf_moddrop_sweep": (C.c_int, [C.POINTER(Mlp), C.c_int, C.c_int, _P, _P, _P, _P, _P]),
     "pdf_moe_sweep": (C.c_int, [C.POINTER(Moe), C.c_int, C.c_int, C.POINTER(_P), _P, _P, _P]),
+    "pdf_gemm_f32": (C.c_int, [C.c_int, C.c_int, C.c_int, _P, C.c_long, C.c_long, _P, C.c_long, C.c_long, _P, C.c_long, _P, C.c_int, C.c_int, _P]),
+    "pdf_conv_dgrad_f32": (C.c_int, [C.POINTER(Op), _P, _P, _P, C.c_int, _P]),
+    "pdf_conv_wgrad_f32": (C.c_int, [C.POINTER(Op), _P, _P, _P, _P]),
+    "pdf_bn_train_forward": (C.c_int, [C.c_int, _P, C.c_int, _P, _P, _P, C.c_float, _P, C.c_int, _P, _P, _P, _P, _P]),
+    "pdf_bn_train_backward": (C.c_int, [C.c_int, _P, C.c_int, _P, _P, _P, _P, _P, _P, C.c_int, _P, _P, _P, C.c_int, _P, _P, _P]),
+    "pdf_bn_update_running": (C.c_int, [C.c_int, C.c_int, _P, _P, C.c_float, _P, _P, _P]),
+    "pdf_maxpool_backward_f32": (C.c_int, [C.c_int, C.c_int, C.c_int, C.c_int, _P, _P, _P, _P]),
+    "pdf_avgpool_backward_f32": (C.c_int, [C.c_int, C.c_int, C.c_int, _P, _P, _P]),
+    "pdf_mil_pool_train": (C.c_int, [C.POINTER(MilWeights), C.POINTER(MilTrain), C.c_int, C.c_int, _P, _P, _P, _P, _P, _P, _P, _P, _P]),
+    "pdf_colsum_f32": (C.c_int, [C.c_int, C.c_int, _P, _P, C.c_int, _P]),
+    "pdf_relu_mask_backward": (C.c_int, [_P, _P, _P, C.c_size_t, _P]),
+    "pdf_mul_f32": (C.c_int, [_P, _P, C.c_size_t, _P]),
+    "pdf_sumsq_f32": (C.c_int, [_P, C.c_size_t, _P, _P]),
+    "pdf_clip_scale": (C.c_int, [_P, C.c_float, _P, _P]),
+    "pdf_adam_step": (C.c_int, [_P, _P, _P, _P, C.c_size_t, C.c_float, C.c_float, C.c_float, C.c_float, C.c_float, C.c_int, _P, _P]),
     "pdf_selftest_umma": (C.c_int, [C.c_int, C.c_int, C.c_int, _P, _P, _P, _P]),
     "pdf_selftest_umma_shift": (C.c_int, [C.c_int, C.c_int, C.c_int, _P, _P, _P, _P]),
     "pdf_selftest_umma_rate": (C.c_int, [C.c_int, C.c_int, C.c_int, C.c_int, _P, _P]),

@@ -2,8 +2,8 @@
 
 `MILAttentionNet` keeps the reference's parameter names so its `state_dict` is the weight-interchange format
 (SURVEY.md A.6).  Inference (`predict_proba`) runs ALL bags in one launch of pdf_mil_forward instead of the
-reference's per-bag B=1 loop with a `.cpu()` per bag (mil_attention.py:169-177).  Training stays host-side torch
-autograd on the CUDA device (device-native head training is a "next" row).
+reference's per-bag B=1 loop with a `.cpu()` per bag (mil_attention.py:169-177).  Training (`train`) runs the native forward/backward/Adam
+kernels of csrc/train.cu through pd_fusion_b200/training.py.
 """
 from __future__ import annotations
 
@@ -60,20 +60,33 @@ class MilAttentionModel(BaseModel):
         self.missing_prob = float(p.get("missing_prob", 0.5))
         self.model = MILAttentionNet(input_dim, int(p.get("hidden_dim", 128)), int(p.get("attn_dim", 64)),
                                      float(p.get("dropout", 0.3)), gated=self.gated)
-        self.optimizer = torch.optim.Adam(self.model.parameters(), lr=float(p.get("lr", 1e-3)),
-                                          weight_decay=float(p.get("weight_decay", 0.0)))
-        self.criterion = nn.BCELoss(reduction="none")
         self.pos_weight = float(p["pos_weight"]) if (p.get("class_weight") != "balanced" and p.get("pos_weight") is not None) else None
         # "fp32" (default: FFMA GEMMs, <= 5e-6 against the reference) | "tf32" (tcgen05 kind::tf32 projection, the throughput path)
         self.precision = str(p.get("precision", "fp32"))
         self._head: Optional[MilHead] = None
+        self._train = None
 
-    # -- training: torch autograd on the device (not the accelerated path) -----------------------
+    # -- training: native forward/backward/Adam kernels (csrc/train.cu) ---------------------------
+    def _trainer(self):
+        if self._train is None:
+            from ..training import MilHeadTrainer, NativeAdam
+            self.model.to(get_torch_device()).float()
+            ht = MilHeadTrainer(self.model, self.gated)
+            p = self.params
+            self._train = (ht, NativeAdam([([q for q, _ in ht.param_grads()], float(p.get("lr", 1e-3)))],
+                                          weight_decay=float(p.get("weight_decay", 0.0))))
+        return self._train
+
     def train(self, bags, y, val_data=None):
+        """Same loop as the reference (models/mil_attention.py:88-155: torch.randperm batches, BCE x pos_weight, mean, optional
+        clip_grad_norm_, Adam, early stopping on validation AUC); each step is pdf_gemm_f32 / pdf_mil_pool_train / pdf_adam_step
+        launches on the padded bag tensor resident on the device -- no autograd graph."""
         X, M = _pad_bags(bags)
         dev = get_torch_device()
-        self.model.to(dev)
-        Xt, Mt, yt = torch.from_numpy(X).to(dev), torch.from_numpy(M).to(dev), torch.as_tensor(np.asarray(y), dtype=torch.float32, device=dev)
+        ht, opt = self._trainer()
+        Xt = torch.from_numpy(X).to(dev)
+        lens_all = torch.from_numpy(M.sum(axis=1).astype(np.int32)).to(dev)
+        yt = torch.as_tensor(np.asarray(y), dtype=torch.float32, device=dev)
         p = self.params
         bs, epochs = int(p.get("batch_size", 16)), int(p.get("epochs", 30))
         clip, patience = p.get("max_grad_norm"), int(p.get("early_stopping_patience", 0))
@@ -81,21 +94,20 @@ class MilAttentionModel(BaseModel):
             pos, neg = float((yt == 1).sum()), float((yt == 0).sum())
             if pos > 0:
                 self.pos_weight = neg / pos
+        lr = opt.groups[0][1]
         best_auc, best_state, bad = -1.0, None, 0
+        self.last_losses = []
         for _ in range(epochs):
             self.model.train()
             order = torch.randperm(len(Xt), device="cpu").to(dev)
             for i in range(0, len(order), bs):
                 sel = order[i:i + bs]
-                loss = self.criterion(self.model(Xt[sel], Mt[sel]), yt[sel])
-                if self.pos_weight is not None:
-                    loss = loss * torch.where(yt[sel] >= 0.5, self.pos_weight, 1.0)
-                loss = loss.mean()
-                self.optimizer.zero_grad()
-                loss.backward()
-                if clip:
-                    torch.nn.utils.clip_grad_norm_(self.model.parameters(), float(clip))
-                self.optimizer.step()
+                ht.zero_grad()
+                loss, _, _ = ht.forward_backward(Xt[sel], lens_all[sel], yt[sel], "bce", self.pos_weight)
+                pg = [(q, g, lr) for q, g in ht.param_grads()]
+                scale = opt.clip([g for _, g, _ in pg], float(clip)) if clip else None
+                opt.step(pg, scale)
+                self.last_losses.append(loss)
             self._head = None
             if val_data is not None and patience > 0:
                 from sklearn.metrics import roc_auc_score

@@ -20,7 +20,6 @@ from typing import Dict, List, Optional, Sequence
 import numpy as np
 import torch
 import torch.nn as nn
-import torch.nn.functional as F
 
 from .. import _lib
 from ..backbone import ResNetEncoder
@@ -68,11 +67,11 @@ class MilAttentionFineTuneModel(BaseModel):
         self.attn = MILAttentionNet(self.emb_dim, int(p.get("hidden_dim", 256)), int(p.get("attn_dim", 128)), float(p.get("dropout", 0.2)),
                                     gated=self.gated).to(self.device).float()
         self.mean_vals, self.std_vals = onf._mean_std(self.weights)
-        self.optimizer = torch.optim.Adam([{"params": self.backbone.parameters(), "lr": float(p.get("lr_backbone", 1e-4))},
-                                           {"params": self.attn.parameters(), "lr": float(p.get("lr", 3e-4))}],
-                                          weight_decay=float(p.get("weight_decay", 1e-3)))
+        # (the optimiser -- Adam, two learning-rate groups, L2 weight decay, `:73-79` -- is the native one of training.py, created
+        #  on first use by _trainers(); its moments persist across train() calls like the reference's self.optimizer)
         self.pos_weight = None if (p.get("class_weight") == "balanced" or p.get("pos_weight") is None) else float(p["pos_weight"])
         self._native: Dict[str, object] = {}
+        self._trainer = None
 
     # ------------------------------------------------------------------------------------------ native inference
     def invalidate(self):
@@ -192,40 +191,13 @@ class MilAttentionFineTuneModel(BaseModel):
         out[live] = (acc / passes).cpu().numpy().astype(np.float64)
         return out
 
-    # ------------------------------------------------------------------------------------------ training (torch autograd)
-    def _torch_features(self, bag, augment: bool) -> Optional[torch.Tensor]:
-        if bag is None:
-            return None
-        sl = torch.from_numpy(np.ascontiguousarray(self._bag_slices(bag))).to(self.device)
-        if augment and not isinstance(bag, np.ndarray):          # the reference augments bags it loads itself, not ready arrays
-            sl = self._augment(sl, np.random.default_rng())
-        x = F.interpolate(sl.unsqueeze(1), size=(self.input_size, self.input_size), mode="bilinear", align_corners=False).repeat(1, 3, 1, 1)
-        mean = torch.tensor(self.mean_vals, device=self.device).view(1, 3, 1, 1)
-        std = torch.tensor(self.std_vals, device=self.device).view(1, 3, 1, 1)
-        x = (x - mean) / std
-        return torch.cat([self.backbone(x[i:i + self.slice_batch_size]) for i in range(0, x.shape[0], self.slice_batch_size)], dim=0)
-
-    def _padded_batch(self, feats: List[Optional[torch.Tensor]]):
-        lmax = max(f.shape[0] for f in feats if f is not None)
-        X = torch.zeros((len(feats), lmax, self.emb_dim), device=self.device)
-        M = torch.zeros((len(feats), lmax), device=self.device)
-        for i, f in enumerate(feats):
-            if f is not None:
-                X[i, : f.shape[0]] = f
-                M[i, : f.shape[0]] = 1.0
-        return X, M
-
-    def _loss(self, preds: torch.Tensor, target: torch.Tensor) -> torch.Tensor:
-        per = F.binary_cross_entropy(preds, target, reduction="none")
-        pos = target >= 0.5
-        if self.loss_type == "focal":
-            w = (1.0 - torch.where(pos, preds, 1.0 - preds)) ** self.focal_gamma
-            if self.focal_alpha is not None:
-                w = w * torch.where(pos, float(self.focal_alpha), 1.0 - float(self.focal_alpha))
-            return (w * per).mean()
-        if self.pos_weight is not None:
-            return (per * torch.where(pos, float(self.pos_weight), 1.0)).mean()
-        return per.mean()
+    # ------------------------------------------------------------------------------------------ training (native kernels)
+    def _train_resizer(self) -> VolumePreprocessor:
+        """slices [L,H,W] in [0,1] -> the reference's float32 3-channel network input [L,S,S,3] ((x-mean)/std per channel)."""
+        if "resize_f32" not in self._native:
+            self._native["resize_f32"] = VolumePreprocessor((8, 8, 8), (8, 8, 8), (2,), (1,), self.input_size, self.mean_vals, self.std_vals,
+                                                            _lib.OUT_F32_NHWC3, 1, self.device)
+        return self._native["resize_f32"]
 
     def _epoch_batches(self, y: np.ndarray) -> List[np.ndarray]:
         n, bs = len(y), self.bag_batch_size
@@ -237,27 +209,89 @@ class MilAttentionFineTuneModel(BaseModel):
         order = np.random.permutation(n)
         return [order[s:s + bs] for s in range(0, n, bs)]
 
+    def _trainers(self):
+        """Native trainers over the live nn.Module parameters (created once; Adam state persists across train() calls like the
+        reference's self.optimizer)."""
+        if self._trainer is None:
+            from ..training import MilHeadTrainer, NativeAdam, ResNetTrainer
+            p = self.params
+            rt = ResNetTrainer(self.backbone, "resnet50" if self.backbone_name == "resnet50" else "resnet18", self.input_size)
+            ht = MilHeadTrainer(self.attn, self.gated)
+            opt = NativeAdam([([q for q, _ in rt.param_grads()], float(p.get("lr_backbone", 1e-4))),
+                              ([q for q, _ in ht.param_grads()], float(p.get("lr", 3e-4)))], weight_decay=float(p.get("weight_decay", 1e-3)))
+            self._trainer = (rt, ht, opt)
+        return self._trainer
+
+    def train_step(self, batch_bags, y_batch: np.ndarray, frozen: bool, clip=None, augment: bool = True):
+        """One optimisation step on a batch of bags (reference: the loop body of train(), mil_attention_finetune.py:206-229):
+        slices -> network input -> backbone in TRAIN mode, 16-slice chunks -> MIL head -> loss -> backward -> clip -> Adam.
+        Returns (loss, probabilities) as device tensors."""
+        rt, ht, opt = self._trainers()
+        pre = self._train_resizer()
+        stacks, groups = [], [0]
+        for bag in batch_bags:
+            if bag is None:
+                stacks.append(None)
+                continue
+            sl = torch.from_numpy(np.ascontiguousarray(self._bag_slices(bag))).to(self.device)
+            if augment and self.train_aug and not isinstance(bag, np.ndarray):      # the reference augments bags it loads itself
+                sl = self._augment(sl, np.random.default_rng())
+            stacks.append(sl)
+            L = int(sl.shape[0])
+            for c0 in range(0, L, self.slice_batch_size):                          # BatchNorm statistics per chunk of one bag
+                groups.append(groups[-1] + min(self.slice_batch_size, L - c0))
+        live = [s for s in stacks if s is not None]
+        total = groups[-1]
+        H, W = int(live[0].shape[1]), int(live[0].shape[2])
+        x = torch.empty((total, self.input_size, self.input_size, 3), dtype=torch.float32, device=self.device)
+        pre.resize_slices(torch.cat(live, dim=0).contiguous().view(1, total, H, W), out=x.view(1, total, self.input_size, self.input_size, 3))
+        emb = rt.forward(x, groups)
+        B, lmax = len(stacks), max(int(s.shape[0]) for s in live)
+        X = torch.zeros((B, lmax, self.emb_dim), dtype=torch.float32, device=self.device)
+        lens = torch.zeros(B, dtype=torch.int32)
+        k = 0
+        for i, sl in enumerate(stacks):
+            if sl is not None:
+                L = int(sl.shape[0])
+                X[i, :L].copy_(emb[k:k + L])
+                lens[i] = L
+                k += L
+        ht.zero_grad()
+        loss, prob, dX = ht.forward_backward(X, lens, torch.from_numpy(np.asarray(y_batch, dtype=np.float32)), self.loss_type, self.pos_weight,
+                                             self.focal_gamma, self.focal_alpha, need_dx=not frozen)
+        pg = [(q, g, opt.groups[1][1]) for q, g in ht.param_grads()]
+        if not frozen:
+            rt.zero_grad()
+            demb = torch.empty((total, self.emb_dim), dtype=torch.float32, device=self.device)
+            k = 0
+            for i, sl in enumerate(stacks):
+                if sl is not None:
+                    L = int(sl.shape[0])
+                    demb[k:k + L].copy_(dX[i, :L])
+                    k += L
+            rt.backward(demb)
+            pg = [(q, g, opt.groups[0][1]) for q, g in rt.param_grads()] + pg
+        scale = opt.clip([g for _, g, _ in pg], float(clip)) if clip else None
+        opt.step(pg, scale)
+        if not frozen:
+            rt.sync_weights()
+        return loss, prob
+
     def train(self, bags, y, val_data=None):
         y = np.asarray(y, dtype=np.float32)
         p = self.params
         clip, patience = p.get("max_grad_norm"), int(p.get("early_stopping_patience", 0))
         if self.pos_weight is None and p.get("class_weight") == "balanced" and (y == 1).sum() > 0:
             self.pos_weight = float((y == 0).sum()) / float((y == 1).sum())
-        every = list(self.backbone.parameters()) + list(self.attn.parameters())
         best_auc, best, stale = -1.0, None, 0
         for epoch in range(int(p.get("epochs", 20))):
             self.backbone.train()
             self.attn.train()
+            frozen = epoch < self.freeze_backbone_epochs
             for q in self.backbone.parameters():
-                q.requires_grad = epoch >= self.freeze_backbone_epochs
+                q.requires_grad = not frozen
             for sel in self._epoch_batches(y):
-                X, M = self._padded_batch([self._torch_features(bags[i], self.train_aug) for i in sel])
-                loss = self._loss(self.attn(X, M), torch.from_numpy(y[sel]).to(self.device))
-                self.optimizer.zero_grad()
-                loss.backward()
-                if clip:
-                    torch.nn.utils.clip_grad_norm_(every, float(clip))
-                self.optimizer.step()
+                self.train_step([bags[i] for i in sel], y[sel], frozen, clip)
             self.invalidate()
             if val_data is not None and patience > 0:
                 from sklearn.metrics import roc_auc_score

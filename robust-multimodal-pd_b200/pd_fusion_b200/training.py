@@ -1,0 +1,355 @@
+"""Host side of K5: device-native training steps built from the hand-written backward kernels of csrc/train.cu.
+
+Replaces torch autograd under
+  * `MilAttentionFineTuneModel.train` / `_forward_bags` (models/mil_attention_finetune.py:135-162, 164-253): ResNet backbone in
+    TRAIN mode (BatchNorm statistics per 16-slice chunk of one bag), MIL head, BCE / focal loss, backward, clip_grad_norm_, Adam
+    with two learning-rate groups;
+  * `MilAttentionModel.train` (models/mil_attention.py:88-155).
+
+Parameters stay where the reference keeps them -- in the `nn.Module`s, whose `state_dict` is the weight-interchange format --
+and are updated in place by `pdf_adam_step`; torch supplies device memory and the random draws (permutations, dropout masks),
+nothing on the arithmetic path.  FP32 throughout (gradients are checked against torch autograd in tests/test_gpu_training.py).
+"""
+from __future__ import annotations
+
+import ctypes as C
+from typing import Dict, List, Optional, Sequence, Tuple
+
+import torch
+import torch.nn as nn
+
+from . import _lib
+from .backbone import RESNET_SPECS, conv_list
+
+
+def _p(t: Optional[torch.Tensor]):
+    return None if t is None else t.data_ptr()
+
+
+class NativeAdam:
+    """torch.optim.Adam (betas 0.9/0.999, eps 1e-8, L2-style weight decay) + clip_grad_norm_ on device tensors.
+    groups: [(params: List[Tensor], lr)], gradients in `grads` (same order)."""
+
+    def __init__(self, groups: Sequence[Tuple[List[torch.Tensor], float]], weight_decay: float = 0.0, betas=(0.9, 0.999), eps: float = 1e-8):
+        self.lib = _lib.load()
+        self.groups = [(list(ps), float(lr)) for ps, lr in groups]
+        self.wd, self.b1, self.b2, self.eps = float(weight_decay), float(betas[0]), float(betas[1]), float(eps)
+        self.state: Dict[int, Tuple[torch.Tensor, torch.Tensor]] = {}
+        self.steps: Dict[int, int] = {}
+        dev = self.groups[0][0][0].device
+        self._acc = torch.zeros(1, dtype=torch.float32, device=dev)
+        self._scale = torch.ones(2, dtype=torch.float32, device=dev)
+
+    def clip(self, grads: Sequence[torch.Tensor], max_norm: float) -> torch.Tensor:
+        """Global L2 norm over `grads`; returns the device tensor [scale, norm] consumed by step()."""
+        s = _lib.stream_ptr()
+        self._acc.zero_()
+        for g in grads:
+            _lib.check(self.lib.pdf_sumsq_f32(g.data_ptr(), g.numel(), self._acc.data_ptr(), s), "pdf_sumsq_f32")
+        _lib.check(self.lib.pdf_clip_scale(self._acc.data_ptr(), float(max_norm), self._scale.data_ptr(), s), "pdf_clip_scale")
+        return self._scale
+
+    def step(self, params_and_grads: Sequence[Tuple[torch.Tensor, torch.Tensor, float]], scale: Optional[torch.Tensor] = None):
+        """params_and_grads: (param, grad, lr); parameters without an entry are left alone (as torch skips grad=None)."""
+        s = _lib.stream_ptr()
+        for p, g, lr in params_and_grads:
+            key = p.data_ptr()
+            if key not in self.state:
+                self.state[key] = (torch.zeros_like(p), torch.zeros_like(p))
+                self.steps[key] = 0
+            self.steps[key] += 1
+            m, v = self.state[key]
+            _lib.check(self.lib.pdf_adam_step(p.data_ptr(), g.data_ptr(), m.data_ptr(), v.data_ptr(), p.numel(), float(lr), self.b1, self.b2,
+                                              self.eps, self.wd, self.steps[key], _p(scale), s), "pdf_adam_step")
+
+
+class MilHeadTrainer:
+    """Forward + backward of MILAttentionNet (models/mil_attention.py:10-51) in train mode on [B, Lmax, D] padded bags."""
+
+    def __init__(self, net: nn.Module, gated: bool):
+        _lib.require_cuda()
+        self.lib = _lib.load()
+        self.net, self.gated = net, bool(gated)
+        sd = dict(net.named_parameters())
+        self.p = {k: v.data for k, v in sd.items()}
+        for v in self.p.values():
+            if not (v.is_cuda and v.dtype == torch.float32 and v.is_contiguous()):
+                raise ValueError("MilHeadTrainer needs contiguous float32 CUDA parameters")
+        self.g = {k: torch.zeros_like(v) for k, v in self.p.items()}
+        self.H, self.D = self.p["instance.0.weight"].shape
+        self.A = (self.p["attn_v.0.weight"] if self.gated else self.p["attn.0.weight"]).shape[0]
+        self.NA = 2 * self.A if self.gated else self.A
+        self.dropout = float(net.instance[2].p) if len(net.instance) > 2 else 0.0
+        self.dev = self.p["instance.0.weight"].device
+
+    def param_grads(self) -> List[Tuple[torch.Tensor, torch.Tensor]]:
+        return [(self.p[k], self.g[k]) for k in self.p]
+
+    def zero_grad(self):
+        for g in self.g.values():
+            g.zero_()
+
+    def _gemm(self, M, N, K, A, a_rs, a_cs, B, b_rs, b_cs, Cm, c_rs, bias=None, act=0, acc=0):
+        _lib.check(self.lib.pdf_gemm_f32(M, N, K, A.data_ptr() if isinstance(A, torch.Tensor) else A, a_rs, a_cs,
+                                         B.data_ptr() if isinstance(B, torch.Tensor) else B, b_rs, b_cs,
+                                         Cm.data_ptr() if isinstance(Cm, torch.Tensor) else Cm, c_rs, _p(bias), act, acc, _lib.stream_ptr()),
+                   "pdf_gemm_f32")
+
+    def forward_backward(self, X: torch.Tensor, lens: torch.Tensor, y: torch.Tensor, loss_type: str = "bce", pos_weight: Optional[float] = None,
+                         focal_gamma: float = 2.0, focal_alpha: Optional[float] = None, need_dx: bool = False, train: bool = True):
+        """X [B, Lmax, D] f32 (zero padded), lens [B] i32, y [B] f32 -> (loss [1] device tensor, prob [B], dX or None).
+        Gradients are ACCUMULATED into self.g (call zero_grad() first)."""
+        B, Lmax, D = (int(v) for v in X.shape)
+        rows, H, A, NA = B * Lmax, self.H, self.A, self.NA
+        dev, p, g = self.dev, self.p, self.g
+        X = X.contiguous()
+        h = torch.empty((rows, H), dtype=torch.float32, device=dev)
+        self._gemm(rows, H, D, X, D, 1, p["instance.0.weight"], 1, D, h, H, p["instance.0.bias"], act=1)
+        mask = None
+        if train and self.dropout > 0:
+            keep = 1.0 - self.dropout
+            mask = (torch.rand((rows, H), device=dev) < keep).to(torch.float32) / keep        # inverted dropout (random draw only)
+            _lib.check(self.lib.pdf_mul_f32(h.data_ptr(), mask.data_ptr(), h.numel(), _lib.stream_ptr()), "pdf_mul_f32")
+        vu = torch.empty((rows, NA), dtype=torch.float32, device=dev)
+        if self.gated:
+            self._gemm(rows, A, H, h, H, 1, p["attn_v.0.weight"], 1, H, vu, NA, p["attn_v.0.bias"])
+            self._gemm(rows, A, H, h, H, 1, p["attn_u.0.weight"], 1, H, vu.data_ptr() + 4 * A, NA, p["attn_u.0.bias"])
+            w_w, b_w, gw_w, gb_w = p["attn_w.weight"], p["attn_w.bias"], g["attn_w.weight"], g["attn_w.bias"]
+        else:
+            self._gemm(rows, A, H, h, H, 1, p["attn.0.weight"], 1, H, vu, NA, p["attn.0.bias"])
+            w_w, b_w, gw_w, gb_w = p["attn.2.weight"], p["attn.2.bias"], g["attn.2.weight"], g["attn.2.bias"]
+        w = _lib.MilWeights()
+        w.D, w.H, w.A, w.gated = D, H, A, 1 if self.gated else 0
+        w.w_w, w.b_w, w.w_cls, w.b_cls = w_w.data_ptr(), b_w.data_ptr(), p["classifier.0.weight"].data_ptr(), p["classifier.0.bias"].data_ptr()
+        t = _lib.MilTrain()
+        t.loss_type = 1 if loss_type == "focal" else 0
+        t.pos_weight = 1.0 if pos_weight is None else float(pos_weight)
+        t.focal_gamma = float(focal_gamma)
+        t.focal_alpha = -1.0 if focal_alpha is None else float(focal_alpha)
+        t.d_w_w, t.d_b_w = gw_w.data_ptr(), gb_w.data_ptr()
+        t.d_w_cls, t.d_b_cls = g["classifier.0.weight"].data_ptr(), g["classifier.0.bias"].data_ptr()
+        prob = torch.empty(B, dtype=torch.float32, device=dev)
+        loss = torch.zeros(1, dtype=torch.float32, device=dev)
+        dh = torch.empty((rows, H), dtype=torch.float32, device=dev)
+        dvu = torch.empty((rows, NA), dtype=torch.float32, device=dev)
+        lens = lens.to(device=dev, dtype=torch.int32).contiguous()
+        y = y.to(device=dev, dtype=torch.float32).contiguous()
+        _lib.check(self.lib.pdf_mil_pool_train(C.byref(w), C.byref(t), B, Lmax, h.data_ptr(), vu.data_ptr(), lens.data_ptr(), y.data_ptr(),
+                                               prob.data_ptr(), loss.data_ptr(), dh.data_ptr(), dvu.data_ptr(), _lib.stream_ptr()),
+                   "pdf_mil_pool_train")
+        # attention layers: dW = dvu^T h, db = colsum(dvu), dh += dvu W
+        s = _lib.stream_ptr()
+        names = [("attn_v.0", 0), ("attn_u.0", A)] if self.gated else [("attn.0", 0)]
+        for name, off in names:
+            dv = dvu.data_ptr() + 4 * off
+            self._gemm(A, H, rows, dv, 1, NA, h, H, 1, g[name + ".weight"], H, acc=1)                 # dW[a, i] += sum_r dv[r, a] h[r, i]
+            _lib.check(self.lib.pdf_gemm_f32(1, A, rows, self._ones(rows).data_ptr(), 0, 1, dv, NA, 1, g[name + ".bias"].data_ptr(), A, None, 0, 1, s),
+                       "pdf_gemm_f32")
+            self._gemm(rows, H, A, dv, NA, 1, p[name + ".weight"], H, 1, dh, H, acc=1)                # dh[r, i] += sum_a dv[r, a] W[a, i]
+        # instance layer: ReLU (+ dropout) backward, dW_i = dh^T X, db_i, (dX = dh W_i)
+        _lib.check(self.lib.pdf_relu_mask_backward(dh.data_ptr(), h.data_ptr(), _p(mask), dh.numel(), s), "pdf_relu_mask_backward")
+        self._gemm(H, D, rows, dh, 1, H, X, D, 1, g["instance.0.weight"], D, acc=1)
+        _lib.check(self.lib.pdf_colsum_f32(rows, H, dh.data_ptr(), g["instance.0.bias"].data_ptr(), 1, s), "pdf_colsum_f32")
+        dX = None
+        if need_dx:
+            dX = torch.empty((B, Lmax, D), dtype=torch.float32, device=dev)
+            self._gemm(rows, D, H, dh, H, 1, p["instance.0.weight"], D, 1, dX, D)
+        return loss, prob, dX
+
+    def _ones(self, n: int) -> torch.Tensor:
+        if getattr(self, "_ones_buf", None) is None or self._ones_buf.numel() < n:
+            self._ones_buf = torch.ones(n, dtype=torch.float32, device=self.dev)
+        return self._ones_buf
+
+
+class _Act:
+    __slots__ = ("data", "grad", "n", "hw", "c")
+
+    def __init__(self, data, n, hw, c):
+        self.data, self.grad, self.n, self.hw, self.c = data, None, n, hw, c
+
+
+class ResNetTrainer:
+    """Train-mode forward and backward of a torchvision-layout ResNet18/50 (fc = Identity) on NHWC float32 images.
+
+    BatchNorm uses BATCH statistics over each group of images (`groups`: image offsets; one group = one 16-slice chunk of one
+    bag, the unit the reference pushes through `self.backbone(batch)`, mil_attention_finetune.py:147-150) and updates the
+    module's running statistics group by group.  Parameters are read from / updated in the nn.Module (torchvision layout
+    [K,C,R,S]); the kernels consume an [R,S,C,K] copy refreshed by `sync_weights()`."""
+
+    def __init__(self, module: nn.Module, arch: str, input_size: int = 224):
+        _lib.require_cuda()
+        self.lib = _lib.load()
+        self.m, self.arch, self.S = module, arch, int(input_size)
+        self.kind, self.layers, self.emb_dim = RESNET_SPECS[arch]
+        self.params = dict(module.named_parameters())
+        self.buffers = dict(module.named_buffers())
+        self.dev = self.params["conv1.weight"].device
+        self.convs = {cv["name"]: cv for cv in conv_list(arch)}
+        self.wk: Dict[str, torch.Tensor] = {}
+        self.grad: Dict[str, torch.Tensor] = {k: torch.zeros_like(v.data) for k, v in self.params.items() if not k.startswith("fc.")}
+        self._gwk: Dict[str, torch.Tensor] = {}
+        self.sync_weights()
+
+    # -- parameters --------------------------------------------------------------------------------
+    def sync_weights(self):
+        for name in self.convs:
+            w = self.params[name + ".weight"].data
+            self.wk[name] = w.permute(2, 3, 1, 0).contiguous()          # [R,S,C,K] (layout change only)
+
+    def zero_grad(self):
+        for g in self.grad.values():
+            g.zero_()
+
+    def param_grads(self) -> List[Tuple[torch.Tensor, torch.Tensor]]:
+        return [(self.params[k].data, self.grad[k]) for k in self.grad]
+
+    # -- forward ---------------------------------------------------------------------------------------
+    def _op(self, n, h, c, cv, ho) -> "_lib.Op":
+        op = _lib.Op()
+        op.kind, op.precision = _lib.OP_CONV, _lib.PREC_F32
+        op.n, op.h, op.w, op.c, op.k, op.r, op.s = n, h, h, c, cv["cout"], cv["k"], cv["k"]
+        op.stride, op.pad, op.ho, op.wo, op.relu = cv["stride"], cv["pad"], ho, ho, 0
+        return op
+
+    def _goff(self, groups: Sequence[int], hw: int) -> torch.Tensor:
+        key = (tuple(groups), hw)
+        if key not in self._goff_cache:
+            self._goff_cache[key] = torch.tensor([g * hw for g in groups], dtype=torch.int32, device=self.dev)
+        return self._goff_cache[key]
+
+    def _convbn(self, x: _Act, h: int, name: str, bn: str, relu: bool, res: Optional[_Act], groups) -> Tuple[_Act, int]:
+        cv = self.convs[name]
+        ho = (h + 2 * cv["pad"] - cv["k"]) // cv["stride"] + 1
+        n, K = x.n, cv["cout"]
+        op = self._op(n, h, x.c, cv, ho)
+        conv_out = torch.empty((n * ho * ho, K), dtype=torch.float32, device=self.dev)
+        op.d_in, op.d_weight, op.d_out = x.data.data_ptr(), self.wk[name].data_ptr(), conv_out.data_ptr()
+        plan = C.c_void_p()
+        _lib.check(self.lib.pdf_plan_create(C.byref(plan), (_lib.Op * 1)(op), 1), "pdf_plan_create")
+        _lib.check(self.lib.pdf_plan_run(plan, _lib.stream_ptr()), "pdf_plan_run")
+        self.lib.pdf_plan_destroy(plan)
+        G = len(groups) - 1
+        goff = self._goff(groups, ho * ho)
+        y = torch.empty_like(conv_out)
+        mean = torch.empty((G, K), dtype=torch.float32, device=self.dev)
+        invstd, varu = torch.empty_like(mean), torch.empty_like(mean)
+        bnm = self._bn_module(bn)
+        _lib.check(self.lib.pdf_bn_train_forward(G, goff.data_ptr(), K, conv_out.data_ptr(), self.params[bn + ".weight"].data.data_ptr(),
+                                                 self.params[bn + ".bias"].data.data_ptr(), float(bnm.eps), _p(res.data if res else None),
+                                                 1 if relu else 0, y.data_ptr(), mean.data_ptr(), invstd.data_ptr(), varu.data_ptr(),
+                                                 _lib.stream_ptr()), "pdf_bn_train_forward")
+        if self.update_running:
+            _lib.check(self.lib.pdf_bn_update_running(G, K, mean.data_ptr(), varu.data_ptr(), float(bnm.momentum),
+                                                      self.buffers[bn + ".running_mean"].data_ptr(), self.buffers[bn + ".running_var"].data_ptr(),
+                                                      _lib.stream_ptr()), "pdf_bn_update_running")
+            self.buffers[bn + ".num_batches_tracked"] += G
+        out = _Act(y, n, ho * ho, K)
+        self.tape.append(("convbn", name, bn, x, conv_out, out, relu, res, op, goff, mean, invstd, h))
+        return out, ho
+
+    def _bn_module(self, bn: str) -> nn.BatchNorm2d:
+        mod = self.m
+        for part in bn.split("."):
+            mod = mod[int(part)] if part.isdigit() else getattr(mod, part)
+        return mod
+
+    def forward(self, x: torch.Tensor, groups: Sequence[int], update_running: bool = True) -> torch.Tensor:
+        """x [n, S, S, 3] f32 NHWC (the reference's (x-mean)/std 3-channel input); groups: image offsets [0, ..., n] of the
+        BatchNorm groups.  Returns the embeddings [n, D] f32 and records the tape for backward()."""
+        n = int(x.shape[0])
+        assert groups[0] == 0 and groups[-1] == n
+        self.tape, self._goff_cache, self.update_running = [], {}, bool(update_running)
+        t, h = self._convbn(_Act(x.contiguous(), n, self.S * self.S, 3), self.S, "conv1", "bn1", True, None, groups)
+        ho = (h + 2 - 3) // 2 + 1
+        pooled = torch.empty((n * ho * ho, 64), dtype=torch.float32, device=self.dev)
+        op = _lib.Op()
+        op.kind, op.precision = _lib.OP_MAXPOOL, _lib.PREC_F32
+        op.n, op.h, op.w, op.c, op.ho, op.wo = n, h, h, 64, ho, ho
+        op.d_in, op.d_out = t.data.data_ptr(), pooled.data_ptr()
+        plan = C.c_void_p()
+        _lib.check(self.lib.pdf_plan_create(C.byref(plan), (_lib.Op * 1)(op), 1), "pdf_plan_create")
+        _lib.check(self.lib.pdf_plan_run(plan, _lib.stream_ptr()), "pdf_plan_run")
+        self.lib.pdf_plan_destroy(plan)
+        t2 = _Act(pooled, n, ho * ho, 64)
+        self.tape.append(("maxpool", t, t2, h))
+        t, h = t2, ho
+        for li, nblocks in enumerate(self.layers, start=1):
+            for bi in range(nblocks):
+                pfx = f"layer{li}.{bi}"
+                idn, h_in = t, h
+                if pfx + ".downsample.0" in self.convs:
+                    idn, _ = self._convbn(t, h_in, pfx + ".downsample.0", pfx + ".downsample.1", False, None, groups)
+                o, h = self._convbn(t, h_in, pfx + ".conv1", pfx + ".bn1", True, None, groups)
+                if self.kind == "basic":
+                    o, h = self._convbn(o, h, pfx + ".conv2", pfx + ".bn2", True, idn, groups)
+                else:
+                    o, h = self._convbn(o, h, pfx + ".conv2", pfx + ".bn2", True, None, groups)
+                    o, h = self._convbn(o, h, pfx + ".conv3", pfx + ".bn3", True, idn, groups)
+                t = o
+        emb = self._avgpool(t)
+        self.tape.append(("avgpool", t))
+        return emb
+
+    def _avgpool(self, t: _Act) -> torch.Tensor:
+        out = torch.empty((t.n, t.c), dtype=torch.float32, device=self.dev)
+        op = _lib.Op()
+        op.kind, op.precision = _lib.OP_AVGPOOL, _lib.PREC_F32
+        hw = int(round(t.hw ** 0.5))
+        op.n, op.h, op.w, op.c = t.n, hw, hw, t.c
+        op.d_in, op.d_out = t.data.data_ptr(), out.data_ptr()
+        plan = C.c_void_p()
+        _lib.check(self.lib.pdf_plan_create(C.byref(plan), (_lib.Op * 1)(op), 1), "pdf_plan_create")
+        _lib.check(self.lib.pdf_plan_run(plan, _lib.stream_ptr()), "pdf_plan_run")
+        self.lib.pdf_plan_destroy(plan)
+        return out
+
+    # -- backward --------------------------------------------------------------------------------------
+    def backward(self, demb: torch.Tensor):
+        """demb [n, D] f32: gradient of the loss w.r.t. the embeddings.  Accumulates parameter gradients into self.grad
+        (torchvision layout)."""
+        s = _lib.stream_ptr()
+        lib = self.lib
+        gwk: Dict[str, torch.Tensor] = {}
+        for entry in reversed(self.tape):
+            kind = entry[0]
+            if kind == "avgpool":
+                t = entry[1]
+                t.grad = torch.empty_like(t.data)
+                _lib.check(lib.pdf_avgpool_backward_f32(t.n, t.hw, t.c, demb.contiguous().data_ptr(), t.grad.data_ptr(), s), "pdf_avgpool_backward_f32")
+            elif kind == "maxpool":
+                _, tin, tout, h = entry
+                tin.grad = torch.empty_like(tin.data)
+                _lib.check(lib.pdf_maxpool_backward_f32(tin.n, h, h, tin.c, tin.data.data_ptr(), tout.grad.data_ptr(), tin.grad.data_ptr(), s),
+                           "pdf_maxpool_backward_f32")
+                tout.grad = None
+            else:
+                _, name, bn, x, conv_out, out, relu, res, op, goff, mean, invstd, h = entry
+                G, K = int(mean.shape[0]), int(mean.shape[1])
+                dconv = torch.empty_like(conv_out)
+                scratch = torch.empty((2, G, K), dtype=torch.float32, device=self.dev)
+                dres, acc = None, 0
+                if res is not None:
+                    if res.grad is None:
+                        res.grad = torch.empty_like(res.data)
+                    else:
+                        acc = 1
+                    dres = res.grad
+                _lib.check(lib.pdf_bn_train_backward(G, goff.data_ptr(), K, out.grad.data_ptr(), out.data.data_ptr(), conv_out.data_ptr(),
+                                                     self.params[bn + ".weight"].data.data_ptr(), mean.data_ptr(), invstd.data_ptr(),
+                                                     1 if relu else 0, scratch.data_ptr(), dconv.data_ptr(), _p(dres), acc,
+                                                     self.grad[bn + ".weight"].data_ptr(), self.grad[bn + ".bias"].data_ptr(), s),
+                           "pdf_bn_train_backward")
+                out.grad = None
+                if name not in gwk:
+                    gwk[name] = torch.zeros_like(self.wk[name])
+                _lib.check(lib.pdf_conv_wgrad_f32(C.byref(op), x.data.data_ptr(), dconv.data_ptr(), gwk[name].data_ptr(), s), "pdf_conv_wgrad_f32")
+                if name != "conv1":                                  # the network input needs no gradient
+                    acc = 0 if x.grad is None else 1
+                    if x.grad is None:
+                        x.grad = torch.empty_like(x.data)
+                    _lib.check(lib.pdf_conv_dgrad_f32(C.byref(op), dconv.data_ptr(), self.wk[name].data_ptr(), x.grad.data_ptr(), acc, s),
+                               "pdf_conv_dgrad_f32")
+        for name, gw in gwk.items():                                 # [R,S,C,K] -> torchvision [K,C,R,S] (layout change only;
+            self.grad[name + ".weight"].copy_(gw.permute(3, 2, 0, 1))   #  one backward per zero_grad, as the reference's step)
+        self.tape = []

@@ -52,6 +52,9 @@ WORKLOADS = {
     "c2": dict(arch="resnet18", axes=[2], counts=[24], batch_size=32, name="configs/openneuro_ds001907_resnet2d.yaml"),
     # configs/openneuro_ds001907_resnet2d_mil.yaml (BASELINE configs[2])
     "c3": dict(arch="resnet50", axes=[2], counts=[48], batch_size=16, name="configs/openneuro_ds001907_resnet2d_mil.yaml"),
+    # BASELINE configs[4]: fine-tune forward/backward (configs/openneuro_ds001907_resnet2d_mil_ft.yaml: resnet50, 64 slices,
+    # 4 bags per step, 16-slice chunks, gated MIL head, focal loss, clip 1.0, Adam 1e-4 / 3e-4) -- its own leg (run_c5)
+    "c5": dict(arch="resnet50", axes=[2], counts=[64], batch_size=16, name="configs/openneuro_ds001907_resnet2d_mil_ft.yaml"),
 }
 IN_SHAPE, TARGET, INPUT_SIZE = (256, 256, 176), (160, 160, 160), 224
 METRIC, UNIT = "mri_subjects_per_sec_resnet2d_embed_fuse", "subjects/s"
@@ -254,6 +257,86 @@ def heads_leg(dev, peaks, timed):
     return out
 
 
+def run_c5(args, wl):
+    """Fine-tune training steps (BASELINE config 5): slices -> backbone in TRAIN mode (BatchNorm statistics per 16-slice chunk) -> MIL
+    head -> focal loss -> backward -> clip -> Adam, all on the native FP32 kernels of csrc/train.cu; one process per GPU, bags
+    sharded, gradients averaged with one NCCL all-reduce per flat buffer.  value = subjects (bags) per second, weak scaling."""
+    import torch
+    from pd_fusion_b200 import _lib
+    from pd_fusion_b200.backbone import flops_per_image
+    from pd_fusion_b200.models.mil_attention_finetune import MilAttentionFineTuneModel
+    from pd_fusion_b200.parallel import barrier, init_distributed
+    rank, local_rank, ws = init_distributed()
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py needs a CUDA device: the product path has no CPU fallback")
+    torch.cuda.set_device(local_rank)
+    dev = torch.device("cuda", local_rank)
+    peaks = measured_peaks()
+    bags_per_step, L = 4, sum(wl["counts"])
+    params = {"backbone": wl["arch"], "pretrained": False, "target_shape": list(TARGET), "slice_axis": 2, "slice_count": L, "input_size": INPUT_SIZE,
+              "slice_batch_size": 16, "batch_size": bags_per_step, "hidden_dim": 256, "attn_dim": 128, "dropout": 0.2, "gated": True,
+              "loss_type": "focal", "focal_gamma": 2.0, "focal_alpha": 0.25, "lr": 3e-4, "lr_backbone": 1e-4, "weight_decay": 1e-3,
+              "max_grad_norm": 1.0, "train_aug": False, "missing_prob": 0.5}
+    torch.manual_seed(1234)
+    model = MilAttentionFineTuneModel(params)
+    rng = np.random.default_rng(100 + rank)
+    host_bags = [rng.random((L, TARGET[0], TARGET[1])).astype(np.float32) for _ in range(bags_per_step)]
+    dev_bags = [torch.from_numpy(b).to(dev) for b in host_bags]
+    y = np.array([1.0, 0.0, 1.0, 0.0], dtype=np.float32)
+
+    def timed(fn, steps):
+        barrier(); torch.cuda.synchronize()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        for _ in range(steps):
+            fn()
+        e1.record()
+        torch.cuda.synchronize(); barrier()
+        ms = torch.tensor([e0.elapsed_time(e1)], device=dev)
+        if ws > 1:
+            torch.distributed.all_reduce(ms, op=torch.distributed.ReduceOp.MAX)
+        return float(ms.item())
+
+    step_dev = lambda: model.train_step(dev_bags, y, frozen=False, clip=1.0)
+    step_host = lambda: model.train_step(host_bags, y, frozen=False, clip=1.0)[0].item()     # loss read back: the step's result
+    for _ in range(max(args.warmup, 3)):
+        step_dev()
+    torch.cuda.synchronize()
+    steps = min(args.steps, 20)
+    l0 = _lib.launch_count()
+    with ClockSampler(local_rank) as clk:
+        ms = timed(step_dev, steps)
+    launches = _lib.launch_count() - l0
+    step_host()
+    barrier(); torch.cuda.synchronize()
+    t0 = time.perf_counter()
+    for _ in range(steps):
+        step_host()
+    torch.cuda.synchronize(); barrier()
+    ms_e2e = (time.perf_counter() - t0) * 1e3
+    flops = 3.0 * bags_per_step * L * flops_per_image(wl["arch"], INPUT_SIZE)              # forward + dgrad + wgrad
+    tf = flops / (ms / steps / 1e3) / 1e12
+    line = {"metric": "mri_subjects_per_sec_resnet2d_mil_finetune_fwd_bwd", "value": ws * bags_per_step * steps / (ms / 1e3), "unit": UNIT,
+            "n_gpus": ws, "steps": steps, "warmup": max(args.warmup, 3), "ms_per_step": ms / steps, "higher_is_better": True, "scaling": "weak",
+            "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+            "config": {"workload": wl["name"], "backbone": wl["arch"], "slices": L, "bags_per_step_per_gpu": bags_per_step, "slice_batch_size": 16,
+                       "input_size": INPUT_SIZE, "loss": "focal(2.0, 0.25)", "optimizer": "Adam 1e-4 / 3e-4, wd 1e-3, clip 1.0",
+                       "l2": "activations of one step (~25 GB) exceed L2 many times over",
+                       "parallelism": f"bags sharded x{ws}, one gradient all-reduce per flat buffer" if ws > 1 else "1 GPU"},
+            "clocks": clk.summary(),
+            "e2e": {"value": ws * bags_per_step * steps / (ms_e2e / 1e3), "unit": UNIT, "h2d_bytes_per_step": int(sum(b.nbytes for b in host_bags)),
+                    "d2h_bytes_per_step": 4, "ms_per_step": ms_e2e / steps},
+            "gpu_launches": int(launches),
+            "roofline": {"bound": "tensor", "kernel": "conv_f32 / conv_dgrad_f32 / conv_wgrad_f32 (CUDA-core FFMA implicit GEMMs: the FP32 parity "
+                                                      "path of training; no tcgen05 backward yet)",
+                         "achieved": tf, "peak": peaks["tf"], "unit": "TFLOP/s", "frac": tf / peaks["tf"], "traffic": None,
+                         "flops_per_step": flops, "peak_source": peaks["src"] + " burst bf16 tensor peak (the kernels run on the FP32 CUDA cores)"}}
+    if rank == 0:
+        print(json.dumps(line), flush=True)
+    if ws > 1:
+        torch.distributed.destroy_process_group()
+
+
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
@@ -277,6 +360,8 @@ def main():
     wl = WORKLOADS[args.workload]
     if args.impl == "reference":
         return run_reference(args, wl)
+    if args.workload == "c5":
+        return run_c5(args, wl)
 
     import torch
     from pd_fusion_b200 import _lib

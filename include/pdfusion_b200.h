@@ -200,6 +200,8 @@ typedef struct pdf_plan pdf_plan; /* opaque: validated ops + pre-encoded TMA des
 int pdf_debug_set_pw(int mode);
 /* persistent kernels size their grids for `cap` SMs instead of the device's (0 = off): two streams can then share the GPU */
 int pdf_debug_set_sm_cap(int cap);
+/* A/B hook: 0 = warp-per-pair ModDrop kernel at every size, 1 (default) = tiled in-block GEMM kernel from 4096 (scenario, subject) pairs up */
+int pdf_debug_set_moddrop_tiled(int enable);
 /* ring depth (2..6) and staging-buffer count (2..4) of conv_pw_kernel launches (the ring shrinks to what fits 227 KB) */
 int pdf_debug_set_pw_config(int stages, int staging_buffers);
 int pdf_plan_create(pdf_plan** out, const pdf_op* ops, int n_ops);
@@ -286,6 +288,11 @@ typedef struct {
 int pdf_mil_pool_train(const pdf_mil_weights* w, const pdf_mil_train* t, int n_bags, int Lmax, const float* d_h, const float* d_vu,
                        const int32_t* d_len, const float* d_target, float* d_prob, float* d_loss, float* d_dh, float* d_dvu,
                        pdf_stream_t stream);
+/* heads (models/fusion_moddrop.py:69-91, models/moe.py:60-70): Sigmoid + nn.BCELoss (mean) forward and d loss / d logit in one launch;
+ * MoE: out = sum_e sigmoid(z[:,e]) * softmax(r)[:,e], BCE(out, y), gradients of the expert logits z and the router logits r */
+int pdf_bce_sigmoid_train(int n, const float* d_z, const float* d_y, float* d_prob, float* d_loss, float* d_dz, pdf_stream_t stream);
+int pdf_moe_combine_train(int n, int n_experts, const float* d_z, const float* d_r, const float* d_y, float* d_out, float* d_loss,
+                          float* d_dz, float* d_dr, pdf_stream_t stream);
 int pdf_colsum_f32(int M, int N, const float* d_x, float* d_out, int accumulate, pdf_stream_t stream);
 /* in place: grad *= (act > 0) * mask   (ReLU + inverted-dropout backward; mask NULL = no dropout) */
 int pdf_relu_mask_backward(float* d_grad, const float* d_act, const float* d_mask, size_t n, pdf_stream_t stream);

@@ -230,6 +230,94 @@ moddrop_sweep_kernel(pdf_mlp net, const float* __restrict__ partials, const uint
   }
 }
 
+// Large S*N: a block takes a tile of TP (scenario, subject) pairs and runs layers 2.. as shared-memory-tiled FFMA GEMMs, so every
+// weight element is fetched once per TILE instead of once per pair (the warp-per-pair kernel above re-reads 164 KB of weights per pair
+// at the C2 widths: 1.1 TB of L2 traffic at N = 1e6, S = 7).  Same arithmetic, summation over k in ascending order per output.
+template <int TP>
+__global__ void __launch_bounds__(256)
+moddrop_tile_kernel(pdf_mlp net, const float* __restrict__ partials, const uint8_t* __restrict__ masks, int N, int S, int maxw,
+                    float* __restrict__ prob) {
+  extern __shared__ float sm[];
+  const int stride = maxw + 1;
+  float* bufA = sm;                                  // [TP][stride]
+  float* bufB = bufA + TP * stride;
+  float* Ws = bufB + TP * stride;                    // [16][64 + 4]
+  const int tid = threadIdx.x;
+  const int M = net.n_mods, h1 = net.dims[1];
+  const long long total = (long long)N * S;
+  constexpr int RT = TP / 16;                        // rows per thread (thread grid 16 x 16)
+  const int ty = tid >> 4, tx = tid & 15;
+  for (long long p0 = (long long)blockIdx.x * TP; p0 < total; p0 += (long long)gridDim.x * TP) {
+    // layer 1 from the per-modality partials
+    for (int idx = tid; idx < TP * h1; idx += 256) {
+      const int r = idx / h1, i = idx - r * h1;
+      const long long pair = p0 + r;
+      float v = 0.f;
+      if (pair < total) {
+        const int s = (int)(pair / N), n = (int)(pair - (long long)s * N);
+        const uint8_t* mk = masks + ((size_t)s * N + n) * M;
+        for (int m = 0; m < M; ++m)
+          if (mk[m] && net.mod_off[m + 1] > net.mod_off[m]) v += partials[((size_t)m * N + n) * h1 + i];
+        v += __ldg(net.b[0] + i);
+        if (net.n_layers > 1) v = fmaxf(v, 0.f);
+      }
+      bufA[r * stride + i] = v;
+    }
+    __syncthreads();
+    float* in = bufA;
+    float* out = bufB;
+    for (int l = 1; l < net.n_layers; ++l) {
+      const int n_in = net.dims[l], n_out = net.dims[l + 1];
+      const float* W = net.w[l];
+      const int relu = l < net.n_layers - 1;
+      for (int c0 = 0; c0 < n_out; c0 += 64) {
+        float acc[RT][4];
+#pragma unroll
+        for (int i = 0; i < RT; ++i)
+#pragma unroll
+          for (int j = 0; j < 4; ++j) acc[i][j] = 0.f;
+        for (int k0 = 0; k0 < n_in; k0 += 16) {
+          {   // W chunk: 64 output columns x 16 k  (thread -> column tid>>2, 4 consecutive k)
+            const int col = c0 + (tid >> 2), kk = (tid & 3) * 4;
+#pragma unroll
+            for (int e = 0; e < 4; ++e)
+              Ws[(kk + e) * 68 + (tid >> 2)] = (col < n_out && k0 + kk + e < n_in) ? __ldg(W + (size_t)col * n_in + k0 + kk + e) : 0.f;
+          }
+          __syncthreads();
+          const int kmax = min(16, n_in - k0);
+          for (int kk = 0; kk < kmax; ++kk) {
+            float a[RT], b[4];
+#pragma unroll
+            for (int i = 0; i < RT; ++i) a[i] = in[(ty * RT + i) * stride + k0 + kk];
+#pragma unroll
+            for (int j = 0; j < 4; ++j) b[j] = Ws[kk * 68 + tx * 4 + j];
+#pragma unroll
+            for (int i = 0; i < RT; ++i)
+#pragma unroll
+              for (int j = 0; j < 4; ++j) acc[i][j] = fmaf(a[i], b[j], acc[i][j]);
+          }
+          __syncthreads();
+        }
+#pragma unroll
+        for (int i = 0; i < RT; ++i)
+#pragma unroll
+          for (int j = 0; j < 4; ++j) {
+            const int col = c0 + tx * 4 + j;
+            if (col < n_out) {
+              const float v = acc[i][j] + __ldg(net.b[l] + col);
+              out[(ty * RT + i) * stride + col] = relu ? fmaxf(v, 0.f) : v;
+            }
+          }
+      }
+      __syncthreads();
+      float* t = in; in = out; out = t;
+    }
+    for (int r = tid; r < TP; r += 256)
+      if (p0 + r < total) prob[p0 + r] = sigmoidf_(in[r * stride]);       // prob is [S, N] = pair order
+    __syncthreads();
+  }
+}
+
 struct MoeArgs {
   pdf_moe net;
   const float* x[PDF_MAX_MODS];
@@ -242,23 +330,36 @@ moe_sweep_kernel(MoeArgs a, const uint8_t* __restrict__ masks, int N, int S, int
   float* bufA = sm + (size_t)warp * 2 * maxw;
   float* bufB = bufA + maxw;
   const int E = a.net.n_experts, R = a.net.router_hidden;
+  // every warp first evaluates the experts on the all-zero input (a few thousand MACs, once per warp instead of once per subject)
+  float e_zero[PDF_MAX_MODS];
+  for (int e = 0; e < E; ++e) {
+    const pdf_mlp& ex = a.net.expert[e];
+    for (int i = lane; i < ex.dims[0]; i += 32) bufA[i] = 0.f;
+    __syncwarp();
+    float* in = bufA;
+    float* out = bufB;
+    for (int l = 0; l < ex.n_layers; ++l) {
+      warp_dense(ex.w[l], ex.b[l], ex.dims[l], ex.dims[l + 1], in, out, l < ex.n_layers - 1, lane);
+      float* t = in; in = out; out = t;
+    }
+    e_zero[e] = sigmoidf_(in[0]);
+    __syncwarp();
+  }
   for (int n = blockIdx.x * 8 + warp; n < N; n += gridDim.x * 8) {
     float e_x[PDF_MAX_MODS], e_0[PDF_MAX_MODS];
     for (int e = 0; e < E; ++e) {
       const pdf_mlp& ex = a.net.expert[e];
-      for (int pass = 0; pass < 2; ++pass) {   // pass 0: the subject's features, pass 1: the masked (all-zero) input
-        for (int i = lane; i < ex.dims[0]; i += 32) bufA[i] = pass == 0 ? a.x[e][(size_t)n * ex.dims[0] + i] : 0.f;
-        __syncwarp();
-        float* in = bufA;
-        float* out = bufB;
-        for (int l = 0; l < ex.n_layers; ++l) {
-          warp_dense(ex.w[l], ex.b[l], ex.dims[l], ex.dims[l + 1], in, out, l < ex.n_layers - 1, lane);
-          float* t = in; in = out; out = t;
-        }
-        const float v = sigmoidf_(in[0]);
-        if (pass == 0) e_x[e] = v; else e_0[e] = v;
-        __syncwarp();
+      e_0[e] = e_zero[e];                      // expert(0): the masked (all-zero) input gives the same output for every subject
+      for (int i = lane; i < ex.dims[0]; i += 32) bufA[i] = a.x[e][(size_t)n * ex.dims[0] + i];
+      __syncwarp();
+      float* in = bufA;
+      float* out = bufB;
+      for (int l = 0; l < ex.n_layers; ++l) {
+        warp_dense(ex.w[l], ex.b[l], ex.dims[l], ex.dims[l + 1], in, out, l < ex.n_layers - 1, lane);
+        float* t = in; in = out; out = t;
       }
+      e_x[e] = sigmoidf_(in[0]);
+      __syncwarp();
     }
     for (int s = 0; s < S; ++s) {
       const uint8_t* mk = masks + ((size_t)s * N + n) * E;
@@ -287,6 +388,8 @@ moe_sweep_kernel(MoeArgs a, const uint8_t* __restrict__ masks, int N, int S, int
     }
   }
 }
+
+static bool g_moddrop_tiled = true;   // pdf_debug_set_moddrop_tiled
 
 static int check_mlp(const pdf_mlp& m, const char* what) {
   PDF_REQUIRE(m.n_layers >= 1 && m.n_layers <= PDF_MAX_LAYERS, "%s: n_layers out of range", what);
@@ -383,7 +486,25 @@ extern "C" int pdf_moddrop_sweep(const pdf_mlp* net, int n_subjects, int n_scena
   for (int l = 2; l <= net->n_layers; ++l) maxw = max(maxw, net->dims[l]);
   const size_t smem = (size_t)8 * 2 * maxw * sizeof(float);
   if (smem > 48 * 1024) PDF_CHECK_CUDA(cudaFuncSetAttribute(moddrop_sweep_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-  const int blocks = max(1, min(ceil_div((long long)n_subjects * n_scenarios, 8), num_sms() * 8));
+  const long long pairs = (long long)n_subjects * n_scenarios;
+  if (g_moddrop_tiled && pairs >= 4096 && net->n_layers >= 2) {
+    // batched path: tiles of 64 (32 for wide networks) pairs, layers 2.. as in-block GEMMs
+    const int TP = maxw <= 384 ? 64 : 32;
+    const size_t tsmem = ((size_t)2 * TP * (maxw + 1) + 16 * 68) * sizeof(float);
+    if (tsmem <= 200 * 1024) {
+      const int tblocks = (int)max(1LL, min((pairs + TP - 1) / TP, (long long)num_sms() * (tsmem > 100 * 1024 ? 1 : 2)));
+      if (TP == 64) {
+        PDF_CHECK_CUDA(cudaFuncSetAttribute(moddrop_tile_kernel<64>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)tsmem));
+        moddrop_tile_kernel<64><<<tblocks, 256, tsmem, s>>>(*net, partials, d_masks, n_subjects, n_scenarios, maxw, d_prob);
+      } else {
+        PDF_CHECK_CUDA(cudaFuncSetAttribute(moddrop_tile_kernel<32>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)tsmem));
+        moddrop_tile_kernel<32><<<tblocks, 256, tsmem, s>>>(*net, partials, d_masks, n_subjects, n_scenarios, maxw, d_prob);
+      }
+      PDF_CHECK_LAUNCH();
+      return PDF_OK;
+    }
+  }
+  const int blocks = max(1, min(ceil_div(pairs, 8), num_sms() * 8));
   moddrop_sweep_kernel<<<blocks, 256, smem, s>>>(*net, partials, d_masks, n_subjects, n_scenarios, d_prob);
   PDF_CHECK_LAUNCH();
   return PDF_OK;
@@ -409,5 +530,11 @@ extern "C" int pdf_moe_sweep(const pdf_moe* net, int n_subjects, int n_scenarios
   const int blocks = max(1, min(ceil_div(n_subjects, 8), num_sms() * 8));
   moe_sweep_kernel<<<blocks, 256, smem, as_stream(stream)>>>(a, d_masks, n_subjects, n_scenarios, maxw, d_prob);
   PDF_CHECK_LAUNCH();
+  return PDF_OK;
+}
+
+/* A/B hook: 0 = the warp-per-pair ModDrop kernel for every size, 1 (default) = the tiled GEMM kernel from 4096 (scenario, subject) pairs up */
+extern "C" int pdf_debug_set_moddrop_tiled(int enable) {
+  pdf::g_moddrop_tiled = enable != 0;
   return PDF_OK;
 }

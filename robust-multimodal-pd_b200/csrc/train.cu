@@ -229,31 +229,33 @@ conv_wgrad_f32_kernel(const float* __restrict__ x, const float* __restrict__ dy,
 __global__ void __launch_bounds__(256)
 bn_stats_kernel(const float* __restrict__ x, const int* __restrict__ goff, int C, float eps, float* __restrict__ mean,
                 float* __restrict__ invstd, float* __restrict__ var_unbiased) {
-  __shared__ float red[8][33];
+  // float64 accumulators: these per-(group, channel) sums feed (x - mean) * invstd, whose cancellation amplifies every ulp of the
+  // statistics into the gradients (and Adam's sign-like first steps amplify THAT); the reductions are a negligible share of the work
+  __shared__ double red[8][33];
   const int g = blockIdx.y;
   const int c = blockIdx.x * 32 + (threadIdx.x & 31);
   const int ry = threadIdx.x >> 5;
   const int r0 = goff[g], r1 = goff[g + 1];
   const int rows = r1 - r0;
-  float s = 0.f;
-  if (c < C) for (int r = r0 + ry; r < r1; r += 8) s += x[(size_t)r * C + c];
+  double s = 0.0;
+  if (c < C) for (int r = r0 + ry; r < r1; r += 8) s += (double)x[(size_t)r * C + c];
   red[ry][threadIdx.x & 31] = s;
   __syncthreads();
-  float mu = 0.f;
+  double mu = 0.0;
   for (int i = 0; i < 8; ++i) mu += red[i][threadIdx.x & 31];
-  mu /= (float)max(rows, 1);
+  mu /= (double)max(rows, 1);
   __syncthreads();
-  float q = 0.f;
-  if (c < C) for (int r = r0 + ry; r < r1; r += 8) { const float d = x[(size_t)r * C + c] - mu; q = fmaf(d, d, q); }
+  double q = 0.0;
+  if (c < C) for (int r = r0 + ry; r < r1; r += 8) { const double d = (double)x[(size_t)r * C + c] - mu; q += d * d; }
   red[ry][threadIdx.x & 31] = q;
   __syncthreads();
   if (ry == 0 && c < C) {
-    float v = 0.f;
+    double v = 0.0;
     for (int i = 0; i < 8; ++i) v += red[i][threadIdx.x & 31];
-    const float var = v / (float)max(rows, 1);
-    mean[(size_t)g * C + c] = mu;
-    invstd[(size_t)g * C + c] = rsqrtf(var + eps);
-    var_unbiased[(size_t)g * C + c] = rows > 1 ? v / (float)(rows - 1) : var;
+    const double var = v / (double)max(rows, 1);
+    mean[(size_t)g * C + c] = (float)mu;
+    invstd[(size_t)g * C + c] = (float)(1.0 / sqrt(var + (double)eps));
+    var_unbiased[(size_t)g * C + c] = (float)(rows > 1 ? v / (double)(rows - 1) : var);
   }
 }
 
@@ -278,31 +280,31 @@ __global__ void __launch_bounds__(256)
 bn_bwd_reduce_kernel(const float* __restrict__ dy, const float* __restrict__ y, const float* __restrict__ x, const int* __restrict__ goff,
                      int C, const float* __restrict__ mean, const float* __restrict__ invstd, int relu, float* __restrict__ sum_g,
                      float* __restrict__ sum_gx, float* __restrict__ dgamma, float* __restrict__ dbeta) {
-  __shared__ float red0[8][33], red1[8][33];
+  __shared__ double red0[8][33], red1[8][33];        // float64 accumulators, as in bn_stats_kernel
   const int g = blockIdx.y;
   const int c = blockIdx.x * 32 + (threadIdx.x & 31);
   const int ry = threadIdx.x >> 5;
   const int r0 = goff[g], r1 = goff[g + 1];
-  float s0 = 0.f, s1 = 0.f;
+  double s0 = 0.0, s1 = 0.0;
   if (c < C) {
     const float mu = mean[(size_t)g * C + c], is = invstd[(size_t)g * C + c];
     for (int r = r0 + ry; r < r1; r += 8) {
       const size_t i = (size_t)r * C + c;
       float gr = dy[i];
       if (relu && !(y[i] > 0.f)) gr = 0.f;
-      s0 += gr;
-      s1 = fmaf(gr, (x[i] - mu) * is, s1);
+      s0 += (double)gr;
+      s1 += (double)gr * (double)((x[i] - mu) * is);
     }
   }
   red0[ry][threadIdx.x & 31] = s0; red1[ry][threadIdx.x & 31] = s1;
   __syncthreads();
   if (ry == 0 && c < C) {
-    float a = 0.f, b = 0.f;
+    double a = 0.0, b = 0.0;
     for (int i = 0; i < 8; ++i) { a += red0[i][threadIdx.x & 31]; b += red1[i][threadIdx.x & 31]; }
-    sum_g[(size_t)g * C + c] = a;
-    sum_gx[(size_t)g * C + c] = b;
-    atomicAdd(dbeta + c, a);
-    atomicAdd(dgamma + c, b);
+    sum_g[(size_t)g * C + c] = (float)a;
+    sum_gx[(size_t)g * C + c] = (float)b;
+    atomicAdd(dbeta + c, (float)a);
+    atomicAdd(dgamma + c, (float)b);
   }
 }
 
@@ -580,6 +582,54 @@ __global__ void adam_kernel(float* __restrict__ p, const float* __restrict__ g, 
   }
 }
 
+// p = sigmoid(z); loss += mean_i BCE(p_i, y_i); dz_i = d loss / d z_i   (nn.BCELoss on a Sigmoid output, logs clamped at -100 as torch)
+__global__ void bce_sigmoid_kernel(const float* __restrict__ z, const float* __restrict__ y, int n, float* __restrict__ p_out,
+                                   float* __restrict__ loss_sum, float* __restrict__ dz) {
+  __shared__ float red[8];
+  float ls = 0.f;
+  const float inv_n = 1.f / (float)n;
+  for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) {
+    const float p = sigm(z[i]), t = y[i];
+    const float lp = fmaxf(logf(p), -100.f), l1p = fmaxf(logf(1.f - p), -100.f);
+    ls -= t * lp + (1.f - t) * l1p;
+    const float dl_dp = -(t / fmaxf(p, 1e-44f)) * (lp > -100.f ? 1.f : 0.f) + ((1.f - t) / fmaxf(1.f - p, 1e-44f)) * (l1p > -100.f ? 1.f : 0.f);
+    p_out[i] = p;
+    dz[i] = dl_dp * p * (1.f - p) * inv_n;
+  }
+  ls = block_sum(ls, red);
+  if (threadIdx.x == 0) atomicAdd(loss_sum, ls * inv_n);
+}
+
+// MoE combine (models/moe.py:37-47) + BCE, forward and backward: out_i = sum_e sigmoid(z[i,e]) * softmax_e(r[i,:]);
+// loss = mean BCE(out, y); dz [n,E] (expert logits), dr [n,E] (router logits)
+__global__ void moe_combine_train_kernel(const float* __restrict__ z, const float* __restrict__ r, const float* __restrict__ y, int n, int E,
+                                         float* __restrict__ out, float* __restrict__ loss_sum, float* __restrict__ dz, float* __restrict__ dr) {
+  __shared__ float red[8];
+  float ls = 0.f;
+  const float inv_n = 1.f / (float)n;
+  for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) {
+    float mx = -INFINITY;
+    for (int e = 0; e < E; ++e) mx = fmaxf(mx, r[(size_t)i * E + e]);
+    float se = 0.f;
+    for (int e = 0; e < E; ++e) se += expf(r[(size_t)i * E + e] - mx);
+    float o = 0.f;
+    for (int e = 0; e < E; ++e) o += sigm(z[(size_t)i * E + e]) * (expf(r[(size_t)i * E + e] - mx) / se);
+    const float t = y[i];
+    const float lp = fmaxf(logf(o), -100.f), l1p = fmaxf(logf(1.f - o), -100.f);
+    ls -= t * lp + (1.f - t) * l1p;
+    const float dl_do = (-(t / fmaxf(o, 1e-44f)) * (lp > -100.f ? 1.f : 0.f) + ((1.f - t) / fmaxf(1.f - o, 1e-44f)) * (l1p > -100.f ? 1.f : 0.f)) * inv_n;
+    out[i] = o;
+    for (int e = 0; e < E; ++e) {
+      const float pe = sigm(z[(size_t)i * E + e]);
+      const float we = expf(r[(size_t)i * E + e] - mx) / se;
+      dz[(size_t)i * E + e] = dl_do * we * pe * (1.f - pe);
+      dr[(size_t)i * E + e] = dl_do * we * (pe - o);               // softmax backward: w_e * (d_w_e - sum_j w_j d_w_j), d_w_e = dl_do * p_e
+    }
+  }
+  ls = block_sum(ls, red);
+  if (threadIdx.x == 0) atomicAdd(loss_sum, ls * inv_n);
+}
+
 static inline int ew_blocks(size_t n) { return (int)std::max<size_t>(1, std::min<size_t>((n + 255) / 256, (size_t)num_sms() * 16)); }
 
 }  // namespace pdf
@@ -749,6 +799,22 @@ extern "C" int pdf_adam_step(float* d_param, const float* d_grad, float* d_m, fl
   PDF_REQUIRE(d_param && d_grad && d_m && d_v && n > 0 && step >= 1, "pdf_adam_step: bad arguments");
   const float bc1 = 1.f - powf(beta1, (float)step), bc2 = 1.f - powf(beta2, (float)step);
   adam_kernel<<<ew_blocks(n), 256, 0, as_stream(stream)>>>(d_param, d_grad, d_m, d_v, n, lr, beta1, beta2, eps, weight_decay, bc1, bc2, d_grad_scale);
+  PDF_CHECK_LAUNCH();
+  return PDF_OK;
+}
+
+extern "C" int pdf_bce_sigmoid_train(int n, const float* d_z, const float* d_y, float* d_prob, float* d_loss, float* d_dz, pdf_stream_t stream) {
+  PDF_REQUIRE(n > 0 && d_z && d_y && d_prob && d_loss && d_dz, "pdf_bce_sigmoid_train: bad arguments");
+  bce_sigmoid_kernel<<<ew_blocks((size_t)n), 256, 0, as_stream(stream)>>>(d_z, d_y, n, d_prob, d_loss, d_dz);
+  PDF_CHECK_LAUNCH();
+  return PDF_OK;
+}
+
+extern "C" int pdf_moe_combine_train(int n, int n_experts, const float* d_z, const float* d_r, const float* d_y, float* d_out, float* d_loss,
+                                     float* d_dz, float* d_dr, pdf_stream_t stream) {
+  PDF_REQUIRE(n > 0 && n_experts > 0 && n_experts <= PDF_MAX_MODS && d_z && d_r && d_y && d_out && d_loss && d_dz && d_dr,
+              "pdf_moe_combine_train: bad arguments");
+  moe_combine_train_kernel<<<ew_blocks((size_t)n), 256, 0, as_stream(stream)>>>(d_z, d_r, d_y, n, n_experts, d_out, d_loss, d_dz, d_dr);
   PDF_CHECK_LAUNCH();
   return PDF_OK;
 }

@@ -133,6 +133,8 @@ PROTOTYPES = {
     "pdf_maxpool_backward_f32": (C.c_int, [C.c_int, C.c_int, C.c_int, C.c_int, _P, _P, _P, _P]),
     "pdf_avgpool_backward_f32": (C.c_int, [C.c_int, C.c_int, C.c_int, _P, _P, _P]),
     "pdf_mil_pool_train": (C.c_int, [C.POINTER(MilWeights), C.POINTER(MilTrain), C.c_int, C.c_int, _P, _P, _P, _P, _P, _P, _P, _P, _P]),
+    "pdf_bce_sigmoid_train": (C.c_int, [C.c_int, _P, _P, _P, _P, _P, _P]),
+    "pdf_moe_combine_train": (C.c_int, [C.c_int, C.c_int, _P, _P, _P, _P, _P, _P, _P, _P]),
     "pdf_colsum_f32": (C.c_int, [C.c_int, C.c_int, _P, _P, C.c_int, _P]),
     "pdf_relu_mask_backward": (C.c_int, [_P, _P, _P, C.c_size_t, _P]),
     "pdf_mul_f32": (C.c_int, [_P, _P, C.c_size_t, _P]),
@@ -151,6 +153,7 @@ PROTOTYPES = {
     "pdf_debug_disable_halo": (C.c_int, [C.c_int]),
     "pdf_debug_set_pw": (C.c_int, [C.c_int]),
     "pdf_debug_set_sm_cap": (C.c_int, [C.c_int]),
+    "pdf_debug_set_moddrop_tiled": (C.c_int, [C.c_int]),
     "pdf_debug_set_pw_config": (C.c_int, [C.c_int, C.c_int]),
 }
 

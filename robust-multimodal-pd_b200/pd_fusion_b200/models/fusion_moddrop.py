@@ -49,24 +49,54 @@ class ModalityDropoutModel(BaseModel):
         self.params = params
         self.modality_dims = modality_dims
         self.model = ModalityDropoutNet(modality_dims, params["hidden_dims"], params.get("dropout", 0.2))
-        self.optimizer = torch.optim.Adam(self.model.parameters(), lr=params["lr"], weight_decay=params.get("weight_decay", 0.0))
-        self.criterion = nn.BCELoss()
         self._sweep: Optional[ModDropSweep] = None
+        self._train = None      # (MlpTrainer, NativeAdam): created on first train(), Adam moments persist like the reference's self.optimizer
 
     def train(self, X, y, val_data=None):
-        """Host-side torch training (SURVEY.md 8f rank 2 'next'); modality dropout draws follow the reference."""
-        Xt = torch.as_tensor(np.asarray(X), dtype=torch.float32)
-        yt = torch.as_tensor(np.asarray(y), dtype=torch.float32).view(-1, 1)
+        """The reference's loop (models/fusion_moddrop.py:69-91: torch.randperm mini-batches, one np.random.rand() per modality per
+        batch for the modality dropout, nn.BCELoss, Adam) with every step on the native kernels: pdf_gemm_f32 forward / dgrad / wgrad,
+        pdf_bce_sigmoid_train, pdf_adam_step.  The table stays resident on the device."""
+        from .. import _lib
+        from ..training import MlpTrainer, NativeAdam
+        dev = get_torch_device()
+        if self._train is None:
+            self.model.to(dev).float()
+            mt = MlpTrainer(self.model.net, "net.")
+            self._train = (mt, NativeAdam([([q for q, _ in mt.param_grads()], float(self.params["lr"]))],
+                                          weight_decay=float(self.params.get("weight_decay", 0.0))))
+        mt, opt = self._train
+        lib = _lib.load()
+        Xt = torch.as_tensor(np.asarray(X), dtype=torch.float32).to(dev)
+        yt = torch.as_tensor(np.asarray(y), dtype=torch.float32).to(dev)
         rate, bs = self.params.get("moddrop_rate", 0.2), self.params.get("batch_size", 32)
+        lr = opt.groups[0][1]
+        net = self.model
+        self.last_losses = []
         for _ in range(self.params["epochs"]):
-            self.model.train()
-            order = torch.randperm(len(Xt))
+            net.train()
+            order = torch.randperm(len(Xt)).to(dev)
             for i in range(0, len(Xt), bs):
                 sel = order[i:i + bs]
-                self.optimizer.zero_grad()
-                loss = self.criterion(self.model(Xt[sel], training_dropout=True, drop_rate=rate), yt[sel])
-                loss.backward()
-                self.optimizer.step()
+                xb, yb = Xt[sel].contiguous(), yt[sel].contiguous()
+                keep = None
+                for mod in net.mod_names:       # one np.random.rand() per modality per batch, as the reference draws them
+                    if np.random.rand() < rate:
+                        if keep is None:
+                            keep = torch.ones_like(xb)
+                        a, b = net.slices[mod]
+                        keep[:, a:b] = 0.0
+                if keep is not None:
+                    _lib.check(lib.pdf_mul_f32(xb.data_ptr(), keep.data_ptr(), xb.numel(), _lib.stream_ptr()), "pdf_mul_f32")
+                mt.zero_grad()
+                z = mt.forward(xb, train=True)
+                n = int(z.shape[0])
+                prob, dz = torch.empty(n, dtype=torch.float32, device=dev), torch.empty((n, 1), dtype=torch.float32, device=dev)
+                loss = torch.zeros(1, dtype=torch.float32, device=dev)
+                _lib.check(lib.pdf_bce_sigmoid_train(n, z.data_ptr(), yb.data_ptr(), prob.data_ptr(), loss.data_ptr(), dz.data_ptr(),
+                                                     _lib.stream_ptr()), "pdf_bce_sigmoid_train")
+                mt.backward(dz)
+                opt.step([(q, g, lr) for q, g in mt.param_grads()])
+                self.last_losses.append(loss)
         self._sweep = None
 
     def invalidate(self):

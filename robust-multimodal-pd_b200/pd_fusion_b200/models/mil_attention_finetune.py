@@ -233,8 +233,11 @@ class MilAttentionFineTuneModel(BaseModel):
             if bag is None:
                 stacks.append(None)
                 continue
-            sl = torch.from_numpy(np.ascontiguousarray(self._bag_slices(bag))).to(self.device)
-            if augment and self.train_aug and not isinstance(bag, np.ndarray):      # the reference augments bags it loads itself
+            if isinstance(bag, torch.Tensor):                                       # slice stack already resident on the device
+                sl = bag.to(device=self.device, dtype=torch.float32)
+            else:
+                sl = torch.from_numpy(np.ascontiguousarray(self._bag_slices(bag))).to(self.device)
+            if augment and self.train_aug and not isinstance(bag, (np.ndarray, torch.Tensor)):   # the reference augments bags it loads itself
                 sl = self._augment(sl, np.random.default_rng())
             stacks.append(sl)
             L = int(sl.shape[0])
@@ -271,6 +274,8 @@ class MilAttentionFineTuneModel(BaseModel):
                     k += L
             rt.backward(demb)
             pg = [(q, g, opt.groups[0][1]) for q, g in rt.param_grads()] + pg
+        from ..training import allreduce_mean
+        allreduce_mean([ht.flat_grad] + ([] if frozen else [rt.flat_grad]))          # data-parallel over bags under torchrun
         scale = opt.clip([g for _, g, _ in pg], float(clip)) if clip else None
         opt.step(pg, scale)
         if not frozen:

@@ -47,18 +47,46 @@ class MoEModel(BaseModel):
         self.params = params
         self.modality_dims = dict(modality_dims)
         self.model = MoENet(modality_dims, params)
-        self.optimizer = torch.optim.Adam(self.model.parameters(), lr=params["lr"], weight_decay=params.get("weight_decay", 0.0))
-        self.criterion = nn.BCELoss()
         self._sweep: Optional[MoeSweep] = None
+        self._train = None      # (expert trainers, router trainer, NativeAdam), created on first train()
 
     def train(self, X_dict, y, mask, val_data=None):
-        yt = torch.as_tensor(np.asarray(y), dtype=torch.float32).view(-1, 1)
-        for _ in range(self.params["epochs"]):      # full-batch steps, as the reference
+        """Full-batch steps as the reference (models/moe.py:60-70), every step on the native kernels: the experts' and the router's
+        linear layers through pdf_gemm_f32 (forward, dgrad, wgrad), the gated combination + BCE and their backward in
+        pdf_moe_combine_train, then pdf_adam_step.  Inputs stay resident on the device."""
+        from .. import _lib
+        from ..training import MlpTrainer, NativeAdam
+        dev = get_torch_device()
+        mods = sorted(X_dict)                                # MoENet.forward pairs router output i with sorted(modality) i
+        if self._train is None:
+            self.model.to(dev).float()
+            experts = {m: MlpTrainer(self.model.experts[m].net, f"experts.{m}.net.") for m in mods}
+            router = MlpTrainer(self.model.router, "router.")
+            allp = [q for t in list(experts.values()) + [router] for q, _ in t.param_grads()]
+            self._train = (experts, router, NativeAdam([(allp, float(self.params["lr"]))], weight_decay=float(self.params.get("weight_decay", 0.0))))
+        experts, router, opt = self._train
+        lib = _lib.load()
+        X = {m: torch.as_tensor(np.asarray(X_dict[m]), dtype=torch.float32).to(dev).contiguous() for m in mods}
+        mk = torch.as_tensor(np.asarray(mask), dtype=torch.float32).to(dev).contiguous()
+        yt = torch.as_tensor(np.asarray(y), dtype=torch.float32).to(dev).contiguous()
+        n, E = int(yt.shape[0]), len(mods)
+        lr = opt.groups[0][1]
+        self.last_losses = []
+        for _ in range(self.params["epochs"]):
             self.model.train()
-            self.optimizer.zero_grad()
-            loss = self.criterion(self.model(X_dict, mask), yt)
-            loss.backward()
-            self.optimizer.step()
+            for t in list(experts.values()) + [router]:
+                t.zero_grad()
+            z = torch.stack([experts[m].forward(X[m])[:, 0] for m in mods], dim=1).contiguous()       # [n, E] expert logits (layout only)
+            r = router.forward(mk)                                                                     # [n, E] router logits
+            out, dz, dr = torch.empty(n, dtype=torch.float32, device=dev), torch.empty_like(z), torch.empty_like(r)
+            loss = torch.zeros(1, dtype=torch.float32, device=dev)
+            _lib.check(lib.pdf_moe_combine_train(n, E, z.data_ptr(), r.data_ptr(), yt.data_ptr(), out.data_ptr(), loss.data_ptr(),
+                                                 dz.data_ptr(), dr.data_ptr(), _lib.stream_ptr()), "pdf_moe_combine_train")
+            for e, m in enumerate(mods):
+                experts[m].backward(dz[:, e:e + 1].contiguous())
+            router.backward(dr)
+            opt.step([(q, g, lr) for t in list(experts.values()) + [router] for q, g in t.param_grads()])
+            self.last_losses.append(loss)
         self._sweep = None
 
     def invalidate(self):

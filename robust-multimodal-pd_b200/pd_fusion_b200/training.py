@@ -26,6 +26,34 @@ def _p(t: Optional[torch.Tensor]):
     return None if t is None else t.data_ptr()
 
 
+def _flat_like(params: Dict[str, torch.Tensor]):
+    """One flat gradient buffer with a view per parameter: zeroing and the data-parallel all-reduce are ONE call each."""
+    first = next(iter(params.values()))
+    offs, total = {}, 0
+    for k, v in params.items():
+        offs[k] = total
+        total += (v.numel() + 7) // 8 * 8                    # 32-byte aligned views
+    flat = torch.zeros(total, dtype=torch.float32, device=first.device)
+    return flat, {k: flat[offs[k]:offs[k] + v.numel()].view(v.shape) for k, v in params.items()}
+
+
+def allreduce_mean(flat_grads: Sequence[torch.Tensor]) -> None:
+    """Data-parallel fine-tuning: every rank runs its own bags, the gradients are averaged with one NCCL
+    all-reduce per flat buffer before clip + Adam.  No-op in a single process."""
+    if not (torch.distributed.is_available() and torch.distributed.is_initialized()):
+        return
+    ws = torch.distributed.get_world_size()
+    if ws == 1:
+        return
+    nccl = torch.distributed.get_backend() == "nccl"
+    for f in flat_grads:
+        if nccl:
+            torch.distributed.all_reduce(f, op=torch.distributed.ReduceOp.AVG)       # averaged inside the collective
+        else:                                                                          # gloo (CPU tests) has no AVG
+            torch.distributed.all_reduce(f, op=torch.distributed.ReduceOp.SUM)
+            f.mul_(1.0 / ws)
+
+
 class NativeAdam:
     """torch.optim.Adam (betas 0.9/0.999, eps 1e-8, L2-style weight decay) + clip_grad_norm_ on device tensors.
     groups: [(params: List[Tensor], lr)], gradients in `grads` (same order)."""
@@ -75,7 +103,7 @@ class MilHeadTrainer:
         for v in self.p.values():
             if not (v.is_cuda and v.dtype == torch.float32 and v.is_contiguous()):
                 raise ValueError("MilHeadTrainer needs contiguous float32 CUDA parameters")
-        self.g = {k: torch.zeros_like(v) for k, v in self.p.items()}
+        self.flat_grad, self.g = _flat_like(self.p)
         self.H, self.D = self.p["instance.0.weight"].shape
         self.A = (self.p["attn_v.0.weight"] if self.gated else self.p["attn.0.weight"]).shape[0]
         self.NA = 2 * self.A if self.gated else self.A
@@ -86,8 +114,7 @@ class MilHeadTrainer:
         return [(self.p[k], self.g[k]) for k in self.p]
 
     def zero_grad(self):
-        for g in self.g.values():
-            g.zero_()
+        self.flat_grad.zero_()
 
     def _gemm(self, M, N, K, A, a_rs, a_cs, B, b_rs, b_cs, Cm, c_rs, bias=None, act=0, acc=0):
         _lib.check(self.lib.pdf_gemm_f32(M, N, K, A.data_ptr() if isinstance(A, torch.Tensor) else A, a_rs, a_cs,
@@ -162,6 +189,73 @@ class MilHeadTrainer:
         return self._ones_buf
 
 
+class MlpTrainer:
+    """Forward to the LOGITS and backward from d(logits) of an `nn.Sequential` MLP made of Linear / ReLU / Dropout / (final Sigmoid or
+    Softmax, which the loss kernels own): the fusion heads' networks (models/fusion_moddrop.py:25-35, models/moe.py:7-35).
+    Parameters are the module's tensors; gradients live in one flat buffer."""
+
+    def __init__(self, seq: nn.Sequential, prefix: str = ""):
+        _lib.require_cuda()
+        self.lib = _lib.load()
+        self.layers: List[Tuple[str, nn.Linear, bool, float]] = []        # (name, linear, relu after, dropout p after)
+        mods = list(seq)
+        for i, m in enumerate(mods):
+            if isinstance(m, nn.Linear):
+                relu = i + 1 < len(mods) and isinstance(mods[i + 1], nn.ReLU)
+                drop = float(mods[i + 2].p) if relu and i + 2 < len(mods) and isinstance(mods[i + 2], nn.Dropout) else 0.0
+                self.layers.append((f"{prefix}{i}", m, relu, drop))
+        self.p = {}
+        for name, lin, _, _ in self.layers:
+            self.p[name + ".weight"], self.p[name + ".bias"] = lin.weight.data, lin.bias.data
+        for v in self.p.values():
+            if not (v.is_cuda and v.dtype == torch.float32 and v.is_contiguous()):
+                raise ValueError("MlpTrainer needs contiguous float32 CUDA parameters")
+        self.flat_grad, self.g = _flat_like(self.p)
+        self.dev = next(iter(self.p.values())).device
+
+    def param_grads(self):
+        return [(self.p[k], self.g[k]) for k in self.p]
+
+    def zero_grad(self):
+        self.flat_grad.zero_()
+
+    def forward(self, X: torch.Tensor, train: bool = True) -> torch.Tensor:
+        s = _lib.stream_ptr()
+        a = X.contiguous()
+        self.saved = []
+        for name, lin, relu, drop in self.layers:
+            n_out, n_in = lin.weight.shape
+            out = torch.empty((a.shape[0], n_out), dtype=torch.float32, device=self.dev)
+            _lib.check(self.lib.pdf_gemm_f32(a.shape[0], n_out, n_in, a.data_ptr(), n_in, 1, lin.weight.data.data_ptr(), 1, n_in, out.data_ptr(), n_out,
+                                             lin.bias.data.data_ptr(), 1 if relu else 0, 0, s), "pdf_gemm_f32")
+            mask = None
+            if train and relu and drop > 0:
+                keep = 1.0 - drop
+                mask = (torch.rand(out.shape, device=self.dev) < keep).to(torch.float32) / keep       # random draw only
+                _lib.check(self.lib.pdf_mul_f32(out.data_ptr(), mask.data_ptr(), out.numel(), s), "pdf_mul_f32")
+            self.saved.append((a, out, mask))
+            a = out
+        return a
+
+    def backward(self, dlogits: torch.Tensor) -> None:
+        s = _lib.stream_ptr()
+        d = dlogits.contiguous()
+        for (name, lin, relu, drop), (a_in, out, mask) in zip(reversed(self.layers), reversed(self.saved)):
+            n_out, n_in = lin.weight.shape
+            rows = a_in.shape[0]
+            if relu:
+                _lib.check(self.lib.pdf_relu_mask_backward(d.data_ptr(), out.data_ptr(), _p(mask), d.numel(), s), "pdf_relu_mask_backward")
+            _lib.check(self.lib.pdf_gemm_f32(n_out, n_in, rows, d.data_ptr(), 1, n_out, a_in.data_ptr(), n_in, 1, self.g[name + ".weight"].data_ptr(), n_in,
+                                             None, 0, 1, s), "pdf_gemm_f32")
+            _lib.check(self.lib.pdf_colsum_f32(rows, n_out, d.data_ptr(), self.g[name + ".bias"].data_ptr(), 1, s), "pdf_colsum_f32")
+            if name != self.layers[0][0]:
+                dn = torch.empty((rows, n_in), dtype=torch.float32, device=self.dev)
+                _lib.check(self.lib.pdf_gemm_f32(rows, n_in, n_out, d.data_ptr(), n_out, 1, lin.weight.data.data_ptr(), n_in, 1, dn.data_ptr(), n_in,
+                                                 None, 0, 0, s), "pdf_gemm_f32")
+                d = dn
+        self.saved = []
+
+
 class _Act:
     __slots__ = ("data", "grad", "n", "hw", "c")
 
@@ -187,7 +281,7 @@ class ResNetTrainer:
         self.dev = self.params["conv1.weight"].device
         self.convs = {cv["name"]: cv for cv in conv_list(arch)}
         self.wk: Dict[str, torch.Tensor] = {}
-        self.grad: Dict[str, torch.Tensor] = {k: torch.zeros_like(v.data) for k, v in self.params.items() if not k.startswith("fc.")}
+        self.flat_grad, self.grad = _flat_like({k: v.data for k, v in self.params.items() if not k.startswith("fc.")})
         self._gwk: Dict[str, torch.Tensor] = {}
         self.sync_weights()
 
@@ -198,8 +292,7 @@ class ResNetTrainer:
             self.wk[name] = w.permute(2, 3, 1, 0).contiguous()          # [R,S,C,K] (layout change only)
 
     def zero_grad(self):
-        for g in self.grad.values():
-            g.zero_()
+        self.flat_grad.zero_()
 
     def param_grads(self) -> List[Tuple[torch.Tensor, torch.Tensor]]:
         return [(self.params[k].data, self.grad[k]) for k in self.grad]

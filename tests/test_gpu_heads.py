@@ -158,3 +158,33 @@ def test_mil_tensor_path(D, H, A, gated, L):
     sdn = {k: v.numpy() for k, v in sd.items()}
     ref = O.mil_predict_proba(sdn, [X[i, :lens[i]] if lens[i] else None for i in range(8)], gated, None, 0.37)
     np.testing.assert_allclose(MilHead(sd, gated, 0.37).forward(Xd[:8].contiguous(), ld[:8]).cpu().numpy(), ref, atol=5e-6, rtol=0)
+
+
+@pytest.mark.parametrize("dims,hidden,N", [({"clinical": 0, "datspect": 0, "mri": 512}, [256, 128, 64], 3001),
+                                            ({"clinical": 10, "datspect": 5, "mri": 20}, [64, 32], 5000),
+                                            ({"clinical": 7, "datspect": 3, "mri": 33}, [500, 40], 1100)])
+def test_moddrop_tiled_path_equals_warp_path_and_oracle(dims, hidden, N):
+    """From 4096 (scenario, subject) pairs up the sweep runs layers 2.. as in-block tiled GEMMs (weights fetched once per 64-pair
+    tile): same probabilities as the warp-per-pair kernel (2e-6) and as the oracle evaluated scenario by scenario (5e-6)."""
+    from pd_fusion_b200 import _lib
+    from pd_fusion_b200.models.fusion_moddrop import ModalityDropoutNet
+    lib = _lib.load()
+    torch.manual_seed(N)
+    sd = ModalityDropoutNet(dims, hidden, 0.3).state_dict()
+    F = sum(dims.values())
+    rng = np.random.default_rng(N)
+    X = rng.standard_normal((N, F)).astype(np.float32)
+    mk = (rng.random((7, N, 3)) < 0.7).astype(np.uint8)
+    sweep = ModDropSweep(sd, dims)
+    Xd, md = torch.from_numpy(X).cuda(), torch.from_numpy(mk).cuda()
+    p_t = sweep.forward(Xd, md).cpu().numpy()
+    lib.pdf_debug_set_moddrop_tiled(0)
+    try:
+        p_w = sweep.forward(Xd, md).cpu().numpy()
+    finally:
+        lib.pdf_debug_set_moddrop_tiled(1)
+    np.testing.assert_allclose(p_t, p_w, atol=2e-6, rtol=0)
+    sdn = {k: v.numpy() for k, v in sd.items()}
+    for s in (0, 3, 6):
+        ref = O.moddrop_predict_proba(sdn, dims, X, {m: mk[s][:, i] for i, m in enumerate(O.MODALITIES)})
+        np.testing.assert_allclose(p_t[s], ref, atol=5e-6, rtol=0)

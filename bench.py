@@ -578,7 +578,17 @@ def main():
     # --- fusion heads: every scenario in one call at N = 10 000 and 1 000 000 subjects
     heads = None
     if not args.no_heads and rank == 0:
-        heads = heads_leg(dev, peaks, timed)
+        def timed_local(fn, steps):          # rank 0 only: NO collective inside (the other ranks are not here)
+            torch.cuda.synchronize()
+            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            e0.record()
+            for _ in range(steps):
+                fn()
+            e1.record()
+            torch.cuda.synchronize()
+            return float(e0.elapsed_time(e1))
+        heads = heads_leg(dev, peaks, timed_local)
+    barrier()
 
     run_e2e()                                            # warm-up (allocates the second device buffer)
     barrier(); torch.cuda.synchronize()
@@ -611,6 +621,7 @@ def main():
         if ws > 1:
             torch.distributed.all_reduce(t_i16, op=torch.distributed.ReduceOp.MAX)
         e2e_i16 = {"value": ws * B * args.steps / (float(t_i16.item()) / 1e3), "unit": UNIT, "h2d_bytes_per_step": int(pinned_i16.numel() * 2),
+                   "h2d_gbs_per_gpu": pinned_i16.numel() * 2 / (float(t_i16.item()) / args.steps / 1e3) / 1e9,
                    "ms_per_step": float(t_i16.item()) / args.steps,
                    "input": "voxels as an int16 NIfTI stores them (Fortran order); float64 scaling rule, cast and transpose on the device"}
 
@@ -628,7 +639,8 @@ def main():
                    "streams": ("preprocessing of batch i+1 overlaps the conv stack of batch i (2 streams); " if overlap else "preprocessing + conv stack on one stream; ") +
                               "fusion head and gathers on a side stream next to the following batch"},
         "clocks": clk.summary(),
-        "e2e": {"value": e2e, "unit": UNIT, "h2d_bytes_per_step": int(pinned.numel() * 4), "d2h_bytes_per_step": int(host_out.numel() * 4 + B * S_scen * 4), "overlap": "H2D of batch i+1 on a copy stream overlaps the kernels of batch i", "timer": "host wall clock around K steps, device synchronised on both sides",
+        "e2e": {"value": e2e, "unit": UNIT, "h2d_gbs_per_gpu": pinned.numel() * 4 / (ms_e2e / args.steps / 1e3) / 1e9,
+                "h2d_bytes_per_step": int(pinned.numel() * 4), "d2h_bytes_per_step": int(host_out.numel() * 4 + B * S_scen * 4), "overlap": "H2D of batch i+1 on a copy stream overlaps the kernels of batch i", "timer": "host wall clock around K steps, device synchronised on both sides",
                 "ms_per_step": ms_e2e / args.steps},
         "e2e_stored_int16": e2e_i16,
         "gpu_launches": int(launches),

@@ -5,6 +5,7 @@ assembled with an NCCL all-gather over NVLink.  The reference has no distributed
 """
 from __future__ import annotations
 
+import datetime
 import os
 from typing import Tuple
 
@@ -23,11 +24,14 @@ def init_distributed(backend: str | None = None) -> Tuple[int, int, int]:
         os.environ.setdefault("MASTER_PORT", "29531")
         if backend is None:
             backend = "nccl" if torch.cuda.is_available() else "gloo"
+        # a mismatched collective should fail in minutes, not hold N GPUs for the default 10
+        timeout = datetime.timedelta(seconds=int(os.environ.get("PD_FUSION_B200_DIST_TIMEOUT_S", "180")))
         if backend == "nccl":
             torch.cuda.set_device(local_rank)
-            torch.distributed.init_process_group(backend=backend, rank=rank, world_size=ws, device_id=torch.device("cuda", local_rank))
+            torch.distributed.init_process_group(backend=backend, rank=rank, world_size=ws, device_id=torch.device("cuda", local_rank),
+                                                 timeout=timeout)
         else:
-            torch.distributed.init_process_group(backend=backend, rank=rank, world_size=ws)
+            torch.distributed.init_process_group(backend=backend, rank=rank, world_size=ws, timeout=timeout)
     return rank, local_rank, ws
 
 

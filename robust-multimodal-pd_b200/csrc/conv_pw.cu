@@ -42,6 +42,7 @@ struct PwParams {
   int Ho, Wo, stride;           // im2col (strided 1x1) geometry
   int N2;                       // chained output channels
   int stages, nry;              // ring depth, staging buffers
+  int bias_staged;              // 1: bias vector copied to shared memory at kernel start, 0: read from global memory (L1-resident)
   const float* bias;
   const float* bias3;
   __nv_bfloat16* out3;
@@ -53,8 +54,10 @@ struct PwSmem {
   static constexpr int kRyBytes = NC * 256;                                         // 128 rows x NC channels bf16 = NC/64 sub-tiles of 16 KB
   // layout: ring [stages] | staging [nry] | barriers | TMEM slot | bias
   static constexpr int kNumBars = 2 * kPwMaxStages + 4 + 3 * kPwMaxRy + 2;
-  static constexpr int kTail = kNumBars * 8 + 16 + 16 + (kPwBiasMax + 256) * 4;
-  static int dynamic_bytes(int stages, int nry) { return stages * kStageBytes + nry * kRyBytes + kTail + 1024; }
+  // tail: barriers | TMEM slot | chained bias [256] | bias [bias_floats] (0 = the epilogue reads the bias from global memory)
+  static int dynamic_bytes(int stages, int nry, int bias_floats) {
+    return stages * kStageBytes + nry * kRyBytes + kNumBars * 8 + 16 + 16 + (256 + bias_floats) * 4 + 1024;
+  }
 };
 
 __device__ __forceinline__ void tma_store_2d(const void* tmap, uint32_t src, int c0, int c1) {
@@ -100,11 +103,12 @@ conv_pw_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant
   const uint32_t bar_acc2full = bar_yready + 8 * kPwMaxRy;
   const uint32_t bar_acc2empty = bar_acc2full + 8;
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(smem + bar_off + L::kNumBars * 8);
-  float* s_bias = reinterpret_cast<float*>(smem + bar_off + L::kNumBars * 8 + 16);
-  float* s_bias3 = s_bias + kPwBiasMax;
+  float* s_bias3 = reinterpret_cast<float*>(smem + bar_off + L::kNumBars * 8 + 16);
+  float* s_bias = s_bias3 + 256;
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  for (int i = threadIdx.x; i < p.Cout; i += blockDim.x) s_bias[i] = p.bias ? __ldg(p.bias + i) : 0.f;
+  if (p.bias_staged)
+    for (int i = threadIdx.x; i < p.Cout; i += blockDim.x) s_bias[i] = p.bias ? __ldg(p.bias + i) : 0.f;
   if (CHAIN)
     for (int i = threadIdx.x; i < p.N2; i += blockDim.x) s_bias3[i] = p.bias3 ? __ldg(p.bias3 + i) : 0.f;
 
@@ -284,7 +288,7 @@ conv_pw_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant
         uint32_t v[32];
         tmem_ld32(tmem_base + ((uint32_t)(quad * 32) << 16) + (uint32_t)(acc * NC + ch * 32), v);
         const uint32_t sub = ry + (uint32_t)(ch >> 1) * kABytes + row_off;      // 64-channel sub-tile, this thread's 128-byte row
-        const float* bp = s_bias + n0 + ch * 32;
+        const float* bp = (p.bias_staged ? s_bias : p.bias) + n0 + ch * 32;
 #pragma unroll
         for (int q = 0; q < 4; ++q) {                                          // 8 channels = one 16-byte unit
           const uint32_t addr = sub + ((((uint32_t)((ch & 1) * 4 + q)) ^ sw) << 4);
@@ -389,15 +393,19 @@ static int launch_pw(const TcConv& tc, cudaStream_t s) {
   // u+1 streams in while unit u is still in its buffer), the others the fourth ring stage
   const bool wants_staging = tc.residual != nullptr || CHAIN;
   int stages = g_pw_stages ? g_pw_stages : (wants_staging ? 3 : 4), nry = g_pw_ry ? g_pw_ry : (wants_staging ? 3 : 2);
-  while (L::dynamic_bytes(stages, nry) > 227 * 1024 && stages > 2) --stages;
-  const int smem = L::dynamic_bytes(stages, nry);
+  // the bias vector is staged in shared memory when it fits next to the requested ring; a deeper ring wins over bias staging
+  // (the epilogue then reads the bias through L1), and the ring shrinks only when even that does not fit
+  int bias_floats = tc.Cout;
+  if (L::dynamic_bytes(stages, nry, bias_floats) > 227 * 1024 && tc.bias != nullptr) bias_floats = 0;
+  while (L::dynamic_bytes(stages, nry, bias_floats) > 227 * 1024 && stages > 2) --stages;
+  const int smem = L::dynamic_bytes(stages, nry, bias_floats);
   static int configured = 0;
   if (smem > configured) {
     PDF_CHECK_CUDA(cudaFuncSetAttribute(conv_pw_kernel<NC, CHAIN>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
     configured = smem;
   }
   PwParams p;
-  p.stages = stages; p.nry = nry;
+  p.stages = stages; p.nry = nry; p.bias_staged = bias_floats > 0 || tc.bias == nullptr;
   p.M_total = tc.M_total; p.Cout = tc.Cout; p.K = tc.Cin; p.n_chunks = tc.Cout / NC; p.m_tiles = ceil_div(tc.M_total, kBlockM);
   p.relu = tc.relu; p.im2col = tc.im2col; p.has_res = tc.residual != nullptr;
   p.Ho = tc.Ho; p.Wo = tc.Wo; p.stride = tc.stride;

@@ -293,6 +293,15 @@ int pdf_mil_pool_train(const pdf_mil_weights* w, const pdf_mil_train* t, int n_b
 int pdf_bce_sigmoid_train(int n, const float* d_z, const float* d_y, float* d_prob, float* d_loss, float* d_dz, pdf_stream_t stream);
 int pdf_moe_combine_train(int n, int n_experts, const float* d_z, const float* d_r, const float* d_y, float* d_out, float* d_loss,
                           float* d_dz, float* d_dr, pdf_stream_t stream);
+/* tensor-core training path (bf16 operands, f32 accumulation and f32 results):
+ * pdf_conv_wgrad_bf16: weight gradient as a tcgen05 GEMM over pixels with MN-major operands (csrc/wgrad_tc.cu); d_x [n,h,w,c] bf16,
+ *   d_dy [n,ho,wo,k] bf16, d_dw [k][r][s][c] f32 ACCUMULATED into; c % 64 == 0, k % 64 == 0.
+ * data gradients run through pdf_plan_* (the forward implicit-GEMM kernels on rotated weights); for strided convolutions the host
+ *   first builds pdf_dilate_bf16's zero-dilated copy of dY ([n,hd,wd,k] bf16, dY[p,q] at (offset + p*stride, offset + q*stride)). */
+int pdf_conv_wgrad_bf16(const pdf_op* op, const void* d_x, const void* d_dy, float* d_dw, pdf_stream_t stream);
+int pdf_cast_bf16(const float* d_x, void* d_y, size_t n, pdf_stream_t stream);
+int pdf_add_f32(float* d_x, const float* d_y, size_t n, pdf_stream_t stream);
+int pdf_dilate_bf16(int n, int ho, int wo, int k, int hd, int wd, int stride, int offset, const float* d_dy, void* d_out, pdf_stream_t stream);
 int pdf_colsum_f32(int M, int N, const float* d_x, float* d_out, int accumulate, pdf_stream_t stream);
 /* in place: grad *= (act > 0) * mask   (ReLU + inverted-dropout backward; mask NULL = no dropout) */
 int pdf_relu_mask_backward(float* d_grad, const float* d_act, const float* d_mask, size_t n, pdf_stream_t stream);

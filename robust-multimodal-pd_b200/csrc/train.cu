@@ -630,6 +630,34 @@ __global__ void moe_combine_train_kernel(const float* __restrict__ z, const floa
   if (threadIdx.x == 0) atomicAdd(loss_sum, ls * inv_n);
 }
 
+// f32 -> bf16 (round to nearest even): operands of the tensor-core training path
+__global__ void cast_bf16_kernel(const float* __restrict__ x, __nv_bfloat16* __restrict__ y, size_t n) {
+  for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (size_t)gridDim.x * blockDim.x) y[i] = __float2bfloat16(x[i]);
+}
+__global__ void add_kernel(float* __restrict__ x, const float* __restrict__ y, size_t n) {
+  for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (size_t)gridDim.x * blockDim.x) x[i] += y[i];
+}
+// dY [n, ho, wo, k] -> zero-dilated, zero-bordered copy [n, hd, wd, k] with dY[p, q] at (off + p*stride, off + q*stride): the input
+// of the stride-1 convolution that computes the data gradient of a strided convolution (transposed convolution)
+__global__ void dilate_bf16_kernel(const float* __restrict__ dy, __nv_bfloat16* __restrict__ out, int N, int Ho, int Wo, int K, int Hd, int Wd,
+                                   int stride, int off) {
+  const size_t total = (size_t)N * Hd * Wd * K;
+  for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (size_t)gridDim.x * blockDim.x) {
+    const int k = (int)(i % K);
+    size_t t = i / K;
+    const int x = (int)(t % Wd); t /= Wd;
+    const int y = (int)(t % Hd);
+    const int n = (int)(t / Hd);
+    const int py = y - off, px = x - off;
+    float v = 0.f;
+    if (py >= 0 && px >= 0 && py % stride == 0 && px % stride == 0) {
+      const int p = py / stride, q = px / stride;
+      if (p < Ho && q < Wo) v = dy[(((size_t)n * Ho + p) * Wo + q) * K + k];
+    }
+    out[i] = __float2bfloat16(v);
+  }
+}
+
 static inline int ew_blocks(size_t n) { return (int)std::max<size_t>(1, std::min<size_t>((n + 255) / 256, (size_t)num_sms() * 16)); }
 
 }  // namespace pdf
@@ -815,6 +843,30 @@ extern "C" int pdf_moe_combine_train(int n, int n_experts, const float* d_z, con
   PDF_REQUIRE(n > 0 && n_experts > 0 && n_experts <= PDF_MAX_MODS && d_z && d_r && d_y && d_out && d_loss && d_dz && d_dr,
               "pdf_moe_combine_train: bad arguments");
   moe_combine_train_kernel<<<ew_blocks((size_t)n), 256, 0, as_stream(stream)>>>(d_z, d_r, d_y, n, n_experts, d_out, d_loss, d_dz, d_dr);
+  PDF_CHECK_LAUNCH();
+  return PDF_OK;
+}
+
+extern "C" int pdf_cast_bf16(const float* d_x, void* d_y, size_t n, pdf_stream_t stream) {
+  PDF_REQUIRE(d_x && d_y && n > 0, "pdf_cast_bf16: bad arguments");
+  cast_bf16_kernel<<<ew_blocks(n), 256, 0, as_stream(stream)>>>(d_x, reinterpret_cast<__nv_bfloat16*>(d_y), n);
+  PDF_CHECK_LAUNCH();
+  return PDF_OK;
+}
+
+extern "C" int pdf_add_f32(float* d_x, const float* d_y, size_t n, pdf_stream_t stream) {
+  PDF_REQUIRE(d_x && d_y && n > 0, "pdf_add_f32: bad arguments");
+  add_kernel<<<ew_blocks(n), 256, 0, as_stream(stream)>>>(d_x, d_y, n);
+  PDF_CHECK_LAUNCH();
+  return PDF_OK;
+}
+
+extern "C" int pdf_dilate_bf16(int n, int ho, int wo, int k, int hd, int wd, int stride, int offset, const float* d_dy, void* d_out,
+                               pdf_stream_t stream) {
+  PDF_REQUIRE(n > 0 && ho > 0 && wo > 0 && k > 0 && hd >= offset + (ho - 1) * stride + 1 && wd >= offset + (wo - 1) * stride + 1 && stride >= 1 &&
+              offset >= 0 && d_dy && d_out, "pdf_dilate_bf16: bad arguments");
+  dilate_bf16_kernel<<<ew_blocks((size_t)n * hd * wd * k), 256, 0, as_stream(stream)>>>(d_dy, reinterpret_cast<__nv_bfloat16*>(d_out), n, ho, wo, k,
+                                                                                        hd, wd, stride, offset);
   PDF_CHECK_LAUNCH();
   return PDF_OK;
 }

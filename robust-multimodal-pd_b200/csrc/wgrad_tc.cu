@@ -1,0 +1,200 @@
+// K5 (tensor path): convolution weight gradient on the 5th-gen tensor cores.
+//
+//   dW[k][r][s][c] += sum_{m = (n,p,q)} dY[m, k] * X[n, p*stride + r - pad, q*stride + s - pad, c]          bf16 x bf16 -> f32 (TMEM)
+//
+// As a GEMM the reduction runs over PIXELS, and both operands are stored pixel-major (dY is [M, Cout], an NHWC activation is
+// [pixels, Cin]): each is the TRANSPOSE of a K-major operand.  tcgen05 takes them as they are -- "MN-major" operands (instruction
+// descriptor bits 15/16), whose canonical SWIZZLE_128B layout ((64 MN elements = 128 bytes) x (8 K rows), next 64 MN elements at
+// LBO, next 8 K rows at SBO = 1024) is exactly what a TMA tile [64 pixels x 64 channels] lands in shared memory.  So the forward
+// pass's tensor maps are reused unchanged: dY through a 2-D map, X through the im2col-mode map (padding / stride / image wrap
+// in hardware) with the tap's (s, r) offsets; no transposed copy of anything is ever made.
+//
+// One CTA = one (128-Cout block, tap group, Cin block, pixel slab): it streams its slab in k-blocks of 64 pixels through a TMA
+// ring, accumulates [128 x T*N] in TMEM (T taps of one filter row share the dY tile), and adds its partial sum into dW with
+// red.global.add.f32 at the end -- the pixel range is split over as many CTAs as fill the machine.
+//   warp 0: TMA producer | warp 1: tcgen05.mma issuer | warps 2..5: epilogue (once, after the slab)
+//
+// Replaces the weight-gradient half of `loss.backward()` through torchvision's convolutions (models/mil_attention_finetune.py:225).
+#include "tc_common.cuh"
+#include "ops.cuh"
+
+namespace pdf {
+
+constexpr int kWgPix = 64;                  // pixels (GEMM K) per k-block
+constexpr int kWgStages = 3;
+constexpr int kWgSub = kWgPix * 128;        // one [64 px x 64 ch] swizzled sub-tile = 8 KB
+
+struct WgParams {
+  int M, Cout, C, R, S, Ho, Wo, stride, pad;
+  int T;            // taps per CTA (consecutive s of one filter row, or 1)
+  int N;            // Cin columns per tap in this CTA (64 | 128 | 256)
+  int tap_groups, cin_blocks, slabs, slab_kb;   // grid decomposition; slab_kb = k-blocks per slab
+  float* dw;        // [Cout][R][S][C] f32
+};
+
+// kind::f16 instruction descriptor with BOTH operands MN-major: D = f32, A = B = bf16
+__host__ __device__ constexpr uint32_t make_idesc_mn(int n) {
+  return (1u << 4) | (1u << 7) | (1u << 10) | (1u << 15) | (1u << 16) | ((uint32_t)(n >> 3) << 17) | ((uint32_t)(kBlockM >> 4) << 24);
+}
+// MN-major SWIZZLE_128B descriptor: LBO = byte distance between 64-element blocks along M/N, SBO = 1024 (8 K rows)
+__device__ __forceinline__ uint64_t make_desc_mn(uint32_t smem_addr, uint32_t lbo_bytes) {
+  return (uint64_t)((smem_addr & 0x3ffffu) >> 4) | ((uint64_t)(lbo_bytes >> 4) << 16) | ((uint64_t)(1024 >> 4) << 32) | (1ull << 46) | (2ull << 61);
+}
+
+__global__ void __launch_bounds__(192, 1)
+wgrad_tc_kernel(const __grid_constant__ CUtensorMap tmap_dy, const __grid_constant__ CUtensorMap tmap_x, const WgParams p) {
+  extern __shared__ uint8_t smem_raw[];
+  const uint32_t raw_addr = smem_u32(smem_raw);
+  const uint32_t base = (raw_addr + 1023u) & ~1023u;
+  uint8_t* smem = smem_raw + (base - raw_addr);
+  const int nsub = p.N / 64;                                   // 64-channel sub-tiles per tap
+  const uint32_t stage_bytes = (uint32_t)(2 * kWgSub + p.T * nsub * kWgSub);
+  const uint32_t bar_full = base + kWgStages * stage_bytes;
+  const uint32_t bar_empty = bar_full + 8 * kWgStages;
+  const uint32_t bar_done = bar_empty + 8 * kWgStages;
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(smem + kWgStages * stage_bytes + 8 * (2 * kWgStages + 1));
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+
+  // unit decomposition
+  int u = blockIdx.x;
+  const int slab = u % p.slabs; u /= p.slabs;
+  const int cb = u % p.cin_blocks; u /= p.cin_blocks;
+  const int tg = u % p.tap_groups; u /= p.tap_groups;
+  const int kb0 = u;                                            // Cout block
+  const int taps_total = p.R * p.S;
+  const int tap0 = tg * p.T;
+  const int n_taps = min(p.T, taps_total - tap0);
+  const int total_kb = (p.M + kWgPix - 1) / kWgPix;
+  const int kb_lo = slab * p.slab_kb, kb_hi = min(total_kb, kb_lo + p.slab_kb);
+
+  if (threadIdx.x == 0) {
+    prefetch_tmap(&tmap_dy); prefetch_tmap(&tmap_x);
+    for (int s = 0; s < kWgStages; ++s) { mbar_init(bar_full + 8 * s, 1); mbar_init(bar_empty + 8 * s, 1); }
+    mbar_init(bar_done, 1);
+    fence_barrier_init();
+  }
+  const uint32_t tmem_cols = 512;
+  if (warp == 1) tmem_alloc(smem_u32(tmem_slot), tmem_cols);
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_slot;
+  pdl_launch_dependents();
+  pdl_wait();
+
+  if (kb_lo < kb_hi) {
+    if (warp == 0) {
+      if (elect_one()) {
+        const int hw = p.Ho * p.Wo;
+        for (int kb = kb_lo, g = 0; kb < kb_hi; ++kb, ++g) {
+          const uint32_t stage = g % kWgStages;
+          mbar_wait(bar_empty + 8 * stage, (((uint32_t)(g / kWgStages)) & 1u) ^ 1u);
+          mbar_expect_tx(bar_full + 8 * stage, (uint32_t)(2 * kWgSub + n_taps * nsub * kWgSub));
+          const uint32_t sa = base + stage * stage_bytes;
+          const int m0 = kb * kWgPix;
+          tma_load_2d(sa, &tmap_dy, bar_full + 8 * stage, kb0 * 128, m0);                 // [64 px x 64 couts] x 2 (columns past Cout: zero fill)
+          tma_load_2d(sa + kWgSub, &tmap_dy, bar_full + 8 * stage, kb0 * 128 + 64, m0);
+          const int n_img = m0 / hw;
+          const int rem = m0 - n_img * hw;
+          const int pp = rem / p.Wo, qq = rem - pp * p.Wo;
+          const int w0 = qq * p.stride - p.pad, h0 = pp * p.stride - p.pad;
+          for (int t = 0; t < n_taps; ++t) {
+            const int tap = tap0 + t;
+            const int r = tap / p.S, s = tap - r * p.S;
+            for (int j = 0; j < nsub; ++j)
+              tma_load_im2col_4d(sa + 2 * kWgSub + (t * nsub + j) * kWgSub, &tmap_x, bar_full + 8 * stage, cb * p.N + j * 64, w0, h0, n_img,
+                                 (uint16_t)s, (uint16_t)r);
+          }
+        }
+      }
+    } else if (warp == 1) {
+      if (elect_one()) {
+        const uint32_t idesc = make_idesc_mn(p.N);
+        for (int kb = kb_lo, g = 0; kb < kb_hi; ++kb, ++g) {
+          const uint32_t stage = g % kWgStages;
+          mbar_wait(bar_full + 8 * stage, ((uint32_t)(g / kWgStages)) & 1u);
+          tc_fence_after();
+          const uint32_t sa = base + stage * stage_bytes;
+#pragma unroll
+          for (int k = 0; k < kWgPix / 16; ++k) {                 // 16 pixels per instruction = 2 swizzle atoms = 2048 bytes of rows
+            const uint64_t da = make_desc_mn(sa + k * 2048, kWgSub);
+            for (int t = 0; t < n_taps; ++t) {
+              const uint64_t db = make_desc_mn(sa + 2 * kWgSub + t * nsub * kWgSub + k * 2048, kWgSub);
+              umma_f16(tmem_base + (uint32_t)(t * p.N), da, db, idesc, (g | k) != 0 ? 1u : 0u);
+            }
+          }
+          umma_commit(bar_empty + 8 * stage);
+        }
+        umma_commit(bar_done);
+      }
+    } else {
+      const int quad = warp & 3;
+      const int row = quad * 32 + lane;                          // Cout row inside the block
+      const int k = kb0 * 128 + row;
+      mbar_wait(bar_done, 0);
+      tc_fence_after();
+      for (int t = 0; t < n_taps; ++t) {
+        const int tap = tap0 + t;
+        for (int c0 = 0; c0 < p.N; c0 += 32) {
+          uint32_t v[32];
+          tmem_ld32(tmem_base + ((uint32_t)(quad * 32) << 16) + (uint32_t)(t * p.N + c0), v);
+          if (k < p.Cout) {
+            float* dst = p.dw + ((size_t)k * taps_total + tap) * p.C + cb * p.N + c0;
+#pragma unroll
+            for (int i = 0; i < 32; ++i) atomicAdd(dst + i, __uint_as_float(v[i]));
+          }
+        }
+      }
+    }
+  }
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 1) tmem_dealloc(tmem_base, tmem_cols);
+}
+
+}  // namespace pdf
+
+using namespace pdf;
+
+/* Weight gradient of a bf16 NHWC convolution on the tensor cores.  geometry from `op`; d_x [n,h,w,c] bf16, d_dy [n,ho,wo,k] bf16,
+ * d_dw [k][r][s][c] f32 (ACCUMULATED into: zero it first).  Needs c % 64 == 0 and k % 64 == 0. */
+extern "C" int pdf_conv_wgrad_bf16(const pdf_op* op, const void* d_x, const void* d_dy, float* d_dw, pdf_stream_t stream) {
+  PDF_REQUIRE(op && d_x && d_dy && d_dw, "pdf_conv_wgrad_bf16: null pointer");
+  PDF_REQUIRE(op->n > 0 && op->c % 64 == 0 && op->k % 64 == 0 && op->r == op->s && op->stride >= 1 && op->stride <= 8,
+              "pdf_conv_wgrad_bf16: needs Cin %% 64 == 0, Cout %% 64 == 0, square filter (c=%d k=%d)", op->c, op->k);
+  PDF_REQUIRE(op->ho == (op->h + 2 * op->pad - op->r) / op->stride + 1 && op->wo == (op->w + 2 * op->pad - op->s) / op->stride + 1,
+              "pdf_conv_wgrad_bf16: inconsistent output size");
+  PDF_REQUIRE((reinterpret_cast<uintptr_t>(d_x) & 15) == 0 && (reinterpret_cast<uintptr_t>(d_dy) & 15) == 0, "pdf_conv_wgrad_bf16: pointers must be 16-byte aligned");
+  if (int rc = load_driver_entry_points()) return rc;
+  const int M = op->n * op->ho * op->wo;
+  TensorMapBlob tdy, tx;
+  if (int rc = encode_2d(&tdy, d_dy, (uint64_t)M, (uint64_t)op->k, kWgPix)) return rc;
+  pdf_op xo = *op;
+  xo.d_in = d_x;
+  if (int rc = encode_im2col(&tx, xo, 0, kWgPix)) return rc;
+  WgParams p;
+  p.M = M; p.Cout = op->k; p.C = op->c; p.R = op->r; p.S = op->s; p.Ho = op->ho; p.Wo = op->wo; p.stride = op->stride; p.pad = op->pad;
+  p.N = op->c % 256 == 0 ? 256 : (op->c % 128 == 0 ? 128 : 64);
+  p.T = (op->s > 1 && p.N <= 128) ? min(op->s, 512 / p.N) : 1;         // the taps of one filter row share the dY tile (T * N <= 512 columns)
+  p.tap_groups = op->r * ((op->s + p.T - 1) / p.T);
+  if (p.T > 1 && op->s % p.T != 0) { p.T = 1; p.tap_groups = op->r * op->s; }   // (tap groups never straddle filter rows)
+  p.cin_blocks = op->c / p.N;
+  const int cout_blocks = (op->k + 127) / 128;
+  const int units = cout_blocks * p.tap_groups * p.cin_blocks;
+  const int total_kb = (M + kWgPix - 1) / kWgPix;
+  int slabs = max(1, min(total_kb, (2 * num_sms() + units - 1) / units));
+  p.slab_kb = (total_kb + slabs - 1) / slabs;
+  slabs = (total_kb + p.slab_kb - 1) / p.slab_kb;
+  p.slabs = slabs;
+  p.dw = d_dw;
+  const int smem = kWgStages * (2 * kWgSub + p.T * (p.N / 64) * kWgSub) + 8 * (2 * kWgStages + 1) + 16 + 1024;
+  static int configured = 0;
+  if (smem > configured) {
+    PDF_CHECK_CUDA(cudaFuncSetAttribute(wgrad_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
+    configured = smem;
+  }
+  PDF_CHECK_CUDA(launch_pdl(wgrad_tc_kernel, dim3(units * slabs), dim3(192), (size_t)smem, as_stream(stream),
+                            *reinterpret_cast<const CUtensorMap*>(&tdy), *reinterpret_cast<const CUtensorMap*>(&tx), p));
+  PDF_CHECK_LAUNCH();
+  return PDF_OK;
+}

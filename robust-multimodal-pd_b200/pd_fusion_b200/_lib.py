@@ -135,6 +135,10 @@ PROTOTYPES = {
     "pdf_mil_pool_train": (C.c_int, [C.POINTER(MilWeights), C.POINTER(MilTrain), C.c_int, C.c_int, _P, _P, _P, _P, _P, _P, _P, _P, _P]),
     "pdf_bce_sigmoid_train": (C.c_int, [C.c_int, _P, _P, _P, _P, _P, _P]),
     "pdf_moe_combine_train": (C.c_int, [C.c_int, C.c_int, _P, _P, _P, _P, _P, _P, _P, _P]),
+    "pdf_conv_wgrad_bf16": (C.c_int, [C.POINTER(Op), _P, _P, _P, _P]),
+    "pdf_cast_bf16": (C.c_int, [_P, _P, C.c_size_t, _P]),
+    "pdf_add_f32": (C.c_int, [_P, _P, C.c_size_t, _P]),
+    "pdf_dilate_bf16": (C.c_int, [C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, _P, _P, _P]),
     "pdf_colsum_f32": (C.c_int, [C.c_int, C.c_int, _P, _P, C.c_int, _P]),
     "pdf_relu_mask_backward": (C.c_int, [_P, _P, _P, C.c_size_t, _P]),
     "pdf_mul_f32": (C.c_int, [_P, _P, C.c_size_t, _P]),

@@ -171,7 +171,7 @@ DEFAULT_CHAIN_STAGES = (1, 2, 3)
 
 
 def lower_resnet(arch: str, n: int, S: int, bf16: bool, fused_stem: bool, chunks: List[int], in_bytes: int | None = None,
-                 dual_stages: Sequence[int] = (), chain_stages: Sequence[int] = ()):
+                 dual_stages: Sequence[int] = (), chain_stages: Sequence[int] = (), cross_stage_chain: bool = True):
     """The network as a flat, ordered list of ops over symbolic buffers.
 
     Returns (ops, extents, final_hw): ops = [(name, fields, refs, weight_name)], where refs maps the pointer fields
@@ -182,7 +182,9 @@ def lower_resnet(arch: str, n: int, S: int, bf16: bool, fused_stem: bool, chunks
     launch (bf16 path; the conv op then carries `_weight2` = the downsample's weight name and a `d_out2` reference).
 
     chain_stages: residual stages (1..3) of a Bottleneck network whose conv3 launch also computes the next block's conv1 (the op
-    carries `_weight3` and a `d_out3` reference; that conv1 is not emitted).
+    carries `_weight3` and a `d_out3` reference; that conv1 is not emitted).  With cross_stage_chain the LAST conv3 of such a stage
+    also computes the first conv1 of the following stage (stride 1 in torchvision's v1.5 Bottleneck; <= 256 output channels), into
+    buffer x<k+1>.
 
     chunks[k] = images per launch of stage k (0 = stem, 1..4 = residual stages).  The op list is depth-first: a
     stage-k chunk is preceded by the stage-(k-1) chunks that produce its input, so the big early tensors are consumed
@@ -243,12 +245,23 @@ def lower_resnet(arch: str, n: int, S: int, bf16: bool, fused_stem: bool, chunks
         add("maxpool", dict(d_in=conv_out, d_out=dst), None, kind=_lib.OP_MAXPOOL, precision=prec, n=count, h=h1, w=h1, c=64, ho=h2,
             wo=h2)
 
-    def emit_stage(k, count, src, dst):
-        """All blocks of residual stage k over `count` images: src = stage k-1 output, dst = stage k output."""
+    def cross_chain(k):
+        """conv1 of stage k+1's first block, if the last conv3 launch of stage k may compute it (chained, conv_pw.cu)."""
+        if not (bf16 and kind == "bottleneck" and k in chain_stages and 1 <= k < 4 and stage_blocks[k + 1]):
+            return None
+        nxt = stage_blocks[k + 1][0]["a"]
+        if nxt["k"] == 1 and nxt["stride"] == 1 and nxt["cout"] in (64, 128, 256) and ch[k] % 128 == 0 and cross_stage_chain:
+            return nxt
+        return None
+
+    def emit_stage(k, count, src, dst, chain_out=None, pre_chained=None):
+        """All blocks of residual stage k over `count` images: src = stage k-1 output, dst = stage k output.
+        chain_out: (ref, conv) -- the stage's last conv3 launch also computes the NEXT stage's first conv1 into ref;
+        pre_chained: that tensor, handed to the stage that consumes it."""
         x, x_h, x_c = src, hw[k - 1], ch[k - 1]
         blocks = stage_blocks[k]
         free = list(scratch)
-        chained = None
+        chained = pre_chained
         for bi, cvs in enumerate(blocks):
             last_block = bi == len(blocks) - 1
             idn, idn_slot = x, None
@@ -289,6 +302,10 @@ def lower_resnet(arch: str, n: int, S: int, bf16: bool, fused_stem: bool, chunks
                 if fuse_down is not None and cv["role"] == "a":
                     refs["d_out2"] = idn
                     extra["_weight2"] = fuse_down
+                if is_last and last_block and chain_out is not None:
+                    refs["d_out3"] = chain_out[0]
+                    extra["_weight3"] = chain_out[1]["name"]
+                    extra["k3"] = chain_out[1]["cout"]
                 if is_last and chain_next:
                     c_slot = free.pop(0)
                     refs["d_out3"] = ref(c_slot, 0, count * ho * ho * nxt["cout"] * esz)
@@ -307,17 +324,20 @@ def lower_resnet(arch: str, n: int, S: int, bf16: bool, fused_stem: bool, chunks
                 free.append(x[0])
             x, x_h, x_c = t, t_h, t_c
 
-    def emit(k, start, count, dst):
+    def emit(k, start, count, dst, chain_out=None):
         """Produce the stage-k output of images [start, start+count) at `dst`, depth-first over the earlier stages."""
         if k == 0:
             emit_stem(start, count, dst)
             return
         below = f"o{k - 1}"                       # holds the stage k-1 output of this chunk only
         per = hw[k - 1] * hw[k - 1] * ch[k - 1] * esz
+        nxt = cross_chain(k - 1)                  # this stage's first conv1, computed by the stage below (its input never re-read)
+        perc = hw[k - 1] * hw[k - 1] * nxt["cout"] * esz if nxt else 0
         for s0 in range(0, count, chunks[k - 1]):
             cnt = min(chunks[k - 1], count - s0)
-            emit(k - 1, start + s0, cnt, ref(below, s0 * per, cnt * per))
-        emit_stage(k, count, (below, 0), dst)
+            emit(k - 1, start + s0, cnt, ref(below, s0 * per, cnt * per),
+                 (ref(f"x{k}", s0 * perc, cnt * perc), nxt) if nxt else None)
+        emit_stage(k, count, (below, 0), dst, chain_out, ((f"x{k}", 0), hw[k - 1], nxt["cout"], None) if nxt else None)
 
     per4 = out_bytes(4, 1, final=True)
     for s0 in range(0, n, chunks[4]):
@@ -479,7 +499,7 @@ class ResNetEncoder:
         self.output = torch.empty((n, self.emb_dim), dtype=torch.float32, device=self.device)
         self.chunks = self._chunk_sizes(h2, esz)
         ops, extents, self.final_hw = lower_resnet(self.arch, n, S, self.bf16, self.fused_stem, self.chunks, in_bytes, self.dual_stages,
-                                                     self.chain_stages)
+                                                     self.chain_stages, os.environ.get("PDFUSION_B200_XCHAIN", "1") != "0")
         weights = {cv["name"]: self._conv_weights(sd, cv) for cv in conv_list(self.arch)}
 
         self.buffers = {name: torch.empty(nbytes, dtype=torch.uint8, device=self.device) for name, nbytes in extents.items()

@@ -282,9 +282,17 @@ def test_lowering_bf16_buffers_are_written_before_read():
     from pd_fusion_b200.backbone import lower_resnet
     for arch in ("resnet18", "resnet50"):
         for fused in (True, False):
-            for dual in ((), (2, 3, 4)):
+            for dual, chain in (((), ()), ((2, 3, 4), ()), ((), (1, 2, 3))):
                 n, S = 7, 64
-                ops, extents, _ = lower_resnet(arch, n, S, bf16=True, fused_stem=fused, chunks=[2, 2, 4, 4, 7], dual_stages=dual)
+                ops, extents, _ = lower_resnet(arch, n, S, bf16=True, fused_stem=fused, chunks=[2, 2, 4, 4, 7], dual_stages=dual,
+                                               chain_stages=chain)
+                chained = {o[1]["_weight3"] for o in ops if "_weight3" in o[1]}
+                if arch == "resnet50" and chain:         # conv1 of every block of stages 1..3 but the very first rides on the conv3 before
+                    emitted = {o[0] for o in ops if o[0].endswith(".conv1")}          # it, ACROSS the stage boundaries 1->2 and 2->3 too
+                    assert emitted == {"layer1.0.conv1", "layer4.0.conv1", "layer4.1.conv1", "layer4.2.conv1"}
+                    assert len(chained) == 12 and {"layer2.0.conv1", "layer3.0.conv1"} <= chained
+                else:
+                    assert not chained
                 n_down = sum("downsample" in o[0] for o in ops)
                 n_dual = sum("_weight2" in o[1] for o in ops)
                 if arch == "resnet18" and dual:          # BasicBlock: the three downsample convs ride inside conv1
@@ -311,6 +319,11 @@ def test_lowering_bf16_buffers_are_written_before_read():
                         nbytes = f["n"] * f["ho"] * f["wo"] * f["k"] * (4 if f.get("out_f32") else esz)
                     assert (ob, oo) != refs["d_in"] and oo + nbytes <= extents[ob]
                     written[ob][oo:oo + nbytes] = True
+                    if "d_out3" in refs:                 # chained conv1 of the next block / next stage
+                        b3, o3 = refs["d_out3"]
+                        n3 = f["n"] * f["ho"] * f["wo"] * f["k3"] * esz
+                        assert (b3, o3) not in (refs["d_in"], refs["d_out"], refs["d_residual"]) and o3 + n3 <= extents[b3]
+                        written[b3][o3:o3 + n3] = True
                     if "d_out2" in refs:
                         b2, o2 = refs["d_out2"]
                         n2 = f["n"] * f["ho"] * f["wo"] * f["k"] * esz

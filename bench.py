@@ -279,6 +279,7 @@ def run_c5(args, wl):
               "max_grad_norm": 1.0, "train_aug": False, "missing_prob": 0.5}
     torch.manual_seed(1234)
     model = MilAttentionFineTuneModel(params)
+    precision = os.environ.get("PD_FUSION_B200_TRAIN_PRECISION", "bf16")      # training.ResNetTrainer reads the same variable
     rng = np.random.default_rng(100 + rank)
     host_bags = [rng.random((L, TARGET[0], TARGET[1])).astype(np.float32) for _ in range(bags_per_step)]
     dev_bags = [torch.from_numpy(b).to(dev) for b in host_bags]
@@ -318,8 +319,8 @@ def run_c5(args, wl):
     tf = flops / (ms / steps / 1e3) / 1e12
     line = {"metric": "mri_subjects_per_sec_resnet2d_mil_finetune_fwd_bwd", "value": ws * bags_per_step * steps / (ms / 1e3), "unit": UNIT,
             "n_gpus": ws, "steps": steps, "warmup": max(args.warmup, 3), "ms_per_step": ms / steps, "higher_is_better": True, "scaling": "weak",
-            "vs_baseline": None, "dtype": "f32", "data": "synthetic",
-            "config": {"workload": wl["name"], "backbone": wl["arch"], "slices": L, "bags_per_step_per_gpu": bags_per_step, "slice_batch_size": 16,
+            "vs_baseline": None, "dtype": "bf16" if precision == "bf16" else "f32", "data": "synthetic",
+            "config": {"workload": wl["name"], "backbone": wl["arch"], "slices": L, "train_precision": precision, "bags_per_step_per_gpu": bags_per_step, "slice_batch_size": 16,
                        "input_size": INPUT_SIZE, "loss": "focal(2.0, 0.25)", "optimizer": "Adam 1e-4 / 3e-4, wd 1e-3, clip 1.0",
                        "l2": "activations of one step (~25 GB) exceed L2 many times over",
                        "parallelism": f"bags sharded x{ws}, one gradient all-reduce per flat buffer" if ws > 1 else "1 GPU"},
@@ -327,10 +328,13 @@ def run_c5(args, wl):
             "e2e": {"value": ws * bags_per_step * steps / (ms_e2e / 1e3), "unit": UNIT, "h2d_bytes_per_step": int(sum(b.nbytes for b in host_bags)),
                     "d2h_bytes_per_step": 4, "ms_per_step": ms_e2e / steps},
             "gpu_launches": int(launches),
-            "roofline": {"bound": "tensor", "kernel": "conv_f32 / conv_dgrad_f32 / conv_wgrad_f32 (CUDA-core FFMA implicit GEMMs: the FP32 parity "
-                                                      "path of training; no tcgen05 backward yet)",
+            "roofline": {"bound": "tensor",
+                         "kernel": ("whole training step: tcgen05 forward / data-gradient implicit GEMMs (conv_tc, conv_tc2) + wgrad_tc_kernel on bf16 "
+                                    "operands, f32 BatchNorm / pooling / head / Adam kernels between them" if precision == "bf16" else
+                                    "conv_f32 / conv_dgrad_f32 / conv_wgrad_f32 (CUDA-core FFMA implicit GEMMs: the FP32 parity path of training)"),
                          "achieved": tf, "peak": peaks["tf"], "unit": "TFLOP/s", "frac": tf / peaks["tf"], "traffic": None,
-                         "flops_per_step": flops, "peak_source": peaks["src"] + " burst bf16 tensor peak (the kernels run on the FP32 CUDA cores)"}}
+                         "flops_per_step": flops, "peak_source": peaks["src"] + " burst bf16 tensor peak; the numerator is the step's convolution "
+                                                                               "FLOPs over the WHOLE step time"}}
     if rank == 0:
         print(json.dumps(line), flush=True)
     if ws > 1:

@@ -259,18 +259,21 @@ int pdf_gemm_f32(int M, int N, int K, const float* A, long a_rs, long a_cs, cons
  * dgrad d_dx [n,h,w,c] (+)= conv^T(d_dy [n,ho,wo,k], w);  wgrad d_dw [R][S][C][K] += x^T * dy (accumulates: zero it first). */
 int pdf_conv_dgrad_f32(const pdf_op* op, const float* d_dy, const float* d_weight, float* d_dx, int accumulate, pdf_stream_t stream);
 int pdf_conv_wgrad_f32(const pdf_op* op, const float* d_x, const float* d_dy, float* d_dw, pdf_stream_t stream);
-/* train-mode BatchNorm over row groups of the [M, C] activation matrix: group g = rows [d_goff[g], d_goff[g+1]) (one 16-slice chunk of
- * one bag).  forward: y = (x - mean_g) * invstd_g * gamma + beta (+ residual) (ReLU); saves mean, invstd (biased variance, eps inside)
- * and the unbiased variance (for the running statistics) per (group, channel). */
-int pdf_bn_train_forward(int n_groups, const int32_t* d_goff, int C, const float* d_x, const float* d_gamma, const float* d_beta, float eps,
-                         const float* d_residual, int relu, float* d_y, float* d_mean, float* d_invstd, float* d_var_unbiased,
-                         pdf_stream_t stream);
+/* train-mode BatchNorm over row groups of the [M, C] activation matrix (C % 4 == 0): group g = rows [d_goff[g], d_goff[g+1]) (one
+ * 16-slice chunk of one bag); max_group_rows = the longest group (sizes the reduction grid).  forward: y = (x - mean_g) * invstd_g * gamma
+ * + beta (+ residual) (ReLU); saves mean, invstd (biased variance, eps inside) and the unbiased variance (for the running statistics)
+ * per (group, channel); d_y_bf16 (or NULL): a bf16 copy of y, the operand of the next tensor-core convolution.
+ * d_scratch: 2 * n_groups * C doubles (float64 partial sums). */
+int pdf_bn_train_forward(int n_groups, const int32_t* d_goff, int max_group_rows, int C, const float* d_x, const float* d_gamma,
+                         const float* d_beta, float eps, const float* d_residual, int relu, float* d_y, void* d_y_bf16, float* d_mean,
+                         float* d_invstd, float* d_var_unbiased, double* d_scratch, pdf_stream_t stream);
 /* backward of the same: g = d_dy * (d_y > 0 if relu); d_dgamma += sum g*xhat, d_dbeta += sum g (accumulate over calls: zero first);
- * d_dx = gamma*invstd*(g - mean_g(g) - xhat*mean_g(g*xhat)); d_dres (or NULL) (+)= g, the gradient of the residual branch.
- * d_scratch: 2 * n_groups * C floats. */
-int pdf_bn_train_backward(int n_groups, const int32_t* d_goff, int C, const float* d_dy, const float* d_y, const float* d_x,
-                          const float* d_gamma, const float* d_mean, const float* d_invstd, int relu, float* d_scratch, float* d_dx,
-                          float* d_dres, int dres_accumulate, float* d_dgamma, float* d_dbeta, pdf_stream_t stream);
+ * d_dx = gamma*invstd*(g - mean_g(g) - xhat*mean_g(g*xhat)), d_dx_bf16 (or NULL) its bf16 copy; d_dres (or NULL) (+)= g, the gradient
+ * of the residual branch.  d_scratch: 3 * n_groups * C doubles. */
+int pdf_bn_train_backward(int n_groups, const int32_t* d_goff, int max_group_rows, int C, const float* d_dy, const float* d_y,
+                          const float* d_x, const float* d_gamma, const float* d_mean, const float* d_invstd, int relu, double* d_scratch,
+                          float* d_dx, void* d_dx_bf16, float* d_dres, int dres_accumulate, float* d_dgamma, float* d_dbeta,
+                          pdf_stream_t stream);
 /* running = (1-momentum)*running + momentum*batch, group after group (the reference forwards its chunks one at a time) */
 int pdf_bn_update_running(int n_groups, int C, const float* d_mean, const float* d_var_unbiased, float momentum, float* d_running_mean,
                           float* d_running_var, pdf_stream_t stream);

@@ -225,70 +225,115 @@ conv_wgrad_f32_kernel(const float* __restrict__ x, const float* __restrict__ dy,
 // ------------------------------------------------------------------------------------------------------
 // BatchNorm, train mode.  x is the [M, C] matrix of one layer's conv output (rows = pixels in NHWC order); group g covers rows
 // [goff[g], goff[g+1]) -- one 16-slice chunk of one bag, the unit the reference pushes through the backbone at a time.
-// stats: mean and biased variance per (group, channel); two passes over the group's rows (mean first), f32.
+//
+// Reductions: grid (C/32, groups, row slabs) -- a (group, channel-block) pair alone would put 32 blocks on the machine for the
+// 64-channel layers.  Every block sums its slab in float64 (these per-(group, channel) sums feed (x - mean) * invstd, whose
+// cancellation amplifies every ulp of the statistics into the gradients, and Adam's sign-like first steps amplify THAT) and adds
+// its partial sums into a float64 scratch with atomicAdd(double); a tiny finalize kernel turns them into mean / invstd.
+// With float64 sums the one-pass form var = E[x^2] - mean^2 is exact to ~1e-16 * mean^2 / var.
+constexpr int kBnRowsPerBlock = 2048;     // rows of a slab (8 row lanes x 256 iterations)
+
 __global__ void __launch_bounds__(256)
-bn_stats_kernel(const float* __restrict__ x, const int* __restrict__ goff, int C, float eps, float* __restrict__ mean,
-                float* __restrict__ invstd, float* __restrict__ var_unbiased) {
-  // float64 accumulators: these per-(group, channel) sums feed (x - mean) * invstd, whose cancellation amplifies every ulp of the
-  // statistics into the gradients (and Adam's sign-like first steps amplify THAT); the reductions are a negligible share of the work
-  __shared__ double red[8][33];
+bn_stats_kernel(const float* __restrict__ x, const int* __restrict__ goff, int C, double* __restrict__ acc) {
+  __shared__ double red0[8][33], red1[8][33];
   const int g = blockIdx.y;
   const int c = blockIdx.x * 32 + (threadIdx.x & 31);
   const int ry = threadIdx.x >> 5;
-  const int r0 = goff[g], r1 = goff[g + 1];
-  const int rows = r1 - r0;
-  double s = 0.0;
-  if (c < C) for (int r = r0 + ry; r < r1; r += 8) s += (double)x[(size_t)r * C + c];
-  red[ry][threadIdx.x & 31] = s;
-  __syncthreads();
-  double mu = 0.0;
-  for (int i = 0; i < 8; ++i) mu += red[i][threadIdx.x & 31];
-  mu /= (double)max(rows, 1);
-  __syncthreads();
-  double q = 0.0;
-  if (c < C) for (int r = r0 + ry; r < r1; r += 8) { const double d = (double)x[(size_t)r * C + c] - mu; q += d * d; }
-  red[ry][threadIdx.x & 31] = q;
+  const int r0 = goff[g] + blockIdx.z * kBnRowsPerBlock;
+  const int r1 = min(goff[g + 1], r0 + kBnRowsPerBlock);
+  if (r0 >= r1) return;
+  double s = 0.0, q = 0.0;
+  if (c < C) {
+    int r = r0 + ry;
+    for (; r + 24 < r1; r += 32) {                      // four independent loads in flight per thread
+      const float a0 = x[(size_t)r * C + c], a1 = x[(size_t)(r + 8) * C + c], a2 = x[(size_t)(r + 16) * C + c], a3 = x[(size_t)(r + 24) * C + c];
+      s += ((double)a0 + (double)a1) + ((double)a2 + (double)a3);
+      q += ((double)a0 * (double)a0 + (double)a1 * (double)a1) + ((double)a2 * (double)a2 + (double)a3 * (double)a3);
+    }
+    for (; r < r1; r += 8) { const double a = (double)x[(size_t)r * C + c]; s += a; q += a * a; }
+  }
+  red0[ry][threadIdx.x & 31] = s; red1[ry][threadIdx.x & 31] = q;
   __syncthreads();
   if (ry == 0 && c < C) {
-    double v = 0.0;
-    for (int i = 0; i < 8; ++i) v += red[i][threadIdx.x & 31];
-    const double var = v / (double)max(rows, 1);
-    mean[(size_t)g * C + c] = (float)mu;
-    invstd[(size_t)g * C + c] = (float)(1.0 / sqrt(var + (double)eps));
-    var_unbiased[(size_t)g * C + c] = (float)(rows > 1 ? v / (double)(rows - 1) : var);
+    double a = 0.0, b = 0.0;
+    for (int i = 0; i < 8; ++i) { a += red0[i][threadIdx.x & 31]; b += red1[i][threadIdx.x & 31]; }
+    atomicAdd(acc + ((size_t)g * C + c) * 2, a);
+    atomicAdd(acc + ((size_t)g * C + c) * 2 + 1, b);
   }
 }
 
-// y = (x - mean) * invstd * gamma + beta (+ residual) (ReLU)
+__global__ void bn_stats_finalize_kernel(const double* __restrict__ acc, const int* __restrict__ goff, int G, int C, float eps,
+                                         float* __restrict__ mean, float* __restrict__ invstd, float* __restrict__ var_unbiased) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= G * C) return;
+  const int g = i / C;
+  const int rows = goff[g + 1] - goff[g];
+  const double m = (double)max(rows, 1);
+  const double mu = acc[(size_t)i * 2] / m;
+  const double v = fmax(acc[(size_t)i * 2 + 1] - m * mu * mu, 0.0);   // sum of squared deviations
+  const double var = v / m;
+  mean[i] = (float)mu;
+  invstd[i] = (float)(1.0 / sqrt(var + (double)eps));
+  var_unbiased[i] = (float)(rows > 1 ? v / (double)(rows - 1) : var);
+}
+
+__device__ __forceinline__ void store_bf16x4(__nv_bfloat16* p, float4 v) {
+  __nv_bfloat162 lo = __floats2bfloat162_rn(v.x, v.y), hi = __floats2bfloat162_rn(v.z, v.w);
+  uint2 o;
+  o.x = *reinterpret_cast<uint32_t*>(&lo); o.y = *reinterpret_cast<uint32_t*>(&hi);
+  *reinterpret_cast<uint2*>(p) = o;
+}
+
+// y = (x - mean) * invstd * gamma + beta (+ residual) (ReLU); four channels per thread (C % 4 == 0); optional bf16 copy of y (the
+// operand of the next tensor-core convolution)
 __global__ void __launch_bounds__(256)
 bn_apply_kernel(const float* __restrict__ x, const int* __restrict__ goff, int C, const float* __restrict__ mean,
                 const float* __restrict__ invstd, const float* __restrict__ gamma, const float* __restrict__ beta,
-                const float* __restrict__ residual, int relu, float* __restrict__ y) {
+                const float* __restrict__ residual, int relu, float* __restrict__ y, __nv_bfloat16* __restrict__ y16) {
   const int g = blockIdx.y;
-  const size_t lo = (size_t)goff[g] * C, hi = (size_t)goff[g + 1] * C;
+  const size_t lo = (size_t)goff[g] * C / 4, hi = (size_t)goff[g + 1] * C / 4;
+  const int C4 = C / 4;
+  const float4* mu4 = reinterpret_cast<const float4*>(mean + (size_t)g * C);
+  const float4* is4 = reinterpret_cast<const float4*>(invstd + (size_t)g * C);
   for (size_t i = lo + (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < hi; i += (size_t)gridDim.x * blockDim.x) {
-    const int c = (int)(i % C);
-    float v = (x[i] - mean[(size_t)g * C + c]) * invstd[(size_t)g * C + c] * gamma[c] + beta[c];
-    if (residual) v += residual[i];
-    if (relu) v = fmaxf(v, 0.f);
-    y[i] = v;
+    const int c4 = (int)(i % C4);
+    const float4 xv = reinterpret_cast<const float4*>(x)[i];
+    const float4 mu = mu4[c4], is = is4[c4];
+    const float4 ga = reinterpret_cast<const float4*>(gamma)[c4], be = reinterpret_cast<const float4*>(beta)[c4];
+    float4 v;
+    v.x = (xv.x - mu.x) * is.x * ga.x + be.x; v.y = (xv.y - mu.y) * is.y * ga.y + be.y;
+    v.z = (xv.z - mu.z) * is.z * ga.z + be.z; v.w = (xv.w - mu.w) * is.w * ga.w + be.w;
+    if (residual) { const float4 r = reinterpret_cast<const float4*>(residual)[i]; v.x += r.x; v.y += r.y; v.z += r.z; v.w += r.w; }
+    if (relu) { v.x = fmaxf(v.x, 0.f); v.y = fmaxf(v.y, 0.f); v.z = fmaxf(v.z, 0.f); v.w = fmaxf(v.w, 0.f); }
+    reinterpret_cast<float4*>(y)[i] = v;
+    if (y16) store_bf16x4(y16 + i * 4, v);
   }
 }
 
-// backward, pass 1: per (group, channel) sums of g = dy * relu'(y) and g * xhat; d_gamma / d_beta accumulate over groups
+// backward, pass 1: per (group, channel) sums of g = dy * relu'(y) and g * xhat (same grid / float64 scheme as bn_stats_kernel)
 __global__ void __launch_bounds__(256)
 bn_bwd_reduce_kernel(const float* __restrict__ dy, const float* __restrict__ y, const float* __restrict__ x, const int* __restrict__ goff,
-                     int C, const float* __restrict__ mean, const float* __restrict__ invstd, int relu, float* __restrict__ sum_g,
-                     float* __restrict__ sum_gx, float* __restrict__ dgamma, float* __restrict__ dbeta) {
-  __shared__ double red0[8][33], red1[8][33];        // float64 accumulators, as in bn_stats_kernel
+                     int C, const float* __restrict__ mean, const float* __restrict__ invstd, int relu, double* __restrict__ acc) {
+  __shared__ double red0[8][33], red1[8][33];
   const int g = blockIdx.y;
   const int c = blockIdx.x * 32 + (threadIdx.x & 31);
   const int ry = threadIdx.x >> 5;
-  const int r0 = goff[g], r1 = goff[g + 1];
+  const int r0 = goff[g] + blockIdx.z * kBnRowsPerBlock;
+  const int r1 = min(goff[g + 1], r0 + kBnRowsPerBlock);
+  if (r0 >= r1) return;
   double s0 = 0.0, s1 = 0.0;
   if (c < C) {
     const float mu = mean[(size_t)g * C + c], is = invstd[(size_t)g * C + c];
-    for (int r = r0 + ry; r < r1; r += 8) {
+    int r = r0 + ry;
+    for (; r + 8 < r1; r += 16) {
+      const size_t i0 = (size_t)r * C + c, i1 = (size_t)(r + 8) * C + c;
+      float g0 = dy[i0], g1 = dy[i1];
+      const float x0 = x[i0], x1 = x[i1];
+      if (relu) { const float y0 = y[i0], y1 = y[i1]; if (!(y0 > 0.f)) g0 = 0.f; if (!(y1 > 0.f)) g1 = 0.f; }
+      s0 += (double)g0 + (double)g1;
+      s1 += (double)g0 * (double)((x0 - mu) * is) + (double)g1 * (double)((x1 - mu) * is);
+    }
+    for (; r < r1; r += 8) {
       const size_t i = (size_t)r * C + c;
       float gr = dy[i];
       if (relu && !(y[i] > 0.f)) gr = 0.f;
@@ -301,30 +346,66 @@ bn_bwd_reduce_kernel(const float* __restrict__ dy, const float* __restrict__ y, 
   if (ry == 0 && c < C) {
     double a = 0.0, b = 0.0;
     for (int i = 0; i < 8; ++i) { a += red0[i][threadIdx.x & 31]; b += red1[i][threadIdx.x & 31]; }
-    sum_g[(size_t)g * C + c] = (float)a;
-    sum_gx[(size_t)g * C + c] = (float)b;
-    atomicAdd(dbeta + c, (float)a);
-    atomicAdd(dgamma + c, (float)b);
+    atomicAdd(acc + ((size_t)g * C + c) * 2, a);
+    atomicAdd(acc + ((size_t)g * C + c) * 2 + 1, b);
   }
 }
 
-// backward, pass 2: dx = gamma * invstd * (g - sum_g/m - xhat * sum_gx/m);  dres (+)= g  (the residual branch sees the masked gradient)
+// d_gamma / d_beta accumulate over the groups (and over calls); sums[g][c] = (sum g, sum g*xhat) as floats for the apply pass
+__global__ void bn_bwd_finalize_kernel(const double* __restrict__ acc, int G, int C, float* __restrict__ sums, float* __restrict__ dgamma,
+                                       float* __restrict__ dbeta) {
+  const int c = blockIdx.x * blockDim.x + threadIdx.x;
+  if (c >= C) return;
+  double a = 0.0, b = 0.0;
+  for (int g = 0; g < G; ++g) {
+    const double s0 = acc[((size_t)g * C + c) * 2], s1 = acc[((size_t)g * C + c) * 2 + 1];
+    sums[(size_t)g * C + c] = (float)s0;
+    sums[(size_t)(G + g) * C + c] = (float)s1;
+    a += s0; b += s1;
+  }
+  dbeta[c] += (float)a;
+  dgamma[c] += (float)b;
+}
+
+// backward, pass 2: dx = gamma * invstd * (g - sum_g/m - xhat * sum_gx/m);  dres (+)= g  (the residual branch sees the masked gradient);
+// optional bf16 copy of dx (the operand of the tensor-core dgrad / wgrad)
 __global__ void __launch_bounds__(256)
 bn_bwd_apply_kernel(const float* __restrict__ dy, const float* __restrict__ y, const float* __restrict__ x, const int* __restrict__ goff,
                     int C, const float* __restrict__ mean, const float* __restrict__ invstd, const float* __restrict__ gamma, int relu,
-                    const float* __restrict__ sum_g, const float* __restrict__ sum_gx, float* __restrict__ dx, float* __restrict__ dres,
-                    int dres_accumulate) {
+                    const float* __restrict__ sum_g, const float* __restrict__ sum_gx, float* __restrict__ dx, __nv_bfloat16* __restrict__ dx16,
+                    float* __restrict__ dres, int dres_accumulate) {
   const int g = blockIdx.y;
   const float inv_m = 1.0f / (float)max(goff[g + 1] - goff[g], 1);
-  const size_t lo = (size_t)goff[g] * C, hi = (size_t)goff[g + 1] * C;
+  const size_t lo = (size_t)goff[g] * C / 4, hi = (size_t)goff[g + 1] * C / 4;
+  const int C4 = C / 4;
+  const float4* mu4 = reinterpret_cast<const float4*>(mean + (size_t)g * C);
+  const float4* is4 = reinterpret_cast<const float4*>(invstd + (size_t)g * C);
+  const float4* sg4 = reinterpret_cast<const float4*>(sum_g + (size_t)g * C);
+  const float4* sx4 = reinterpret_cast<const float4*>(sum_gx + (size_t)g * C);
   for (size_t i = lo + (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < hi; i += (size_t)gridDim.x * blockDim.x) {
-    const int c = (int)(i % C);
-    float gr = dy[i];
-    if (relu && !(y[i] > 0.f)) gr = 0.f;
-    const float is = invstd[(size_t)g * C + c];
-    const float xh = (x[i] - mean[(size_t)g * C + c]) * is;
-    dx[i] = gamma[c] * is * (gr - sum_g[(size_t)g * C + c] * inv_m - xh * sum_gx[(size_t)g * C + c] * inv_m);
-    if (dres) dres[i] = dres_accumulate ? dres[i] + gr : gr;
+    const int c4 = (int)(i % C4);
+    float4 gr = reinterpret_cast<const float4*>(dy)[i];
+    if (relu) {
+      const float4 yv = reinterpret_cast<const float4*>(y)[i];
+      if (!(yv.x > 0.f)) gr.x = 0.f;
+      if (!(yv.y > 0.f)) gr.y = 0.f;
+      if (!(yv.z > 0.f)) gr.z = 0.f;
+      if (!(yv.w > 0.f)) gr.w = 0.f;
+    }
+    const float4 xv = reinterpret_cast<const float4*>(x)[i];
+    const float4 mu = mu4[c4], is = is4[c4], ga = reinterpret_cast<const float4*>(gamma)[c4], sg = sg4[c4], sx = sx4[c4];
+    float4 o;
+    o.x = ga.x * is.x * (gr.x - sg.x * inv_m - (xv.x - mu.x) * is.x * sx.x * inv_m);
+    o.y = ga.y * is.y * (gr.y - sg.y * inv_m - (xv.y - mu.y) * is.y * sx.y * inv_m);
+    o.z = ga.z * is.z * (gr.z - sg.z * inv_m - (xv.z - mu.z) * is.z * sx.z * inv_m);
+    o.w = ga.w * is.w * (gr.w - sg.w * inv_m - (xv.w - mu.w) * is.w * sx.w * inv_m);
+    reinterpret_cast<float4*>(dx)[i] = o;
+    if (dx16) store_bf16x4(dx16 + i * 4, o);
+    if (dres) {
+      float4* dr = reinterpret_cast<float4*>(dres) + i;
+      if (dres_accumulate) { const float4 d = *dr; gr.x += d.x; gr.y += d.y; gr.z += d.z; gr.w += d.w; }
+      *dr = gr;
+    }
   }
 }
 
@@ -710,33 +791,42 @@ extern "C" int pdf_conv_wgrad_f32(const pdf_op* op, const float* d_x, const floa
   return PDF_OK;
 }
 
-extern "C" int pdf_bn_train_forward(int n_groups, const int32_t* d_goff, int C, const float* d_x, const float* d_gamma, const float* d_beta,
-                                    float eps, const float* d_residual, int relu, float* d_y, float* d_mean, float* d_invstd,
-                                    float* d_var_unbiased, pdf_stream_t stream) {
-  PDF_REQUIRE(n_groups > 0 && d_goff && C > 0 && d_x && d_gamma && d_beta && d_y && d_mean && d_invstd && d_var_unbiased,
-              "pdf_bn_train_forward: bad arguments");
+extern "C" int pdf_bn_train_forward(int n_groups, const int32_t* d_goff, int max_group_rows, int C, const float* d_x, const float* d_gamma,
+                                    const float* d_beta, float eps, const float* d_residual, int relu, float* d_y, void* d_y_bf16, float* d_mean,
+                                    float* d_invstd, float* d_var_unbiased, double* d_scratch, pdf_stream_t stream) {
+  PDF_REQUIRE(n_groups > 0 && d_goff && max_group_rows > 0 && C > 0 && C % 4 == 0 && d_x && d_gamma && d_beta && d_y && d_mean && d_invstd &&
+              d_var_unbiased && d_scratch, "pdf_bn_train_forward: bad arguments (C %% 4 == 0, scratch of 2*groups*C doubles)");
   cudaStream_t s = as_stream(stream);
-  bn_stats_kernel<<<dim3(ceil_div(C, 32), n_groups), 256, 0, s>>>(d_x, d_goff, C, eps, d_mean, d_invstd, d_var_unbiased);
+  PDF_CHECK_CUDA(cudaMemsetAsync(d_scratch, 0, (size_t)2 * n_groups * C * sizeof(double), s));
+  bn_stats_kernel<<<dim3(ceil_div(C, 32), n_groups, ceil_div(max_group_rows, kBnRowsPerBlock)), 256, 0, s>>>(d_x, d_goff, C, d_scratch);
+  PDF_CHECK_LAUNCH();
+  bn_stats_finalize_kernel<<<ceil_div(n_groups * C, 256), 256, 0, s>>>(d_scratch, d_goff, n_groups, C, eps, d_mean, d_invstd, d_var_unbiased);
   PDF_CHECK_LAUNCH();
   bn_apply_kernel<<<dim3(std::max(1, 8 * num_sms() / n_groups), n_groups), 256, 0, s>>>(d_x, d_goff, C, d_mean, d_invstd, d_gamma, d_beta,
-                                                                                       d_residual, relu, d_y);
+                                                                                       d_residual, relu, d_y,
+                                                                                       reinterpret_cast<__nv_bfloat16*>(d_y_bf16));
   PDF_CHECK_LAUNCH();
   return PDF_OK;
 }
 
-extern "C" int pdf_bn_train_backward(int n_groups, const int32_t* d_goff, int C, const float* d_dy, const float* d_y, const float* d_x,
-                                     const float* d_gamma, const float* d_mean, const float* d_invstd, int relu, float* d_scratch,
-                                     float* d_dx, float* d_dres, int dres_accumulate, float* d_dgamma, float* d_dbeta, pdf_stream_t stream) {
-  PDF_REQUIRE(n_groups > 0 && d_goff && C > 0 && d_dy && d_y && d_x && d_gamma && d_mean && d_invstd && d_scratch && d_dx && d_dgamma && d_dbeta,
-              "pdf_bn_train_backward: bad arguments");
+extern "C" int pdf_bn_train_backward(int n_groups, const int32_t* d_goff, int max_group_rows, int C, const float* d_dy, const float* d_y,
+                                     const float* d_x, const float* d_gamma, const float* d_mean, const float* d_invstd, int relu,
+                                     double* d_scratch, float* d_dx, void* d_dx_bf16, float* d_dres, int dres_accumulate, float* d_dgamma,
+                                     float* d_dbeta, pdf_stream_t stream) {
+  PDF_REQUIRE(n_groups > 0 && d_goff && max_group_rows > 0 && C > 0 && C % 4 == 0 && d_dy && d_y && d_x && d_gamma && d_mean && d_invstd &&
+              d_scratch && d_dx && d_dgamma && d_dbeta, "pdf_bn_train_backward: bad arguments (C %% 4 == 0, scratch of 3*groups*C doubles)");
   cudaStream_t s = as_stream(stream);
-  float* sum_g = d_scratch;                           // [2][G][C]
-  float* sum_gx = d_scratch + (size_t)n_groups * C;
-  bn_bwd_reduce_kernel<<<dim3(ceil_div(C, 32), n_groups), 256, 0, s>>>(d_dy, d_y, d_x, d_goff, C, d_mean, d_invstd, relu, sum_g, sum_gx,
-                                                                      d_dgamma, d_dbeta);
+  double* acc = d_scratch;                                                // [G][C][2] float64 partial sums
+  float* sums = reinterpret_cast<float*>(d_scratch + (size_t)2 * n_groups * C);   // [2][G][C] f32: sum g | sum g*xhat
+  PDF_CHECK_CUDA(cudaMemsetAsync(acc, 0, (size_t)2 * n_groups * C * sizeof(double), s));
+  bn_bwd_reduce_kernel<<<dim3(ceil_div(C, 32), n_groups, ceil_div(max_group_rows, kBnRowsPerBlock)), 256, 0, s>>>(d_dy, d_y, d_x, d_goff, C, d_mean,
+                                                                                                             d_invstd, relu, acc);
   PDF_CHECK_LAUNCH();
-  bn_bwd_apply_kernel<<<dim3(std::max(1, 8 * num_sms() / n_groups), n_groups), 256, 0, s>>>(d_dy, d_y, d_x, d_goff, C, d_mean, d_invstd, d_gamma,
-                                                                                           relu, sum_g, sum_gx, d_dx, d_dres, dres_accumulate);
+  bn_bwd_finalize_kernel<<<ceil_div(C, 128), 128, 0, s>>>(acc, n_groups, C, sums, d_dgamma, d_dbeta);
+  PDF_CHECK_LAUNCH();
+  bn_bwd_apply_kernel<<<dim3(std::max(1, 8 * num_sms() / n_groups), n_groups), 256, 0, s>>>(
+      d_dy, d_y, d_x, d_goff, C, d_mean, d_invstd, d_gamma, relu, sums, sums + (size_t)n_groups * C, d_dx,
+      reinterpret_cast<__nv_bfloat16*>(d_dx_bf16), d_dres, dres_accumulate);
   PDF_CHECK_LAUNCH();
   return PDF_OK;
 }

@@ -127,8 +127,8 @@ PROTOTYPES = {
     "pdf_gemm_f32": (C.c_int, [C.c_int, C.c_int, C.c_int, _P, C.c_long, C.c_long, _P, C.c_long, C.c_long, _P, C.c_long, _P, C.c_int, C.c_int, _P]),
     "pdf_conv_dgrad_f32": (C.c_int, [C.POINTER(Op), _P, _P, _P, C.c_int, _P]),
     "pdf_conv_wgrad_f32": (C.c_int, [C.POINTER(Op), _P, _P, _P, _P]),
-    "pdf_bn_train_forward": (C.c_int, [C.c_int, _P, C.c_int, _P, _P, _P, C.c_float, _P, C.c_int, _P, _P, _P, _P, _P]),
-    "pdf_bn_train_backward": (C.c_int, [C.c_int, _P, C.c_int, _P, _P, _P, _P, _P, _P, C.c_int, _P, _P, _P, C.c_int, _P, _P, _P]),
+    "pdf_bn_train_forward": (C.c_int, [C.c_int, _P, C.c_int, C.c_int, _P, _P, _P, C.c_float, _P, C.c_int, _P, _P, _P, _P, _P, _P, _P]),
+    "pdf_bn_train_backward": (C.c_int, [C.c_int, _P, C.c_int, C.c_int, _P, _P, _P, _P, _P, _P, C.c_int, _P, _P, _P, _P, C.c_int, _P, _P, _P]),
     "pdf_bn_update_running": (C.c_int, [C.c_int, C.c_int, _P, _P, C.c_float, _P, _P, _P]),
     "pdf_maxpool_backward_f32": (C.c_int, [C.c_int, C.c_int, C.c_int, C.c_int, _P, _P, _P, _P]),
     "pdf_avgpool_backward_f32": (C.c_int, [C.c_int, C.c_int, C.c_int, _P, _P, _P]),

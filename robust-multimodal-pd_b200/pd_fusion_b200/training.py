@@ -13,6 +13,7 @@ nothing on the arithmetic path.  FP32 throughout (gradients are checked against 
 from __future__ import annotations
 
 import ctypes as C
+import os
 from typing import Dict, List, Optional, Sequence, Tuple
 
 import torch
@@ -257,10 +258,10 @@ class MlpTrainer:
 
 
 class _Act:
-    __slots__ = ("data", "grad", "n", "hw", "c")
+    __slots__ = ("data", "grad", "n", "hw", "c", "b16")
 
-    def __init__(self, data, n, hw, c):
-        self.data, self.grad, self.n, self.hw, self.c = data, None, n, hw, c
+    def __init__(self, data, n, hw, c, b16=None):
+        self.data, self.grad, self.n, self.hw, self.c, self.b16 = data, None, n, hw, c, b16     # b16: bf16 copy (tensor path)
 
 
 class ResNetTrainer:
@@ -271,9 +272,17 @@ class ResNetTrainer:
     module's running statistics group by group.  Parameters are read from / updated in the nn.Module (torchvision layout
     [K,C,R,S]); the kernels consume an [R,S,C,K] copy refreshed by `sync_weights()`."""
 
-    def __init__(self, module: nn.Module, arch: str, input_size: int = 224):
+    def __init__(self, module: nn.Module, arch: str, input_size: int = 224, precision: Optional[str] = None):
+        """precision "bf16" (default; PD_FUSION_B200_TRAIN_PRECISION overrides): every convolution but the 3-channel stem runs on the
+        tcgen05 kernels -- forward and data gradient through the implicit-GEMM forward kernels (the data gradient on rotated weights,
+        strided ones on a zero-dilated dY), weight gradient through wgrad_tc.cu -- with bf16 operands, f32 accumulation, f32
+        BatchNorm / activations / gradients and f32 master weights.  "fp32": the CUDA-core parity path."""
         _lib.require_cuda()
         self.lib = _lib.load()
+        self.precision = precision or os.environ.get("PD_FUSION_B200_TRAIN_PRECISION", "bf16")
+        if self.precision not in ("bf16", "fp32"):
+            raise ValueError(f"ResNetTrainer: precision {self.precision!r} (bf16 | fp32)")
+        self.bf16 = self.precision == "bf16"
         self.m, self.arch, self.S = module, arch, int(input_size)
         self.kind, self.layers, self.emb_dim = RESNET_SPECS[arch]
         self.params = dict(module.named_parameters())
@@ -281,15 +290,27 @@ class ResNetTrainer:
         self.dev = self.params["conv1.weight"].device
         self.convs = {cv["name"]: cv for cv in conv_list(arch)}
         self.wk: Dict[str, torch.Tensor] = {}
+        self.wk16: Dict[str, torch.Tensor] = {}       # tensor path: [K][R][S][C] bf16 (forward operand)
+        self.wrot16: Dict[str, torch.Tensor] = {}     # tensor path: [C][R][S][K] bf16, taps rotated by 180 degrees (data-gradient operand)
         self.flat_grad, self.grad = _flat_like({k: v.data for k, v in self.params.items() if not k.startswith("fc.")})
         self._gwk: Dict[str, torch.Tensor] = {}
+        self._zero_bias = torch.zeros(4096, dtype=torch.float32, device=self.dev)
         self.sync_weights()
+
+    def _tc(self, name: str) -> bool:
+        """Does this convolution run on the tensor cores?  (the stem's 3 input channels do not fill a 64-channel k-block)"""
+        cv = self.convs[name]
+        return self.bf16 and cv["cin"] % 64 == 0 and cv["cout"] % 64 == 0
 
     # -- parameters --------------------------------------------------------------------------------
     def sync_weights(self):
         for name in self.convs:
             w = self.params[name + ".weight"].data
-            self.wk[name] = w.permute(2, 3, 1, 0).contiguous()          # [R,S,C,K] (layout change only)
+            if self._tc(name):
+                self.wk16[name] = w.permute(0, 2, 3, 1).contiguous().to(torch.bfloat16)
+                self.wrot16[name] = w.flip(2, 3).permute(1, 2, 3, 0).contiguous().to(torch.bfloat16)
+            else:
+                self.wk[name] = w.permute(2, 3, 1, 0).contiguous()      # [R,S,C,K] (layout change only)
 
     def zero_grad(self):
         self.flat_grad.zero_()
@@ -317,29 +338,51 @@ class ResNetTrainer:
         n, K = x.n, cv["cout"]
         op = self._op(n, h, x.c, cv, ho)
         conv_out = torch.empty((n * ho * ho, K), dtype=torch.float32, device=self.dev)
-        op.d_in, op.d_weight, op.d_out = x.data.data_ptr(), self.wk[name].data_ptr(), conv_out.data_ptr()
-        plan = C.c_void_p()
-        _lib.check(self.lib.pdf_plan_create(C.byref(plan), (_lib.Op * 1)(op), 1), "pdf_plan_create")
-        _lib.check(self.lib.pdf_plan_run(plan, _lib.stream_ptr()), "pdf_plan_run")
-        self.lib.pdf_plan_destroy(plan)
+        if self._tc(name):
+            # bf16 operands (the producer's BatchNorm wrote the bf16 copy), f32 accumulation, f32 result
+            op.precision, op.out_f32 = _lib.PREC_BF16, 1
+            op.d_in, op.d_weight, op.d_bias, op.d_out = self._b16(x).data_ptr(), self.wk16[name].data_ptr(), self._zero_bias.data_ptr(), conv_out.data_ptr()
+        else:
+            op.d_in, op.d_weight, op.d_out = x.data.data_ptr(), self.wk[name].data_ptr(), conv_out.data_ptr()
+        self._run_op(op)
         G = len(groups) - 1
         goff = self._goff(groups, ho * ho)
+        max_rows = max(b - a for a, b in zip(groups[:-1], groups[1:])) * ho * ho
         y = torch.empty_like(conv_out)
+        y16 = torch.empty(conv_out.shape, dtype=torch.bfloat16, device=self.dev) if (self.bf16 and name != "conv1") else None
         mean = torch.empty((G, K), dtype=torch.float32, device=self.dev)
         invstd, varu = torch.empty_like(mean), torch.empty_like(mean)
         bnm = self._bn_module(bn)
-        _lib.check(self.lib.pdf_bn_train_forward(G, goff.data_ptr(), K, conv_out.data_ptr(), self.params[bn + ".weight"].data.data_ptr(),
+        _lib.check(self.lib.pdf_bn_train_forward(G, goff.data_ptr(), max_rows, K, conv_out.data_ptr(), self.params[bn + ".weight"].data.data_ptr(),
                                                  self.params[bn + ".bias"].data.data_ptr(), float(bnm.eps), _p(res.data if res else None),
-                                                 1 if relu else 0, y.data_ptr(), mean.data_ptr(), invstd.data_ptr(), varu.data_ptr(),
-                                                 _lib.stream_ptr()), "pdf_bn_train_forward")
+                                                 1 if relu else 0, y.data_ptr(), _p(y16), mean.data_ptr(), invstd.data_ptr(), varu.data_ptr(),
+                                                 self._scratch(3 * G * K).data_ptr(), _lib.stream_ptr()), "pdf_bn_train_forward")
         if self.update_running:
             _lib.check(self.lib.pdf_bn_update_running(G, K, mean.data_ptr(), varu.data_ptr(), float(bnm.momentum),
                                                       self.buffers[bn + ".running_mean"].data_ptr(), self.buffers[bn + ".running_var"].data_ptr(),
                                                       _lib.stream_ptr()), "pdf_bn_update_running")
             self.buffers[bn + ".num_batches_tracked"] += G
-        out = _Act(y, n, ho * ho, K)
-        self.tape.append(("convbn", name, bn, x, conv_out, out, relu, res, op, goff, mean, invstd, h))
+        out = _Act(y, n, ho * ho, K, y16)
+        self.tape.append(("convbn", name, bn, x, conv_out, out, relu, res, op, goff, mean, invstd, h, max_rows))
         return out, ho
+
+    def _run_op(self, op: "_lib.Op") -> None:
+        plan = C.c_void_p()
+        _lib.check(self.lib.pdf_plan_create(C.byref(plan), (_lib.Op * 1)(op), 1), "pdf_plan_create")
+        _lib.check(self.lib.pdf_plan_run(plan, _lib.stream_ptr()), "pdf_plan_run")
+        self.lib.pdf_plan_destroy(plan)
+
+    def _scratch(self, n_doubles: int) -> torch.Tensor:
+        if getattr(self, "_scr", None) is None or self._scr.numel() < n_doubles:
+            self._scr = torch.empty(max(n_doubles, 3 * 16 * 2048), dtype=torch.float64, device=self.dev)
+        return self._scr
+
+    def _b16(self, a: _Act) -> torch.Tensor:
+        """bf16 copy of an activation (written by the BatchNorm that produced it; cast here for pooled tensors)."""
+        if a.b16 is None:
+            a.b16 = torch.empty(a.data.shape, dtype=torch.bfloat16, device=self.dev)
+            _lib.check(self.lib.pdf_cast_bf16(a.data.data_ptr(), a.b16.data_ptr(), a.data.numel(), _lib.stream_ptr()), "pdf_cast_bf16")
+        return a.b16
 
     def _bn_module(self, bn: str) -> nn.BatchNorm2d:
         mod = self.m
@@ -417,10 +460,11 @@ class ResNetTrainer:
                            "pdf_maxpool_backward_f32")
                 tout.grad = None
             else:
-                _, name, bn, x, conv_out, out, relu, res, op, goff, mean, invstd, h = entry
+                _, name, bn, x, conv_out, out, relu, res, op, goff, mean, invstd, h, max_rows = entry
                 G, K = int(mean.shape[0]), int(mean.shape[1])
+                tc = self._tc(name)
                 dconv = torch.empty_like(conv_out)
-                scratch = torch.empty((2, G, K), dtype=torch.float32, device=self.dev)
+                dconv16 = torch.empty(conv_out.shape, dtype=torch.bfloat16, device=self.dev) if tc else None
                 dres, acc = None, 0
                 if res is not None:
                     if res.grad is None:
@@ -428,12 +472,15 @@ class ResNetTrainer:
                     else:
                         acc = 1
                     dres = res.grad
-                _lib.check(lib.pdf_bn_train_backward(G, goff.data_ptr(), K, out.grad.data_ptr(), out.data.data_ptr(), conv_out.data_ptr(),
+                _lib.check(lib.pdf_bn_train_backward(G, goff.data_ptr(), max_rows, K, out.grad.data_ptr(), out.data.data_ptr(), conv_out.data_ptr(),
                                                      self.params[bn + ".weight"].data.data_ptr(), mean.data_ptr(), invstd.data_ptr(),
-                                                     1 if relu else 0, scratch.data_ptr(), dconv.data_ptr(), _p(dres), acc,
-                                                     self.grad[bn + ".weight"].data_ptr(), self.grad[bn + ".bias"].data_ptr(), s),
+                                                     1 if relu else 0, self._scratch(3 * G * K).data_ptr(), dconv.data_ptr(), _p(dconv16),
+                                                     _p(dres), acc, self.grad[bn + ".weight"].data_ptr(), self.grad[bn + ".bias"].data_ptr(), s),
                            "pdf_bn_train_backward")
                 out.grad = None
+                if tc:
+                    self._backward_conv_tc(name, op, x, dconv, dconv16, h, gwk)
+                    continue
                 if name not in gwk:
                     gwk[name] = torch.zeros_like(self.wk[name])
                 _lib.check(lib.pdf_conv_wgrad_f32(C.byref(op), x.data.data_ptr(), dconv.data_ptr(), gwk[name].data_ptr(), s), "pdf_conv_wgrad_f32")
@@ -443,6 +490,42 @@ class ResNetTrainer:
                         x.grad = torch.empty_like(x.data)
                     _lib.check(lib.pdf_conv_dgrad_f32(C.byref(op), dconv.data_ptr(), self.wk[name].data_ptr(), x.grad.data_ptr(), acc, s),
                                "pdf_conv_dgrad_f32")
-        for name, gw in gwk.items():                                 # [R,S,C,K] -> torchvision [K,C,R,S] (layout change only;
-            self.grad[name + ".weight"].copy_(gw.permute(3, 2, 0, 1))   #  one backward per zero_grad, as the reference's step)
+        for name, gw in gwk.items():                                 # -> torchvision [K,C,R,S] (layout change only; one backward per
+            if self._tc(name):                                       #    zero_grad, as the reference's step)
+                self.grad[name + ".weight"].copy_(gw.permute(0, 3, 1, 2))       # tensor path accumulates [K,R,S,C]
+            else:
+                self.grad[name + ".weight"].copy_(gw.permute(3, 2, 0, 1))       # FP32 path accumulates [R,S,C,K]
         self.tape = []
+
+    def _backward_conv_tc(self, name: str, op: "_lib.Op", x: _Act, dconv: torch.Tensor, dconv16: torch.Tensor, h: int, gwk) -> None:
+        """Weight and data gradient of one convolution on the tensor cores (bf16 operands, f32 results).
+        wgrad: dW[k][r][s][c] += dY^T im2col(X) (wgrad_tc.cu).  dgrad: a stride-1 convolution of dY with the 180-degree-rotated,
+        transposed filter (the forward implicit-GEMM kernels, pad' = R-1-pad); for stride 2 dY is first zero-dilated to the input's
+        size (dY[p,q] at (2p, 2q)), which turns the transposed convolution into the same stride-1 form."""
+        lib, s = self.lib, _lib.stream_ptr()
+        cv = self.convs[name]
+        n, C_in, K, R, stride, pad, ho = x.n, x.c, cv["cout"], cv["k"], cv["stride"], cv["pad"], int(op.ho)
+        if name not in gwk:
+            gwk[name] = torch.zeros((K, R, R, C_in), dtype=torch.float32, device=self.dev)
+        gop = self._op(n, h, C_in, cv, ho)
+        gop.precision = _lib.PREC_BF16
+        _lib.check(lib.pdf_conv_wgrad_bf16(C.byref(gop), self._b16(x).data_ptr(), dconv16.data_ptr(), gwk[name].data_ptr(), s), "pdf_conv_wgrad_bf16")
+        if stride == 1:
+            src, hs = dconv16, ho
+        else:
+            src, hs = torch.empty((n * h * h, K), dtype=torch.bfloat16, device=self.dev), h
+            _lib.check(lib.pdf_dilate_bf16(n, ho, ho, K, h, h, stride, 0, dconv.data_ptr(), src.data_ptr(), s), "pdf_dilate_bf16")
+        dop = _lib.Op()
+        dop.kind, dop.precision, dop.out_f32 = _lib.OP_CONV, _lib.PREC_BF16, 1
+        dop.n, dop.h, dop.w, dop.c, dop.k, dop.r, dop.s = n, hs, hs, K, C_in, R, R
+        dop.stride, dop.pad, dop.ho, dop.wo, dop.relu = 1, R - 1 - pad, h, h, 0
+        assert hs + 2 * (R - 1 - pad) - R + 1 == h, (name, hs, h)
+        if x.grad is None:
+            x.grad = torch.empty_like(x.data)
+            dst, tmp = x.grad, None
+        else:
+            dst = tmp = torch.empty_like(x.data)
+        dop.d_in, dop.d_weight, dop.d_bias, dop.d_out = src.data_ptr(), self.wrot16[name].data_ptr(), self._zero_bias.data_ptr(), dst.data_ptr()
+        self._run_op(dop)
+        if tmp is not None:
+            _lib.check(lib.pdf_add_f32(x.grad.data_ptr(), tmp.data_ptr(), tmp.numel(), s), "pdf_add_f32")

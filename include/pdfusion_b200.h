@@ -259,26 +259,37 @@ int pdf_gemm_f32(int M, int N, int K, const float* A, long a_rs, long a_cs, cons
  * dgrad d_dx [n,h,w,c] (+)= conv^T(d_dy [n,ho,wo,k], w);  wgrad d_dw [R][S][C][K] += x^T * dy (accumulates: zero it first). */
 int pdf_conv_dgrad_f32(const pdf_op* op, const float* d_dy, const float* d_weight, float* d_dx, int accumulate, pdf_stream_t stream);
 int pdf_conv_wgrad_f32(const pdf_op* op, const float* d_x, const float* d_dy, float* d_dw, pdf_stream_t stream);
-/* train-mode BatchNorm over row groups of the [M, C] activation matrix (C % 4 == 0): group g = rows [d_goff[g], d_goff[g+1]) (one
- * 16-slice chunk of one bag); max_group_rows = the longest group (sizes the reduction grid).  forward: y = (x - mean_g) * invstd_g * gamma
- * + beta (+ residual) (ReLU); saves mean, invstd (biased variance, eps inside) and the unbiased variance (for the running statistics)
- * per (group, channel); d_y_bf16 (or NULL): a bf16 copy of y, the operand of the next tensor-core convolution.
- * d_scratch: 2 * n_groups * C doubles (float64 partial sums). */
+/* train-mode BatchNorm over row groups of the [M, C] activation matrix: group g = rows [d_goff[g], d_goff[g+1]) (one 16-slice chunk
+ * of one bag); max_group_rows = the longest group (sizes the reduction grid).  forward: y = (x - mean_g) * invstd_g * gamma + beta
+ * (+ residual) (ReLU); saves mean, invstd (biased variance, eps inside) and the unbiased variance (for the running statistics) per
+ * (group, channel).  d_scratch: 3 * n_groups * C doubles (float64 partial sums of the slab-split reductions).
+ * backward: g = d_dy * (d_y > 0 if relu); d_dgamma += sum g*xhat, d_dbeta += sum g (accumulate over calls: zero first);
+ * d_dx = gamma*invstd*(g - mean_g(g) - xhat*mean_g(g*xhat)); d_dres (or NULL) (+)= g, the gradient of the residual branch.
+ * Two storage types: f32 (C % 4 == 0; the FP32 parity path) and bf16 (C % 8 == 0; x, residual, y, dy, dx, dres are bf16, everything
+ * computed in f32 / f64 -- the tensor-core path, csrc/train_bf16.cu). */
 int pdf_bn_train_forward(int n_groups, const int32_t* d_goff, int max_group_rows, int C, const float* d_x, const float* d_gamma,
-                         const float* d_beta, float eps, const float* d_residual, int relu, float* d_y, void* d_y_bf16, float* d_mean,
-                         float* d_invstd, float* d_var_unbiased, double* d_scratch, pdf_stream_t stream);
-/* backward of the same: g = d_dy * (d_y > 0 if relu); d_dgamma += sum g*xhat, d_dbeta += sum g (accumulate over calls: zero first);
- * d_dx = gamma*invstd*(g - mean_g(g) - xhat*mean_g(g*xhat)), d_dx_bf16 (or NULL) its bf16 copy; d_dres (or NULL) (+)= g, the gradient
- * of the residual branch.  d_scratch: 3 * n_groups * C doubles. */
+                         const float* d_beta, float eps, const float* d_residual, int relu, float* d_y, float* d_mean, float* d_invstd,
+                         float* d_var_unbiased, double* d_scratch, pdf_stream_t stream);
 int pdf_bn_train_backward(int n_groups, const int32_t* d_goff, int max_group_rows, int C, const float* d_dy, const float* d_y,
                           const float* d_x, const float* d_gamma, const float* d_mean, const float* d_invstd, int relu, double* d_scratch,
-                          float* d_dx, void* d_dx_bf16, float* d_dres, int dres_accumulate, float* d_dgamma, float* d_dbeta,
-                          pdf_stream_t stream);
+                          float* d_dx, float* d_dres, int dres_accumulate, float* d_dgamma, float* d_dbeta, pdf_stream_t stream);
+int pdf_bn_train_forward_bf16(int n_groups, const int32_t* d_goff, int max_group_rows, int C, const void* d_x, const float* d_gamma,
+                              const float* d_beta, float eps, const void* d_residual, int relu, void* d_y, float* d_mean, float* d_invstd,
+                              float* d_var_unbiased, double* d_scratch, pdf_stream_t stream);
+int pdf_bn_train_backward_bf16(int n_groups, const int32_t* d_goff, int max_group_rows, int C, const void* d_dy, const void* d_y,
+                               const void* d_x, const float* d_gamma, const float* d_mean, const float* d_invstd, int relu,
+                               double* d_scratch, void* d_dx, void* d_dres, int dres_accumulate, float* d_dgamma, float* d_dbeta,
+                               pdf_stream_t stream);
 /* running = (1-momentum)*running + momentum*batch, group after group (the reference forwards its chunks one at a time) */
 int pdf_bn_update_running(int n_groups, int C, const float* d_mean, const float* d_var_unbiased, float momentum, float* d_running_mean,
                           float* d_running_var, pdf_stream_t stream);
 int pdf_maxpool_backward_f32(int n, int h, int w, int c, const float* d_x, const float* d_dy, float* d_dx, pdf_stream_t stream);
 int pdf_avgpool_backward_f32(int n, int hw, int c, const float* d_demb, float* d_dx, pdf_stream_t stream);
+/* bf16 storage (c % 8 == 0): x, y, dy, dx bf16; the training-mode max pool records the winning window position (r*3+s of the first
+ * maximum, u8 [n,ho,wo,c]) and its backward gathers through it; the average pool's incoming gradient d_demb stays f32 */
+int pdf_maxpool_train_forward_bf16(int n, int h, int w, int c, const void* d_x, void* d_y, uint8_t* d_idx, pdf_stream_t stream);
+int pdf_maxpool_backward_bf16(int n, int h, int w, int c, const uint8_t* d_idx, const void* d_dy, void* d_dx, pdf_stream_t stream);
+int pdf_avgpool_backward_bf16(int n, int hw, int c, const float* d_demb, void* d_dx, pdf_stream_t stream);
 /* MIL head, training: everything after the linear layers, forward AND backward, in one kernel (one block per bag).
  * d_h [n_bags*Lmax, H] = dropout(relu(instance(x))); d_vu [n_bags*Lmax, NA] = attention pre-activations incl. bias (NA = 2A gated: v|u).
  * Writes d_prob [n_bags], adds the batch-mean loss to d_loss[0], writes d_dh (pooling path only) and d_dvu, and ACCUMULATES the
@@ -305,6 +316,17 @@ int pdf_conv_wgrad_bf16(const pdf_op* op, const void* d_x, const void* d_dy, flo
 int pdf_cast_bf16(const float* d_x, void* d_y, size_t n, pdf_stream_t stream);
 int pdf_add_f32(float* d_x, const float* d_y, size_t n, pdf_stream_t stream);
 int pdf_dilate_bf16(int n, int ho, int wo, int k, int hd, int wd, int stride, int offset, const float* d_dy, void* d_out, pdf_stream_t stream);
+/* tensor-core path helpers (csrc/train_bf16.cu):
+ * pdf_stem_im2col3_bf16: f32 NHWC3 network input [n,h,w,3] -> bf16 patch matrix [n*ho*wo, 192] of the 7x7 s2 p3 stem (column
+ *   (r*7+s)*3+ch, columns 147..191 zero): conv1's forward and weight gradient become 1x1 tensor-core GEMMs (c = 192, k = 64);
+ * pdf_dilate2_bf16: zero-dilated copy [n,hd,wd,k] of a bf16 dY [n,ho,wo,k] (dY[p,q] at (2p,2q)): data gradient of a stride-2 3x3 conv;
+ * pdf_scatter_add2_bf16: d_dx[n,2p,2q,:] += d_t[n,p,q,:] (bf16): data gradient of a stride-2 1x1 conv after its GEMM on dY;
+ * pdf_pack_conv_weights: f32 [K,C,R,S] (torchvision) -> bf16 [K][R][S][C] and (d_wrot may be NULL) bf16 [C][R][S][K] with the taps
+ *   rotated by 180 degrees, the operand of the data-gradient convolution. */
+int pdf_stem_im2col3_bf16(int n, int h, int w, const float* d_x, void* d_out, pdf_stream_t stream);
+int pdf_dilate2_bf16(int n, int ho, int wo, int k, int hd, int wd, const void* d_src, void* d_out, pdf_stream_t stream);
+int pdf_scatter_add2_bf16(int n, int ho, int wo, int c, int h, int w, const void* d_t, void* d_dx, pdf_stream_t stream);
+int pdf_pack_conv_weights(int k, int c, int r, int s, const float* d_w, void* d_wk, void* d_wrot, pdf_stream_t stream);
 int pdf_colsum_f32(int M, int N, const float* d_x, float* d_out, int accumulate, pdf_stream_t stream);
 /* in place: grad *= (act > 0) * mask   (ReLU + inverted-dropout backward; mask NULL = no dropout) */
 int pdf_relu_mask_backward(float* d_grad, const float* d_act, const float* d_mask, size_t n, pdf_stream_t stream);

@@ -792,7 +792,7 @@ extern "C" int pdf_conv_wgrad_f32(const pdf_op* op, const float* d_x, const floa
 }
 
 extern "C" int pdf_bn_train_forward(int n_groups, const int32_t* d_goff, int max_group_rows, int C, const float* d_x, const float* d_gamma,
-                                    const float* d_beta, float eps, const float* d_residual, int relu, float* d_y, void* d_y_bf16, float* d_mean,
+                                    const float* d_beta, float eps, const float* d_residual, int relu, float* d_y, float* d_mean,
                                     float* d_invstd, float* d_var_unbiased, double* d_scratch, pdf_stream_t stream) {
   PDF_REQUIRE(n_groups > 0 && d_goff && max_group_rows > 0 && C > 0 && C % 4 == 0 && d_x && d_gamma && d_beta && d_y && d_mean && d_invstd &&
               d_var_unbiased && d_scratch, "pdf_bn_train_forward: bad arguments (C %% 4 == 0, scratch of 2*groups*C doubles)");
@@ -803,15 +803,14 @@ extern "C" int pdf_bn_train_forward(int n_groups, const int32_t* d_goff, int max
   bn_stats_finalize_kernel<<<ceil_div(n_groups * C, 256), 256, 0, s>>>(d_scratch, d_goff, n_groups, C, eps, d_mean, d_invstd, d_var_unbiased);
   PDF_CHECK_LAUNCH();
   bn_apply_kernel<<<dim3(std::max(1, 8 * num_sms() / n_groups), n_groups), 256, 0, s>>>(d_x, d_goff, C, d_mean, d_invstd, d_gamma, d_beta,
-                                                                                       d_residual, relu, d_y,
-                                                                                       reinterpret_cast<__nv_bfloat16*>(d_y_bf16));
+                                                                                       d_residual, relu, d_y, nullptr);
   PDF_CHECK_LAUNCH();
   return PDF_OK;
 }
 
 extern "C" int pdf_bn_train_backward(int n_groups, const int32_t* d_goff, int max_group_rows, int C, const float* d_dy, const float* d_y,
                                      const float* d_x, const float* d_gamma, const float* d_mean, const float* d_invstd, int relu,
-                                     double* d_scratch, float* d_dx, void* d_dx_bf16, float* d_dres, int dres_accumulate, float* d_dgamma,
+                                     double* d_scratch, float* d_dx, float* d_dres, int dres_accumulate, float* d_dgamma,
                                      float* d_dbeta, pdf_stream_t stream) {
   PDF_REQUIRE(n_groups > 0 && d_goff && max_group_rows > 0 && C > 0 && C % 4 == 0 && d_dy && d_y && d_x && d_gamma && d_mean && d_invstd &&
               d_scratch && d_dx && d_dgamma && d_dbeta, "pdf_bn_train_backward: bad arguments (C %% 4 == 0, scratch of 3*groups*C doubles)");
@@ -825,8 +824,8 @@ extern "C" int pdf_bn_train_backward(int n_groups, const int32_t* d_goff, int ma
   bn_bwd_finalize_kernel<<<ceil_div(C, 128), 128, 0, s>>>(acc, n_groups, C, sums, d_dgamma, d_dbeta);
   PDF_CHECK_LAUNCH();
   bn_bwd_apply_kernel<<<dim3(std::max(1, 8 * num_sms() / n_groups), n_groups), 256, 0, s>>>(
-      d_dy, d_y, d_x, d_goff, C, d_mean, d_invstd, d_gamma, relu, sums, sums + (size_t)n_groups * C, d_dx,
-      reinterpret_cast<__nv_bfloat16*>(d_dx_bf16), d_dres, dres_accumulate);
+      d_dy, d_y, d_x, d_goff, C, d_mean, d_invstd, d_gamma, relu, sums, sums + (size_t)n_groups * C, d_dx, nullptr, d_dres,
+      dres_accumulate);
   PDF_CHECK_LAUNCH();
   return PDF_OK;
 }

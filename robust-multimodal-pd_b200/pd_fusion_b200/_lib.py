@@ -127,8 +127,17 @@ PROTOTYPES = {
     "pdf_gemm_f32": (C.c_int, [C.c_int, C.c_int, C.c_int, _P, C.c_long, C.c_long, _P, C.c_long, C.c_long, _P, C.c_long, _P, C.c_int, C.c_int, _P]),
     "pdf_conv_dgrad_f32": (C.c_int, [C.POINTER(Op), _P, _P, _P, C.c_int, _P]),
     "pdf_conv_wgrad_f32": (C.c_int, [C.POINTER(Op), _P, _P, _P, _P]),
-    "pdf_bn_train_forward": (C.c_int, [C.c_int, _P, C.c_int, C.c_int, _P, _P, _P, C.c_float, _P, C.c_int, _P, _P, _P, _P, _P, _P, _P]),
-    "pdf_bn_train_backward": (C.c_int, [C.c_int, _P, C.c_int, C.c_int, _P, _P, _P, _P, _P, _P, C.c_int, _P, _P, _P, _P, C.c_int, _P, _P, _P]),
+    "pdf_bn_train_forward": (C.c_int, [C.c_int, _P, C.c_int, C.c_int, _P, _P, _P, C.c_float, _P, C.c_int, _P, _P, _P, _P, _P, _P]),
+    "pdf_bn_train_backward": (C.c_int, [C.c_int, _P, C.c_int, C.c_int, _P, _P, _P, _P, _P, _P, C.c_int, _P, _P, _P, C.c_int, _P, _P, _P]),
+    "pdf_bn_train_forward_bf16": (C.c_int, [C.c_int, _P, C.c_int, C.c_int, _P, _P, _P, C.c_float, _P, C.c_int, _P, _P, _P, _P, _P, _P]),
+    "pdf_bn_train_backward_bf16": (C.c_int, [C.c_int, _P, C.c_int, C.c_int, _P, _P, _P, _P, _P, _P, C.c_int, _P, _P, _P, C.c_int, _P, _P, _P]),
+    "pdf_maxpool_train_forward_bf16": (C.c_int, [C.c_int, C.c_int, C.c_int, C.c_int, _P, _P, _P, _P]),
+    "pdf_maxpool_backward_bf16": (C.c_int, [C.c_int, C.c_int, C.c_int, C.c_int, _P, _P, _P, _P]),
+    "pdf_avgpool_backward_bf16": (C.c_int, [C.c_int, C.c_int, C.c_int, _P, _P, _P]),
+    "pdf_stem_im2col3_bf16": (C.c_int, [C.c_int, C.c_int, C.c_int, _P, _P, _P]),
+    "pdf_dilate2_bf16": (C.c_int, [C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, _P, _P, _P]),
+    "pdf_scatter_add2_bf16": (C.c_int, [C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, _P, _P, _P]),
+    "pdf_pack_conv_weights": (C.c_int, [C.c_int, C.c_int, C.c_int, C.c_int, _P, _P, _P, _P]),
     "pdf_bn_update_running": (C.c_int, [C.c_int, C.c_int, _P, _P, C.c_float, _P, _P, _P]),
     "pdf_maxpool_backward_f32": (C.c_int, [C.c_int, C.c_int, C.c_int, C.c_int, _P, _P, _P, _P]),
     "pdf_avgpool_backward_f32": (C.c_int, [C.c_int, C.c_int, C.c_int, _P, _P, _P]),

@@ -217,8 +217,9 @@ class MilAttentionFineTuneModel(BaseModel):
             p = self.params
             rt = ResNetTrainer(self.backbone, "resnet50" if self.backbone_name == "resnet50" else "resnet18", self.input_size)
             ht = MilHeadTrainer(self.attn, self.gated)
-            opt = NativeAdam([([q for q, _ in rt.param_grads()], float(p.get("lr_backbone", 1e-4))),
-                              ([q for q, _ in ht.param_grads()], float(p.get("lr", 3e-4)))], weight_decay=float(p.get("weight_decay", 1e-3)))
+            # (the trainers keep every parameter / gradient of a module in one flat buffer: one Adam launch per group)
+            opt = NativeAdam([([rt.flat_param], float(p.get("lr_backbone", 1e-4))), ([ht.flat_param], float(p.get("lr", 3e-4)))],
+                             weight_decay=float(p.get("weight_decay", 1e-3)))
             self._trainer = (rt, ht, opt)
         return self._trainer
 
@@ -262,7 +263,7 @@ class MilAttentionFineTuneModel(BaseModel):
         ht.zero_grad()
         loss, prob, dX = ht.forward_backward(X, lens, torch.from_numpy(np.asarray(y_batch, dtype=np.float32)), self.loss_type, self.pos_weight,
                                              self.focal_gamma, self.focal_alpha, need_dx=not frozen)
-        pg = [(q, g, opt.groups[1][1]) for q, g in ht.param_grads()]
+        pg = [(ht.flat_param, ht.flat_grad, opt.groups[1][1])]
         if not frozen:
             rt.zero_grad()
             demb = torch.empty((total, self.emb_dim), dtype=torch.float32, device=self.device)
@@ -273,7 +274,7 @@ class MilAttentionFineTuneModel(BaseModel):
                     demb[k:k + L].copy_(dX[i, :L])
                     k += L
             rt.backward(demb)
-            pg = [(q, g, opt.groups[0][1]) for q, g in rt.param_grads()] + pg
+            pg = [(rt.flat_param, rt.flat_grad, opt.groups[0][1])] + pg
         from ..training import allreduce_mean
         allreduce_mean([ht.flat_grad] + ([] if frozen else [rt.flat_grad]))          # data-parallel over bags under torchrun
         scale = opt.clip([g for _, g, _ in pg], float(clip)) if clip else None

@@ -38,6 +38,17 @@ def _flat_like(params: Dict[str, torch.Tensor]):
     return flat, {k: flat[offs[k]:offs[k] + v.numel()].view(v.shape) for k, v in params.items()}
 
 
+def flatten_parameters(params: Dict[str, torch.Tensor]) -> torch.Tensor:
+    """Moves the parameters into ONE flat f32 buffer with `_flat_like`'s layout and re-points every `param.data` at its view, so
+    that the global gradient norm and the Adam update are one launch per buffer instead of one per tensor (ResNet50: 161).
+    The nn.Module keeps working unchanged: state_dict / load_state_dict / save see the same tensors."""
+    flat, views = _flat_like({k: v.data for k, v in params.items()})
+    for k, v in params.items():
+        views[k].copy_(v.data)
+        v.data = views[k]
+    return flat
+
+
 def allreduce_mean(flat_grads: Sequence[torch.Tensor]) -> None:
     """Data-parallel fine-tuning: every rank runs its own bags, the gradients are averaged with one NCCL
     all-reduce per flat buffer before clip + Adam.  No-op in a single process."""
@@ -100,10 +111,11 @@ class MilHeadTrainer:
         self.lib = _lib.load()
         self.net, self.gated = net, bool(gated)
         sd = dict(net.named_parameters())
-        self.p = {k: v.data for k, v in sd.items()}
-        for v in self.p.values():
-            if not (v.is_cuda and v.dtype == torch.float32 and v.is_contiguous()):
+        for v in sd.values():
+            if not (v.data.is_cuda and v.data.dtype == torch.float32 and v.data.is_contiguous()):
                 raise ValueError("MilHeadTrainer needs contiguous float32 CUDA parameters")
+        self.flat_param = flatten_parameters(sd)                 # same layout as flat_grad: clip / Adam in one launch each
+        self.p = {k: v.data for k, v in sd.items()}
         self.flat_grad, self.g = _flat_like(self.p)
         self.H, self.D = self.p["instance.0.weight"].shape
         self.A = (self.p["attn_v.0.weight"] if self.gated else self.p["attn.0.weight"]).shape[0]
@@ -258,10 +270,10 @@ class MlpTrainer:
 
 
 class _Act:
-    __slots__ = ("data", "grad", "n", "hw", "c", "b16")
+    __slots__ = ("data", "grad", "n", "hw", "c")
 
-    def __init__(self, data, n, hw, c, b16=None):
-        self.data, self.grad, self.n, self.hw, self.c, self.b16 = data, None, n, hw, c, b16     # b16: bf16 copy (tensor path)
+    def __init__(self, data, n, hw, c):
+        self.data, self.grad, self.n, self.hw, self.c = data, None, n, hw, c     # data / grad: f32 (fp32 path) or bf16 (tensor path)
 
 
 class ResNetTrainer:
@@ -270,13 +282,18 @@ class ResNetTrainer:
     BatchNorm uses BATCH statistics over each group of images (`groups`: image offsets; one group = one 16-slice chunk of one
     bag, the unit the reference pushes through `self.backbone(batch)`, mil_attention_finetune.py:147-150) and updates the
     module's running statistics group by group.  Parameters are read from / updated in the nn.Module (torchvision layout
-    [K,C,R,S]); the kernels consume an [R,S,C,K] copy refreshed by `sync_weights()`."""
+    [K,C,R,S]); the kernels consume re-laid-out copies refreshed by `sync_weights()`.
+
+    precision "bf16" (default; PD_FUSION_B200_TRAIN_PRECISION overrides) -- the tensor-core path: every convolution runs on the
+    tcgen05 kernels with bf16 operands and f32 accumulation.  Forward and data gradient go through the inference path's
+    implicit-GEMM kernels (the data gradient as a stride-1 convolution of dY with the 180-degree-rotated, transposed filter; for
+    the stride-2 3x3 convolutions dY is zero-dilated first, the stride-2 1x1 downsamples are a GEMM on dY scattered onto the even
+    pixels), the weight gradient through wgrad_tc.cu, the 3-channel stem as a [M,192] patch-matrix GEMM.  Activations, conv
+    outputs and activation gradients are STORED in bf16; BatchNorm statistics (float64 sums), normalisation, parameter gradients,
+    master weights and the optimiser are f32 -- the numerics of torch's bf16 autocast (csrc/train_bf16.cu).
+    precision "fp32": the CUDA-core parity path (csrc/train.cu), f32 everywhere."""
 
     def __init__(self, module: nn.Module, arch: str, input_size: int = 224, precision: Optional[str] = None):
-        """precision "bf16" (default; PD_FUSION_B200_TRAIN_PRECISION overrides): every convolution but the 3-channel stem runs on the
-        tcgen05 kernels -- forward and data gradient through the implicit-GEMM forward kernels (the data gradient on rotated weights,
-        strided ones on a zero-dilated dY), weight gradient through wgrad_tc.cu -- with bf16 operands, f32 accumulation, f32
-        BatchNorm / activations / gradients and f32 master weights.  "fp32": the CUDA-core parity path."""
         _lib.require_cuda()
         self.lib = _lib.load()
         self.precision = precision or os.environ.get("PD_FUSION_B200_TRAIN_PRECISION", "bf16")
@@ -289,28 +306,44 @@ class ResNetTrainer:
         self.buffers = dict(module.named_buffers())
         self.dev = self.params["conv1.weight"].device
         self.convs = {cv["name"]: cv for cv in conv_list(arch)}
-        self.wk: Dict[str, torch.Tensor] = {}
-        self.wk16: Dict[str, torch.Tensor] = {}       # tensor path: [K][R][S][C] bf16 (forward operand)
+        self.wk: Dict[str, torch.Tensor] = {}         # fp32 path: [R,S,C,K] f32
+        self.wk16: Dict[str, torch.Tensor] = {}       # tensor path: [K][R][S][C] bf16 (forward / wgrad layout; the stem: [64][192])
         self.wrot16: Dict[str, torch.Tensor] = {}     # tensor path: [C][R][S][K] bf16, taps rotated by 180 degrees (data-gradient operand)
-        self.flat_grad, self.grad = _flat_like({k: v.data for k, v in self.params.items() if not k.startswith("fc.")})
-        self._gwk: Dict[str, torch.Tensor] = {}
+        trainable = {k: v for k, v in self.params.items() if not k.startswith("fc.")}
+        self.flat_param = flatten_parameters(trainable)              # same layout as flat_grad: clip / Adam in one launch each
+        self.flat_grad, self.grad = _flat_like({k: v.data for k, v in trainable.items()})
         self._zero_bias = torch.zeros(4096, dtype=torch.float32, device=self.dev)
+        self._scr = None
+        if self.bf16:
+            for name, cv in self.convs.items():
+                if name == "conv1":
+                    self.wk16[name] = torch.zeros((cv["cout"], 192), dtype=torch.bfloat16, device=self.dev)
+                    continue
+                assert cv["cin"] % 64 == 0 and cv["cout"] % 64 == 0, name
+                self.wk16[name] = torch.empty((cv["cout"], cv["k"], cv["k"], cv["cin"]), dtype=torch.bfloat16, device=self.dev)
+                self.wrot16[name] = torch.empty((cv["cin"], cv["k"], cv["k"], cv["cout"]), dtype=torch.bfloat16, device=self.dev)
+            # weight-gradient accumulators [K][R][S][C] f32 of every convolution in ONE buffer (zeroed with one memset per step)
+            sizes = {n: (192 * cv["cout"] if n == "conv1" else cv["cout"] * cv["k"] * cv["k"] * cv["cin"]) for n, cv in self.convs.items()}
+            self._gw_flat = torch.zeros(sum(sizes.values()), dtype=torch.float32, device=self.dev)
+            self._gw, off = {}, 0
+            for n, cv in self.convs.items():
+                shape = (cv["cout"], 192) if n == "conv1" else (cv["cout"], cv["k"], cv["k"], cv["cin"])
+                self._gw[n] = self._gw_flat[off:off + sizes[n]].view(shape)
+                off += sizes[n]
         self.sync_weights()
-
-    def _tc(self, name: str) -> bool:
-        """Does this convolution run on the tensor cores?  (the stem's 3 input channels do not fill a 64-channel k-block)"""
-        cv = self.convs[name]
-        return self.bf16 and cv["cin"] % 64 == 0 and cv["cout"] % 64 == 0
 
     # -- parameters --------------------------------------------------------------------------------
     def sync_weights(self):
-        for name in self.convs:
+        s = _lib.stream_ptr()
+        for name, cv in self.convs.items():
             w = self.params[name + ".weight"].data
-            if self._tc(name):
-                self.wk16[name] = w.permute(0, 2, 3, 1).contiguous().to(torch.bfloat16)
-                self.wrot16[name] = w.flip(2, 3).permute(1, 2, 3, 0).contiguous().to(torch.bfloat16)
-            else:
+            if not self.bf16:
                 self.wk[name] = w.permute(2, 3, 1, 0).contiguous()      # [R,S,C,K] (layout change only)
+            elif name == "conv1":                                       # [64][7][7][3] -> 147 of the 192 patch-matrix columns
+                self.wk16[name][:, :147].copy_(w.permute(0, 2, 3, 1).reshape(w.shape[0], 147))
+            else:
+                _lib.check(self.lib.pdf_pack_conv_weights(cv["cout"], cv["cin"], cv["k"], cv["k"], w.data_ptr(), self.wk16[name].data_ptr(),
+                                                          self.wrot16[name].data_ptr(), s), "pdf_pack_conv_weights")
 
     def zero_grad(self):
         self.flat_grad.zero_()
@@ -318,7 +351,7 @@ class ResNetTrainer:
     def param_grads(self) -> List[Tuple[torch.Tensor, torch.Tensor]]:
         return [(self.params[k].data, self.grad[k]) for k in self.grad]
 
-    # -- forward ---------------------------------------------------------------------------------------
+    # -- shared helpers ----------------------------------------------------------------------------
     def _op(self, n, h, c, cv, ho) -> "_lib.Op":
         op = _lib.Op()
         op.kind, op.precision = _lib.OP_CONV, _lib.PREC_F32
@@ -326,63 +359,29 @@ class ResNetTrainer:
         op.stride, op.pad, op.ho, op.wo, op.relu = cv["stride"], cv["pad"], ho, ho, 0
         return op
 
-    def _goff(self, groups: Sequence[int], hw: int) -> torch.Tensor:
-        key = (tuple(groups), hw)
-        if key not in self._goff_cache:
-            self._goff_cache[key] = torch.tensor([g * hw for g in groups], dtype=torch.int32, device=self.dev)
-        return self._goff_cache[key]
-
-    def _convbn(self, x: _Act, h: int, name: str, bn: str, relu: bool, res: Optional[_Act], groups) -> Tuple[_Act, int]:
-        cv = self.convs[name]
-        ho = (h + 2 * cv["pad"] - cv["k"]) // cv["stride"] + 1
-        n, K = x.n, cv["cout"]
-        op = self._op(n, h, x.c, cv, ho)
-        conv_out = torch.empty((n * ho * ho, K), dtype=torch.float32, device=self.dev)
-        if self._tc(name):
-            # bf16 operands (the producer's BatchNorm wrote the bf16 copy), f32 accumulation, f32 result
-            op.precision, op.out_f32 = _lib.PREC_BF16, 1
-            op.d_in, op.d_weight, op.d_bias, op.d_out = self._b16(x).data_ptr(), self.wk16[name].data_ptr(), self._zero_bias.data_ptr(), conv_out.data_ptr()
-        else:
-            op.d_in, op.d_weight, op.d_out = x.data.data_ptr(), self.wk[name].data_ptr(), conv_out.data_ptr()
-        self._run_op(op)
-        G = len(groups) - 1
-        goff = self._goff(groups, ho * ho)
-        max_rows = max(b - a for a, b in zip(groups[:-1], groups[1:])) * ho * ho
-        y = torch.empty_like(conv_out)
-        y16 = torch.empty(conv_out.shape, dtype=torch.bfloat16, device=self.dev) if (self.bf16 and name != "conv1") else None
-        mean = torch.empty((G, K), dtype=torch.float32, device=self.dev)
-        invstd, varu = torch.empty_like(mean), torch.empty_like(mean)
-        bnm = self._bn_module(bn)
-        _lib.check(self.lib.pdf_bn_train_forward(G, goff.data_ptr(), max_rows, K, conv_out.data_ptr(), self.params[bn + ".weight"].data.data_ptr(),
-                                                 self.params[bn + ".bias"].data.data_ptr(), float(bnm.eps), _p(res.data if res else None),
-                                                 1 if relu else 0, y.data_ptr(), _p(y16), mean.data_ptr(), invstd.data_ptr(), varu.data_ptr(),
-                                                 self._scratch(3 * G * K).data_ptr(), _lib.stream_ptr()), "pdf_bn_train_forward")
-        if self.update_running:
-            _lib.check(self.lib.pdf_bn_update_running(G, K, mean.data_ptr(), varu.data_ptr(), float(bnm.momentum),
-                                                      self.buffers[bn + ".running_mean"].data_ptr(), self.buffers[bn + ".running_var"].data_ptr(),
-                                                      _lib.stream_ptr()), "pdf_bn_update_running")
-            self.buffers[bn + ".num_batches_tracked"] += G
-        out = _Act(y, n, ho * ho, K, y16)
-        self.tape.append(("convbn", name, bn, x, conv_out, out, relu, res, op, goff, mean, invstd, h, max_rows))
-        return out, ho
-
     def _run_op(self, op: "_lib.Op") -> None:
         plan = C.c_void_p()
         _lib.check(self.lib.pdf_plan_create(C.byref(plan), (_lib.Op * 1)(op), 1), "pdf_plan_create")
         _lib.check(self.lib.pdf_plan_run(plan, _lib.stream_ptr()), "pdf_plan_run")
         self.lib.pdf_plan_destroy(plan)
 
+    def _pool_op(self, kind, prec, n, h, c, ho, d_in, d_out):
+        op = _lib.Op()
+        op.kind, op.precision = kind, prec
+        op.n, op.h, op.w, op.c, op.ho, op.wo = n, h, h, c, ho, ho
+        op.d_in, op.d_out = d_in, d_out
+        self._run_op(op)
+
     def _scratch(self, n_doubles: int) -> torch.Tensor:
-        if getattr(self, "_scr", None) is None or self._scr.numel() < n_doubles:
+        if self._scr is None or self._scr.numel() < n_doubles:
             self._scr = torch.empty(max(n_doubles, 3 * 16 * 2048), dtype=torch.float64, device=self.dev)
         return self._scr
 
-    def _b16(self, a: _Act) -> torch.Tensor:
-        """bf16 copy of an activation (written by the BatchNorm that produced it; cast here for pooled tensors)."""
-        if a.b16 is None:
-            a.b16 = torch.empty(a.data.shape, dtype=torch.bfloat16, device=self.dev)
-            _lib.check(self.lib.pdf_cast_bf16(a.data.data_ptr(), a.b16.data_ptr(), a.data.numel(), _lib.stream_ptr()), "pdf_cast_bf16")
-        return a.b16
+    def _goff(self, groups: Sequence[int], hw: int) -> torch.Tensor:
+        key = (tuple(groups), hw)
+        if key not in self._goff_cache:
+            self._goff_cache[key] = torch.tensor([g * hw for g in groups], dtype=torch.int32, device=self.dev)
+        return self._goff_cache[key]
 
     def _bn_module(self, bn: str) -> nn.BatchNorm2d:
         mod = self.m
@@ -390,25 +389,88 @@ class ResNetTrainer:
             mod = mod[int(part)] if part.isdigit() else getattr(mod, part)
         return mod
 
+    # -- forward ---------------------------------------------------------------------------------------
+    def _bn_forward(self, bn: str, conv_out: torch.Tensor, res: Optional[_Act], relu: bool, groups, hw: int):
+        """Train-mode BatchNorm (+ residual, ReLU) of a conv output [M, K] in the path's storage type; returns (y, goff, mean, invstd, max_rows)."""
+        G, K = len(groups) - 1, int(conv_out.shape[1])
+        goff = self._goff(groups, hw)
+        max_rows = max(b - a for a, b in zip(groups[:-1], groups[1:])) * hw
+        y = torch.empty_like(conv_out)
+        mean = torch.empty((G, K), dtype=torch.float32, device=self.dev)
+        invstd, varu = torch.empty_like(mean), torch.empty_like(mean)
+        bnm = self._bn_module(bn)
+        fn = self.lib.pdf_bn_train_forward_bf16 if self.bf16 else self.lib.pdf_bn_train_forward
+        _lib.check(fn(G, goff.data_ptr(), max_rows, K, conv_out.data_ptr(), self.params[bn + ".weight"].data.data_ptr(),
+                      self.params[bn + ".bias"].data.data_ptr(), float(bnm.eps), _p(res.data if res else None), 1 if relu else 0, y.data_ptr(),
+                      mean.data_ptr(), invstd.data_ptr(), varu.data_ptr(), self._scratch(3 * G * K).data_ptr(), _lib.stream_ptr()),
+                   "pdf_bn_train_forward")
+        if self.update_running:
+            _lib.check(self.lib.pdf_bn_update_running(G, K, mean.data_ptr(), varu.data_ptr(), float(bnm.momentum),
+                                                      self.buffers[bn + ".running_mean"].data_ptr(), self.buffers[bn + ".running_var"].data_ptr(),
+                                                      _lib.stream_ptr()), "pdf_bn_update_running")
+            self.buffers[bn + ".num_batches_tracked"] += G
+        return y, goff, mean, invstd, max_rows
+
+    def _convbn(self, x: _Act, h: int, name: str, bn: str, relu: bool, res: Optional[_Act], groups) -> Tuple[_Act, int]:
+        cv = self.convs[name]
+        ho = (h + 2 * cv["pad"] - cv["k"]) // cv["stride"] + 1
+        n, K = x.n, cv["cout"]
+        op = self._op(n, h, x.c, cv, ho)
+        if self.bf16:
+            conv_out = torch.empty((n * ho * ho, K), dtype=torch.bfloat16, device=self.dev)
+            op.precision = _lib.PREC_BF16
+            op.d_in, op.d_weight, op.d_bias, op.d_out = x.data.data_ptr(), self.wk16[name].data_ptr(), self._zero_bias.data_ptr(), conv_out.data_ptr()
+        else:
+            conv_out = torch.empty((n * ho * ho, K), dtype=torch.float32, device=self.dev)
+            op.d_in, op.d_weight, op.d_out = x.data.data_ptr(), self.wk[name].data_ptr(), conv_out.data_ptr()
+        self._run_op(op)
+        y, goff, mean, invstd, max_rows = self._bn_forward(bn, conv_out, res, relu, groups, ho * ho)
+        out = _Act(y, n, ho * ho, K)
+        self.tape.append(("convbn", name, bn, x, conv_out, out, relu, res, op, goff, mean, invstd, h, max_rows))
+        return out, ho
+
+    def _stem_tc(self, x: torch.Tensor, n: int, groups) -> Tuple[_Act, int]:
+        """conv1 7x7/2 on the 3-channel f32 input as a tensor-core GEMM: patch matrix [M, 192] bf16 (147 columns + zero padding)
+        x W1^T [192, 64]; the same matrix is the X operand of the stem's weight gradient."""
+        S = self.S
+        ho = (S + 6 - 7) // 2 + 1
+        patches = torch.empty((n * ho * ho, 192), dtype=torch.bfloat16, device=self.dev)
+        _lib.check(self.lib.pdf_stem_im2col3_bf16(n, S, S, x.data_ptr(), patches.data_ptr(), _lib.stream_ptr()), "pdf_stem_im2col3_bf16")
+        conv_out = torch.empty((n * ho * ho, 64), dtype=torch.bfloat16, device=self.dev)
+        op = _lib.Op()
+        op.kind, op.precision = _lib.OP_CONV, _lib.PREC_BF16
+        op.n, op.h, op.w, op.c, op.k, op.r, op.s, op.stride, op.pad, op.ho, op.wo, op.relu = n, ho, ho, 192, 64, 1, 1, 1, 0, ho, ho, 0
+        op.d_in, op.d_weight, op.d_bias, op.d_out = patches.data_ptr(), self.wk16["conv1"].data_ptr(), self._zero_bias.data_ptr(), conv_out.data_ptr()
+        self._run_op(op)
+        y, goff, mean, invstd, max_rows = self._bn_forward("bn1", conv_out, None, True, groups, ho * ho)
+        out = _Act(y, n, ho * ho, 64)
+        self.tape.append(("stem", patches, conv_out, out, op, goff, mean, invstd, max_rows))
+        return out, ho
+
     def forward(self, x: torch.Tensor, groups: Sequence[int], update_running: bool = True) -> torch.Tensor:
         """x [n, S, S, 3] f32 NHWC (the reference's (x-mean)/std 3-channel input); groups: image offsets [0, ..., n] of the
         BatchNorm groups.  Returns the embeddings [n, D] f32 and records the tape for backward()."""
         n = int(x.shape[0])
         assert groups[0] == 0 and groups[-1] == n
         self.tape, self._goff_cache, self.update_running = [], {}, bool(update_running)
-        t, h = self._convbn(_Act(x.contiguous(), n, self.S * self.S, 3), self.S, "conv1", "bn1", True, None, groups)
+        prec = _lib.PREC_BF16 if self.bf16 else _lib.PREC_F32
+        adt = torch.bfloat16 if self.bf16 else torch.float32
+        x = x.contiguous()
+        if self.bf16:
+            t, h = self._stem_tc(x, n, groups)
+        else:
+            t, h = self._convbn(_Act(x, n, self.S * self.S, 3), self.S, "conv1", "bn1", True, None, groups)
         ho = (h + 2 - 3) // 2 + 1
-        pooled = torch.empty((n * ho * ho, 64), dtype=torch.float32, device=self.dev)
-        op = _lib.Op()
-        op.kind, op.precision = _lib.OP_MAXPOOL, _lib.PREC_F32
-        op.n, op.h, op.w, op.c, op.ho, op.wo = n, h, h, 64, ho, ho
-        op.d_in, op.d_out = t.data.data_ptr(), pooled.data_ptr()
-        plan = C.c_void_p()
-        _lib.check(self.lib.pdf_plan_create(C.byref(plan), (_lib.Op * 1)(op), 1), "pdf_plan_create")
-        _lib.check(self.lib.pdf_plan_run(plan, _lib.stream_ptr()), "pdf_plan_run")
-        self.lib.pdf_plan_destroy(plan)
+        pooled = torch.empty((n * ho * ho, 64), dtype=adt, device=self.dev)
+        widx = None
+        if self.bf16:                              # records the winning window position: the backward is a gather through it
+            widx = torch.empty((n * ho * ho, 64), dtype=torch.uint8, device=self.dev)
+            _lib.check(self.lib.pdf_maxpool_train_forward_bf16(n, h, h, 64, t.data.data_ptr(), pooled.data_ptr(), widx.data_ptr(), _lib.stream_ptr()),
+                       "pdf_maxpool_train_forward_bf16")
+        else:
+            self._pool_op(_lib.OP_MAXPOOL, prec, n, h, 64, ho, t.data.data_ptr(), pooled.data_ptr())
         t2 = _Act(pooled, n, ho * ho, 64)
-        self.tape.append(("maxpool", t, t2, h))
+        self.tape.append(("maxpool", t, t2, h, widx))
         t, h = t2, ho
         for li, nblocks in enumerate(self.layers, start=1):
             for bi in range(nblocks):
@@ -423,63 +485,68 @@ class ResNetTrainer:
                     o, h = self._convbn(o, h, pfx + ".conv2", pfx + ".bn2", True, None, groups)
                     o, h = self._convbn(o, h, pfx + ".conv3", pfx + ".bn3", True, idn, groups)
                 t = o
-        emb = self._avgpool(t)
+        emb = torch.empty((t.n, t.c), dtype=torch.float32, device=self.dev)
+        hw = int(round(t.hw ** 0.5))
+        self._pool_op(_lib.OP_AVGPOOL, prec, t.n, hw, t.c, 1, t.data.data_ptr(), emb.data_ptr())
         self.tape.append(("avgpool", t))
         return emb
 
-    def _avgpool(self, t: _Act) -> torch.Tensor:
-        out = torch.empty((t.n, t.c), dtype=torch.float32, device=self.dev)
-        op = _lib.Op()
-        op.kind, op.precision = _lib.OP_AVGPOOL, _lib.PREC_F32
-        hw = int(round(t.hw ** 0.5))
-        op.n, op.h, op.w, op.c = t.n, hw, hw, t.c
-        op.d_in, op.d_out = t.data.data_ptr(), out.data_ptr()
-        plan = C.c_void_p()
-        _lib.check(self.lib.pdf_plan_create(C.byref(plan), (_lib.Op * 1)(op), 1), "pdf_plan_create")
-        _lib.check(self.lib.pdf_plan_run(plan, _lib.stream_ptr()), "pdf_plan_run")
-        self.lib.pdf_plan_destroy(plan)
-        return out
-
     # -- backward --------------------------------------------------------------------------------------
+    def _bn_backward(self, bn, out: _Act, conv_out, relu, res: Optional[_Act], goff, mean, invstd, max_rows) -> torch.Tensor:
+        """BatchNorm (+ReLU, + residual branch) backward: returns d(conv output) in the path's storage type; the residual
+        branch's gradient is written / accumulated into res.grad."""
+        G, K = int(mean.shape[0]), int(mean.shape[1])
+        dconv = torch.empty_like(conv_out)
+        dres, acc = None, 0
+        if res is not None:
+            if res.grad is None:
+                res.grad = torch.empty_like(res.data)
+            else:
+                acc = 1
+            dres = res.grad
+        fn = self.lib.pdf_bn_train_backward_bf16 if self.bf16 else self.lib.pdf_bn_train_backward
+        _lib.check(fn(G, goff.data_ptr(), max_rows, K, out.grad.data_ptr(), out.data.data_ptr(), conv_out.data_ptr(),
+                      self.params[bn + ".weight"].data.data_ptr(), mean.data_ptr(), invstd.data_ptr(), 1 if relu else 0,
+                      self._scratch(3 * G * K).data_ptr(), dconv.data_ptr(), _p(dres), acc, self.grad[bn + ".weight"].data_ptr(),
+                      self.grad[bn + ".bias"].data_ptr(), _lib.stream_ptr()), "pdf_bn_train_backward")
+        out.grad = None
+        return dconv
+
     def backward(self, demb: torch.Tensor):
         """demb [n, D] f32: gradient of the loss w.r.t. the embeddings.  Accumulates parameter gradients into self.grad
         (torchvision layout)."""
         s = _lib.stream_ptr()
         lib = self.lib
         gwk: Dict[str, torch.Tensor] = {}
+        if self.bf16:
+            self._gw_flat.zero_()
         for entry in reversed(self.tape):
             kind = entry[0]
             if kind == "avgpool":
                 t = entry[1]
                 t.grad = torch.empty_like(t.data)
-                _lib.check(lib.pdf_avgpool_backward_f32(t.n, t.hw, t.c, demb.contiguous().data_ptr(), t.grad.data_ptr(), s), "pdf_avgpool_backward_f32")
+                fn = lib.pdf_avgpool_backward_bf16 if self.bf16 else lib.pdf_avgpool_backward_f32
+                _lib.check(fn(t.n, t.hw, t.c, demb.contiguous().data_ptr(), t.grad.data_ptr(), s), "pdf_avgpool_backward")
             elif kind == "maxpool":
-                _, tin, tout, h = entry
+                _, tin, tout, h, widx = entry
                 tin.grad = torch.empty_like(tin.data)
-                _lib.check(lib.pdf_maxpool_backward_f32(tin.n, h, h, tin.c, tin.data.data_ptr(), tout.grad.data_ptr(), tin.grad.data_ptr(), s),
-                           "pdf_maxpool_backward_f32")
+                if self.bf16:
+                    _lib.check(lib.pdf_maxpool_backward_bf16(tin.n, h, h, tin.c, widx.data_ptr(), tout.grad.data_ptr(), tin.grad.data_ptr(), s),
+                               "pdf_maxpool_backward_bf16")
+                else:
+                    _lib.check(lib.pdf_maxpool_backward_f32(tin.n, h, h, tin.c, tin.data.data_ptr(), tout.grad.data_ptr(), tin.grad.data_ptr(), s),
+                               "pdf_maxpool_backward_f32")
                 tout.grad = None
+            elif kind == "stem":                                     # tensor path: the network input needs no gradient
+                _, patches, conv_out, out, op, goff, mean, invstd, max_rows = entry
+                dconv = self._bn_backward("bn1", out, conv_out, True, None, goff, mean, invstd, max_rows)
+                _lib.check(lib.pdf_conv_wgrad_bf16(C.byref(op), patches.data_ptr(), dconv.data_ptr(), self._gw["conv1"].data_ptr(), s),
+                           "pdf_conv_wgrad_bf16")
             else:
                 _, name, bn, x, conv_out, out, relu, res, op, goff, mean, invstd, h, max_rows = entry
-                G, K = int(mean.shape[0]), int(mean.shape[1])
-                tc = self._tc(name)
-                dconv = torch.empty_like(conv_out)
-                dconv16 = torch.empty(conv_out.shape, dtype=torch.bfloat16, device=self.dev) if tc else None
-                dres, acc = None, 0
-                if res is not None:
-                    if res.grad is None:
-                        res.grad = torch.empty_like(res.data)
-                    else:
-                        acc = 1
-                    dres = res.grad
-                _lib.check(lib.pdf_bn_train_backward(G, goff.data_ptr(), max_rows, K, out.grad.data_ptr(), out.data.data_ptr(), conv_out.data_ptr(),
-                                                     self.params[bn + ".weight"].data.data_ptr(), mean.data_ptr(), invstd.data_ptr(),
-                                                     1 if relu else 0, self._scratch(3 * G * K).data_ptr(), dconv.data_ptr(), _p(dconv16),
-                                                     _p(dres), acc, self.grad[bn + ".weight"].data_ptr(), self.grad[bn + ".bias"].data_ptr(), s),
-                           "pdf_bn_train_backward")
-                out.grad = None
-                if tc:
-                    self._backward_conv_tc(name, op, x, dconv, dconv16, h, gwk)
+                dconv = self._bn_backward(bn, out, conv_out, relu, res, goff, mean, invstd, max_rows)
+                if self.bf16:
+                    self._backward_conv_tc(name, op, x, dconv, h)
                     continue
                 if name not in gwk:
                     gwk[name] = torch.zeros_like(self.wk[name])
@@ -490,42 +557,51 @@ class ResNetTrainer:
                         x.grad = torch.empty_like(x.data)
                     _lib.check(lib.pdf_conv_dgrad_f32(C.byref(op), dconv.data_ptr(), self.wk[name].data_ptr(), x.grad.data_ptr(), acc, s),
                                "pdf_conv_dgrad_f32")
-        for name, gw in gwk.items():                                 # -> torchvision [K,C,R,S] (layout change only; one backward per
-            if self._tc(name):                                       #    zero_grad, as the reference's step)
-                self.grad[name + ".weight"].copy_(gw.permute(0, 3, 1, 2))       # tensor path accumulates [K,R,S,C]
-            else:
-                self.grad[name + ".weight"].copy_(gw.permute(3, 2, 0, 1))       # FP32 path accumulates [R,S,C,K]
+        # -> torchvision [K,C,R,S] (layout change only; one backward per zero_grad, as the reference's step)
+        if self.bf16:
+            for name, gw in self._gw.items():                        # tensor path accumulated [K,R,S,C]
+                if name == "conv1":
+                    self.grad[name + ".weight"].copy_(gw[:, :147].reshape(gw.shape[0], 7, 7, 3).permute(0, 3, 1, 2))
+                else:
+                    self.grad[name + ".weight"].copy_(gw.permute(0, 3, 1, 2))
+        for name, gw in gwk.items():                                 # FP32 path accumulated [R,S,C,K]
+            self.grad[name + ".weight"].copy_(gw.permute(3, 2, 0, 1))
         self.tape = []
 
-    def _backward_conv_tc(self, name: str, op: "_lib.Op", x: _Act, dconv: torch.Tensor, dconv16: torch.Tensor, h: int, gwk) -> None:
-        """Weight and data gradient of one convolution on the tensor cores (bf16 operands, f32 results).
+    def _backward_conv_tc(self, name: str, op: "_lib.Op", x: _Act, dconv: torch.Tensor, h: int) -> None:
+        """Weight and data gradient of one convolution on the tensor cores (bf16 operands and results, f32 accumulation).
         wgrad: dW[k][r][s][c] += dY^T im2col(X) (wgrad_tc.cu).  dgrad: a stride-1 convolution of dY with the 180-degree-rotated,
-        transposed filter (the forward implicit-GEMM kernels, pad' = R-1-pad); for stride 2 dY is first zero-dilated to the input's
-        size (dY[p,q] at (2p, 2q)), which turns the transposed convolution into the same stride-1 form."""
+        transposed filter through the forward implicit-GEMM kernels (pad' = R-1-pad), a gradient already present in x.grad riding
+        in as the kernel's residual operand; stride-2 3x3: dY zero-dilated to the input's size first (dY[p,q] at (2p, 2q));
+        stride-2 1x1 (downsample): a GEMM on dY whose result is scatter-added onto the even pixels."""
         lib, s = self.lib, _lib.stream_ptr()
         cv = self.convs[name]
         n, C_in, K, R, stride, pad, ho = x.n, x.c, cv["cout"], cv["k"], cv["stride"], cv["pad"], int(op.ho)
-        if name not in gwk:
-            gwk[name] = torch.zeros((K, R, R, C_in), dtype=torch.float32, device=self.dev)
-        gop = self._op(n, h, C_in, cv, ho)
-        gop.precision = _lib.PREC_BF16
-        _lib.check(lib.pdf_conv_wgrad_bf16(C.byref(gop), self._b16(x).data_ptr(), dconv16.data_ptr(), gwk[name].data_ptr(), s), "pdf_conv_wgrad_bf16")
+        _lib.check(lib.pdf_conv_wgrad_bf16(C.byref(op), x.data.data_ptr(), dconv.data_ptr(), self._gw[name].data_ptr(), s), "pdf_conv_wgrad_bf16")
+        assert stride in (1, 2), name
+        dop = _lib.Op()
+        dop.kind, dop.precision = _lib.OP_CONV, _lib.PREC_BF16
+        dop.c, dop.k, dop.r, dop.s, dop.stride, dop.relu = K, C_in, R, R, 1, 0
+        dop.d_weight, dop.d_bias = self.wrot16[name].data_ptr(), self._zero_bias.data_ptr()
+        if stride == 2 and R == 1:
+            tmp = torch.empty((n * ho * ho, C_in), dtype=torch.bfloat16, device=self.dev)
+            dop.n, dop.h, dop.w, dop.pad, dop.ho, dop.wo = n, ho, ho, 0, ho, ho
+            dop.d_in, dop.d_out = dconv.data_ptr(), tmp.data_ptr()
+            self._run_op(dop)
+            if x.grad is None:
+                x.grad = torch.zeros_like(x.data)
+            _lib.check(lib.pdf_scatter_add2_bf16(n, ho, ho, C_in, h, h, tmp.data_ptr(), x.grad.data_ptr(), s), "pdf_scatter_add2_bf16")
+            return
         if stride == 1:
-            src, hs = dconv16, ho
+            src, hs = dconv, ho
         else:
             src, hs = torch.empty((n * h * h, K), dtype=torch.bfloat16, device=self.dev), h
-            _lib.check(lib.pdf_dilate_bf16(n, ho, ho, K, h, h, stride, 0, dconv.data_ptr(), src.data_ptr(), s), "pdf_dilate_bf16")
-        dop = _lib.Op()
-        dop.kind, dop.precision, dop.out_f32 = _lib.OP_CONV, _lib.PREC_BF16, 1
-        dop.n, dop.h, dop.w, dop.c, dop.k, dop.r, dop.s = n, hs, hs, K, C_in, R, R
-        dop.stride, dop.pad, dop.ho, dop.wo, dop.relu = 1, R - 1 - pad, h, h, 0
+            _lib.check(lib.pdf_dilate2_bf16(n, ho, ho, K, h, h, dconv.data_ptr(), src.data_ptr(), s), "pdf_dilate2_bf16")
+        dop.n, dop.h, dop.w, dop.pad, dop.ho, dop.wo = n, hs, hs, R - 1 - pad, h, h
         assert hs + 2 * (R - 1 - pad) - R + 1 == h, (name, hs, h)
-        if x.grad is None:
-            x.grad = torch.empty_like(x.data)
-            dst, tmp = x.grad, None
-        else:
-            dst = tmp = torch.empty_like(x.data)
-        dop.d_in, dop.d_weight, dop.d_bias, dop.d_out = src.data_ptr(), self.wrot16[name].data_ptr(), self._zero_bias.data_ptr(), dst.data_ptr()
+        dst = torch.empty_like(x.data)
+        dop.d_in, dop.d_out = src.data_ptr(), dst.data_ptr()
+        if x.grad is not None:
+            dop.d_residual = x.grad.data_ptr()                       # accumulate: out = conv + the gradient already there
         self._run_op(dop)
-        if tmp is not None:
-            _lib.check(lib.pdf_add_f32(x.grad.data_ptr(), tmp.data_ptr(), tmp.numel(), s), "pdf_add_f32")
+        x.grad = dst

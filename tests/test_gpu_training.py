@@ -158,7 +158,7 @@ def test_backbone_train_tensor_path_vs_autograd(arch, n, S, groups):
     x = torch.randn(n, 3, S, S, generator=g).cuda()
     Rw = torch.randn(n, 512 if arch == "resnet18" else 2048, generator=g).cuda()
     rt = ResNetTrainer(net, arch, S, precision="bf16")
-    assert rt._tc("layer1.0.conv1") and not rt._tc("conv1")
+    assert rt.bf16 and rt.wk16["conv1"].shape == (64, 192)
     emb = rt.forward(x.permute(0, 2, 3, 1).contiguous(), groups)
     rt.zero_grad()
     rt.backward(Rw)

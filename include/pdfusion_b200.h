@@ -103,6 +103,19 @@ int pdf_preprocess(const pdf_preproc_cfg* cfg, int batch, const float* d_raw, fl
                    pdf_stream_t stream);
 
 /* ------------------------------------------------------------------------------------------
+ * f4 -- the "simple" feature mode.  Replaces `_compute_simple_features` (data/openneuro_features.py:34-73): over vals =
+ * volume[volume > 0] (all voxels when none is positive) mean / std / min / max, np.median, np.percentile 10 / 90 / 1 / 99 (exact
+ * order statistics, numpy's float32 'linear' rule), the counts of np.histogram(np.clip(vals, p1, p99), bins, range=(p1, p99)) with
+ * its float32 edges, and the central-moment sums behind scipy.stats.skew / kurtosis.  The grid means of the same function are a
+ * second trilinear zoom: pdf_resample_stats with out_shape = grid.  d_vol [batch, voxels] f32 (a resampled volume each);
+ * d_out: batch * pdf_simple_stats_stride() doubles, per subject
+ *   0 n | 1 sum | 2 min | 3 max | 4..6 sum (v-mean)^2,3,4 | 7 median | 8 p10 | 9 p90 | 10 p1 | 11 p99 | 12 all-voxel fallback flag |
+ *   16 .. counts[hist_bins] | 16+hist_bins .. edges[hist_bins+1].
+ * ------------------------------------------------------------------------------------------ */
+int pdf_simple_stats_stride(void);
+int pdf_simple_stats(int batch, size_t voxels, int hist_bins, const float* d_vol, double* d_out, pdf_stream_t stream);
+
+/* ------------------------------------------------------------------------------------------
  * a6 -- test-time augmentation (`tta > 1`): data/openneuro_features.py:166-178,235-248 and
  * scripts/build_resnet2d_mil_embeddings.py:124-146.  The random draws (angle, translation, scale, shift and the
  * N(0, sigma) field) are made ON THE HOST with the reference's exact numpy calls and passed in as data; the

@@ -473,9 +473,44 @@ def gold_c45():
     print("c45.npz moe auc", json.loads(str(out["c4/metrics"]))["full_observation"]["roc_auc"], out["c4/probs"].shape)
 
 
+def gold_simple():
+    """The reference's `_compute_simple_features` and `load_simple_features` (data/openneuro_features.py:34-104) on seeded
+    synthetic volumes: the features of single resampled volumes (incl. a volume without positive voxels and a constant one) and
+    the parquet of a 3-row manifest (256x256x176 -> 96^3, default config + extra_stats)."""
+    out = {}
+    cases = {"brain48": (synthetic_volume(3, (64, 48, 44)), (48, 48, 48)), "brain96": (synthetic_volume(5, (120, 110, 100)), (96, 96, 96))}
+    rng = np.random.default_rng(11)
+    cases["nonpositive"] = ((-rng.random((40, 40, 40))).astype(np.float32), (32, 32, 32))
+    cases["constant"] = (np.full((36, 36, 36), 2.5, dtype=np.float32), (24, 24, 24))
+    cases["sparse"] = ((rng.random((50, 40, 30)) > 0.97).astype(np.float32) * rng.random((50, 40, 30)).astype(np.float32) * 900, (40, 40, 40))
+    for tag, (raw, tgt) in cases.items():
+        vol = _load_volume_npy_arr(raw, tgt)
+        out[f"{tag}/raw"] = raw
+        out[f"{tag}/target"] = np.array(tgt)
+        for bins, grid, extra in ((10, 8, False), (16, 4, True), (10, 0, True)):
+            out[f"{tag}/feats_{bins}_{grid}_{int(extra)}"] = of._compute_simple_features(vol, hist_bins=bins, grid_size=grid, extra_stats=extra)
+    of._load_volume = _load_volume_npy
+    with tempfile.TemporaryDirectory() as td:
+        manifest = write_synthetic_manifest(Path(td) / "vols", 3, start=40)
+        cfg = {"hist_bins": 10, "grid_size": 8, "target_shape": [96, 96, 96], "extra_stats": True}
+        df = of.load_simple_features(manifest, Path(td) / "cache", cfg)
+        out["manifest/start"], out["manifest/n"] = np.array(40), np.array(3)
+        out["manifest/cfg"] = np.array(json.dumps(cfg))
+        out["manifest/columns"] = np.array(list(df.columns))
+        out["manifest/feats"] = df[[c for c in df.columns if c.startswith("mri_feat_")]].values
+        out["manifest/file"] = np.array(sorted(p.name for p in (Path(td) / "cache").iterdir())[0].split("_")[0])
+    np.savez_compressed(GOLD / "simple.npz", **out)
+    print("simple.npz", {k: v.shape for k, v in out.items() if k.endswith("_0") or k == "manifest/feats"})
+
+
+def _load_volume_npy_arr(raw, target_shape):
+    d = np.nan_to_num(raw.astype(np.float32), nan=0.0, posinf=0.0, neginf=0.0)
+    return ndimage.zoom(d, [t / s for t, s in zip(target_shape, d.shape)], order=1)
+
+
 if __name__ == "__main__":
     GOLD.mkdir(parents=True, exist_ok=True)
-    which = sys.argv[1:] or ["preproc", "embed", "scripts", "heads", "tta", "ft", "c45"]
+    which = sys.argv[1:] or ["preproc", "embed", "scripts", "heads", "tta", "ft", "c45", "simple"]
     os.environ.setdefault("PYTHONHASHSEED", "0")
     for w in which:
         globals()[f"gold_{w}"]()

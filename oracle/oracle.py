@@ -136,6 +136,52 @@ def normalize_volume_for_resnet(vol: np.ndarray) -> np.ndarray:
 # ----------------------------------------------------------------------------------------
 # a3  _select_slices  (data/openneuro_features.py:134-151)
 # ----------------------------------------------------------------------------------------
+def uniform_histogram_counts(vals: np.ndarray, lo: np.float32, hi: np.float32, bins: int):
+    """Counts and float32 edges of np.histogram(vals, bins, range=(lo, hi)) for float32 values inside [lo, hi]
+    (numpy/lib/_histograms_impl.py, uniform-bin path): equal outer edges are widened by 0.5; the edges are
+    np.linspace(first, last, bins + 1) evaluated in float32 (arange * step + start, last edge = stop); after numpy's +-1
+    corrections a value sits in the bin with edges[i] <= v < edges[i+1], the last bin closed on the right."""
+    first, last = np.float32(lo), np.float32(hi)
+    if first == last:
+        first, last = np.float32(first - np.float32(0.5)), np.float32(last + np.float32(0.5))
+    step = np.float32(np.float32(last - first) / np.float32(bins))
+    edges = (np.arange(bins, dtype=np.float32) * step + first).astype(np.float32)
+    edges = np.concatenate([edges, np.array([last], dtype=np.float32)])
+    v = vals.astype(np.float32)
+    idx = np.searchsorted(edges[1:bins], v, side="right")            # interior edges <= v
+    return np.bincount(idx, minlength=bins).astype(np.int64), edges
+
+
+def simple_features(volume: np.ndarray, hist_bins: int = 10, grid_size: int = 8, extra_stats: bool = False) -> np.ndarray:
+    """`_compute_simple_features` (data/openneuro_features.py:34-73): statistics of the positive voxels (all voxels when there is
+    none), a density histogram of the values clipped to [p1, p99], the trilinear zoom of the volume to grid_size^3, optionally
+    skewness / excess kurtosis (scipy.stats defaults: biased moments, Fisher) and the entropy of the histogram."""
+    vol = volume.astype(np.float32)
+    sel = vol > 0
+    vals = vol[sel] if sel.any() else vol.reshape(-1)
+    s = np.sort(vals)
+    n = s.shape[0]
+    mean = np.float32(vals.astype(np.float64).sum() / n)
+    var = ((vals.astype(np.float64) - vals.astype(np.float64).mean()) ** 2).mean()
+    std = np.float32(np.sqrt(var))
+    median = s[n // 2] if n % 2 else np.float32(np.float32(s[n // 2 - 1] + s[n // 2]) / np.float32(2))
+    p10, p90 = percentile_linear(s, 10.0), percentile_linear(s, 90.0)
+    lo, hi = percentile_linear(s, 1.0), percentile_linear(s, 99.0)
+    counts, edges = uniform_histogram_counts(np.clip(vals, lo, hi), lo, hi, hist_bins)
+    hist = counts / np.array(np.diff(edges), float) / counts.sum()
+    feats = [float(mean), float(std), float(s[0]), float(s[-1]), float(median), float(p10), float(p90)] + hist.tolist()
+    if grid_size:
+        feats += zoom_trilinear(vol, (grid_size,) * 3).reshape(-1).tolist()
+    if extra_stats:
+        d = vals.astype(np.float64) - vals.astype(np.float64).mean()
+        m2, m3, m4 = (d ** 2).mean(), (d ** 3).mean(), (d ** 4).mean()
+        sk = float(np.nan_to_num(m3 / m2 ** 1.5 if m2 > 0 else np.nan, nan=0.0))
+        kt = float(np.nan_to_num(m4 / m2 ** 2 - 3.0 if m2 > 0 else np.nan, nan=0.0))
+        h = hist + 1e-12
+        feats += [sk, kt, float(-(h * np.log(h)).sum())]
+    return np.array(feats, dtype=np.float32)
+
+
 def linspace_indices(lo: int, hi: int, count: int) -> np.ndarray:
     """np.linspace(lo, hi, count).astype(int): f64 `i*step + lo`, last forced to hi, truncation."""
     if count <= 0:

@@ -170,10 +170,10 @@ def _decode_on_device(batch, dev) -> torch.Tensor:
 _PRE_CACHE: Dict[tuple, VolumePreprocessor] = {}
 
 
-def _preprocessor(in_shape, target_shape, axes=(2,), counts=(1,), input_size=8, mode=_lib.OUT_F32_NHWC3) -> VolumePreprocessor:
-    key = (tuple(in_shape), tuple(target_shape), tuple(axes), tuple(counts), int(input_size), mode, torch.cuda.current_device())
+def _preprocessor(in_shape, target_shape, axes=(2,), counts=(1,), input_size=8, mode=_lib.OUT_F32_NHWC3, max_batch: int = 1) -> VolumePreprocessor:
+    key = (tuple(in_shape), tuple(target_shape), tuple(axes), tuple(counts), int(input_size), mode, int(max_batch), torch.cuda.current_device())
     if key not in _PRE_CACHE:
-        _PRE_CACHE[key] = VolumePreprocessor(in_shape, target_shape, axes, counts, input_size, out_mode=mode, max_batch=1)
+        _PRE_CACHE[key] = VolumePreprocessor(in_shape, target_shape, axes, counts, input_size, out_mode=mode, max_batch=int(max_batch))
     return _PRE_CACHE[key]
 
 
@@ -401,14 +401,93 @@ def load_cnn_embeddings(manifest_path: Path, cache_dir: Path, config: Dict) -> p
     return pd.read_parquet(out_path)
 
 
+def _simple_features_device(vols: torch.Tensor, hist_bins: int, grid_size: int, extra_stats: bool) -> np.ndarray:
+    """`_compute_simple_features` for a batch of resampled volumes [B, T0, T1, T2] f32 resident on the device -> [B, F] f32.
+    The statistics come from `pdf_simple_stats` (one block per subject: exact order statistics by radix select, np.histogram's
+    bin rule, float64 moments); the grid means are a second scipy-exact trilinear zoom through K1a's resample kernel; the host
+    only assembles the feature vector the way the reference does (data/openneuro_features.py:34-73)."""
+    lib = _lib.load()
+    B = int(vols.shape[0])
+    shape = tuple(int(v) for v in vols.shape[1:])
+    stride = int(lib.pdf_simple_stats_stride())
+    out = torch.empty((B, stride), dtype=torch.float64, device=vols.device)
+    _lib.check(lib.pdf_simple_stats(B, shape[0] * shape[1] * shape[2], int(hist_bins), vols.data_ptr(), out.data_ptr(), _lib.stream_ptr()),
+               "pdf_simple_stats")
+    grid = None
+    if grid_size:
+        pre = _preprocessor(shape, (int(grid_size),) * 3, max_batch=B)
+        grid = pre.resample(vols).reshape(B, -1).cpu().numpy()
+    st = out.cpu().numpy()
+    feats = []
+    for b in range(B):
+        r = st[b]
+        n = r[0]
+        mean = np.float32(r[1] / n)
+        std = np.float32(np.sqrt(r[4] / n))
+        counts = r[16:16 + hist_bins]
+        edges = r[16 + hist_bins:16 + 2 * hist_bins + 1].astype(np.float32)
+        hist = counts / np.array(np.diff(edges), float) / counts.sum()          # np.histogram(density=True)
+        f = [float(mean), float(std), float(np.float32(r[2])), float(np.float32(r[3])), float(np.float32(r[7])), float(np.float32(r[8])),
+             float(np.float32(r[9]))]
+        f.extend(hist.tolist())
+        if grid is not None:
+            f.extend(grid[b].tolist())
+        if extra_stats:
+            m2, m3, m4 = r[4] / n, r[5] / n, r[6] / n
+            sk = float(np.nan_to_num(np.float32(m3 / m2 ** 1.5) if m2 > 0 else np.nan, nan=0.0))       # scipy.stats.skew (biased)
+            kt = float(np.nan_to_num(np.float32(m4 / m2 ** 2 - 3.0) if m2 > 0 else np.nan, nan=0.0))    # scipy.stats.kurtosis (Fisher)
+            h = hist + 1e-12
+            f.extend([sk, kt, float(-(h * np.log(h)).sum())])
+        feats.append(np.array(f, dtype=np.float32))
+    return np.stack(feats)
+
+
+def _compute_simple_features(volume: np.ndarray, hist_bins=10, grid_size=8, extra_stats: bool = False) -> np.ndarray:
+    """Histogram / grid statistics of one resampled volume (reference: data/openneuro_features.py:34-73), computed on the device."""
+    _lib.require_cuda()
+    vol = torch.from_numpy(np.ascontiguousarray(volume, dtype=np.float32)).cuda()
+    return _simple_features_device(vol[None], int(hist_bins), int(grid_size) if grid_size else 0, bool(extra_stats))[0]
+
+
 def load_simple_features(manifest_path: Path, cache_dir: Path, config: Dict) -> pd.DataFrame:
-    """Reader of the `simple` (histogram / grid statistics) cache, `features_<mh>_<ch>.parquet` (reference:
-    data/openneuro_features.py:75-104).  The reference computes a missing cache on the fly on the CPU; that feature mode is
-    outside the ResNet2D path and this package has no CPU fallback, so a missing cache is an error."""
+    """The `simple` feature mode: `features_<mh>_<ch>.parquet` with columns subject_id, session, label, mri_feat_0.. (reference:
+    data/openneuro_features.py:75-104, which loops `_load_volume` + `_compute_simple_features` per row on the CPU).  Here the rows go
+    through the device in batches: stored voxels -> decode -> scipy-exact resample -> statistics -> grid zoom."""
     cache_dir = Path(cache_dir)
     cache_dir.mkdir(parents=True, exist_ok=True)
     out_path = cache_dir / f"features_{_hash_file(manifest_path)}_{_hash_config(config)}.parquet"
-    if not out_path.exists():
-        raise FileNotFoundError(f"Simple features not found at {out_path}: build them with the reference's load_simple_features "
-                                "(this feature mode is not part of the B200 path).")
-    return pd.read_parquet(out_path)
+    if out_path.exists():
+        return pd.read_parquet(out_path)
+    _lib.require_cuda()
+    df = pd.read_csv(manifest_path)
+    hist_bins, grid_size = int(config.get("hist_bins", 10)), int(config.get("grid_size", 8))
+    target_shape = tuple(int(v) for v in config.get("target_shape", (96, 96, 96)))
+    extra_stats = bool(config.get("extra_stats", False))
+    dev = torch.device("cuda", torch.cuda.current_device())
+    bsz = max(1, int(os.environ.get("PD_FUSION_B200_SUBJECT_BATCH", "8")))
+    paths = df["t1wbrain_path"].tolist()
+    reader = _ReadAhead(paths, 0, len(paths), window=2 * bsz)
+    feats: List[np.ndarray] = []
+    i = 0
+    while i < len(paths):
+        first = reader.get(i)
+        batch, j = [first], i + 1
+        while j < len(paths) and len(batch) < bsz:
+            nxt = reader.get(j)
+            if nxt.key() != first.key():
+                break
+            batch.append(nxt)
+            j += 1
+        reader.release(i, j)
+        raw = _decode_on_device(batch, dev)
+        zoomed = _preprocessor(first.shape, target_shape, max_batch=bsz).resample(raw)
+        feats.append(_simple_features_device(zoomed, hist_bins, grid_size, extra_stats))
+        i = j
+    F = np.concatenate(feats, axis=0).astype(np.float64)          # the reference stores python floats -> float64 columns
+    cols = {"subject_id": df["subject_id"].values, "session": df["session"].values, "label": df["label"].astype(int).values}
+    cols.update({f"mri_feat_{k}": F[:, k] for k in range(F.shape[1])})
+    feat_df = pd.DataFrame(cols)
+    tmp = out_path.with_name(out_path.name + f".tmp{os.getpid()}")
+    feat_df.to_parquet(tmp, index=False)
+    os.replace(tmp, out_path)
+    return feat_df

@@ -188,3 +188,31 @@ def test_oracle_moe_c4_dims_vs_reference(golden):
         mk = masks[s].astype(np.float32)
         p = O.moe_predict_proba(sd, {m: X[m] * mk[:, i:i + 1] for i, m in enumerate(mods)}, mk)
         np.testing.assert_allclose(p, g["c4/probs"][s], atol=5e-6, rtol=0)
+
+
+SIMPLE_CASES = ["brain48", "brain96", "nonpositive", "constant", "sparse"]
+SIMPLE_CFGS = [(10, 8, False), (16, 4, True), (10, 0, True)]
+
+
+def check_simple_features(got, want, bins, grid, extra):
+    """Layout: [mean, std, min, max, median, p10, p90 | hist[bins] | grid^3 | skew, kurtosis, entropy].  Order statistics, the grid
+    zoom and the histogram (exact counts over exact float32 edges) are bit-exact; the float32 pairwise sums behind numpy's mean /
+    std and scipy's moments are reproduced to 1e-5 relative (float64 sums here)."""
+    assert got.shape == want.shape and got.dtype == np.float32
+    np.testing.assert_allclose(got[:2], want[:2], rtol=2e-5, atol=1e-6)
+    assert np.array_equal(got[2:7], want[2:7]), (got[2:7], want[2:7])
+    assert np.array_equal(got[7:7 + bins], want[7:7 + bins]), (got[7:7 + bins], want[7:7 + bins])
+    g3 = grid ** 3
+    assert np.array_equal(got[7 + bins:7 + bins + g3], want[7 + bins:7 + bins + g3])
+    if extra:
+        np.testing.assert_allclose(got[-3:-1], want[-3:-1], rtol=2e-3, atol=2e-3)
+        np.testing.assert_allclose(got[-1], want[-1], rtol=1e-6, atol=1e-7)
+
+
+@pytest.mark.parametrize("case", SIMPLE_CASES)
+def test_simple_features_vs_reference(golden, case):
+    """oracle.simple_features against the reference's `_compute_simple_features` outputs (data/openneuro_features.py:34-73)."""
+    g = golden("simple")
+    vol = O.load_volume(g[f"{case}/raw"], tuple(int(v) for v in g[f"{case}/target"]))
+    for bins, grid, extra in SIMPLE_CFGS:
+        check_simple_features(O.simple_features(vol, bins, grid, extra), g[f"{case}/feats_{bins}_{grid}_{int(extra)}"], bins, grid, extra)

@@ -116,6 +116,26 @@ int pdf_simple_stats_stride(void);
 int pdf_simple_stats(int batch, size_t voxels, int hist_bins, const float* d_vol, double* d_out, pdf_stream_t stream);
 
 /* ------------------------------------------------------------------------------------------
+ * f4 -- the "cnn3d" feature mode (scripts/build_cnn3d_embeddings.py:28-88, 132-156): pieces of the 3-D conv auto-encoder that are not
+ * a 2-D kernel already.  Channels-last [N, D, H, W, C] f32.  The 3x3x3 convolutions run depth-decomposed through the FP32 2-D
+ * kernels (pdf_plan_* with residual accumulation, pdf_conv_dgrad_f32, pdf_conv_wgrad_f32), the 2x2x2 stride-2 transposed
+ * convolutions as pdf_gemm_f32 + pixel shuffle.
+ * pdf_maxpool3d_forward: MaxPool3d(2) with the winner's position (i*4+j*2+k, first maximum in scan order) -> d_idx u8; backward
+ *   scatters through it.  pdf_shuffle2_3d: y[n,2d+i,2h+j,2w+k,co] = act(t[v,(i*4+j*2+k)*cout+co] + bias[co]); pdf_unshuffle2_3d: its
+ *   backward (ReLU mask from d_y).  pdf_mse_train: d_loss[0] += mean (p-t)^2, d_dpred (or NULL) = 2(p-t)/n.
+ * pdf_standardize_volume: load_volume's (v - mean) / (std + 1e-6) over the positive voxels (statistics rows of pdf_simple_stats;
+ *   volumes without a positive voxel pass through).
+ * ------------------------------------------------------------------------------------------ */
+int pdf_maxpool3d_forward(int n, int d, int h, int w, int c, const float* d_x, float* d_y, uint8_t* d_idx, pdf_stream_t stream);
+int pdf_maxpool3d_backward(int n, int d, int h, int w, int c, const uint8_t* d_idx, const float* d_dy, float* d_dx, pdf_stream_t stream);
+int pdf_shuffle2_3d(int n, int d, int h, int w, int cout, const float* d_t, const float* d_bias, int relu, float* d_y, pdf_stream_t stream);
+int pdf_unshuffle2_3d(int n, int d, int h, int w, int cout, const float* d_dy, const float* d_y, int relu, float* d_dt, pdf_stream_t stream);
+int pdf_relu_f32(float* d_x, size_t n, pdf_stream_t stream);
+int pdf_mse_train(size_t n, const float* d_pred, const float* d_target, float* d_loss, float* d_dpred, pdf_stream_t stream);
+int pdf_standardize_volume(int batch, size_t voxels, const float* d_x, const double* d_stats, int stats_stride, float* d_y,
+                           pdf_stream_t stream);
+
+/* ------------------------------------------------------------------------------------------
  * a6 -- test-time augmentation (`tta > 1`): data/openneuro_features.py:166-178,235-248 and
  * scripts/build_resnet2d_mil_embeddings.py:124-146.  The random draws (angle, translation, scale, shift and the
  * N(0, sigma) field) are made ON THE HOST with the reference's exact numpy calls and passed in as data; the

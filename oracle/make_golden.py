@@ -503,6 +503,48 @@ def gold_simple():
     print("simple.npz", {k: v.shape for k, v in out.items() if k.endswith("_0") or k == "manifest/feats"})
 
 
+def gold_cnn3d():
+    """The UNMODIFIED reference script scripts/build_cnn3d_embeddings.py on six small synthetic volumes (CPU): the only patch is a
+    stand-in `nibabel` module whose load(path).get_fdata() returns the .npy array as float64 (nibabel is not installed here; the
+    script imports it at module top).  Stores the embeddings parquet's values and the state the run started from / ended with."""
+    import types
+    nib = types.ModuleType("nibabel")
+
+    class _Img:
+        def __init__(self, p):
+            self._p = p
+
+        def get_fdata(self):
+            return np.load(self._p).astype(np.float64)
+
+    nib.load = lambda p: _Img(p)
+    sys.modules["nibabel"] = nib
+    out = {}
+    shape, target, n, epochs, bs, seed = (40, 36, 32), [16, 16, 16], 6, 2, 4, 42
+    with tempfile.TemporaryDirectory() as td:
+        manifest = write_synthetic_manifest(Path(td) / "vols", n, shape=shape, start=60)
+        od = Path(td) / "out"
+        args = ["--target-shape"] + [str(v) for v in target] + ["--embedding-dim", "32", "--epochs", str(epochs), "--batch-size", str(bs),
+                                                                  "--lr", "0.001", "--seed", str(seed)]
+        argv = sys.argv
+        sys.argv = ["build_cnn3d_embeddings.py", "--manifest", str(manifest), "--out-dir", str(od)] + args
+        try:
+            runpy.run_path(str(REF / "scripts" / "build_cnn3d_embeddings.py"), run_name="__main__")
+        finally:
+            sys.argv = argv
+        pq = sorted(od.glob("*.parquet"))[0]
+        import pandas as pd
+        df = pd.read_parquet(pq)
+        out["columns"] = np.array(list(df.columns))
+        out["emb"] = df[[c for c in df.columns if c.startswith("mri_cnn_")]].values.astype(np.float32)
+        out["file_prefix"] = np.array(pq.name.split("_")[0])
+        out["argv"] = np.array(args)
+        out["spec"] = np.array(json.dumps({"shape": shape, "target": target, "n": n, "start": 60, "epochs": epochs, "batch_size": bs, "seed": seed,
+                                           "embedding_dim": 32}))
+    np.savez_compressed(GOLD / "cnn3d.npz", **out)
+    print("cnn3d.npz", out["emb"].shape, float(np.abs(out["emb"]).mean()))
+
+
 def _load_volume_npy_arr(raw, target_shape):
     d = np.nan_to_num(raw.astype(np.float32), nan=0.0, posinf=0.0, neginf=0.0)
     return ndimage.zoom(d, [t / s for t, s in zip(target_shape, d.shape)], order=1)
@@ -510,7 +552,7 @@ def _load_volume_npy_arr(raw, target_shape):
 
 if __name__ == "__main__":
     GOLD.mkdir(parents=True, exist_ok=True)
-    which = sys.argv[1:] or ["preproc", "embed", "scripts", "heads", "tta", "ft", "c45", "simple"]
+    which = sys.argv[1:] or ["preproc", "embed", "scripts", "heads", "tta", "ft", "c45", "simple", "cnn3d"]
     os.environ.setdefault("PYTHONHASHSEED", "0")
     for w in which:
         globals()[f"gold_{w}"]()

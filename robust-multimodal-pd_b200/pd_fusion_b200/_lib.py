@@ -131,6 +131,13 @@ PROTOTYPES = {
     "pdf_bn_train_backward": (C.c_int, [C.c_int, _P, C.c_int, C.c_int, _P, _P, _P, _P, _P, _P, C.c_int, _P, _P, _P, C.c_int, _P, _P, _P]),
     "pdf_bn_train_forward_bf16": (C.c_int, [C.c_int, _P, C.c_int, C.c_int, _P, _P, _P, C.c_float, _P, C.c_int, _P, _P, _P, _P, _P, _P]),
     "pdf_bn_train_backward_bf16": (C.c_int, [C.c_int, _P, C.c_int, C.c_int, _P, _P, _P, _P, _P, _P, C.c_int, _P, _P, _P, C.c_int, _P, _P, _P]),
+    "pdf_maxpool3d_forward": (C.c_int, [C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, _P, _P, _P, _P]),
+    "pdf_maxpool3d_backward": (C.c_int, [C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, _P, _P, _P, _P]),
+    "pdf_shuffle2_3d": (C.c_int, [C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, _P, _P, C.c_int, _P, _P]),
+    "pdf_unshuffle2_3d": (C.c_int, [C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, _P, _P, C.c_int, _P, _P]),
+    "pdf_relu_f32": (C.c_int, [_P, C.c_size_t, _P]),
+    "pdf_mse_train": (C.c_int, [C.c_size_t, _P, _P, _P, _P, _P]),
+    "pdf_standardize_volume": (C.c_int, [C.c_int, C.c_size_t, _P, _P, C.c_int, _P, _P]),
     "pdf_simple_stats_stride": (C.c_int, []),
     "pdf_simple_stats": (C.c_int, [C.c_int, C.c_size_t, C.c_int, _P, _P, _P]),
     "pdf_maxpool_train_forward_bf16": (C.c_int, [C.c_int, C.c_int, C.c_int, C.c_int, _P, _P, _P, _P]),

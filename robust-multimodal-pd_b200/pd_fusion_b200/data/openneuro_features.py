@@ -391,8 +391,8 @@ def load_resnet2d_mil_embeddings(manifest_path: Path, cache_dir: Path, config: D
 
 
 def load_cnn_embeddings(manifest_path: Path, cache_dir: Path, config: Dict) -> pd.DataFrame:
-    """Reader of the `cnn3d` cache (reference: data/openneuro_features.py:106-119); the builder of that feature mode
-    (scripts/build_cnn3d_embeddings.py, a 3-D conv auto-encoder) is outside the ResNet2D path and not rebuilt here."""
+    """Reader of the `cnn3d` cache (reference: data/openneuro_features.py:106-119); its builder is scripts/build_cnn3d_embeddings.py
+    (the 3-D conv auto-encoder on the native kernels of pd_fusion_b200/cnn3d.py)."""
     cache_dir = Path(cache_dir)
     cache_dir.mkdir(parents=True, exist_ok=True)
     out_path = cache_dir / f"embeddings_{_hash_file(manifest_path)}_{_hash_config(config)}.parquet"

@@ -7,15 +7,17 @@
 //           the attention scores come straight out of the epilogue (one thread owns one instance row)
 //
 // The bags [n_bags * L, D] are the only large operand (4*L*D bytes per subject): they are read ONCE from HBM by
-// TMA; the weight matrix is re-streamed from L2 per 128-row tile.  Warp roles as in conv_tc.cu: TMA producer, single-thread
-// MMA issuer, 4 epilogue warps, two TMEM accumulator sets, persistent over row tiles.
+// TMA; the weight matrix is re-streamed from L2 per row tile.  Warp roles as in conv_tc.cu: TMA producer, single-thread
+// MMA issuer, 4 epilogue warps, persistent over row tiles.  Two tile shapes: MT = 1 (128 rows, two TMEM accumulator sets: the
+// epilogue of tile i overlaps the MMAs of tile i+1), the default, and MT = 2 (256 rows against ONE pass of the weight k-blocks,
+// all 512 TMEM columns as one accumulator set), an opt-in that halves the weight share of the shared-memory fill but measured
+// no faster (pdf_debug_set_mil_mt).
 #include "tc_common.cuh"
 #include "ops.cuh"
 
 namespace pdf {
 
 constexpr int kTfK = 32;                       // f32 elements per 128-byte swizzle row
-constexpr int kTfStages = 4;
 
 struct TfParams {
   int M, N, K, mode, gated, A;
@@ -39,10 +41,23 @@ __device__ __forceinline__ void umma_tf32_lo(uint32_t tmem_d, uint32_t a_lo, uin
       : "memory");
 }
 
-template <int BN>
+// hardware transcendental approximations (MUFU.TANH / MUFU.EX2 / MUFU.RCP, relative error ~2^-11 / 2^-22): the products feeding them
+// carry tf32's 10-bit mantissa already, and the score epilogue -- 128..256 tanh + sigmoid per instance row, one row per thread --
+// was 4x the GEMM it follows with libm's tanhf / expf
+__device__ __forceinline__ float tanh_fast(float x) {
+  float y;
+  asm("tanh.approx.f32 %0, %1;" : "=f"(y) : "f"(x));
+  return y;
+}
+__device__ __forceinline__ float sigmoid_fast(float x) { return __fdividef(1.0f, 1.0f + __expf(-x)); }
+
+template <int BN, int MT>
 __global__ void __launch_bounds__(192, 1)
 gemm_tf32_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant__ CUtensorMap tmap_b, const TfParams p) {
-  constexpr int kStage = kABytes + BN * 128;
+  constexpr int kStage = MT * kABytes + BN * 128;
+  constexpr int kTfStages = (MT == 1) ? 4 : 3;
+  constexpr int kAccSets = (2 * MT * BN <= 512) ? 2 : 1;
+  constexpr int kTmemCols = (kAccSets * MT * BN <= 64) ? 64 : (kAccSets * MT * BN <= 128 ? 128 : (kAccSets * MT * BN <= 256 ? 256 : 512));
   extern __shared__ uint8_t smem_raw[];
   const uint32_t raw_addr = smem_u32(smem_raw);
   const uint32_t base = (raw_addr + 1023u) & ~1023u;
@@ -64,7 +79,7 @@ gemm_tf32_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_consta
     for (int a = 0; a < 2; ++a) { mbar_init(bar_accfull + 8 * a, 1); mbar_init(bar_accempty + 8 * a, 4); }
     fence_barrier_init();
   }
-  if (warp == 1) tmem_alloc(smem_u32(tmem_slot), 2 * BN);
+  if (warp == 1) tmem_alloc(smem_u32(tmem_slot), kTmemCols);
   tc_fence_before();
   __syncthreads();
   tc_fence_after();
@@ -72,7 +87,7 @@ gemm_tf32_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_consta
   pdl_launch_dependents();
   pdl_wait();
 
-  const int m_tiles = (p.M + kBlockM - 1) / kBlockM;
+  const int m_tiles = (p.M + MT * kBlockM - 1) / (MT * kBlockM);
   const int num_kb = p.K / kTfK;
   if (warp == 0) {
     if (elect_one()) {
@@ -83,8 +98,10 @@ gemm_tf32_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_consta
           mbar_wait(bar_empty + 8 * stage, ((g / kTfStages) & 1u) ^ 1u);
           mbar_expect_tx(bar_full + 8 * stage, (uint32_t)kStage);
           const uint32_t sa = base + stage * kStage;
-          tma_load_2d(sa, &tmap_a, bar_full + 8 * stage, kb * kTfK, tile * kBlockM);
-          tma_load_2d(sa + kABytes, &tmap_b, bar_full + 8 * stage, kb * kTfK, 0);
+#pragma unroll
+          for (int mt = 0; mt < MT; ++mt)                           // (rows past M: zero fill)
+            tma_load_2d(sa + mt * kABytes, &tmap_a, bar_full + 8 * stage, kb * kTfK, (tile * MT + mt) * kBlockM);
+          tma_load_2d(sa + MT * kABytes, &tmap_b, bar_full + 8 * stage, kb * kTfK, 0);
         }
       }
     }
@@ -94,18 +111,21 @@ gemm_tf32_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_consta
       uint32_t g = 0;
       int it = 0;
       for (int tile = blockIdx.x; tile < m_tiles; tile += gridDim.x, ++it) {
-        const int acc = it & 1;
-        mbar_wait(bar_accempty + 8 * acc, (((uint32_t)(it >> 1)) & 1u) ^ 1u);
+        const int acc = it % kAccSets;
+        mbar_wait(bar_accempty + 8 * acc, (((uint32_t)(it / kAccSets)) & 1u) ^ 1u);
         tc_fence_after();
-        const uint32_t d0 = tmem_base + (uint32_t)(acc * BN);
+        const uint32_t d0 = tmem_base + (uint32_t)(acc * MT * BN);
         for (int kb = 0; kb < num_kb; ++kb, ++g) {
           const uint32_t stage = g % kTfStages;
           mbar_wait(bar_full + 8 * stage, (g / kTfStages) & 1u);
           tc_fence_after();
-          const uint32_t a_lo = smem_desc_lo(base + stage * kStage), b_lo = a_lo + (uint32_t)(kABytes / 16);
+          const uint32_t a_lo = smem_desc_lo(base + stage * kStage), b_lo = a_lo + (uint32_t)(MT * kABytes / 16);
 #pragma unroll
-          for (int k = 0; k < 4; ++k)    // K = 8 f32 = 32 bytes per instruction
-            umma_tf32_lo(d0, a_lo + (uint32_t)(k * 2), b_lo + (uint32_t)(k * 2), idesc, (kb | k) != 0 ? 1u : 0u);
+          for (int mt = 0; mt < MT; ++mt)
+#pragma unroll
+            for (int k = 0; k < 4; ++k)    // K = 8 f32 = 32 bytes per instruction
+              umma_tf32_lo(d0 + (uint32_t)(mt * BN), a_lo + (uint32_t)(mt * (kABytes / 16) + k * 2), b_lo + (uint32_t)(k * 2), idesc,
+                           (kb | k) != 0 ? 1u : 0u);
           umma_commit(bar_empty + 8 * stage);
         }
         umma_commit(bar_accfull + 8 * acc);
@@ -116,11 +136,13 @@ gemm_tf32_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_consta
     const int row = quad * 32 + lane;
     int it = 0;
     for (int tile = blockIdx.x; tile < m_tiles; tile += gridDim.x, ++it) {
-      const int acc = it & 1;
-      const int m = tile * kBlockM + row;
-      mbar_wait(bar_accfull + 8 * acc, ((uint32_t)(it >> 1)) & 1u);
+      const int acc = it % kAccSets;
+      mbar_wait(bar_accfull + 8 * acc, ((uint32_t)(it / kAccSets)) & 1u);
       tc_fence_after();
-      const uint32_t t0 = tmem_base + ((uint32_t)(quad * 32) << 16) + (uint32_t)(acc * BN);
+#pragma unroll 1
+      for (int mt = 0; mt < MT; ++mt) {
+      const int m = (tile * MT + mt) * kBlockM + row;
+      const uint32_t t0 = tmem_base + ((uint32_t)(quad * 32) << 16) + (uint32_t)((acc * MT + mt) * BN);
       if (p.mode == 0) {
 #pragma unroll 1
         for (int c0 = 0; c0 < p.N; c0 += 32) {
@@ -147,12 +169,13 @@ gemm_tf32_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_consta
           if (p.gated) tmem_ld32(t0 + (uint32_t)(p.A + c0), u);
 #pragma unroll
           for (int i = 0; i < 32; ++i) {
-            float t = tanhf(__uint_as_float(v[i]) + s_bias[c0 + i]);
-            if (p.gated) t *= 1.0f / (1.0f + expf(-(__uint_as_float(u[i]) + s_bias[p.A + c0 + i])));
+            float t = tanh_fast(__uint_as_float(v[i]) + s_bias[c0 + i]);
+            if (p.gated) t *= sigmoid_fast(__uint_as_float(u[i]) + s_bias[p.A + c0 + i]);
             sc = fmaf(s_bias[BN + c0 + i], t, sc);
           }
         }
         if (m < p.M) p.out[m] = sc + __ldg(p.b_w);
+      }
       }
       tc_fence_before();
       __syncwarp();
@@ -161,7 +184,7 @@ gemm_tf32_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_consta
   }
   tc_fence_before();
   __syncthreads();
-  if (warp == 1) tmem_dealloc(tmem_base, 2 * BN);
+  if (warp == 1) tmem_dealloc(tmem_base, kTmemCols);
 }
 
 // [rows, cols] row-major f32 matrix, box = [box_rows x 32 cols] (one 128-byte swizzle row of K per matrix row)
@@ -192,16 +215,19 @@ static int encode_2d_f32(TensorMapBlob* out, const void* ptr, uint64_t rows, uin
 
 bool gemm_tf32_supported(int N, int K) { return (N == 64 || N == 128 || N == 256) && K >= kTfK && K % kTfK == 0; }
 
-template <int BN>
+static int g_tf32_mt = 0;      // pdf_debug_set_mil_mt: 0 = by batch size, 1 / 2 = forced
+
+template <int BN, int MT>
 static int launch_tf32(const TensorMapBlob& ta, const TensorMapBlob& tb, const TfParams& p, cudaStream_t s) {
-  constexpr int smem = kTfStages * (kABytes + BN * 128) + 8 * (2 * kTfStages + 4) + 16 + 2 * BN * 4 + 1024;
+  constexpr int kStages = (MT == 1) ? 4 : 3;
+  constexpr int smem = kStages * (MT * kABytes + BN * 128) + 8 * (2 * kStages + 4) + 16 + 2 * BN * 4 + 1024;
   static bool configured = false;
   if (!configured) {
-    PDF_CHECK_CUDA(cudaFuncSetAttribute(gemm_tf32_kernel<BN>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
+    PDF_CHECK_CUDA(cudaFuncSetAttribute(gemm_tf32_kernel<BN, MT>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
     configured = true;
   }
-  const int grid = max(1, min(ceil_div(p.M, kBlockM), num_sms()));
-  PDF_CHECK_CUDA(launch_pdl(gemm_tf32_kernel<BN>, dim3(grid), dim3(192), (size_t)smem, s, *reinterpret_cast<const CUtensorMap*>(&ta),
+  const int grid = max(1, min(ceil_div(p.M, MT * kBlockM), num_sms()));
+  PDF_CHECK_CUDA(launch_pdl(gemm_tf32_kernel<BN, MT>, dim3(grid), dim3(192), (size_t)smem, s, *reinterpret_cast<const CUtensorMap*>(&ta),
                             *reinterpret_cast<const CUtensorMap*>(&tb), p));
   PDF_CHECK_LAUNCH();
   return PDF_OK;
@@ -218,11 +244,21 @@ int launch_gemm_tf32(const float* A, const float* B, int M, int N, int K, int mo
   if (int rc = encode_2d_f32(&tb, B, (uint64_t)N, (uint64_t)K, (uint32_t)N)) return rc;
   TfParams p;
   p.M = M; p.N = N; p.K = K; p.mode = mode; p.gated = gated; p.A = A_dim; p.bias = bias; p.w_w = w_w; p.b_w = b_w; p.out = out;
+  // measured (profiles/r02_mil_times.txt, 2048 bags): 256-row tiles are NOT faster (253 vs 248 us per sweep) -- what they save in
+  // weight re-streaming they lose with the single TMEM accumulator set and the shallower ring; they stay an opt-in
+  const bool two = g_tf32_mt == 2;
   switch (N) {
-    case 64: return launch_tf32<64>(ta, tb, p, s);
-    case 128: return launch_tf32<128>(ta, tb, p, s);
-    default: return launch_tf32<256>(ta, tb, p, s);
+    case 64: return two ? launch_tf32<64, 2>(ta, tb, p, s) : launch_tf32<64, 1>(ta, tb, p, s);
+    case 128: return two ? launch_tf32<128, 2>(ta, tb, p, s) : launch_tf32<128, 1>(ta, tb, p, s);
+    default: return two ? launch_tf32<256, 2>(ta, tb, p, s) : launch_tf32<256, 1>(ta, tb, p, s);
   }
 }
 
 }  // namespace pdf
+
+/* tuning / A-B hook: row tiles per weight pass of the MIL tf32 GEMMs (0 = chosen from the batch size, 1, 2) */
+extern "C" int pdf_debug_set_mil_mt(int mt) {
+  if (mt < 0 || mt > 2) { pdf::set_error("pdf_debug_set_mil_mt: 0, 1 or 2"); return PDF_ERR_ARG; }
+  pdf::g_tf32_mt = mt;
+  return PDF_OK;
+}

@@ -138,6 +138,7 @@ PROTOTYPES = {
     "pdf_relu_f32": (C.c_int, [_P, C.c_size_t, _P]),
     "pdf_mse_train": (C.c_int, [C.c_size_t, _P, _P, _P, _P, _P]),
     "pdf_standardize_volume": (C.c_int, [C.c_int, C.c_size_t, _P, _P, C.c_int, _P, _P]),
+    "pdf_debug_set_mil_mt": (C.c_int, [C.c_int]),
     "pdf_simple_stats_stride": (C.c_int, []),
     "pdf_simple_stats": (C.c_int, [C.c_int, C.c_size_t, C.c_int, _P, _P, _P]),
     "pdf_maxpool_train_forward_bf16": (C.c_int, [C.c_int, C.c_int, C.c_int, C.c_int, _P, _P, _P, _P]),

@@ -147,13 +147,20 @@ def test_mil_tensor_path(D, H, A, gated, L):
     live = rng.integers(0, 2, (7, n)).astype(np.uint8)
     Xd, ld, lv = torch.from_numpy(X).cuda(), torch.from_numpy(lens).cuda(), torch.from_numpy(live).cuda()
     p32 = MilHead(sd, gated, 0.37, precision="fp32").sweep(Xd, ld, lv)
-    ptf = MilHead(sd, gated, 0.37, precision="tf32").sweep(Xd, ld, lv)
-    torch.cuda.synchronize()
-    p32, ptf = p32.cpu().numpy(), ptf.cpu().numpy()
+    p32 = p32.cpu().numpy()
     dead = (live == 0) | (lens[None, :] == 0)
-    assert np.all(ptf[dead] == np.float32(0.37)) and np.all(p32[dead] == np.float32(0.37))
+    assert np.all(p32[dead] == np.float32(0.37))
     assert p32[~dead].std() > 1e-3                        # the comparison is not between constants
-    np.testing.assert_allclose(ptf, p32, atol=2e-3, rtol=0)
+    from pd_fusion_b200 import _lib
+    lib = _lib.load()
+    try:
+        for mt in (1, 2, 0):                              # 128-row tiles, 256-row tiles (one weight pass per two tiles), automatic
+            _lib.check(lib.pdf_debug_set_mil_mt(mt))
+            ptf = MilHead(sd, gated, 0.37, precision="tf32").sweep(Xd, ld, lv).cpu().numpy()
+            assert np.all(ptf[dead] == np.float32(0.37)), mt
+            np.testing.assert_allclose(ptf, p32, atol=2e-3, rtol=0, err_msg=f"row tiles per weight pass = {mt}")
+    finally:
+        lib.pdf_debug_set_mil_mt(0)
     # and the FP32 path against the oracle on a few bags
     sdn = {k: v.numpy() for k, v in sd.items()}
     ref = O.mil_predict_proba(sdn, [X[i, :lens[i]] if lens[i] else None for i in range(8)], gated, None, 0.37)

@@ -58,7 +58,15 @@ typedef struct {
   float std[3];
   int32_t extent_raw;           /* 0: extent = any(normalised voxel > 0) (the fused pipeline); 1: any(voxel > 0) on the
                                    resampled volume itself (stand-alone _select_slices on an already-normalised volume) */
+  int32_t slice_major;          /* 1: d_zoomed is written / read slice-axis-major, [B][T2][T0][T1], so that the selected planes of a
+                                   single-axis axis-2 configuration are contiguous (no plane-gather pass; the stride-T2 gather of
+                                   the C-order volume touches every sector of it).  Only where pdf_preproc_slice_major_ok() says
+                                   so; pdf_gather_slices / pdf_normalize_volume take the C-order volume only.  0: [B][T0][T1][T2] */
 } pdf_preproc_cfg;
+
+/* 1 when cfg (one axis group on axis 2, bulk-copy resample tiles of eight rows: Z % 4 == 0, T1 % 8 == 0, T2 <= 160) can use
+ * slice_major = 1 */
+int pdf_preproc_slice_major_ok(const pdf_preproc_cfg* cfg);
 
 /* output layouts of pdf_gather_resize_normalize */
 #define PDF_OUT_BF16_C1 0 /* [B, L, S, S]    bf16, one channel (requires channel-uniform mean/std) */

@@ -21,6 +21,7 @@ namespace pdf {
 constexpr int kPlaneMax = 1024;   // max target dim
 constexpr int kH0 = 4096, kH1 = 2048, kH2 = 256;
 constexpr int kNQ = 4;            // sorted[f0], sorted[f1] for q=1 and q=99
+constexpr int kResStages = 4;     // bulk-copy ring depth of resample_tma_kernel
 
 struct SubjState {
   uint32_t hist0[kH0];
@@ -91,7 +92,20 @@ static int validate(const pdf_preproc_cfg* cfg, int batch) {
     PDF_REQUIRE(cfg->counts[a] >= 1 && cfg->counts[a] <= kPlaneMax, "preproc: slice count out of range");
   }
   PDF_REQUIRE(cfg->input_size >= 1, "preproc: input_size must be positive");
+  if (cfg->slice_major)
+    PDF_REQUIRE(cfg->n_axes == 1 && cfg->axes[0] == 2, "preproc: slice_major is the layout of single-axis axis-2 configurations");
   return PDF_OK;
+}
+
+// the resample kernel writes slice-major only from its 8-row bulk-copy tiles (see resample_tma_kernel / pdf_resample_stats)
+static bool slice_major_ok(const pdf_preproc_cfg* cfg) {
+  if (!cfg || cfg->n_axes != 1 || cfg->axes[0] != 2) return false;
+  const int Y = cfg->in_shape[1], Z = cfg->in_shape[2], T0 = cfg->out_shape[0], T1 = cfg->out_shape[1], T2 = cfg->out_shape[2];
+  if (Z % 4 != 0 || (T2 + 31) / 32 * 32 > 160 || T1 < 8 || T1 % 8 != 0) return false;
+  const double ystep = (double)(Y - 1) / (double)(T1 - 1);
+  const int NR = (int)(7 * ystep) + 3;
+  const size_t smem = (size_t)kResStages * 2 * NR * Z * 4 + (size_t)(kH0 + T0 + T1) * 4 + 16 + (size_t)T1 * 32 + 2 * kResStages * 8 + 128;
+  return smem <= 110 * 1024;
 }
 
 // ------------------------------------------------------------------------------------------------------
@@ -228,7 +242,6 @@ resample_kernel(const float* __restrict__ raw, float* __restrict__ zoomed, SubjS
 // path) into a ring of shared-memory stages while the compute warps work on earlier tiles: warp 0 is the producer
 // (one lane issues two bulk copies per tile and arms the stage's mbarrier with the byte count), the other warps
 // consume.  Needs 16-byte aligned rows (Z % 4 == 0).  Compute threads: [half][k], half = row parity inside the tile.
-constexpr int kResStages = 4;
 
 __device__ __forceinline__ void bulk_load(uint32_t dst, const void* src, uint32_t bytes, uint32_t bar) {
   asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
@@ -260,7 +273,12 @@ __device__ __forceinline__ uint32_t key_of(float f) { return float_to_ordered(f)
 
 // NEED_JMAX: plane maxima along axis 1 are only needed when axis 1 is one of the slicing axes; they cost a warp
 // reduction + shared atomic per output row, so the common axis-2 / axis-0 configurations skip them.
-template <bool NEED_JMAX>
+// ZMAJOR: the resampled volume is written slice-axis-major, [T2][T0][T1] (pdf_preproc_cfg.slice_major: single-axis axis-2
+// configurations, whose selected planes are then CONTIGUOUS -- the stride-T2 plane gather touched every sector of the volume to
+// deliver L of T2 planes).  The two row halves then own rows [j0, j0+4) and [j0+4, j0+8) of a tile instead of alternating rows, a
+// thread keeps its four results in registers and stores them as ONE 16-byte vector at (k, i, j0 + 4*half): no shared-memory
+// transpose, no extra barrier, and half a sector per lane and store (the other half comes from the other row half; L2 merges).
+template <bool NEED_JMAX, bool ZMAJOR>
 __global__ void __launch_bounds__(352, 2)
 resample_tma_kernel(const float* __restrict__ raw, float* __restrict__ zoomed, SubjState* __restrict__ states,
                     const ZoomTables* __restrict__ tabs, int X, int Y, int Z, int T0, int T1, int T2, int TJ, int NR, int KT) {
@@ -341,8 +359,8 @@ resample_tma_kernel(const float* __restrict__ raw, float* __restrict__ zoomed, S
       float* op = zb + ((size_t)i * T1 + (j0 + half)) * T2 + k;
       mbar_wait(bar_full + stage * 8, phase);
       float tmaxf = -INFINITY;
-#pragma unroll 2
-      for (int j = j0 + half; j < j1; j += 2, op += 2 * (size_t)T2) {
+      float acc4[4] = {0.f, 0.f, 0.f, 0.f};
+      auto do_row = [&](const int j, const int r) {
         const JEntry e = s_jtab[j];
         const uint32_t r0 = sbase + (uint32_t)e.y0b, r1 = sbase + (uint32_t)e.y1b;
         const float f000 = lds_f32(r0 + z0b), f001 = lds_f32(r0 + z1b), f010 = lds_f32(r1 + z0b), f011 = lds_f32(r1 + z1b);
@@ -374,7 +392,8 @@ resample_tma_kernel(const float* __restrict__ raw, float* __restrict__ zoomed, S
           out = __double2float_rn(t);
         }
         if (act) {
-          *op = out;
+          if (ZMAJOR) acc4[r] = out;
+          else *op = out;
           tmaxf = fmaxf(tmaxf, out);
           vmin = fminf(vmin, out);
           if (out > 0.0f) atomicAdd(&s_hist[__float_as_uint(out) >> 19], 1u);
@@ -383,7 +402,17 @@ resample_tma_kernel(const float* __restrict__ raw, float* __restrict__ zoomed, S
           const uint32_t wmax = __reduce_max_sync(0xffffffffu, act ? key_of(out) : 0u);
           if (lane == 0 && wmax != 0) atomicMax(&s_jmax[j], wmax);
         }
+            };
+      const int jbeg = ZMAJOR ? j0 + 4 * half : j0 + half;
+      if (ZMAJOR) {
+#pragma unroll
+        for (int r = 0; r < 4; ++r) do_row(jbeg + r, r);       // (T1 % 8 == 0: every tile has its eight rows)
+      } else {
+#pragma unroll 2
+        for (int j = jbeg; j < j1; j += 2, op += 2 * (size_t)T2) do_row(j, 0);
       }
+      if (ZMAJOR && act)
+        *reinterpret_cast<float4*>(zb + ((size_t)k * T0 + i) * T1 + jbeg) = make_float4(acc4[0], acc4[1], acc4[2], acc4[3]);
       __syncwarp();
       if (lane == 0) mbar_arrive(bar_empty + stage * 8);    // this warp is done reading the stage
       kmaxf = fmaxf(kmaxf, tmaxf);
@@ -760,6 +789,7 @@ __global__ void extract_planes_kernel(const float* __restrict__ zoomed, const in
 }
 
 struct ResizeArgs {
+  int zmajor;       // 1: zoomed is slice-major [T2][T0][T1] (axis-2 planes contiguous, un-clipped); `planes` is not used
   int T[3];
   int n_axes;
   int axes[PDF_MAX_AXES];
@@ -803,6 +833,7 @@ resize_kernel(const float* __restrict__ zoomed, const float* __restrict__ planes
     size_t rs;
     if (axis == 0) { src = zoomed + ((size_t)b * T0 + idx) * T1 * T2; H = T1; W = T2; rs = T2; }
     else if (axis == 1) { src = zoomed + (size_t)b * T0 * T1 * T2 + (size_t)idx * T2; H = T0; W = T2; rs = (size_t)T1 * T2; }
+    else if (ra.zmajor) { src = zoomed + ((size_t)b * T2 + idx) * T0 * T1; H = T0; W = T1; rs = T1; }
     else { src = planes + ((size_t)b * ra.cnt2 + off2 + t) * T0 * T1; H = T0; W = T1; rs = T1; }
     const float* l4 = lohi + 4 * (size_t)b;
     const float lo = ra.ready ? 0.0f : l4[0], hi = ra.ready ? 1.0f : l4[1];       // ready slices already lie in [0, 1]
@@ -883,6 +914,7 @@ resize_band_kernel(const float* __restrict__ zoomed, const float* __restrict__ p
   size_t rs;
   if (axis == 0) { src = zoomed + ((size_t)b * T0 + idx) * T1 * T2; H = T1; W = T2; rs = T2; }
   else if (axis == 1) { src = zoomed + (size_t)b * T0 * T1 * T2 + (size_t)idx * T2; H = T0; W = T2; rs = (size_t)T1 * T2; }
+  else if (ra.zmajor) { src = zoomed + ((size_t)b * T2 + idx) * T0 * T1; H = T0; W = T1; rs = T1; }
   else { src = planes + ((size_t)b * ra.cnt2 + off2 + t) * T0 * T1; H = T0; W = T1; rs = T1; }
   float lo = 0.0f, hi = 1.0f, inv_den = 1.0f;                 // ready slices already lie in [0, 1]
   if (!ra.ready && valid) { const float* l4 = lohi + 4 * (size_t)b; lo = l4[0]; hi = l4[1]; inv_den = __frcp_rn(l4[2]); }
@@ -1099,6 +1131,8 @@ using namespace pdf;
 
 static int g_pre_chunk = 0;   // subjects per pdf_preprocess sub-batch (0 = whole batch); pdf_debug_set_pre_chunk
 
+extern "C" int pdf_preproc_slice_major_ok(const pdf_preproc_cfg* cfg) { return slice_major_ok(cfg) ? 1 : 0; }
+
 extern "C" size_t pdf_preproc_workspace_bytes(const pdf_preproc_cfg* cfg, int batch) {
   if (!cfg || batch <= 0) return 0;
   size_t n = align_up(sizeof(ZoomTables), 256) + align_up(sizeof(SubjState) * (size_t)batch, 256);
@@ -1135,26 +1169,36 @@ extern "C" int pdf_resample_stats(const pdf_preproc_cfg* cfg, int batch, const f
     if (TJ >= 2 && smem <= 200 * 1024) {
       bool need_jmax = false;
       for (int a = 0; a < cfg->n_axes; ++a) need_jmax |= cfg->axes[a] == 1;
-      static size_t configured[2] = {0, 0};
-      if (smem > configured[need_jmax]) {
-        if (need_jmax) PDF_CHECK_CUDA(cudaFuncSetAttribute(resample_tma_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-        else PDF_CHECK_CUDA(cudaFuncSetAttribute(resample_tma_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-        configured[need_jmax] = smem;
+      static size_t configured[3] = {0, 0, 0};
+      const int variant = cfg->slice_major ? 2 : (need_jmax ? 1 : 0);
+      if (cfg->slice_major)
+        PDF_REQUIRE(TJ == 8 && T1 % 8 == 0 && !need_jmax, "pdf_resample_stats: slice_major needs 8-row tiles (T1 %% 8 == 0, rows that fit "
+                    "the staging ring) -- check pdf_preproc_slice_major_ok first");
+      if (smem > configured[variant]) {
+        if (variant == 2) PDF_CHECK_CUDA(cudaFuncSetAttribute(resample_tma_kernel<false, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        else if (need_jmax) PDF_CHECK_CUDA(cudaFuncSetAttribute(resample_tma_kernel<true, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        else PDF_CHECK_CUDA(cudaFuncSetAttribute(resample_tma_kernel<false, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        configured[variant] = smem;
       }
       const int ntiles = T0 * ceil_div(T1, TJ);
       const int per_sm = max(1, min(4, (int)((220 * 1024) / (smem + 1024))));
       // one resident wave: never more blocks than the chip holds at once (a second partial wave would double the time)
       const int blocks_per_subject = max(1, min(ntiles, (num_sms() * per_sm) / batch));
-      if (need_jmax)
-        resample_tma_kernel<true><<<dim3(blocks_per_subject, batch), 32 + 2 * KT, smem, s>>>(d_raw, d_zoomed, w.st, w.tabs, X, Y, Z, T0,
-                                                                                           T1, T2, TJ, NR, KT);
+      if (variant == 2)
+        resample_tma_kernel<false, true><<<dim3(blocks_per_subject, batch), 32 + 2 * KT, smem, s>>>(d_raw, d_zoomed, w.st, w.tabs, X, Y, Z,
+                                                                                                  T0, T1, T2, TJ, NR, KT);
+      else if (need_jmax)
+        resample_tma_kernel<true, false><<<dim3(blocks_per_subject, batch), 32 + 2 * KT, smem, s>>>(d_raw, d_zoomed, w.st, w.tabs, X, Y, Z,
+                                                                                                  T0, T1, T2, TJ, NR, KT);
       else
-        resample_tma_kernel<false><<<dim3(blocks_per_subject, batch), 32 + 2 * KT, smem, s>>>(d_raw, d_zoomed, w.st, w.tabs, X, Y, Z, T0,
-                                                                                            T1, T2, TJ, NR, KT);
+        resample_tma_kernel<false, false><<<dim3(blocks_per_subject, batch), 32 + 2 * KT, smem, s>>>(d_raw, d_zoomed, w.st, w.tabs, X, Y, Z,
+                                                                                                   T0, T1, T2, TJ, NR, KT);
       PDF_CHECK_LAUNCH();
       return PDF_OK;
     }
   }
+  PDF_REQUIRE(!cfg->slice_major, "pdf_resample_stats: slice_major needs the bulk-copy resample kernel (Z %% 4 == 0, T2 <= 160): check "
+              "pdf_preproc_slice_major_ok first");
   const int threads = min(256, (T2 + 31) / 32 * 32);
   // rows per tile: as many as fit the shared-memory staging buffer (2 planes x NR input rows x Z doubles)
   int TJ = 8, NR = 0;
@@ -1217,7 +1261,7 @@ static bool launch_resize_band(const ResizeArgs& ra, int out_mode, int batch, co
   if (out_mode == PDF_OUT_F32_NHWC3 || groups > 64) return false;
   const dim3 grid(ceil_div(ra.S, kBandRows), ra.lmax, batch), block(64, 4);
   __nv_bfloat16* o = reinterpret_cast<__nv_bfloat16*>(d_out);
-  bool preclip = !ra.ready;                      // all slots on axis 2: their planes were clipped by extract_planes_kernel
+  bool preclip = !ra.ready && !ra.zmajor;        // all slots on axis 2: their planes were clipped by extract_planes_kernel
   for (int a = 0; a < ra.n_axes; ++a) preclip = preclip && ra.axes[a] == 2;
   if (out_mode == PDF_OUT_BF16_C1_PAD) {
     if (preclip) resize_band_kernel<PDF_OUT_BF16_C1_PAD, true><<<grid, block, 0, s>>>(d_zoomed, planes, d_lohi, d_indices, d_nslices, o, ra);
@@ -1244,6 +1288,7 @@ extern "C" int pdf_gather_resize_normalize(const pdf_preproc_cfg* cfg, int batch
   cudaStream_t s = as_stream(stream);
   Workspace w = carve(cfg, batch, d_workspace);
   ResizeArgs ra;
+  ra.zmajor = cfg->slice_major ? 1 : 0;
   ra.lmax = 0;
   ra.n_axes = cfg->n_axes;
   ra.S = cfg->input_size;
@@ -1258,7 +1303,7 @@ extern "C" int pdf_gather_resize_normalize(const pdf_preproc_cfg* cfg, int batch
   const int T0 = cfg->out_shape[0], T1 = cfg->out_shape[1], T2 = cfg->out_shape[2];
   int off = 0, off2 = 0;
   for (int a = 0; a < cfg->n_axes; ++a) {
-    if (cfg->axes[a] == 2) {
+    if (cfg->axes[a] == 2 && !cfg->slice_major) {
       const int xb = max(1, min(ceil_div((long long)T0 * T1, 256 * 4), 64));
       // (plain launch: with programmatic dependent launch the next kernel's blocks would sit on the SMs waiting while this
       //  multi-wave grid still has blocks to place -- measured 220 -> 403 us for gather + resize)
@@ -1341,6 +1386,7 @@ extern "C" int pdf_gather_slices(const pdf_preproc_cfg* cfg, int batch, const fl
                                  const int32_t* d_indices, const int32_t* d_nslices, float* d_slices, pdf_stream_t stream) {
   if (int rc = validate(cfg, batch)) return rc;
   PDF_REQUIRE(d_zoomed && d_lohi && d_indices && d_nslices && d_slices, "pdf_gather_slices: null device pointer");
+  PDF_REQUIRE(!cfg->slice_major, "pdf_gather_slices reads the C-order resampled volume (slice_major = 0)");
   FinalizeArgs fa;
   fa.lmax = 0; fa.n_axes = cfg->n_axes; fa.extent_raw = 0;
   for (int i = 0; i < 3; ++i) fa.T[i] = cfg->out_shape[i];

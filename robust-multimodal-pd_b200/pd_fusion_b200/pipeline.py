@@ -45,8 +45,10 @@ class EmbeddingPipeline:
             if precision == "bf16":      # one channel, normalised with the channel-averaged statistics (backbone.py folds the rest)
                 m_avg, s_avg = self.enc.input_mean_std
                 mean, std = (m_avg,) * 3, (s_avg,) * 3
+            # (embed() keeps the resampled volume slice-major where the library can: contiguous planes, no gather pass)
             self.pre = VolumePreprocessor(in_shape, target_shape, axes, counts, input_size, mean, std, mode,
-                                          self.max_subjects, self.device)
+                                          self.max_subjects, self.device,
+                                          slice_major=os.environ.get("PDFUSION_B200_SLICE_MAJOR", "1") != "0")
             self.L = self.pre.lmax
             self.D = self.enc.emb_dim
             # preprocessing writes straight into the encoder's input buffer

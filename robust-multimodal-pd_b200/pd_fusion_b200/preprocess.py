@@ -19,7 +19,7 @@ from . import _lib
 @dataclass
 class PreprocResult:
     net_input: torch.Tensor   # [B, L, S, S] bf16, [B, L, rows, pitch] bf16 (zero-padded) or [B, L, S, S, 3] f32
-    zoomed: torch.Tensor      # [B, T0, T1, T2] f32 (resampled, un-normalised)
+    zoomed: torch.Tensor      # [B, T0, T1, T2] f32 (resampled, un-normalised); [B, T2, T0, T1] from a slice-major run()
     lohi: torch.Tensor        # [B, 4] f32: lo, hi, denominator, has_positive
     indices: torch.Tensor     # [B, L] i32 (-1 in unused slots)
     nslices: torch.Tensor     # [B, n_axes] i32
@@ -29,7 +29,12 @@ class VolumePreprocessor:
     def __init__(self, in_shape: Sequence[int], target_shape: Sequence[int] = (160, 160, 160),
                  axes: Sequence[int] = (2,), counts: Sequence[int] = (24,), input_size: int = 224,
                  mean=(0.5, 0.5, 0.5), std=(0.5, 0.5, 0.5), out_mode: int = _lib.OUT_BF16_C1,
-                 max_batch: int = 1, device=None):
+                 max_batch: int = 1, device=None, slice_major: bool = False):
+        """slice_major: `run()` (the fused pipeline) keeps the resampled volume slice-axis-major, [B, T2, T0, T1], when the library
+        supports it for this configuration (one axis group on axis 2; `pdf_preproc_slice_major_ok`): the selected planes are then
+        contiguous and the plane-gather pass disappears.  `PreprocResult.zoomed` of such a run has that layout
+        (`self.run_slice_major`); the stage-level entry points (resample / select / gather / gather_slices) always use the
+        reference's C order."""
         _lib.require_cuda()
         self.lib = _lib.load()
         if len(axes) != len(counts) or not 1 <= len(axes) <= _lib.PDF_MAX_AXES:
@@ -53,6 +58,12 @@ class VolumePreprocessor:
         cfg.mean[:] = [float(m) for m in mean]
         cfg.std[:] = [float(s) for s in std]
         self.cfg = cfg
+        self.cfg_run = cfg                                    # configuration of the fused run(): slice-major where possible
+        self.run_slice_major = False
+        if slice_major and self.lib.pdf_preproc_slice_major_ok(C.byref(cfg)):
+            self.cfg_run = _lib.PreprocCfg.from_buffer_copy(cfg)
+            self.cfg_run.slice_major = 1
+            self.run_slice_major = True
         ws = self.lib.pdf_preproc_workspace_bytes(C.byref(cfg), self.max_batch)
         if ws == 0:
             raise _lib.PdfusionError("pdf_preproc_workspace_bytes returned 0 (bad configuration)")
@@ -82,11 +93,15 @@ class VolumePreprocessor:
         """Enqueues resample+stats, select, gather/resize on the current stream (no sync)."""
         B = self._check_raw(raw)
         out = self.net_input if net_input is None else net_input
-        rc = self.lib.pdf_preprocess(C.byref(self.cfg), B, raw.data_ptr(), self.zoomed.data_ptr(), self.workspace.data_ptr(),
+        rc = self.lib.pdf_preprocess(C.byref(self.cfg_run), B, raw.data_ptr(), self.zoomed.data_ptr(), self.workspace.data_ptr(),
                                      self.lohi.data_ptr(), self.indices.data_ptr(), self.nslices.data_ptr(), out.data_ptr(),
                                      self.out_mode, _lib.stream_ptr())
         _lib.check(rc, "pdf_preprocess")
-        return PreprocResult(out[:B], self.zoomed[:B], self.lohi[:B], self.indices[:B], self.nslices[:B])
+        zoomed = self.zoomed[:B]
+        if self.run_slice_major:                              # same bytes, [B, T2, T0, T1]
+            T0, T1, T2 = self.target_shape
+            zoomed = zoomed.view(B, T2, T0, T1)
+        return PreprocResult(out[:B], zoomed, self.lohi[:B], self.indices[:B], self.nslices[:B])
 
     # stage-level entry points (parity tests, per-kernel timing)
     def resample(self, raw: torch.Tensor) -> torch.Tensor:

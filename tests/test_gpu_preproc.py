@@ -152,3 +152,26 @@ def test_resample_property_full_size():
     z = z.cpu().numpy()
     assert np.isfinite(z).all() and z.max() <= 3.25 and z.min() >= 0.0
     assert (z == 3.25).mean() > 0.99
+
+
+@pytest.mark.parametrize("shape,target,count,size,mode", [((64, 48, 44), (40, 40, 40), 6, 56, _lib.OUT_F32_NHWC3),
+                                                           ((96, 80, 72), (64, 56, 48), 10, 96, _lib.OUT_BF16_C1_PAD),
+                                                           ((256, 256, 176), (160, 160, 160), 48, 224, _lib.OUT_BF16_C1_PAD)])
+def test_slice_major_run_equals_c_order_run(shape, target, count, size, mode):
+    """The fused run() with the resampled volume kept slice-axis-major ([B, T2, T0, T1]: contiguous planes, no gather pass) must
+    give the C-order run's results bit for bit: the volume (transposed), lo/hi, the indices and the network input."""
+    raws = np.stack([synthetic_volume(20 + i, shape, 1e-4) for i in range(2)])
+    raw = torch.from_numpy(raws).cuda()
+    a = VolumePreprocessor(shape, target, [2], [count], size, out_mode=mode, max_batch=2)
+    b = VolumePreprocessor(shape, target, [2], [count], size, out_mode=mode, max_batch=2, slice_major=True)
+    assert b.run_slice_major and not a.run_slice_major
+    ra, rb = a.run(raw), b.run(raw)
+    torch.cuda.synchronize()
+    assert tuple(rb.zoomed.shape) == (2, target[2], target[0], target[1])
+    assert torch.equal(rb.zoomed.permute(0, 2, 3, 1), ra.zoomed), "slice-major volume differs"
+    assert torch.equal(ra.lohi, rb.lohi) and torch.equal(ra.indices, rb.indices) and torch.equal(ra.nslices, rb.nslices)
+    assert torch.equal(ra.net_input.view(torch.int16) if ra.net_input.dtype == torch.bfloat16 else ra.net_input,
+                       rb.net_input.view(torch.int16) if rb.net_input.dtype == torch.bfloat16 else rb.net_input), "network input differs"
+    # configurations the layout does not apply to fall back silently to C order
+    c = VolumePreprocessor(shape, target, [0, 2], [3, 3], size, out_mode=mode, max_batch=2, slice_major=True)
+    assert not c.run_slice_major

@@ -315,11 +315,13 @@ int pdf_bn_train_forward(int n_groups, const int32_t* d_goff, int max_group_rows
 int pdf_bn_train_backward(int n_groups, const int32_t* d_goff, int max_group_rows, int C, const float* d_dy, const float* d_y,
                           const float* d_x, const float* d_gamma, const float* d_mean, const float* d_invstd, int relu, double* d_scratch,
                           float* d_dx, float* d_dres, int dres_accumulate, float* d_dgamma, float* d_dbeta, pdf_stream_t stream);
+/* (bf16 storage: the forward also writes the ReLU mask as ONE BIT per element, d_relu_mask [M*C/8] bytes, bit j of byte i = element
+ *  8i+j survived; the backward reads it instead of y -- 1/16 of the bytes) */
 int pdf_bn_train_forward_bf16(int n_groups, const int32_t* d_goff, int max_group_rows, int C, const void* d_x, const float* d_gamma,
-                              const float* d_beta, float eps, const void* d_residual, int relu, void* d_y, float* d_mean, float* d_invstd,
-                              float* d_var_unbiased, double* d_scratch, pdf_stream_t stream);
-int pdf_bn_train_backward_bf16(int n_groups, const int32_t* d_goff, int max_group_rows, int C, const void* d_dy, const void* d_y,
-                               const void* d_x, const float* d_gamma, const float* d_mean, const float* d_invstd, int relu,
+                              const float* d_beta, float eps, const void* d_residual, int relu, void* d_y, uint8_t* d_relu_mask,
+                              float* d_mean, float* d_invstd, float* d_var_unbiased, double* d_scratch, pdf_stream_t stream);
+int pdf_bn_train_backward_bf16(int n_groups, const int32_t* d_goff, int max_group_rows, int C, const void* d_dy,
+                               const uint8_t* d_relu_mask, const void* d_x, const float* d_gamma, const float* d_mean, const float* d_invstd, int relu,
                                double* d_scratch, void* d_dx, void* d_dres, int dres_accumulate, float* d_dgamma, float* d_dbeta,
                                pdf_stream_t stream);
 /* running = (1-momentum)*running + momentum*batch, group after group (the reference forwards its chunks one at a time) */

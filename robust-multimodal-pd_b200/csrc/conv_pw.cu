@@ -79,6 +79,28 @@ __device__ __forceinline__ void sts128(uint32_t a, uint4 v) {
   asm volatile("st.shared.v4.b32 [%0], {%1,%2,%3,%4};" ::"r"(a), "r"(v.x), "r"(v.y), "r"(v.z), "r"(v.w) : "memory");
 }
 
+// Packed float32 pairs (Blackwell FADD2) and the fused ReLU + bf16x2 pack (F2FP.RELU): the epilogue of a 128 x 128 unit was ~36 ALU
+// instructions per 8 channels (8 bias adds, 8 bf16 unpacks, 8 residual adds, 8 max, 4 packs) on 8 warps -- in stages 2-4, where the
+// unit's MMAs take 0.5 us, the epilogue WAS the unit time.  With pairs: 4 + 8 + 4 + 4.
+__device__ __forceinline__ uint64_t f2_pack(uint32_t lo, uint32_t hi) {
+  uint64_t r;
+  asm("mov.b64 %0, {%1, %2};" : "=l"(r) : "r"(lo), "r"(hi));
+  return r;
+}
+__device__ __forceinline__ uint64_t f2_add(uint64_t a, uint64_t b) {
+  uint64_t r;
+  asm("add.rn.f32x2 %0, %1, %2;" : "=l"(r) : "l"(a), "l"(b));
+  return r;
+}
+__device__ __forceinline__ uint32_t f2_to_bf16x2(uint64_t v, bool relu) {     // low half = first element
+  uint32_t lo, hi, r;
+  asm("mov.b64 {%0, %1}, %2;" : "=r"(lo), "=r"(hi) : "l"(v));
+  if (relu) asm("cvt.rn.relu.bf16x2.f32 %0, %1, %2;" : "=r"(r) : "f"(__uint_as_float(hi)), "f"(__uint_as_float(lo)));
+  else asm("cvt.rn.bf16x2.f32 %0, %1, %2;" : "=r"(r) : "f"(__uint_as_float(hi)), "f"(__uint_as_float(lo)));
+  return r;
+}
+__device__ __forceinline__ uint64_t bf16x2_to_f2(uint32_t w) { return f2_pack(w << 16, w & 0xffff0000u); }
+
 template <int NC, bool CHAIN>
 __global__ void __launch_bounds__(kPwThreads, 1)
 conv_pw_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant__ CUtensorMap tmap_b,
@@ -252,20 +274,17 @@ conv_pw_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant
         uint32_t v[32];
         tmem_ld32(tmem_acc2 + ((uint32_t)(quad * 32) << 16) + (uint32_t)(ch * 32), v);
         if (m < p.M_total) {
-          float f[32];
+          uint32_t h[16];
 #pragma unroll
           for (int i = 0; i < 32; i += 4) {
-            const float4 b = *reinterpret_cast<const float4*>(s_bias3 + ch * 32 + i);
-            f[i] = fmaxf(__uint_as_float(v[i]) + b.x, 0.f); f[i + 1] = fmaxf(__uint_as_float(v[i + 1]) + b.y, 0.f);
-            f[i + 2] = fmaxf(__uint_as_float(v[i + 2]) + b.z, 0.f); f[i + 3] = fmaxf(__uint_as_float(v[i + 3]) + b.w, 0.f);
+            const ulonglong2 b = *reinterpret_cast<const ulonglong2*>(s_bias3 + ch * 32 + i);
+            h[i / 2] = f2_to_bf16x2(f2_add(f2_pack(v[i], v[i + 1]), b.x), true);
+            h[i / 2 + 1] = f2_to_bf16x2(f2_add(f2_pack(v[i + 2], v[i + 3]), b.y), true);
           }
           __nv_bfloat16* op = p.out3 + (size_t)m * p.N2 + ch * 32;
 #pragma unroll
           for (int i = 0; i < 2; ++i)
-            stg256(op + i * 16, pack_bf16x2(f[i * 16 + 0], f[i * 16 + 1]), pack_bf16x2(f[i * 16 + 2], f[i * 16 + 3]),
-                   pack_bf16x2(f[i * 16 + 4], f[i * 16 + 5]), pack_bf16x2(f[i * 16 + 6], f[i * 16 + 7]),
-                   pack_bf16x2(f[i * 16 + 8], f[i * 16 + 9]), pack_bf16x2(f[i * 16 + 10], f[i * 16 + 11]),
-                   pack_bf16x2(f[i * 16 + 12], f[i * 16 + 13]), pack_bf16x2(f[i * 16 + 14], f[i * 16 + 15]));
+            stg256(op + i * 16, h[i * 8 + 0], h[i * 8 + 1], h[i * 8 + 2], h[i * 8 + 3], h[i * 8 + 4], h[i * 8 + 5], h[i * 8 + 6], h[i * 8 + 7]);
         }
       }
       tc_fence_before();
@@ -292,22 +311,17 @@ conv_pw_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant
 #pragma unroll
         for (int q = 0; q < 4; ++q) {                                          // 8 channels = one 16-byte unit
           const uint32_t addr = sub + ((((uint32_t)((ch & 1) * 4 + q)) ^ sw) << 4);
-          const float4 b0 = *reinterpret_cast<const float4*>(bp + q * 8), b1 = *reinterpret_cast<const float4*>(bp + q * 8 + 4);
-          float f0 = __uint_as_float(v[q * 8 + 0]) + b0.x, f1 = __uint_as_float(v[q * 8 + 1]) + b0.y;
-          float f2 = __uint_as_float(v[q * 8 + 2]) + b0.z, f3 = __uint_as_float(v[q * 8 + 3]) + b0.w;
-          float f4 = __uint_as_float(v[q * 8 + 4]) + b1.x, f5 = __uint_as_float(v[q * 8 + 5]) + b1.y;
-          float f6 = __uint_as_float(v[q * 8 + 6]) + b1.z, f7 = __uint_as_float(v[q * 8 + 7]) + b1.w;
+          const ulonglong2 b0 = *reinterpret_cast<const ulonglong2*>(bp + q * 8), b1 = *reinterpret_cast<const ulonglong2*>(bp + q * 8 + 4);
+          uint64_t p0 = f2_add(f2_pack(v[q * 8 + 0], v[q * 8 + 1]), b0.x), p1 = f2_add(f2_pack(v[q * 8 + 2], v[q * 8 + 3]), b0.y);
+          uint64_t p2 = f2_add(f2_pack(v[q * 8 + 4], v[q * 8 + 5]), b1.x), p3 = f2_add(f2_pack(v[q * 8 + 6], v[q * 8 + 7]), b1.y);
           if (p.has_res) {
             const uint4 r = lds128(addr);
-            f0 += bf16_lo(r.x); f1 += bf16_hi(r.x); f2 += bf16_lo(r.y); f3 += bf16_hi(r.y);
-            f4 += bf16_lo(r.z); f5 += bf16_hi(r.z); f6 += bf16_lo(r.w); f7 += bf16_hi(r.w);
-          }
-          if (p.relu) {
-            f0 = fmaxf(f0, 0.f); f1 = fmaxf(f1, 0.f); f2 = fmaxf(f2, 0.f); f3 = fmaxf(f3, 0.f);
-            f4 = fmaxf(f4, 0.f); f5 = fmaxf(f5, 0.f); f6 = fmaxf(f6, 0.f); f7 = fmaxf(f7, 0.f);
+            p0 = f2_add(p0, bf16x2_to_f2(r.x)); p1 = f2_add(p1, bf16x2_to_f2(r.y));
+            p2 = f2_add(p2, bf16x2_to_f2(r.z)); p3 = f2_add(p3, bf16x2_to_f2(r.w));
           }
           uint4 o;
-          o.x = pack_bf16x2(f0, f1); o.y = pack_bf16x2(f2, f3); o.z = pack_bf16x2(f4, f5); o.w = pack_bf16x2(f6, f7);
+          const bool relu = p.relu != 0;
+          o.x = f2_to_bf16x2(p0, relu); o.y = f2_to_bf16x2(p1, relu); o.z = f2_to_bf16x2(p2, relu); o.w = f2_to_bf16x2(p3, relu);
           sts128(addr, o);
         }
       }

@@ -107,7 +107,7 @@ __global__ void bn16_stats_finalize_kernel(const double* __restrict__ acc, const
 __global__ void __launch_bounds__(256)
 bn16_apply_kernel(const __nv_bfloat16* __restrict__ x, const int* __restrict__ goff, int C, const float* __restrict__ mean,
                   const float* __restrict__ invstd, const float* __restrict__ gamma, const float* __restrict__ beta,
-                  const __nv_bfloat16* __restrict__ residual, int relu, __nv_bfloat16* __restrict__ y) {
+                  const __nv_bfloat16* __restrict__ residual, int relu, __nv_bfloat16* __restrict__ y, uint8_t* __restrict__ mask8) {
   const int g = blockIdx.y;
   const size_t lo = (size_t)goff[g] * C / 8, hi = (size_t)goff[g + 1] * C / 8;
   const int c = (int)(threadIdx.x % (C / 8)) * 8;
@@ -121,19 +121,21 @@ bn16_apply_kernel(const __nv_bfloat16* __restrict__ x, const int* __restrict__ g
     float f[8], r[8];
     unpack8(reinterpret_cast<const uint4*>(x)[i], f);
     if (residual) unpack8(reinterpret_cast<const uint4*>(residual)[i], r);
+    uint32_t bits = 0;
 #pragma unroll
     for (int j = 0; j < 8; ++j) {
       float v = fmaf(f[j], sc[j], sh[j]);
       if (residual) v += r[j];
-      if (relu) v = fmaxf(v, 0.f);
+      if (relu) { bits |= (v > 0.f ? 1u : 0u) << j; v = fmaxf(v, 0.f); }
       f[j] = v;
     }
     reinterpret_cast<uint4*>(y)[i] = pack8(f);
+    if (relu && mask8) mask8[i] = (uint8_t)bits;     // one bit per element: the backward passes read 1/16 of y's bytes for the ReLU mask
   }
 }
 
 __global__ void __launch_bounds__(256)
-bn16_bwd_reduce_kernel(const __nv_bfloat16* __restrict__ dy, const __nv_bfloat16* __restrict__ y, const __nv_bfloat16* __restrict__ x,
+bn16_bwd_reduce_kernel(const __nv_bfloat16* __restrict__ dy, const uint8_t* __restrict__ mask8, const __nv_bfloat16* __restrict__ x,
                        const int* __restrict__ goff, int C, const float* __restrict__ mean, const float* __restrict__ invstd, int relu,
                        double* __restrict__ acc) {
   __shared__ double red[4][8][33];
@@ -147,20 +149,20 @@ bn16_bwd_reduce_kernel(const __nv_bfloat16* __restrict__ dy, const __nv_bfloat16
     const float mu0 = mean[(size_t)g * C + c], mu1 = mean[(size_t)g * C + c + 1];
     const float is0 = invstd[(size_t)g * C + c], is1 = invstd[(size_t)g * C + c + 1];
     const uint32_t* dp = reinterpret_cast<const uint32_t*>(dy);
-    const uint32_t* yp = reinterpret_cast<const uint32_t*>(y);
     const uint32_t* xp = reinterpret_cast<const uint32_t*>(x);
+    const int sh = c & 7;                                   // this lane's two channels sit in bits sh, sh+1 of their mask byte
     int r = r0 + ry;
     for (; r + 8 < r1; r += 16) {
       const size_t i0 = ((size_t)r * C + c) >> 1, i1 = ((size_t)(r + 8) * C + c) >> 1;
       const uint32_t d0 = dp[i0], d1 = dp[i1], x0 = xp[i0], x1 = xp[i1];
-      uint32_t y0 = 0x3f803f80u, y1 = 0x3f803f80u;
-      if (relu) { y0 = yp[i0]; y1 = yp[i1]; }
+      uint32_t m0 = 3u, m1 = 3u;
+      if (relu) { m0 = (uint32_t)mask8[i0 >> 2] >> sh; m1 = (uint32_t)mask8[i1 >> 2] >> sh; }
       float2 gA = bf2_to_f2(d0), gB = bf2_to_f2(d1);
-      const float2 yA = bf2_to_f2(y0), yB = bf2_to_f2(y1), xA = bf2_to_f2(x0), xB = bf2_to_f2(x1);
-      if (!(yA.x > 0.f)) gA.x = 0.f;
-      if (!(yA.y > 0.f)) gA.y = 0.f;
-      if (!(yB.x > 0.f)) gB.x = 0.f;
-      if (!(yB.y > 0.f)) gB.y = 0.f;
+      const float2 xA = bf2_to_f2(x0), xB = bf2_to_f2(x1);
+      if (!(m0 & 1u)) gA.x = 0.f;
+      if (!(m0 & 2u)) gA.y = 0.f;
+      if (!(m1 & 1u)) gB.x = 0.f;
+      if (!(m1 & 2u)) gB.y = 0.f;
       a0 += (double)gA.x + (double)gB.x; a1 += (double)gA.y + (double)gB.y;
       b0 += (double)gA.x * (double)((xA.x - mu0) * is0) + (double)gB.x * (double)((xB.x - mu0) * is0);
       b1 += (double)gA.y * (double)((xA.y - mu1) * is1) + (double)gB.y * (double)((xB.y - mu1) * is1);
@@ -169,7 +171,7 @@ bn16_bwd_reduce_kernel(const __nv_bfloat16* __restrict__ dy, const __nv_bfloat16
       const size_t i = ((size_t)r * C + c) >> 1;
       float2 gr = bf2_to_f2(dp[i]);
       const float2 xv = bf2_to_f2(xp[i]);
-      if (relu) { const float2 yv = bf2_to_f2(yp[i]); if (!(yv.x > 0.f)) gr.x = 0.f; if (!(yv.y > 0.f)) gr.y = 0.f; }
+      if (relu) { const uint32_t m = (uint32_t)mask8[i >> 2] >> sh; if (!(m & 1u)) gr.x = 0.f; if (!(m & 2u)) gr.y = 0.f; }
       a0 += (double)gr.x; a1 += (double)gr.y;
       b0 += (double)gr.x * (double)((xv.x - mu0) * is0); b1 += (double)gr.y * (double)((xv.y - mu1) * is1);
     }
@@ -201,7 +203,7 @@ __global__ void bn16_bwd_finalize_kernel(const double* __restrict__ acc, int G, 
 // dx = gamma * invstd * (g - sum_g/m - xhat * sum_gx/m);  dres (+)= g.  Per-thread channel constants as in bn16_apply_kernel:
 // dx = k0 * g - k1 - k2 * x  with k0 = gamma*invstd, k2 = k0 * invstd * sum_gx/m, k1 = k0 * sum_g/m - k2 * mean
 __global__ void __launch_bounds__(256)
-bn16_bwd_apply_kernel(const __nv_bfloat16* __restrict__ dy, const __nv_bfloat16* __restrict__ y, const __nv_bfloat16* __restrict__ x,
+bn16_bwd_apply_kernel(const __nv_bfloat16* __restrict__ dy, const uint8_t* __restrict__ mask8, const __nv_bfloat16* __restrict__ x,
                       const int* __restrict__ goff, int C, const float* __restrict__ mean, const float* __restrict__ invstd,
                       const float* __restrict__ gamma, int relu, const float* __restrict__ sum_g, const float* __restrict__ sum_gx,
                       __nv_bfloat16* __restrict__ dx, __nv_bfloat16* __restrict__ dres, int dres_accumulate) {
@@ -219,13 +221,13 @@ bn16_bwd_apply_kernel(const __nv_bfloat16* __restrict__ dy, const __nv_bfloat16*
     k1[j] = k0[j] * sum_g[gc] * inv_m - k2[j] * mean[gc];
   }
   for (size_t i = lo + (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < hi; i += (size_t)gridDim.x * blockDim.x) {
-    float gr[8], xv[8], yv[8], o[8];
+    float gr[8], xv[8], o[8];
     unpack8(reinterpret_cast<const uint4*>(dy)[i], gr);
     unpack8(reinterpret_cast<const uint4*>(x)[i], xv);
     if (relu) {
-      unpack8(reinterpret_cast<const uint4*>(y)[i], yv);
+      const uint32_t m = mask8[i];
 #pragma unroll
-      for (int j = 0; j < 8; ++j) if (!(yv[j] > 0.f)) gr[j] = 0.f;
+      for (int j = 0; j < 8; ++j) if (!((m >> j) & 1u)) gr[j] = 0.f;
     }
 #pragma unroll
     for (int j = 0; j < 8; ++j) o[j] = fmaf(k0[j], gr[j], -fmaf(k2[j], xv[j], k1[j]));
@@ -328,29 +330,34 @@ __global__ void avgpool16_bwd_kernel(const float* __restrict__ demb, __nv_bfloat
 
 // f32 NHWC3 image -> bf16 patch matrix [N*Ho*Wo, 192] of the 7x7 stride-2 pad-3 stem: column (r*7 + s)*3 + ch, columns 147..191 zero.
 // One thread writes 8 columns (16 bytes).
+// Block = 8 output pixels of one row x 24 column groups (192 threads... rounded to 256: x = column group, y = pixel); a thread's
+// 8 columns map to fixed (r, s, ch) triples, decoded ONCE per thread (the first version divided by 3 and 7 per element).
 __global__ void __launch_bounds__(256)
 stem_im2col3_kernel(const float* __restrict__ x, __nv_bfloat16* __restrict__ out, int N, int H, int W, int Ho, int Wo) {
-  const size_t total = (size_t)N * Ho * Wo * 24;
-  for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (size_t)gridDim.x * blockDim.x) {
-    const int c8 = (int)(i % 24);
-    size_t t = i / 24;
-    const int q = (int)(t % Wo); t /= Wo;
+  const int c8 = threadIdx.x;                        // 0..23 (threads 24..31 of each row idle)
+  if (c8 >= 24) return;
+  int dr[8], ds[8];                                  // tap row, (tap column * 3 + channel); -1 = zero padding column
+#pragma unroll
+  for (int j = 0; j < 8; ++j) {
+    const int col = c8 * 8 + j;
+    if (col < 147) { const int rs = col / 3; dr[j] = rs / 7; ds[j] = (rs - dr[j] * 7) * 3 + (col - rs * 3); }
+    else { dr[j] = -1; ds[j] = 0; }
+  }
+  const size_t pixels = (size_t)N * Ho * Wo;
+  for (size_t pix = (size_t)blockIdx.x * blockDim.y + threadIdx.y; pix < pixels; pix += (size_t)gridDim.x * blockDim.y) {
+    const int q = (int)(pix % Wo);
+    const size_t t = pix / Wo;
     const int p = (int)(t % Ho);
     const int n = (int)(t / Ho);
+    const float* img = x + (size_t)n * H * W * 3;
+    const int ih0 = 2 * p - 3, iw0 = (2 * q - 3) * 3;
     float f[8];
 #pragma unroll
     for (int j = 0; j < 8; ++j) {
-      const int col = c8 * 8 + j;
-      float v = 0.f;
-      if (col < 147) {
-        const int ch = col % 3, rs = col / 3;
-        const int r = rs / 7, s = rs - r * 7;
-        const int ih = 2 * p - 3 + r, iw = 2 * q - 3 + s;
-        if (ih >= 0 && ih < H && iw >= 0 && iw < W) v = __ldg(x + (((size_t)n * H + ih) * W + iw) * 3 + ch);
-      }
-      f[j] = v;
+      const int ih = ih0 + dr[j], iw3 = iw0 + ds[j];
+      f[j] = (dr[j] >= 0 && ih >= 0 && ih < H && iw3 >= 0 && iw3 < W * 3) ? __ldg(img + (size_t)ih * W * 3 + iw3) : 0.f;
     }
-    reinterpret_cast<uint4*>(out)[i] = pack8(f);
+    reinterpret_cast<uint4*>(out)[pix * 24 + c8] = pack8(f);
   }
 }
 
@@ -419,10 +426,11 @@ using namespace pdf;
 typedef __nv_bfloat16 bf16_t;
 
 extern "C" int pdf_bn_train_forward_bf16(int n_groups, const int32_t* d_goff, int max_group_rows, int C, const void* d_x, const float* d_gamma,
-                                         const float* d_beta, float eps, const void* d_residual, int relu, void* d_y, float* d_mean,
-                                         float* d_invstd, float* d_var_unbiased, double* d_scratch, pdf_stream_t stream) {
+                                         const float* d_beta, float eps, const void* d_residual, int relu, void* d_y, uint8_t* d_relu_mask,
+                                         float* d_mean, float* d_invstd, float* d_var_unbiased, double* d_scratch, pdf_stream_t stream) {
   PDF_REQUIRE(n_groups > 0 && d_goff && max_group_rows > 0 && C > 0 && C % 8 == 0 && d_x && d_gamma && d_beta && d_y && d_mean && d_invstd &&
-              d_var_unbiased && d_scratch, "pdf_bn_train_forward_bf16: bad arguments (C %% 8 == 0, scratch of 2*groups*C doubles)");
+              d_var_unbiased && d_scratch && (!relu || d_relu_mask),
+              "pdf_bn_train_forward_bf16: bad arguments (C %% 8 == 0, scratch of 2*groups*C doubles, a mask buffer when relu)");
   cudaStream_t s = as_stream(stream);
   PDF_CHECK_CUDA(cudaMemsetAsync(d_scratch, 0, (size_t)2 * n_groups * C * sizeof(double), s));
   bn16_stats_kernel<<<dim3(ceil_div(C, 64), n_groups, ceil_div(max_group_rows, kBn16Rows)), 256, 0, s>>>((const bf16_t*)d_x, d_goff, C, d_scratch);
@@ -430,28 +438,29 @@ extern "C" int pdf_bn_train_forward_bf16(int n_groups, const int32_t* d_goff, in
   bn16_stats_finalize_kernel<<<ceil_div(n_groups * C, 256), 256, 0, s>>>(d_scratch, d_goff, n_groups, C, eps, d_mean, d_invstd, d_var_unbiased);
   PDF_CHECK_LAUNCH();
   bn16_apply_kernel<<<dim3(std::max(1, 8 * num_sms() / n_groups), n_groups), 256, 0, s>>>((const bf16_t*)d_x, d_goff, C, d_mean, d_invstd, d_gamma,
-                                                                                         d_beta, (const bf16_t*)d_residual, relu, (bf16_t*)d_y);
+                                                                                         d_beta, (const bf16_t*)d_residual, relu, (bf16_t*)d_y, d_relu_mask);
   PDF_CHECK_LAUNCH();
   return PDF_OK;
 }
 
-extern "C" int pdf_bn_train_backward_bf16(int n_groups, const int32_t* d_goff, int max_group_rows, int C, const void* d_dy, const void* d_y,
-                                          const void* d_x, const float* d_gamma, const float* d_mean, const float* d_invstd, int relu,
+extern "C" int pdf_bn_train_backward_bf16(int n_groups, const int32_t* d_goff, int max_group_rows, int C, const void* d_dy,
+                                          const uint8_t* d_relu_mask, const void* d_x, const float* d_gamma, const float* d_mean, const float* d_invstd, int relu,
                                           double* d_scratch, void* d_dx, void* d_dres, int dres_accumulate, float* d_dgamma, float* d_dbeta,
                                           pdf_stream_t stream) {
-  PDF_REQUIRE(n_groups > 0 && d_goff && max_group_rows > 0 && C > 0 && C % 8 == 0 && d_dy && d_y && d_x && d_gamma && d_mean && d_invstd &&
-              d_scratch && d_dx && d_dgamma && d_dbeta, "pdf_bn_train_backward_bf16: bad arguments (C %% 8 == 0, scratch of 3*groups*C doubles)");
+  PDF_REQUIRE(n_groups > 0 && d_goff && max_group_rows > 0 && C > 0 && C % 8 == 0 && d_dy && (!relu || d_relu_mask) && d_x && d_gamma && d_mean &&
+              d_invstd && d_scratch && d_dx && d_dgamma && d_dbeta,
+              "pdf_bn_train_backward_bf16: bad arguments (C %% 8 == 0, scratch of 3*groups*C doubles, the forward's mask when relu)");
   cudaStream_t s = as_stream(stream);
   double* acc = d_scratch;
   float* sums = reinterpret_cast<float*>(d_scratch + (size_t)2 * n_groups * C);
   PDF_CHECK_CUDA(cudaMemsetAsync(acc, 0, (size_t)2 * n_groups * C * sizeof(double), s));
   bn16_bwd_reduce_kernel<<<dim3(ceil_div(C, 64), n_groups, ceil_div(max_group_rows, kBn16Rows)), 256, 0, s>>>(
-      (const bf16_t*)d_dy, (const bf16_t*)d_y, (const bf16_t*)d_x, d_goff, C, d_mean, d_invstd, relu, acc);
+      (const bf16_t*)d_dy, d_relu_mask, (const bf16_t*)d_x, d_goff, C, d_mean, d_invstd, relu, acc);
   PDF_CHECK_LAUNCH();
   bn16_bwd_finalize_kernel<<<ceil_div(C, 128), 128, 0, s>>>(acc, n_groups, C, sums, d_dgamma, d_dbeta);
   PDF_CHECK_LAUNCH();
   bn16_bwd_apply_kernel<<<dim3(std::max(1, 8 * num_sms() / n_groups), n_groups), 256, 0, s>>>(
-      (const bf16_t*)d_dy, (const bf16_t*)d_y, (const bf16_t*)d_x, d_goff, C, d_mean, d_invstd, d_gamma, relu, sums,
+      (const bf16_t*)d_dy, d_relu_mask, (const bf16_t*)d_x, d_goff, C, d_mean, d_invstd, d_gamma, relu, sums,
       sums + (size_t)n_groups * C, (bf16_t*)d_dx, (bf16_t*)d_dres, dres_accumulate);
   PDF_CHECK_LAUNCH();
   return PDF_OK;
@@ -485,7 +494,7 @@ extern "C" int pdf_avgpool_backward_bf16(int n, int hw, int c, const float* d_de
 extern "C" int pdf_stem_im2col3_bf16(int n, int h, int w, const float* d_x, void* d_out, pdf_stream_t stream) {
   PDF_REQUIRE(n > 0 && h > 0 && w > 0 && d_x && d_out, "pdf_stem_im2col3_bf16: bad arguments");
   const int ho = (h + 6 - 7) / 2 + 1, wo = (w + 6 - 7) / 2 + 1;
-  stem_im2col3_kernel<<<ew_blocks16((size_t)n * ho * wo * 24), 256, 0, as_stream(stream)>>>(d_x, (bf16_t*)d_out, n, h, w, ho, wo);
+  stem_im2col3_kernel<<<ew_blocks16((size_t)n * ho * wo * 32), dim3(32, 8), 0, as_stream(stream)>>>(d_x, (bf16_t*)d_out, n, h, w, ho, wo);
   PDF_CHECK_LAUNCH();
   return PDF_OK;
 }

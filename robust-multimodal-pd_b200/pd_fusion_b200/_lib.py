@@ -130,7 +130,7 @@ PROTOTYPES = {
     "pdf_conv_wgrad_f32": (C.c_int, [C.POINTER(Op), _P, _P, _P, _P]),
     "pdf_bn_train_forward": (C.c_int, [C.c_int, _P, C.c_int, C.c_int, _P, _P, _P, C.c_float, _P, C.c_int, _P, _P, _P, _P, _P, _P]),
     "pdf_bn_train_backward": (C.c_int, [C.c_int, _P, C.c_int, C.c_int, _P, _P, _P, _P, _P, _P, C.c_int, _P, _P, _P, C.c_int, _P, _P, _P]),
-    "pdf_bn_train_forward_bf16": (C.c_int, [C.c_int, _P, C.c_int, C.c_int, _P, _P, _P, C.c_float, _P, C.c_int, _P, _P, _P, _P, _P, _P]),
+    "pdf_bn_train_forward_bf16": (C.c_int, [C.c_int, _P, C.c_int, C.c_int, _P, _P, _P, C.c_float, _P, C.c_int, _P, _P, _P, _P, _P, _P, _P]),
     "pdf_bn_train_backward_bf16": (C.c_int, [C.c_int, _P, C.c_int, C.c_int, _P, _P, _P, _P, _P, _P, C.c_int, _P, _P, _P, C.c_int, _P, _P, _P]),
     "pdf_maxpool3d_forward": (C.c_int, [C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, _P, _P, _P, _P]),
     "pdf_maxpool3d_backward": (C.c_int, [C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, _P, _P, _P, _P]),

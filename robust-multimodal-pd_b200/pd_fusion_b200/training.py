@@ -399,11 +399,14 @@ class ResNetTrainer:
         mean = torch.empty((G, K), dtype=torch.float32, device=self.dev)
         invstd, varu = torch.empty_like(mean), torch.empty_like(mean)
         bnm = self._bn_module(bn)
-        fn = self.lib.pdf_bn_train_forward_bf16 if self.bf16 else self.lib.pdf_bn_train_forward
-        _lib.check(fn(G, goff.data_ptr(), max_rows, K, conv_out.data_ptr(), self.params[bn + ".weight"].data.data_ptr(),
-                      self.params[bn + ".bias"].data.data_ptr(), float(bnm.eps), _p(res.data if res else None), 1 if relu else 0, y.data_ptr(),
-                      mean.data_ptr(), invstd.data_ptr(), varu.data_ptr(), self._scratch(3 * G * K).data_ptr(), _lib.stream_ptr()),
-                   "pdf_bn_train_forward")
+        args = (G, goff.data_ptr(), max_rows, K, conv_out.data_ptr(), self.params[bn + ".weight"].data.data_ptr(),
+                self.params[bn + ".bias"].data.data_ptr(), float(bnm.eps), _p(res.data if res else None), 1 if relu else 0, y.data_ptr())
+        tail = (mean.data_ptr(), invstd.data_ptr(), varu.data_ptr(), self._scratch(3 * G * K).data_ptr(), _lib.stream_ptr())
+        if self.bf16:        # the ReLU mask as one bit per element: what the backward reads instead of y
+            y.relu_bits = torch.empty(conv_out.numel() // 8, dtype=torch.uint8, device=self.dev) if relu else None
+            _lib.check(self.lib.pdf_bn_train_forward_bf16(*args, _p(y.relu_bits), *tail), "pdf_bn_train_forward_bf16")
+        else:
+            _lib.check(self.lib.pdf_bn_train_forward(*args, *tail), "pdf_bn_train_forward")
         if self.update_running:
             _lib.check(self.lib.pdf_bn_update_running(G, K, mean.data_ptr(), varu.data_ptr(), float(bnm.momentum),
                                                       self.buffers[bn + ".running_mean"].data_ptr(), self.buffers[bn + ".running_var"].data_ptr(),
@@ -505,7 +508,8 @@ class ResNetTrainer:
                 acc = 1
             dres = res.grad
         fn = self.lib.pdf_bn_train_backward_bf16 if self.bf16 else self.lib.pdf_bn_train_backward
-        _lib.check(fn(G, goff.data_ptr(), max_rows, K, out.grad.data_ptr(), out.data.data_ptr(), conv_out.data_ptr(),
+        act = _p(out.data.relu_bits) if self.bf16 else out.data.data_ptr()         # bf16 path: the forward's bit mask; fp32 path: y itself
+        _lib.check(fn(G, goff.data_ptr(), max_rows, K, out.grad.data_ptr(), act, conv_out.data_ptr(),
                       self.params[bn + ".weight"].data.data_ptr(), mean.data_ptr(), invstd.data_ptr(), 1 if relu else 0,
                       self._scratch(3 * G * K).data_ptr(), dconv.data_ptr(), _p(dres), acc, self.grad[bn + ".weight"].data_ptr(),
                       self.grad[bn + ".bias"].data_ptr(), _lib.stream_ptr()), "pdf_bn_train_backward")

@@ -29,7 +29,7 @@ def test_library_exports_every_declared_symbol():
 
 def test_struct_sizes_match_header_layout():
     # natural alignment, same field order as the header
-    assert C.sizeof(_lib.PreprocCfg) == 4 * (3 + 3 + 1 + 3 + 3 + 1 + 3 + 3 + 1)
+    assert C.sizeof(_lib.PreprocCfg) == 4 * (3 + 3 + 1 + 3 + 3 + 1 + 3 + 3 + 1 + 1)        # (+ slice_major)
     assert C.sizeof(_lib.Op) == 15 * 4 + 4 + 12 * 8 + 8     # 15 ints, padding, 6 + 3 (fused 1x1) + 3 (chained 1x1) pointers, k3 + padding
     assert C.sizeof(_lib.Mlp) == 8 + 9 * 4 + 4 + 16 * 8 + 4 + 9 * 4 + 4 or C.sizeof(_lib.Mlp) % 8 == 0
 

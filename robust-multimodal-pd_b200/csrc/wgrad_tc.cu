@@ -26,12 +26,15 @@ constexpr int kWgPix = 64;                  // pixels (GEMM K) per k-block
 constexpr int kWgMaxStages = 6;             // ring depth is a launch parameter: as many stages as fit next to the tile shape
 constexpr int kWgSub = kWgPix * 128;        // one [64 px x 64 ch] swizzled sub-tile = 8 KB
 
+static int g_wg_waves = 2;
+
 struct WgParams {
   int M, Cout, C, R, S, Ho, Wo, stride, pad;
   int T;            // taps per CTA (consecutive s of one filter row, or 1)
   int N;            // Cin columns per tap in this CTA (64 | 128 | 256)
   int tap_groups, cin_blocks, slabs, slab_kb;   // grid decomposition; slab_kb = k-blocks per slab
   int stages;       // TMA ring depth (2..kWgMaxStages)
+  int flat;         // 1x1 stride-1 convolution: X is the plain [M, C] matrix, loaded through a 2-D tiled map (no im2col traversal)
   float* dw;        // [Cout][R][S][C] f32
 };
 
@@ -105,9 +108,11 @@ wgrad_tc_kernel(const __grid_constant__ CUtensorMap tmap_dy, const __grid_consta
           for (int t = 0; t < n_taps; ++t) {
             const int tap = tap0 + t;
             const int r = tap / p.S, s = tap - r * p.S;
-            for (int j = 0; j < nsub; ++j)
-              tma_load_im2col_4d(sa + 2 * kWgSub + (t * nsub + j) * kWgSub, &tmap_x, bar_full + 8 * stage, cb * p.N + j * 64, w0, h0, n_img,
-                                 (uint16_t)s, (uint16_t)r);
+            for (int j = 0; j < nsub; ++j) {
+              const uint32_t dst = sa + 2 * kWgSub + (t * nsub + j) * kWgSub;
+              if (p.flat) tma_load_2d(dst, &tmap_x, bar_full + 8 * stage, cb * p.N + j * 64, m0);
+              else tma_load_im2col_4d(dst, &tmap_x, bar_full + 8 * stage, cb * p.N + j * 64, w0, h0, n_img, (uint16_t)s, (uint16_t)r);
+            }
           }
         }
       }
@@ -162,6 +167,13 @@ wgrad_tc_kernel(const __grid_constant__ CUtensorMap tmap_dy, const __grid_consta
 
 using namespace pdf;
 
+/* tuning / A-B hook: waves of CTAs the pixel range of a weight gradient is split into (default 2) */
+extern "C" int pdf_debug_set_wgrad_waves(int waves) {
+  if (waves < 1 || waves > 8) { pdf::set_error("pdf_debug_set_wgrad_waves: 1..8"); return PDF_ERR_ARG; }
+  pdf::g_wg_waves = waves;
+  return PDF_OK;
+}
+
 /* Weight gradient of a bf16 NHWC convolution on the tensor cores.  geometry from `op`; d_x [n,h,w,c] bf16, d_dy [n,ho,wo,k] bf16,
  * d_dw [k][r][s][c] f32 (ACCUMULATED into: zero it first).  Needs c % 64 == 0 and k % 64 == 0. */
 extern "C" int pdf_conv_wgrad_bf16(const pdf_op* op, const void* d_x, const void* d_dy, float* d_dw, pdf_stream_t stream) {
@@ -177,8 +189,14 @@ extern "C" int pdf_conv_wgrad_bf16(const pdf_op* op, const void* d_x, const void
   if (int rc = encode_2d(&tdy, d_dy, (uint64_t)M, (uint64_t)op->k, kWgPix)) return rc;
   pdf_op xo = *op;
   xo.d_in = d_x;
-  if (int rc = encode_im2col(&tx, xo, 0, kWgPix)) return rc;
+  const bool flat = op->r == 1 && op->s == 1 && op->stride == 1 && op->pad == 0;
+  if (flat) {
+    if (int rc = encode_2d(&tx, d_x, (uint64_t)M, (uint64_t)op->c, kWgPix)) return rc;
+  } else {
+    if (int rc = encode_im2col(&tx, xo, 0, kWgPix)) return rc;
+  }
   WgParams p;
+  p.flat = flat ? 1 : 0;
   p.M = M; p.Cout = op->k; p.C = op->c; p.R = op->r; p.S = op->s; p.Ho = op->ho; p.Wo = op->wo; p.stride = op->stride; p.pad = op->pad;
   // Cin columns per CTA: the whole Cin when it fits an instruction (N <= 256, a multiple of 64) so that dY streams once
   p.N = op->c <= 256 ? op->c : (op->c % 256 == 0 ? 256 : (op->c % 128 == 0 ? 128 : 64));
@@ -189,7 +207,9 @@ extern "C" int pdf_conv_wgrad_bf16(const pdf_op* op, const void* d_x, const void
   const int cout_blocks = (op->k + 127) / 128;
   const int units = cout_blocks * p.tap_groups * p.cin_blocks;
   const int total_kb = (M + kWgPix - 1) / kWgPix;
-  int slabs = max(1, min(total_kb, (2 * num_sms() + units - 1) / units));
+  // pixel slabs: g_wg_waves waves of CTAs over the machine (one CTA per SM: the ring takes most of the shared memory).  Fewer slabs =
+  // fewer partial sums through the L2 atomics, more slabs = shorter tail
+  int slabs = max(1, min(total_kb, (g_wg_waves * num_sms() + units - 1) / units));
   p.slab_kb = (total_kb + slabs - 1) / slabs;
   slabs = (total_kb + p.slab_kb - 1) / p.slab_kb;
   p.slabs = slabs;

@@ -45,3 +45,50 @@ def test_all_gather_rows_world2(tmp_path):
 
 def test_all_gather_rows_world2_fewer_rows_than_ranks(tmp_path):
     _run(1, 2, 29612, tmp_path)      # rank 1 holds an empty shard
+
+
+TRAIN_WORKER = textwrap.dedent("""
+    import os, sys
+    sys.path.insert(0, sys.argv[1])
+    import torch
+    from pd_fusion_b200.parallel import init_distributed, barrier
+    from pd_fusion_b200.training import _flat_like, allreduce_mean, flatten_parameters
+    rank, local_rank, ws = init_distributed(backend="gloo")
+    torch.manual_seed(0)                                     # same initial weights on every rank, as under DDP
+    net = torch.nn.Sequential(torch.nn.Linear(5, 3), torch.nn.ReLU(), torch.nn.Linear(3, 1))
+    before = {k: v.clone() for k, v in net.state_dict().items()}
+    params = dict(net.named_parameters())
+    flat_param = flatten_parameters(params)                  # every parameter becomes a view into ONE buffer
+    flat_grad, grads = _flat_like({k: v.data for k, v in params.items()})
+    assert flat_param.numel() == flat_grad.numel()
+    for k, v in net.state_dict().items():                    # the module still sees the same values ...
+        assert torch.equal(v, before[k]), k
+    flat_param.mul_(2.0)                                     # ... and an in-place update of the flat buffer IS the parameter update
+    for k, v in net.state_dict().items():
+        assert torch.equal(v, before[k] * 2.0), k
+    assert net(torch.ones(2, 5)).shape == (2, 1)
+    for i, g in enumerate(grads.values()):                   # rank-dependent gradients: the data-parallel step averages them
+        g.fill_(float(rank + 1) * (i + 1))
+    allreduce_mean([flat_grad])
+    for i, g in enumerate(grads.values()):
+        assert torch.allclose(g, torch.full_like(g, 1.5 * (i + 1))), (rank, i, g)
+    barrier()
+    if rank == 0:
+        print("ALLREDUCE_OK", ws)
+    torch.distributed.destroy_process_group()
+""")
+
+
+def test_flat_gradient_allreduce_world2(tmp_path):
+    """Config 5's data-parallel step: parameters flattened into one buffer per module, one all-reduce (mean) per
+    flat gradient buffer -- two gloo ranks with different gradients end up with their average."""
+    script = tmp_path / "train_worker.py"
+    script.write_text(TRAIN_WORKER)
+    procs = []
+    for r in range(2):
+        env = dict(os.environ, RANK=str(r), LOCAL_RANK=str(r), WORLD_SIZE="2", MASTER_ADDR="127.0.0.1", MASTER_PORT="29613")
+        procs.append(subprocess.Popen([sys.executable, str(script), str(ROOT / "robust-multimodal-pd_b200")], env=env,
+                                      stdout=subprocess.PIPE, stderr=subprocess.STDOUT, text=True))
+    outs = [p.communicate(timeout=240)[0] for p in procs]
+    assert all(p.returncode == 0 for p in procs), "\n".join(outs)
+    assert any("ALLREDUCE_OK" in o for o in outs)

@@ -26,7 +26,7 @@ constexpr int kWgPix = 64;                  // pixels (GEMM K) per k-block
 constexpr int kWgMaxStages = 6;             // ring depth is a launch parameter: as many stages as fit next to the tile shape
 constexpr int kWgSub = kWgPix * 128;        // one [64 px x 64 ch] swizzled sub-tile = 8 KB
 
-static int g_wg_waves = 2;
+static int g_wg_waves = 1;       // measured (profiles/r02_wgrad_waves.txt): 1 wave 26.2 ms per fine-tune step, 2: 26.8, 3: 27.3, 4: 27.8
 
 struct WgParams {
   int M, Cout, C, R, S, Ho, Wo, stride, pad;
@@ -167,7 +167,7 @@ wgrad_tc_kernel(const __grid_constant__ CUtensorMap tmap_dy, const __grid_consta
 
 using namespace pdf;
 
-/* tuning / A-B hook: waves of CTAs the pixel range of a weight gradient is split into (default 2) */
+/* tuning / A-B hook: waves of CTAs the pixel range of a weight gradient is split into (default 1) */
 extern "C" int pdf_debug_set_wgrad_waves(int waves) {
   if (waves < 1 || waves > 8) { pdf::set_error("pdf_debug_set_wgrad_waves: 1..8"); return PDF_ERR_ARG; }
   pdf::g_wg_waves = waves;
@@ -209,7 +209,9 @@ extern "C" int pdf_conv_wgrad_bf16(const pdf_op* op, const void* d_x, const void
   const int total_kb = (M + kWgPix - 1) / kWgPix;
   // pixel slabs: g_wg_waves waves of CTAs over the machine (one CTA per SM: the ring takes most of the shared memory).  Fewer slabs =
   // fewer partial sums through the L2 atomics, more slabs = shorter tail
-  int slabs = max(1, min(total_kb, (g_wg_waves * num_sms() + units - 1) / units));
+  // (rounded DOWN: units * slabs must not exceed waves * SMs -- rounding up left a last wave of 1..24 CTAs on most layers, a whole
+  //  extra CTA time: 333 -> 222 us on layer 1's 3x3 convolutions, ncu "Waves Per SM 2.01")
+  int slabs = max(1, min(total_kb, (g_wg_waves * num_sms()) / units));
   p.slab_kb = (total_kb + slabs - 1) / slabs;
   slabs = (total_kb + p.slab_kb - 1) / p.slab_kb;
   p.slabs = slabs;

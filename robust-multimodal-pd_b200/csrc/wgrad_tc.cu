@@ -24,8 +24,8 @@ namespace pdf {
 
 constexpr int kWgPix = 64;                  // pixels (GEMM K) per k-block
 constexpr int kWgMaxStages = 6;             // ring depth is a launch parameter: as many stages as fit next to the tile shape
-constexpr int kWgSub = kWgPix * 128;        // one [64 px x 64 ch] swizzled sub-tile = 8 KB
 
+static int g_wg_rowtile = 1;     // pdf_debug_set_wgrad_rowtile: 0 = im2col-mode loads for every filter > 1x1
 static int g_wg_waves = 1;       // measured (profiles/r02_wgrad_waves.txt): 1 wave 26.2 ms per fine-tune step, 2: 26.8, 3: 27.3, 4: 27.8
 
 struct WgParams {
@@ -35,6 +35,10 @@ struct WgParams {
   int tap_groups, cin_blocks, slabs, slab_kb;   // grid decomposition; slab_kb = k-blocks per slab
   int stages;       // TMA ring depth (2..kWgMaxStages)
   int flat;         // 1x1 stride-1 convolution: X is the plain [M, C] matrix, loaded through a 2-D tiled map (no im2col traversal)
+  int px;           // pixels (GEMM K) per k-block: kWgPix, or rows * W in row-tiled mode
+  int rows;         // row-tiled mode (> 0): a k-block = `rows` full image rows; X through a 4-D TILED map whose box is (64 ch, W, rows)
+  int bpi;          //   k-blocks per image = ceil(H / rows)
+  int H, W;
   float* dw;        // [Cout][R][S][C] f32
 };
 
@@ -47,6 +51,11 @@ __device__ __forceinline__ uint64_t make_desc_mn(uint32_t smem_addr, uint32_t lb
   return (uint64_t)((smem_addr & 0x3ffffu) >> 4) | ((uint64_t)(lbo_bytes >> 4) << 16) | ((uint64_t)(1024 >> 4) << 32) | (1ull << 46) | (2ull << 61);
 }
 
+__device__ __forceinline__ void tma_load_4d(uint32_t dst, const void* tmap, uint32_t bar, int c0, int c1, int c2, int c3) {
+  asm volatile("cp.async.bulk.tensor.4d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, %5, %6}], [%2];"
+               ::"r"(dst), "l"(reinterpret_cast<uint64_t>(tmap)), "r"(bar), "r"(c0), "r"(c1), "r"(c2), "r"(c3) : "memory");
+}
+
 __global__ void __launch_bounds__(192, 1)
 wgrad_tc_kernel(const __grid_constant__ CUtensorMap tmap_dy, const __grid_constant__ CUtensorMap tmap_x, const WgParams p) {
   extern __shared__ uint8_t smem_raw[];
@@ -54,7 +63,8 @@ wgrad_tc_kernel(const __grid_constant__ CUtensorMap tmap_dy, const __grid_consta
   const uint32_t base = (raw_addr + 1023u) & ~1023u;
   uint8_t* smem = smem_raw + (base - raw_addr);
   const int nsub = p.N / 64;                                   // 64-channel sub-tiles per tap
-  const uint32_t stage_bytes = (uint32_t)(2 * kWgSub + p.T * nsub * kWgSub);
+  const uint32_t sub = (uint32_t)p.px * 128u;                  // one [px x 64 ch] swizzled sub-tile
+  const uint32_t stage_bytes = (2u + (uint32_t)(p.T * nsub)) * sub;
   const int kWgStages = p.stages;
   const uint32_t bar_full = base + kWgStages * stage_bytes;
   const uint32_t bar_empty = bar_full + 8 * kWgMaxStages;
@@ -71,7 +81,7 @@ wgrad_tc_kernel(const __grid_constant__ CUtensorMap tmap_dy, const __grid_consta
   const int taps_total = p.R * p.S;
   const int tap0 = tg * p.T;
   const int n_taps = min(p.T, taps_total - tap0);
-  const int total_kb = (p.M + kWgPix - 1) / kWgPix;
+  const int total_kb = p.rows ? (p.M / (p.H * p.W)) * p.bpi : (p.M + kWgPix - 1) / kWgPix;
   const int kb_lo = slab * p.slab_kb, kb_hi = min(total_kb, kb_lo + p.slab_kb);
 
   if (threadIdx.x == 0) {
@@ -96,21 +106,37 @@ wgrad_tc_kernel(const __grid_constant__ CUtensorMap tmap_dy, const __grid_consta
         for (int kb = kb_lo, g = 0; kb < kb_hi; ++kb, ++g) {
           const uint32_t stage = g % kWgStages;
           mbar_wait(bar_empty + 8 * stage, (((uint32_t)(g / kWgStages)) & 1u) ^ 1u);
-          mbar_expect_tx(bar_full + 8 * stage, (uint32_t)(2 * kWgSub + n_taps * nsub * kWgSub));
+          mbar_expect_tx(bar_full + 8 * stage, (2u + (uint32_t)(n_taps * nsub)) * sub);
           const uint32_t sa = base + stage * stage_bytes;
-          const int m0 = kb * kWgPix;
-          tma_load_2d(sa, &tmap_dy, bar_full + 8 * stage, kb0 * 128, m0);                 // [64 px x 64 couts] x 2 (columns past Cout: zero fill)
-          tma_load_2d(sa + kWgSub, &tmap_dy, bar_full + 8 * stage, kb0 * 128 + 64, m0);
-          const int n_img = m0 / hw;
-          const int rem = m0 - n_img * hw;
-          const int pp = rem / p.Wo, qq = rem - pp * p.Wo;
+          int m0, n_img, pp, qq;
+          if (p.rows) {                                          // `rows` image rows of image n_img starting at row pp
+            n_img = kb / p.bpi;
+            pp = (kb - n_img * p.bpi) * p.rows; qq = 0;
+            m0 = (n_img * p.H + pp) * p.W;
+          } else {
+            m0 = kb * kWgPix;
+            n_img = m0 / hw;
+            const int rem = m0 - n_img * hw;
+            pp = rem / p.Wo; qq = rem - pp * p.Wo;
+          }
+          if (p.rows) {      // dY through the same kind of 4-D box: output rows past the image are ZERO (an in-bounds X row would
+                             // otherwise meet the next image's dY through the taps above the centre)
+            tma_load_4d(sa, &tmap_dy, bar_full + 8 * stage, kb0 * 128, 0, pp, n_img);
+            tma_load_4d(sa + sub, &tmap_dy, bar_full + 8 * stage, kb0 * 128 + 64, 0, pp, n_img);
+          } else {
+            tma_load_2d(sa, &tmap_dy, bar_full + 8 * stage, kb0 * 128, m0);               // [px x 64 couts] x 2 (columns past Cout: zero fill)
+            tma_load_2d(sa + sub, &tmap_dy, bar_full + 8 * stage, kb0 * 128 + 64, m0);
+          }
           const int w0 = qq * p.stride - p.pad, h0 = pp * p.stride - p.pad;
           for (int t = 0; t < n_taps; ++t) {
             const int tap = tap0 + t;
             const int r = tap / p.S, s = tap - r * p.S;
             for (int j = 0; j < nsub; ++j) {
-              const uint32_t dst = sa + 2 * kWgSub + (t * nsub + j) * kWgSub;
-              if (p.flat) tma_load_2d(dst, &tmap_x, bar_full + 8 * stage, cb * p.N + j * 64, m0);
+              const uint32_t dst = sa + 2 * sub + (uint32_t)(t * nsub + j) * sub;
+              // row-tiled: the box (64 ch, W, rows) starting at column s - pad, row pp + r - pad IS the tap-shifted pixel block, the
+              // zero padding comes from the out-of-bounds fill
+              if (p.rows) tma_load_4d(dst, &tmap_x, bar_full + 8 * stage, cb * p.N + j * 64, s - p.pad, pp + r - p.pad, n_img);
+              else if (p.flat) tma_load_2d(dst, &tmap_x, bar_full + 8 * stage, cb * p.N + j * 64, m0);
               else tma_load_im2col_4d(dst, &tmap_x, bar_full + 8 * stage, cb * p.N + j * 64, w0, h0, n_img, (uint16_t)s, (uint16_t)r);
             }
           }
@@ -124,11 +150,12 @@ wgrad_tc_kernel(const __grid_constant__ CUtensorMap tmap_dy, const __grid_consta
           mbar_wait(bar_full + 8 * stage, ((uint32_t)(g / kWgStages)) & 1u);
           tc_fence_after();
           const uint32_t sa = base + stage * stage_bytes;
-#pragma unroll
-          for (int k = 0; k < kWgPix / 16; ++k) {                 // 16 pixels per instruction = 2 swizzle atoms = 2048 bytes of rows
-            const uint64_t da = make_desc_mn(sa + k * 2048, kWgSub);
+          const int ksteps = p.px / 16;
+#pragma unroll 4
+          for (int k = 0; k < ksteps; ++k) {                      // 16 pixels per instruction = 2 swizzle atoms = 2048 bytes of rows
+            const uint64_t da = make_desc_mn(sa + k * 2048, sub);
             for (int t = 0; t < n_taps; ++t) {
-              const uint64_t db = make_desc_mn(sa + 2 * kWgSub + t * nsub * kWgSub + k * 2048, kWgSub);
+              const uint64_t db = make_desc_mn(sa + 2 * sub + (uint32_t)(t * nsub) * sub + k * 2048, sub);
               umma_f16(tmem_base + (uint32_t)(t * p.N), da, db, idesc, (g | k) != 0 ? 1u : 0u);
             }
           }
@@ -167,6 +194,35 @@ wgrad_tc_kernel(const __grid_constant__ CUtensorMap tmap_dy, const __grid_consta
 
 using namespace pdf;
 
+// NHWC activation as a 4-D tiled map whose box is `rows` full image rows (W columns) x 64 channels of one image
+static int encode_rows_4d(TensorMapBlob* out, const void* ptr, int n, int h, int w, int c, int rows) {
+  typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*, const cuuint64_t*,
+                                    const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave, CUtensorMapSwizzle,
+                                    CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+  static EncodeTiledFn encode = nullptr;
+  if (!encode) {
+    void* fn = nullptr;
+    cudaDriverEntryPointQueryResult qres;
+    PDF_CHECK_CUDA(cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &fn, cudaEnableDefault, &qres));
+    PDF_REQUIRE(fn && qres == cudaDriverEntryPointSuccess, "cuTensorMapEncodeTiled not available from the driver");
+    encode = reinterpret_cast<EncodeTiledFn>(fn);
+  }
+  const cuuint64_t dims[4] = {(cuuint64_t)c, (cuuint64_t)w, (cuuint64_t)h, (cuuint64_t)n};
+  const cuuint64_t strides[3] = {(cuuint64_t)c * 2, (cuuint64_t)w * c * 2, (cuuint64_t)h * w * c * 2};
+  const cuuint32_t box[4] = {64, (cuuint32_t)w, (cuuint32_t)rows, 1};
+  const cuuint32_t estr[4] = {1, 1, 1, 1};
+  CUresult r = encode(reinterpret_cast<CUtensorMap*>(out), CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 4, const_cast<void*>(ptr), dims, strides, box,
+                      estr, CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                      CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  PDF_REQUIRE(r == CUDA_SUCCESS, "cuTensorMapEncodeTiled(4d rows) failed (%d) nhwc=%d,%d,%d,%d rows=%d", (int)r, n, h, w, c, rows);
+  return PDF_OK;
+}
+
+extern "C" int pdf_debug_set_wgrad_rowtile(int enable) {
+  pdf::g_wg_rowtile = enable != 0;
+  return PDF_OK;
+}
+
 /* tuning / A-B hook: waves of CTAs the pixel range of a weight gradient is split into (default 1) */
 extern "C" int pdf_debug_set_wgrad_waves(int waves) {
   if (waves < 1 || waves > 8) { pdf::set_error("pdf_debug_set_wgrad_waves: 1..8"); return PDF_ERR_ARG; }
@@ -186,17 +242,33 @@ extern "C" int pdf_conv_wgrad_bf16(const pdf_op* op, const void* d_x, const void
   if (int rc = load_driver_entry_points()) return rc;
   const int M = op->n * op->ho * op->wo;
   TensorMapBlob tdy, tx;
-  if (int rc = encode_2d(&tdy, d_dy, (uint64_t)M, (uint64_t)op->k, kWgPix)) return rc;
   pdf_op xo = *op;
   xo.d_in = d_x;
   const bool flat = op->r == 1 && op->s == 1 && op->stride == 1 && op->pad == 0;
-  if (flat) {
+  // row-tiled mode (same-size stride-1 filters on maps whose rows pack into 16-pixel MMA steps: 56 -> 2 rows, 28 -> 4, 14 -> 8 = 112
+  // pixels per k-block): X through a 4-D TILED map instead of the im2col traversal, which delivers a fraction of the tiled rate
+  // (the stem's patch matrix went 752 -> 240 us when its 1x1 "convolution" switched to a 2-D tiled map)
+  int rows = 0;
+  // (Cin <= 128 only: at N = 256 a 112-pixel stage is 86 KB, two ring stages, and those layers run at 680 TFLOP/s on the im2col path)
+  if (g_wg_rowtile && !flat && op->c <= 128 && op->stride == 1 && op->r % 2 == 1 && op->pad == op->r / 2 && op->ho == op->h && op->wo == op->w &&
+      op->w <= 128) {
+    for (int rr = 1; rr <= 16 && rr * op->w <= 128; ++rr)                          // the largest block of whole rows <= 128 pixels that
+      if ((rr * op->w) % 16 == 0 && (double)((op->h + rr - 1) / rr) * rr <= 1.15 * op->h) rows = rr;   // wastes <= 15 % on an image's last block
+  }
+  const int px = rows ? rows * op->w : kWgPix;
+  if (rows) {
+    if (int rc = encode_rows_4d(&tdy, d_dy, op->n, op->ho, op->wo, op->k, rows)) return rc;
+    if (int rc = encode_rows_4d(&tx, d_x, op->n, op->h, op->w, op->c, rows)) return rc;
+  } else if (int rc = encode_2d(&tdy, d_dy, (uint64_t)M, (uint64_t)op->k, (uint32_t)px)) {
+    return rc;
+  } else if (flat) {
     if (int rc = encode_2d(&tx, d_x, (uint64_t)M, (uint64_t)op->c, kWgPix)) return rc;
   } else {
     if (int rc = encode_im2col(&tx, xo, 0, kWgPix)) return rc;
   }
   WgParams p;
   p.flat = flat ? 1 : 0;
+  p.px = px; p.rows = rows; p.bpi = rows ? (op->h + rows - 1) / rows : 0; p.H = op->h; p.W = op->w;
   p.M = M; p.Cout = op->k; p.C = op->c; p.R = op->r; p.S = op->s; p.Ho = op->ho; p.Wo = op->wo; p.stride = op->stride; p.pad = op->pad;
   // Cin columns per CTA: the whole Cin when it fits an instruction (N <= 256, a multiple of 64) so that dY streams once
   p.N = op->c <= 256 ? op->c : (op->c % 256 == 0 ? 256 : (op->c % 128 == 0 ? 128 : 64));
@@ -206,7 +278,7 @@ extern "C" int pdf_conv_wgrad_bf16(const pdf_op* op, const void* d_x, const void
   p.cin_blocks = op->c / p.N;
   const int cout_blocks = (op->k + 127) / 128;
   const int units = cout_blocks * p.tap_groups * p.cin_blocks;
-  const int total_kb = (M + kWgPix - 1) / kWgPix;
+  const int total_kb = rows ? op->n * p.bpi : (M + kWgPix - 1) / kWgPix;
   // pixel slabs: g_wg_waves waves of CTAs over the machine (one CTA per SM: the ring takes most of the shared memory).  Fewer slabs =
   // fewer partial sums through the L2 atomics, more slabs = shorter tail
   // (rounded DOWN: units * slabs must not exceed waves * SMs -- rounding up left a last wave of 1..24 CTAs on most layers, a whole
@@ -216,7 +288,7 @@ extern "C" int pdf_conv_wgrad_bf16(const pdf_op* op, const void* d_x, const void
   slabs = (total_kb + p.slab_kb - 1) / p.slab_kb;
   p.slabs = slabs;
   p.dw = d_dw;
-  const int stage_bytes = 2 * kWgSub + p.T * (p.N / 64) * kWgSub;
+  const int stage_bytes = (2 + p.T * (p.N / 64)) * px * 128;
   const int tail = 8 * (2 * kWgMaxStages + 1) + 16 + 1024;
   p.stages = std::max(2, std::min(kWgMaxStages, (227 * 1024 - tail) / stage_bytes));
   const int smem = p.stages * stage_bytes + tail;

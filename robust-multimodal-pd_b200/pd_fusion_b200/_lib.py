@@ -141,6 +141,7 @@ PROTOTYPES = {
     "pdf_standardize_volume": (C.c_int, [C.c_int, C.c_size_t, _P, _P, C.c_int, _P, _P]),
     "pdf_debug_set_mil_mt": (C.c_int, [C.c_int]),
     "pdf_debug_set_wgrad_waves": (C.c_int, [C.c_int]),
+    "pdf_debug_set_wgrad_rowtile": (C.c_int, [C.c_int]),
     "pdf_preproc_slice_major_ok": (C.c_int, [C.POINTER(PreprocCfg)]),
     "pdf_simple_stats_stride": (C.c_int, []),
     "pdf_simple_stats": (C.c_int, [C.c_int, C.c_size_t, C.c_int, _P, _P, _P]),

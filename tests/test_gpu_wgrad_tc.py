@@ -16,7 +16,10 @@ CASES = [  # n, h, c, k, r, stride, pad
     (2, 9, 256, 64, 1, 1, 0),       # Cout = 64: the second dY sub-tile is out of bounds (zero fill)
     (3, 7, 512, 256, 3, 1, 1),      # N = 256, T = 1, two Cin blocks, two Cout blocks
     (2, 15, 128, 256, 1, 2, 0),     # strided 1x1 (downsample)
-    (40, 28, 64, 64, 3, 1, 1),      # many pixel slabs (split reduction through atomics)
+    (40, 28, 64, 64, 3, 1, 1),      # many pixel slabs (split reduction through atomics); row-tiled X loads, 4 rows per k-block
+    (3, 56, 64, 64, 3, 1, 1),       # row-tiled, 2 rows of 56 pixels per k-block
+    (5, 12, 128, 64, 3, 1, 1),      # row-tiled, 4 rows of 12 pixels (48-pixel k-blocks), Cin = 128 (three taps share the dY tile)
+    (2, 20, 64, 128, 5, 1, 2),      # 5x5 filter, row-tiled (4 rows of 20), taps of a filter row in separate CTAs
 ]
 
 

@@ -29,6 +29,7 @@
 namespace pdf {
 
 static int g_pw_mode = 1;   // pdf_debug_set_pw: 0 = never, 1 = default policy, 2 = every eligible 1x1 convolution
+static int g_pw_mc = 0;     // pdf_debug_set_pw_multicast: 0 (default) = single CTAs, 1 = weight-multicast CTA pairs where K >= 128
 
 constexpr int kPwMaxStages = 6;     // ring depth and staging-buffer count are launch parameters (pdf_debug_set_pw_config)
 constexpr int kPwMaxRy = 4;         // staging buffers (residual in / output out / chained A operand)
@@ -79,6 +80,31 @@ __device__ __forceinline__ void sts128(uint32_t a, uint4 v) {
   asm volatile("st.shared.v4.b32 [%0], {%1,%2,%3,%4};" ::"r"(a), "r"(v.x), "r"(v.y), "r"(v.z), "r"(v.w) : "memory");
 }
 
+// ---- weight multicast (MC): two CTAs of a cluster own DIFFERENT 128-row tiles but walk the SAME sequence of weight tiles (main B
+// k-blocks and chained W3 blocks).  Each CTA fetches HALF of every weight tile and multicasts it into both CTAs' rings, so a unit
+// costs each SM 160 instead of 224 KB of L2 requests in stage 3 (A 64 + B 32 + W3 32 + residual 32).  MEASURED: no gain (9.34 vs
+// 9.23 ms on the ResNet50 stack, per-launch times unchanged) -- a stage still needs its full 32 KB to land before the MMAs start and
+// the ring holds the same three stages, so halving the REQUESTS does not raise the bytes in flight per unit of work; only a real
+// cta_group::2 tile (half of B RESIDENT per CTA: 24 KB stages, a deeper ring) would.  Kept as a tested opt-in
+// (pdf_debug_set_pw_multicast / PDFUSION_B200_PW_MC=1); bit-identical to the single-CTA launches.  The MMAs stay cta_group::1 (each CTA
+// its own accumulators); only the ring is shared: a stage is free once BOTH CTAs' MMAs have read it (multicast tcgen05.commit, "empty"
+// barriers count two arrivals), and its "full" barrier collects the CTA's own A load plus both weight halves.
+__device__ __forceinline__ uint32_t pw_cluster_rank() {
+  uint32_t r;
+  asm volatile("mov.u32 %0, %%cluster_ctarank;" : "=r"(r));
+  return r;
+}
+__device__ __forceinline__ void pw_cluster_sync() {
+  asm volatile("barrier.cluster.arrive.release.aligned;\n\tbarrier.cluster.wait.acquire.aligned;" ::: "memory");
+}
+__device__ __forceinline__ void tma_load_2d_mc(uint32_t dst, const void* tmap, uint32_t bar, int c0, int c1, uint16_t mask) {
+  asm volatile("cp.async.bulk.tensor.2d.shared::cluster.global.mbarrier::complete_tx::bytes.multicast::cluster [%0], [%1, {%3, %4}], [%2], %5;"
+               ::"r"(dst), "l"(reinterpret_cast<uint64_t>(tmap)), "r"(bar), "r"(c0), "r"(c1), "h"(mask) : "memory");
+}
+__device__ __forceinline__ void umma_commit_mc(uint32_t bar, uint16_t mask) {
+  asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.multicast::cluster.b64 [%0], %1;" ::"r"(bar), "h"(mask) : "memory");
+}
+
 // Packed float32 pairs (Blackwell FADD2) and the fused ReLU + bf16x2 pack (F2FP.RELU): the epilogue of a 128 x 128 unit was ~36 ALU
 // instructions per 8 channels (8 bias adds, 8 bf16 unpacks, 8 residual adds, 8 max, 4 packs) on 8 warps -- in stages 2-4, where the
 // unit's MMAs take 0.5 us, the epilogue WAS the unit time.  With pairs: 4 + 8 + 4 + 4.
@@ -101,7 +127,7 @@ __device__ __forceinline__ uint32_t f2_to_bf16x2(uint64_t v, bool relu) {     //
 }
 __device__ __forceinline__ uint64_t bf16x2_to_f2(uint32_t w) { return f2_pack(w << 16, w & 0xffff0000u); }
 
-template <int NC, bool CHAIN>
+template <int NC, bool CHAIN, bool MC>
 __global__ void __launch_bounds__(kPwThreads, 1)
 conv_pw_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant__ CUtensorMap tmap_b,
                const __grid_constant__ CUtensorMap tmap_out, const __grid_constant__ CUtensorMap tmap_res,
@@ -138,7 +164,7 @@ conv_pw_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant
     prefetch_tmap(&tmap_a); prefetch_tmap(&tmap_b); prefetch_tmap(&tmap_out);
     if (p.has_res) prefetch_tmap(&tmap_res);
     if (CHAIN) prefetch_tmap(&tmap_w3);
-    for (int s = 0; s < kPwStages; ++s) { mbar_init(bar_full + 8 * s, 1); mbar_init(bar_empty + 8 * s, 1); }
+    for (int s = 0; s < kPwStages; ++s) { mbar_init(bar_full + 8 * s, 1); mbar_init(bar_empty + 8 * s, MC ? 2 : 1); }
     for (int a = 0; a < 2; ++a) { mbar_init(bar_accfull + 8 * a, 1); mbar_init(bar_accempty + 8 * a, kPwEpiWarps); }
     for (int b = 0; b < kPwRy; ++b) {
       mbar_init(bar_resfull + 8 * b, 1);
@@ -156,10 +182,18 @@ conv_pw_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant
   tc_fence_after();
   const uint32_t tmem_base = *tmem_slot;
   const uint32_t tmem_acc2 = tmem_base + 2 * NC;
+  if (MC) pw_cluster_sync();                     // both CTAs' barriers exist before any multicast load / commit reaches them
   pdl_launch_dependents();
   pdl_wait();
 
-  const int my_tiles = (p.m_tiles - (int)blockIdx.x + (int)gridDim.x - 1) / (int)gridDim.x;   // M tiles of this CTA
+  // M tiles of this CTA: tile(ti).  MC: cluster c of gridDim/2 walks tile PAIRS c, c + gridDim/2, ...; both CTAs run the same
+  // number of units (a pair's second tile may lie past the end: its loads are zero-filled, its stores clipped)
+  const uint32_t rank = MC ? pw_cluster_rank() : 0u;
+  const int n_walkers = MC ? (int)gridDim.x / 2 : (int)gridDim.x;
+  const int walker = MC ? (int)blockIdx.x / 2 : (int)blockIdx.x;
+  const int n_items = MC ? (p.m_tiles + 1) / 2 : p.m_tiles;
+  const int my_tiles = (n_items - walker + n_walkers - 1) / n_walkers;
+  auto tile_of = [&](int ti) { return MC ? (walker + ti * n_walkers) * 2 + (int)rank : walker + ti * n_walkers; };
   const int n_units = my_tiles * p.n_chunks;
   const int num_kb = p.K / kBlockK;
 
@@ -177,12 +211,15 @@ conv_pw_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant
           uint32_t stage;
           ring_wait(stage);
           mbar_expect_tx(bar_full + 8 * stage, (uint32_t)p.N2 * 128u);
-          tma_load_2d(s_ring + stage * L::kStageBytes + (p.N2 > 128 ? 0 : kABytes), &tmap_w3, bar_full + 8 * stage, nc * NC + j * 64, 0);
+          const uint32_t dst = s_ring + stage * L::kStageBytes + (p.N2 > 128 ? 0 : kABytes);
+          if (MC)      // this CTA's half of the [N2 x 64] block (tmap_w3's box is N2/2 rows), into both rings
+            tma_load_2d_mc(dst + rank * (uint32_t)(p.N2 * 64), &tmap_w3, bar_full + 8 * stage, nc * NC + j * 64, (int)rank * (p.N2 / 2), (uint16_t)3);
+          else tma_load_2d(dst, &tmap_w3, bar_full + 8 * stage, nc * NC + j * 64, 0);
         }
       };
       for (int u = 0; u < n_units; ++u) {
         const int ti = u / p.n_chunks, nc = u - ti * p.n_chunks;
-        const int m0 = ((int)blockIdx.x + ti * (int)gridDim.x) * kBlockM, n0 = nc * NC;
+        const int m0 = tile_of(ti) * kBlockM, n0 = nc * NC;
         if (p.has_res) {
           const int b = u % kPwRy;
           mbar_wait(bar_ryfree + 8 * b, (((uint32_t)(u / kPwRy)) & 1u) ^ 1u);
@@ -204,7 +241,9 @@ conv_pw_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant
           const uint32_t sa = s_ring + stage * L::kStageBytes;
           if (p.im2col) tma_load_im2col_4d(sa, &tmap_a, bar_full + 8 * stage, kb * kBlockK, w0, h0, n_img, 0, 0);
           else tma_load_2d(sa, &tmap_a, bar_full + 8 * stage, kb * kBlockK, m0);
-          tma_load_2d(sa + kABytes, &tmap_b, bar_full + 8 * stage, kb * kBlockK, n0);
+          if (MC)      // this CTA's half of the [NC x 64] weight tile (tmap_b's box is NC/2 rows), into both rings
+            tma_load_2d_mc(sa + kABytes + rank * (uint32_t)(NC * 64), &tmap_b, bar_full + 8 * stage, kb * kBlockK, n0 + (int)rank * (NC / 2), (uint16_t)3);
+          else tma_load_2d(sa + kABytes, &tmap_b, bar_full + 8 * stage, kb * kBlockK, n0);
         }
         if (CHAIN && u > 0) load_chain(u - 1);
       }
@@ -230,7 +269,7 @@ conv_pw_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant
 #pragma unroll
           for (int k = 0; k < kBlockK / 16; ++k)
             umma_f16_lo(tmem_acc2, a_lo + (uint32_t)(k * 2), b_lo + (uint32_t)(k * 2), idesc2, (nc | j | k) != 0 ? 1u : 0u);
-          umma_commit(bar_empty + 8 * stage);
+          if (MC) umma_commit_mc(bar_empty + 8 * stage, (uint16_t)3); else umma_commit(bar_empty + 8 * stage);
         }
         umma_commit(bar_ryfree + 8 * b);
         if (nc == p.n_chunks - 1) umma_commit(bar_acc2full);
@@ -248,7 +287,7 @@ conv_pw_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant
 #pragma unroll
           for (int k = 0; k < kBlockK / 16; ++k)
             umma_f16_lo(d0, a_lo + (uint32_t)(k * 2), b_lo + (uint32_t)(k * 2), idesc, (kb | k) != 0 ? 1u : 0u);
-          umma_commit(bar_empty + 8 * stage);
+          if (MC) umma_commit_mc(bar_empty + 8 * stage, (uint16_t)3); else umma_commit(bar_empty + 8 * stage);
         }
         umma_commit(bar_accfull + 8 * acc);
         if (CHAIN && u > 0) do_chain(u - 1);
@@ -268,7 +307,7 @@ conv_pw_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant
     auto acc2_epilogue = [&](int ti) {              // chained conv output of M tile ti: relu(acc2 + bias3) -> out3 (bf16)
       mbar_wait(bar_acc2full, (uint32_t)ti & 1u);
       tc_fence_after();
-      const int m = ((int)blockIdx.x + ti * (int)gridDim.x) * kBlockM + row;
+      const int m = tile_of(ti) * kBlockM + row;
       const int chunks2 = p.N2 / 32;
       for (int ch = half; ch < chunks2; ch += 2) {
         uint32_t v[32];
@@ -294,7 +333,7 @@ conv_pw_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant
 
     for (int u = 0; u < n_units; ++u) {
       const int ti = u / p.n_chunks, nc = u - ti * p.n_chunks;
-      const int m0 = ((int)blockIdx.x + ti * (int)gridDim.x) * kBlockM, n0 = nc * NC;
+      const int m0 = tile_of(ti) * kBlockM, n0 = nc * NC;
       const int b = u % kPwRy, acc = u & 1;
       const uint32_t ry = s_ry + b * L::kRyBytes;
       if (p.has_res) mbar_wait(bar_resfull + 8 * b, ((uint32_t)(u / kPwRy)) & 1u);
@@ -349,6 +388,7 @@ conv_pw_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant
   }
   tc_fence_before();
   __syncthreads();
+  if (MC) pw_cluster_sync();                     // the peer's multicast loads / commits must not target a CTA that has exited
   if (warp == 1) tmem_dealloc(tmem_base, kTmemCols);
 }
 
@@ -386,7 +426,9 @@ int prepare_conv_pw(const pdf_op& op, TcConv* tc) {
   } else {
     if (int rc = encode_2d(&tc->tmap_a, op.d_in, (uint64_t)tc->M_total, (uint64_t)op.c, kBlockM)) return rc;
   }
-  if (int rc = encode_2d(&tc->tmap_b, op.d_weight, (uint64_t)op.k, (uint64_t)op.c, (uint32_t)NC)) return rc;
+  // weight-multicast CTA pairs (see the kernel): where the weight tiles are a large share of a unit's ring traffic
+  tc->pw_mc = (g_pw_mc && NC == 128 && op.c >= 128 && (!op.d_weight3 || op.k3 % 2 == 0)) ? 1 : 0;
+  if (int rc = encode_2d(&tc->tmap_b, op.d_weight, (uint64_t)op.k, (uint64_t)op.c, (uint32_t)(tc->pw_mc ? NC / 2 : NC))) return rc;
   if (int rc = encode_2d(&tc->tmap_out, op.d_out, (uint64_t)tc->M_total, (uint64_t)op.k, kBlockM)) return rc;
   if (op.d_residual)
     if (int rc = encode_2d(&tc->tmap_res, op.d_residual, (uint64_t)tc->M_total, (uint64_t)op.k, kBlockM)) return rc;
@@ -395,12 +437,12 @@ int prepare_conv_pw(const pdf_op& op, TcConv* tc) {
                 (reinterpret_cast<uintptr_t>(op.d_weight3) & 15) == 0 && (reinterpret_cast<uintptr_t>(op.d_out3) & 31) == 0,
                 "pointwise conv: a chained 1x1 convolution needs Cout %% 128 == 0, k3 in {64,128,256} and aligned pointers");
     tc->k3 = op.k3; tc->bias3 = op.d_bias3; tc->out3 = op.d_out3;
-    if (int rc = encode_2d(&tc->tmap_w3, op.d_weight3, (uint64_t)op.k3, (uint64_t)op.k, (uint32_t)op.k3)) return rc;
+    if (int rc = encode_2d(&tc->tmap_w3, op.d_weight3, (uint64_t)op.k3, (uint64_t)op.k, (uint32_t)(tc->pw_mc ? op.k3 / 2 : op.k3))) return rc;
   }
   return PDF_OK;
 }
 
-template <int NC, bool CHAIN>
+template <int NC, bool CHAIN, bool MC>
 static int launch_pw(const TcConv& tc, cudaStream_t s) {
   using L = PwSmem<NC>;
   // measured (profiles/r02_pw_cfg.txt): launches that fetch a residual tile want the third staging buffer (the residual of unit
@@ -415,7 +457,7 @@ static int launch_pw(const TcConv& tc, cudaStream_t s) {
   const int smem = L::dynamic_bytes(stages, nry, bias_floats);
   static int configured = 0;
   if (smem > configured) {
-    PDF_CHECK_CUDA(cudaFuncSetAttribute(conv_pw_kernel<NC, CHAIN>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
+    PDF_CHECK_CUDA(cudaFuncSetAttribute(conv_pw_kernel<NC, CHAIN, MC>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
     configured = smem;
   }
   PwParams p;
@@ -424,20 +466,34 @@ static int launch_pw(const TcConv& tc, cudaStream_t s) {
   p.relu = tc.relu; p.im2col = tc.im2col; p.has_res = tc.residual != nullptr;
   p.Ho = tc.Ho; p.Wo = tc.Wo; p.stride = tc.stride;
   p.N2 = tc.k3; p.bias = tc.bias; p.bias3 = tc.bias3; p.out3 = reinterpret_cast<__nv_bfloat16*>(tc.out3);
-  const int grid = max(1, min(p.m_tiles, num_sms()));
+  int grid = max(1, min(p.m_tiles, num_sms()));
+  if (MC) grid = max(2, min((p.m_tiles + 1) / 2 * 2, num_sms() / 2 * 2));      // whole clusters of two CTAs
   const CUtensorMap& ta = *reinterpret_cast<const CUtensorMap*>(&tc.tmap_a);
   const CUtensorMap& tb = *reinterpret_cast<const CUtensorMap*>(&tc.tmap_b);
   const CUtensorMap& to = *reinterpret_cast<const CUtensorMap*>(&tc.tmap_out);
   const CUtensorMap& tr = p.has_res ? *reinterpret_cast<const CUtensorMap*>(&tc.tmap_res) : to;
   const CUtensorMap& tw = CHAIN ? *reinterpret_cast<const CUtensorMap*>(&tc.tmap_w3) : tb;
-  PDF_CHECK_CUDA(launch_pdl(conv_pw_kernel<NC, CHAIN>, dim3(grid), dim3(kPwThreads), (size_t)smem, s, ta, tb, to, tr, tw, p));
+  if (MC) {
+    cudaLaunchConfig_t cfg = {};
+    cfg.gridDim = dim3(grid); cfg.blockDim = dim3(kPwThreads); cfg.dynamicSmemBytes = (size_t)smem; cfg.stream = s;
+    cudaLaunchAttribute attr[2];
+    attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+    attr[0].val.programmaticStreamSerializationAllowed = pdl_enabled() ? 1 : 0;
+    attr[1].id = cudaLaunchAttributeClusterDimension;
+    attr[1].val.clusterDim.x = 2; attr[1].val.clusterDim.y = 1; attr[1].val.clusterDim.z = 1;
+    cfg.attrs = attr; cfg.numAttrs = 2;
+    PDF_CHECK_CUDA(cudaLaunchKernelEx(&cfg, conv_pw_kernel<NC, CHAIN, MC>, ta, tb, to, tr, tw, p));
+  } else {
+    PDF_CHECK_CUDA(launch_pdl(conv_pw_kernel<NC, CHAIN, MC>, dim3(grid), dim3(kPwThreads), (size_t)smem, s, ta, tb, to, tr, tw, p));
+  }
   PDF_CHECK_LAUNCH();
   return PDF_OK;
 }
 
 int launch_conv_pw(const TcConv& tc, cudaStream_t s) {
-  if (tc.pw == 128) return tc.k3 ? launch_pw<128, true>(tc, s) : launch_pw<128, false>(tc, s);
-  if (tc.pw == 64) return launch_pw<64, false>(tc, s);
+  if (tc.pw == 128 && tc.pw_mc) return tc.k3 ? launch_pw<128, true, true>(tc, s) : launch_pw<128, false, true>(tc, s);
+  if (tc.pw == 128) return tc.k3 ? launch_pw<128, true, false>(tc, s) : launch_pw<128, false, false>(tc, s);
+  if (tc.pw == 64) return launch_pw<64, false, false>(tc, s);
   set_error("launch_conv_pw: bad chunk width %d", tc.pw);
   return PDF_ERR_ARG;
 }
@@ -453,6 +509,12 @@ extern "C" int pdf_debug_set_pw_config(int stages, int staging_buffers) {
     return PDF_ERR_ARG;
   }
   pdf::g_pw_stages = stages; pdf::g_pw_ry = staging_buffers;
+  return PDF_OK;
+}
+/* 0 (default) = single CTAs everywhere, 1 = weight-multicast CTA pairs for the pointwise launches with Cin >= 128 (measured neutral).
+ * Takes effect for plans created afterwards. */
+extern "C" int pdf_debug_set_pw_multicast(int enable) {
+  pdf::g_pw_mc = enable != 0;
   return PDF_OK;
 }
 extern "C" int pdf_debug_set_pw(int mode) {

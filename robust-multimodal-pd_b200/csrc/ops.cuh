@@ -33,6 +33,7 @@ struct TcConv {
   // pointwise kernel (conv_pw.cu): 1x1 convolution whose epilogue goes through shared memory (TMA residual load, TMA store),
   // optionally chained with the NEXT 1x1 convolution (out3 = relu(out * W3^T + bias3)) while the output tile is still on chip
   int pw;                  // 0 | NC (64 or 128): the launch goes to conv_pw_kernel<NC, ...>
+  int pw_mc;               // 1: weight-multicast CTA pairs (tmap_b / tmap_w3 boxes hold half the rows)
   int Cin;
   TensorMapBlob tmap_out, tmap_res, tmap_w3;
   int k3;                  // chained output channels (0 = no chain)

@@ -98,3 +98,27 @@ def test_chained_encoder_equals_unchained():
                                                            # + layer2.0.conv1 and layer3.0.conv1 across the stage boundaries
     rel = (a - b).norm() / b.norm()
     assert rel < 2e-3, rel
+
+
+@pytest.mark.parametrize("n,S", [(5, 96), (3, 64), (16, 128)])
+def test_weight_multicast_pairs_equal_single_ctas(n, S):
+    """conv_pw_kernel as weight-multicast CTA pairs (two CTAs of a cluster share every weight tile of the ring, each fetching half)
+    must reproduce the single-CTA launches bit for bit -- odd tile counts (a pair's second tile past the end), chained and
+    un-chained launches, strided downsamples."""
+    from pd_fusion_b200 import _lib
+    from pd_fusion_b200.backbone import ResNet2D, ResNetEncoder
+    lib = _lib.load()
+    torch.manual_seed(1234)
+    sd = {k: v for k, v in ResNet2D("resnet50").state_dict().items() if not k.startswith("fc.")}
+    x = (torch.rand(n, S, S) * 2 - 1).to(torch.bfloat16).cuda()
+    outs = []
+    try:
+        for mc in (0, 1):
+            _lib.check(lib.pdf_debug_set_pw_multicast(mc))
+            enc = ResNetEncoder(sd, n, S, precision="bf16")
+            outs.append(enc.forward(x).clone())
+            torch.cuda.synchronize()
+    finally:
+        lib.pdf_debug_set_pw_multicast(0)
+    assert torch.isfinite(outs[1]).all() and float(outs[1].abs().max()) > 0
+    assert torch.equal(outs[0], outs[1]), float((outs[0] - outs[1]).abs().max())

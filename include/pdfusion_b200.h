@@ -239,6 +239,7 @@ typedef struct pdf_plan pdf_plan; /* opaque: validated ops + pre-encoded TMA des
 /* tuning / A-B hook for the pointwise kernel (conv_pw.cu): 0 = 1x1 convolutions stay on the generic kernel, 1 = default
  * policy, 2 = every eligible 1x1 convolution.  Affects plans created afterwards. */
 int pdf_debug_set_pw(int mode);
+int pdf_debug_set_pw_prefetch(int enable);    /* pointwise kernel: L2 prefetch of the next row tile's A operand (default 0) */
 int pdf_debug_set_pw_multicast(int enable);   /* pointwise kernel: weight-multicast CTA pairs for Cin >= 128 (default 0: measured neutral) */
 int pdf_debug_set_wgrad_rowtile(int enable);   /* wgrad_tc: 0 = im2col-mode loads for every filter > 1x1 (default 1: row-tiled) */
 int pdf_debug_set_wgrad_waves(int waves);  /* wgrad_tc: CTA waves the pixel range is split into (default 1) */

@@ -29,6 +29,7 @@
 namespace pdf {
 
 static int g_pw_mode = 1;   // pdf_debug_set_pw: 0 = never, 1 = default policy, 2 = every eligible 1x1 convolution
+static int g_pw_prefetch = 0;   // pdf_debug_set_pw_prefetch: L2 prefetch of the next row tile's A operand
 static int g_pw_mc = 0;     // pdf_debug_set_pw_multicast: 0 (default) = single CTAs, 1 = weight-multicast CTA pairs where K >= 128
 
 constexpr int kPwMaxStages = 6;     // ring depth and staging-buffer count are launch parameters (pdf_debug_set_pw_config)
@@ -44,6 +45,7 @@ struct PwParams {
   int N2;                       // chained output channels
   int stages, nry;              // ring depth, staging buffers
   int bias_staged;              // 1: bias vector copied to shared memory at kernel start, 0: read from global memory (L1-resident)
+  int l2_prefetch;              // 1: prefetch the next row tile's A k-blocks into L2
   const float* bias;
   const float* bias3;
   __nv_bfloat16* out3;
@@ -220,6 +222,14 @@ conv_pw_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant
       for (int u = 0; u < n_units; ++u) {
         const int ti = u / p.n_chunks, nc = u - ti * p.n_chunks;
         const int m0 = tile_of(ti) * kBlockM, n0 = nc * NC;
+        if (p.l2_prefetch && nc == 0 && !p.im2col && ti + 1 < my_tiles) {
+          // the NEXT row tile's A k-blocks into L2 while this tile's n_chunks units run: its first ring fills then hit L2 instead of
+          // paying the HBM latency inside the ring (pdf_debug_set_pw_prefetch)
+          const int m1 = tile_of(ti + 1) * kBlockM;
+          for (int kb = 0; kb < num_kb; ++kb)
+            asm volatile("cp.async.bulk.prefetch.tensor.2d.L2.global.tile [%0, {%1, %2}];"
+                         ::"l"(reinterpret_cast<uint64_t>(&tmap_a)), "r"(kb * kBlockK), "r"(m1) : "memory");
+        }
         if (p.has_res) {
           const int b = u % kPwRy;
           mbar_wait(bar_ryfree + 8 * b, (((uint32_t)(u / kPwRy)) & 1u) ^ 1u);
@@ -462,6 +472,7 @@ static int launch_pw(const TcConv& tc, cudaStream_t s) {
   }
   PwParams p;
   p.stages = stages; p.nry = nry; p.bias_staged = bias_floats > 0 || tc.bias == nullptr;
+  p.l2_prefetch = g_pw_prefetch;
   p.M_total = tc.M_total; p.Cout = tc.Cout; p.K = tc.Cin; p.n_chunks = tc.Cout / NC; p.m_tiles = ceil_div(tc.M_total, kBlockM);
   p.relu = tc.relu; p.im2col = tc.im2col; p.has_res = tc.residual != nullptr;
   p.Ho = tc.Ho; p.Wo = tc.Wo; p.stride = tc.stride;
@@ -515,6 +526,10 @@ extern "C" int pdf_debug_set_pw_config(int stages, int staging_buffers) {
  * Takes effect for plans created afterwards. */
 extern "C" int pdf_debug_set_pw_multicast(int enable) {
   pdf::g_pw_mc = enable != 0;
+  return PDF_OK;
+}
+extern "C" int pdf_debug_set_pw_prefetch(int enable) {
+  pdf::g_pw_prefetch = enable != 0;
   return PDF_OK;
 }
 extern "C" int pdf_debug_set_pw(int mode) {

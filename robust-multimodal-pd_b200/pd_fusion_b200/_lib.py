@@ -141,6 +141,7 @@ PROTOTYPES = {
     "pdf_standardize_volume": (C.c_int, [C.c_int, C.c_size_t, _P, _P, C.c_int, _P, _P]),
     "pdf_debug_set_mil_mt": (C.c_int, [C.c_int]),
     "pdf_debug_set_pw_multicast": (C.c_int, [C.c_int]),
+    "pdf_debug_set_pw_prefetch": (C.c_int, [C.c_int]),
     "pdf_debug_set_wgrad_waves": (C.c_int, [C.c_int]),
     "pdf_debug_set_wgrad_rowtile": (C.c_int, [C.c_int]),
     "pdf_preproc_slice_major_ok": (C.c_int, [C.POINTER(PreprocCfg)]),
@@ -212,6 +213,8 @@ def load():
         lib.pdf_debug_set_hs_mode(int(os.environ["PDFUSION_B200_HS"]))
     if os.environ.get("PDFUSION_B200_CONV_PROBE"):       # timing probe (garbage outputs): see pdf_debug_set_conv_probe
         lib.pdf_debug_set_conv_probe(int(os.environ["PDFUSION_B200_CONV_PROBE"]))
+    if os.environ.get("PDFUSION_B200_PW_PREFETCH") is not None:   # tuning hook: L2 prefetch of the next row tile's A operand
+        lib.pdf_debug_set_pw_prefetch(int(os.environ["PDFUSION_B200_PW_PREFETCH"]))
     if os.environ.get("PDFUSION_B200_PW_MC") is not None:   # tuning hook: weight-multicast CTA pairs in the pointwise kernel (0 off)
         lib.pdf_debug_set_pw_multicast(int(os.environ["PDFUSION_B200_PW_MC"]))
     if os.environ.get("PDFUSION_B200_PW") is not None:   # tuning hook: pointwise kernel (0 off, 1 default policy, 2 every 1x1 conv)

@@ -273,10 +273,15 @@ class MilAttentionFineTuneModel(BaseModel):
                     L = int(sl.shape[0])
                     demb[k:k + L].copy_(dX[i, :L])
                     k += L
-            rt.backward(demb)
+            # data-parallel over bags under torchrun: every residual block's gradients are averaged on a side stream as soon as the
+            # backward has left the block (training.BucketedAllReduce); the head's small buffer follows in one call
+            from ..training import BucketedAllReduce
+            reducer = BucketedAllReduce(rt.flat_grad)
+            rt.backward(demb, reducer)
+            reducer.finish()
             pg = [(rt.flat_param, rt.flat_grad, opt.groups[0][1])] + pg
         from ..training import allreduce_mean
-        allreduce_mean([ht.flat_grad] + ([] if frozen else [rt.flat_grad]))          # data-parallel over bags under torchrun
+        allreduce_mean([ht.flat_grad])
         scale = opt.clip([g for _, g, _ in pg], float(clip)) if clip else None
         opt.step(pg, scale)
         if not frozen:

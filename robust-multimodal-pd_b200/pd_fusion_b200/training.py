@@ -35,7 +35,11 @@ def _flat_like(params: Dict[str, torch.Tensor]):
         offs[k] = total
         total += (v.numel() + 7) // 8 * 8                    # 32-byte aligned views
     flat = torch.zeros(total, dtype=torch.float32, device=first.device)
+    _flat_like.last_offsets = dict(offs)                         # (layout of the buffer just built: used for the gradient buckets)
     return flat, {k: flat[offs[k]:offs[k] + v.numel()].view(v.shape) for k, v in params.items()}
+
+
+_flat_like.last_offsets = {}
 
 
 def flatten_parameters(params: Dict[str, torch.Tensor]) -> torch.Tensor:
@@ -47,6 +51,56 @@ def flatten_parameters(params: Dict[str, torch.Tensor]) -> torch.Tensor:
         views[k].copy_(v.data)
         v.data = views[k]
     return flat
+
+
+def block_of(param_name: str) -> str:
+    """Bucket key of a backbone parameter: the residual block it belongs to ("layer3.4"), or "stem" (conv1 / bn1)."""
+    parts = param_name.split(".")
+    return ".".join(parts[:2]) if parts[0].startswith("layer") else "stem"
+
+
+def bucket_ranges(offsets: Dict[str, int], sizes: Dict[str, int]) -> Dict[str, Tuple[int, int]]:
+    """Flat-buffer range [lo, hi) of every block's parameters (`_flat_like` lays the parameters out in named_parameters order, so
+    a block is one contiguous range; hi includes the alignment padding up to the next block)."""
+    names = list(offsets)
+    out: Dict[str, List[int]] = {}
+    for i, k in enumerate(names):
+        b = block_of(k)
+        hi = offsets[names[i + 1]] if i + 1 < len(names) else offsets[k] + (sizes[k] + 7) // 8 * 8
+        if b not in out:
+            out[b] = [offsets[k], hi]
+        else:
+            assert offsets[k] == out[b][1], f"block {b} is not contiguous in the flat buffer ({k})"
+            out[b][1] = hi
+    return {b: (lo, hi) for b, (lo, hi) in out.items()}
+
+
+class BucketedAllReduce:
+    """DDP-style overlap for the fine-tune step: the backward walks the blocks from layer4 down to the stem, and as soon
+    as a block's last gradient (its weight gradients copied out of the wgrad accumulators, its BatchNorm gradients) is final, the
+    block's contiguous range of the flat gradient buffer is averaged over the ranks on a SIDE stream, under the kernels of the
+    blocks below it.  `finish()` makes the compute stream wait for the last bucket."""
+
+    def __init__(self, flat: torch.Tensor):
+        self.flat = flat
+        self.enabled = torch.distributed.is_available() and torch.distributed.is_initialized() and torch.distributed.get_world_size() > 1
+        self.stream = torch.cuda.Stream(device=flat.device) if (self.enabled and flat.is_cuda) else None
+        self.calls = 0
+
+    def ready(self, lo: int, hi: int) -> None:
+        if not self.enabled or hi <= lo:
+            return
+        self.calls += 1
+        if self.stream is None:                                    # CPU tensors (gloo tests): no streams
+            allreduce_mean([self.flat[lo:hi]])
+            return
+        self.stream.wait_stream(torch.cuda.current_stream())
+        with torch.cuda.stream(self.stream):
+            allreduce_mean([self.flat[lo:hi]])
+
+    def finish(self) -> None:
+        if self.stream is not None:
+            torch.cuda.current_stream().wait_stream(self.stream)
 
 
 def allreduce_mean(flat_grads: Sequence[torch.Tensor]) -> None:
@@ -312,6 +366,7 @@ class ResNetTrainer:
         trainable = {k: v for k, v in self.params.items() if not k.startswith("fc.")}
         self.flat_param = flatten_parameters(trainable)              # same layout as flat_grad: clip / Adam in one launch each
         self.flat_grad, self.grad = _flat_like({k: v.data for k, v in trainable.items()})
+        self.buckets = bucket_ranges(_flat_like.last_offsets, {k: v.numel() for k, v in trainable.items()})
         self._zero_bias = torch.zeros(4096, dtype=torch.float32, device=self.dev)
         self._scr = None
         if self.bf16:
@@ -516,16 +571,39 @@ class ResNetTrainer:
         out.grad = None
         return dconv
 
-    def backward(self, demb: torch.Tensor):
+    def _finalize_weight_grad(self, name: str, gwk) -> None:
+        """-> torchvision [K,C,R,S] (layout change only; one backward per zero_grad, as the reference's step)"""
+        if self.bf16:                                                # tensor path accumulated [K,R,S,C]
+            gw = self._gw[name]
+            if name == "conv1":
+                self.grad[name + ".weight"].copy_(gw[:, :147].reshape(gw.shape[0], 7, 7, 3).permute(0, 3, 1, 2))
+            else:
+                self.grad[name + ".weight"].copy_(gw.permute(0, 3, 1, 2))
+        else:                                                        # FP32 path accumulated [R,S,C,K]
+            self.grad[name + ".weight"].copy_(gwk[name].permute(3, 2, 0, 1))
+
+    def backward(self, demb: torch.Tensor, reducer: Optional["BucketedAllReduce"] = None):
         """demb [n, D] f32: gradient of the loss w.r.t. the embeddings.  Accumulates parameter gradients into self.grad
-        (torchvision layout)."""
+        (torchvision layout).  reducer: data-parallel runs hand in a BucketedAllReduce over self.flat_grad -- every residual block's
+        range of the flat buffer is all-reduced on a side stream as soon as the backward has left the block."""
         s = _lib.stream_ptr()
         lib = self.lib
         gwk: Dict[str, torch.Tensor] = {}
         if self.bf16:
             self._gw_flat.zero_()
+        cur_block = None
+
+        def leave(block):
+            if reducer is not None and block is not None:
+                reducer.ready(*self.buckets[block])
+
         for entry in reversed(self.tape):
             kind = entry[0]
+            if kind in ("stem", "convbn"):
+                blk = "stem" if kind == "stem" else block_of(entry[1])
+                if blk != cur_block:
+                    leave(cur_block)
+                    cur_block = blk
             if kind == "avgpool":
                 t = entry[1]
                 t.grad = torch.empty_like(t.data)
@@ -546,11 +624,13 @@ class ResNetTrainer:
                 dconv = self._bn_backward("bn1", out, conv_out, True, None, goff, mean, invstd, max_rows)
                 _lib.check(lib.pdf_conv_wgrad_bf16(C.byref(op), patches.data_ptr(), dconv.data_ptr(), self._gw["conv1"].data_ptr(), s),
                            "pdf_conv_wgrad_bf16")
+                self._finalize_weight_grad("conv1", gwk)
             else:
                 _, name, bn, x, conv_out, out, relu, res, op, goff, mean, invstd, h, max_rows = entry
                 dconv = self._bn_backward(bn, out, conv_out, relu, res, goff, mean, invstd, max_rows)
                 if self.bf16:
                     self._backward_conv_tc(name, op, x, dconv, h)
+                    self._finalize_weight_grad(name, gwk)
                     continue
                 if name not in gwk:
                     gwk[name] = torch.zeros_like(self.wk[name])
@@ -561,15 +641,8 @@ class ResNetTrainer:
                         x.grad = torch.empty_like(x.data)
                     _lib.check(lib.pdf_conv_dgrad_f32(C.byref(op), dconv.data_ptr(), self.wk[name].data_ptr(), x.grad.data_ptr(), acc, s),
                                "pdf_conv_dgrad_f32")
-        # -> torchvision [K,C,R,S] (layout change only; one backward per zero_grad, as the reference's step)
-        if self.bf16:
-            for name, gw in self._gw.items():                        # tensor path accumulated [K,R,S,C]
-                if name == "conv1":
-                    self.grad[name + ".weight"].copy_(gw[:, :147].reshape(gw.shape[0], 7, 7, 3).permute(0, 3, 1, 2))
-                else:
-                    self.grad[name + ".weight"].copy_(gw.permute(0, 3, 1, 2))
-        for name, gw in gwk.items():                                 # FP32 path accumulated [R,S,C,K]
-            self.grad[name + ".weight"].copy_(gw.permute(3, 2, 0, 1))
+                self._finalize_weight_grad(name, gwk)
+        leave(cur_block)
         self.tape = []
 
     def _backward_conv_tc(self, name: str, op: "_lib.Op", x: _Act, dconv: torch.Tensor, h: int) -> None:

@@ -52,7 +52,7 @@ TRAIN_WORKER = textwrap.dedent("""
     sys.path.insert(0, sys.argv[1])
     import torch
     from pd_fusion_b200.parallel import init_distributed, barrier
-    from pd_fusion_b200.training import _flat_like, allreduce_mean, flatten_parameters
+    from pd_fusion_b200.training import BucketedAllReduce, _flat_like, allreduce_mean, bucket_ranges, flatten_parameters
     rank, local_rank, ws = init_distributed(backend="gloo")
     torch.manual_seed(0)                                     # same initial weights on every rank, as under DDP
     net = torch.nn.Sequential(torch.nn.Linear(5, 3), torch.nn.ReLU(), torch.nn.Linear(3, 1))
@@ -72,6 +72,20 @@ TRAIN_WORKER = textwrap.dedent("""
     allreduce_mean([flat_grad])
     for i, g in enumerate(grads.values()):
         assert torch.allclose(g, torch.full_like(g, 1.5 * (i + 1))), (rank, i, g)
+    # bucketed form (what the fine-tune backward does block by block, last block first): same result, several collectives
+    names = {"conv1.weight": (4, 3), "bn1.weight": (4,), "layer1.0.conv1.weight": (6, 4), "layer1.0.bn1.bias": (6,), "layer1.1.conv1.weight": (5, 6)}
+    flat2, g2 = _flat_like({k: torch.zeros(v) for k, v in names.items()})
+    buckets = bucket_ranges(_flat_like.last_offsets, {k: int(torch.zeros(v).numel()) for k, v in names.items()})
+    assert list(buckets) == ["stem", "layer1.0", "layer1.1"] and buckets["stem"][0] == 0 and buckets["layer1.1"][1] == flat2.numel()
+    for i, g in enumerate(g2.values()):
+        g.fill_(float(rank) * 2.0 + i)
+    red = BucketedAllReduce(flat2)
+    for b in reversed(list(buckets)):
+        red.ready(*buckets[b])
+    red.finish()
+    assert red.calls == 3
+    for i, g in enumerate(g2.values()):
+        assert torch.allclose(g, torch.full_like(g, 1.0 + i)), (rank, i, g)
     barrier()
     if rank == 0:
         print("ALLREDUCE_OK", ws)

@@ -324,10 +324,11 @@ class MlpTrainer:
 
 
 class _Act:
-    __slots__ = ("data", "grad", "n", "hw", "c")
+    __slots__ = ("data", "grad", "n", "hw", "c", "relu_bits")
 
-    def __init__(self, data, n, hw, c):
+    def __init__(self, data, n, hw, c, relu_bits=None):
         self.data, self.grad, self.n, self.hw, self.c = data, None, n, hw, c     # data / grad: f32 (fp32 path) or bf16 (tensor path)
+        self.relu_bits = relu_bits      # tensor path: the producing BatchNorm's ReLU mask, one bit per element (read by its backward)
 
 
 class ResNetTrainer:
@@ -446,7 +447,7 @@ class ResNetTrainer:
 
     # -- forward ---------------------------------------------------------------------------------------
     def _bn_forward(self, bn: str, conv_out: torch.Tensor, res: Optional[_Act], relu: bool, groups, hw: int):
-        """Train-mode BatchNorm (+ residual, ReLU) of a conv output [M, K] in the path's storage type; returns (y, goff, mean, invstd, max_rows)."""
+        """Train-mode BatchNorm (+ residual, ReLU) of a conv output [M, K] in the path's storage type; returns (y, goff, mean, invstd, max_rows, relu_bits)."""
         G, K = len(groups) - 1, int(conv_out.shape[1])
         goff = self._goff(groups, hw)
         max_rows = max(b - a for a, b in zip(groups[:-1], groups[1:])) * hw
@@ -457,9 +458,10 @@ class ResNetTrainer:
         args = (G, goff.data_ptr(), max_rows, K, conv_out.data_ptr(), self.params[bn + ".weight"].data.data_ptr(),
                 self.params[bn + ".bias"].data.data_ptr(), float(bnm.eps), _p(res.data if res else None), 1 if relu else 0, y.data_ptr())
         tail = (mean.data_ptr(), invstd.data_ptr(), varu.data_ptr(), self._scratch(3 * G * K).data_ptr(), _lib.stream_ptr())
+        bits = None
         if self.bf16:        # the ReLU mask as one bit per element: what the backward reads instead of y
-            y.relu_bits = torch.empty(conv_out.numel() // 8, dtype=torch.uint8, device=self.dev) if relu else None
-            _lib.check(self.lib.pdf_bn_train_forward_bf16(*args, _p(y.relu_bits), *tail), "pdf_bn_train_forward_bf16")
+            bits = torch.empty(conv_out.numel() // 8, dtype=torch.uint8, device=self.dev) if relu else None
+            _lib.check(self.lib.pdf_bn_train_forward_bf16(*args, _p(bits), *tail), "pdf_bn_train_forward_bf16")
         else:
             _lib.check(self.lib.pdf_bn_train_forward(*args, *tail), "pdf_bn_train_forward")
         if self.update_running:
@@ -467,7 +469,7 @@ class ResNetTrainer:
                                                       self.buffers[bn + ".running_mean"].data_ptr(), self.buffers[bn + ".running_var"].data_ptr(),
                                                       _lib.stream_ptr()), "pdf_bn_update_running")
             self.buffers[bn + ".num_batches_tracked"] += G
-        return y, goff, mean, invstd, max_rows
+        return y, goff, mean, invstd, max_rows, bits
 
     def _convbn(self, x: _Act, h: int, name: str, bn: str, relu: bool, res: Optional[_Act], groups) -> Tuple[_Act, int]:
         cv = self.convs[name]
@@ -482,8 +484,8 @@ class ResNetTrainer:
             conv_out = torch.empty((n * ho * ho, K), dtype=torch.float32, device=self.dev)
             op.d_in, op.d_weight, op.d_out = x.data.data_ptr(), self.wk[name].data_ptr(), conv_out.data_ptr()
         self._run_op(op)
-        y, goff, mean, invstd, max_rows = self._bn_forward(bn, conv_out, res, relu, groups, ho * ho)
-        out = _Act(y, n, ho * ho, K)
+        y, goff, mean, invstd, max_rows, bits = self._bn_forward(bn, conv_out, res, relu, groups, ho * ho)
+        out = _Act(y, n, ho * ho, K, bits)
         self.tape.append(("convbn", name, bn, x, conv_out, out, relu, res, op, goff, mean, invstd, h, max_rows))
         return out, ho
 
@@ -500,8 +502,8 @@ class ResNetTrainer:
         op.n, op.h, op.w, op.c, op.k, op.r, op.s, op.stride, op.pad, op.ho, op.wo, op.relu = n, ho, ho, 192, 64, 1, 1, 1, 0, ho, ho, 0
         op.d_in, op.d_weight, op.d_bias, op.d_out = patches.data_ptr(), self.wk16["conv1"].data_ptr(), self._zero_bias.data_ptr(), conv_out.data_ptr()
         self._run_op(op)
-        y, goff, mean, invstd, max_rows = self._bn_forward("bn1", conv_out, None, True, groups, ho * ho)
-        out = _Act(y, n, ho * ho, 64)
+        y, goff, mean, invstd, max_rows, bits = self._bn_forward("bn1", conv_out, None, True, groups, ho * ho)
+        out = _Act(y, n, ho * ho, 64, bits)
         self.tape.append(("stem", patches, conv_out, out, op, goff, mean, invstd, max_rows))
         return out, ho
 
@@ -563,7 +565,7 @@ class ResNetTrainer:
                 acc = 1
             dres = res.grad
         fn = self.lib.pdf_bn_train_backward_bf16 if self.bf16 else self.lib.pdf_bn_train_backward
-        act = _p(out.data.relu_bits) if self.bf16 else out.data.data_ptr()         # bf16 path: the forward's bit mask; fp32 path: y itself
+        act = _p(out.relu_bits) if self.bf16 else out.data.data_ptr()              # bf16 path: the forward's bit mask; fp32 path: y itself
         _lib.check(fn(G, goff.data_ptr(), max_rows, K, out.grad.data_ptr(), act, conv_out.data_ptr(),
                       self.params[bn + ".weight"].data.data_ptr(), mean.data_ptr(), invstd.data_ptr(), 1 if relu else 0,
                       self._scratch(3 * G * K).data_ptr(), dconv.data_ptr(), _p(dres), acc, self.grad[bn + ".weight"].data_ptr(),
